@@ -1,0 +1,294 @@
+"""Backend-neutral scene descriptions + the procedural scenes of BASELINE.json's configs.
+
+The reference ships no assets, so every benchmark/test scene is generated here with
+fixed seeds and pushed through the C ABI (`HdMoonshine*` / `HdMoonshineExt*`). Engine space is +Z up.
+A `Scene` is plain data; `load_scene(backend, scene)` replays it into any object exposing the
+backend protocol (moonshine_b200.hydra.HdMoonshine for the CUDA library, oracle/binding.py for the
+CPU oracle in tests).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional, Tuple
+
+import numpy as np
+
+# TextureFormat codes shared with include/moonshine_ext.h (MsneTexFormat)
+TEX_R32F, TEX_RG32F, TEX_RGBA32F, TEX_R8_UNORM, TEX_RG8_UNORM, TEX_RGBA8_SRGB, TEX_RGBA16F = range(7)
+# MaterialType (shaders/hrtsystem/world.hlsl:31-36)
+MAT_GLASS, MAT_LAMBERT, MAT_PERFECT_MIRROR, MAT_STANDARD_PBR = range(4)
+
+
+@dataclass
+class Texture:
+    data: np.ndarray  # raw bytes/floats, C-contiguous
+    width: int
+    height: int
+    fmt: int
+
+
+@dataclass
+class Material:
+    type: int
+    normal: int
+    emissive: int
+    color: int = 0
+    metalness: int = 0
+    roughness: int = 0
+    ior: float = 1.5
+
+
+@dataclass
+class Mesh:
+    positions: np.ndarray  # (n,3) f32
+    indices: np.ndarray  # (m,3) u32
+    normals: Optional[np.ndarray] = None  # (n,3) when indexed_attributes else (3m,3)
+    texcoords: Optional[np.ndarray] = None  # (n,2) / (3m,2)
+
+
+@dataclass
+class Instance:
+    transform: np.ndarray  # (3,4) f32 row-major
+    geometries: List[Tuple[int, int, bool]]  # (mesh, material, sampled)
+    visible: bool = True
+
+
+@dataclass
+class Lens:
+    origin: Tuple[float, float, float]
+    forward: Tuple[float, float, float]
+    up: Tuple[float, float, float]
+    vfov: float
+    aperture: float = 0.0
+    focus_distance: float = 1.0
+
+    def as_array(self) -> np.ndarray:
+        return np.array([*self.origin, *self.forward, *self.up, self.vfov, self.aperture, self.focus_distance], dtype=np.float32)
+
+
+@dataclass
+class Constants:
+    """Specialization constants (shaders/hrtsystem/main.hlsl:34-40). Defaults = offline/main.zig:106-111."""
+    samples_per_run: int = 1
+    max_bounces: int = 1024
+    env_samples_per_bounce: int = 1
+    mesh_samples_per_bounce: int = 1
+    flip_image: bool = True
+    indexed_attributes: bool = True
+    two_component_normal_texture: bool = True
+
+
+@dataclass
+class Scene:
+    name: str
+    textures: List[Texture] = field(default_factory=list)
+    materials: List[Material] = field(default_factory=list)
+    meshes: List[Mesh] = field(default_factory=list)
+    instances: List[Instance] = field(default_factory=list)
+    background: Optional[np.ndarray] = None  # (H,W,4) f32 equirect; None = default 1x1 white
+    constants: Constants = field(default_factory=Constants)
+    lens: Lens = field(default_factory=lambda: Lens((-3, 0, 0), (1, 0, 0), (0, 0, 1), math.pi / 4))
+    extent: Tuple[int, int] = (64, 64)  # (width, height)
+    build_emitter_table: bool = True  # Accel.create semantics (Accel.zig:491-538)
+
+    # -- small builders ---------------------------------------------------------------------
+    def solid1(self, v: float) -> int:
+        self.textures.append(Texture(np.array([v], np.float32), 1, 1, TEX_R32F))
+        return len(self.textures) - 1
+
+    def solid2(self, x: float, y: float) -> int:
+        self.textures.append(Texture(np.array([x, y], np.float32), 1, 1, TEX_RG32F))
+        return len(self.textures) - 1
+
+    def solid3(self, r: float, g: float, b: float) -> int:
+        # stored as f32x4 (MaterialManager.zig:364-373); the 4th lane is never sampled
+        self.textures.append(Texture(np.array([r, g, b, 1.0], np.float32), 1, 1, TEX_RGBA32F))
+        return len(self.textures) - 1
+
+    def raw_texture(self, data: np.ndarray, fmt: int) -> int:
+        h, w = data.shape[:2]
+        self.textures.append(Texture(np.ascontiguousarray(data), w, h, fmt))
+        return len(self.textures) - 1
+
+    def add_material(self, **kw) -> int:
+        self.materials.append(Material(**kw))
+        return len(self.materials) - 1
+
+    def add_mesh(self, positions, indices, normals=None, texcoords=None) -> int:
+        self.meshes.append(Mesh(np.ascontiguousarray(positions, np.float32), np.ascontiguousarray(indices, np.uint32),
+                                None if normals is None else np.ascontiguousarray(normals, np.float32),
+                                None if texcoords is None else np.ascontiguousarray(texcoords, np.float32)))
+        return len(self.meshes) - 1
+
+    def add_instance(self, geometries, transform=None, visible=True) -> int:
+        t = np.eye(3, 4, dtype=np.float32) if transform is None else np.ascontiguousarray(transform, np.float32)
+        self.instances.append(Instance(t, list(geometries), visible))
+        return len(self.instances) - 1
+
+    def triangle_count(self) -> int:
+        return sum(len(self.meshes[g[0]].indices) for i in self.instances for g in i.geometries)
+
+
+def load_scene(backend, scene: Scene):
+    """Replay `scene` into a backend; returns (texture, material, mesh, instance) handle lists."""
+    tex = [backend.create_texture(t.data, t.width, t.height, t.fmt) for t in scene.textures]
+    mats = [backend.create_material(m.type, tex[m.normal], tex[m.emissive], tex[m.color], tex[m.metalness], tex[m.roughness], m.ior)
+            for m in scene.materials]
+    meshes = [backend.create_mesh(m.positions, m.normals, m.texcoords, m.indices) for m in scene.meshes]
+    backend.set_constants(scene.constants)
+    insts = [backend.create_instance(i.transform, [(meshes[g[0]], mats[g[1]], g[2]) for g in i.geometries], i.visible)
+             for i in scene.instances]
+    if scene.background is not None:
+        backend.set_background(scene.background)
+    if scene.build_emitter_table:
+        backend.build_emitter_table()
+    return tex, mats, meshes, insts
+
+
+# ---------------------------------------------------------------------------------------------
+# geometry helpers
+# ---------------------------------------------------------------------------------------------
+def icosphere(order: int, reverse_winding: bool = False):
+    """Unit icosphere, restating engine/tests.zig:115-247 (same vertex/triangle order)."""
+    t = np.float32((1.0 + math.sqrt(5.0)) / 2.0)
+    pos = [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t), (0, -1, -t), (0, 1, -t),
+           (t, 0, -1), (t, 0, 1), (-t, 0, -1), (-t, 0, 1)]
+    pos = [np.array(p, np.float32) for p in pos]
+    tris = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2), (10, 7, 6), (7, 1, 8),
+            (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10), (8, 6, 7), (9, 8, 1)]
+    cache = {}
+
+    def midpoint(a, b):
+        key = (min(a, b), max(a, b))
+        if key in cache:
+            return cache[key]
+        pos.append(((pos[a] + pos[b]) / np.float32(2.0)).astype(np.float32))
+        cache[key] = len(pos) - 1
+        return cache[key]
+
+    for _ in range(order):
+        nxt = []
+        for (x, y, z) in tris:
+            a, b, c = midpoint(x, y), midpoint(y, z), midpoint(z, x)
+            nxt += [(x, a, c), (y, b, a), (z, c, b), (a, b, c)]
+        tris = nxt
+    p = np.stack(pos).astype(np.float32)
+    # Vec3.unit(): div_scalar(length), length = sqrt(x*x + y*y + z*z) in f32
+    ln = np.sqrt((p[:, 0] * p[:, 0] + p[:, 1] * p[:, 1] + p[:, 2] * p[:, 2]).astype(np.float32)).astype(np.float32)
+    p = (p / ln[:, None]).astype(np.float32)
+    idx = np.array(tris, np.uint32)
+    if reverse_winding:
+        idx = idx[:, ::-1].copy()
+    return p, idx
+
+
+def _quad(p0, p1, p2, p3):
+    """Two triangles (p0,p1,p2),(p0,p2,p3)."""
+    return np.array([p0, p1, p2, p3], np.float32), np.array([[0, 1, 2], [0, 2, 3]], np.uint32)
+
+
+def _merge(parts):
+    ps, idx, off = [], [], 0
+    for p, i in parts:
+        ps.append(p)
+        idx.append(i + off)
+        off += len(p)
+    return np.concatenate(ps).astype(np.float32), np.concatenate(idx).astype(np.uint32)
+
+
+def _box(lo, hi, rot_z=0.0, center=None):
+    lo, hi = np.array(lo, np.float32), np.array(hi, np.float32)
+    c = [(lo[0], lo[1], lo[2]), (hi[0], lo[1], lo[2]), (hi[0], hi[1], lo[2]), (lo[0], hi[1], lo[2]),
+         (lo[0], lo[1], hi[2]), (hi[0], lo[1], hi[2]), (hi[0], hi[1], hi[2]), (lo[0], hi[1], hi[2])]
+    v = np.array(c, np.float32)
+    if rot_z:
+        ctr = v.mean(0) if center is None else np.array(center, np.float32)
+        cs, sn = math.cos(rot_z), math.sin(rot_z)
+        d = v - ctr
+        v = np.stack([d[:, 0] * cs - d[:, 1] * sn, d[:, 0] * sn + d[:, 1] * cs, d[:, 2]], 1) + ctr
+    # outward-facing (counter-clockwise seen from outside)
+    f = [(0, 3, 2, 1), (4, 5, 6, 7), (0, 1, 5, 4), (1, 2, 6, 5), (2, 3, 7, 6), (3, 0, 4, 7)]
+    idx = []
+    for a, b, c_, d in f:
+        idx += [(a, b, c_), (a, c_, d)]
+    return v.astype(np.float32), np.array(idx, np.uint32)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configs + parity scenes
+# ---------------------------------------------------------------------------------------------
+def test_lens() -> Lens:
+    """engine/tests.zig:302-309."""
+    return Lens((-3, 0, 0), (1, 0, 0), (0, 0, 1), math.pi / 4.0, 0.0, 1.0)
+
+
+def single_triangle(extent=(64, 64)) -> Scene:
+    """cfg1: one Lambert(0.8) triangle, 1x1 white env through addBackground, test lens, offline constants."""
+    s = Scene("cfg1-single-triangle", extent=extent, lens=test_lens())
+    n, e, c = s.solid2(0.5, 0.5), s.solid3(0, 0, 0), s.solid3(0.8, 0.8, 0.8)
+    m = s.add_material(type=MAT_LAMBERT, normal=n, emissive=e, color=c)
+    mesh = s.add_mesh([(0, -1, -1), (0, 1, -1), (0, 0, 1)], [(0, 1, 2)])
+    s.add_instance([(mesh, m, False)])
+    s.background = np.ones((1, 1, 4), np.float32)
+    return s
+
+
+def furnace_white_sphere(env_samples: int, spr: int = 512, order: int = 5, extent=(32, 32)) -> Scene:
+    """engine/tests.zig:257-364 — "white sphere on white background is white"."""
+    s = Scene("furnace-white-sphere", extent=extent, lens=test_lens())
+    n, c, e = s.solid2(0.5, 0.5), s.solid3(1, 1, 1), s.solid3(0, 0, 0)
+    m = s.add_material(type=MAT_LAMBERT, normal=n, emissive=e, color=c)
+    p, i = icosphere(order, False)
+    mesh = s.add_mesh(p, i)
+    s.add_instance([(mesh, m, False)])
+    s.background = np.ones((1, 1, 4), np.float32)
+    s.constants = Constants(samples_per_run=spr, max_bounces=1024, env_samples_per_bounce=env_samples, mesh_samples_per_bounce=0)
+    s.build_emitter_table = False  # uploadInstance path: "alias table currently unimplemented" (Accel.zig:187)
+    return s
+
+
+def furnace_emissive_interior(mesh_samples: int = 0, spr: int = 1024, order: int = 5, extent=(32, 32)) -> Scene:
+    """engine/tests.zig:366-455 — "inside illuminating sphere is white" (mesh_samples=1 revives :457-487)."""
+    s = Scene("furnace-emissive-interior", extent=extent, lens=Lens((0, 0, 0), (1, 0, 0), (0, 0, 1), math.pi / 3.0, 0.0, 1.0))
+    n, c, e = s.solid2(0.5, 0.5), s.solid3(0.5, 0.5, 0.5), s.solid3(0.5, 0.5, 0.5)
+    m = s.add_material(type=MAT_LAMBERT, normal=n, emissive=e, color=c)
+    p, i = icosphere(order, True)
+    mesh = s.add_mesh(p, i)
+    s.add_instance([(mesh, m, mesh_samples > 0)])
+    s.background = np.array([[[0, 0, 0, 1]]], np.float32)
+    s.constants = Constants(samples_per_run=spr, max_bounces=1024, env_samples_per_bounce=0, mesh_samples_per_bounce=mesh_samples)
+    s.build_emitter_table = mesh_samples > 0
+    return s
+
+
+def cornell_box(extent=(512, 512)) -> Scene:
+    """cfg2: Cornell box in the unit cube, 36 triangles: 5 walls (10) + 2 boxes (24) + quad light (2)."""
+    s = Scene("cfg2-cornell-box", extent=extent)
+    n, black = s.solid2(0.5, 0.5), s.solid3(0, 0, 0)
+    white = s.add_material(type=MAT_LAMBERT, normal=n, emissive=black, color=s.solid3(0.73, 0.73, 0.73))
+    red = s.add_material(type=MAT_LAMBERT, normal=n, emissive=black, color=s.solid3(0.65, 0.05, 0.05))
+    green = s.add_material(type=MAT_LAMBERT, normal=n, emissive=black, color=s.solid3(0.12, 0.45, 0.15))
+    light = s.add_material(type=MAT_LAMBERT, normal=n, emissive=s.solid3(17, 12, 4), color=s.solid3(0.78, 0.78, 0.78))
+    # room: x in [0,1] (depth, camera looks +x), y in [0,1] (left/right), z in [0,1] (up); normals face inward
+    floor = _quad((0, 0, 0), (1, 0, 0), (1, 1, 0), (0, 1, 0))
+    ceil_ = _quad((0, 0, 1), (0, 1, 1), (1, 1, 1), (1, 0, 1))
+    back = _quad((1, 0, 0), (1, 0, 1), (1, 1, 1), (1, 1, 0))
+    left = _quad((0, 1, 0), (1, 1, 0), (1, 1, 1), (0, 1, 1))
+    right = _quad((0, 0, 0), (0, 0, 1), (1, 0, 1), (1, 0, 0))
+    m_white = s.add_mesh(*_merge([floor, ceil_, back]))
+    m_left = s.add_mesh(*left)
+    m_right = s.add_mesh(*right)
+    tall = _box((0.55, 0.52, 0.0), (0.85, 0.82, 0.6), rot_z=math.radians(-17))
+    short = _box((0.25, 0.15, 0.0), (0.55, 0.45, 0.3), rot_z=math.radians(18))
+    m_boxes = s.add_mesh(*_merge([tall, short]))
+    # emitter faces down (front face = side the normal points to; lights emit from the front face only)
+    lq = _quad((0.37, 0.35, 0.998), (0.63, 0.35, 0.998), (0.63, 0.65, 0.998), (0.37, 0.65, 0.998))
+    lq = (lq[0], lq[1][:, ::-1].copy())
+    m_light = s.add_mesh(*lq)
+    s.add_instance([(m_white, white, False), (m_left, red, False), (m_right, green, False), (m_boxes, white, False)])
+    s.add_instance([(m_light, light, True)])
+    s.background = np.array([[[0, 0, 0, 1]]], np.float32)
+    s.lens = Lens((-1.95, 0.5, 0.5), (1, 0, 0), (0, 0, 1), math.radians(39.3), 0.0, 1.0)
+    s.constants = Constants()
+    return s

@@ -1,0 +1,227 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY. Never linked, imported or executed by the product path;
+// only tests/, __graft_entry__.smoke() and bench.py's CPU legs (cpu_baseline / --impl reference)
+// may load liboracle.so.
+//
+// C entry points around the CPU restatement (vec.h, utils.h, scene.h, bvh.h, shading.h, host.h) of
+// ashpil/moonshine's path-tracing hot path. The entry points mirror the shape of the reference's
+// C ABI (hydra/moonshine.h:71-95) plus what offline/tests reach through Zig, so the same Python
+// scene description can drive the oracle and the CUDA library.
+//
+// PARITY STATUS: the reference cannot be built or run here (Zig + DXC + Vulkan-RT absent) and its
+// tests hold no numeric golden vectors; this oracle is pinned only by (a) the RNG known-answer
+// values derived from shaders/utils/random.hlsl:8-45 and (b) the reference's own
+// furnace tests engine/tests.zig:257-364,366-455 (tests/test_oracle_furnace.py). Ray/triangle
+// arithmetic and texture filtering (driver/hardware in the reference) are "parity unpinned" and
+// are defined in bvh.h / scene.h.
+#include <atomic>
+#include <thread>
+#include "host.h"
+
+using namespace orc;
+
+struct Oracle {
+    SceneData sc;
+    bool dirty = true;
+    std::vector<std::vector<uint32_t>> instGeomMeshes;  // per instance mesh-id list (BLAS dedupe key, Accel.zig:315-343)
+};
+
+static void commit(Oracle* o) {
+    SceneData& sc = o->sc;
+    sc.accel.blases.clear();
+    sc.accel.instanceBlas.assign(sc.instances.size(), 0);
+    std::vector<std::vector<uint32_t>> keys;
+    for (uint32_t i = 0; i < sc.instances.size(); i++) {
+        const std::vector<uint32_t>& key = o->instGeomMeshes[i];
+        uint32_t b = 0;
+        for (; b < keys.size(); b++) if (keys[b] == key) break;
+        if (b == keys.size()) {
+            keys.push_back(key);
+            Blas blas;
+            std::vector<AABB> boxes;
+            for (uint32_t g = 0; g < key.size(); g++) {
+                const MeshRec& m = sc.meshes[key[g]];
+                for (uint32_t p = 0; p < m.indices.size(); p++) {
+                    uint3 id = m.indices[p];
+                    float3 v0 = m.positions[id.x], v1 = m.positions[id.y], v2 = m.positions[id.z];
+                    blas.tris.push_back({v0, v1, v2, g, p});
+                    AABB bb; bb.grow(v0); bb.grow(v1); bb.grow(v2);
+                    boxes.push_back(bb);
+                }
+            }
+            blas.bvh.build(boxes, 4);
+            sc.accel.blases.push_back(std::move(blas));
+        }
+        sc.accel.instanceBlas[i] = b;
+    }
+    sc.accel.instances = &sc.instances;
+    sc.accel.buildTlas();
+    o->dirty = false;
+}
+
+extern "C" {
+
+Oracle* OracleCreate(void) {
+    Oracle* o = new Oracle();
+    // default 1x1 white background (BackgroundManager.zig:116-126)
+    const float white[4] = {1, 1, 1, 1};
+    buildEnvMap(o->sc.env, white, 1, 1);
+    return o;
+}
+void OracleDestroy(Oracle* o) { delete o; }
+
+// attribute arrays are raw: `n_attr` elements, indexed by vertex index (indexed_attributes) or by 3*prim+k
+uint32_t OracleCreateMesh(Oracle* o, const float* pos, const float* normals, const float* uvs, size_t n_pos, size_t n_attr,
+                          const uint32_t* idx, size_t n_tri) {
+    MeshRec m;
+    m.positions.resize(n_pos);
+    for (size_t i = 0; i < n_pos; i++) m.positions[i] = {pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]};
+    if (normals) { m.normals.resize(n_attr); for (size_t i = 0; i < n_attr; i++) m.normals[i] = {normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]}; }
+    if (uvs) { m.texcoords.resize(n_attr); for (size_t i = 0; i < n_attr; i++) m.texcoords[i] = {uvs[2 * i], uvs[2 * i + 1]}; }
+    m.indices.resize(n_tri);
+    for (size_t i = 0; i < n_tri; i++) m.indices[i] = {idx[3 * i], idx[3 * i + 1], idx[3 * i + 2]};
+    o->sc.meshes.push_back(std::move(m));
+    o->dirty = true;
+    return (uint32_t)o->sc.meshes.size() - 1;
+}
+
+uint32_t OracleCreateTexture(Oracle* o, const void* data, uint32_t w, uint32_t h, uint32_t fmt) {
+    o->sc.textures.push_back(decode_texture(data, w, h, fmt));
+    return (uint32_t)o->sc.textures.size() - 1;
+}
+
+uint32_t OracleCreateMaterial(Oracle* o, uint32_t type, uint32_t normal, uint32_t emissive, uint32_t color, uint32_t metalness, uint32_t roughness, float ior) {
+    o->sc.materials.push_back({normal, emissive, type, color, metalness, roughness, ior});
+    return (uint32_t)o->sc.materials.size() - 1;
+}
+void OracleSetMaterial(Oracle* o, uint32_t handle, uint32_t type, uint32_t normal, uint32_t emissive, uint32_t color, uint32_t metalness, uint32_t roughness, float ior) {
+    o->sc.materials[handle] = {normal, emissive, type, color, metalness, roughness, ior};
+}
+
+struct OrcGeometry { uint32_t mesh, material; uint8_t sampled; };
+
+uint32_t OracleCreateInstance(Oracle* o, const float* m12, const OrcGeometry* geoms, size_t n, int visible) {
+    InstanceRec in;
+    std::memcpy(in.transform.m, m12, 48);
+    in.worldToInstance = inverseAffine(in.transform);
+    in.customIndex = (uint32_t)o->sc.geometries.size();
+    in.geometryCount = (uint32_t)n;
+    in.visible = visible != 0;
+    std::vector<uint32_t> key;
+    for (size_t i = 0; i < n; i++) {
+        o->sc.geometries.push_back({geoms[i].mesh, geoms[i].material, geoms[i].sampled != 0});
+        key.push_back(geoms[i].mesh);
+    }
+    o->sc.instances.push_back(in);
+    o->instGeomMeshes.push_back(key);
+    o->dirty = true;
+    return (uint32_t)o->sc.instances.size() - 1;
+}
+void OracleSetInstanceTransform(Oracle* o, uint32_t h, const float* m12) {
+    std::memcpy(o->sc.instances[h].transform.m, m12, 48);
+    o->sc.instances[h].worldToInstance = inverseAffine(o->sc.instances[h].transform);
+    o->dirty = true;
+}
+void OracleSetInstanceVisibility(Oracle* o, uint32_t h, int visible) { o->sc.instances[h].visible = visible != 0; o->dirty = true; }
+
+void OracleSetBackground(Oracle* o, const float* rgba, uint32_t w, uint32_t h) { buildEnvMap(o->sc.env, rgba, w, h); }
+
+// Accel.create semantics: (re)build the emitter alias table over every sampled geometry
+void OracleBuildEmitterTable(Oracle* o) { buildEmitterTable(o->sc); }
+
+void OracleSetConstants(Oracle* o, uint32_t spr, uint32_t max_bounces, uint32_t env, uint32_t mesh, int flip, int indexed, int two_comp) {
+    o->sc.consts = {spr, max_bounces, env, mesh, flip != 0, indexed != 0, two_comp != 0};
+}
+void OracleSetBruteForce(Oracle* o, int brute) { o->sc.brute = brute != 0; }
+
+// Runs `n_launches` consecutive raygen launches (offline/main.zig:131-165 loop) over the pixels
+// [y0,y1) x [0,W) with `stride`-interleaved pixel subsampling (stride 1 = every pixel) on `threads`
+// host threads. image = W*H RGBA32F, read-modify-written exactly like storeColor.
+// counts[0] += closest-hit TraceRay calls, counts[1] += shadow TraceRay calls.
+void OracleRender(Oracle* o, const float* lens12, uint32_t W, uint32_t H, float* image, uint32_t sample_count, uint32_t n_launches,
+                  int threads, uint32_t pixel_stride, uint64_t* counts) {
+    if (o->dirty) commit(o);
+    Lens lens; std::memcpy(&lens, lens12, 48);
+    if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+    if (pixel_stride == 0) pixel_stride = 1;
+    std::atomic<uint32_t> nextRow{0};
+    std::atomic<uint64_t> nc{0}, ns{0};
+    const SceneData& sc = o->sc;
+    auto work = [&]() {
+        TraceCounters tc;
+        for (;;) {
+            uint32_t y = nextRow.fetch_add(1);
+            if (y >= H) break;
+            for (uint32_t x = 0; x < W; x++) {
+                if (((size_t)y * W + x) % pixel_stride) continue;
+                float* texel = image + 4 * ((size_t)y * W + x);
+                for (uint32_t l = 0; l < n_launches; l++)
+                    raygenPixel(sc, tc, lens, W, H, x, y, sample_count + l * sc.consts.samples_per_run, texel);
+            }
+        }
+        nc += tc.closest; ns += tc.shadow;
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; t++) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    if (counts) { counts[0] += nc; counts[1] += ns; }
+}
+
+// ---- per-function entry points for known-answer / stage tests ---------------------------
+uint32_t OracleHashPcg(uint32_t a) { return Hash::pcg(a); }
+uint32_t OracleHashLcg(uint32_t a) { return Hash::lcg(a); }
+uint32_t OracleRngSeed(uint32_t s, uint32_t x, uint32_t y) { return Rng::fromSeed(s, x, y).state; }
+void OracleRngFloats(uint32_t s, uint32_t x, uint32_t y, uint32_t n, float* out) {
+    Rng r = Rng::fromSeed(s, x, y);
+    for (uint32_t i = 0; i < n; i++) out[i] = r.getFloat();
+}
+// primary rays for one launch sample: out rays = 6 floats (origin, dir) per pixel, rng_state per pixel after the 4 draws
+void OraclePrimaryRays(Oracle* o, const float* lens12, uint32_t W, uint32_t H, uint32_t sample, float* rays6, uint32_t* rng_state) {
+    Lens lens; std::memcpy(&lens, lens12, 48);
+    for (uint32_t y = 0; y < H; y++)
+        for (uint32_t x = 0; x < W; x++) {
+            Rng rng = Rng::fromSeed(sample, x, y);
+            float2 r0 = rng.getFloat2(); float2 r1 = rng.getFloat2();
+            RayDesc r = generateRay(lens, W, H, dispatchUV(o->sc.consts, x, y, W, H, r0), r1);
+            float* p = rays6 + 6 * ((size_t)y * W + x);
+            p[0] = r.Origin.x; p[1] = r.Origin.y; p[2] = r.Origin.z; p[3] = r.Direction.x; p[4] = r.Direction.y; p[5] = r.Direction.z;
+            if (rng_state) rng_state[(size_t)y * W + x] = rng.state;
+        }
+}
+// rays: n x 8 floats (origin, tmin, dir, tmax); hits: n x {u32 inst, u32 geom, u32 prim, f32 u, f32 v}
+void OracleTrace(Oracle* o, const float* rays8, size_t n, int any_hit, int brute, uint32_t* hits5) {
+    if (o->dirty) commit(o);
+    for (size_t i = 0; i < n; i++) {
+        const float* r = rays8 + 8 * i;
+        Intersection its = o->sc.accel.trace({r[0], r[1], r[2]}, {r[4], r[5], r[6]}, r[3], r[7], any_hit != 0, brute != 0);
+        uint32_t* h = hits5 + 5 * i;
+        h[0] = its.instanceIndex; h[1] = its.geometryIndex; h[2] = its.primitiveIndex;
+        std::memcpy(h + 3, &its.barycentrics.x, 4); std::memcpy(h + 4, &its.barycentrics.y, 4);
+    }
+}
+uint32_t OracleEnvSize(Oracle* o) { return o->sc.env.size; }
+void OracleEnvData(Oracle* o, float* rgba, float* lum_all_levels) {
+    std::memcpy(rgba, o->sc.env.rgb.data(), o->sc.env.rgb.size() * 16);
+    size_t off = 0;
+    for (auto& l : o->sc.env.lum) { std::memcpy(lum_all_levels + off, l.data(), l.size() * 4); off += l.size(); }
+}
+uint32_t OracleAliasCount(Oracle* o) { return (uint32_t)o->sc.aliasTable.size(); }
+void OracleAliasData(Oracle* o, void* out20) { std::memcpy(out20, o->sc.aliasTable.data(), o->sc.aliasTable.size() * sizeof(AliasEntry)); }
+void OracleWorldToInstance(Oracle* o, uint32_t inst, float* out12) { std::memcpy(out12, o->sc.instances[inst].worldToInstance.m, 48); }
+// direct function probes (mappings / BSDF) used by unit tests
+void OracleSquareToEqualAreaSphere(float x, float y, float* out3) { float3 d = squareToEqualAreaSphere({x, y}); out3[0] = d.x; out3[1] = d.y; out3[2] = d.z; }
+void OracleSquareToEqualAreaSphereInverse(float x, float y, float z, float* out2) { float2 u = squareToEqualAreaSphereInverse({x, y, z}); out2[0] = u.x; out2[1] = u.y; }
+void OracleOffsetAlongNormal(const float* p, const float* n, float* out3) { float3 r = offsetAlongNormal({p[0], p[1], p[2]}, {n[0], n[1], n[2]}); out3[0] = r.x; out3[1] = r.y; out3[2] = r.z; }
+// type: MaterialType; params = {color r,g,b, metalness, roughness, ior}; op 0=eval(w_i,w_o) 1=pdf(w_i,w_o) 2=sample(w_o, sq=(w_i.x,w_i.y)) -> out4
+void OracleBsdf(uint32_t type, const float* params6, int op, const float* w_i, const float* w_o, float* out4) {
+    MaterialVariant v; v.type = type;
+    v.pbr.color = {params6[0], params6[1], params6[2]}; v.pbr.metalness = params6[3];
+    v.pbr.distr.a = std::fmax(params6[4] * params6[4], 0.001f); v.pbr.ior = params6[5];
+    v.lambert.r = v.pbr.color; v.glass.intIOR = params6[5];
+    float3 wi = {w_i[0], w_i[1], w_i[2]}, wo = {w_o[0], w_o[1], w_o[2]};
+    if (op == 0) { float3 e = v.eval(wi, wo); out4[0] = e.x; out4[1] = e.y; out4[2] = e.z; out4[3] = 0; }
+    else if (op == 1) { out4[0] = v.pdf(wi, wo); out4[1] = out4[2] = out4[3] = 0; }
+    else { MaterialSample s = v.sample(wo, {w_i[0], w_i[1]}); out4[0] = s.dirFs.x; out4[1] = s.dirFs.y; out4[2] = s.dirFs.z; out4[3] = s.pdf; }
+}
+
+}  // extern "C"
