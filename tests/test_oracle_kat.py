@@ -159,11 +159,11 @@ def test_bvh_matches_brute_force(maker):
     o = Oracle()
     scenes.load_scene(o, sc)
     rs = np.random.RandomState(11)
-    rays = _random_rays(rs, 4000, np.array([0.3, 0.4, 0.5]), 1.5)
+    rays = _random_rays(rs, 4000, np.array([0.3, 0.4, 0.5]), 0.5)
     a = o.trace(rays, brute=False)
     b = o.trace(rays, brute=True)
     np.testing.assert_array_equal(a, b)
-    assert (a["instance"] != 0xFFFFFFFF).sum() > 300
+    assert (a["instance"] != 0xFFFFFFFF).sum() > 1500
     sa = o.trace(rays, any_hit=True, brute=False)
     sb = o.trace(rays, any_hit=True, brute=True)
     np.testing.assert_array_equal(sa["instance"] != 0xFFFFFFFF, sb["instance"] != 0xFFFFFFFF)
