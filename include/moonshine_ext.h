@@ -1,0 +1,98 @@
+/* moonshine_ext.h — additions to the reference's C ABI (SURVEY.md §8b "Needed ABI additions").
+ *
+ * The Hydra ABI (moonshine.h) only covers what hydra/hydra.zig exports. The offline entry point and
+ * the reference's tests reach the rest of the integrator through Zig; those Zig interfaces are
+ * mirrored here as plain C so a cgo/ctypes/Zig `extern fn` caller can drive the same path:
+ *
+ *   specialization constants  engine/hrtsystem/pipeline.zig:319-327  (shaders/hrtsystem/main.hlsl:34-40)
+ *   BackgroundManager.addBackground   engine/hrtsystem/BackgroundManager.zig:142-394
+ *   MaterialManager.upload (all four variants)  engine/hrtsystem/MaterialManager.zig:140-170
+ *   TextureManager.upload raw formats  engine/hrtsystem/MaterialManager.zig:351-413; World.zig:72,101,184
+ *   MeshManager.upload with indexed attributes  engine/hrtsystem/MeshManager.zig:70-156
+ *   Accel.create's emitter alias table  engine/hrtsystem/Accel.zig:491-538
+ *   offline/main.zig:131-194 (spp launches, then one read-back)
+ *
+ * plus what a multi-GPU deployment needs (device selection, pixel-tile sharding, ray counters,
+ * device-resident sensor access for an NCCL reduce) and debug probes used by the parity tests.
+ */
+#pragma once
+#include "moonshine.h"
+
+typedef struct MsneSpecConstants {      /* pipeline.zig:319-327 — identical field order */
+    uint32_t samples_per_run;
+    uint32_t max_bounces;
+    uint32_t env_samples_per_bounce;    /* 0 or 1 (values >1 are rejected: returns false) */
+    uint32_t mesh_samples_per_bounce;   /* 0 or 1 */
+    uint32_t flip_image;                /* Bool32 */
+    uint32_t indexed_attributes;        /* Bool32 */
+    uint32_t two_component_normal_texture; /* Bool32 */
+} MsneSpecConstants;
+
+typedef enum MsneTexFormat {
+    MSNE_TEX_R32F = 0, MSNE_TEX_RG32F = 1, MSNE_TEX_RGBA32F = 2,   /* MaterialManager.zig:364-388 */
+    MSNE_TEX_R8_UNORM = 3, MSNE_TEX_RG8_UNORM = 4,                 /* World.zig:72,184 */
+    MSNE_TEX_RGBA8_SRGB = 5, MSNE_TEX_RGBA16F = 6,                 /* World.zig:101; hydra.zig:47-52 */
+} MsneTexFormat;
+
+typedef enum MsneMaterialType {         /* shaders/hrtsystem/world.hlsl:31-36 */
+    MSNE_MAT_GLASS = 0, MSNE_MAT_LAMBERT = 1, MSNE_MAT_PERFECT_MIRROR = 2, MSNE_MAT_STANDARD_PBR = 3,
+} MsneMaterialType;
+
+typedef struct MsneMaterialInfo {       /* MaterialManager.zig:22-77 flattened */
+    uint32_t type;                      /* MsneMaterialType */
+    ImageHandle normal, emissive;
+    ImageHandle color, metalness, roughness;  /* StandardPBR; Lambert uses color */
+    float ior;                          /* StandardPBR / Glass */
+} MsneMaterialInfo;
+
+typedef struct MsneStats {
+    uint64_t rays_closest;              /* closest-hit queries traced (intersection.hlsl:18-22) */
+    uint64_t rays_shadow;               /* any-hit queries traced   (intersection.hlsl:34-47) */
+    uint64_t samples;                   /* camera samples started */
+    uint64_t kernel_launches;           /* this library's kernels launched */
+    double   device_ms;                 /* CUDA-event time of the render loops (first generate .. last accumulate) */
+    double   trace_ms;                  /* CUDA-event time spent in the trace kernel (valid when profiling is on) */
+    uint64_t trace_launches;
+    uint64_t max_bounce_reached;
+} MsneStats;
+
+/* must be called before HdMoonshineCreate; selects the CUDA device of objects created afterwards */
+MSNE_API bool HdMoonshineExtSetDevice(int ordinal);
+
+MSNE_API bool HdMoonshineExtSetSpecConstants(HdMoonshine*, const MsneSpecConstants*);    /* = Pipeline.recreate, pipeline.zig:180-243 */
+MSNE_API void HdMoonshineExtGetSpecConstants(const HdMoonshine*, MsneSpecConstants*);
+MSNE_API bool HdMoonshineExtSetBackground(HdMoonshine*, const float* rgba_equirect, Extent2D); /* addBackground (replaces the current one) */
+MSNE_API ImageHandle HdMoonshineExtCreateTexture(HdMoonshine*, const void* data, Extent2D, MsneTexFormat, const char* name);
+MSNE_API MaterialHandle HdMoonshineExtCreateMaterial(HdMoonshine*, const MsneMaterialInfo*);
+/* attributes of length position_count, looked up through the index buffer (indexed_attributes = true) */
+MSNE_API MeshHandle HdMoonshineExtCreateMeshIndexed(HdMoonshine*, const F32x3* positions, const F32x3* normals_or_null,
+                                                    const F32x2* texcoords_or_null, size_t position_count,
+                                                    const U32x3* indices, size_t triangle_count);
+/* Accel.create semantics: rebuild the emitter alias table over every `sampled` geometry of every instance */
+MSNE_API bool HdMoonshineExtBuildEmitterTable(HdMoonshine*);
+
+/* offline loop: n_launches x (push constants, trace rays), sensor.sample_count advances; no read-back */
+MSNE_API bool HdMoonshineExtRenderLaunches(HdMoonshine*, SensorHandle, LensHandle, uint32_t n_launches);
+MSNE_API bool HdMoonshineExtReadSensor(HdMoonshine*, SensorHandle);      /* device image -> host buffer of GetSensorData */
+MSNE_API void HdMoonshineExtClearSensor(HdMoonshine*, SensorHandle);     /* Sensor.clear (core/Sensor.zig:81-83) */
+MSNE_API uint32_t HdMoonshineExtGetSensorSampleCount(const HdMoonshine*, SensorHandle);
+MSNE_API void* HdMoonshineExtGetSensorDevicePtr(const HdMoonshine*, SensorHandle);  /* RGBA32F W*H, for NCCL */
+
+/* multi-GPU: this object renders only the pixels of 32x32 tiles t with t % world == rank; the rest stay 0 */
+MSNE_API bool HdMoonshineExtSetTileShard(HdMoonshine*, uint32_t rank, uint32_t world);
+MSNE_API void HdMoonshineExtSetPathsInFlight(HdMoonshine*, uint64_t max_paths);   /* wavefront pool size (0 = default) */
+MSNE_API void HdMoonshineExtSetProfiling(HdMoonshine*, bool per_kernel_events);
+
+MSNE_API void HdMoonshineExtGetStats(const HdMoonshine*, MsneStats*);
+MSNE_API void HdMoonshineExtResetStats(HdMoonshine*);
+
+/* ---- debug probes used by tests/ (stage-level parity against the oracle) ---- */
+/* rays: n x {origin.xyz, tmin, dir.xyz, tmax}; hits: n x {u32 instance, u32 geometry, u32 primitive, f32 u, f32 v} */
+MSNE_API bool HdMoonshineExtTraceRays(HdMoonshine*, const float* rays8, size_t n, bool any_hit, uint32_t* hits5);
+/* primary rays of launch sample `sample`: rays6 = W*H x {origin, dir}; rng_state = W*H (after the 4 camera draws) */
+MSNE_API bool HdMoonshineExtPrimaryRays(HdMoonshine*, SensorHandle, LensHandle, uint32_t sample, float* rays6, uint32_t* rng_state);
+MSNE_API uint32_t HdMoonshineExtGetEnvSize(const HdMoonshine*);
+MSNE_API bool HdMoonshineExtGetEnvData(HdMoonshine*, float* rgba, float* lum_all_levels);
+MSNE_API uint32_t HdMoonshineExtGetEmitterTableSize(const HdMoonshine*);            /* entries incl. header */
+MSNE_API bool HdMoonshineExtGetEmitterTable(HdMoonshine*, void* entries20);
+MSNE_API const char* HdMoonshineExtLastError(void);

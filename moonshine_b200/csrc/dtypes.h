@@ -1,0 +1,129 @@
+// Plain-old-data layouts shared by the host runtime (runtime.cpp) and the sm_100a kernels (kernels.cu).
+//
+// The reference binds 7 storage buffers + a bindless texture array + 2 env images + the TLAS
+// (shaders/hrtsystem/main.hlsl:10-24). Here the same tables live in HBM as flat arrays reachable
+// through one `DeviceScene` parameter block; "device addresses" become raw pointers.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#ifdef __CUDACC__
+#define MSNE_HD __host__ __device__
+#else
+#define MSNE_HD
+#endif
+
+namespace msne {
+
+// ---- acceleration structure -----------------------------------------------------------------
+// BVH2 node, 64 B (four 16-byte lanes, one 128-bit load each):
+//   n0 = (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)   n1 = (c1.lo.x, c1.hi.x, c1.lo.y, c1.hi.y)
+//   n2 = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)   c  = (child0, child1, count0, count1)
+// count == 0: child is an inner-node index (-1 = empty child, never entered); count > 0: child is the
+// first item (triangle index in the pooled triangle array for a BLAS, slot in tlasItems for the TLAS)
+// and count the number of items. Every BVH has at least one inner node (the root).
+struct BvhNode2 {
+    float n0[4], n1[4], n2[4];
+    int32_t c[4];
+};
+static_assert(sizeof(BvhNode2) == 64, "BvhNode2 must be 64 B");
+
+// Triangle record, 48 B: three vertices in object space + ids (watertight edge test needs all three)
+//   t0 = (v0.xyz, geometryIndex)  t1 = (v1.xyz, primitiveIndex)  t2 = (v2.xyz, 0)
+struct TriRec { float v0[3]; uint32_t geom; float v1[3]; uint32_t prim; float v2[3]; uint32_t pad; };
+static_assert(sizeof(TriRec) == 48, "TriRec must be 48 B");
+
+// world.hlsl:6-15 + worldToInstance[] (main.hlsl:13) + our BLAS references, 128 B
+struct DInstance {
+    float o2w[12];         // instance transform, row-major 3x4
+    float w2o[12];         // inverse_affine(transform) (engine/vector.zig:350-362)
+    uint32_t customIndex;  // offset into geometries[] (low 24 bits of instanceCustomIndexAndMask)
+    uint32_t blasRoot;     // index of the BLAS root in the pooled node array
+    uint32_t visible;      // mask != 0
+    uint32_t pad[5];
+};
+static_assert(sizeof(DInstance) == 128, "DInstance must be 128 B");
+
+struct DGeometry { uint32_t mesh, material, sampled; };                      // world.hlsl:17-21
+struct DMesh { const float* pos; const float* uv; const float* nrm; const uint32_t* idx; };  // world.hlsl:23-29
+struct DMaterial {                                                            // world.hlsl:38-47 + variant payload
+    uint32_t normal, emissive, type;
+    uint32_t color, metalness, roughness;                                     // material.hlsl:186-190 / :146-147
+    float ior;                                                                // material.hlsl:189 / :348-351
+    uint32_t pad;
+};
+struct DTexture { const void* data; uint32_t w, h, fmt, pad; };               // bindless dTextures[] (material.hlsl:3)
+struct DAlias { uint32_t alias; float select; uint32_t inst, geom, prim; };   // light.hlsl:17-22,105-109
+static_assert(sizeof(DAlias) == 20, "alias entry is 20 B (Accel.zig:51-55)");
+
+struct DeviceScene {
+    const BvhNode2* tlasNodes;     // may be null when there are no visible instances
+    const uint32_t* tlasItems;     // TLAS leaf slot -> instance index
+    const BvhNode2* blasNodes;     // pooled BLAS nodes
+    const TriRec* tris;            // pooled triangles (leaf order)
+    const DInstance* instances;
+    const DGeometry* geometries;
+    const DMesh* meshes;
+    const DMaterial* materials;
+    const DTexture* textures;
+    const DAlias* alias;           // [0] = header {alias = count, select = sum of areas}
+    uint32_t aliasEntries;         // 0 when no table was built
+    // environment (BackgroundManager.zig:154-163)
+    const float* envRgb;           // S*S float4
+    const float* envLum;           // mip 0 .. log2(S), tightly packed, SUM pyramid
+    uint32_t envSize;
+    uint32_t envLevels;
+    uint32_t envLevelOffset[12];   // float offset of each mip inside envLum
+    const float* srgbLut;          // 256 floats
+};
+
+// specialization constants (main.hlsl:34-40) as runtime values
+struct DConstants {
+    uint32_t samples_per_run, max_bounces, env_samples, mesh_samples;
+    uint32_t flip_image, indexed_attributes, two_component_normal;
+};
+
+// camera basis hoisted out of Camera::generateRay (camera.hlsl:14-43); computed once per launch on
+// the host with the arithmetic of the HLSL (runtime.cpp: makeCamera)
+struct DCamera {
+    float origin[3], u[3], v[3], horizontal[3], vertical[3], llc[3];
+    float aperture;
+    uint32_t width, height;
+};
+
+// ---- wavefront pool ---------------------------------------------------------------------------
+// One path = six 16-byte lanes per ping-pong buffer (SoA arrays of float4, index q = queue slot):
+//   R0 = (origin.xyz, lastMaterialPdf)      R1 = (dir.xyz, bits: bounce | DELTA<<30 | DEAD<<31)
+//   S0 = (throughput.xyz, rng state bits)   S1 = (accumulated.xyz, result-slot bits)
+//   N0 = pending env-NEE contribution       N1 = pending mesh-NEE contribution (zeroed by the trace
+//        kernel when the shadow ray is occluded; folded into `accumulated` by the next shade pass)
+//   H  = hit record written by the trace kernel: (instanceIndex, triangle index, u bits, v bits)
+// Shadow queue: Q0 = (origin.xyz, tmax)  Q1 = (dir.xyz, bits: target q*2 + light)
+struct Counters { uint32_t nLive, nDead, nShadow, pad; };
+
+struct PathBuffers {
+    float4* R0[2]; float4* R1[2]; float4* S0[2]; float4* S1[2]; float4* N0[2]; float4* N1[2];
+    uint4* H;
+    float4* Q0; float4* Q1;
+    float4* result;        // per sample-slot final radiance
+    uint32_t capacity;     // P
+};
+
+struct WaveState {
+    Counters* counters;        // [2] ping-pong
+    uint32_t* traceTicket;     // work-stealing ticket of the trace kernel (self-resetting)
+    uint32_t* traceDone;       // finished-block counter of the trace kernel
+    uint32_t* shadeDone;       // finished-block counter of the shade kernel
+    unsigned long long* rayCounts;  // [0] closest, [1] shadow
+    uint32_t* maxBounce;
+};
+
+static const uint32_t FLAG_DEAD = 0x80000000u;
+static const uint32_t FLAG_DELTA = 0x40000000u;
+static const uint32_t BOUNCE_MASK = 0x3FFFFFFFu;
+static const uint32_t MISS_ID = 0xFFFFFFFFu;
+
+enum TexFormat : uint32_t { TEX_R32F = 0, TEX_RG32F, TEX_RGBA32F, TEX_R8_UNORM, TEX_RG8_UNORM, TEX_RGBA8_SRGB, TEX_RGBA16F };
+enum MatType : uint32_t { MAT_GLASS = 0, MAT_LAMBERT, MAT_PERFECT_MIRROR, MAT_STANDARD_PBR };
+
+}  // namespace msne

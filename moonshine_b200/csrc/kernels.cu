@@ -1,0 +1,503 @@
+// sm_100a wavefront path-tracing kernels — the B200-native replacement of the reference's ray-tracing
+// pipeline (shaders/hrtsystem/main.hlsl raygen/closesthit/miss/shadowmiss driven by vkCmdTraceRaysKHR,
+// engine/hrtsystem/pipeline.zig:269-271).
+//
+// One camera sample of one pixel = one path. Paths live in SoA float4 queues in HBM (dtypes.h) and move
+// through two kernels per bounce:
+//
+//   k_trace  persistent threads; warps pull 32-ray tickets from ONE index space that holds this bounce's
+//            extension rays (closest hit -> H[q]) followed by the previous bounce's shadow rays (any hit ->
+//            zero the pending NEE contribution of path q when occluded).
+//   k_shade  integrator.hlsl:68-183 for one bounce: fold pending NEE, emission (+MIS), termination /
+//            Russian roulette, env + mesh NEE sample generation (-> shadow queue), BSDF sample -> next
+//            extension ray; survivors are compacted into the other ping-pong buffer with warp-ballot
+//            aggregated atomics, finished paths write their radiance to result[slot].
+//
+// k_generate starts a wave (main.hlsl:85-88), k_accumulate applies storeColor (main.hlsl:43-51) in sample
+// order. Compiled with -fmad=false (see device_math.cuh).
+#include "kernels.h"
+#include "shading.cuh"
+#include "traverse.cuh"
+
+namespace msne {
+
+// ------------------------------------------------------------------------------------------------
+// generate
+// ------------------------------------------------------------------------------------------------
+DI void cameraRay(const DCamera& cam, const DConstants& k, uint32_t px, uint32_t py, float2 r0, float2 r1, float3& origin, float3& dir) {
+    // dispatchUV (main.hlsl:54-59)
+    const float2 randomCenter = mk2(0.5f, 0.5f) + 0.5f * squareToGaussian(r0);
+    float2 uv = (mk2((float)px, (float)py) + randomCenter) / mk2((float)cam.width, (float)cam.height);
+    if (k.flip_image) uv.y = 1.0f - uv.y;
+    // Camera::generateRay (camera.hlsl:31-41); basis hoisted to the host (runtime.cpp makeCamera)
+    const float3 u = mk3(cam.u[0], cam.u[1], cam.u[2]), v = mk3(cam.v[0], cam.v[1], cam.v[2]);
+    const float3 horizontal = mk3(cam.horizontal[0], cam.horizontal[1], cam.horizontal[2]);
+    const float3 vertical = mk3(cam.vertical[0], cam.vertical[1], cam.vertical[2]);
+    const float3 llc = mk3(cam.llc[0], cam.llc[1], cam.llc[2]);
+    const float3 camOrigin = mk3(cam.origin[0], cam.origin[1], cam.origin[2]);
+    const float2 sampled = squareToUniformDiskConcentric(r1);
+    const float2 rd = (cam.aperture * sampled) / 2.0f;
+    const float3 defocusOffset = u * rd.x + v * rd.y;
+    origin = camOrigin + defocusOffset;
+    dir = normalize(llc + uv.x * horizontal + uv.y * vertical - defocusOffset - camOrigin);
+}
+
+__global__ void __launch_bounds__(256) k_generate(DCamera cam, DConstants k, PathBuffers pb, Counters* counters, const uint32_t* __restrict__ pixIds,
+                                                  uint32_t nPix, uint32_t nSamples, uint32_t firstSample) {
+    const uint32_t total = nPix * nSamples;
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p == 0) {
+        counters[0].nLive = total; counters[0].nDead = 0; counters[0].nShadow = 0;
+        counters[1].nLive = 0; counters[1].nDead = 0; counters[1].nShadow = 0;
+    }
+    if (p >= total) return;
+    const uint32_t s = p / nPix, pi = p - s * nPix;
+    const uint32_t pix = __ldg(pixIds + pi);
+    const uint32_t px = pix % cam.width, py = pix / cam.width;
+    Rng rng = Rng::fromSeed(firstSample + s, px, py);
+    const float2 r0 = rng.getFloat2();
+    const float2 r1 = rng.getFloat2();
+    float3 o, d;
+    cameraRay(cam, k, px, py, r0, r1, o, d);
+    pb.R0[0][p] = make_float4(o.x, o.y, o.z, 0.0f);
+    pb.R1[0][p] = make_float4(d.x, d.y, d.z, __uint_as_float(0u));
+    pb.S0[0][p] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(rng.state));
+    pb.S1[0][p] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(p));
+    pb.N0[0][p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    pb.N1[0][p] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// debug probe: primary rays + rng state (HdMoonshineExtPrimaryRays)
+__global__ void k_primary_probe(DCamera cam, DConstants k, uint32_t sample, float* rays6, uint32_t* rngState) {
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= cam.width * cam.height) return;
+    const uint32_t px = p % cam.width, py = p / cam.width;
+    Rng rng = Rng::fromSeed(sample, px, py);
+    const float2 r0 = rng.getFloat2();
+    const float2 r1 = rng.getFloat2();
+    float3 o, d;
+    cameraRay(cam, k, px, py, r0, r1, o, d);
+    float* r = rays6 + 6 * (size_t)p;
+    r[0] = o.x; r[1] = o.y; r[2] = o.z; r[3] = d.x; r[4] = d.y; r[5] = d.z;
+    rngState[p] = rng.state;
+}
+
+// ------------------------------------------------------------------------------------------------
+// trace (persistent threads)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TRACE_THREADS, TRACE_BLOCKS_PER_SM) k_trace(DeviceScene sc, PathBuffers pb, WaveState ws, uint32_t buf) {
+    const Counters cin = ws.counters[buf];
+    const uint32_t nLive = cin.nLive, total = cin.nLive + cin.nShadow;
+    const uint32_t lane = threadIdx.x & 31;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(ws.traceTicket, 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= total) break;
+        const uint32_t idx = base + lane;
+        if (idx < total) {
+            if (idx < nLive) {
+                const float4 r0 = pb.R0[buf][idx], r1 = pb.R1[buf][idx];
+                HitRec h;
+                traceRay<false>(sc, mk3(r0.x, r0.y, r0.z), mk3(r1.x, r1.y, r1.z), 0.0f, MS_INFINITY, h);
+                pb.H[idx] = make_uint4(h.inst, h.tri, __float_as_uint(h.u), __float_as_uint(h.v));
+            } else {
+                const uint32_t si = idx - nLive;
+                const float4 q0 = pb.Q0[si], q1 = pb.Q1[si];
+                HitRec h;
+                if (traceRay<true>(sc, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), 0.0f, q0.w, h)) {
+                    const uint32_t target = __float_as_uint(q1.w);
+                    float4* n = (target & 1u) ? pb.N1[buf] : pb.N0[buf];
+                    n[target >> 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+    }
+    // last block out: re-arm the ticket for the next launch and publish ray counts
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const uint32_t done = atomicAdd(ws.traceDone, 1u);
+        if (done == gridDim.x - 1) {
+            *ws.traceTicket = 0; *ws.traceDone = 0;
+            ws.rayCounts[0] += nLive; ws.rayCounts[1] += cin.nShadow;
+            __threadfence();
+        }
+    }
+}
+
+// debug probe: arbitrary rays (HdMoonshineExtTraceRays); rays8 = {o, tmin, d, tmax}
+__global__ void k_trace_probe(DeviceScene sc, const float* __restrict__ rays8, uint32_t n, int anyHit, uint32_t* hits5) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* r = rays8 + 8 * (size_t)i;
+    HitRec h;
+    uint32_t geom = 0, prim = 0;
+    if (anyHit) traceRay<true>(sc, mk3(r[0], r[1], r[2]), mk3(r[4], r[5], r[6]), r[3], r[7], h);
+    else {
+        traceRay<false>(sc, mk3(r[0], r[1], r[2]), mk3(r[4], r[5], r[6]), r[3], r[7], h);
+        if (h.inst != MISS_ID) { geom = sc.tris[h.tri].geom; prim = sc.tris[h.tri].prim; }
+    }
+    uint32_t* o = hits5 + 5 * (size_t)i;
+    o[0] = h.inst; o[1] = geom; o[2] = prim; o[3] = __float_as_uint(h.u); o[4] = __float_as_uint(h.v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// shade (one bounce of PathTracingIntegrator::incomingRadiance, integrator.hlsl:68-183)
+// ------------------------------------------------------------------------------------------------
+struct ShadeOut {
+    int kind;               // 0 = finished (result written), 1 = live, 2 = dead-with-pending-NEE
+    float4 R0, R1, S0, S1, N0, N1;
+    bool envRay, meshRay;
+    float4 envQ0, envQ1, meshQ0, meshQ1;   // Q1.w (target) filled in after the slot is known
+};
+
+DI void shadeOne(const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, uint32_t buf, uint32_t q, ShadeOut& out, uint32_t& bounceOut) {
+    const float4 R0 = pb.R0[buf][q], R1 = pb.R1[buf][q], S0 = pb.S0[buf][q], S1 = pb.S1[buf][q];
+    const float4 N0 = pb.N0[buf][q], N1 = pb.N1[buf][q];
+    const uint32_t flags = __float_as_uint(R1.w);
+    const uint32_t bounceCount = flags & BOUNCE_MASK;
+    const uint32_t slot = __float_as_uint(S1.w);
+    bounceOut = bounceCount;
+    out.kind = 0; out.envRay = false; out.meshRay = false;
+
+    float3 acc = mk3(S1.x, S1.y, S1.z);
+    // NEE of the previous bounce, in the reference's order: env first, then mesh (integrator.hlsl:141-150)
+    acc = acc + mk3(N0.x, N0.y, N0.z);
+    acc = acc + mk3(N1.x, N1.y, N1.z);
+
+    if (flags & FLAG_DEAD) { pb.result[slot] = make_float4(acc.x, acc.y, acc.z, 1.0f); return; }
+
+    const float3 rayOrigin = mk3(R0.x, R0.y, R0.z), rayDir = mk3(R1.x, R1.y, R1.z);
+    const float lastMaterialPdf = R0.w;
+    const bool isLastMaterialDelta = (flags & FLAG_DELTA) != 0;
+    float3 throughput = mk3(S0.x, S0.y, S0.z);
+    Rng rng; rng.state = __float_as_uint(S0.w);
+
+    const uint4 H = pb.H[q];
+    if (H.x == MISS_ID) {
+        // integrator.hlsl:169-180
+        if (k.env_samples == 0 || bounceCount == 0 || isLastMaterialDelta) {
+            acc = acc + throughput * envIncomingRadiance(sc, rayDir);
+        } else {
+            float3 rad; float pdf;
+            envEval(sc, rayDir, rad, pdf);
+            if (pdf > 0.0f) {
+                const float weight = powerHeuristic(1, lastMaterialPdf, k.env_samples, pdf);
+                acc = acc + throughput * rad * weight;
+            }
+        }
+        pb.result[slot] = make_float4(acc.x, acc.y, acc.z, 1.0f);
+        return;
+    }
+
+    // decode hit (integrator.hlsl:82-88)
+    const uint32_t instanceIndex = H.x;
+    const TriRec* tr = sc.tris + H.y;
+    const uint32_t geometryIndex = __ldg(&tr->geom), primitiveIndex = __ldg(&tr->prim);
+    const float2 bary = mk2(__uint_as_float(H.z), __uint_as_float(H.w));
+    const uint32_t instanceID = __ldg(&sc.instances[instanceIndex].customIndex);
+    const DGeometry geometry = sc.geometries[instanceID + geometryIndex];
+    const bool geomSampled = (geometry.sampled & 0xFFu) != 0;   // only the low byte is defined (Accel.zig:40-44)
+    const MeshAttributes attrs = lookupAttributes(sc, k, instanceIndex, geometry.mesh, primitiveIndex, bary);
+    const DMaterial dm = sc.materials[geometry.material];
+    const Frame textureFrame = getTextureFrame(sc, k, dm, attrs.texcoord, attrs.frame);
+    const float3 emissiveLight = xyz(sampleTexture(sc, dm.emissive, attrs.texcoord));
+    const MaterialParams material = loadMaterial(sc, dm, attrs.texcoord);
+
+    const float3 outgoingDirWs = -rayDir;
+
+    // shading-frame selection (integrator.hlsl:93-104)
+    const bool frontfacing = dot(attrs.triangleFrame.n, outgoingDirWs) > 0;
+    Frame shadingFrame;
+    if ((frontfacing && dot(outgoingDirWs, textureFrame.n) > 0) || (!frontfacing && -dot(outgoingDirWs, textureFrame.n) > 0)) shadingFrame = textureFrame;
+    else if ((frontfacing && dot(outgoingDirWs, attrs.frame.n) > 0) || (!frontfacing && -dot(outgoingDirWs, attrs.frame.n) > 0)) shadingFrame = attrs.frame;
+    else shadingFrame = attrs.triangleFrame;
+    const float3 outgoingDirSs = shadingFrame.worldToFrame(outgoingDirWs);
+
+    // emission (integrator.hlsl:109-124)
+    if (k.mesh_samples == 0 || bounceCount == 0 || !geomSampled || isLastMaterialDelta) {
+        if (dot(outgoingDirWs, attrs.triangleFrame.n) > 0.0f) acc = acc + throughput * emissiveLight;
+    } else {
+        const float sum = __ldg(&sc.alias[0].select);
+        const float lightPdf = areaMeasureToSolidAngleMeasure(attrs.position, rayOrigin, rayDir, attrs.triangleFrame.n) / sum;
+        if (lightPdf > 0.0f) {
+            const float weight = powerHeuristic(1, lastMaterialPdf, k.mesh_samples, lightPdf);
+            acc = acc + throughput * emissiveLight * weight;
+        }
+    }
+
+    // termination (integrator.hlsl:128-135)
+    if (bounceCount >= k.max_bounces + 1) { pb.result[slot] = make_float4(acc.x, acc.y, acc.z, 1.0f); return; }
+    if (bounceCount > 3) {
+        const float pSurvive = fminf(0.95f, luminance(throughput));
+        if (rng.getFloat() > pSurvive) { pb.result[slot] = make_float4(acc.x, acc.y, acc.z, 1.0f); return; }
+        throughput = throughput / pSurvive;
+    }
+
+    const bool isCurrentMaterialDelta = matIsDelta(material.type);
+    float3 neeEnv = mk3(0.0f), neeMesh = mk3(0.0f);
+    if (!isCurrentMaterialDelta) {
+        // env NEE (integrator.hlsl:141-144 -> estimateDirectMISLight :20-35 -> EnvMap::sample light.hlsl:47-80)
+        if (k.env_samples) {
+            const float2 rand = rng.getFloat2();
+            const LightSample ls = envSample(sc, rand);
+            if (ls.pdf > 0.0f) {
+                const float3 lightDirFs = shadingFrame.worldToFrame(ls.dirWs);
+                const float scatteringPdf = matPdf(material, lightDirFs, outgoingDirSs);
+                if (scatteringPdf > 0.0f) {
+                    const float3 brdf = matEval(material, lightDirFs, outgoingDirSs);
+                    const float weight = powerHeuristic(k.env_samples, ls.pdf, 1, scatteringPdf);
+                    const float3 est = ls.radiance * brdf * fabsf(cosTheta(lightDirFs)) * weight / ls.pdf;
+                    neeEnv = (throughput * est) / (float)k.env_samples;
+                    const float3 so = offsetAlongNormal(attrs.position, faceForward(attrs.triangleFrame.n, ls.dirWs));
+                    out.envRay = true;
+                    out.envQ0 = make_float4(so.x, so.y, so.z, MS_INFINITY);
+                    out.envQ1 = make_float4(ls.dirWs.x, ls.dirWs.y, ls.dirWs.z, 0.0f);
+                }
+            }
+        }
+        // mesh NEE (integrator.hlsl:147-150 -> MeshLights::sample light.hlsl:130-158)
+        if (k.mesh_samples) {
+            float2 rand = rng.getFloat2();
+            if (sc.aliasEntries > 1) {
+                const uint32_t entryCount = __ldg(&sc.alias[0].alias);
+                const float sum = __ldg(&sc.alias[0].select);
+                if (entryCount != 0 && sum != 0) {
+                    // sampleAlias (mappings.hlsl:114-126), offset 1
+                    const float scaled = rand.x * (float)entryCount;
+                    uint32_t idx = (uint32_t)scaled;
+                    if (idx >= entryCount) idx = entryCount - 1;   // hazard: float rounding past the table end
+                    rand.x = scaled - floorf(scaled);
+                    DAlias e = sc.alias[1 + idx];
+                    if (!coinFlipRemap(e.select, rand.x)) { idx = e.alias; e = sc.alias[1 + idx]; }
+                    const uint32_t lInstanceID = __ldg(&sc.instances[e.inst].customIndex);
+                    const DGeometry lg = sc.geometries[lInstanceID + e.geom];
+                    const float2 lbary = squareToTriangle(rand);
+                    const MeshAttributes la = lookupAttributes(sc, k, e.inst, lg.mesh, e.prim, lbary);
+                    const float3 radiance = xyz(sampleTexture(sc, sc.materials[lg.material].emissive, la.texcoord));
+                    const float3 dirWs = normalize(la.position - attrs.position);
+                    const float pdf = areaMeasureToSolidAngleMeasure(la.position, attrs.position, dirWs, la.triangleFrame.n) / sum;
+                    if (pdf > 0.0f) {
+                        const float3 lightDirFs = shadingFrame.worldToFrame(dirWs);
+                        const float scatteringPdf = matPdf(material, lightDirFs, outgoingDirSs);
+                        if (scatteringPdf > 0.0f) {
+                            const float3 brdf = matEval(material, lightDirFs, outgoingDirSs);
+                            const float weight = powerHeuristic(k.mesh_samples, pdf, 1, scatteringPdf);
+                            const float3 est = radiance * brdf * fabsf(cosTheta(lightDirFs)) * weight / pdf;
+                            neeMesh = (throughput * est) / (float)k.mesh_samples;
+                            const float3 offL = offsetAlongNormal(la.position, la.triangleFrame.n);
+                            const float3 offS = offsetAlongNormal(attrs.position, faceForward(attrs.triangleFrame.n, dirWs));
+                            const float tmax = length(offL - offS);
+                            const float3 sd = normalize(offL - offS);
+                            out.meshRay = true;
+                            out.meshQ0 = make_float4(offS.x, offS.y, offS.z, tmax);
+                            out.meshQ1 = make_float4(sd.x, sd.y, sd.z, 0.0f);
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    // BSDF sample (integrator.hlsl:154-163)
+    const MatSample sample = matSample(material, outgoingDirSs, rng.getFloat2());
+    out.N0 = make_float4(neeEnv.x, neeEnv.y, neeEnv.z, 0.0f);
+    out.N1 = make_float4(neeMesh.x, neeMesh.y, neeMesh.z, 0.0f);
+    out.S1 = make_float4(acc.x, acc.y, acc.z, __uint_as_float(slot));
+    if (sample.pdf == 0.0f) {
+        if (!out.envRay && !out.meshRay) { pb.result[slot] = make_float4(acc.x, acc.y, acc.z, 1.0f); return; }
+        out.kind = 2;
+        out.R0 = make_float4(0.f, 0.f, 0.f, 0.f);
+        out.R1 = make_float4(0.f, 0.f, 0.f, __uint_as_float(FLAG_DEAD | bounceCount));
+        out.S0 = make_float4(throughput.x, throughput.y, throughput.z, __uint_as_float(rng.state));
+        return;
+    }
+    const float3 newDir = shadingFrame.frameToWorld(sample.dirFs);
+    const float3 newOrigin = offsetAlongNormal(attrs.position, faceForward(attrs.triangleFrame.n, newDir));
+    throughput = throughput * (matEval(material, sample.dirFs, outgoingDirSs) * fabsf(cosTheta(sample.dirFs)) / sample.pdf);
+    out.kind = 1;
+    out.R0 = make_float4(newOrigin.x, newOrigin.y, newOrigin.z, sample.pdf);
+    out.R1 = make_float4(newDir.x, newDir.y, newDir.z, __uint_as_float((bounceCount + 1) | (isCurrentMaterialDelta ? FLAG_DELTA : 0u)));
+    out.S0 = make_float4(throughput.x, throughput.y, throughput.z, __uint_as_float(rng.state));
+}
+
+__global__ void __launch_bounds__(SHADE_THREADS) k_shade(DeviceScene sc, DConstants k, PathBuffers pb, WaveState ws, uint32_t buf) {
+    const Counters cin = ws.counters[buf];
+    Counters* cout = ws.counters + (buf ^ 1u);
+    const uint32_t nLive = cin.nLive, total = cin.nLive + cin.nDead;
+    const uint32_t P = pb.capacity;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t ltMask = (1u << lane) - 1u;
+    const uint32_t ob = buf ^ 1u;
+    uint32_t localMaxBounce = 0;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    // every lane of a warp runs the same number of iterations so the ballots below are convergent
+    for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < total; base += stride) {
+        const uint32_t i = base + lane;
+        ShadeOut out;
+        out.kind = 0; out.envRay = false; out.meshRay = false;
+        if (i < total) {
+            const uint32_t q = i < nLive ? i : (P - 1u - (i - nLive));
+            uint32_t b;
+            shadeOne(sc, k, pb, buf, q, out, b);
+            localMaxBounce = max(localMaxBounce, b);
+        }
+        // ---- warp-ballot compaction into the other ping-pong buffer -----------------------------
+        const uint32_t liveMask = __ballot_sync(0xFFFFFFFFu, out.kind == 1);
+        const uint32_t deadMask = __ballot_sync(0xFFFFFFFFu, out.kind == 2);
+        const uint32_t envMask = __ballot_sync(0xFFFFFFFFu, out.envRay);
+        const uint32_t meshMask = __ballot_sync(0xFFFFFFFFu, out.meshRay);
+        uint32_t liveBase = 0, deadBase = 0, shadowBase = 0;
+        if (lane == 0) {
+            if (liveMask) liveBase = atomicAdd(&cout->nLive, (uint32_t)__popc(liveMask));
+            if (deadMask) deadBase = atomicAdd(&cout->nDead, (uint32_t)__popc(deadMask));
+            if (envMask | meshMask) shadowBase = atomicAdd(&cout->nShadow, (uint32_t)(__popc(envMask) + __popc(meshMask)));
+        }
+        liveBase = __shfl_sync(0xFFFFFFFFu, liveBase, 0);
+        deadBase = __shfl_sync(0xFFFFFFFFu, deadBase, 0);
+        shadowBase = __shfl_sync(0xFFFFFFFFu, shadowBase, 0);
+        if (out.kind != 0) {
+            const uint32_t oq = out.kind == 1 ? liveBase + __popc(liveMask & ltMask) : P - 1u - (deadBase + __popc(deadMask & ltMask));
+            pb.R0[ob][oq] = out.R0; pb.R1[ob][oq] = out.R1; pb.S0[ob][oq] = out.S0; pb.S1[ob][oq] = out.S1;
+            pb.N0[ob][oq] = out.N0; pb.N1[ob][oq] = out.N1;
+            if (out.envRay) {
+                const uint32_t si = shadowBase + __popc(envMask & ltMask);
+                out.envQ1.w = __uint_as_float(oq * 2u + 0u);
+                pb.Q0[si] = out.envQ0; pb.Q1[si] = out.envQ1;
+            }
+            if (out.meshRay) {
+                const uint32_t si = shadowBase + __popc(envMask) + __popc(meshMask & ltMask);
+                out.meshQ1.w = __uint_as_float(oq * 2u + 1u);
+                pb.Q0[si] = out.meshQ0; pb.Q1[si] = out.meshQ1;
+            }
+        }
+    }
+    // last block out: clear the consumed counters, publish the deepest bounce seen
+    if (localMaxBounce) atomicMax(ws.maxBounce, localMaxBounce);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const uint32_t done = atomicAdd(ws.shadeDone, 1u);
+        if (done == gridDim.x - 1) {
+            ws.counters[buf].nLive = 0; ws.counters[buf].nDead = 0; ws.counters[buf].nShadow = 0;
+            *ws.shadeDone = 0;
+            __threadfence();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// accumulate: raygen's sample loop sum + storeColor (main.hlsl:79-94, :43-51), in sample-index order
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_accumulate(const float4* __restrict__ result, float4* image, float4* runState, const uint32_t* __restrict__ pixIds,
+                                                    uint32_t nPix, uint32_t nSamples, uint32_t firstSample, uint32_t spr) {
+    const uint32_t pi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pi >= nPix) return;
+    const uint32_t pix = __ldg(pixIds + pi);
+    float4 rs = runState[pi];   // (sum.rgb, samples summed so far in the current launch)
+    float3 color = mk3(rs.x, rs.y, rs.z);
+    uint32_t cnt = __float_as_uint(rs.w);
+    float4 texel = image[pix];
+    for (uint32_t s = 0; s < nSamples; s++) {
+        const float4 c = result[(size_t)s * nPix + pi];
+        color = color + mk3(c.x, c.y, c.z);
+        cnt++;
+        if (cnt == spr) {
+            const uint32_t pushSampleCount = (firstSample + s + 1u) - spr;   // sampleCount of the launch that just completed
+            if (pushSampleCount == 0) {
+                const float3 o = color / (float)spr;
+                texel = make_float4(o.x, o.y, o.z, 1.0f);
+            } else {
+                const float3 prior = mk3(texel.x, texel.y, texel.z);
+                const float3 dlt = (color - prior) / (float)(pushSampleCount + spr);
+                texel = make_float4(texel.x + dlt.x, texel.y + dlt.y, texel.z + dlt.z, texel.w + 1.0f);
+            }
+            color = mk3(0.0f); cnt = 0;
+        }
+    }
+    image[pix] = texel;
+    runState[pi] = make_float4(color.x, color.y, color.z, __uint_as_float(cnt));
+}
+
+// ------------------------------------------------------------------------------------------------
+// environment pre-process (shaders/background/{equirectangular_to_equal_area,luminance,fold}.hlsl)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_env_resample(const float4* __restrict__ src, uint32_t W, uint32_t H, float4* dstRgb, float* dstLum, uint32_t S) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= S || y >= S) return;
+    float3 color = mk3(0.0f);
+    for (uint32_t i = 0; i < 3; i++)
+        for (uint32_t j = 0; j < 3; j++) {
+            const float2 subpixel = mk2((float)(1 + i), (float)(1 + j)) / mk2(4.0f, 4.0f);
+            const float2 dstCoords = (mk2((float)x, (float)y) + subpixel) / mk2((float)S, (float)S);
+            const float3 dir = squareToEqualAreaSphere(dstCoords);
+            const float2 uv = cartesianToSpherical(dir) / mk2(2 * MS_PI, MS_PI);
+            float4 t;
+            if (W == 1 && H == 1) t = src[0];
+            else {
+                const float u = uv.x * (float)W - 0.5f, v = uv.y * (float)H - 0.5f;
+                const float fu = floorf(u), fv = floorf(v);
+                const float a = u - fu, b = v - fv;
+                const int i0 = wrapMirror((int)fu, W), i1 = wrapMirror((int)fu + 1, W), j0 = wrapMirror((int)fv, H), j1 = wrapMirror((int)fv + 1, H);
+                t = lerp4(lerp4(src[(size_t)j0 * W + i0], src[(size_t)j0 * W + i1], a), lerp4(src[(size_t)j1 * W + i0], src[(size_t)j1 * W + i1], a), b);
+            }
+            color = color + mk3(t.x, t.y, t.z);
+        }
+    const float3 c = color / 9.0f;
+    dstRgb[(size_t)y * S + x] = make_float4(c.x, c.y, c.z, 1.0f);
+    dstLum[(size_t)y * S + x] = luminance(c);
+}
+__global__ void k_env_fold(const float* __restrict__ srcMip, float* dstMip, uint32_t dstSize) {
+    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    if (x >= dstSize || y >= dstSize) return;
+    const uint32_t ps = dstSize * 2;
+    dstMip[(size_t)y * dstSize + x] = srcMip[(size_t)(2 * y) * ps + 2 * x] + srcMip[(size_t)(2 * y) * ps + 2 * x + 1] +
+                                      srcMip[(size_t)(2 * y + 1) * ps + 2 * x] + srcMip[(size_t)(2 * y + 1) * ps + 2 * x + 1];
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-callable launch wrappers
+// ------------------------------------------------------------------------------------------------
+static inline dim3 grid1(uint64_t n, uint32_t block) { return dim3((uint32_t)((n + block - 1) / block)); }
+
+void launchGenerate(cudaStream_t st, const DCamera& cam, const DConstants& k, const PathBuffers& pb, Counters* counters, const uint32_t* pixIds,
+                    uint32_t nPix, uint32_t nSamples, uint32_t firstSample) {
+    k_generate<<<grid1((uint64_t)nPix * nSamples, 256), 256, 0, st>>>(cam, k, pb, counters, pixIds, nPix, nSamples, firstSample);
+}
+void launchTrace(cudaStream_t st, int blocks, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf) {
+    k_trace<<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf);
+}
+void launchShade(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf) {
+    k_shade<<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf);
+}
+void launchAccumulate(cudaStream_t st, const float4* result, float4* image, float4* runState, const uint32_t* pixIds, uint32_t nPix, uint32_t nSamples,
+                      uint32_t firstSample, uint32_t spr) {
+    k_accumulate<<<grid1(nPix, 256), 256, 0, st>>>(result, image, runState, pixIds, nPix, nSamples, firstSample, spr);
+}
+void launchEnvResample(cudaStream_t st, const float4* src, uint32_t W, uint32_t H, float4* dstRgb, float* dstLum, uint32_t S) {
+    dim3 b(8, 8), g((S + 7) / 8, (S + 7) / 8);
+    k_env_resample<<<g, b, 0, st>>>(src, W, H, dstRgb, dstLum, S);
+}
+void launchEnvFold(cudaStream_t st, const float* srcMip, float* dstMip, uint32_t dstSize) {
+    dim3 b(8, 8), g((dstSize + 7) / 8, (dstSize + 7) / 8);
+    k_env_fold<<<g, b, 0, st>>>(srcMip, dstMip, dstSize);
+}
+void launchTraceProbe(cudaStream_t st, const DeviceScene& sc, const float* rays8, uint32_t n, int anyHit, uint32_t* hits5) {
+    k_trace_probe<<<grid1(n, 128), 128, 0, st>>>(sc, rays8, n, anyHit, hits5);
+}
+void launchPrimaryProbe(cudaStream_t st, const DCamera& cam, const DConstants& k, uint32_t sample, float* rays6, uint32_t* rngState) {
+    k_primary_probe<<<grid1((uint64_t)cam.width * cam.height, 256), 256, 0, st>>>(cam, k, sample, rays6, rngState);
+}
+int traceOccupancyBlocksPerSm() {
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace, TRACE_THREADS, 0);
+    return n;
+}
+int shadeOccupancyBlocksPerSm() {
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade, SHADE_THREADS, 0);
+    return n;
+}
+
+}  // namespace msne

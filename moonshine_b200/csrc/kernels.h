@@ -1,0 +1,31 @@
+// Launch wrappers of the sm_100a kernels (kernels.cu), callable from the host runtime (runtime.cpp).
+#pragma once
+#include <cuda_runtime.h>
+#include "dtypes.h"
+
+namespace msne {
+
+#ifndef TRACE_THREADS
+#define TRACE_THREADS 128
+#endif
+#ifndef TRACE_BLOCKS_PER_SM
+#define TRACE_BLOCKS_PER_SM 4
+#endif
+#ifndef SHADE_THREADS
+#define SHADE_THREADS 128
+#endif
+
+void launchGenerate(cudaStream_t st, const DCamera& cam, const DConstants& k, const PathBuffers& pb, Counters* counters, const uint32_t* pixIds,
+                    uint32_t nPix, uint32_t nSamples, uint32_t firstSample);
+void launchTrace(cudaStream_t st, int blocks, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf);
+void launchShade(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf);
+void launchAccumulate(cudaStream_t st, const float4* result, float4* image, float4* runState, const uint32_t* pixIds, uint32_t nPix, uint32_t nSamples,
+                      uint32_t firstSample, uint32_t spr);
+void launchEnvResample(cudaStream_t st, const float4* src, uint32_t W, uint32_t H, float4* dstRgb, float* dstLum, uint32_t S);
+void launchEnvFold(cudaStream_t st, const float* srcMip, float* dstMip, uint32_t dstSize);
+void launchTraceProbe(cudaStream_t st, const DeviceScene& sc, const float* rays8, uint32_t n, int anyHit, uint32_t* hits5);
+void launchPrimaryProbe(cudaStream_t st, const DCamera& cam, const DConstants& k, uint32_t sample, float* rays6, uint32_t* rngState);
+int traceOccupancyBlocksPerSm();
+int shadeOccupancyBlocksPerSm();
+
+}  // namespace msne

@@ -1,0 +1,923 @@
+// Host runtime of libmoonshine.so: the `HdMoonshine` object behind the reference's C ABI
+// (include/moonshine.h <- hydra/moonshine.h:71-95, implemented in the reference by hydra/hydra.zig:107-558)
+// plus the extensions of include/moonshine_ext.h.
+//
+// Replaces, for the hot path only: engine/hrtsystem/{Accel,MeshManager,MaterialManager,BackgroundManager,
+// Camera,pipeline}.zig and engine/core (Vulkan context/allocator/commands) with CUDA-runtime equivalents:
+// device buffers, one stream, events, and the wavefront scheduler that drives kernels.cu.
+// There is NO CPU fallback: every entry point that renders requires a CUDA device and fails otherwise.
+//
+// Host FP32 arithmetic that feeds the device (camera basis, inverse transforms, alias table, emitter
+// areas) is compiled with -ffp-contract=off and follows the reference's operation order
+// (engine/vector.zig:350-362,501-521; engine/hrtsystem/alias_table.zig:28-91; Accel.zig:503-521).
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/moonshine_ext.h"
+#include "bvh_build.h"
+#include "dtypes.h"
+#include "kernels.h"
+
+using namespace msne;
+
+namespace {
+
+thread_local std::string g_lastError;
+int g_device = 0;
+
+struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
+
+#define CK(expr)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (expr);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            char buf_[512];                                                                              \
+            snprintf(buf_, sizeof(buf_), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            throw CudaError(buf_);                                                                       \
+        }                                                                                                \
+    } while (0)
+
+[[noreturn]] void fatal(const char* what) {
+    // hydra.zig: `catch unreachable` — everything but Create/Render/RebuildPipeline aborts on failure
+    fprintf(stderr, "libmoonshine: fatal: %s\n", what);
+    abort();
+}
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    void alloc(size_t count) { release(); if (count) { CK(cudaMalloc((void**)&p, count * sizeof(T))); n = count; } }
+    void ensure(size_t count) { if (count > n) alloc(count); }
+    void upload(const T* src, size_t count, cudaStream_t st) {
+        ensure(count);
+        if (count) CK(cudaMemcpyAsync(p, src, count * sizeof(T), cudaMemcpyHostToDevice, st));
+    }
+};
+
+struct HostMesh {
+    std::vector<float> pos, nrm, uv;     // host copies (alias table + BLAS builds; MeshManager.zig:46-48)
+    std::vector<uint32_t> idx;
+    DevBuf<float> dPos, dNrm, dUv;
+    DevBuf<uint32_t> dIdx;
+};
+
+struct HostTexture { DevBuf<uint8_t> data; uint32_t w, h, fmt; };
+
+struct HostInstance {
+    float transform[12];
+    float inverse[12];
+    bool visible;
+    uint32_t customIndex, geometryCount;
+    std::vector<uint32_t> meshKey;   // BLAS dedupe key: the mesh ids of the geometry list (Accel.zig:315-343)
+    uint32_t blas;                   // index into blases
+};
+
+struct Blas { uint32_t rootNode; BuildBox bounds; };
+
+struct Sensor {
+    Extent2D extent{};
+    uint32_t sample_count = 0;
+    DevBuf<float4> image;
+    float* host = nullptr;           // pinned, W*H*4 floats, returned by HdMoonshineGetSensorData
+    DevBuf<uint32_t> pixIds;         // owned pixels in tile order
+    DevBuf<float4> runState;
+    uint32_t nPix = 0;
+    uint32_t shardRank = 0, shardWorld = 0;   // shard the pixIds were built for
+};
+
+// engine/vector.zig:350-362 (inverse_affine) on row-major 3x4
+void inverseAffine(const float* M, float* R) {
+    auto cross = [](const float* a, const float* b, float* o) { o[0] = a[1] * b[2] - b[1] * a[2]; o[1] = a[2] * b[0] - b[2] * a[0]; o[2] = a[0] * b[1] - b[0] * a[1]; };
+    const float px[3] = {M[0], M[4], M[8]}, py[3] = {M[1], M[5], M[9]}, pz[3] = {M[2], M[6], M[10]};
+    const float v[3] = {M[3], M[7], M[11]};
+    float c[3];
+    cross(py, pz, c);
+    const float det = px[0] * c[0] + px[1] * c[1] + px[2] * c[2];
+    const float rd = 1 / det;
+    float v1[3], v2[3], v3[3];
+    cross(py, pz, v1); cross(pz, px, v2); cross(px, py, v3);
+    for (int i = 0; i < 3; i++) { v1[i] *= rd; v2[i] *= rd; v3[i] *= rd; }
+    const float ix[3] = {v1[0], v2[0], v3[0]}, iy[3] = {v1[1], v2[1], v3[1]}, iz[3] = {v1[2], v2[2], v3[2]};
+    float res[3];
+    for (int i = 0; i < 3; i++) {
+        float r = (ix[i] * -1.0f) * v[0];
+        r = (iy[i] * -1.0f) * v[1] + r;
+        r = (iz[i] * -1.0f) * v[2] + r;
+        res[i] = r;
+    }
+    for (int r = 0; r < 3; r++) { R[4 * r + 0] = ix[r]; R[4 * r + 1] = iy[r]; R[4 * r + 2] = iz[r]; R[4 * r + 3] = res[r]; }
+}
+
+// engine/hrtsystem/alias_table.zig:28-91 (Vose); entries carry their payload already
+float buildAliasTable(const std::vector<float>& w, std::vector<DAlias>& e) {
+    const uint32_t NONE = 0xFFFFFFFFu, n = (uint32_t)w.size();
+    float sum = 0.0f;
+    for (float x : w) sum += x;
+    uint32_t less = NONE, more = NONE;
+    for (uint32_t i = 0; i < n; i++) {
+        const float adj = (w[i] * (float)n) / sum;
+        e[i].select = adj;
+        if (adj < 1.0f) { e[i].alias = less; less = i; } else { e[i].alias = more; more = i; }
+    }
+    while (less != NONE && more != NONE) {
+        const uint32_t l = less; less = e[l].alias;
+        const uint32_t m = more; more = e[m].alias;
+        e[l].alias = m;
+        e[m].select = (e[m].select + e[l].select) - 1.0f;
+        if (e[m].select < 1.0f) { e[m].alias = less; less = m; } else { e[m].alias = more; more = m; }
+    }
+    while (less != NONE) { const uint32_t l = less; less = e[l].alias; e[l].select = 1.0f; }
+    return sum;
+}
+
+float srgbToLinear(int c) {
+    const double s = c / 255.0;
+    return (float)(s <= 0.04045 ? s / 12.92 : std::pow((s + 0.055) / 1.055, 2.4));
+}
+
+size_t texelBytes(uint32_t fmt) {
+    switch (fmt) {
+        case TEX_R32F: return 4; case TEX_RG32F: return 8; case TEX_RGBA32F: return 16; case TEX_R8_UNORM: return 1;
+        case TEX_RG8_UNORM: return 2; case TEX_RGBA8_SRGB: return 4; case TEX_RGBA16F: return 8; default: return 0;
+    }
+}
+
+}  // namespace
+
+struct HdMoonshine {
+    int device = 0;
+    int smCount = 148;
+    cudaStream_t stream = nullptr;
+    std::mutex mutex;   // hydra.zig:78 — every entry point is serialised
+
+    // scene (host mirrors + device tables)
+    std::vector<std::unique_ptr<HostMesh>> meshes;
+    std::vector<std::unique_ptr<HostTexture>> textures;
+    std::vector<DMaterial> materials;
+    std::vector<HostInstance> instances;
+    std::vector<DGeometry> geometries;
+    std::vector<DAlias> alias;   // [0] header; always at least the header
+    std::map<std::vector<uint32_t>, uint32_t> blasByKey;
+    std::vector<Blas> blases;
+    std::vector<BvhNode2> blasNodePool;
+    std::vector<TriRec> triPool;
+
+    bool tablesDirty = true, accelDirty = true, poolDirty = true, aliasDirty = true;
+
+    DevBuf<BvhNode2> dTlasNodes, dBlasNodes;
+    DevBuf<uint32_t> dTlasItems;
+    DevBuf<TriRec> dTris;
+    DevBuf<DInstance> dInstances;
+    DevBuf<DGeometry> dGeometries;
+    DevBuf<DMesh> dMeshes;
+    DevBuf<DMaterial> dMaterials;
+    DevBuf<DTexture> dTextures;
+    DevBuf<DAlias> dAlias;
+    DevBuf<float> dSrgbLut;
+    DevBuf<float4> dEnvRgb;
+    DevBuf<float> dEnvLum;
+    uint32_t envSize = 0, envLevels = 0, envLevelOffset[12] = {0};
+    bool hasTlas = false;
+
+    MsneSpecConstants consts{};   // hydra defaults (hydra.zig:97-105)
+    std::vector<Lens> lenses;
+    std::vector<std::unique_ptr<Sensor>> sensors;
+    uint32_t shardRank = 0, shardWorld = 1;
+
+    // wavefront pool
+    uint64_t pathsInFlight = 1ull << 24;
+    PathBuffers pb{};
+    std::vector<DevBuf<float4>> poolBufs;
+    DevBuf<uint4> poolH;
+    DevBuf<Counters> dCounters;
+    DevBuf<uint32_t> dScalars;       // [0] traceTicket [1] traceDone [2] shadeDone [3] maxBounce
+    DevBuf<unsigned long long> dRayCounts;
+    Counters* hostCounters = nullptr;   // pinned ring of 4
+    cudaEvent_t bounceEvents[4]{};
+    cudaEvent_t evStart = nullptr, evStop = nullptr;
+    int traceBlocks = 0, shadeBlocks = 0;
+
+    // profiling
+    bool profiling = false;
+    static const int kProfEvents = 96;
+    cudaEvent_t profEv[kProfEvents][2]{};
+    MsneStats stats{};
+
+    // ---- lifecycle ---------------------------------------------------------------------------
+    void init() {
+        device = g_device;
+        CK(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, device));
+        smCount = prop.multiProcessorCount;
+        CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        for (auto& e : bounceEvents) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        CK(cudaEventCreate(&evStart)); CK(cudaEventCreate(&evStop));
+        for (auto& p : profEv) { CK(cudaEventCreate(&p[0])); CK(cudaEventCreate(&p[1])); }
+        CK(cudaMallocHost((void**)&hostCounters, 4 * sizeof(Counters)));
+        dCounters.alloc(2); dScalars.alloc(4); dRayCounts.alloc(2);
+        CK(cudaMemsetAsync(dCounters.p, 0, 2 * sizeof(Counters), stream));
+        CK(cudaMemsetAsync(dScalars.p, 0, 4 * sizeof(uint32_t), stream));
+        CK(cudaMemsetAsync(dRayCounts.p, 0, 2 * sizeof(unsigned long long), stream));
+        float lut[256];
+        for (int i = 0; i < 256; i++) lut[i] = srgbToLinear(i);
+        dSrgbLut.upload(lut, 256, stream);
+        alias.assign(1, DAlias{0, 0.0f, 0, 0, 0});
+        // hydra.zig:97-105
+        consts = MsneSpecConstants{1, 1024, 0, 0, 0, 0, 0};
+        const float white[4] = {1, 1, 1, 1};
+        setBackground(white, 1, 1);   // addDefaultBackground (BackgroundManager.zig:116-126)
+        traceBlocks = smCount * std::max(1, traceOccupancyBlocksPerSm());
+        shadeBlocks = smCount * std::max(1, shadeOccupancyBlocksPerSm());
+        CK(cudaStreamSynchronize(stream));
+    }
+
+    ~HdMoonshine() {
+        cudaSetDevice(device);
+        if (stream) cudaStreamSynchronize(stream);
+        for (auto& s : sensors) if (s && s->host) cudaFreeHost(s->host);
+        if (hostCounters) cudaFreeHost(hostCounters);
+        for (auto& e : bounceEvents) if (e) cudaEventDestroy(e);
+        if (evStart) cudaEventDestroy(evStart);
+        if (evStop) cudaEventDestroy(evStop);
+        for (auto& p : profEv) { if (p[0]) cudaEventDestroy(p[0]); if (p[1]) cudaEventDestroy(p[1]); }
+        if (stream) cudaStreamDestroy(stream);
+    }
+
+    void use() { CK(cudaSetDevice(device)); }
+
+    // ---- environment (BackgroundManager.zig:142-394) -----------------------------------------
+    void setBackground(const float* rgba, uint32_t W, uint32_t H) {
+        DevBuf<float4> src;
+        src.upload(reinterpret_cast<const float4*>(rgba), (size_t)W * H, stream);
+        uint32_t p2 = 1;
+        while (p2 * 2 <= H) p2 *= 2;
+        const uint32_t S = std::min(p2, 1024u);
+        envSize = S;
+        envLevels = 0;
+        size_t total = 0;
+        for (uint32_t s = S; s >= 1; s >>= 1) { envLevelOffset[envLevels++] = (uint32_t)total; total += (size_t)s * s; if (s == 1) break; }
+        dEnvRgb.ensure((size_t)S * S);
+        dEnvLum.ensure(total);
+        launchEnvResample(stream, src.p, W, H, dEnvRgb.p, dEnvLum.p, S);
+        stats.kernel_launches++;
+        for (uint32_t l = 1; l < envLevels; l++) {
+            launchEnvFold(stream, dEnvLum.p + envLevelOffset[l - 1], dEnvLum.p + envLevelOffset[l], S >> l);
+            stats.kernel_launches++;
+        }
+        CK(cudaStreamSynchronize(stream));   // src is freed on return
+    }
+
+    // ---- acceleration structure --------------------------------------------------------------
+    uint32_t getBlas(const std::vector<uint32_t>& key) {
+        auto it = blasByKey.find(key);
+        if (it != blasByKey.end()) return it->second;
+        std::vector<BuildBox> boxes;
+        std::vector<TriRec> tris;
+        for (uint32_t g = 0; g < key.size(); g++) {
+            const HostMesh& m = *meshes[key[g]];
+            const uint32_t nTri = (uint32_t)(m.idx.size() / 3);
+            for (uint32_t p = 0; p < nTri; p++) {
+                TriRec t{};
+                const float* v[3] = {&m.pos[3 * (size_t)m.idx[3 * p]], &m.pos[3 * (size_t)m.idx[3 * p + 1]], &m.pos[3 * (size_t)m.idx[3 * p + 2]]};
+                memcpy(t.v0, v[0], 12); memcpy(t.v1, v[1], 12); memcpy(t.v2, v[2], 12);
+                t.geom = g; t.prim = p; t.pad = 0;
+                BuildBox b;
+                for (int a = 0; a < 3; a++) {
+                    b.lo[a] = std::min(v[0][a], std::min(v[1][a], v[2][a]));
+                    b.hi[a] = std::max(v[0][a], std::max(v[1][a], v[2][a]));
+                }
+                tris.push_back(t); boxes.push_back(b);
+            }
+        }
+        BuiltBvh bvh;
+        buildBvh2(boxes.data(), (uint32_t)boxes.size(), 4, bvh);
+        const uint32_t nodeBase = (uint32_t)blasNodePool.size(), triBase = (uint32_t)triPool.size();
+        for (BvhNode2 n : bvh.nodes) {
+            for (int s = 0; s < 2; s++) {
+                if (n.c[2 + s] > 0) n.c[s] += (int32_t)triBase;          // leaf: first triangle in the pool
+                else if (n.c[s] >= 0) n.c[s] += (int32_t)nodeBase;       // inner: pooled node index
+            }
+            blasNodePool.push_back(n);
+        }
+        for (uint32_t i = 0; i < bvh.order.size(); i++) triPool.push_back(tris[bvh.order[i]]);
+        Blas b; b.rootNode = nodeBase; b.bounds = bvh.bounds;
+        blases.push_back(b);
+        const uint32_t id = (uint32_t)blases.size() - 1;
+        blasByKey[key] = id;
+        poolDirty = true;
+        return id;
+    }
+
+    void syncScene() {
+        if (tablesDirty) {
+            std::vector<DMesh> dm(meshes.size());
+            for (size_t i = 0; i < meshes.size(); i++) dm[i] = DMesh{meshes[i]->dPos.p, meshes[i]->dUv.p, meshes[i]->dNrm.p, meshes[i]->dIdx.p};
+            dMeshes.upload(dm.data(), dm.size(), stream);
+            std::vector<DTexture> dt(textures.size());
+            for (size_t i = 0; i < textures.size(); i++) dt[i] = DTexture{textures[i]->data.p, textures[i]->w, textures[i]->h, textures[i]->fmt, 0};
+            dTextures.upload(dt.data(), dt.size(), stream);
+            dMaterials.upload(materials.data(), materials.size(), stream);
+            dGeometries.upload(geometries.data(), geometries.size(), stream);
+            CK(cudaStreamSynchronize(stream));   // staging vectors die here
+            tablesDirty = false;
+        }
+        if (accelDirty) {
+            for (auto& in : instances) in.blas = getBlas(in.meshKey);
+            if (poolDirty) {
+                dBlasNodes.upload(blasNodePool.data(), blasNodePool.size(), stream);
+                dTris.upload(triPool.data(), triPool.size(), stream);
+                poolDirty = false;
+            }
+            std::vector<DInstance> di(instances.size());
+            std::vector<BuildBox> boxes;
+            std::vector<uint32_t> items;
+            for (uint32_t i = 0; i < instances.size(); i++) {
+                const HostInstance& in = instances[i];
+                DInstance d{};
+                memcpy(d.o2w, in.transform, 48); memcpy(d.w2o, in.inverse, 48);
+                d.customIndex = in.customIndex; d.blasRoot = blases[in.blas].rootNode; d.visible = in.visible ? 1 : 0;
+                di[i] = d;
+                if (!in.visible) continue;
+                const BuildBox& bb = blases[in.blas].bounds;
+                BuildBox w; for (int a = 0; a < 3; a++) { w.lo[a] = 1e30f; w.hi[a] = -1e30f; }
+                for (int c = 0; c < 8; c++) {
+                    const float p[3] = {(c & 1) ? bb.hi[0] : bb.lo[0], (c & 2) ? bb.hi[1] : bb.lo[1], (c & 4) ? bb.hi[2] : bb.lo[2]};
+                    for (int r = 0; r < 3; r++) {
+                        const float q = ((in.transform[4 * r] * p[0] + in.transform[4 * r + 1] * p[1]) + in.transform[4 * r + 2] * p[2]) + in.transform[4 * r + 3];
+                        w.lo[r] = std::min(w.lo[r], q); w.hi[r] = std::max(w.hi[r], q);
+                    }
+                }
+                padBox(w);
+                boxes.push_back(w); items.push_back(i);
+            }
+            dInstances.upload(di.data(), di.size(), stream);
+            hasTlas = !items.empty();
+            if (hasTlas) {
+                BuiltBvh tl;
+                buildBvh2(boxes.data(), (uint32_t)boxes.size(), 1, tl);
+                std::vector<uint32_t> slots(tl.order.size());
+                for (size_t s = 0; s < tl.order.size(); s++) slots[s] = items[tl.order[s]];
+                dTlasNodes.upload(tl.nodes.data(), tl.nodes.size(), stream);
+                dTlasItems.upload(slots.data(), slots.size(), stream);
+            }
+            CK(cudaStreamSynchronize(stream));
+            accelDirty = false;
+        }
+        if (aliasDirty) {
+            dAlias.upload(alias.data(), alias.size(), stream);
+            CK(cudaStreamSynchronize(stream));
+            aliasDirty = false;
+        }
+    }
+
+    DeviceScene deviceScene() const {
+        DeviceScene sc{};
+        sc.tlasNodes = hasTlas ? dTlasNodes.p : nullptr;
+        sc.tlasItems = dTlasItems.p;
+        sc.blasNodes = dBlasNodes.p; sc.tris = dTris.p; sc.instances = dInstances.p; sc.geometries = dGeometries.p;
+        sc.meshes = dMeshes.p; sc.materials = dMaterials.p; sc.textures = dTextures.p;
+        sc.alias = dAlias.p; sc.aliasEntries = (uint32_t)alias.size();
+        sc.envRgb = reinterpret_cast<const float*>(dEnvRgb.p); sc.envLum = dEnvLum.p; sc.envSize = envSize; sc.envLevels = envLevels;
+        for (int i = 0; i < 12; i++) sc.envLevelOffset[i] = envLevelOffset[i];
+        sc.srgbLut = dSrgbLut.p;
+        return sc;
+    }
+    DConstants deviceConstants() const {
+        return DConstants{consts.samples_per_run, consts.max_bounces, consts.env_samples_per_bounce, consts.mesh_samples_per_bounce,
+                          consts.flip_image, consts.indexed_attributes, consts.two_component_normal_texture};
+    }
+
+    // Accel.zig:491-538
+    void buildEmitterTable() {
+        std::vector<float> weights;
+        std::vector<DAlias> entries;
+        for (uint32_t i = 0; i < instances.size(); i++) {
+            const HostInstance& in = instances[i];
+            for (uint32_t j = 0; j < in.geometryCount; j++) {
+                const DGeometry& g = geometries[in.customIndex + j];
+                if (!(g.sampled & 0xFF)) continue;
+                const HostMesh& m = *meshes[g.mesh];
+                const uint32_t nTri = (uint32_t)(m.idx.size() / 3);
+                for (uint32_t k = 0; k < nTri; k++) {
+                    float p[3][3];
+                    for (int v = 0; v < 3; v++) {
+                        const float* q = &m.pos[3 * (size_t)m.idx[3 * k + v]];
+                        // Mat3x4.mul_point (vector.zig:283-288): row.dot((q,1)) = x*x' + y*y' + z*z' + w*1
+                        for (int r = 0; r < 3; r++) p[v][r] = in.transform[4 * r] * q[0] + in.transform[4 * r + 1] * q[1] + in.transform[4 * r + 2] * q[2] + in.transform[4 * r + 3] * 1.0f;
+                    }
+                    const float a[3] = {p[1][0] - p[0][0], p[1][1] - p[0][1], p[1][2] - p[0][2]}, b[3] = {p[2][0] - p[0][0], p[2][1] - p[0][1], p[2][2] - p[0][2]};
+                    const float c[3] = {a[1] * b[2] - b[1] * a[2], a[2] * b[0] - b[2] * a[0], a[0] * b[1] - b[0] * a[1]};
+                    const float area = std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]) / 2.0f;
+                    weights.push_back(area);
+                    entries.push_back(DAlias{0, 0.0f, i, j, k});
+                }
+            }
+        }
+        const float sum = buildAliasTable(weights, entries);
+        alias.clear();
+        alias.push_back(DAlias{(uint32_t)entries.size(), sum, 0, 0, 0});
+        alias.insert(alias.end(), entries.begin(), entries.end());
+        aliasDirty = true;
+    }
+
+    // ---- camera (camera.hlsl:14-30 hoisted) ----------------------------------------------------
+    static DCamera makeCamera(const Lens& c, uint32_t W, uint32_t H) {
+        auto cross = [](const float* a, const float* b, float* o) { o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0]; };
+        DCamera cam{};
+        const float aspect = float(W) / float(H);
+        const float fw[3] = {c.forward.x, c.forward.y, c.forward.z}, up[3] = {c.up.x, c.up.y, c.up.z}, org[3] = {c.origin.x, c.origin.y, c.origin.z};
+        float w[3] = {fw[0] * -1.0f, fw[1] * -1.0f, fw[2] * -1.0f};
+        float u[3], v[3];
+        cross(up, w, u);
+        const float inv = 1.0f / std::sqrt((u[0] * u[0] + u[1] * u[1]) + u[2] * u[2]);
+        for (int i = 0; i < 3; i++) u[i] = u[i] * inv;
+        cross(w, u, v);
+        const float h = std::tan(c.vfov / 2.0f);
+        const float viewport_height = 2.0f * h * c.focus_distance;
+        const float viewport_width = aspect * viewport_height;
+        for (int i = 0; i < 3; i++) {
+            cam.origin[i] = org[i]; cam.u[i] = u[i]; cam.v[i] = v[i];
+            cam.horizontal[i] = u[i] * viewport_width;
+            cam.vertical[i] = v[i] * viewport_height;
+            cam.llc[i] = org[i] - (cam.horizontal[i] / 2.0f) - (cam.vertical[i] / 2.0f) - (w[i] * c.focus_distance);
+        }
+        cam.aperture = c.aperture; cam.width = W; cam.height = H;
+        return cam;
+    }
+
+    // ---- sensors -------------------------------------------------------------------------------
+    void buildPixIds(Sensor& s) {
+        // 32x32 tiles, round-robin over ranks; inside a tile 8x4 blocks so a warp of 32
+        // consecutive queue slots is a compact 8x4 pixel block (coherent primary rays)
+        const uint32_t W = s.extent.width, H = s.extent.height;
+        const uint32_t tx = (W + 31) / 32, ty = (H + 31) / 32;
+        std::vector<uint32_t> ids;
+        ids.reserve((size_t)W * H / std::max(1u, shardWorld) + 1024);
+        for (uint32_t t = 0; t < tx * ty; t++) {
+            if (t % shardWorld != shardRank) continue;
+            const uint32_t x0 = (t % tx) * 32, y0 = (t / tx) * 32;
+            for (uint32_t by = 0; by < 32; by += 4)
+                for (uint32_t bx = 0; bx < 32; bx += 8)
+                    for (uint32_t y = 0; y < 4; y++)
+                        for (uint32_t x = 0; x < 8; x++) {
+                            const uint32_t px = x0 + bx + x, py = y0 + by + y;
+                            if (px < W && py < H) ids.push_back(py * W + px);
+                        }
+        }
+        s.nPix = (uint32_t)ids.size();
+        s.pixIds.upload(ids.data(), ids.size(), stream);
+        s.runState.alloc(std::max<size_t>(1, ids.size()));
+        CK(cudaMemsetAsync(s.runState.p, 0, std::max<size_t>(1, ids.size()) * sizeof(float4), stream));
+        CK(cudaStreamSynchronize(stream));
+        s.shardRank = shardRank; s.shardWorld = shardWorld;
+    }
+    void clearSensor(Sensor& s) {
+        s.sample_count = 0;   // Sensor.clear (core/Sensor.zig:81-83); partial launch sums are dropped too
+        if (s.runState.p) CK(cudaMemsetAsync(s.runState.p, 0, s.runState.n * sizeof(float4), stream));
+    }
+    void clearAllSensors() { for (auto& s : sensors) clearSensor(*s); }
+
+    // ---- wavefront pool --------------------------------------------------------------------------
+    void ensurePool(uint64_t wanted) {
+        const uint32_t P = (uint32_t)std::min<uint64_t>(wanted, 0x7FFFFFFFull / 4);
+        if (pb.capacity >= P && pb.capacity != 0) return;
+        poolBufs.clear();
+        poolBufs.resize(12 + 2 + 1);
+        for (int i = 0; i < 12; i++) poolBufs[i].alloc(P);
+        poolBufs[12].alloc((size_t)2 * P); poolBufs[13].alloc((size_t)2 * P);
+        poolBufs[14].alloc(P);
+        poolH.alloc(P);
+        for (int b = 0; b < 2; b++) {
+            pb.R0[b] = poolBufs[0 + b].p; pb.R1[b] = poolBufs[2 + b].p; pb.S0[b] = poolBufs[4 + b].p; pb.S1[b] = poolBufs[6 + b].p;
+            pb.N0[b] = poolBufs[8 + b].p; pb.N1[b] = poolBufs[10 + b].p;
+        }
+        pb.Q0 = poolBufs[12].p; pb.Q1 = poolBufs[13].p; pb.result = poolBufs[14].p; pb.H = poolH.p; pb.capacity = P;
+    }
+    WaveState waveState() const {
+        WaveState ws{};
+        ws.counters = dCounters.p; ws.traceTicket = dScalars.p + 0; ws.traceDone = dScalars.p + 1; ws.shadeDone = dScalars.p + 2;
+        ws.maxBounce = dScalars.p + 3; ws.rayCounts = dRayCounts.p;
+        return ws;
+    }
+
+    // one wave: `nSamples` consecutive samples of `nPix` owned pixels starting at pixIds + pixOffset
+    void runWave(Sensor& s, const DCamera& cam, const DeviceScene& sc, const DConstants& k, uint32_t pixOffset, uint32_t nPix, uint32_t firstSample, uint32_t nSamples) {
+        const WaveState ws = waveState();
+        launchGenerate(stream, cam, k, pb, dCounters.p, s.pixIds.p + pixOffset, nPix, nSamples, firstSample);
+        stats.kernel_launches++;
+        int profUsed = 0;
+        auto enqueueBounce = [&](uint32_t b) {
+            const uint32_t buf = b & 1u;
+            const bool prof = profiling && profUsed < kProfEvents;
+            if (prof) CK(cudaEventRecord(profEv[profUsed][0], stream));
+            launchTrace(stream, traceBlocks, sc, pb, ws, buf);
+            if (prof) { CK(cudaEventRecord(profEv[profUsed][1], stream)); profUsed++; }
+            launchShade(stream, shadeBlocks, sc, k, pb, ws, buf);
+            stats.kernel_launches += 2;
+            CK(cudaMemcpyAsync(&hostCounters[b & 3u], dCounters.p + (buf ^ 1u), sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+            CK(cudaEventRecord(bounceEvents[b & 3u], stream));
+        };
+        // keep one bounce queued ahead of the one whose survivor count we wait for
+        const uint32_t maxIter = k.max_bounces + 4;
+        enqueueBounce(0);
+        for (uint32_t b = 0; b < maxIter; b++) {
+            enqueueBounce(b + 1);
+            CK(cudaEventSynchronize(bounceEvents[b & 3u]));
+            const Counters c = hostCounters[b & 3u];
+            if (c.nLive + c.nDead == 0) break;   // bounce b+1 then runs on empty queues
+        }
+        launchAccumulate(stream, pb.result, s.image.p, s.runState.p + pixOffset, s.pixIds.p + pixOffset, nPix, nSamples, firstSample, k.samples_per_run);
+        stats.kernel_launches++;
+        if (profUsed) {
+            CK(cudaStreamSynchronize(stream));
+            for (int i = 0; i < profUsed; i++) {
+                float ms = 0;
+                CK(cudaEventElapsedTime(&ms, profEv[i][0], profEv[i][1]));
+                stats.trace_ms += ms; stats.trace_launches++;
+            }
+        }
+    }
+
+    // offline/main.zig:131-165: n launches of samples_per_run samples each; sensor.sample_count advances
+    void renderLaunches(Sensor& s, const Lens& lens, uint32_t nLaunches) {
+        use();
+        if (s.shardRank != shardRank || s.shardWorld != shardWorld || s.pixIds.p == nullptr) { buildPixIds(s); clearSensor(s); }
+        syncScene();
+        const DeviceScene sc = deviceScene();
+        const DConstants k = deviceConstants();
+        const DCamera cam = makeCamera(lens, s.extent.width, s.extent.height);
+        const uint64_t totalSamples = (uint64_t)nLaunches * k.samples_per_run;
+        if (s.nPix == 0 || totalSamples == 0) { s.sample_count += (uint32_t)totalSamples; return; }
+        ensurePool(std::min<uint64_t>(pathsInFlight, (uint64_t)s.nPix * totalSamples));
+        const uint32_t P = pb.capacity;
+        CK(cudaEventRecord(evStart, stream));
+        const uint32_t pixChunk = std::min(s.nPix, P);
+        const uint32_t samplesPerWave = std::max(1u, P / pixChunk);
+        for (uint32_t p0 = 0; p0 < s.nPix; p0 += pixChunk) {
+            const uint32_t np = std::min(pixChunk, s.nPix - p0);
+            for (uint64_t s0 = 0; s0 < totalSamples; s0 += samplesPerWave) {
+                const uint32_t ns = (uint32_t)std::min<uint64_t>(samplesPerWave, totalSamples - s0);
+                runWave(s, cam, sc, k, p0, np, s.sample_count + (uint32_t)s0, ns);
+            }
+        }
+        CK(cudaEventRecord(evStop, stream));
+        CK(cudaStreamSynchronize(stream));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, evStart, evStop));
+        stats.device_ms += ms;
+        stats.samples += (uint64_t)s.nPix * totalSamples;
+        s.sample_count += (uint32_t)totalSamples;
+    }
+
+    void readSensor(Sensor& s) {
+        use();
+        CK(cudaMemcpyAsync(s.host, s.image.p, (size_t)s.extent.width * s.extent.height * sizeof(float4), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+    }
+
+    void fetchStats(MsneStats& out) {
+        use();
+        unsigned long long rc[2] = {0, 0};
+        uint32_t sc[4] = {0, 0, 0, 0};
+        CK(cudaMemcpyAsync(rc, dRayCounts.p, sizeof(rc), cudaMemcpyDeviceToHost, stream));
+        CK(cudaMemcpyAsync(sc, dScalars.p, sizeof(sc), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+        out = stats;
+        out.rays_closest = rc[0]; out.rays_shadow = rc[1]; out.max_bounce_reached = sc[3];
+    }
+};
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+#define LOCK(h) std::lock_guard<std::mutex> lock_((h)->mutex)
+#define ABORT_ON_THROW(...)                          \
+    try { __VA_ARGS__ } catch (const std::exception& e) { fatal(e.what()); }
+
+static uint32_t uploadTexture(HdMoonshine* h, const void* data, uint32_t w, uint32_t hgt, uint32_t fmt) {
+    h->use();
+    auto t = std::make_unique<HostTexture>();
+    t->w = w; t->h = hgt; t->fmt = fmt;
+    const size_t bytes = (size_t)w * hgt * texelBytes(fmt);
+    t->data.alloc(bytes);
+    CK(cudaMemcpyAsync(t->data.p, data, bytes, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));   // `data` is borrowed for the duration of the call
+    h->textures.push_back(std::move(t));
+    h->tablesDirty = true;
+    return (uint32_t)h->textures.size() - 1;
+}
+
+static uint32_t createMesh(HdMoonshine* h, const F32x3* pos, const F32x3* nrm, const F32x2* uv, size_t nPos, size_t nAttr, const U32x3* idx, size_t nTri) {
+    h->use();
+    auto m = std::make_unique<HostMesh>();
+    m->pos.assign((const float*)pos, (const float*)pos + 3 * nPos);
+    m->idx.assign((const uint32_t*)idx, (const uint32_t*)idx + 3 * nTri);
+    m->dPos.upload(m->pos.data(), m->pos.size(), h->stream);
+    m->dIdx.upload(m->idx.data(), m->idx.size(), h->stream);
+    if (nrm) { m->nrm.assign((const float*)nrm, (const float*)nrm + 3 * nAttr); m->dNrm.upload(m->nrm.data(), m->nrm.size(), h->stream); }
+    if (uv) { m->uv.assign((const float*)uv, (const float*)uv + 2 * nAttr); m->dUv.upload(m->uv.data(), m->uv.size(), h->stream); }
+    CK(cudaStreamSynchronize(h->stream));
+    h->meshes.push_back(std::move(m));
+    h->tablesDirty = true;
+    return (uint32_t)h->meshes.size() - 1;
+}
+
+extern "C" {
+
+const char* HdMoonshineExtLastError(void) { return g_lastError.c_str(); }
+
+bool HdMoonshineExtSetDevice(int ordinal) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || ordinal < 0 || ordinal >= n) { g_lastError = "no such CUDA device"; return false; }
+    g_device = ordinal;
+    return true;
+}
+
+HdMoonshine* HdMoonshineCreate(void) {
+    HdMoonshine* h = nullptr;
+    try {
+        h = new HdMoonshine();
+        h->init();
+        return h;
+    } catch (const std::exception& e) {
+        g_lastError = e.what();
+        fprintf(stderr, "libmoonshine: HdMoonshineCreate failed: %s\n", e.what());
+        delete h;
+        return nullptr;   // hydra.zig:111-135: any failure -> null
+    }
+}
+
+void HdMoonshineDestroy(HdMoonshine* h) { delete h; }
+
+bool HdMoonshineRender(HdMoonshine* h, SensorHandle sensor, LensHandle lens) {
+    LOCK(h);
+    try {
+        Sensor& s = *h->sensors.at(sensor);
+        h->renderLaunches(s, h->lenses.at(lens), 1);   // hydra.zig:316-329: one traceRays per call
+        h->readSensor(s);                              // hydra.zig:332-358: copy to the persistent host buffer, wait idle
+        return true;
+    } catch (const std::exception& e) { g_lastError = e.what(); return false; }
+}
+
+bool HdMoonshineRebuildPipeline(HdMoonshine* h) {
+    LOCK(h);
+    try { h->use(); h->clearAllSensors(); return true; } catch (const std::exception& e) { g_lastError = e.what(); return false; }
+}
+
+MeshHandle HdMoonshineCreateMesh(HdMoonshine* h, const F32x3* pos, const F32x3* nrm, const F32x2* uv, size_t nPos, const U32x3* idx, size_t nTri) {
+    LOCK(h);
+    // hydra.zig:379-380: normals/texcoords are per-corner arrays of length 3*triangle_count
+    ABORT_ON_THROW(return createMesh(h, pos, nrm, uv, nPos, 3 * nTri, idx, nTri);)
+}
+MeshHandle HdMoonshineExtCreateMeshIndexed(HdMoonshine* h, const F32x3* pos, const F32x3* nrm, const F32x2* uv, size_t nPos, const U32x3* idx, size_t nTri) {
+    LOCK(h);
+    ABORT_ON_THROW(return createMesh(h, pos, nrm, uv, nPos, nPos, idx, nTri);)
+}
+
+ImageHandle HdMoonshineCreateSolidTexture1(HdMoonshine* h, float v, const char*) {
+    LOCK(h);
+    ABORT_ON_THROW(return uploadTexture(h, &v, 1, 1, TEX_R32F);)
+}
+ImageHandle HdMoonshineCreateSolidTexture2(HdMoonshine* h, F32x2 v, const char*) {
+    LOCK(h);
+    ABORT_ON_THROW(return uploadTexture(h, &v, 1, 1, TEX_RG32F);)
+}
+ImageHandle HdMoonshineCreateSolidTexture3(HdMoonshine* h, F32x3 v, const char*) {
+    LOCK(h);
+    const float rgba[4] = {v.x, v.y, v.z, 1.0f};   // stored as f32x4 (MaterialManager.zig:364-373)
+    ABORT_ON_THROW(return uploadTexture(h, rgba, 1, 1, TEX_RGBA32F);)
+}
+ImageHandle HdMoonshineCreateRawTexture(HdMoonshine* h, uint8_t* data, Extent2D e, TextureFormat f, const char*) {
+    LOCK(h);
+    ABORT_ON_THROW(return uploadTexture(h, data, e.width, e.height, f == f16x4 ? TEX_RGBA16F : TEX_RGBA8_SRGB);)
+}
+ImageHandle HdMoonshineExtCreateTexture(HdMoonshine* h, const void* data, Extent2D e, MsneTexFormat f, const char*) {
+    LOCK(h);
+    if (texelBytes((uint32_t)f) == 0) fatal("HdMoonshineExtCreateTexture: unknown format");
+    ABORT_ON_THROW(return uploadTexture(h, data, e.width, e.height, (uint32_t)f);)
+}
+
+MaterialHandle HdMoonshineCreateMaterial(HdMoonshine* h, Material m) {
+    LOCK(h);
+    h->materials.push_back(DMaterial{m.normal, m.emissive, MAT_STANDARD_PBR, m.color, m.metalness, m.roughness, m.ior, 0});
+    h->tablesDirty = true;
+    return (uint32_t)h->materials.size() - 1;
+}
+MaterialHandle HdMoonshineExtCreateMaterial(HdMoonshine* h, const MsneMaterialInfo* m) {
+    LOCK(h);
+    if (m->type > MAT_STANDARD_PBR) fatal("HdMoonshineExtCreateMaterial: bad material type");
+    h->materials.push_back(DMaterial{m->normal, m->emissive, m->type, m->color, m->metalness, m->roughness, m->ior, 0});
+    h->tablesDirty = true;
+    return (uint32_t)h->materials.size() - 1;
+}
+// hydra.zig:435-481: queued in the reference and flushed by the next Render; applied to the host table
+// here and uploaded by the next render — same observable order. (No sensor clear, as in the reference.)
+void HdMoonshineSetMaterialNormal(HdMoonshine* h, MaterialHandle m, ImageHandle i) { LOCK(h); h->materials.at(m).normal = i; h->tablesDirty = true; }
+void HdMoonshineSetMaterialEmissive(HdMoonshine* h, MaterialHandle m, ImageHandle i) { LOCK(h); h->materials.at(m).emissive = i; h->tablesDirty = true; }
+void HdMoonshineSetMaterialColor(HdMoonshine* h, MaterialHandle m, ImageHandle i) { LOCK(h); h->materials.at(m).color = i; h->tablesDirty = true; }
+void HdMoonshineSetMaterialMetalness(HdMoonshine* h, MaterialHandle m, ImageHandle i) { LOCK(h); h->materials.at(m).metalness = i; h->tablesDirty = true; }
+void HdMoonshineSetMaterialRoughness(HdMoonshine* h, MaterialHandle m, ImageHandle i) { LOCK(h); h->materials.at(m).roughness = i; h->tablesDirty = true; }
+void HdMoonshineSetMaterialIOR(HdMoonshine* h, MaterialHandle m, float ior) { LOCK(h); h->materials.at(m).ior = ior; h->tablesDirty = true; }
+
+InstanceHandle HdMoonshineCreateInstance(HdMoonshine* h, Mat3x4 t, const Geometry* geoms, size_t n, bool visible) {
+    LOCK(h);
+    ABORT_ON_THROW(
+        h->use();
+        HostInstance in{};
+        memcpy(in.transform, &t, 48);
+        inverseAffine(in.transform, in.inverse);
+        in.visible = visible;
+        in.customIndex = (uint32_t)h->geometries.size();
+        in.geometryCount = (uint32_t)n;
+        for (size_t i = 0; i < n; i++) {
+            h->geometries.push_back(DGeometry{geoms[i].mesh, geoms[i].material, geoms[i].sampled ? 1u : 0u});
+            in.meshKey.push_back(geoms[i].mesh);
+        }
+        h->instances.push_back(in);
+        h->tablesDirty = true; h->accelDirty = true;
+        h->clearAllSensors();   // hydra.zig:491
+        return (uint32_t)h->instances.size() - 1;
+    )
+}
+void HdMoonshineSetInstanceVisibility(HdMoonshine* h, InstanceHandle i, bool visible) {
+    LOCK(h);
+    ABORT_ON_THROW(h->use(); h->instances.at(i).visible = visible; h->accelDirty = true; h->clearAllSensors();)
+}
+void HdMoonshineDestroyInstance(HdMoonshine* h, InstanceHandle i) { HdMoonshineSetInstanceVisibility(h, i, false); }   // hydra.zig:495-497
+void HdMoonshineSetInstanceTransform(HdMoonshine* h, InstanceHandle i, Mat3x4 t) {
+    LOCK(h);
+    ABORT_ON_THROW(
+        h->use();
+        HostInstance& in = h->instances.at(i);
+        memcpy(in.transform, &t, 48);
+        inverseAffine(in.transform, in.inverse);
+        h->accelDirty = true; h->clearAllSensors();
+    )
+}
+
+SensorHandle HdMoonshineCreateSensor(HdMoonshine* h, Extent2D e) {
+    LOCK(h);
+    ABORT_ON_THROW(
+        h->use();
+        auto s = std::make_unique<Sensor>();
+        s->extent = e;
+        const size_t n = (size_t)e.width * e.height;
+        s->image.alloc(std::max<size_t>(1, n));
+        CK(cudaMemsetAsync(s->image.p, 0, std::max<size_t>(1, n) * sizeof(float4), h->stream));
+        CK(cudaMallocHost((void**)&s->host, std::max<size_t>(1, n) * sizeof(float4)));
+        memset(s->host, 0, n * sizeof(float4));
+        h->buildPixIds(*s);
+        h->sensors.push_back(std::move(s));
+        return (uint32_t)h->sensors.size() - 1;
+    )
+}
+float* HdMoonshineGetSensorData(const HdMoonshine* h, SensorHandle s) { return h->sensors.at(s)->host; }   // no lock (hydra.zig:522-524)
+
+LensHandle HdMoonshineCreateLens(HdMoonshine* h, Lens l) { LOCK(h); h->lenses.push_back(l); return (uint32_t)h->lenses.size() - 1; }
+void HdMoonshineSetLens(HdMoonshine* h, LensHandle i, Lens l) {
+    LOCK(h);
+    ABORT_ON_THROW(h->use(); h->lenses.at(i) = l; h->clearAllSensors();)
+}
+
+// ---- extensions ------------------------------------------------------------------------------------
+bool HdMoonshineExtSetSpecConstants(HdMoonshine* h, const MsneSpecConstants* c) {
+    LOCK(h);
+    if (c->env_samples_per_bounce > 1 || c->mesh_samples_per_bounce > 1 || c->samples_per_run == 0) {
+        g_lastError = "env/mesh samples per bounce must be 0 or 1 and samples_per_run >= 1";
+        return false;
+    }
+    try { h->use(); h->consts = *c; h->clearAllSensors(); return true; } catch (const std::exception& e) { g_lastError = e.what(); return false; }
+}
+void HdMoonshineExtGetSpecConstants(const HdMoonshine* h, MsneSpecConstants* c) { *c = h->consts; }
+
+bool HdMoonshineExtSetBackground(HdMoonshine* h, const float* rgba, Extent2D e) {
+    LOCK(h);
+    try { h->use(); h->setBackground(rgba, e.width, e.height); h->clearAllSensors(); return true; } catch (const std::exception& ex) { g_lastError = ex.what(); return false; }
+}
+bool HdMoonshineExtBuildEmitterTable(HdMoonshine* h) {
+    LOCK(h);
+    try { h->use(); h->buildEmitterTable(); h->clearAllSensors(); return true; } catch (const std::exception& e) { g_lastError = e.what(); return false; }
+}
+bool HdMoonshineExtRenderLaunches(HdMoonshine* h, SensorHandle s, LensHandle l, uint32_t n) {
+    LOCK(h);
+    try { h->renderLaunches(*h->sensors.at(s), h->lenses.at(l), n); return true; } catch (const std::exception& e) { g_lastError = e.what(); return false; }
+}
+bool HdMoonshineExtReadSensor(HdMoonshine* h, SensorHandle s) {
+    LOCK(h);
+    try { h->readSensor(*h->sensors.at(s)); return true; } catch (const std::exception& e) { g_lastError = e.what(); return false; }
+}
+void HdMoonshineExtClearSensor(HdMoonshine* h, SensorHandle s) {
+    LOCK(h);
+    ABORT_ON_THROW(h->use(); h->clearSensor(*h->sensors.at(s));)
+}
+uint32_t HdMoonshineExtGetSensorSampleCount(const HdMoonshine* h, SensorHandle s) { return h->sensors.at(s)->sample_count; }
+void* HdMoonshineExtGetSensorDevicePtr(const HdMoonshine* h, SensorHandle s) { return h->sensors.at(s)->image.p; }
+
+bool HdMoonshineExtSetTileShard(HdMoonshine* h, uint32_t rank, uint32_t world) {
+    LOCK(h);
+    if (world == 0 || rank >= world) { g_lastError = "bad shard"; return false; }
+    try {
+        h->use();
+        h->shardRank = rank; h->shardWorld = world;
+        for (auto& s : h->sensors) {
+            h->buildPixIds(*s);
+            CK(cudaMemsetAsync(s->image.p, 0, (size_t)s->extent.width * s->extent.height * sizeof(float4), h->stream));
+            h->clearSensor(*s);
+        }
+        CK(cudaStreamSynchronize(h->stream));
+        return true;
+    } catch (const std::exception& e) { g_lastError = e.what(); return false; }
+}
+void HdMoonshineExtSetPathsInFlight(HdMoonshine* h, uint64_t n) { LOCK(h); h->pathsInFlight = n ? n : (1ull << 24); h->pb.capacity = 0; }
+void HdMoonshineExtSetProfiling(HdMoonshine* h, bool on) { LOCK(h); h->profiling = on; }
+void HdMoonshineExtGetStats(const HdMoonshine* h, MsneStats* out) {
+    HdMoonshine* m = const_cast<HdMoonshine*>(h);
+    std::lock_guard<std::mutex> lock_(m->mutex);
+    ABORT_ON_THROW(m->fetchStats(*out);)
+}
+void HdMoonshineExtResetStats(HdMoonshine* h) {
+    LOCK(h);
+    ABORT_ON_THROW(
+        h->use();
+        h->stats = MsneStats{};
+        CK(cudaMemsetAsync(h->dRayCounts.p, 0, 2 * sizeof(unsigned long long), h->stream));
+        CK(cudaMemsetAsync(h->dScalars.p + 3, 0, sizeof(uint32_t), h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    )
+}
+
+// ---- debug probes ----------------------------------------------------------------------------------
+bool HdMoonshineExtTraceRays(HdMoonshine* h, const float* rays8, size_t n, bool anyHit, uint32_t* hits5) {
+    LOCK(h);
+    try {
+        h->use(); h->syncScene();
+        DevBuf<float> dr; DevBuf<uint32_t> dh;
+        dr.upload(rays8, 8 * n, h->stream); dh.alloc(5 * n);
+        launchTraceProbe(h->stream, h->deviceScene(), dr.p, (uint32_t)n, anyHit ? 1 : 0, dh.p);
+        h->stats.kernel_launches++;
+        CK(cudaMemcpyAsync(hits5, dh.p, 5 * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return true;
+    } catch (const std::exception& e) { g_lastError = e.what(); return false; }
+}
+bool HdMoonshineExtPrimaryRays(HdMoonshine* h, SensorHandle s, LensHandle l, uint32_t sample, float* rays6, uint32_t* rngState) {
+    LOCK(h);
+    try {
+        h->use();
+        const Sensor& se = *h->sensors.at(s);
+        const size_t n = (size_t)se.extent.width * se.extent.height;
+        DevBuf<float> dr; DevBuf<uint32_t> ds;
+        dr.alloc(6 * n); ds.alloc(n);
+        launchPrimaryProbe(h->stream, HdMoonshine::makeCamera(h->lenses.at(l), se.extent.width, se.extent.height), h->deviceConstants(), sample, dr.p, ds.p);
+        h->stats.kernel_launches++;
+        CK(cudaMemcpyAsync(rays6, dr.p, 6 * n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(rngState, ds.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return true;
+    } catch (const std::exception& e) { g_lastError = e.what(); return false; }
+}
+uint32_t HdMoonshineExtGetEnvSize(const HdMoonshine* h) { return h->envSize; }
+bool HdMoonshineExtGetEnvData(HdMoonshine* h, float* rgba, float* lum) {
+    LOCK(h);
+    try {
+        h->use();
+        size_t total = 0;
+        for (uint32_t s = h->envSize; s >= 1; s >>= 1) { total += (size_t)s * s; if (s == 1) break; }
+        CK(cudaMemcpyAsync(rgba, h->dEnvRgb.p, (size_t)h->envSize * h->envSize * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(lum, h->dEnvLum.p, total * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return true;
+    } catch (const std::exception& e) { g_lastError = e.what(); return false; }
+}
+uint32_t HdMoonshineExtGetEmitterTableSize(const HdMoonshine* h) { return (uint32_t)h->alias.size(); }
+bool HdMoonshineExtGetEmitterTable(HdMoonshine* h, void* entries20) {
+    LOCK(h);
+    try {
+        h->use(); h->syncScene();
+        CK(cudaMemcpyAsync(entries20, h->dAlias.p, h->alias.size() * sizeof(DAlias), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return true;
+    } catch (const std::exception& e) { g_lastError = e.what(); return false; }
+}
+
+}  // extern "C"

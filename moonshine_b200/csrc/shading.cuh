@@ -1,0 +1,377 @@
+// Device restatement of the reference's shading code for the wavefront kernels:
+//   shaders/hrtsystem/reflection_frame.hlsl (Frame), material.hlsl (GGX, Fresnel, Lambert, StandardPBR,
+//   PerfectMirror, Glass, MaterialVariant, getTextureFrame, getEmissive), world.hlsl (MeshAttributes),
+//   light.hlsl (EnvMap, MeshLights without their embedded shadow TraceRay — shadow rays are queued and
+//   traced by the next trace pass, see kernels.cu).
+// Texture sampling restates the reference's samplers in software so that filtering is exact FP32
+// (MaterialManager.zig:425-444 repeat/linear; BackgroundManager.zig:78-95 mirrored-repeat/linear):
+//   u = s*W - 0.5, i0 = floor(u), a = u - i0, texel = lerp(lerp(t00,t10,a), lerp(t01,t11,a), b).
+#pragma once
+#include <cuda_fp16.h>
+#include "device_math.cuh"
+
+namespace msne {
+
+// ---- textures ------------------------------------------------------------------------------------
+DI float4 fetchTexel(const DeviceScene& sc, const DTexture& t, uint32_t x, uint32_t y) {
+    const size_t i = (size_t)y * t.w + x;
+    switch (t.fmt) {
+        case TEX_R32F: return make_float4(__ldg((const float*)t.data + i), 0.f, 0.f, 1.f);
+        case TEX_RG32F: { float2 v = __ldg((const float2*)t.data + i); return make_float4(v.x, v.y, 0.f, 1.f); }
+        case TEX_RGBA32F: return __ldg((const float4*)t.data + i);
+        case TEX_R8_UNORM: return make_float4((float)__ldg((const uint8_t*)t.data + i) / 255.0f, 0.f, 0.f, 1.f);
+        case TEX_RG8_UNORM: { uchar2 v = __ldg((const uchar2*)t.data + i); return make_float4((float)v.x / 255.0f, (float)v.y / 255.0f, 0.f, 1.f); }
+        case TEX_RGBA8_SRGB: {
+            uchar4 v = __ldg((const uchar4*)t.data + i);
+            return make_float4(__ldg(sc.srgbLut + v.x), __ldg(sc.srgbLut + v.y), __ldg(sc.srgbLut + v.z), (float)v.w / 255.0f);
+        }
+        default: {  // TEX_RGBA16F
+            uint2 raw = __ldg((const uint2*)t.data + i);
+            __half2 a = *reinterpret_cast<__half2*>(&raw.x), b = *reinterpret_cast<__half2*>(&raw.y);
+            return make_float4(__low2float(a), __high2float(a), __low2float(b), __high2float(b));
+        }
+    }
+}
+DI int wrapRepeat(int i, int n) { int m = i % n; return m < 0 ? m + n : m; }
+DI int wrapMirror(int i, int n) {
+    int m = i % (2 * n); if (m < 0) m += 2 * n;
+    const int k = m - n;
+    const int mir = k >= 0 ? k : -(1 + k);
+    return (n - 1) - mir;
+}
+DI float4 lerp4(float4 a, float4 b, float t) { return make_float4(a.x + t * (b.x - a.x), a.y + t * (b.y - a.y), a.z + t * (b.z - a.z), a.w + t * (b.w - a.w)); }
+
+// dTextures[idx].SampleLevel(dTextureSampler, uv, 0)
+DI float4 sampleTexture(const DeviceScene& sc, uint32_t idx, float2 uv) {
+    const DTexture t = sc.textures[idx];
+    if (t.w == 1 && t.h == 1) return fetchTexel(sc, t, 0, 0);
+    const float u = uv.x * (float)t.w - 0.5f, v = uv.y * (float)t.h - 0.5f;
+    const float fu = floorf(u), fv = floorf(v);
+    const float a = u - fu, b = v - fv;
+    const int i0 = wrapRepeat((int)fu, t.w), i1 = wrapRepeat((int)fu + 1, t.w), j0 = wrapRepeat((int)fv, t.h), j1 = wrapRepeat((int)fv + 1, t.h);
+    const float4 t00 = fetchTexel(sc, t, i0, j0), t10 = fetchTexel(sc, t, i1, j0), t01 = fetchTexel(sc, t, i0, j1), t11 = fetchTexel(sc, t, i1, j1);
+    return lerp4(lerp4(t00, t10, a), lerp4(t01, t11, a), b);
+}
+
+// ---- reflection_frame.hlsl:3-85 ------------------------------------------------------------------
+struct Frame {
+    float3 n, s, t;
+    DI Frame inSpaceTranspose(const float* toMesh) const {                              // :23-29
+        Frame f;
+        f.n = normalize(mulTranspose3(toMesh, n));
+        f.s = normalize(mulTranspose3(toMesh, s));
+        f.t = normalize(mulTranspose3(toMesh, t));
+        return f;
+    }
+    DI void reorthogonalize() { s = normalize(s - n * dot(n, s)); t = normalize(cross(n, s)); }   // :31-35
+    DI float3 worldToFrame(float3 v) const { return mk3(dot(s, v), dot(t, v), dot(n, v)); }       // :37-40
+    DI float3 frameToWorld(float3 v) const {                                              // :42-45
+        return mk3((s.x * v.x + t.x * v.y) + n.x * v.z, (s.y * v.x + t.y * v.y) + n.y * v.z, (s.z * v.x + t.z * v.y) + n.z * v.z);
+    }
+};
+DI float cosTheta(float3 v) { return v.z; }
+DI float cos2Theta(float3 v) { return v.z * v.z; }
+DI float sin2Theta(float3 v) { return fmaxf(0.0f, 1.0f - cos2Theta(v)); }
+DI float tan2Theta(float3 v) { return sin2Theta(v) / cos2Theta(v); }
+DI bool sameHemisphere(float3 a, float3 b) { return a.z * b.z > 0.0f; }
+
+// ---- material.hlsl -------------------------------------------------------------------------------
+DI float ggxD(float a, float3 m) {                                                        // :31-35
+    const float a2 = a * a, c = cosTheta(m);
+    const float inner = (c * c) * (a2 - 1) + 1;
+    const float denom = MS_PI * (inner * inner);
+    return a2 / denom;
+}
+DI float ggxLambda(float a, float3 v) {                                                   // :37-41
+    const float t2 = tan2Theta(v);
+    if (isinf(t2)) return 0.0f;
+    return (sqrtf(1.0f + (a * a) * t2) - 1.0f) / 2.0f;
+}
+DI float ggxG(float a, float3 w_i, float3 w_o) { return 1.0f / (1.0f + ggxLambda(a, w_i) + ggxLambda(a, w_o)); }   // :44-46
+DI float3 ggxSample(float a, float3 w_o, float2 sq) {                                     // :50-62
+    const float tanThetaSquared = a * a * sq.x / (1 - sq.x);
+    const float cosThetaSquared = 1 / (1 + tanThetaSquared);
+    const float sinT = sqrtf(fmaxf(0.0f, 1 - cosThetaSquared));
+    const float cosT = sqrtf(cosThetaSquared);
+    const float phi = 2 * MS_PI * sq.y;
+    float3 h = sphericalToCartesian(sinT, cosT, phi);
+    if (!sameHemisphere(w_o, h)) h = -h;
+    return h;
+}
+DI float ggxPdf(float a, float3 m) { return ggxD(a, m) * fabsf(cosTheta(m)); }          // :64-66
+
+DI float schlickWeight(float c) { const float x = 1 - c; const float x2 = x * x; return x2 * x2 * x; }   // :76-78
+DI float3 schlick3(float c, float3 R0) { const float w = schlickWeight(c); return lerp3(mk3(w), mk3(1.0f), R0); }   // :84-86
+DI float fresnelDielectric(float cosThetaI, float etaI, float etaT) {                     // :96-122
+    cosThetaI = clampf(cosThetaI, -1, 1);
+    if (!(cosThetaI > 0)) { const float tmp = etaI; etaI = etaT; etaT = tmp; cosThetaI = fabsf(cosThetaI); }
+    const float sinThetaI = sqrtf(fmaxf(0.0f, 1 - cosThetaI * cosThetaI));
+    const float sinThetaT = etaI / etaT * sinThetaI;
+    if (sinThetaT >= 1) return 1;
+    const float cosThetaT = sqrtf(fmaxf(0.0f, 1 - sinThetaT * sinThetaT));
+    const float r_parl = ((etaT * cosThetaI) - (etaI * cosThetaT)) / ((etaT * cosThetaI) + (etaI * cosThetaT));
+    const float r_perp = ((etaI * cosThetaI) - (etaT * cosThetaT)) / ((etaI * cosThetaI) + (etaT * cosThetaT));
+    return (r_parl * r_parl + r_perp * r_perp) / 2;
+}
+
+struct MatSample { float3 dirFs; float pdf; };
+
+// the four variants share one parameter block, loaded ONCE per hit (the reference re-runs ::load and its
+// texture fetches inside each of pdf/eval/sample, material.hlsl:411,432,453 — the fetches are pure)
+struct MaterialParams {
+    uint32_t type;
+    float3 color;     // StandardPBR.color / Lambert.r
+    float metalness;
+    float alpha;      // GGX α = max(roughness², 0.001)
+    float ior;        // StandardPBR.ior / Glass.intIOR
+};
+
+DI float lambertPdf(float3 w_i, float3 w_o) { return sameHemisphere(w_i, w_o) ? fabsf(cosTheta(w_i)) / MS_PI : 0.0f; }   // :157-159
+DI MatSample lambertSample(float3 w_o, float2 sq) {                                       // :165-173
+    float3 w_i = squareToCosineHemisphere(sq);
+    if (w_o.z < 0.0f) w_i.z *= -1;
+    MatSample s; s.dirFs = w_i; s.pdf = lambertPdf(w_i, w_o);
+    return s;
+}
+DI float microfacetPdf(const MaterialParams& m, float3 w_i, float3 w_o) {                // :201-205
+    if (!sameHemisphere(w_o, w_i)) return 0.0f;
+    const float3 h = normalize(w_i + w_o);
+    return ggxPdf(m.alpha, h) / (4.0f * dot(w_o, h));
+}
+DI float pbrPdf(const MaterialParams& m, float3 w_i, float3 w_o) {                        // :240-249
+    const float pSpec = 1.0f / (1.0f + (1 - m.metalness));
+    return lerp1(lambertPdf(w_i, w_o), microfacetPdf(m, w_i, w_o), pSpec);
+}
+DI float3 pbrEval(const MaterialParams& m, float3 w_i, float3 w_o) {                      // :251-266
+    const float3 h = normalize(w_i + w_o);
+    const float fD = fresnelDielectric(dot(w_i, h), MS_AIR_IOR, m.ior);
+    const float3 fMetallic = schlick3(dot(w_i, h), m.color);
+    const float3 F = lerp3(mk3(fD), fMetallic, m.metalness);
+    const float G = ggxG(m.alpha, w_i, w_o);
+    const float D = ggxD(m.alpha, h);
+    const float3 specular = sameHemisphere(w_o, w_i) ? (F * G * D) / (4.0f * fabsf(cosTheta(w_i)) * fabsf(cosTheta(w_o))) : mk3(0.0f);
+    const float3 diffuse = m.color / MS_PI;
+    return specular + (1.0f - m.metalness) * diffuse;
+}
+DI MatSample pbrSample(const MaterialParams& m, float3 w_o, float2 sq) {                  // :217-238 (+ :207-215)
+    const float pSpec = 1.0f / (1.0f + (1 - m.metalness));
+    MatSample s;
+    if (coinFlipRemap(pSpec, sq.x)) {
+        const float3 h = ggxSample(m.alpha, w_o, sq);
+        const float3 refl = w_o - (2.0f * h) * dot(w_o, h);   // reflect(w_o, h)
+        const float3 w_i = -refl;
+        const float microPdf = sameHemisphere(w_o, w_i) ? ggxPdf(m.alpha, h) / (4.0f * dot(w_o, h)) : 0.0f;
+        const float pdf2 = lambertPdf(w_i, w_o);
+        s.pdf = lerp1(pdf2, microPdf, pSpec);
+        s.dirFs = w_i;
+    } else {
+        const MatSample ds = lambertSample(w_o, sq);
+        const float pdf2 = microfacetPdf(m, ds.dirFs, w_o);
+        s.pdf = lerp1(ds.pdf, pdf2, pSpec);
+        s.dirFs = ds.dirFs;
+    }
+    return s;
+}
+DI float3 refractDir(float3 wi, float3 n, float eta) {                                    // :334-343
+    const float cosThetaI = dot(n, wi);
+    const float sin2ThetaI = fmaxf(0.0f, 1 - cosThetaI * cosThetaI);
+    const float sin2ThetaT = eta * eta * sin2ThetaI;
+    if (sin2ThetaT >= 1) return mk3(0.0f);
+    const float cosThetaT = sqrtf(1 - sin2ThetaT);
+    return eta * -wi + (eta * cosThetaI - cosThetaT) * n;
+}
+DI MatSample glassSample(float ior, float3 w_o, float2 sq) {                              // :359-381
+    const float fresnel = fresnelDielectric(cosTheta(w_o), MS_AIR_IOR, ior);
+    MatSample s;
+    if (sq.x < fresnel) {
+        s.pdf = fresnel;
+        s.dirFs = mk3(-w_o.x, -w_o.y, w_o.z);
+    } else {
+        float etaI, etaT;
+        if (cosTheta(w_o) > 0) { etaI = MS_AIR_IOR; etaT = ior; } else { etaT = MS_AIR_IOR; etaI = ior; }
+        s.dirFs = refractDir(w_o, faceForward(mk3(0.0f, 0.0f, 1.0f), w_o), etaI / etaT);
+        s.pdf = allZero(s.dirFs) ? 0.0f : 1.0f - fresnel;
+    }
+    return s;
+}
+DI float3 glassEval(float ior, float3 w_i, float3 w_o) {                                  // :387-394
+    const float fresnel = fresnelDielectric(cosTheta(w_o), MS_AIR_IOR, ior);
+    if (sameHemisphere(w_i, w_o)) return mk3(fresnel / fabsf(cosTheta(w_i)));
+    return mk3((1.0f - fresnel) / fabsf(cosTheta(w_i)));
+}
+
+// MaterialVariant (material.hlsl:395-487)
+DI bool matIsDelta(uint32_t type) { return type == MAT_PERFECT_MIRROR || type == MAT_GLASS; }
+DI float matPdf(const MaterialParams& m, float3 w_i, float3 w_o) {
+    if (m.type == MAT_STANDARD_PBR) return pbrPdf(m, w_i, w_o);
+    if (m.type == MAT_LAMBERT) return lambertPdf(w_i, w_o);
+    return 0.0f;
+}
+DI float3 matEval(const MaterialParams& m, float3 w_i, float3 w_o) {
+    if (m.type == MAT_STANDARD_PBR) return pbrEval(m, w_i, w_o);
+    if (m.type == MAT_LAMBERT) return m.color / MS_PI;
+    if (m.type == MAT_PERFECT_MIRROR) return mk3(1.0f / fabsf(cosTheta(w_i)));
+    return glassEval(m.ior, w_i, w_o);
+}
+DI MatSample matSample(const MaterialParams& m, float3 w_o, float2 sq) {
+    if (m.type == MAT_STANDARD_PBR) return pbrSample(m, w_o, sq);
+    if (m.type == MAT_LAMBERT) return lambertSample(w_o, sq);
+    if (m.type == MAT_PERFECT_MIRROR) { MatSample s; s.pdf = 1.0f; s.dirFs = mk3(-w_o.x, -w_o.y, w_o.z); return s; }
+    return glassSample(m.ior, w_o, sq);
+}
+DI MaterialParams loadMaterial(const DeviceScene& sc, const DMaterial& dm, float2 uv) {
+    MaterialParams m;
+    m.type = dm.type; m.color = mk3(0.0f); m.metalness = 0.0f; m.alpha = 0.001f; m.ior = dm.ior;
+    if (dm.type == MAT_STANDARD_PBR) {                                                    // :192-199
+        m.color = xyz(sampleTexture(sc, dm.color, uv));
+        m.metalness = sampleTexture(sc, dm.metalness, uv).x;
+        const float roughness = sampleTexture(sc, dm.roughness, uv).x;
+        m.alpha = fmaxf(roughness * roughness, 0.001f);
+    } else if (dm.type == MAT_LAMBERT) {                                                  // :149-155
+        m.color = xyz(sampleTexture(sc, dm.color, uv));
+    }
+    return m;
+}
+DI float3 decodeNormal(float2 rg) {                                                       // :489-492
+    rg = 2.0f * rg - mk2(1.0f, 1.0f);
+    return mk3(rg.x, rg.y, sqrtf(1.0f - clampf(dot(rg, rg), 0.0f, 1.0f)));
+}
+DI Frame getTextureFrame(const DeviceScene& sc, const DConstants& k, const DMaterial& dm, float2 uv, const Frame& tangentFrame) {   // :506-517
+    const float4 s = sampleTexture(sc, dm.normal, uv);
+    const float3 nTs = k.two_component_normal ? decodeNormal(mk2(s.x, s.y)) : mk3(s.x, s.y, s.z);
+    Frame f = tangentFrame;
+    f.n = normalize(tangentFrame.frameToWorld(nTs));
+    f.reorthogonalize();
+    return f;
+}
+
+// ---- world.hlsl:86-176 -----------------------------------------------------------------------------
+struct MeshAttributes { float3 position; float2 texcoord; Frame triangleFrame, frame; };
+
+DI float3 ld3(const float* p, uint32_t i) { return mk3(__ldg(p + 3 * (size_t)i), __ldg(p + 3 * (size_t)i + 1), __ldg(p + 3 * (size_t)i + 2)); }
+DI float2 ld2(const float* p, uint32_t i) { return mk2(__ldg(p + 2 * (size_t)i), __ldg(p + 2 * (size_t)i + 1)); }
+DI float3 interp3(float3 b, float3 v1, float3 v2, float3 v3) { return (b.x * v1 + b.y * v2) + b.z * v3; }
+DI float2 interp2(float3 b, float2 v1, float2 v2, float2 v3) { return (b.x * v1 + b.y * v2) + b.z * v3; }
+
+DI void getTangentBitangent(float3 p0, float3 p1, float3 p2, float2 t0, float2 t1, float2 t2, float3& tangent, float3& bitangent) {   // :86-100
+    const float2 dT02 = t0 - t2, dT12 = t1 - t2;
+    const float3 dP02 = p0 - p2, dP12 = p1 - p2;
+    const float det = dT02.x * dT12.y - dT02.y * dT12.x;
+    if (det == 0.0f) {
+        coordinateSystem(normalize(cross(p2 - p0, p1 - p0)), tangent, bitangent);
+    } else {
+        tangent = normalize((dT12.y * dP02 - dT02.y * dP12) / det);
+        bitangent = normalize((-dT12.x * dP02 + dT02.x * dP12) / det);
+    }
+}
+
+// MeshAttributes::lookupAndInterpolate(...).inWorld(...)  (world.hlsl:114-176)
+DI MeshAttributes lookupAttributes(const DeviceScene& sc, const DConstants& k, uint32_t instanceIndex, uint32_t meshIdx, uint32_t primitiveIndex, float2 attribs) {
+    const DMesh mesh = sc.meshes[meshIdx];
+    const float3 bary = mk3(1.0f - attribs.x - attribs.y, attribs.x, attribs.y);
+    MeshAttributes a;
+    const uint32_t ix = __ldg(mesh.idx + 3 * (size_t)primitiveIndex), iy = __ldg(mesh.idx + 3 * (size_t)primitiveIndex + 1), iz = __ldg(mesh.idx + 3 * (size_t)primitiveIndex + 2);
+    const float3 p0 = ld3(mesh.pos, ix), p1 = ld3(mesh.pos, iy), p2 = ld3(mesh.pos, iz);
+    a.position = interp3(bary, p0, p1, p2);
+    // :130 — `cond ? uint3 : float3` promotes both arms to float3 before converting back to uint3
+    uint32_t ax, ay, az;
+    if (k.indexed_attributes) { ax = (uint32_t)(float)ix; ay = (uint32_t)(float)iy; az = (uint32_t)(float)iz; }
+    else { ax = (uint32_t)(float)(primitiveIndex * 3 + 0); ay = (uint32_t)(float)(primitiveIndex * 3 + 1); az = (uint32_t)(float)(primitiveIndex * 3 + 2); }
+    float2 t0, t1, t2;
+    if (mesh.uv != nullptr) { t0 = ld2(mesh.uv, ax); t1 = ld2(mesh.uv, ay); t2 = ld2(mesh.uv, az); }
+    else { t0 = mk2(0, 0); t1 = mk2(1, 0); t2 = mk2(1, 1); }
+    a.texcoord = interp2(bary, t0, t1, t2);
+    getTangentBitangent(p0, p1, p2, t0, t1, t2, a.triangleFrame.s, a.triangleFrame.t);
+    a.triangleFrame.n = normalize(cross(p0 - p2, p1 - p2));
+    a.triangleFrame.reorthogonalize();
+    a.frame = a.triangleFrame;
+    if (mesh.nrm != nullptr) {
+        const float3 n0 = ld3(mesh.nrm, ax), n1 = ld3(mesh.nrm, ay), n2 = ld3(mesh.nrm, az);
+        a.frame.n = normalize(interp3(bary, n0, n1, n2));
+        a.frame.reorthogonalize();
+    }
+    // inWorld
+    const DInstance* in = sc.instances + instanceIndex;
+    float m[12];
+#pragma unroll
+    for (int i = 0; i < 3; i++) { const float4 r = __ldg(reinterpret_cast<const float4*>(in->o2w) + i); m[4 * i] = r.x; m[4 * i + 1] = r.y; m[4 * i + 2] = r.z; m[4 * i + 3] = r.w; }
+    a.position = mulPoint(m, a.position);
+#pragma unroll
+    for (int i = 0; i < 3; i++) { const float4 r = __ldg(reinterpret_cast<const float4*>(in->w2o) + i); m[4 * i] = r.x; m[4 * i + 1] = r.y; m[4 * i + 2] = r.z; m[4 * i + 3] = r.w; }
+    a.triangleFrame = a.triangleFrame.inSpaceTranspose(m);
+    a.frame = a.frame.inSpaceTranspose(m);
+    return a;
+}
+
+// ---- light.hlsl ------------------------------------------------------------------------------------
+DI float areaMeasureToSolidAngleMeasure(float3 pos1, float3 pos2, float3 dir1, float3 dir2) {    // :105-110
+    const float3 dlt = pos1 - pos2;
+    const float r2 = dot(dlt, dlt);
+    const float lightCos = dot(-dir1, dir2);
+    return lightCos > 0.0f ? r2 / lightCos : 0.0f;
+}
+DI float powerHeuristic(uint32_t numf, float fPdf, uint32_t numg, float gPdf) {                  // integrator.hlsl:10-16
+    const float f = numf * fPdf, g = numg * gPdf;
+    const float f2 = f * f;
+    return f2 / (f2 + g * g);
+}
+
+// luminanceTexture.Load(uint3(x,y,level)) with out-of-bounds -> 0 (SURVEY §8 a17 hazard)
+DI float envLumLoad(const DeviceScene& sc, uint32_t x, uint32_t y, uint32_t level) {
+    const uint32_t sz = sc.envSize >> level;
+    if (x >= sz || y >= sz) return 0.0f;
+    return __ldg(sc.envLum + sc.envLevelOffset[level] + (size_t)y * sz + x);
+}
+DI float3 envRgbLoad(const DeviceScene& sc, uint32_t x, uint32_t y) {
+    if (x >= sc.envSize || y >= sc.envSize) return mk3(0.0f);
+    return xyz(__ldg(reinterpret_cast<const float4*>(sc.envRgb) + (size_t)y * sc.envSize + x));
+}
+struct LightSample { float3 dirWs, radiance; float pdf; };
+// EnvMap::sample without the shadow ray (light.hlsl:47-73)
+DI LightSample envSample(const DeviceScene& sc, float2 rand) {
+    const uint32_t size = sc.envSize, mipCount = sc.envLevels;
+    uint32_t ix = 0, iy = 0;
+    for (uint32_t level = mipCount; level-- > 0;) {
+        ix *= 2; iy *= 2;
+        const float px0 = envLumLoad(sc, ix + 0, iy + 0, level) + envLumLoad(sc, ix + 0, iy + 1, level);
+        const float px1 = envLumLoad(sc, ix + 1, iy + 0, level) + envLumLoad(sc, ix + 1, iy + 1, level);
+        ix += coinFlipRemap(px1 / (px0 + px1), rand.x) ? 1u : 0u;
+        const float py0 = envLumLoad(sc, ix, iy + 0, level);
+        const float py1 = envLumLoad(sc, ix, iy + 1, level);
+        iy += coinFlipRemap(py1 / (py0 + py1), rand.y) ? 1u : 0u;
+    }
+    const float integral = envLumLoad(sc, 0, 0, mipCount - 1);
+    const float discretePdf = envLumLoad(sc, ix, iy, 0) * float(size * size) / integral;
+    const float2 uv = (mk2((float)ix, (float)iy) + rand) / mk2((float)size, (float)size);
+    LightSample ls;
+    ls.pdf = discretePdf / (4.0f * MS_PI);
+    ls.dirWs = squareToEqualAreaSphere(uv);
+    ls.radiance = envRgbLoad(sc, ix, iy);
+    return ls;
+}
+// EnvMap::eval (light.hlsl:83-97)
+DI void envEval(const DeviceScene& sc, float3 dirWs, float3& radiance, float& pdf) {
+    const uint32_t size = sc.envSize, mipCount = sc.envLevels;
+    const float2 uv = squareToEqualAreaSphereInverse(dirWs);
+    const float integral = envLumLoad(sc, 0, 0, mipCount - 1);
+    const uint32_t ix = min(floatToUint(uv.x * (float)size), size), iy = min(floatToUint(uv.y * (float)size), size);   // upper clamp is `size` (sic)
+    const float discretePdf = envLumLoad(sc, ix, iy, 0) * float(size * size) / integral;
+    pdf = discretePdf / (4.0f * MS_PI);
+    radiance = envRgbLoad(sc, ix, iy);
+}
+// EnvMap::incomingRadiance (light.hlsl:99-102): bilinear, mirrored repeat
+DI float3 envIncomingRadiance(const DeviceScene& sc, float3 dirWs) {
+    const float2 uv = squareToEqualAreaSphereInverse(dirWs);
+    const int n = (int)sc.envSize;
+    const float4* rgb = reinterpret_cast<const float4*>(sc.envRgb);
+    if (n == 1) return xyz(__ldg(rgb));
+    const float u = uv.x * (float)n - 0.5f, v = uv.y * (float)n - 0.5f;
+    const float fu = floorf(u), fv = floorf(v);
+    const float a = u - fu, b = v - fv;
+    const int i0 = wrapMirror((int)fu, n), i1 = wrapMirror((int)fu + 1, n), j0 = wrapMirror((int)fv, n), j1 = wrapMirror((int)fv + 1, n);
+    const float4 r = lerp4(lerp4(__ldg(rgb + (size_t)j0 * n + i0), __ldg(rgb + (size_t)j0 * n + i1), a),
+                           lerp4(__ldg(rgb + (size_t)j1 * n + i0), __ldg(rgb + (size_t)j1 * n + i1), a), b);
+    return xyz(r);
+}
+
+}  // namespace msne

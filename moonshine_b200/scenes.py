@@ -132,11 +132,11 @@ class Scene:
 
 def load_scene(backend, scene: Scene):
     """Replay `scene` into a backend; returns (texture, material, mesh, instance) handle lists."""
+    backend.set_constants(scene.constants)  # first: indexed_attributes decides how mesh attributes are read
     tex = [backend.create_texture(t.data, t.width, t.height, t.fmt) for t in scene.textures]
     mats = [backend.create_material(m.type, tex[m.normal], tex[m.emissive], tex[m.color], tex[m.metalness], tex[m.roughness], m.ior)
             for m in scene.materials]
     meshes = [backend.create_mesh(m.positions, m.normals, m.texcoords, m.indices) for m in scene.meshes]
-    backend.set_constants(scene.constants)
     insts = [backend.create_instance(i.transform, [(meshes[g[0]], mats[g[1]], g[2]) for g in i.geometries], i.visible)
              for i in scene.instances]
     if scene.background is not None:
@@ -289,6 +289,104 @@ def cornell_box(extent=(512, 512)) -> Scene:
     s.add_instance([(m_white, white, False), (m_left, red, False), (m_right, green, False), (m_boxes, white, False)])
     s.add_instance([(m_light, light, True)])
     s.background = np.array([[[0, 0, 0, 1]]], np.float32)
-    s.lens = Lens((-1.95, 0.5, 0.5), (1, 0, 0), (0, 0, 1), math.radians(39.3), 0.0, 1.0)
+    s.lens = Lens((-1.4, 0.5, 0.5), (1, 0, 0), (0, 0, 1), math.radians(39.3), 0.0, 1.0)
+    s.constants = Constants()
+    return s
+
+
+def uv_sphere(nu: int, nv: int, radius=1.0, center=(0, 0, 0)):
+    """Lat-long sphere with per-vertex normals and texcoords (indexed attributes)."""
+    u = np.linspace(0.0, 1.0, nu + 1, dtype=np.float32)
+    v = np.linspace(0.0, 1.0, nv + 1, dtype=np.float32)
+    uu, vv = np.meshgrid(u, v)
+    phi, theta = uu * np.float32(2 * math.pi), vv * np.float32(math.pi)
+    n = np.stack([np.sin(theta) * np.cos(phi), np.sin(theta) * np.sin(phi), np.cos(theta)], -1).reshape(-1, 3).astype(np.float32)
+    p = (n * np.float32(radius) + np.array(center, np.float32)).astype(np.float32)
+    t = np.stack([uu, vv], -1).reshape(-1, 2).astype(np.float32)
+    idx = []
+    for j in range(nv):
+        for i in range(nu):
+            a, b = j * (nu + 1) + i, j * (nu + 1) + i + 1
+            c, d = (j + 1) * (nu + 1) + i, (j + 1) * (nu + 1) + i + 1
+            if j != 0:
+                idx.append((a, c, b))
+            if j != nv - 1:
+                idx.append((b, c, d))
+    return p, np.array(idx, np.uint32), n, t
+
+
+def procedural_sky(width: int, height: int, sun_dir=(0.3, 0.4, 0.8), sun_power=200.0, seed=0x4D4F4F4E) -> np.ndarray:
+    """Equirectangular RGBA32F sky: gradient + sun lobe; row = theta in [0,pi] from +Z, column = phi."""
+    phi = (np.arange(width, dtype=np.float64) + 0.5) / width * 2 * math.pi
+    theta = (np.arange(height, dtype=np.float64) + 0.5) / height * math.pi
+    pp, tt = np.meshgrid(phi, theta)
+    d = np.stack([np.sin(tt) * np.cos(pp), np.sin(tt) * np.sin(pp), np.cos(tt)], -1)
+    s = np.array(sun_dir, np.float64)
+    s /= np.linalg.norm(s)
+    cosang = np.clip((d * s).sum(-1), -1, 1)
+    up = np.clip(d[..., 2], 0, 1)
+    sky = np.stack([0.25 + 0.35 * (1 - up), 0.35 + 0.35 * (1 - up), 0.6 + 0.3 * up], -1)
+    ground = np.array([0.08, 0.07, 0.06])
+    col = np.where(d[..., 2:3] >= 0, sky, ground)
+    col = col + sun_power * np.exp((cosang[..., None] - 1.0) * 400.0) * np.array([1.0, 0.9, 0.75])
+    out = np.ones((height, width, 4), np.float32)
+    out[..., :3] = col.astype(np.float32)
+    return out
+
+
+def _checker_srgb(n: int, a=(200, 60, 50), b=(230, 230, 220), cells=8) -> np.ndarray:
+    y, x = np.mgrid[0:n, 0:n]
+    m = (((x * cells) // n + (y * cells) // n) % 2).astype(bool)
+    img = np.zeros((n, n, 4), np.uint8)
+    img[m] = (*a, 255)
+    img[~m] = (*b, 255)
+    return img
+
+
+def material_zoo(extent=(96, 64)) -> Scene:
+    """Parity scene touching every branch of the hot path: StandardPBR with textures of every format, Lambert,
+    Glass, PerfectMirror, a sampled emitter, an env map, vertex normals + texcoords, a transformed instance
+    sharing a BLAS with an untransformed one, and a thin-lens aperture."""
+    s = Scene("material-zoo", extent=extent)
+    rs = np.random.RandomState(0x4D4F4F4E & 0x7FFFFFFF)
+    n_flat, black = s.solid2(0.5, 0.5), s.solid3(0, 0, 0)
+    # textures
+    checker = s.raw_texture(_checker_srgb(64), TEX_RGBA8_SRGB)
+    rough = s.raw_texture((np.clip(rs.rand(32, 32) * 0.6 + 0.2, 0, 1) * 255).astype(np.uint8), TEX_R8_UNORM)
+    metal = s.raw_texture(((np.indices((16, 16)).sum(0) % 2) * 255).astype(np.uint8), TEX_R8_UNORM)
+    nm = np.zeros((32, 32, 2), np.uint8)
+    yy, xx = np.mgrid[0:32, 0:32]
+    nm[..., 0] = (127.5 + 40 * np.sin(xx * 0.8)).astype(np.uint8)
+    nm[..., 1] = (127.5 + 40 * np.cos(yy * 0.6)).astype(np.uint8)
+    normal_map = s.raw_texture(nm, TEX_RG8_UNORM)
+    half = s.raw_texture(np.stack([rs.rand(8, 8), rs.rand(8, 8), rs.rand(8, 8), np.ones((8, 8))], -1).astype(np.float16), TEX_RGBA16F)
+    # materials
+    floor_m = s.add_material(type=MAT_STANDARD_PBR, normal=normal_map, emissive=black, color=checker, metalness=metal, roughness=rough, ior=1.5)
+    pbr_m = s.add_material(type=MAT_STANDARD_PBR, normal=n_flat, emissive=black, color=half, metalness=s.solid1(0.3), roughness=s.solid1(0.35), ior=1.45)
+    lambert_m = s.add_material(type=MAT_LAMBERT, normal=n_flat, emissive=black, color=s.solid3(0.2, 0.5, 0.8))
+    glass_m = s.add_material(type=MAT_GLASS, normal=n_flat, emissive=black, ior=1.5)
+    mirror_m = s.add_material(type=MAT_PERFECT_MIRROR, normal=n_flat, emissive=black)
+    light_m = s.add_material(type=MAT_LAMBERT, normal=n_flat, emissive=s.solid3(12, 10, 8), color=s.solid3(0.5, 0.5, 0.5))
+    # meshes
+    fp = np.array([(-4, -4, 0), (4, -4, 0), (4, 4, 0), (-4, 4, 0)], np.float32)
+    floor = s.add_mesh(fp, [(0, 1, 2), (0, 2, 3)], normals=np.tile([[0, 0, 1]], (4, 1)), texcoords=[(0, 0), (3, 0), (3, 3), (0, 3)])
+    sp, si, sn, st = uv_sphere(24, 12, 0.5)
+    sphere = s.add_mesh(sp, si, normals=sn, texcoords=st)
+    ip, ii = icosphere(2)
+    ico = s.add_mesh(ip * np.float32(0.45), ii)
+    bx = s.add_mesh(*_box((-0.4, -0.4, 0.0), (0.4, 0.4, 0.9), rot_z=0.5))
+    lq = _quad((-0.6, -0.6, 2.6), (0.6, -0.6, 2.6), (0.6, 0.6, 2.6), (-0.6, 0.6, 2.6))
+    lightq = s.add_mesh(lq[0], lq[1][:, ::-1].copy())
+    # instances
+    s.add_instance([(floor, floor_m, False)])
+    s.add_instance([(sphere, pbr_m, False)], transform=[[1, 0, 0, -1.2], [0, 1, 0, 0.2], [0, 0, 1, 0.5]])
+    c, sn_ = math.cos(0.7), math.sin(0.7)
+    s.add_instance([(sphere, lambert_m, False)], transform=[[1.4 * c, -0.8 * sn_, 0, 1.3], [1.4 * sn_, 0.8 * c, 0, -0.9], [0, 0, 1.1, 0.55]])
+    s.add_instance([(ico, glass_m, False)], transform=[[1, 0, 0, 0.1], [0, 1, 0, -0.3], [0, 0, 1, 0.46]])
+    s.add_instance([(bx, mirror_m, False)], transform=[[1, 0, 0, 0.2], [0, 1, 0, 1.6], [0, 0, 1, 0.0]])
+    s.add_instance([(lightq, light_m, True)])
+    s.add_instance([(ico, light_m, True)], transform=[[0.3, 0, 0, -0.4], [0, 0.3, 0, -1.5], [0, 0, 0.3, 0.2]])
+    s.background = procedural_sky(32, 16, sun_power=60.0)
+    s.lens = Lens((-4.2, -1.0, 1.6), tuple(np.array([0.95, 0.2, -0.25]) / np.linalg.norm([0.95, 0.2, -0.25])), (0, 0, 1), math.radians(42), 0.05, 4.0)
     s.constants = Constants()
     return s
