@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s of the B200 wavefront path tracer on BASELINE.json's metric config.
+
+Workload (config.workload): cfg3, the procedural "Salle-de-bain-class" bathroom (moonshine_b200/scenes.py
+`bathroom`, ~1.4 M triangles, 34 materials, sun+sky env map) at 1920x1080, offline constants
+(offline/main.zig:106-111). One STEP = one wave batch of `batch_spp` samples per pixel over every pixel this
+rank owns (default 8 spp; the default 128 timed steps are the full 1024 spp of the metric config). With N
+GPUs the image is sharded into 32x32 tiles round-robin over ranks and each step renders batch_spp*N samples
+of the rank's tiles (weak scaling: per-GPU work fixed), followed by ONE NCCL reduce of the RGBA32F radiance
+buffer to rank 0 inside the timed region.
+
+  value    Mrays/s = (closest-hit + shadow rays traced by all ranks) / max-over-ranks device time (CUDA events
+           on the library's stream around each step, first k_generate .. last k_accumulate).
+  e2e      same metric through the reference-facing call HdMoonshineRender (hydra/moonshine.h:74): per step
+           one launch of samples_per_run = batch_spp samples + the D2H copy of the sensor into the host buffer,
+           wall-clock, host<->device copies inside the timed region.
+  roofline dominant kernel k_trace: algorithmic bytes (48 B per traced ray) / CUDA-event duration.
+  cpu_baseline / --impl reference: the CPU oracle (line-by-line restatement of the reference shaders; the
+           reference itself has no CPU path and cannot be built here) on the host cores, bounded pixel sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "Mrays/sec at 1920x1080x1024spp"
+UNIT = "Mrays/s"
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+def make_scene(args):
+    from moonshine_b200 import scenes
+    if args.workload == "cfg3":
+        return scenes.bathroom((args.width, args.height), detail=args.detail)
+    if args.workload == "cfg2":
+        return scenes.cornell_box((512, 512))
+    raise SystemExit(f"unknown workload {args.workload}")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    p = os.path.join(ROOT, "profiles", "trace_kernel_traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p))
+        except Exception:
+            return None
+    return None
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU legs (oracle) — the only place bench.py touches oracle/
+# ------------------------------------------------------------------------------------------------------
+def cpu_oracle_run(scene, steps, warmup, target_seconds):
+    """Times the oracle on all host cores; each step = 1 spp over a stride-subsampled pixel set."""
+    from moonshine_b200 import scenes
+    from oracle.binding import Oracle
+    o = Oracle()
+    scenes.load_scene(o, scene)
+    W, H = scene.extent
+    cores = os.cpu_count() or 1
+    # probe throughput on ~2000 pixels (also builds the oracle's BVH outside the timed part)
+    probe_stride = max(1, (W * H) // 2000)
+    o.render(scene.lens, W, H, n_launches=1, pixel_stride=max(1, (W * H) // 64))
+    t = time.perf_counter()
+    _, c = o.render(scene.lens, W, H, n_launches=1, pixel_stride=probe_stride)
+    dt = max(time.perf_counter() - t, 1e-6)
+    rays_per_pixel = float(c.sum()) / max(1, (W * H) // probe_stride)
+    speed = float(c.sum()) / dt
+    per_step = target_seconds / max(1, steps + warmup)
+    n_pix = max(64, min(W * H, int(speed * per_step / max(rays_per_pixel, 1.0))))
+    stride = max(1, (W * H) // n_pix)
+    for i in range(warmup):
+        o.render(scene.lens, W, H, n_launches=1, sample_count=i, pixel_stride=stride)
+    rays = 0
+    t0 = time.perf_counter()
+    for i in range(steps):
+        _, c = o.render(scene.lens, W, H, n_launches=1, sample_count=warmup + i, pixel_stride=stride)
+        rays += int(c.sum())
+    dt = time.perf_counter() - t0
+    return {"value": rays / dt / 1e6, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{steps} steps x 1 spp over every {stride}th pixel of {W}x{H} ({(W * H) // stride} pixels/step), {dt:.1f} s, oracle/liboracle.so on {cores} threads",
+            "ms_per_step": dt / steps * 1e3}
+
+
+def run_reference(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    scene = make_scene(args)
+    steps = min(args.steps, 64)
+    r = cpu_oracle_run(scene, steps, min(args.warmup, 3), target_seconds=120.0)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3),
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args, scene, 1),
+            "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference has no CPU path and cannot be built here (Zig/DXC/Vulkan-RT absent): this is the CPU oracle, a line-by-line restatement of its shaders"}
+    print(json.dumps(line))
+    return 0
+
+
+def config_dict(args, scene, world):
+    return {"workload": f"{args.workload}: {scene.name}, {scene.triangle_count()} triangles, {len(scene.materials)} materials, "
+                        f"{scene.extent[0]}x{scene.extent[1]}, offline constants (max_bounces 1024, env 1, mesh 1)",
+            "step": f"{args.batch_spp * world} spp over the rank's tiles ({args.batch_spp} spp x {world} GPUs, weak scaling)",
+            "target_spp": 1024, "batch_spp": args.batch_spp, "parallelism": f"tile-dp{world}",
+            "l2": "per-step working set (path queues, >4 GB) exceeds the 126 MB L2; no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=128)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3")
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--detail", type=float, default=1.0)
+    ap.add_argument("--batch-spp", type=int, default=8)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps (capped at 32)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (libmoonshine has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from moonshine_b200 import hydra, scenes
+    scene = make_scene(args)
+    W, H = scene.extent
+    m = hydra.HdMoonshine(local_rank)
+    scenes.load_scene(m, scene)
+    m.SetTileShard(rank, world)
+    sensor, lens = m.CreateSensor(W, H), m.CreateLens(scene.lens)
+    m.SetProfiling(True)
+    batch = args.batch_spp * world
+
+    class _Dev:  # zero-copy view of the library-owned radiance buffer for torch.distributed
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+    radiance = torch.as_tensor(_Dev(m.SensorDevicePtr(sensor), W * H * 4), device=f"cuda:{local_rank}")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        m.RenderLaunches(sensor, lens, batch)
+    if world > 1:
+        warm = radiance.clone()
+        dist.reduce(warm, dst=0)
+
+    # ---- timed region: K steps, inputs resident in HBM ------------------------------------------------
+    barrier()
+    m.ResetStats()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        m.RenderLaunches(sensor, lens, batch)
+    reduce_ms = 0.0
+    if world > 1:
+        ev0.record()
+        dist.reduce(radiance, dst=0)
+        ev1.record()
+        torch.cuda.synchronize()
+        reduce_ms = ev0.elapsed_time(ev1)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    clk = clocks.stop()
+    st = m.GetStats()
+    dev_ms = st.device_ms + reduce_ms
+
+    def allreduce(v, op):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    rays_local = float(st.rays_closest + st.rays_shadow)
+    rays_total = allreduce(rays_local, dist.ReduceOp.SUM if world > 1 else None)
+    dev_ms_max = allreduce(dev_ms, dist.ReduceOp.MAX if world > 1 else None)
+    wall_ms_max = allreduce(wall_ms, dist.ReduceOp.MAX if world > 1 else None)
+    value = rays_total / (dev_ms_max / 1e3) / 1e6
+
+    # ---- roofline of the dominant kernel (k_trace), from CUDA events recorded on the library's stream ----
+    peak, peak_src = hbm_peak()
+    trace_bytes = 48.0 * rays_local  # 32 B ray read + 16 B hit write / conditional NEE clear
+    trace_s = st.trace_ms / 1e3 if st.trace_ms > 0 else float("nan")
+    achieved = trace_bytes / trace_s / 1e9
+    traffic = ncu_traffic()
+    step_bytes = 224.0 * st.rays_closest + 112.0 * st.rays_shadow + 32.0 * st.samples
+    roofline = {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
+                "peak_source": peak_src, "launches": int(st.trace_launches), "avg_launch_ms": st.trace_ms / max(1, st.trace_launches),
+                "kernel_share_of_step": st.trace_ms / max(st.device_ms, 1e-9),
+                "algorithmic_bytes_per_launch": trace_bytes / max(1, st.trace_launches),
+                "note": "software BVH traversal is L2-latency bound, not streaming bound: see DESIGN.md and profiles/"}
+    roofline_step = {"bytes_formula": "224*N_ext + 112*N_shadow + 32*N_samples (SURVEY.md 8d)", "achieved": step_bytes / (st.device_ms / 1e3) / 1e9,
+                     "peak": peak, "unit": "GB/s", "frac": step_bytes / (st.device_ms / 1e3) / 1e9 / peak}
+    timed_launches = int(st.kernel_launches)
+    max_bounce = int(st.max_bounce_reached)
+
+    # ---- e2e: the reference-facing call, host buffers, copies inside the timed region ------------------
+    e2e_steps = args.e2e_steps or min(args.steps, 32)
+    c = scenes.Constants(samples_per_run=batch)
+    m.SetSpecConstants(c)  # = pipeline re-creation in the reference; clears the sensor
+    host = m.GetSensorData(sensor)
+    m.Render(sensor, lens)
+    barrier()
+    m.ResetStats()
+    t0 = time.perf_counter()
+    checksum = 0.0
+    for _ in range(e2e_steps):
+        if not m.Render(sensor, lens):
+            raise SystemExit("HdMoonshineRender failed: " + m.last_error())
+        checksum += float(host[H // 2, W // 2, 0])  # the host buffer is really read
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    st2 = m.GetStats()
+    e2e_rays = allreduce(float(st2.rays_closest + st2.rays_shadow), dist.ReduceOp.SUM if world > 1 else None)
+    e2e_wall = allreduce(e2e_wall, dist.ReduceOp.MAX if world > 1 else None)
+    e2e = {"value": e2e_rays / e2e_wall / 1e6, "unit": UNIT, "h2d_bytes_per_step": 52, "d2h_bytes_per_step": W * H * 16,
+           "steps": e2e_steps, "ms_per_step": e2e_wall / e2e_steps * 1e3,
+           "call": "HdMoonshineRender(sensor, lens) with samples_per_run = batch spp; sensor copied to the pinned host buffer every call"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_oracle_run(scene, 4, 1, target_seconds=20.0)
+        cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                "ms_per_step": dev_ms_max / args.steps, "wall_ms_per_step": wall_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args, scene, world),
+                "clocks": clk, "e2e": e2e, "gpu_launches": timed_launches, "roofline": roofline, "roofline_step": roofline_step,
+                "cpu_baseline": cpu, "rays": {"closest": int(st.rays_closest), "shadow": int(st.rays_shadow), "samples": int(st.samples), "max_bounce": max_bounce,
+                                              "total_all_ranks": rays_total},
+                "reduce_ms": reduce_ms}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    m.Destroy()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

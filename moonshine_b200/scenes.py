@@ -390,3 +390,230 @@ def material_zoo(extent=(96, 64)) -> Scene:
     s.lens = Lens((-4.2, -1.0, 1.6), tuple(np.array([0.95, 0.2, -0.25]) / np.linalg.norm([0.95, 0.2, -0.25])), (0, 0, 1), math.radians(42), 0.05, 4.0)
     s.constants = Constants()
     return s
+
+
+# ---------------------------------------------------------------------------------------------
+# cfg3/cfg4: procedural "Salle-de-bain-class" bathroom: ~1.2 M triangles in primitives of
+# <= 65 535 vertices, ~40 materials (textured GGX, glass, mirror), window to a sun+sky equirect.
+# ---------------------------------------------------------------------------------------------
+def param_surface(fn, nu: int, nv: int, wrap_u=False, flip=False):
+    """Tessellate p = fn(u, v), u,v in [0,1], into (nu x nv) quads with smooth normals and texcoords."""
+    assert (nu + 1) * (nv + 1) <= 65535
+    u = np.linspace(0.0, 1.0, nu + 1)
+    v = np.linspace(0.0, 1.0, nv + 1)
+    uu, vv = np.meshgrid(u, v)
+    p = fn(uu, vv).astype(np.float64)  # (nv+1, nu+1, 3)
+    e = 1e-4
+    du = (fn(np.clip(uu + e, 0, 1), vv) - fn(np.clip(uu - e, 0, 1), vv)).astype(np.float64)
+    dv = (fn(uu, np.clip(vv + e, 0, 1)) - fn(uu, np.clip(vv - e, 0, 1))).astype(np.float64)
+    n = np.cross(du, dv)
+    ln = np.linalg.norm(n, axis=-1, keepdims=True)
+    n = np.where(ln > 1e-20, n / np.maximum(ln, 1e-20), np.array([0.0, 0.0, 1.0]))
+    if flip:
+        n = -n
+    j, i = np.mgrid[0:nv, 0:nu]
+    a = (j * (nu + 1) + i).reshape(-1)
+    b, c, d = a + 1, a + (nu + 1), a + (nu + 2)
+    tri = np.concatenate([np.stack([a, b, d], 1), np.stack([a, d, c], 1)])
+    if flip:
+        tri = tri[:, ::-1]
+    t = np.stack([uu, vv], -1).reshape(-1, 2)
+    return p.reshape(-1, 3).astype(np.float32), tri.astype(np.uint32), n.reshape(-1, 3).astype(np.float32), t.astype(np.float32)
+
+
+def _superellipsoid(center, radii, e1=0.4, e2=0.4, v0=0.0, v1=1.0):
+    cx, cy, cz = center
+    rx, ry, rz = radii
+
+    def spow(x, p):
+        return np.sign(x) * np.abs(x) ** p
+
+    def fn(u, v):
+        phi = u * 2 * math.pi
+        th = (v0 + (v1 - v0) * v) * math.pi - math.pi / 2
+        return np.stack([cx + rx * spow(np.cos(th), e1) * spow(np.cos(phi), e2),
+                         cy + ry * spow(np.cos(th), e1) * spow(np.sin(phi), e2),
+                         cz + rz * spow(np.sin(th), e1)], -1)
+    return fn
+
+
+def _torus(center, R, r, axis=2):
+    def fn(u, v):
+        a, b = u * 2 * math.pi, v * 2 * math.pi
+        x, y, z = (R + r * np.cos(b)) * np.cos(a), (R + r * np.cos(b)) * np.sin(a), r * np.sin(b)
+        q = [x, y, z]
+        if axis == 0:
+            q = [z, x, y]
+        elif axis == 1:
+            q = [y, z, x]
+        return np.stack([center[0] + q[0], center[1] + q[1], center[2] + q[2]], -1)
+    return fn
+
+
+def _lathe(center, profile_r, height):
+    """Surface of revolution around +Z; profile_r(v) -> radius at height v*height."""
+    def fn(u, v):
+        a = u * 2 * math.pi
+        r = profile_r(v)
+        return np.stack([center[0] + r * np.cos(a), center[1] + r * np.sin(a), center[2] + v * height], -1)
+    return fn
+
+
+def _cloth(corner, ex, ey, normal, amp, fx, fy, phase=0.0):
+    corner, ex, ey, normal = (np.array(x, np.float64) for x in (corner, ex, ey, normal))
+
+    def fn(u, v):
+        w = amp * (np.sin(u * fx + phase) * np.cos(v * fy) + 0.35 * np.sin(u * fx * 2.7 + v * 3.1))
+        return corner + u[..., None] * ex + v[..., None] * ey + w[..., None] * normal
+    return fn
+
+
+def _tile_textures(n=1024, tiles=8, base=(225, 228, 230), grout=(120, 118, 115), seed=1):
+    """sRGB colour + RG8 tangent-space normal for a glazed tile grid with bevelled grout lines."""
+    rs = np.random.RandomState(seed)
+    y, x = np.mgrid[0:n, 0:n]
+    cell = n // tiles
+    fx, fy = (x % cell) / cell, (y % cell) / cell
+    edge = np.minimum(np.minimum(fx, 1 - fx), np.minimum(fy, 1 - fy))
+    g = np.clip(edge / 0.035, 0, 1)
+    tint = rs.rand(tiles, tiles, 3) * 18 - 9
+    tile_col = np.array(base)[None, None] + tint[(y // cell) % tiles, (x // cell) % tiles]
+    col = np.array(grout)[None, None] * (1 - g[..., None]) + tile_col * g[..., None]
+    rgba = np.zeros((n, n, 4), np.uint8)
+    rgba[..., :3] = np.clip(col, 0, 255).astype(np.uint8)
+    rgba[..., 3] = 255
+    h = g + 0.004 * rs.rand(n, n)
+    gx, gy = np.gradient(h, axis=1), np.gradient(h, axis=0)
+    nrm = np.zeros((n, n, 2), np.uint8)
+    nrm[..., 0] = np.clip(127.5 - gx * 900, 0, 255).astype(np.uint8)
+    nrm[..., 1] = np.clip(127.5 - gy * 900, 0, 255).astype(np.uint8)
+    rough = np.clip(60 + (1 - g) * 150 + rs.rand(n, n) * 12, 0, 255).astype(np.uint8)
+    return rgba, nrm, rough
+
+
+def bathroom(extent=(1920, 1080), detail: float = 1.0, seed: int = 0x4D4F4F4E) -> Scene:
+    """cfg3 (and cfg4). `detail` scales tessellation: 1.0 ~ 1.2 M triangles; tests use ~0.05."""
+    s = Scene("cfg3-salle-de-bain-class", extent=extent)
+    rs = np.random.RandomState(seed & 0x7FFFFFFF)
+    flat, black = s.solid2(0.5, 0.5), s.solid3(0, 0, 0)
+
+    def res(nu, nv):
+        k = math.sqrt(detail)
+        a, b = max(4, int(nu * k)), max(3, int(nv * k))
+        while (a + 1) * (b + 1) > 65535:
+            a, b = int(a * 0.97), int(b * 0.97)
+        return a, b
+
+    def pbr(color, metal, rough, ior=1.5, normal=flat, emissive=black):
+        c = color if isinstance(color, int) else s.solid3(*color)
+        m = metal if isinstance(metal, int) and not isinstance(metal, bool) and metal > 1 else s.solid1(float(metal))
+        r = rough if isinstance(rough, int) and rough > 1 else s.solid1(float(rough))
+        return s.add_material(type=MAT_STANDARD_PBR, normal=normal, emissive=emissive, color=c, metalness=m, roughness=r, ior=ior)
+
+    # ---- textures -----------------------------------------------------------------------------
+    tex_n = 1024 if detail >= 0.5 else 128
+    wall_rgba, wall_nrm, wall_rough = _tile_textures(tex_n, 8, (228, 232, 233), (128, 126, 122), 1)
+    floor_rgba, floor_nrm, floor_rough = _tile_textures(tex_n, 4, (70, 82, 92), (35, 35, 38), 2)
+    t_wall_c, t_wall_n, t_wall_r = s.raw_texture(wall_rgba, TEX_RGBA8_SRGB), s.raw_texture(wall_nrm, TEX_RG8_UNORM), s.raw_texture(wall_rough, TEX_R8_UNORM)
+    t_floor_c, t_floor_n, t_floor_r = s.raw_texture(floor_rgba, TEX_RGBA8_SRGB), s.raw_texture(floor_nrm, TEX_RG8_UNORM), s.raw_texture(floor_rough, TEX_R8_UNORM)
+    zero1 = s.solid1(0.0)
+    m_wall = s.add_material(type=MAT_STANDARD_PBR, normal=t_wall_n, emissive=black, color=t_wall_c, metalness=zero1, roughness=t_wall_r, ior=1.5)
+    m_floor = s.add_material(type=MAT_STANDARD_PBR, normal=t_floor_n, emissive=black, color=t_floor_c, metalness=zero1, roughness=t_floor_r, ior=1.5)
+    m_ceiling = s.add_material(type=MAT_LAMBERT, normal=flat, emissive=black, color=s.solid3(0.85, 0.85, 0.82))
+    m_ceramic = pbr((0.92, 0.92, 0.9), 0.0, 0.12)
+    m_chrome = pbr((0.95, 0.95, 0.97), 1.0, 0.05)
+    m_brushed = pbr((0.8, 0.8, 0.82), 1.0, 0.32)
+    m_brass = pbr((0.9, 0.72, 0.35), 1.0, 0.2)
+    m_glass = s.add_material(type=MAT_GLASS, normal=flat, emissive=black, ior=1.5)
+    m_mirror = s.add_material(type=MAT_PERFECT_MIRROR, normal=flat, emissive=black)
+    m_wood = pbr((0.42, 0.27, 0.15), 0.0, 0.55)
+    m_rubber = pbr((0.05, 0.05, 0.05), 0.0, 0.8)
+    m_lamp = s.add_material(type=MAT_LAMBERT, normal=flat, emissive=s.solid3(28, 25, 20), color=s.solid3(0.6, 0.6, 0.6))
+    towel_cols = [(0.75, 0.2, 0.2), (0.2, 0.45, 0.7), (0.9, 0.85, 0.7), (0.3, 0.6, 0.4)]
+    m_towels = [pbr(c, 0.0, 0.9) for c in towel_cols]
+    bottle_mats = [pbr(tuple(rs.rand(3) * 0.8 + 0.1), 0.0, float(rs.rand() * 0.5 + 0.08), ior=1.4 + 0.2 * rs.rand()) for _ in range(14)]
+    soap_mats = [pbr(tuple(rs.rand(3) * 0.5 + 0.45), 0.0, 0.6) for _ in range(4)]
+
+    # ---- room: x in [0,4] (camera looks +x), y in [0,3], z in [0,2.6]; window in the y=3 wall -----
+    X, Y, Z = 4.0, 3.0, 2.6
+
+    def wall(p0, ex, ey, nu, nv, uvscale):
+        p0, ex, ey = np.array(p0, np.float64), np.array(ex, np.float64), np.array(ey, np.float64)
+        p, i, n, t = param_surface(lambda u, v: p0 + u[..., None] * ex + v[..., None] * ey, nu, nv)
+        return p, i, n, (t * np.array(uvscale, np.float32)).astype(np.float32)
+
+    geoms_room = []
+    g = wall((0, 0, 0), (X, 0, 0), (0, Y, 0), *res(64, 48), (X / 1.2, Y / 1.2))
+    geoms_room.append((s.add_mesh(g[0], g[1], g[2], g[3]), m_floor, False))
+    g = wall((0, 0, Z), (0, Y, 0), (X, 0, 0), *res(16, 16), (1, 1))
+    geoms_room.append((s.add_mesh(g[0], g[1], g[2], g[3]), m_ceiling, False))
+    walls = [((X, 0, 0), (0, Y, 0), (0, 0, Z), (Y / 1.6, Z / 1.6)),      # far wall x = X
+             ((0, Y, 0), (0, -Y, 0), (0, 0, Z), (Y / 1.6, Z / 1.6)),     # behind camera x = 0
+             ((0, 0, 0), (X, 0, 0), (0, 0, Z), (X / 1.6, Z / 1.6))]      # y = 0
+    for p0, ex, ey, uvs in walls:
+        g = wall(p0, ex, ey, *res(64, 48), uvs)
+        geoms_room.append((s.add_mesh(g[0], g[1], g[2], g[3]), m_wall, False))
+    # y = Y wall with a window hole x in [1.2, 2.8], z in [0.9, 2.1]: four panels
+    for (x0, x1, z0, z1) in [(0, 1.2, 0, Z), (2.8, X, 0, Z), (1.2, 2.8, 0, 0.9), (1.2, 2.8, 2.1, Z)]:
+        g = wall((x1, Y, z0), (x0 - x1, 0, 0), (0, 0, z1 - z0), *res(24, 24), ((x1 - x0) / 1.6, (z1 - z0) / 1.6))
+        geoms_room.append((s.add_mesh(g[0], g[1], g[2], g[3]), m_wall, False))
+    s.add_instance(geoms_room)
+
+    def add(fn, nu, nv, mat, sampled=False, flip=False, transform=None):
+        p, i, n, t = param_surface(fn, *res(nu, nv), flip=flip)
+        mesh = s.add_mesh(p, i, n, t)
+        s.add_instance([(mesh, mat, sampled)], transform=transform)
+        return mesh
+
+    # bathtub (outer shell + inner basin), sink, toilet
+    add(_superellipsoid((2.9, 0.75, 0.32), (0.95, 0.48, 0.32), 0.35, 0.45, 0.0, 0.62), 300, 150, m_ceramic)
+    add(_superellipsoid((2.9, 0.75, 0.36), (0.86, 0.40, 0.27), 0.4, 0.5, 0.0, 0.58), 300, 150, m_ceramic, flip=True)
+    add(_superellipsoid((1.1, 2.55, 0.88), (0.32, 0.26, 0.16), 0.7, 0.8, 0.0, 0.5), 220, 110, m_ceramic)
+    add(_superellipsoid((1.1, 2.55, 0.9), (0.27, 0.21, 0.13), 0.8, 0.9, 0.0, 0.5), 220, 110, m_ceramic, flip=True)
+    add(_lathe((1.1, 2.62, 0.0), lambda v: 0.09 + 0.05 * (1 - v) ** 2, 0.74), 160, 80, m_ceramic)
+    add(_superellipsoid((0.55, 0.6, 0.28), (0.26, 0.22, 0.28), 0.6, 0.8), 200, 100, m_ceramic)
+    add(_superellipsoid((0.32, 0.6, 0.62), (0.1, 0.24, 0.28), 0.5, 0.5), 160, 80, m_ceramic)
+    add(_torus((0.6, 0.6, 0.46), 0.2, 0.035), 200, 60, m_wood)
+    # chrome: faucets, towel rails, shower head + hose
+    add(_torus((1.1, 2.78, 1.08), 0.1, 0.017, axis=0), 220, 48, m_chrome)
+    add(_lathe((1.1, 2.8, 0.92), lambda v: 0.022 + 0.0 * v, 0.16), 96, 24, m_chrome)
+    add(_torus((3.7, 0.75, 0.78), 0.12, 0.02, axis=1), 220, 48, m_chrome)
+    add(_lathe((3.86, 0.75, 0.6), lambda v: 0.025 + 0.0 * v, 0.3), 96, 24, m_chrome)
+    for k, zz in enumerate((1.25, 1.0)):
+        add(lambda u, v, zz=zz: np.stack([0.03 + 0.012 * np.cos(v * 2 * math.pi), 1.3 + u * 0.9, zz + 0.012 * np.sin(v * 2 * math.pi)], -1), 200, 32, m_brushed)
+    add(_superellipsoid((3.55, 0.75, 2.05), (0.13, 0.13, 0.025), 0.6, 1.0), 200, 60, m_chrome)
+    add(lambda u, v: np.stack([3.9 - 0.3 * np.sin(u * 1.4) + 0.011 * np.cos(v * 2 * math.pi),
+                               0.75 + 0.011 * np.sin(v * 2 * math.pi) * np.ones_like(u),
+                               0.95 + u * 1.1 + 0.0 * v], -1), 240, 24, m_brass)
+    # shower screen: two glass panes (thin boxes) + mirror on the far wall
+    for (x0, x1) in [(1.86, 1.88), (1.92, 1.94)]:
+        bp, bi = _box((x0, 0.05 if x0 < 1.9 else 0.75, 0.05), (x1, 0.8 if x0 < 1.9 else 1.45, 2.0))
+        s.add_instance([(s.add_mesh(bp, bi), m_glass, False)])
+    mq = _quad((X - 0.01, 1.7, 1.0), (X - 0.01, 2.7, 1.0), (X - 0.01, 2.7, 1.9), (X - 0.01, 1.7, 1.9))
+    s.add_instance([(s.add_mesh(mq[0], mq[1][:, ::-1].copy()), m_mirror, False)])
+    add(lambda u, v: np.stack([X - 0.012 - 0.0 * u, 1.66 + 1.08 * u, 0.96 + 0.98 * v], -1) +
+        np.stack([0.02 * (np.minimum(np.minimum(u, 1 - u), np.minimum(v, 1 - v)) < 0.04), 0 * u, 0 * u], -1), 64, 64, m_wood, flip=True)
+    # towels (cloth), bath mat
+    for k in range(4):
+        yy = 1.32 + 0.22 * k
+        add(_cloth((0.06, yy, 1.24 if k % 2 == 0 else 0.99), (0.0, 0.2, 0.0), (0.0, 0.0, -0.55), (1, 0, 0), 0.012, 38.0, 9.0, phase=k), 260, 220, m_towels[k])
+    add(_cloth((1.9, 1.55, 0.012), (0.9, 0, 0), (0, 0.6, 0), (0, 0, 1), 0.006, 90.0, 60.0), 250, 250, m_rubber)
+    # shelf with bottles, soaps
+    sp, si = _box((2.2, 2.8, 1.15), (3.6, 2.98, 1.18))
+    s.add_instance([(s.add_mesh(sp, si), m_wood, False)])
+    for k in range(14):
+        bx_, h = 2.28 + 0.095 * k, 0.14 + 0.12 * rs.rand()
+        r0, neck = 0.028 + 0.012 * rs.rand(), 0.3 + 0.3 * rs.rand()
+        prof = (lambda r0, neck: (lambda v: r0 * np.where(v < 0.7, 1.0 - 0.08 * np.sin(v * 9), np.maximum(neck, 1.0 - (v - 0.7) * 2.6))))(r0, neck)
+        add(_lathe((bx_, 2.89, 1.18), prof, h), 128, 64, bottle_mats[k])
+    for k in range(4):
+        add(_superellipsoid((3.3 + 0.12 * k, 0.32, 0.66), (0.045, 0.03, 0.016), 0.5, 0.6), 120, 60, soap_mats[k])
+    # ceiling lamp: sampled emitter (material name prefix "Emitter" in the reference's glTF rule, World.zig:270)
+    add(_superellipsoid((2.0, 1.5, Z - 0.09), (0.22, 0.22, 0.07), 0.9, 1.0), 96, 48, m_lamp, sampled=True)
+
+    sky_w = 2048 if detail >= 0.5 else 256
+    s.background = procedural_sky(sky_w, sky_w // 2, sun_dir=(0.15, 0.75, 0.64), sun_power=5.0e4)
+    fw = np.array([0.93, 0.28, -0.22])
+    s.lens = Lens((0.35, 0.55, 1.55), tuple(fw / np.linalg.norm(fw)), (0, 0, 1), math.radians(58), 0.0, 1.0)
+    s.constants = Constants()
+    return s
