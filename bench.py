@@ -4,7 +4,7 @@
 Workload (config.workload): cfg3, the procedural "Salle-de-bain-class" bathroom (moonshine_b200/scenes.py
 `bathroom`, ~1.4 M triangles, 34 materials, sun+sky env map) at 1920x1080, offline constants
 (offline/main.zig:106-111). One STEP = one wave batch of `batch_spp` samples per pixel over every pixel this
-rank owns (default 8 spp; the default 128 timed steps are the full 1024 spp of the metric config). With N
+rank owns (default 32 spp; the default 32 timed steps are the full 1024 spp of the metric config). With N
 GPUs the image is sharded into 32x32 tiles round-robin over ranks and each step renders batch_spp*N samples
 of the rank's tiles (weak scaling: per-GPU work fixed), followed by ONE NCCL reduce of the RGBA32F radiance
 buffer to rank 0 inside the timed region.
@@ -167,14 +167,15 @@ def config_dict(args, scene, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=128)
+    ap.add_argument("--steps", type=int, default=32)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3")
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--detail", type=float, default=1.0)
-    ap.add_argument("--batch-spp", type=int, default=8)
+    ap.add_argument("--batch-spp", type=int, default=32)
+    ap.add_argument("--paths-in-flight", type=int, default=0, help="wavefront pool size in paths (0 = library default, 64 Mi)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps (capped at 32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -195,6 +196,8 @@ def main():
     scene = make_scene(args)
     W, H = scene.extent
     m = hydra.HdMoonshine(local_rank)
+    if args.paths_in_flight:
+        m.SetPathsInFlight(args.paths_in_flight)
     scenes.load_scene(m, scene)
     m.SetTileShard(rank, world)
     sensor, lens = m.CreateSensor(W, H), m.CreateLens(scene.lens)

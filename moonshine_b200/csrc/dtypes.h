@@ -18,19 +18,27 @@ namespace msne {
 // ---- acceleration structure -----------------------------------------------------------------
 // BVH2 node, 64 B (four 16-byte lanes, one 128-bit load each):
 //   n0 = (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)   n1 = (c1.lo.x, c1.hi.x, c1.lo.y, c1.hi.y)
-//   n2 = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)   c  = (child0, child1, count0, count1)
-// count == 0: child is an inner-node index (-1 = empty child, never entered); count > 0: child is the
-// first item (triangle index in the pooled triangle array for a BLAS, slot in tlasItems for the TLAS)
-// and count the number of items. Every BVH has at least one inner node (the root).
+//   n2 = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)   c  = (ref0, ref1, -, -)
+// The host builder (bvh_build.cpp) emits c = (child0, child1, count0, count1) with local indices; when a BVH is
+// pooled for the device (runtime.cpp) the children become pre-encoded traversal references:
+//   0 <= ref < REF_ITEM      inner node index in the pooled node array
+//   ref < 0                  BLAS leaf: x = ~ref, first triangle = x >> 3, count = (x & 7) + 1
+//   REF_ITEM | slot          TLAS leaf: one instance, tlasItems[slot]
+//   REF_EMPTY                no child;  REF_LEAVE / REF_END are stack sentinels of the traversal loop
+// Every BVH has at least one inner node (the root).
 struct BvhNode2 {
     float n0[4], n1[4], n2[4];
     int32_t c[4];
 };
 static_assert(sizeof(BvhNode2) == 64, "BvhNode2 must be 64 B");
 
+static const int32_t REF_ITEM = 0x40000000, REF_EMPTY = 0x7FFFFFFD, REF_LEAVE = 0x7FFFFFFE, REF_END = 0x7FFFFFFF;
+
 // Triangle record, 48 B: three vertices in object space + ids (watertight edge test needs all three)
-//   t0 = (v0.xyz, geometryIndex)  t1 = (v1.xyz, primitiveIndex)  t2 = (v2.xyz, 0)
-struct TriRec { float v0[3]; uint32_t geom; float v1[3]; uint32_t prim; float v2[3]; uint32_t pad; };
+//   t0 = (v0.xyz, geometryIndex)  t1 = (v1.xyz, primitiveIndex)  t2 = (v2.xyz, instanceIndex)
+// instanceIndex is only meaningful inside the merged static BLAS (all visible identity-transform instances
+// flattened into one world-space BVH: an identity transform leaves the ray bit-identical, so this is exact).
+struct TriRec { float v0[3]; uint32_t geom; float v1[3]; uint32_t prim; float v2[3]; uint32_t inst; };
 static_assert(sizeof(TriRec) == 48, "TriRec must be 48 B");
 
 // world.hlsl:6-15 + worldToInstance[] (main.hlsl:13) + our BLAS references, 128 B
@@ -40,7 +48,8 @@ struct DInstance {
     uint32_t customIndex;  // offset into geometries[] (low 24 bits of instanceCustomIndexAndMask)
     uint32_t blasRoot;     // index of the BLAS root in the pooled node array
     uint32_t visible;      // mask != 0
-    uint32_t pad[5];
+    uint32_t isStatic;     // 1: pseudo-instance holding the merged static BLAS (no transform; hit.inst comes from TriRec.inst)
+    uint32_t pad[4];
 };
 static_assert(sizeof(DInstance) == 128, "DInstance must be 128 B");
 
@@ -122,6 +131,7 @@ static const uint32_t FLAG_DEAD = 0x80000000u;
 static const uint32_t FLAG_DELTA = 0x40000000u;
 static const uint32_t BOUNCE_MASK = 0x3FFFFFFFu;
 static const uint32_t MISS_ID = 0xFFFFFFFFu;
+static const uint32_t STATIC_INST = 0xFFFFFFFEu;
 
 enum TexFormat : uint32_t { TEX_R32F = 0, TEX_RG32F, TEX_RGBA32F, TEX_R8_UNORM, TEX_RG8_UNORM, TEX_RGBA8_SRGB, TEX_RGBA16F };
 enum MatType : uint32_t { MAT_GLASS = 0, MAT_LAMBERT, MAT_PERFECT_MIRROR, MAT_STANDARD_PBR };

@@ -16,6 +16,7 @@
 // k_generate starts a wave (main.hlsl:85-88), k_accumulate applies storeColor (main.hlsl:43-51) in sample
 // order. Compiled with -fmad=false (see device_math.cuh).
 #include "kernels.h"
+#include <cstdlib>
 #include "shading.cuh"
 #include "traverse.cuh"
 
@@ -322,7 +323,8 @@ DI void shadeOne(const DeviceScene& sc, const DConstants& k, const PathBuffers& 
     out.S0 = make_float4(throughput.x, throughput.y, throughput.z, __uint_as_float(rng.state));
 }
 
-__global__ void __launch_bounds__(SHADE_THREADS) k_shade(DeviceScene sc, DConstants k, PathBuffers pb, WaveState ws, uint32_t buf) {
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(SHADE_THREADS, MIN_BLOCKS) k_shade(DeviceScene sc, DConstants k, PathBuffers pb, WaveState ws, uint32_t buf) {
     const Counters cin = ws.counters[buf];
     Counters* cout = ws.counters + (buf ^ 1u);
     const uint32_t nLive = cin.nLive, total = cin.nLive + cin.nDead;
@@ -468,8 +470,18 @@ void launchGenerate(cudaStream_t st, const DCamera& cam, const DConstants& k, co
 void launchTrace(cudaStream_t st, int blocks, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf) {
     k_trace<<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf);
 }
+static int g_shadeVariant = -1;
+static int shadeVariant() {
+    if (g_shadeVariant < 0) { const char* e = getenv("MSNE_SHADE_MINB"); g_shadeVariant = e ? atoi(e) : 6;   // 80 regs, 6 blocks/SM: measured best (profiles/r01_sweeps.md) }
+    return g_shadeVariant;
+}
 void launchShade(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf) {
-    k_shade<<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf);
+    switch (shadeVariant()) {
+        case 4: k_shade<4><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf); break;
+        case 5: k_shade<5><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf); break;
+        case 6: k_shade<6><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf); break;
+        default: k_shade<3><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf); break;
+    }
 }
 void launchAccumulate(cudaStream_t st, const float4* result, float4* image, float4* runState, const uint32_t* pixIds, uint32_t nPix, uint32_t nSamples,
                       uint32_t firstSample, uint32_t spr) {
@@ -496,7 +508,12 @@ int traceOccupancyBlocksPerSm() {
 }
 int shadeOccupancyBlocksPerSm() {
     int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade, SHADE_THREADS, 0);
+    switch (shadeVariant()) {
+        case 4: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade<4>, SHADE_THREADS, 0); break;
+        case 5: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade<5>, SHADE_THREADS, 0); break;
+        case 6: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade<6>, SHADE_THREADS, 0); break;
+        default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade<3>, SHADE_THREADS, 0); break;
+    }
     return n;
 }
 

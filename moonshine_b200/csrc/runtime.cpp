@@ -181,7 +181,7 @@ struct HdMoonshine {
     std::vector<BvhNode2> blasNodePool;
     std::vector<TriRec> triPool;
 
-    bool tablesDirty = true, accelDirty = true, poolDirty = true, aliasDirty = true;
+    bool tablesDirty = true, accelDirty = true, aliasDirty = true;
 
     DevBuf<BvhNode2> dTlasNodes, dBlasNodes;
     DevBuf<uint32_t> dTlasItems;
@@ -204,7 +204,7 @@ struct HdMoonshine {
     uint32_t shardRank = 0, shardWorld = 1;
 
     // wavefront pool
-    uint64_t pathsInFlight = 1ull << 24;
+    uint64_t pathsInFlight = 1ull << 26;   // 64 Mi paths x 288 B = 18 GiB of the 180 GB HBM; amortises the Russian-roulette tail
     PathBuffers pb{};
     std::vector<DevBuf<float4>> poolBufs;
     DevBuf<uint4> poolH;
@@ -287,45 +287,125 @@ struct HdMoonshine {
         CK(cudaStreamSynchronize(stream));   // src is freed on return
     }
 
-    // ---- acceleration structure --------------------------------------------------------------
+    // ---- acceleration structure (replaces Accel.zig:94-184 makeBlases and :440-489 TLAS build) ------
+    // pools a host BVH: children become the pre-encoded traversal references of dtypes.h
+    uint32_t appendBlas(const BuiltBvh& bvh, const std::vector<TriRec>& tris) {
+        const uint32_t nodeBase = (uint32_t)blasNodePool.size(), triBase = (uint32_t)triPool.size();
+        for (BvhNode2 n : bvh.nodes) {
+            for (int s = 0; s < 2; s++) {
+                const int32_t child = n.c[s], count = n.c[2 + s];
+                if (count > 0) n.c[s] = (int32_t)~((((uint32_t)child + triBase) << 3) | (uint32_t)(count - 1));
+                else if (child < 0) n.c[s] = REF_EMPTY;
+                else n.c[s] = child + (int32_t)nodeBase;
+            }
+            n.c[2] = n.c[3] = 0;
+            blasNodePool.push_back(n);
+        }
+        for (uint32_t i = 0; i < bvh.order.size(); i++) triPool.push_back(tris[bvh.order[i]]);
+        return nodeBase;
+    }
+    static void meshTriangles(const HostMesh& m, uint32_t geom, uint32_t inst, std::vector<TriRec>& tris, std::vector<BuildBox>& boxes) {
+        const uint32_t nTri = (uint32_t)(m.idx.size() / 3);
+        for (uint32_t p = 0; p < nTri; p++) {
+            TriRec t{};
+            const float* v[3] = {&m.pos[3 * (size_t)m.idx[3 * p]], &m.pos[3 * (size_t)m.idx[3 * p + 1]], &m.pos[3 * (size_t)m.idx[3 * p + 2]]};
+            memcpy(t.v0, v[0], 12); memcpy(t.v1, v[1], 12); memcpy(t.v2, v[2], 12);
+            t.geom = geom; t.prim = p; t.inst = inst;
+            BuildBox b;
+            for (int a = 0; a < 3; a++) {
+                b.lo[a] = std::min(v[0][a], std::min(v[1][a], v[2][a]));
+                b.hi[a] = std::max(v[0][a], std::max(v[1][a], v[2][a]));
+            }
+            tris.push_back(t); boxes.push_back(b);
+        }
+    }
     uint32_t getBlas(const std::vector<uint32_t>& key) {
         auto it = blasByKey.find(key);
         if (it != blasByKey.end()) return it->second;
         std::vector<BuildBox> boxes;
         std::vector<TriRec> tris;
-        for (uint32_t g = 0; g < key.size(); g++) {
-            const HostMesh& m = *meshes[key[g]];
-            const uint32_t nTri = (uint32_t)(m.idx.size() / 3);
-            for (uint32_t p = 0; p < nTri; p++) {
-                TriRec t{};
-                const float* v[3] = {&m.pos[3 * (size_t)m.idx[3 * p]], &m.pos[3 * (size_t)m.idx[3 * p + 1]], &m.pos[3 * (size_t)m.idx[3 * p + 2]]};
-                memcpy(t.v0, v[0], 12); memcpy(t.v1, v[1], 12); memcpy(t.v2, v[2], 12);
-                t.geom = g; t.prim = p; t.pad = 0;
-                BuildBox b;
-                for (int a = 0; a < 3; a++) {
-                    b.lo[a] = std::min(v[0][a], std::min(v[1][a], v[2][a]));
-                    b.hi[a] = std::max(v[0][a], std::max(v[1][a], v[2][a]));
-                }
-                tris.push_back(t); boxes.push_back(b);
-            }
-        }
+        for (uint32_t g = 0; g < key.size(); g++) meshTriangles(*meshes[key[g]], g, 0, tris, boxes);
         BuiltBvh bvh;
         buildBvh2(boxes.data(), (uint32_t)boxes.size(), 4, bvh);
-        const uint32_t nodeBase = (uint32_t)blasNodePool.size(), triBase = (uint32_t)triPool.size();
-        for (BvhNode2 n : bvh.nodes) {
-            for (int s = 0; s < 2; s++) {
-                if (n.c[2 + s] > 0) n.c[s] += (int32_t)triBase;          // leaf: first triangle in the pool
-                else if (n.c[s] >= 0) n.c[s] += (int32_t)nodeBase;       // inner: pooled node index
-            }
-            blasNodePool.push_back(n);
-        }
-        for (uint32_t i = 0; i < bvh.order.size(); i++) triPool.push_back(tris[bvh.order[i]]);
-        Blas b; b.rootNode = nodeBase; b.bounds = bvh.bounds;
+        Blas b; b.rootNode = appendBlas(bvh, tris); b.bounds = bvh.bounds;
         blases.push_back(b);
         const uint32_t id = (uint32_t)blases.size() - 1;
         blasByKey[key] = id;
-        poolDirty = true;
         return id;
+    }
+    static bool isIdentity(const float* m) {
+        static const float I[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+        return memcmp(m, I, 48) == 0;
+    }
+
+    void buildAccel() {
+        blasNodePool.clear(); triPool.clear(); blasByKey.clear(); blases.clear();
+        const uint32_t nInst = (uint32_t)instances.size();
+        std::vector<DInstance> di(nInst + 1);
+        std::vector<BuildBox> boxes;      // TLAS item bounds (world space)
+        std::vector<uint32_t> items;      // TLAS item -> instance record
+        // 1. every visible identity-transform instance goes into ONE world-space BLAS
+        std::vector<TriRec> stTris;
+        std::vector<BuildBox> stBoxes;
+        for (uint32_t i = 0; i < nInst; i++) {
+            const HostInstance& in = instances[i];
+            if (!in.visible || !isIdentity(in.transform)) continue;
+            for (uint32_t g = 0; g < in.meshKey.size(); g++) meshTriangles(*meshes[in.meshKey[g]], g, i, stTris, stBoxes);
+        }
+        DInstance st{};
+        const float I[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+        memcpy(st.o2w, I, 48); memcpy(st.w2o, I, 48);
+        st.isStatic = 1; st.visible = 1;
+        if (!stTris.empty()) {
+            BuiltBvh bvh;
+            buildBvh2(stBoxes.data(), (uint32_t)stBoxes.size(), 4, bvh);
+            st.blasRoot = appendBlas(bvh, stTris);
+            boxes.push_back(bvh.bounds); items.push_back(nInst);
+        }
+        di[nInst] = st;
+        // 2. transformed instances keep their own (shared) object-space BLAS
+        for (uint32_t i = 0; i < nInst; i++) {
+            HostInstance& in = instances[i];
+            DInstance d{};
+            memcpy(d.o2w, in.transform, 48); memcpy(d.w2o, in.inverse, 48);
+            d.customIndex = in.customIndex; d.visible = in.visible ? 1 : 0;
+            if (in.visible && !isIdentity(in.transform)) {
+                in.blas = getBlas(in.meshKey);
+                d.blasRoot = blases[in.blas].rootNode;
+                const BuildBox& bb = blases[in.blas].bounds;
+                BuildBox w; for (int a = 0; a < 3; a++) { w.lo[a] = 1e30f; w.hi[a] = -1e30f; }
+                for (int c = 0; c < 8; c++) {
+                    const float p[3] = {(c & 1) ? bb.hi[0] : bb.lo[0], (c & 2) ? bb.hi[1] : bb.lo[1], (c & 4) ? bb.hi[2] : bb.lo[2]};
+                    for (int r = 0; r < 3; r++) {
+                        const float q = ((in.transform[4 * r] * p[0] + in.transform[4 * r + 1] * p[1]) + in.transform[4 * r + 2] * p[2]) + in.transform[4 * r + 3];
+                        w.lo[r] = std::min(w.lo[r], q); w.hi[r] = std::max(w.hi[r], q);
+                    }
+                }
+                padBox(w);
+                boxes.push_back(w); items.push_back(i);
+            }
+            di[i] = d;
+        }
+        dBlasNodes.upload(blasNodePool.data(), blasNodePool.size(), stream);
+        dTris.upload(triPool.data(), triPool.size(), stream);
+        dInstances.upload(di.data(), di.size(), stream);
+        hasTlas = !items.empty();
+        if (hasTlas) {
+            BuiltBvh tl;
+            buildBvh2(boxes.data(), (uint32_t)boxes.size(), 1, tl);
+            std::vector<uint32_t> slots(tl.order.size());
+            for (size_t s = 0; s < tl.order.size(); s++) slots[s] = items[tl.order[s]];
+            for (BvhNode2& n : tl.nodes)
+                for (int s = 0; s < 2; s++) {
+                    const int32_t child = n.c[s], count = n.c[2 + s];
+                    if (count > 0) n.c[s] = REF_ITEM | child;   // leaf size is 1: one instance per TLAS leaf
+                    else if (child < 0) n.c[s] = REF_EMPTY;
+                }
+            for (BvhNode2& n : tl.nodes) n.c[2] = n.c[3] = 0;
+            dTlasNodes.upload(tl.nodes.data(), tl.nodes.size(), stream);
+            dTlasItems.upload(slots.data(), slots.size(), stream);
+        }
+        CK(cudaStreamSynchronize(stream));
     }
 
     void syncScene() {
@@ -341,48 +421,7 @@ struct HdMoonshine {
             CK(cudaStreamSynchronize(stream));   // staging vectors die here
             tablesDirty = false;
         }
-        if (accelDirty) {
-            for (auto& in : instances) in.blas = getBlas(in.meshKey);
-            if (poolDirty) {
-                dBlasNodes.upload(blasNodePool.data(), blasNodePool.size(), stream);
-                dTris.upload(triPool.data(), triPool.size(), stream);
-                poolDirty = false;
-            }
-            std::vector<DInstance> di(instances.size());
-            std::vector<BuildBox> boxes;
-            std::vector<uint32_t> items;
-            for (uint32_t i = 0; i < instances.size(); i++) {
-                const HostInstance& in = instances[i];
-                DInstance d{};
-                memcpy(d.o2w, in.transform, 48); memcpy(d.w2o, in.inverse, 48);
-                d.customIndex = in.customIndex; d.blasRoot = blases[in.blas].rootNode; d.visible = in.visible ? 1 : 0;
-                di[i] = d;
-                if (!in.visible) continue;
-                const BuildBox& bb = blases[in.blas].bounds;
-                BuildBox w; for (int a = 0; a < 3; a++) { w.lo[a] = 1e30f; w.hi[a] = -1e30f; }
-                for (int c = 0; c < 8; c++) {
-                    const float p[3] = {(c & 1) ? bb.hi[0] : bb.lo[0], (c & 2) ? bb.hi[1] : bb.lo[1], (c & 4) ? bb.hi[2] : bb.lo[2]};
-                    for (int r = 0; r < 3; r++) {
-                        const float q = ((in.transform[4 * r] * p[0] + in.transform[4 * r + 1] * p[1]) + in.transform[4 * r + 2] * p[2]) + in.transform[4 * r + 3];
-                        w.lo[r] = std::min(w.lo[r], q); w.hi[r] = std::max(w.hi[r], q);
-                    }
-                }
-                padBox(w);
-                boxes.push_back(w); items.push_back(i);
-            }
-            dInstances.upload(di.data(), di.size(), stream);
-            hasTlas = !items.empty();
-            if (hasTlas) {
-                BuiltBvh tl;
-                buildBvh2(boxes.data(), (uint32_t)boxes.size(), 1, tl);
-                std::vector<uint32_t> slots(tl.order.size());
-                for (size_t s = 0; s < tl.order.size(); s++) slots[s] = items[tl.order[s]];
-                dTlasNodes.upload(tl.nodes.data(), tl.nodes.size(), stream);
-                dTlasItems.upload(slots.data(), slots.size(), stream);
-            }
-            CK(cudaStreamSynchronize(stream));
-            accelDirty = false;
-        }
+        if (accelDirty) { buildAccel(); accelDirty = false; }
         if (aliasDirty) {
             dAlias.upload(alias.data(), alias.size(), stream);
             CK(cudaStreamSynchronize(stream));
@@ -848,7 +887,7 @@ bool HdMoonshineExtSetTileShard(HdMoonshine* h, uint32_t rank, uint32_t world) {
         return true;
     } catch (const std::exception& e) { g_lastError = e.what(); return false; }
 }
-void HdMoonshineExtSetPathsInFlight(HdMoonshine* h, uint64_t n) { LOCK(h); h->pathsInFlight = n ? n : (1ull << 24); h->pb.capacity = 0; }
+void HdMoonshineExtSetPathsInFlight(HdMoonshine* h, uint64_t n) { LOCK(h); h->pathsInFlight = n ? n : (1ull << 26); h->pb.capacity = 0; }
 void HdMoonshineExtSetProfiling(HdMoonshine* h, bool on) { LOCK(h); h->profiling = on; }
 void HdMoonshineExtGetStats(const HdMoonshine* h, MsneStats* out) {
     HdMoonshine* m = const_cast<HdMoonshine*>(h);

@@ -10,13 +10,21 @@
 //   T=(U*dot(A,d)+V*dot(B,d))+W*dot(C,d);  t=(T*rdet)*(1/dot(d,d));  hit iff tmin<t<tmax
 //   closest = min t, ties -> smallest (instance, geometry, primitive); no culling; mask 0 skipped.
 // The slab test is only required to be conservative (boxes are padded at build time, bvh_build.h).
+//
+// Loop structure ("while-while with postponed leaves"): a lane walks inner nodes until it holds a leaf,
+// parks it and keeps descending until a second leaf shows up; only then does it run triangle tests. Lanes
+// of a warp therefore meet in the triangle loop instead of executing it one lane at a time (the v1 kernel
+// ran at 4.8/32 active lanes per instruction, profiles/r01a_ncu_summary_baseline.txt).
+// All visible identity-transform instances live in ONE world-space BLAS (runtime.cpp buildAccel): an identity
+// transform leaves the ray bit-identical, so flattening changes no result, and their triangles carry the
+// instance index.
 #pragma once
 #include "device_math.cuh"
 
 namespace msne {
 
 #ifndef MSNE_STACK
-#define MSNE_STACK 64
+#define MSNE_STACK 96
 #endif
 
 struct HitRec { uint32_t inst, tri; float u, v; };
@@ -60,98 +68,88 @@ DI bool triTest(const float4 t0, const float4 t1, const float4 t2, const SpaceRa
     return tmin < t && t < tmax;
 }
 
-// stack entry encoding: >= 0 inner node (of the level currently traversed); -1 end; -2 leave instance;
-// <= -3 TLAS item slot (-e-3)
 template <bool ANY_HIT>
-DI bool traceRay(const DeviceScene& sc, float3 o, float3 d, float tmin, float tmax, HitRec& hit) {
+DI bool traceRay(const DeviceScene& sc, const float3 o, const float3 d, const float tmin, const float tmax, HitRec& hit) {
     hit.inst = MISS_ID; hit.tri = 0; hit.u = 0.0f; hit.v = 0.0f;
     if (sc.tlasNodes == nullptr) return false;
     float bestT = tmax;
     int stack[MSNE_STACK];
     int sp = 0;
-    stack[sp++] = -1;
-    SpaceRay world; world.set(o, d);
-    SpaceRay ray = world;
+    stack[sp++] = REF_END;
+    SpaceRay ray; ray.set(o, d);
     const BvhNode2* nodes = sc.tlasNodes;
-    bool inBlas = false;
-    uint32_t curInst = 0;
-    int node = 0;
-    for (;;) {
-        while (node >= 0) {
+    uint32_t curInst = MISS_ID;
+    int node = 0;   // current reference (see dtypes.h): inner node, leaf (<0), TLAS item, or sentinel
+    int leaf = 0;   // parked leaf reference (0 = none; 0 is never a leaf code)
+    while (node != REF_END) {
+        // ---- inner nodes: descend until two leaves are pending (or the stack yields a non-inner entry) ----
+        while ((uint32_t)node < (uint32_t)REF_ITEM) {
             const float4* np = reinterpret_cast<const float4*>(nodes + node);
             const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
-            const int4 c = __ldg(reinterpret_cast<const int4*>(np + 3));
+            const int2 c = __ldg(reinterpret_cast<const int2*>(np + 3));
             float tn0, tn1;
-            bool h0 = slab(ray, n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, tmin, bestT, tn0) && (c.x != -1 || c.z > 0);
-            bool h1 = slab(ray, n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, tmin, bestT, tn1) && (c.y != -1 || c.w > 0);
-            int next = -1, deferred = -1;
-#pragma unroll
-            for (int s = 0; s < 2; s++) {
-                const bool h = s == 0 ? h0 : h1;
-                const int child = s == 0 ? c.x : c.y;
-                const int count = s == 0 ? c.z : c.w;
-                if (!h) continue;
-                if (count > 0) {
-                    if (inBlas) {
-                        for (int i = 0; i < count; i++) {
-                            const float4* tp = reinterpret_cast<const float4*>(sc.tris + (child + i));
-                            const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
-                            float t, u, v;
-                            if (!triTest(t0, t1, t2, ray, tmin, tmax, t, u, v)) continue;
-                            if (ANY_HIT) { hit.inst = curInst; return true; }
-                            bool better = t < bestT;
-                            if (!better && t == bestT && hit.inst != MISS_ID) {
-                                const uint32_t tri = (uint32_t)(child + i);
-                                if (curInst != hit.inst) better = curInst < hit.inst;
-                                else {
-                                    const uint32_t g = __float_as_uint(t0.w), p = __float_as_uint(t1.w);
-                                    const uint32_t bg = sc.tris[hit.tri].geom, bp = sc.tris[hit.tri].prim;
-                                    better = g != bg ? g < bg : p < bp;
-                                }
-                                (void)tri;
-                            }
-                            if (better) { bestT = t; hit.inst = curInst; hit.tri = (uint32_t)(child + i); hit.u = u; hit.v = v; }
-                        }
-                    } else {
-                        for (int i = 0; i < count; i++) if (sp < MSNE_STACK) stack[sp++] = -(child + i) - 3;
-                    }
-                } else {
-                    if (next < 0) next = child; else deferred = child;
-                }
-            }
-            if (deferred >= 0) {
-                // both children are inner nodes: visit the nearer first
-                if (tn1 < tn0) { const int tmp = next; next = deferred; deferred = tmp; }
-                if (sp < MSNE_STACK) stack[sp++] = deferred;
-            }
-            node = next >= 0 ? next : -1;
-            if (node < 0) break;
+            const bool h0 = slab(ray, n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, tmin, bestT, tn0) && c.x != REF_EMPTY;
+            const bool h1 = slab(ray, n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, tmin, bestT, tn1) && c.y != REF_EMPTY;
+            if (h0 && h1) {
+                const bool swap = tn1 < tn0;
+                node = swap ? c.y : c.x;
+                if (sp < MSNE_STACK) stack[sp++] = swap ? c.x : c.y;
+            } else if (h0) node = c.x;
+            else if (h1) node = c.y;
+            else node = stack[--sp];
+            if (node < 0 && leaf == 0) { leaf = node; node = stack[--sp]; }   // park the first leaf, keep walking
         }
-        // pop
-        for (;;) {
-            const int e = stack[--sp];
-            if (e == -1) return hit.inst != MISS_ID;
-            if (e == -2) { inBlas = false; ray = world; nodes = sc.tlasNodes; continue; }
-            if (e <= -3) {
-                const uint32_t inst = __ldg(sc.tlasItems + (-e - 3));
-                const DInstance* in = sc.instances + inst;
-                const float4* mp = reinterpret_cast<const float4*>(in->w2o);
-                const float4 r0 = __ldg(mp), r1 = __ldg(mp + 1), r2 = __ldg(mp + 2);
-                const float3 oo = mk3(((r0.x * o.x + r0.y * o.y) + r0.z * o.z) + r0.w, ((r1.x * o.x + r1.y * o.y) + r1.z * o.z) + r1.w,
-                                      ((r2.x * o.x + r2.y * o.y) + r2.z * o.z) + r2.w);
-                const float3 od = mk3((r0.x * d.x + r0.y * d.y) + r0.z * d.z, (r1.x * d.x + r1.y * d.y) + r1.z * d.z, (r2.x * d.x + r2.y * d.y) + r2.z * d.z);
-                ray.set(oo, od);
-                curInst = inst;
-                inBlas = true;
-                nodes = sc.blasNodes;
-                stack[sp++] = -2;
-                node = (int)__ldg(&in->blasRoot);
-                break;
+        // ---- triangles of the parked leaf, then of `node` if that is a leaf too --------------------------
+        while (leaf != 0) {
+            const uint32_t x = ~(uint32_t)leaf;
+            const uint32_t first = x >> 3, count = (x & 7u) + 1u;
+            for (uint32_t i = 0; i < count; i++) {
+                const float4* tp = reinterpret_cast<const float4*>(sc.tris + (first + i));
+                const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+                float t, u, v;
+                if (!triTest(t0, t1, t2, ray, tmin, tmax, t, u, v)) continue;
+                const uint32_t inst = curInst == STATIC_INST ? __float_as_uint(t2.w) : curInst;
+                if (ANY_HIT) { hit.inst = inst; return true; }
+                bool better = t < bestT;
+                if (!better && t == bestT && hit.inst != MISS_ID) {
+                    if (inst != hit.inst) better = inst < hit.inst;
+                    else {
+                        const uint32_t g = __float_as_uint(t0.w), p = __float_as_uint(t1.w);
+                        const uint32_t bg = sc.tris[hit.tri].geom, bp = sc.tris[hit.tri].prim;
+                        better = g != bg ? g < bg : p < bp;
+                    }
+                }
+                if (better) { bestT = t; hit.inst = inst; hit.tri = first + i; hit.u = u; hit.v = v; }
             }
-            node = e;
-            break;
+            leaf = 0;
+            if (node < 0) { leaf = node; node = stack[--sp]; }
+        }
+        // ---- level changes (rare relative to node steps) -------------------------------------------------
+        if ((uint32_t)node >= (uint32_t)REF_ITEM && node != REF_END) {
+            if (node == REF_LEAVE) {
+                ray.set(o, d); nodes = sc.tlasNodes; curInst = MISS_ID;
+                node = stack[--sp];
+            } else {
+                const uint32_t inst = __ldg(sc.tlasItems + (node & ~REF_ITEM));
+                const DInstance* in = sc.instances + inst;
+                if (__ldg(&in->isStatic)) {
+                    curInst = STATIC_INST;   // world space == object space
+                } else {
+                    const float4* mp = reinterpret_cast<const float4*>(in->w2o);
+                    const float4 r0 = __ldg(mp), r1 = __ldg(mp + 1), r2 = __ldg(mp + 2);
+                    const float3 oo = mk3(((r0.x * o.x + r0.y * o.y) + r0.z * o.z) + r0.w, ((r1.x * o.x + r1.y * o.y) + r1.z * o.z) + r1.w,
+                                          ((r2.x * o.x + r2.y * o.y) + r2.z * o.z) + r2.w);
+                    const float3 od = mk3((r0.x * d.x + r0.y * d.y) + r0.z * d.z, (r1.x * d.x + r1.y * d.y) + r1.z * d.z, (r2.x * d.x + r2.y * d.y) + r2.z * d.z);
+                    ray.set(oo, od);
+                    curInst = inst;
+                }
+                nodes = sc.blasNodes;
+                if (sp < MSNE_STACK) stack[sp++] = REF_LEAVE;
+                node = (int)__ldg(&in->blasRoot);
+            }
         }
     }
+    return hit.inst != MISS_ID;
 }
 
 }  // namespace msne
