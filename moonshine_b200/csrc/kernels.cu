@@ -472,7 +472,8 @@ void launchTrace(cudaStream_t st, int blocks, const DeviceScene& sc, const PathB
 }
 static int g_shadeVariant = -1;
 static int shadeVariant() {
-    if (g_shadeVariant < 0) { const char* e = getenv("MSNE_SHADE_MINB"); g_shadeVariant = e ? atoi(e) : 6;   // 80 regs, 6 blocks/SM: measured best (profiles/r01_sweeps.md) }
+    // default 6 = 80 registers, 6 blocks/SM: measured best (profiles/r01_sweeps.md)
+    if (g_shadeVariant < 0) { const char* e = getenv("MSNE_SHADE_MINB"); g_shadeVariant = e ? atoi(e) : 6; }
     return g_shadeVariant;
 }
 void launchShade(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf) {
