@@ -189,3 +189,13 @@ def test_spec_constant_limits_are_rejected():
     c = scenes.Constants(env_samples_per_bounce=2)
     with pytest.raises(ValueError):
         m.SetSpecConstants(c)
+
+
+def test_library_tile_ownership_matches_python_mirror():
+    from moonshine_b200 import shard
+    sc = scenes.single_triangle(extent=(100, 70))
+    for world in (2, 3):
+        om = shard.owner_map(100, 70, world)
+        for rank in range(world):
+            img, _, _ = gpu_render(sc, 1, shard=(rank, world))
+            np.testing.assert_array_equal(img[..., 3] != 0, om == rank)
