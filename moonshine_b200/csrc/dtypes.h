@@ -115,6 +115,7 @@ struct PathBuffers {
     uint4* H;
     float4* Q0; float4* Q1;
     float4* result;        // per sample-slot final radiance
+    uint32_t* typeList;    // [NUM_BINS][P] queue slots binned by material type (4 = miss) by the trace kernel
     uint32_t capacity;     // P
 };
 
@@ -125,8 +126,12 @@ struct WaveState {
     uint32_t* shadeDone;       // finished-block counter of the shade kernel
     unsigned long long* rayCounts;  // [0] closest, [1] shadow
     uint32_t* maxBounce;
+    uint32_t* typeCount;       // [NUM_BINS] entries in typeList bins (reset by the shade kernel that consumes the bin)
+    uint32_t* binDone;         // [NUM_BINS] finished-block counters of the specialised shade kernels
 };
 
+static const uint32_t NUM_BINS = 5;   // MaterialType 0..3 + 4 = miss (and dead paths)
+static const uint32_t BIN_MISS = 4;
 static const uint32_t FLAG_DEAD = 0x80000000u;
 static const uint32_t FLAG_DELTA = 0x40000000u;
 static const uint32_t BOUNCE_MASK = 0x3FFFFFFFu;

@@ -86,32 +86,82 @@ __global__ void k_primary_probe(DCamera cam, DConstants k, uint32_t sample, floa
 // ------------------------------------------------------------------------------------------------
 // trace (persistent threads)
 // ------------------------------------------------------------------------------------------------
+// material type of a hit (MaterialType 0..3) or BIN_MISS: world.hlsl:61-71 lookups, done once here so the shade
+// pass can run one specialised kernel per type ("sorting rays by material id")
+DI uint32_t hitBin(const DeviceScene& sc, const HitRec& h) {
+    if (h.inst == MISS_ID) return BIN_MISS;
+    const uint32_t instanceID = __ldg(&sc.instances[h.inst].customIndex);
+    const uint32_t geom = __ldg(&sc.tris[h.tri].geom);
+    const uint32_t mat = __ldg(&sc.geometries[instanceID + geom].material);
+    return __ldg(&sc.materials[mat].type);
+}
+
+// Persistent-threads trace kernel with dynamic ray fetch. Each lane owns a resumable traversal (traverse.cuh
+// `Traversal`); when fewer than DYN_FETCH_MIN lanes of a warp are still walking the BVH, the warp leaves the
+// traversal loop, finished lanes write their results / bin their hit, and idle lanes take new rays from the
+// global ticket counter (ballot + popc compaction of the idle lanes, one atomic per refill).
+#ifndef DYN_FETCH_MIN
+#define DYN_FETCH_MIN 0   // 0 = off. Measured on cfg3: 12/20/24 were 10-18 % slower than off (profiles/r01_sweeps.md)
+#endif
 __global__ void __launch_bounds__(TRACE_THREADS, TRACE_BLOCKS_PER_SM) k_trace(DeviceScene sc, PathBuffers pb, WaveState ws, uint32_t buf) {
     const Counters cin = ws.counters[buf];
     const uint32_t nLive = cin.nLive, total = cin.nLive + cin.nShadow;
     const uint32_t lane = threadIdx.x & 31;
+    const uint32_t ltMask = (1u << lane) - 1u;
+    int stack[MSNE_STACK];
+    Traversal tv;
+    tv.node = REF_END;
+    bool active = false, more = sc.tlasNodes != nullptr || total > 0;
+    uint32_t idx = 0;
     for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(ws.traceTicket, 32u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base >= total) break;
-        const uint32_t idx = base + lane;
-        if (idx < total) {
-            if (idx < nLive) {
-                const float4 r0 = pb.R0[buf][idx], r1 = pb.R1[buf][idx];
-                HitRec h;
-                traceRay<false>(sc, mk3(r0.x, r0.y, r0.z), mk3(r1.x, r1.y, r1.z), 0.0f, MS_INFINITY, h);
-                pb.H[idx] = make_uint4(h.inst, h.tri, __float_as_uint(h.u), __float_as_uint(h.v));
-            } else {
-                const uint32_t si = idx - nLive;
-                const float4 q0 = pb.Q0[si], q1 = pb.Q1[si];
-                HitRec h;
-                if (traceRay<true>(sc, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), 0.0f, q0.w, h)) {
-                    const uint32_t target = __float_as_uint(q1.w);
-                    float4* n = (target & 1u) ? pb.N1[buf] : pb.N0[buf];
-                    n[target >> 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // ---- refill idle lanes -------------------------------------------------------------------------
+        const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !active);
+        if (more && idle) {
+            const uint32_t n = (uint32_t)__popc(idle);
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(ws.traceTicket, n);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            more = base + n < total;
+            if (!active) {
+                idx = base + (uint32_t)__popc(idle & ltMask);
+                if (idx < total) {
+                    active = true;
+                    if (idx < nLive) {
+                        const float4 r0 = pb.R0[buf][idx], r1 = pb.R1[buf][idx];
+                        tv.begin(sc, stack, mk3(r0.x, r0.y, r0.z), mk3(r1.x, r1.y, r1.z), 0.0f, MS_INFINITY);
+                    } else {
+                        const float4 q0 = pb.Q0[idx - nLive], q1 = pb.Q1[idx - nLive];
+                        tv.begin(sc, stack, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), 0.0f, q0.w);
+                        tv.target = __float_as_uint(q1.w);
+                    }
                 }
             }
+        }
+        if (__ballot_sync(0xFFFFFFFFu, active) == 0) break;
+        // ---- traverse ---------------------------------------------------------------------------------------
+        uint32_t bin = 0xFFu;
+        if (active) {
+            const bool anyHit = idx >= nLive;
+            const bool done = anyHit ? tv.template run<true>(sc, stack, more) : tv.template run<false>(sc, stack, more);
+            if (done) {
+                active = false;
+                if (!anyHit) {
+                    pb.H[idx] = make_uint4(tv.hit.inst, tv.hit.tri, __float_as_uint(tv.hit.u), __float_as_uint(tv.hit.v));
+                    bin = hitBin(sc, tv.hit);
+                } else if (tv.hit.inst != MISS_ID) {
+                    float4* n = (tv.target & 1u) ? pb.N1[buf] : pb.N0[buf];
+                    n[tv.target >> 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+        }
+        // ---- warp-level sort by material id: lanes with the same bin elect a leader that reserves their slots
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, bin);
+        if (bin != 0xFFu) {
+            const int leader = __ffs(peers) - 1;
+            uint32_t slot = 0;
+            if ((int)lane == leader) slot = atomicAdd(ws.typeCount + bin, (uint32_t)__popc(peers));
+            slot = __shfl_sync(peers, slot, leader) + __popc(peers & ltMask);
+            pb.typeList[(size_t)bin * pb.capacity + slot] = idx;
         }
     }
     // last block out: re-arm the ticket for the next launch and publish ray counts
@@ -153,6 +203,8 @@ struct ShadeOut {
     float4 envQ0, envQ1, meshQ0, meshQ1;   // Q1.w (target) filled in after the slot is known
 };
 
+// MT: -1 = any (runtime dispatch), 0..3 = MaterialType known at compile time, 4 = miss / dead paths only
+template <int MT>
 DI void shadeOne(const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, uint32_t buf, uint32_t q, ShadeOut& out, uint32_t& bounceOut) {
     const float4 R0 = pb.R0[buf][q], R1 = pb.R1[buf][q], S0 = pb.S0[buf][q], S1 = pb.S1[buf][q];
     const float4 N0 = pb.N0[buf][q], N1 = pb.N1[buf][q];
@@ -167,7 +219,9 @@ DI void shadeOne(const DeviceScene& sc, const DConstants& k, const PathBuffers& 
     acc = acc + mk3(N0.x, N0.y, N0.z);
     acc = acc + mk3(N1.x, N1.y, N1.z);
 
-    if (flags & FLAG_DEAD) { pb.result[slot] = make_float4(acc.x, acc.y, acc.z, 1.0f); return; }
+    if (MT < 0 || MT == (int)BIN_MISS) {
+        if (flags & FLAG_DEAD) { pb.result[slot] = make_float4(acc.x, acc.y, acc.z, 1.0f); return; }
+    }
 
     const float3 rayOrigin = mk3(R0.x, R0.y, R0.z), rayDir = mk3(R1.x, R1.y, R1.z);
     const float lastMaterialPdf = R0.w;
@@ -176,7 +230,7 @@ DI void shadeOne(const DeviceScene& sc, const DConstants& k, const PathBuffers& 
     Rng rng; rng.state = __float_as_uint(S0.w);
 
     const uint4 H = pb.H[q];
-    if (H.x == MISS_ID) {
+    if ((MT < 0 || MT == (int)BIN_MISS) && H.x == MISS_ID) {
         // integrator.hlsl:169-180
         if (k.env_samples == 0 || bounceCount == 0 || isLastMaterialDelta) {
             acc = acc + throughput * envIncomingRadiance(sc, rayDir);
@@ -191,6 +245,7 @@ DI void shadeOne(const DeviceScene& sc, const DConstants& k, const PathBuffers& 
         pb.result[slot] = make_float4(acc.x, acc.y, acc.z, 1.0f);
         return;
     }
+    if (MT == (int)BIN_MISS) return;   // the miss bin holds only misses and dead paths
 
     // decode hit (integrator.hlsl:82-88)
     const uint32_t instanceIndex = H.x;
@@ -204,7 +259,8 @@ DI void shadeOne(const DeviceScene& sc, const DConstants& k, const PathBuffers& 
     const DMaterial dm = sc.materials[geometry.material];
     const Frame textureFrame = getTextureFrame(sc, k, dm, attrs.texcoord, attrs.frame);
     const float3 emissiveLight = xyz(sampleTexture(sc, dm.emissive, attrs.texcoord));
-    const MaterialParams material = loadMaterial(sc, dm, attrs.texcoord);
+    MaterialParams material = loadMaterial(sc, dm, attrs.texcoord);
+    if (MT >= 0) material.type = (uint32_t)MT;   // compile-time constant: the other variants' code is pruned
 
     const float3 outgoingDirWs = -rayDir;
 
@@ -323,12 +379,18 @@ DI void shadeOne(const DeviceScene& sc, const DConstants& k, const PathBuffers& 
     out.S0 = make_float4(throughput.x, throughput.y, throughput.z, __uint_as_float(rng.state));
 }
 
-template <int MIN_BLOCKS>
-__global__ void __launch_bounds__(SHADE_THREADS, MIN_BLOCKS) k_shade(DeviceScene sc, DConstants k, PathBuffers pb, WaveState ws, uint32_t buf) {
+// Shared body of the shade kernels. BIN = -1: every queue slot [0, nLive) + the dead range, any material (used for
+// small queues, one launch per bounce). BIN = 0..4: only the slots the trace kernel binned under that material type
+// (4 = misses + the dead range); five such launches cover a bounce with material-specialised, convergent code.
+template <int BIN, int MIN_BLOCKS>
+__global__ void __launch_bounds__(SHADE_THREADS, MIN_BLOCKS) k_shade(DeviceScene sc, DConstants k, PathBuffers pb, WaveState ws, uint32_t buf, uint32_t lastOfBounce) {
     const Counters cin = ws.counters[buf];
     Counters* cout = ws.counters + (buf ^ 1u);
-    const uint32_t nLive = cin.nLive, total = cin.nLive + cin.nDead;
     const uint32_t P = pb.capacity;
+    const uint32_t nList = BIN < 0 ? cin.nLive : ws.typeCount[BIN];
+    const uint32_t nDeadHere = (BIN < 0 || BIN == (int)BIN_MISS) ? cin.nDead : 0u;
+    const uint32_t total = nList + nDeadHere;
+    const uint32_t* list = BIN < 0 ? nullptr : pb.typeList + (size_t)BIN * P;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t ltMask = (1u << lane) - 1u;
     const uint32_t ob = buf ^ 1u;
@@ -340,9 +402,9 @@ __global__ void __launch_bounds__(SHADE_THREADS, MIN_BLOCKS) k_shade(DeviceScene
         ShadeOut out;
         out.kind = 0; out.envRay = false; out.meshRay = false;
         if (i < total) {
-            const uint32_t q = i < nLive ? i : (P - 1u - (i - nLive));
+            const uint32_t q = i < nList ? (BIN < 0 ? i : __ldg(list + i)) : (P - 1u - (i - nList));
             uint32_t b;
-            shadeOne(sc, k, pb, buf, q, out, b);
+            shadeOne<BIN>(sc, k, pb, buf, q, out, b);
             localMaxBounce = max(localMaxBounce, b);
         }
         // ---- warp-ballot compaction into the other ping-pong buffer -----------------------------
@@ -375,15 +437,18 @@ __global__ void __launch_bounds__(SHADE_THREADS, MIN_BLOCKS) k_shade(DeviceScene
             }
         }
     }
-    // last block out: clear the consumed counters, publish the deepest bounce seen
+    // last block out: clear what this launch consumed, publish the deepest bounce seen
     if (localMaxBounce) atomicMax(ws.maxBounce, localMaxBounce);
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        const uint32_t done = atomicAdd(ws.shadeDone, 1u);
+        uint32_t* doneCtr = BIN < 0 ? ws.shadeDone : ws.binDone + BIN;
+        const uint32_t done = atomicAdd(doneCtr, 1u);
         if (done == gridDim.x - 1) {
-            ws.counters[buf].nLive = 0; ws.counters[buf].nDead = 0; ws.counters[buf].nShadow = 0;
-            *ws.shadeDone = 0;
+            if (BIN < 0) { for (uint32_t b = 0; b < NUM_BINS; b++) ws.typeCount[b] = 0; }
+            else ws.typeCount[BIN] = 0;
+            if (lastOfBounce) { ws.counters[buf].nLive = 0; ws.counters[buf].nDead = 0; ws.counters[buf].nShadow = 0; }
+            *doneCtr = 0;
             __threadfence();
         }
     }
@@ -470,19 +535,21 @@ void launchGenerate(cudaStream_t st, const DCamera& cam, const DConstants& k, co
 void launchTrace(cudaStream_t st, int blocks, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf) {
     k_trace<<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf);
 }
-static int g_shadeVariant = -1;
-static int shadeVariant() {
-    // default 6 = 80 registers, 6 blocks/SM: measured best (profiles/r01_sweeps.md)
-    if (g_shadeVariant < 0) { const char* e = getenv("MSNE_SHADE_MINB"); g_shadeVariant = e ? atoi(e) : 6; }
-    return g_shadeVariant;
-}
+// Register caps (measured, profiles/r01_sweeps.md): the all-material kernel runs best at 80 registers
+// (6 blocks/SM); the specialised kernels are smaller and take the same cap.
+#ifndef SHADE_MINB
+#define SHADE_MINB 6
+#endif
 void launchShade(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf) {
-    switch (shadeVariant()) {
-        case 4: k_shade<4><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf); break;
-        case 5: k_shade<5><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf); break;
-        case 6: k_shade<6><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf); break;
-        default: k_shade<3><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf); break;
-    }
+    k_shade<-1, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, 1u);
+}
+// one launch per material bin; the miss/dead bin goes last and clears the bounce's counters
+void launchShadeBinned(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf) {
+    k_shade<3, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, 0u);   // StandardPBR
+    k_shade<1, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, 0u);   // Lambert
+    k_shade<0, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, 0u);   // Glass
+    k_shade<2, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, 0u);   // PerfectMirror
+    k_shade<4, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, 1u);   // miss + dead
 }
 void launchAccumulate(cudaStream_t st, const float4* result, float4* image, float4* runState, const uint32_t* pixIds, uint32_t nPix, uint32_t nSamples,
                       uint32_t firstSample, uint32_t spr) {
@@ -509,12 +576,7 @@ int traceOccupancyBlocksPerSm() {
 }
 int shadeOccupancyBlocksPerSm() {
     int n = 0;
-    switch (shadeVariant()) {
-        case 4: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade<4>, SHADE_THREADS, 0); break;
-        case 5: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade<5>, SHADE_THREADS, 0); break;
-        case 6: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade<6>, SHADE_THREADS, 0); break;
-        default: cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade<3>, SHADE_THREADS, 0); break;
-    }
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade<-1, SHADE_MINB>, SHADE_THREADS, 0);
     return n;
 }
 

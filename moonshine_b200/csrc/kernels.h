@@ -9,7 +9,7 @@ namespace msne {
 #define TRACE_THREADS 128
 #endif
 #ifndef TRACE_BLOCKS_PER_SM
-#define TRACE_BLOCKS_PER_SM 4
+#define TRACE_BLOCKS_PER_SM 8   // 64 registers: measured best (profiles/r01_sweeps.md)
 #endif
 #ifndef SHADE_THREADS
 #define SHADE_THREADS 128
@@ -19,6 +19,7 @@ void launchGenerate(cudaStream_t st, const DCamera& cam, const DConstants& k, co
                     uint32_t nPix, uint32_t nSamples, uint32_t firstSample);
 void launchTrace(cudaStream_t st, int blocks, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf);
 void launchShade(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf);
+void launchShadeBinned(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf);
 void launchAccumulate(cudaStream_t st, const float4* result, float4* image, float4* runState, const uint32_t* pixIds, uint32_t nPix, uint32_t nSamples,
                       uint32_t firstSample, uint32_t spr);
 void launchEnvResample(cudaStream_t st, const float4* src, uint32_t W, uint32_t H, float4* dstRgb, float* dstLum, uint32_t S);

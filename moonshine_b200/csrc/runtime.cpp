@@ -209,12 +209,14 @@ struct HdMoonshine {
     std::vector<DevBuf<float4>> poolBufs;
     DevBuf<uint4> poolH;
     DevBuf<Counters> dCounters;
-    DevBuf<uint32_t> dScalars;       // [0] traceTicket [1] traceDone [2] shadeDone [3] maxBounce
+    DevBuf<uint32_t> dScalars;       // [0] traceTicket [1] traceDone [2] shadeDone [3] maxBounce [4..8] typeCount [9..13] binDone
+    DevBuf<uint32_t> poolTypeList;
     DevBuf<unsigned long long> dRayCounts;
     Counters* hostCounters = nullptr;   // pinned ring of 4
     cudaEvent_t bounceEvents[4]{};
     cudaEvent_t evStart = nullptr, evStop = nullptr;
     int traceBlocks = 0, shadeBlocks = 0;
+    uint64_t binnedThreshold = 262144;   // survivors below this use the single generic shade launch
 
     // profiling
     bool profiling = false;
@@ -234,9 +236,9 @@ struct HdMoonshine {
         CK(cudaEventCreate(&evStart)); CK(cudaEventCreate(&evStop));
         for (auto& p : profEv) { CK(cudaEventCreate(&p[0])); CK(cudaEventCreate(&p[1])); }
         CK(cudaMallocHost((void**)&hostCounters, 4 * sizeof(Counters)));
-        dCounters.alloc(2); dScalars.alloc(4); dRayCounts.alloc(2);
+        dCounters.alloc(2); dScalars.alloc(16); dRayCounts.alloc(2);
         CK(cudaMemsetAsync(dCounters.p, 0, 2 * sizeof(Counters), stream));
-        CK(cudaMemsetAsync(dScalars.p, 0, 4 * sizeof(uint32_t), stream));
+        CK(cudaMemsetAsync(dScalars.p, 0, 16 * sizeof(uint32_t), stream));
         CK(cudaMemsetAsync(dRayCounts.p, 0, 2 * sizeof(unsigned long long), stream));
         float lut[256];
         for (int i = 0; i < 256; i++) lut[i] = srgbToLinear(i);
@@ -546,16 +548,17 @@ struct HdMoonshine {
         poolBufs[12].alloc((size_t)2 * P); poolBufs[13].alloc((size_t)2 * P);
         poolBufs[14].alloc(P);
         poolH.alloc(P);
+        poolTypeList.alloc((size_t)NUM_BINS * P);
         for (int b = 0; b < 2; b++) {
             pb.R0[b] = poolBufs[0 + b].p; pb.R1[b] = poolBufs[2 + b].p; pb.S0[b] = poolBufs[4 + b].p; pb.S1[b] = poolBufs[6 + b].p;
             pb.N0[b] = poolBufs[8 + b].p; pb.N1[b] = poolBufs[10 + b].p;
         }
-        pb.Q0 = poolBufs[12].p; pb.Q1 = poolBufs[13].p; pb.result = poolBufs[14].p; pb.H = poolH.p; pb.capacity = P;
+        pb.Q0 = poolBufs[12].p; pb.Q1 = poolBufs[13].p; pb.result = poolBufs[14].p; pb.H = poolH.p; pb.typeList = poolTypeList.p; pb.capacity = P;
     }
     WaveState waveState() const {
         WaveState ws{};
         ws.counters = dCounters.p; ws.traceTicket = dScalars.p + 0; ws.traceDone = dScalars.p + 1; ws.shadeDone = dScalars.p + 2;
-        ws.maxBounce = dScalars.p + 3; ws.rayCounts = dRayCounts.p;
+        ws.maxBounce = dScalars.p + 3; ws.rayCounts = dRayCounts.p; ws.typeCount = dScalars.p + 4; ws.binDone = dScalars.p + 9;
         return ws;
     }
 
@@ -565,14 +568,16 @@ struct HdMoonshine {
         launchGenerate(stream, cam, k, pb, dCounters.p, s.pixIds.p + pixOffset, nPix, nSamples, firstSample);
         stats.kernel_launches++;
         int profUsed = 0;
+        uint64_t lastLive = (uint64_t)nPix * nSamples;   // most recent survivor count known to the host
         auto enqueueBounce = [&](uint32_t b) {
             const uint32_t buf = b & 1u;
             const bool prof = profiling && profUsed < kProfEvents;
             if (prof) CK(cudaEventRecord(profEv[profUsed][0], stream));
             launchTrace(stream, traceBlocks, sc, pb, ws, buf);
             if (prof) { CK(cudaEventRecord(profEv[profUsed][1], stream)); profUsed++; }
-            launchShade(stream, shadeBlocks, sc, k, pb, ws, buf);
-            stats.kernel_launches += 2;
+            // big queues: one material-specialised launch per bin; small queues (tail): one generic launch
+            if (lastLive >= binnedThreshold) { launchShadeBinned(stream, shadeBlocks, sc, k, pb, ws, buf); stats.kernel_launches += 6; }
+            else { launchShade(stream, shadeBlocks, sc, k, pb, ws, buf); stats.kernel_launches += 2; }
             CK(cudaMemcpyAsync(&hostCounters[b & 3u], dCounters.p + (buf ^ 1u), sizeof(Counters), cudaMemcpyDeviceToHost, stream));
             CK(cudaEventRecord(bounceEvents[b & 3u], stream));
         };
@@ -583,6 +588,7 @@ struct HdMoonshine {
             enqueueBounce(b + 1);
             CK(cudaEventSynchronize(bounceEvents[b & 3u]));
             const Counters c = hostCounters[b & 3u];
+            lastLive = c.nLive;
             if (c.nLive + c.nDead == 0) break;   // bounce b+1 then runs on empty queues
         }
         launchAccumulate(stream, pb.result, s.image.p, s.runState.p + pixOffset, s.pixIds.p + pixOffset, nPix, nSamples, firstSample, k.samples_per_run);
@@ -899,6 +905,7 @@ void HdMoonshineExtResetStats(HdMoonshine* h) {
     ABORT_ON_THROW(
         h->use();
         h->stats = MsneStats{};
+        if (const char* e = getenv("MSNE_BINNED_THRESHOLD")) h->binnedThreshold = strtoull(e, nullptr, 10);
         CK(cudaMemsetAsync(h->dRayCounts.p, 0, 2 * sizeof(unsigned long long), h->stream));
         CK(cudaMemsetAsync(h->dScalars.p + 3, 0, sizeof(uint32_t), h->stream));
         CK(cudaStreamSynchronize(h->stream));

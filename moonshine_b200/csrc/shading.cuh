@@ -41,17 +41,27 @@ DI int wrapMirror(int i, int n) {
 }
 DI float4 lerp4(float4 a, float4 b, float t) { return make_float4(a.x + t * (b.x - a.x), a.y + t * (b.y - a.y), a.z + t * (b.z - a.z), a.w + t * (b.w - a.w)); }
 
-// dTextures[idx].SampleLevel(dTextureSampler, uv, 0)
-DI float4 sampleTexture(const DeviceScene& sc, uint32_t idx, float2 uv) {
-    const DTexture t = sc.textures[idx];
+// dTextures[idx].SampleLevel(dTextureSampler, uv, 0).
+// Deliberately NOT inlined: it is used ~6x per hit and each copy carries five 7-way format switches; inlined,
+// k_shade was 189 KB of SASS and stalled on instruction fetch (profiles/r01b). Arguments/return are scalars in
+// registers, so the call costs no local-memory traffic.
+#ifndef MSNE_INLINE_TEX
+__device__ __noinline__
+#else
+DI
+#endif
+float4 sampleTextureImpl(const DTexture* __restrict__ textures, const float* __restrict__ srgbLut, uint32_t idx, float u_, float v_) {
+    DeviceScene sc; sc.srgbLut = srgbLut;
+    const DTexture t = textures[idx];
     if (t.w == 1 && t.h == 1) return fetchTexel(sc, t, 0, 0);
-    const float u = uv.x * (float)t.w - 0.5f, v = uv.y * (float)t.h - 0.5f;
+    const float u = u_ * (float)t.w - 0.5f, v = v_ * (float)t.h - 0.5f;
     const float fu = floorf(u), fv = floorf(v);
     const float a = u - fu, b = v - fv;
     const int i0 = wrapRepeat((int)fu, t.w), i1 = wrapRepeat((int)fu + 1, t.w), j0 = wrapRepeat((int)fv, t.h), j1 = wrapRepeat((int)fv + 1, t.h);
     const float4 t00 = fetchTexel(sc, t, i0, j0), t10 = fetchTexel(sc, t, i1, j0), t01 = fetchTexel(sc, t, i0, j1), t11 = fetchTexel(sc, t, i1, j1);
     return lerp4(lerp4(t00, t10, a), lerp4(t01, t11, a), b);
 }
+DI float4 sampleTexture(const DeviceScene& sc, uint32_t idx, float2 uv) { return sampleTextureImpl(sc.textures, sc.srgbLut, idx, uv.x, uv.y); }
 
 // ---- reflection_frame.hlsl:3-85 ------------------------------------------------------------------
 struct Frame {

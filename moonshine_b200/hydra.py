@@ -15,7 +15,7 @@ from typing import Optional, Sequence, Tuple
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libmoonshine.so")
+LIB_PATH = os.environ.get("MSNE_LIB", os.path.join(_PKG, "libmoonshine.so"))  # MSNE_LIB: tuning builds (tools/)
 _LIB = None
 
 
