@@ -617,3 +617,50 @@ def bathroom(extent=(1920, 1080), detail: float = 1.0, seed: int = 0x4D4F4F4E) -
     s.lens = Lens((0.35, 0.55, 1.55), tuple(fw / np.linalg.norm(fw)), (0, 0, 1), math.radians(58), 0.0, 1.0)
     s.constants = Constants()
     return s
+
+
+# ---------------------------------------------------------------------------------------------
+# cfg5: instanced mesh-light stress scene: n_side^2 emissive 20-triangle icosahedra sharing
+# one BLAS (all `sampled`, per-instance jittered transform, seed 7) + ground plane + 64 occluders, black env.
+# n_side = 1000 is the BASELINE config (10^6 instances, 2*10^7 alias-table entries = 400 MB).
+# ---------------------------------------------------------------------------------------------
+def mesh_light_stress(n_side: int = 1000, extent=(2048, 2048), seed: int = 7) -> Scene:
+    s = Scene(f"cfg5-mesh-light-stress-{n_side}x{n_side}", extent=extent)
+    rs = np.random.RandomState(seed)
+    flat, black = s.solid2(0.5, 0.5), s.solid3(0, 0, 0)
+    m_ground = s.add_material(type=MAT_LAMBERT, normal=flat, emissive=black, color=s.solid3(0.6, 0.6, 0.6))
+    m_light = s.add_material(type=MAT_LAMBERT, normal=flat, emissive=s.solid3(6.0, 5.0, 4.0), color=s.solid3(0.3, 0.3, 0.3))
+    m_occ = [s.add_material(type=MAT_LAMBERT, normal=flat, emissive=black, color=s.solid3(0.7, 0.35, 0.25)),
+             s.add_material(type=MAT_STANDARD_PBR, normal=flat, emissive=black, color=s.solid3(0.85, 0.85, 0.9), metalness=s.solid1(1.0), roughness=s.solid1(0.25), ior=1.5)]
+    size = float(n_side)
+    gp, gi = _quad((0, 0, 0), (size, 0, 0), (size, size, 0), (0, size, 0))
+    s.add_instance([(s.add_mesh(gp, gi), m_ground, False)])
+    ip, ii = icosphere(0)
+    ico = s.add_mesh(ip, ii)
+    # per-instance jittered transform: uniform scale 0.12..0.22, rotation about z, position jitter, height 0.5..1.5
+    ang = rs.rand(n_side * n_side) * 2 * math.pi
+    sc_ = 0.12 + 0.10 * rs.rand(n_side * n_side)
+    jx, jy = rs.rand(n_side * n_side) * 0.5 - 0.25, rs.rand(n_side * n_side) * 0.5 - 0.25
+    hz = 0.5 + rs.rand(n_side * n_side)
+    gx, gy = np.meshgrid(np.arange(n_side), np.arange(n_side))
+    cx, cy = gx.reshape(-1) + 0.5 + jx, gy.reshape(-1) + 0.5 + jy
+    c, sn = np.cos(ang) * sc_, np.sin(ang) * sc_
+    T = np.zeros((n_side * n_side, 3, 4), np.float32)
+    T[:, 0, 0], T[:, 0, 1], T[:, 0, 3] = c, -sn, cx
+    T[:, 1, 0], T[:, 1, 1], T[:, 1, 3] = sn, c, cy
+    T[:, 2, 2], T[:, 2, 3] = sc_, hz
+    geom = [(ico, m_light, True)]
+    for k in range(n_side * n_side):
+        s.instances.append(Instance(T[k], geom, True))
+    # 64 occluders: boxes scattered over the field
+    for k in range(64):
+        x0, y0 = rs.rand(2) * (size - 2.0) + 0.5
+        w, d, h = 0.3 + rs.rand() * min(2.0, size / 8), 0.3 + rs.rand() * min(2.0, size / 8), 0.8 + rs.rand() * 1.5
+        bp, bi = _box((x0, y0, 0.0), (x0 + w, y0 + d, h), rot_z=rs.rand() * 1.5)
+        s.add_instance([(s.add_mesh(bp, bi), m_occ[k % 2], False)])
+    s.background = np.array([[[0, 0, 0, 1]]], np.float32)
+    ctr = size / 2
+    view = min(size, 40.0)
+    s.lens = Lens((ctr - 0.6 * view, ctr - 0.6 * view, 0.45 * view), tuple(np.array([0.6, 0.6, -0.52]) / np.linalg.norm([0.6, 0.6, -0.52])), (0, 0, 1), math.radians(55), 0.0, 1.0)
+    s.constants = Constants()
+    return s

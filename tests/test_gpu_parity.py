@@ -199,3 +199,46 @@ def test_library_tile_ownership_matches_python_mirror():
         for rank in range(world):
             img, _, _ = gpu_render(sc, 1, shard=(rank, world))
             np.testing.assert_array_equal(img[..., 3] != 0, om == rank)
+
+
+def test_cfg5_instanced_mesh_lights_parity():
+    """cfg5 at reduced instance count: 576 transformed instances sharing one BLAS, all sampled emitters."""
+    sc = scenes.mesh_light_stress(24, (128, 128))
+    m, o = _pair(sc)
+    g_tab, r_tab = m.alias_table(), o.alias_table()
+    assert len(g_tab) == 1 + 576 * 20
+    np.testing.assert_array_equal(g_tab.view(np.uint32), r_tab.view(np.uint32))
+    rays = random_rays(9, 20000, np.array([12.0, 12.0, 1.0]), 3.0)
+    g, r = m.trace(rays), o.trace(rays)
+    np.testing.assert_array_equal(g["instance"], r["instance"])
+    hit = r["instance"] != 0xFFFFFFFF
+    assert hit.mean() > 0.2
+    np.testing.assert_array_equal(g["primitive"][hit], r["primitive"][hit])
+    np.testing.assert_array_equal(g["u"][hit].view(np.uint32), r["u"][hit].view(np.uint32))
+    gi, stats, _ = gpu_render(sc, 1)
+    ri, counts, _ = oracle_render(sc, 1)
+    assert within_tol_fraction(gi, ri) >= 0.998
+    assert abs(int(stats.rays_closest) - int(counts[0])) <= max(4, counts[0] * 2e-3)
+
+
+def test_cfg3_bathroom_reduced_parity():
+    """cfg3 generator at reduced tessellation/texture size: textured GGX, glass, mirror, sun+sky env, emitter."""
+    sc = scenes.bathroom((160, 90), detail=0.03)
+    g, stats, _ = gpu_render(sc, 1)
+    r, counts, _ = oracle_render(sc, 1)
+    assert within_tol_fraction(g, r) >= 0.995
+    assert abs(int(stats.rays_closest) - int(counts[0])) <= max(8, counts[0] * 3e-3)
+    assert np.isfinite(g).all()
+
+
+def test_cfg3_full_size_properties():
+    """BASELINE size (1.4 M triangles, 1920x1080): properties that do not need the oracle."""
+    sc = scenes.bathroom()
+    a, sa, _ = gpu_render(sc, 2)
+    assert a.shape == (1080, 1920, 4) and np.isfinite(a).all()
+    np.testing.assert_array_equal(a[..., 3], 2.0)                     # alpha counts launches
+    assert sa.samples == 2 * 1920 * 1080 and sa.rays_closest >= sa.samples
+    assert (a[..., :3] >= 0).all()
+    b, sb, _ = gpu_render(sc, 2, paths_in_flight=1 << 20)              # 2 pixel chunks x 2 waves instead of 1 wave
+    np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert (sa.rays_closest, sa.rays_shadow) == (sb.rays_closest, sb.rays_shadow)
