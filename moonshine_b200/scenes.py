@@ -315,7 +315,7 @@ def uv_sphere(nu: int, nv: int, radius=1.0, center=(0, 0, 0)):
     return p, np.array(idx, np.uint32), n, t
 
 
-def procedural_sky(width: int, height: int, sun_dir=(0.3, 0.4, 0.8), sun_power=200.0, seed=0x4D4F4F4E) -> np.ndarray:
+def procedural_sky(width: int, height: int, sun_dir=(0.3, 0.4, 0.8), sun_power=200.0, seed=0x4D4F4F4E, sharpness=400.0) -> np.ndarray:
     """Equirectangular RGBA32F sky: gradient + sun lobe; row = theta in [0,pi] from +Z, column = phi."""
     phi = (np.arange(width, dtype=np.float64) + 0.5) / width * 2 * math.pi
     theta = (np.arange(height, dtype=np.float64) + 0.5) / height * math.pi
@@ -328,7 +328,7 @@ def procedural_sky(width: int, height: int, sun_dir=(0.3, 0.4, 0.8), sun_power=2
     sky = np.stack([0.25 + 0.35 * (1 - up), 0.35 + 0.35 * (1 - up), 0.6 + 0.3 * up], -1)
     ground = np.array([0.08, 0.07, 0.06])
     col = np.where(d[..., 2:3] >= 0, sky, ground)
-    col = col + sun_power * np.exp((cosang[..., None] - 1.0) * 400.0) * np.array([1.0, 0.9, 0.75])
+    col = col + sun_power * np.exp((cosang[..., None] - 1.0) * sharpness) * np.array([1.0, 0.9, 0.75])
     out = np.ones((height, width, 4), np.float32)
     out[..., :3] = col.astype(np.float32)
     return out
