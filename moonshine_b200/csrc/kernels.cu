@@ -455,6 +455,70 @@ __global__ void __launch_bounds__(SHADE_THREADS, MIN_BLOCKS) k_shade(DeviceScene
 }
 
 // ------------------------------------------------------------------------------------------------
+// tail: once only a few thousand paths survive, every further bounce costs two launches at the latency floor of
+// a single warp (~0.25 ms, ~130 times per wave with max_bounces = 1024). k_tail finishes those stragglers in ONE
+// launch: each thread owns a queue slot and alternates shadeOne / shadow rays / closest hit in place until its
+// path ends. Same device functions, same per-path order of operations -> bit-identical results.
+// Precondition: k_trace has just run on `buf` (H holds this bounce's hits, pending shadow rays are resolved).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_tail(DeviceScene sc, DConstants k, PathBuffers pb, WaveState ws, uint32_t buf) {
+    const Counters cin = ws.counters[buf];
+    const uint32_t nLive = cin.nLive, total = cin.nLive + cin.nDead, P = pb.capacity;
+    unsigned long long nClosest = 0, nShadow = 0;
+    uint32_t localMaxBounce = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t q = i < nLive ? i : (P - 1u - (i - nLive));
+        for (;;) {
+            ShadeOut out;
+            out.kind = 0; out.envRay = false; out.meshRay = false;
+            uint32_t b;
+            shadeOne<-1>(sc, k, pb, buf, q, out, b);
+            localMaxBounce = max(localMaxBounce, b);
+            if (out.kind == 0) break;
+            HitRec h;
+            if (out.envRay) {
+                nShadow++;
+                if (traceRay<true>(sc, mk3(out.envQ0.x, out.envQ0.y, out.envQ0.z), mk3(out.envQ1.x, out.envQ1.y, out.envQ1.z), 0.0f, out.envQ0.w, h))
+                    out.N0 = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if (out.meshRay) {
+                nShadow++;
+                if (traceRay<true>(sc, mk3(out.meshQ0.x, out.meshQ0.y, out.meshQ0.z), mk3(out.meshQ1.x, out.meshQ1.y, out.meshQ1.z), 0.0f, out.meshQ0.w, h))
+                    out.N1 = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            pb.R0[buf][q] = out.R0; pb.R1[buf][q] = out.R1; pb.S0[buf][q] = out.S0; pb.S1[buf][q] = out.S1;
+            pb.N0[buf][q] = out.N0; pb.N1[buf][q] = out.N1;
+            if (out.kind == 1) {
+                nClosest++;
+                traceRay<false>(sc, mk3(out.R0.x, out.R0.y, out.R0.z), mk3(out.R1.x, out.R1.y, out.R1.z), 0.0f, MS_INFINITY, h);
+                pb.H[q] = make_uint4(h.inst, h.tri, __float_as_uint(h.u), __float_as_uint(h.v));
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        nClosest += __shfl_down_sync(0xFFFFFFFFu, nClosest, o);
+        nShadow += __shfl_down_sync(0xFFFFFFFFu, nShadow, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (nClosest) atomicAdd(ws.rayCounts + 0, nClosest);
+        if (nShadow) atomicAdd(ws.rayCounts + 1, nShadow);
+    }
+    if (localMaxBounce) atomicMax(ws.maxBounce, localMaxBounce);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const uint32_t done = atomicAdd(ws.shadeDone, 1u);
+        if (done == gridDim.x - 1) {
+            for (uint32_t b = 0; b < NUM_BINS; b++) ws.typeCount[b] = 0;
+            ws.counters[0].nLive = 0; ws.counters[0].nDead = 0; ws.counters[0].nShadow = 0;
+            ws.counters[1].nLive = 0; ws.counters[1].nDead = 0; ws.counters[1].nShadow = 0;
+            *ws.shadeDone = 0;
+            __threadfence();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // accumulate: raygen's sample loop sum + storeColor (main.hlsl:79-94, :43-51), in sample-index order
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_accumulate(const float4* __restrict__ result, float4* image, float4* runState, const uint32_t* __restrict__ pixIds,
@@ -550,6 +614,9 @@ void launchShadeBinned(cudaStream_t st, int blocks, const DeviceScene& sc, const
     k_shade<0, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, 0u);   // Glass
     k_shade<2, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, 0u);   // PerfectMirror
     k_shade<4, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, 1u);   // miss + dead
+}
+void launchTail(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf) {
+    k_tail<<<blocks, 128, 0, st>>>(sc, k, pb, ws, buf);
 }
 void launchAccumulate(cudaStream_t st, const float4* result, float4* image, float4* runState, const uint32_t* pixIds, uint32_t nPix, uint32_t nSamples,
                       uint32_t firstSample, uint32_t spr) {

@@ -216,6 +216,8 @@ struct HdMoonshine {
     cudaEvent_t bounceEvents[4]{};
     cudaEvent_t evStart = nullptr, evStop = nullptr;
     int traceBlocks = 0, shadeBlocks = 0;
+    uint32_t maxLeaf = 3;   // triangles per BVH leaf (<= 8: 3-bit count in the leaf reference); 2-3 measured best
+    uint64_t tailThreshold = 32768;   // survivors below this are finished by k_tail (0 = never)
     uint64_t binnedThreshold = 262144;   // survivors below this use the single generic shade launch
 
     // profiling
@@ -248,6 +250,8 @@ struct HdMoonshine {
         consts = MsneSpecConstants{1, 1024, 0, 0, 0, 0, 0};
         const float white[4] = {1, 1, 1, 1};
         setBackground(white, 1, 1);   // addDefaultBackground (BackgroundManager.zig:116-126)
+        if (const char* e = getenv("MSNE_MAX_LEAF")) maxLeaf = (uint32_t)std::min(8, std::max(1, atoi(e)));
+        if (const char* e = getenv("MSNE_TAIL_THRESHOLD")) tailThreshold = strtoull(e, nullptr, 10);
         traceBlocks = smCount * std::max(1, traceOccupancyBlocksPerSm());
         shadeBlocks = smCount * std::max(1, shadeOccupancyBlocksPerSm());
         CK(cudaStreamSynchronize(stream));
@@ -328,7 +332,7 @@ struct HdMoonshine {
         std::vector<TriRec> tris;
         for (uint32_t g = 0; g < key.size(); g++) meshTriangles(*meshes[key[g]], g, 0, tris, boxes);
         BuiltBvh bvh;
-        buildBvh2(boxes.data(), (uint32_t)boxes.size(), 4, bvh);
+        buildBvh2(boxes.data(), (uint32_t)boxes.size(), maxLeaf, bvh);
         Blas b; b.rootNode = appendBlas(bvh, tris); b.bounds = bvh.bounds;
         blases.push_back(b);
         const uint32_t id = (uint32_t)blases.size() - 1;
@@ -360,7 +364,7 @@ struct HdMoonshine {
         st.isStatic = 1; st.visible = 1;
         if (!stTris.empty()) {
             BuiltBvh bvh;
-            buildBvh2(stBoxes.data(), (uint32_t)stBoxes.size(), 4, bvh);
+            buildBvh2(stBoxes.data(), (uint32_t)stBoxes.size(), maxLeaf, bvh);
             st.blasRoot = appendBlas(bvh, stTris);
             boxes.push_back(bvh.bounds); items.push_back(nInst);
         }
@@ -590,6 +594,15 @@ struct HdMoonshine {
             const Counters c = hostCounters[b & 3u];
             lastLive = c.nLive;
             if (c.nLive + c.nDead == 0) break;   // bounce b+1 then runs on empty queues
+            if ((uint64_t)c.nLive + c.nDead < tailThreshold) {
+                // few stragglers left: after the already-queued bounce b+1, trace once more and let k_tail finish
+                // every remaining path in a single launch instead of ~130 launch pairs at the latency floor
+                const uint32_t tb = (b + 2) & 1u;
+                launchTrace(stream, traceBlocks, sc, pb, ws, tb);
+                launchTail(stream, smCount * 4, sc, k, pb, ws, tb);
+                stats.kernel_launches += 2;
+                break;
+            }
         }
         launchAccumulate(stream, pb.result, s.image.p, s.runState.p + pixOffset, s.pixIds.p + pixOffset, nPix, nSamples, firstSample, k.samples_per_run);
         stats.kernel_launches++;
