@@ -337,17 +337,28 @@ DI float3 envRgbLoad(const DeviceScene& sc, uint32_t x, uint32_t y) {
     return xyz(__ldg(reinterpret_cast<const float4*>(sc.envRgb) + (size_t)y * sc.envSize + x));
 }
 struct LightSample { float3 dirWs, radiance; float pdf; };
-// EnvMap::sample without the shadow ray (light.hlsl:47-73)
+// EnvMap::sample without the shadow ray (light.hlsl:47-73).
+// Two value-preserving shortcuts relative to the literal loop (bit-exact, checked against the oracle's literal one):
+//  * the first iteration runs at the 1x1 mip where the (1,0),(0,1),(1,1) loads are out of bounds and return 0
+//    (SURVEY 8a hazard): p = 0/(L+0) = 0, coinFlipRemap(0, r) leaves idx at 0 and maps r -> (r-0)/(1-0) = r exactly,
+//    so it is skipped (when L == 0 it yields NaN just like the literal loop: 0/0 one level further down);
+//  * probs_y are two of the four texels already loaded for probs_x, so they are not fetched again.
+// Below the top level idx+1 is always in range, so no bounds checks are needed.
 DI LightSample envSample(const DeviceScene& sc, float2 rand) {
     const uint32_t size = sc.envSize, mipCount = sc.envLevels;
     uint32_t ix = 0, iy = 0;
-    for (uint32_t level = mipCount; level-- > 0;) {
+    for (uint32_t level = mipCount - 1; level-- > 0;) {
         ix *= 2; iy *= 2;
-        const float px0 = envLumLoad(sc, ix + 0, iy + 0, level) + envLumLoad(sc, ix + 0, iy + 1, level);
-        const float px1 = envLumLoad(sc, ix + 1, iy + 0, level) + envLumLoad(sc, ix + 1, iy + 1, level);
-        ix += coinFlipRemap(px1 / (px0 + px1), rand.x) ? 1u : 0u;
-        const float py0 = envLumLoad(sc, ix, iy + 0, level);
-        const float py1 = envLumLoad(sc, ix, iy + 1, level);
+        const uint32_t sz = size >> level;
+        const float* mip = sc.envLum + sc.envLevelOffset[level];
+        const float l00 = __ldg(mip + (size_t)iy * sz + ix), l10 = __ldg(mip + (size_t)iy * sz + ix + 1);
+        const float l01 = __ldg(mip + (size_t)(iy + 1) * sz + ix), l11 = __ldg(mip + (size_t)(iy + 1) * sz + ix + 1);
+        const float px0 = l00 + l01;
+        const float px1 = l10 + l11;
+        const bool right = coinFlipRemap(px1 / (px0 + px1), rand.x);
+        ix += right ? 1u : 0u;
+        const float py0 = right ? l10 : l00;
+        const float py1 = right ? l11 : l01;
         iy += coinFlipRemap(py1 / (py0 + py1), rand.y) ? 1u : 0u;
     }
     const float integral = envLumLoad(sc, 0, 0, mipCount - 1);

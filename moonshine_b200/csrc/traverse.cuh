@@ -96,7 +96,8 @@ DI bool traceRay(const DeviceScene& sc, const float3 o, const float3 d, const fl
             if (h0 && h1) {
                 const bool swap = tn1 < tn0;
                 node = swap ? c.y : c.x;
-                if (sp < MSNE_STACK) stack[sp++] = swap ? c.x : c.y;
+                const int far = swap ? c.x : c.y;
+                if (sp < MSNE_STACK) stack[sp++] = far;
             } else if (h0) node = c.x;
             else if (h1) node = c.y;
             else node = stack[--sp];
@@ -189,7 +190,8 @@ struct Traversal {
                 if (h0 && h1) {
                     const bool swap = tn1 < tn0;
                     node = swap ? c.y : c.x;
-                    if (sp < MSNE_STACK) stack[sp++] = swap ? c.x : c.y;
+                    const int far = swap ? c.x : c.y;
+                    if (sp < MSNE_STACK) stack[sp++] = far;
                 } else if (h0) node = c.x;
                 else if (h1) node = c.y;
                 else node = stack[--sp];

@@ -1,4 +1,5 @@
 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-for t in 0 8192 32768 131072 524288; do echo "== TAIL=$t batch8"; MSNE_TAIL_THRESHOLD=$t python bench.py --steps 3 --warmup 3 --batch-spp 8 --paths-in-flight 16777216 --no-cpu-baseline --e2e-steps 1 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(round(d['value'],1), round(d['ms_per_step'],2), d['gpu_launches'], d['rays']['max_bounce'])"; done
-for t in 0 32768; do echo "== TAIL=$t batch1"; MSNE_TAIL_THRESHOLD=$t python bench.py --steps 16 --warmup 3 --batch-spp 1 --paths-in-flight 2097152 --no-cpu-baseline --e2e-steps 16 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(round(d['value'],1), round(d['ms_per_step'],2), round(d['e2e']['value'],1), round(d['e2e']['ms_per_step'],2))"; done
-echo "== batch32"; python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 2 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(round(d['value'],1), round(d['ms_per_step'],2), round(d['e2e']['value'],1))"
+for rep in 1 2; do
+echo "== default"; python bench.py --steps 3 --warmup 3 --batch-spp 8 --paths-in-flight 16777216 --no-cpu-baseline --e2e-steps 1 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(round(d['value'],1), round(d['ms_per_step'],2), round(d['roofline']['kernel_share_of_step'],3))"
+echo "== prefetch"; MSNE_LIB=$PWD/build_variants/lib_prefetch.so python bench.py --steps 3 --warmup 3 --batch-spp 8 --paths-in-flight 16777216 --no-cpu-baseline --e2e-steps 1 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(round(d['value'],1), round(d['ms_per_step'],2), round(d['roofline']['kernel_share_of_step'],3))"
+done
