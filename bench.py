@@ -147,7 +147,7 @@ def run_reference(args):
     r = cpu_oracle_run(scene, steps, min(args.warmup, 3), target_seconds=120.0)
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3),
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(args, scene, 1),
+            "config": dict(config_dict(args, scene, 1), step=r["sample"]),
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference has no CPU path and cannot be built here (Zig/DXC/Vulkan-RT absent): this is the CPU oracle, a line-by-line restatement of its shaders"}
