@@ -24,8 +24,6 @@ struct Bounds {
 
 constexpr int kBins = 16;
 
-struct Task { uint32_t first, count; int32_t parent; int slot; };  // slot: which child of parent
-
 void setChildBox(BvhNode2& n, int slot, const Bounds& bIn) {
     BuildBox b;
     for (int a = 0; a < 3; a++) { b.lo[a] = bIn.lo[a]; b.hi[a] = bIn.hi[a]; }
@@ -57,13 +55,7 @@ void buildBvh2(const BuildBox* boxes, uint32_t n, uint32_t maxLeaf, BuiltBvh& ou
     out.nodes.push_back(root);
     if (n == 0) return;
 
-    std::vector<Task> stack;
-    auto emitLeafOrSplit = [&](uint32_t first, uint32_t count, int32_t parent, int slot) { stack.push_back({first, count, parent, slot}); };
-
-    // the root's two children come from splitting the full range (or one leaf + empty)
-    // generic routine: process a range, decide leaf vs split; on split create a node and push its halves
-    // For the root we pretend "parent = -1": the split result fills nodes[0].
-    struct Range { uint32_t first, count; int32_t node; };  // node to fill with the split of this range
+    struct Range { uint32_t first, count; int32_t node; };  // node whose two children are the split of this range
     std::vector<Range> work;
     if (n <= maxLeaf) {
         Bounds b;
@@ -73,7 +65,6 @@ void buildBvh2(const BuildBox* boxes, uint32_t n, uint32_t maxLeaf, BuiltBvh& ou
         return;
     }
     work.push_back({0, n, 0});
-    (void)emitLeafOrSplit;
     while (!work.empty()) {
         Range r = work.back(); work.pop_back();
         uint32_t* ord = out.order.data() + r.first;

@@ -1,0 +1,117 @@
+"""Edge cases of the ABI on the GPU: empty / degenerate inputs, object lifecycle, accumulation resets."""
+import math
+
+import numpy as np
+import pytest
+
+from moonshine_b200 import hydra, scenes
+from oracle.binding import Oracle
+from gpu_common import gpu_render, oracle_render, within_tol_fraction
+
+pytestmark = pytest.mark.gpu
+
+
+def test_empty_scene_renders_the_environment():
+    """No instances at all: every primary ray misses -> background (default 1x1 white, BackgroundManager.zig:116-126)."""
+    m = hydra.HdMoonshine()
+    m.SetSpecConstants(scenes.Constants())
+    sensor, lens = m.CreateSensor(33, 17), m.CreateLens(scenes.test_lens())
+    m.RenderLaunches(sensor, lens, 2)
+    img = m.ReadSensor(sensor)
+    np.testing.assert_array_equal(img[..., :3], 1.0)
+    np.testing.assert_array_equal(img[..., 3], 2.0)
+    st = m.GetStats()
+    assert st.rays_closest == 2 * 33 * 17 and st.rays_shadow == 0
+
+
+def test_all_instances_invisible_equals_empty_scene():
+    sc = scenes.cornell_box((24, 24))
+    m = hydra.HdMoonshine()
+    _, _, _, insts = scenes.load_scene(m, sc)
+    for i in insts:
+        m.SetInstanceVisibility(i, False)
+    sensor, lens = m.CreateSensor(24, 24), m.CreateLens(sc.lens)
+    m.RenderLaunches(sensor, lens, 1)
+    np.testing.assert_array_equal(m.ReadSensor(sensor)[..., :3], 0.0)  # black env, nothing to hit
+    m.DestroyInstance(insts[0])  # = set invisible (hydra.zig:495-497); must not crash
+
+
+def test_zero_triangle_mesh_and_transformed_empty_instance():
+    sc = scenes.single_triangle((32, 32))
+    empty = sc.add_mesh(np.zeros((3, 3), np.float32), np.zeros((0, 3), np.uint32))
+    sc.add_instance([(empty, 0, False)])
+    sc.add_instance([(empty, 0, False)], transform=[[2, 0, 0, 1], [0, 2, 0, 0], [0, 0, 2, 0]])
+    g, _, _ = gpu_render(sc, 1)
+    r, _, _ = oracle_render(scenes.single_triangle((32, 32)), 1)
+    assert within_tol_fraction(g, r) >= 0.999
+
+
+def test_multiple_sensors_and_lenses_are_independent():
+    sc = scenes.cornell_box((32, 32))
+    m = hydra.HdMoonshine()
+    scenes.load_scene(m, sc)
+    s0, s1 = m.CreateSensor(32, 32), m.CreateSensor(16, 24)
+    l0 = m.CreateLens(sc.lens)
+    l1 = m.CreateLens(scenes.Lens((-1.0, 0.5, 0.5), (1, 0, 0), (0, 0, 1), math.radians(60)))
+    m.RenderLaunches(s0, l0, 2)
+    m.RenderLaunches(s1, l1, 1)
+    assert (m.SensorSampleCount(s0), m.SensorSampleCount(s1)) == (2, 1)
+    a = m.ReadSensor(s0).copy()
+    ref, _, _ = gpu_render(sc, 2)
+    np.testing.assert_array_equal(a.view(np.uint32), ref.view(np.uint32))
+    assert m.ReadSensor(s1).shape == (24, 16, 4)
+    # SetLens / RebuildPipeline clear every sensor (hydra.zig:539, 370)
+    m.SetLens(l0, sc.lens)
+    assert (m.SensorSampleCount(s0), m.SensorSampleCount(s1)) == (0, 0)
+    m.RenderLaunches(s0, l0, 1)
+    assert m.RebuildPipeline() and m.SensorSampleCount(s0) == 0
+    # material edits do NOT clear accumulation (hydra.zig:435-481)
+    m.RenderLaunches(s0, l0, 1)
+    m.SetMaterialIOR(0, 1.4)
+    assert m.SensorSampleCount(s0) == 1
+
+
+def test_hydra_material_setters_take_effect():
+    """HdMoonshineSetMaterial* are applied by the next Render (hydra.zig:150-223)."""
+    m = hydra.HdMoonshine()
+    normal, black = m.CreateSolidTexture2(0.5, 0.5), m.CreateSolidTexture3(0, 0, 0)
+    red, white = m.CreateSolidTexture3(0.8, 0.1, 0.1), m.CreateSolidTexture3(0.9, 0.9, 0.9)
+    mat = m.CreateMaterial(normal, black, red, m.CreateSolidTexture1(0.0), m.CreateSolidTexture1(0.9), 1.5)
+    p = np.array([(0, -1, -1), (0, 1, -1), (0, 0, 1)], np.float32)
+    mesh = m.CreateMesh(p, None, None, np.array([(0, 1, 2)], np.uint32))
+    m.CreateInstance(np.eye(3, 4, dtype=np.float32), [(mesh, mat, False)])
+    sensor, lens = m.CreateSensor(16, 16), m.CreateLens(scenes.test_lens())
+    assert m.Render(sensor, lens)
+    a = m.GetSensorData(sensor)[8, 8, :3].copy()
+    m.SetMaterialColor(mat, white)
+    m.ClearSensor(sensor)
+    assert m.Render(sensor, lens)
+    b = m.GetSensorData(sensor)[8, 8, :3].copy()
+    assert a[0] > 2 * a[1] and abs(b[0] - b[1]) < 0.05 * b[0]  # red -> grey
+
+
+def test_deep_degenerate_bvh_does_not_overflow_the_stack():
+    """10 000 coincident-centroid triangles (a fan around one point) force index splits; traversal stays correct."""
+    n = 10000
+    ang = np.linspace(0, 2 * math.pi, n, endpoint=False)
+    pos = np.zeros((2 * n + 1, 3), np.float32)
+    pos[1:n + 1] = np.stack([np.zeros(n), np.cos(ang), np.sin(ang)], 1)
+    pos[n + 1:] = np.stack([np.zeros(n), -np.cos(ang), -np.sin(ang)], 1)   # each triangle spans the centre symmetrically
+    idx = np.stack([np.arange(1, n + 1), np.roll(np.arange(1, n + 1), -1), np.arange(n + 1, 2 * n + 1)], 1).astype(np.uint32)
+    sc = scenes.single_triangle((24, 24))
+    sc.meshes[0] = scenes.Mesh(pos, idx)
+    m = hydra.HdMoonshine()
+    scenes.load_scene(m, sc)
+    o = Oracle()
+    scenes.load_scene(o, sc)
+    rs = np.random.RandomState(4)
+    rays = np.zeros((2000, 8), np.float32)
+    rays[:, 0] = -3
+    rays[:, 1:3] = rs.rand(2000, 2) * 1.6 - 0.8
+    rays[:, 4] = 1
+    rays[:, 7] = 1e12
+    g, r = m.trace(rays), o.trace(rays)
+    np.testing.assert_array_equal(g["instance"], r["instance"])
+    hit = r["instance"] != 0xFFFFFFFF
+    assert hit.mean() > 0.5
+    np.testing.assert_array_equal(g["primitive"][hit], r["primitive"][hit])
