@@ -54,6 +54,8 @@ typedef struct MsneStats {
     double   trace_ms;                  /* CUDA-event time spent in the trace kernel (valid when profiling is on) */
     uint64_t trace_launches;
     uint64_t max_bounce_reached;
+    uint64_t static_blas_builds;        /* rebuilds of the BLAS level (merged static BLAS + shared BLASes) */
+    uint64_t tlas_builds;               /* rebuilds of the instance level (TLAS + instance records) */
 } MsneStats;
 
 /* must be called before HdMoonshineCreate; selects the CUDA device of objects created afterwards */

@@ -181,7 +181,9 @@ struct HdMoonshine {
     std::vector<BvhNode2> blasNodePool;
     std::vector<TriRec> triPool;
 
-    bool tablesDirty = true, accelDirty = true, aliasDirty = true;
+    // geomDirty: the set of flattened (identity-transform, visible) instances or the BLAS pool changed -> rebuild BLASes + TLAS.
+    // tlasDirty: only transforms / visibility of transformed instances changed -> rebuild the TLAS and instance records.
+    bool tablesDirty = true, geomDirty = true, tlasDirty = true, aliasDirty = true;
 
     DevBuf<BvhNode2> dTlasNodes, dBlasNodes;
     DevBuf<uint32_t> dTlasItems;
@@ -344,13 +346,15 @@ struct HdMoonshine {
         return memcmp(m, I, 48) == 0;
     }
 
-    void buildAccel() {
+    // (1) BLAS level: merged static BLAS over every visible identity-transform instance + one shared BLAS per mesh-key
+    //     of the transformed instances. Only needed when that set changes (Accel.zig:94-184 equivalent).
+    DInstance staticRec{};
+    bool haveStatic = false;
+    BuildBox staticBounds{};
+    uint64_t stats_static_builds = 0, stats_tlas_builds = 0;
+    void buildGeometry() {
         blasNodePool.clear(); triPool.clear(); blasByKey.clear(); blases.clear();
         const uint32_t nInst = (uint32_t)instances.size();
-        std::vector<DInstance> di(nInst + 1);
-        std::vector<BuildBox> boxes;      // TLAS item bounds (world space)
-        std::vector<uint32_t> items;      // TLAS item -> instance record
-        // 1. every visible identity-transform instance goes into ONE world-space BLAS
         std::vector<TriRec> stTris;
         std::vector<BuildBox> stBoxes;
         for (uint32_t i = 0; i < nInst; i++) {
@@ -358,25 +362,49 @@ struct HdMoonshine {
             if (!in.visible || !isIdentity(in.transform)) continue;
             for (uint32_t g = 0; g < in.meshKey.size(); g++) meshTriangles(*meshes[in.meshKey[g]], g, i, stTris, stBoxes);
         }
-        DInstance st{};
+        staticRec = DInstance{};
         const float I[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
-        memcpy(st.o2w, I, 48); memcpy(st.w2o, I, 48);
-        st.isStatic = 1; st.visible = 1;
-        if (!stTris.empty()) {
+        memcpy(staticRec.o2w, I, 48); memcpy(staticRec.w2o, I, 48);
+        staticRec.isStatic = 1; staticRec.visible = 1;
+        haveStatic = !stTris.empty();
+        if (haveStatic) {
             BuiltBvh bvh;
             buildBvh2(stBoxes.data(), (uint32_t)stBoxes.size(), maxLeaf, bvh);
-            st.blasRoot = appendBlas(bvh, stTris);
-            boxes.push_back(bvh.bounds); items.push_back(nInst);
+            staticRec.blasRoot = appendBlas(bvh, stTris);
+            staticBounds = bvh.bounds;
         }
-        di[nInst] = st;
-        // 2. transformed instances keep their own (shared) object-space BLAS
         for (uint32_t i = 0; i < nInst; i++) {
             HostInstance& in = instances[i];
+            in.blas = isIdentity(in.transform) ? 0xFFFFFFFFu : getBlas(in.meshKey);   // invisible ones too: toggling visibility stays TLAS-only
+        }
+        dBlasNodes.upload(blasNodePool.data(), blasNodePool.size(), stream);
+        dTris.upload(triPool.data(), triPool.size(), stream);
+        CK(cudaStreamSynchronize(stream));
+        stats_static_builds++;
+    }
+
+    // (2) instance level: device instance records, inverse transforms and the TLAS (Accel.zig:394-489 equivalent)
+    void buildTlas() {
+        const uint32_t nInst = (uint32_t)instances.size();
+        std::vector<DInstance> di(nInst + 1);
+        std::vector<BuildBox> boxes;      // TLAS item bounds (world space)
+        std::vector<uint32_t> items;      // TLAS item -> instance record
+        di[nInst] = staticRec;
+        if (haveStatic) { boxes.push_back(staticBounds); items.push_back(nInst); }
+        // transformed instances created since the last BLAS-level build: append their BLAS (or reuse a shared one)
+        const size_t poolNodes = blasNodePool.size();
+        for (HostInstance& in : instances)
+            if (in.blas == 0xFFFFFFFFu && !isIdentity(in.transform)) in.blas = getBlas(in.meshKey);
+        if (blasNodePool.size() != poolNodes) {
+            dBlasNodes.upload(blasNodePool.data(), blasNodePool.size(), stream);
+            dTris.upload(triPool.data(), triPool.size(), stream);
+        }
+        for (uint32_t i = 0; i < nInst; i++) {
+            const HostInstance& in = instances[i];
             DInstance d{};
             memcpy(d.o2w, in.transform, 48); memcpy(d.w2o, in.inverse, 48);
             d.customIndex = in.customIndex; d.visible = in.visible ? 1 : 0;
             if (in.visible && !isIdentity(in.transform)) {
-                in.blas = getBlas(in.meshKey);
                 d.blasRoot = blases[in.blas].rootNode;
                 const BuildBox& bb = blases[in.blas].bounds;
                 BuildBox w; for (int a = 0; a < 3; a++) { w.lo[a] = 1e30f; w.hi[a] = -1e30f; }
@@ -392,8 +420,6 @@ struct HdMoonshine {
             }
             di[i] = d;
         }
-        dBlasNodes.upload(blasNodePool.data(), blasNodePool.size(), stream);
-        dTris.upload(triPool.data(), triPool.size(), stream);
         dInstances.upload(di.data(), di.size(), stream);
         hasTlas = !items.empty();
         if (hasTlas) {
@@ -412,6 +438,7 @@ struct HdMoonshine {
             dTlasItems.upload(slots.data(), slots.size(), stream);
         }
         CK(cudaStreamSynchronize(stream));
+        stats_tlas_builds++;
     }
 
     void syncScene() {
@@ -427,7 +454,8 @@ struct HdMoonshine {
             CK(cudaStreamSynchronize(stream));   // staging vectors die here
             tablesDirty = false;
         }
-        if (accelDirty) { buildAccel(); accelDirty = false; }
+        if (geomDirty) { buildGeometry(); geomDirty = false; tlasDirty = true; }
+        if (tlasDirty) { buildTlas(); tlasDirty = false; }
         if (aliasDirty) {
             dAlias.upload(alias.data(), alias.size(), stream);
             CK(cudaStreamSynchronize(stream));
@@ -662,6 +690,7 @@ struct HdMoonshine {
         CK(cudaStreamSynchronize(stream));
         out = stats;
         out.rays_closest = rc[0]; out.rays_shadow = rc[1]; out.max_bounce_reached = sc[3];
+        out.static_blas_builds = stats_static_builds; out.tlas_builds = stats_tlas_builds;
     }
 };
 
@@ -811,15 +840,27 @@ InstanceHandle HdMoonshineCreateInstance(HdMoonshine* h, Mat3x4 t, const Geometr
             h->geometries.push_back(DGeometry{geoms[i].mesh, geoms[i].material, geoms[i].sampled ? 1u : 0u});
             in.meshKey.push_back(geoms[i].mesh);
         }
+        in.blas = 0xFFFFFFFFu;
         h->instances.push_back(in);
-        h->tablesDirty = true; h->accelDirty = true;
+        h->tablesDirty = true;
+        if (HdMoonshine::isIdentity(in.transform)) h->geomDirty = true;   // joins the flattened static BLAS
+        else h->tlasDirty = true;                                         // own/shared BLAS appended lazily, TLAS rebuilt
         h->clearAllSensors();   // hydra.zig:491
         return (uint32_t)h->instances.size() - 1;
     )
 }
 void HdMoonshineSetInstanceVisibility(HdMoonshine* h, InstanceHandle i, bool visible) {
     LOCK(h);
-    ABORT_ON_THROW(h->use(); h->instances.at(i).visible = visible; h->accelDirty = true; h->clearAllSensors();)
+    ABORT_ON_THROW(
+        h->use();
+        HostInstance& in = h->instances.at(i);
+        if (in.visible != visible) {
+            in.visible = visible;
+            if (HdMoonshine::isIdentity(in.transform)) h->geomDirty = true;   // member of the flattened static BLAS
+            else h->tlasDirty = true;                                         // transformed instance: TLAS only
+        }
+        h->clearAllSensors();
+    )
 }
 void HdMoonshineDestroyInstance(HdMoonshine* h, InstanceHandle i) { HdMoonshineSetInstanceVisibility(h, i, false); }   // hydra.zig:495-497
 void HdMoonshineSetInstanceTransform(HdMoonshine* h, InstanceHandle i, Mat3x4 t) {
@@ -827,9 +868,13 @@ void HdMoonshineSetInstanceTransform(HdMoonshine* h, InstanceHandle i, Mat3x4 t)
     ABORT_ON_THROW(
         h->use();
         HostInstance& in = h->instances.at(i);
+        const bool wasStatic = HdMoonshine::isIdentity(in.transform);
         memcpy(in.transform, &t, 48);
         inverseAffine(in.transform, in.inverse);
-        h->accelDirty = true; h->clearAllSensors();
+        const bool isStatic = HdMoonshine::isIdentity(in.transform);
+        if (wasStatic || isStatic) h->geomDirty = true;   // enters/leaves the flattened static BLAS
+        else h->tlasDirty = true;                         // TLAS + instance records only (hydra.zig:225-311: TLAS update)
+        h->clearAllSensors();
     )
 }
 

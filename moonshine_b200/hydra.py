@@ -63,7 +63,8 @@ class MsneMaterialInfo(C.Structure):
 
 class MsneStats(C.Structure):
     _fields_ = [("rays_closest", C.c_uint64), ("rays_shadow", C.c_uint64), ("samples", C.c_uint64), ("kernel_launches", C.c_uint64),
-                ("device_ms", C.c_double), ("trace_ms", C.c_double), ("trace_launches", C.c_uint64), ("max_bounce_reached", C.c_uint64)]
+                ("device_ms", C.c_double), ("trace_ms", C.c_double), ("trace_launches", C.c_uint64), ("max_bounce_reached", C.c_uint64),
+                ("static_blas_builds", C.c_uint64), ("tlas_builds", C.c_uint64)]
 
 
 # every symbol include/moonshine.h and include/moonshine_ext.h declare: (restype, argtypes)

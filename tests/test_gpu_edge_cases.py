@@ -115,3 +115,45 @@ def test_deep_degenerate_bvh_does_not_overflow_the_stack():
     hit = r["instance"] != 0xFFFFFFFF
     assert hit.mean() > 0.5
     np.testing.assert_array_equal(g["primitive"][hit], r["primitive"][hit])
+
+
+def test_transform_edits_of_instanced_objects_rebuild_only_the_tlas():
+    """§8(f) row 3: SetInstanceTransform / SetInstanceVisibility / CreateInstance on TRANSFORMED instances must not
+    rebuild the BLAS level (the reference does a TLAS update, hydra.zig:225-311); results still match the oracle."""
+    sc = scenes.mesh_light_stress(8, (64, 64))
+    m = hydra.HdMoonshine()
+    _, mats, meshes, insts = scenes.load_scene(m, sc)
+    o = Oracle()
+    _, _, _, oinsts = scenes.load_scene(o, sc)
+    sensor, lens = m.CreateSensor(64, 64), m.CreateLens(sc.lens)
+    m.RenderLaunches(sensor, lens, 1)
+    s0 = m.GetStats()
+    assert s0.static_blas_builds == 1 and s0.tlas_builds == 1
+    moved = sc.instances[5].transform.copy()
+    moved[:, 3] += np.array([0.3, -0.2, 0.4], np.float32)
+    m.SetInstanceTransform(insts[5], moved)
+    o.set_instance_transform(oinsts[5], moved)
+    m.SetInstanceVisibility(insts[9], False)
+    o.set_instance_visibility(oinsts[9], False)
+    extra = np.array([[0.2, 0, 0, 4.0], [0, 0.2, 0, 4.0], [0, 0, 0.2, 2.5]], np.float32)
+    ico_mesh, light_mat = sc.instances[5].geometries[0][0], sc.instances[5].geometries[0][1]
+    m.CreateInstance(extra, [(meshes[ico_mesh], mats[light_mat], True)])
+    o.create_instance(extra, [(ico_mesh, light_mat, True)])
+    m.RenderLaunches(sensor, lens, 1)
+    s1 = m.GetStats()
+    assert s1.static_blas_builds == 1, "BLAS level was rebuilt for a TLAS-only edit"
+    assert s1.tlas_builds == 2
+    rays = np.zeros((4000, 8), np.float32)
+    rs = np.random.RandomState(3)
+    rays[:, 0:3] = rs.rand(4000, 3) * np.array([8, 8, 3]) + np.array([0, 0, 0.2])
+    d = rs.randn(4000, 3); rays[:, 4:7] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    rays[:, 7] = 1e12
+    g, r = m.trace(rays), o.trace(rays)
+    np.testing.assert_array_equal(g["instance"], r["instance"])
+    hit = r["instance"] != 0xFFFFFFFF
+    np.testing.assert_array_equal(g["primitive"][hit], r["primitive"][hit])
+    assert not (g["instance"] == insts[9]).any()
+    # an edit of a flattened (identity) instance does rebuild the BLAS level
+    m.SetInstanceVisibility(insts[0], False)   # the ground plane
+    m.RenderLaunches(sensor, lens, 1)
+    assert m.GetStats().static_blas_builds == 2
