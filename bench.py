@@ -46,6 +46,8 @@ def make_scene(args):
         return scenes.bathroom((args.width, args.height), detail=args.detail)
     if args.workload == "cfg2":
         return scenes.cornell_box((512, 512))
+    if args.workload == "cfg5":
+        return scenes.mesh_light_stress(args.n_side, (2048, 2048))
     raise SystemExit(f"unknown workload {args.workload}")
 
 
@@ -174,6 +176,7 @@ def main():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--detail", type=float, default=1.0)
+    ap.add_argument("--n-side", type=int, default=1000, help="cfg5: instances per side (1000 = 10^6 instances)")
     ap.add_argument("--batch-spp", type=int, default=32)
     ap.add_argument("--paths-in-flight", type=int, default=0, help="wavefront pool size in paths (0 = library default, 64 Mi)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps (capped at 32)")
