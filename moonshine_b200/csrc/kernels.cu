@@ -177,16 +177,75 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_BLOCKS_PER_SM) k_trace(De
     }
 }
 
+template <bool ANY_HIT, bool WIDE>
+DI bool traceScene(const DeviceScene& sc, const float3 o, const float3 d, const float tmin, const float tmax, HitRec& hit) {
+    if (WIDE) return traceRay8<ANY_HIT>(sc, o, d, tmin, tmax, hit);
+    return traceRay<ANY_HIT>(sc, o, d, tmin, tmax, hit);
+}
+
+// Same contract as k_trace on the compressed wide BVH (traverse.cuh traceRay8): persistent warps pull 32-ray
+// tickets from the joint index space [extension rays | shadow rays], every lane walks its ray to the end, then the
+// warp bins its hits by material type.
+__global__ void __launch_bounds__(TRACE_THREADS, TRACE8_BLOCKS_PER_SM) k_trace8(DeviceScene sc, PathBuffers pb, WaveState ws, uint32_t buf) {
+    const Counters cin = ws.counters[buf];
+    const uint32_t nLive = cin.nLive, total = cin.nLive + cin.nShadow;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t ltMask = (1u << lane) - 1u;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(ws.traceTicket, 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= total) break;
+        const uint32_t idx = base + lane;
+        uint32_t bin = 0xFFu;
+        if (idx < nLive) {
+            const float4 r0 = pb.R0[buf][idx], r1 = pb.R1[buf][idx];
+            HitRec h;
+            traceRay8<false>(sc, mk3(r0.x, r0.y, r0.z), mk3(r1.x, r1.y, r1.z), 0.0f, MS_INFINITY, h);
+            pb.H[idx] = make_uint4(h.inst, h.tri, __float_as_uint(h.u), __float_as_uint(h.v));
+            bin = hitBin(sc, h);
+        } else if (idx < total) {
+            const float4 q0 = pb.Q0[idx - nLive], q1 = pb.Q1[idx - nLive];
+            HitRec h;
+            if (traceRay8<true>(sc, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), 0.0f, q0.w, h)) {
+                const uint32_t target = __float_as_uint(q1.w);
+                float4* n = (target & 1u) ? pb.N1[buf] : pb.N0[buf];
+                n[target >> 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        // warp-level sort by material id: lanes with the same bin elect a leader that reserves their slots
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, bin);
+        if (bin != 0xFFu) {
+            const int leader = __ffs(peers) - 1;
+            uint32_t slot = 0;
+            if ((int)lane == leader) slot = atomicAdd(ws.typeCount + bin, (uint32_t)__popc(peers));
+            slot = __shfl_sync(peers, slot, leader) + __popc(peers & ltMask);
+            pb.typeList[(size_t)bin * pb.capacity + slot] = idx;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const uint32_t done = atomicAdd(ws.traceDone, 1u);
+        if (done == gridDim.x - 1) {
+            *ws.traceTicket = 0; *ws.traceDone = 0;
+            ws.rayCounts[0] += nLive; ws.rayCounts[1] += cin.nShadow;
+            __threadfence();
+        }
+    }
+}
+
 // debug probe: arbitrary rays (HdMoonshineExtTraceRays); rays8 = {o, tmin, d, tmax}
+template <bool WIDE>
 __global__ void k_trace_probe(DeviceScene sc, const float* __restrict__ rays8, uint32_t n, int anyHit, uint32_t* hits5) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float* r = rays8 + 8 * (size_t)i;
     HitRec h;
     uint32_t geom = 0, prim = 0;
-    if (anyHit) traceRay<true>(sc, mk3(r[0], r[1], r[2]), mk3(r[4], r[5], r[6]), r[3], r[7], h);
+    if (anyHit) traceScene<true, WIDE>(sc, mk3(r[0], r[1], r[2]), mk3(r[4], r[5], r[6]), r[3], r[7], h);
     else {
-        traceRay<false>(sc, mk3(r[0], r[1], r[2]), mk3(r[4], r[5], r[6]), r[3], r[7], h);
+        traceScene<false, WIDE>(sc, mk3(r[0], r[1], r[2]), mk3(r[4], r[5], r[6]), r[3], r[7], h);
         if (h.inst != MISS_ID) { geom = sc.tris[h.tri].geom; prim = sc.tris[h.tri].prim; }
     }
     uint32_t* o = hits5 + 5 * (size_t)i;
@@ -461,6 +520,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, MIN_BLOCKS) k_shade(DeviceScene
 // path ends. Same device functions, same per-path order of operations -> bit-identical results.
 // Precondition: k_trace has just run on `buf` (H holds this bounce's hits, pending shadow rays are resolved).
 // ------------------------------------------------------------------------------------------------
+template <bool WIDE>
 __global__ void __launch_bounds__(128) k_tail(DeviceScene sc, DConstants k, PathBuffers pb, WaveState ws, uint32_t buf) {
     const Counters cin = ws.counters[buf];
     const uint32_t nLive = cin.nLive, total = cin.nLive + cin.nDead, P = pb.capacity;
@@ -478,19 +538,19 @@ __global__ void __launch_bounds__(128) k_tail(DeviceScene sc, DConstants k, Path
             HitRec h;
             if (out.envRay) {
                 nShadow++;
-                if (traceRay<true>(sc, mk3(out.envQ0.x, out.envQ0.y, out.envQ0.z), mk3(out.envQ1.x, out.envQ1.y, out.envQ1.z), 0.0f, out.envQ0.w, h))
+                if (traceScene<true, WIDE>(sc, mk3(out.envQ0.x, out.envQ0.y, out.envQ0.z), mk3(out.envQ1.x, out.envQ1.y, out.envQ1.z), 0.0f, out.envQ0.w, h))
                     out.N0 = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             if (out.meshRay) {
                 nShadow++;
-                if (traceRay<true>(sc, mk3(out.meshQ0.x, out.meshQ0.y, out.meshQ0.z), mk3(out.meshQ1.x, out.meshQ1.y, out.meshQ1.z), 0.0f, out.meshQ0.w, h))
+                if (traceScene<true, WIDE>(sc, mk3(out.meshQ0.x, out.meshQ0.y, out.meshQ0.z), mk3(out.meshQ1.x, out.meshQ1.y, out.meshQ1.z), 0.0f, out.meshQ0.w, h))
                     out.N1 = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             pb.R0[buf][q] = out.R0; pb.R1[buf][q] = out.R1; pb.S0[buf][q] = out.S0; pb.S1[buf][q] = out.S1;
             pb.N0[buf][q] = out.N0; pb.N1[buf][q] = out.N1;
             if (out.kind == 1) {
                 nClosest++;
-                traceRay<false>(sc, mk3(out.R0.x, out.R0.y, out.R0.z), mk3(out.R1.x, out.R1.y, out.R1.z), 0.0f, MS_INFINITY, h);
+                traceScene<false, WIDE>(sc, mk3(out.R0.x, out.R0.y, out.R0.z), mk3(out.R1.x, out.R1.y, out.R1.z), 0.0f, MS_INFINITY, h);
                 pb.H[q] = make_uint4(h.inst, h.tri, __float_as_uint(h.u), __float_as_uint(h.v));
             }
         }
@@ -596,8 +656,9 @@ void launchGenerate(cudaStream_t st, const DCamera& cam, const DConstants& k, co
                     uint32_t nPix, uint32_t nSamples, uint32_t firstSample) {
     k_generate<<<grid1((uint64_t)nPix * nSamples, 256), 256, 0, st>>>(cam, k, pb, counters, pixIds, nPix, nSamples, firstSample);
 }
-void launchTrace(cudaStream_t st, int blocks, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf) {
-    k_trace<<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf);
+void launchTrace(cudaStream_t st, int blocks, bool wide, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf) {
+    if (wide) k_trace8<<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf);
+    else k_trace<<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf);
 }
 // Register caps (measured, profiles/r01_sweeps.md): the all-material kernel runs best at 80 registers
 // (6 blocks/SM); the specialised kernels are smaller and take the same cap.
@@ -615,8 +676,9 @@ void launchShadeBinned(cudaStream_t st, int blocks, const DeviceScene& sc, const
     k_shade<2, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, 0u);   // PerfectMirror
     k_shade<4, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, 1u);   // miss + dead
 }
-void launchTail(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf) {
-    k_tail<<<blocks, 128, 0, st>>>(sc, k, pb, ws, buf);
+void launchTail(cudaStream_t st, int blocks, bool wide, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf) {
+    if (wide) k_tail<true><<<blocks, 128, 0, st>>>(sc, k, pb, ws, buf);
+    else k_tail<false><<<blocks, 128, 0, st>>>(sc, k, pb, ws, buf);
 }
 void launchAccumulate(cudaStream_t st, const float4* result, float4* image, float4* runState, const uint32_t* pixIds, uint32_t nPix, uint32_t nSamples,
                       uint32_t firstSample, uint32_t spr) {
@@ -630,15 +692,17 @@ void launchEnvFold(cudaStream_t st, const float* srcMip, float* dstMip, uint32_t
     dim3 b(8, 8), g((dstSize + 7) / 8, (dstSize + 7) / 8);
     k_env_fold<<<g, b, 0, st>>>(srcMip, dstMip, dstSize);
 }
-void launchTraceProbe(cudaStream_t st, const DeviceScene& sc, const float* rays8, uint32_t n, int anyHit, uint32_t* hits5) {
-    k_trace_probe<<<grid1(n, 128), 128, 0, st>>>(sc, rays8, n, anyHit, hits5);
+void launchTraceProbe(cudaStream_t st, bool wide, const DeviceScene& sc, const float* rays8, uint32_t n, int anyHit, uint32_t* hits5) {
+    if (wide) k_trace_probe<true><<<grid1(n, 128), 128, 0, st>>>(sc, rays8, n, anyHit, hits5);
+    else k_trace_probe<false><<<grid1(n, 128), 128, 0, st>>>(sc, rays8, n, anyHit, hits5);
 }
 void launchPrimaryProbe(cudaStream_t st, const DCamera& cam, const DConstants& k, uint32_t sample, float* rays6, uint32_t* rngState) {
     k_primary_probe<<<grid1((uint64_t)cam.width * cam.height, 256), 256, 0, st>>>(cam, k, sample, rays6, rngState);
 }
-int traceOccupancyBlocksPerSm() {
+int traceOccupancyBlocksPerSm(bool wide) {
     int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace, TRACE_THREADS, 0);
+    if (wide) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace8, TRACE_THREADS, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace, TRACE_THREADS, 0);
     return n;
 }
 int shadeOccupancyBlocksPerSm() {

@@ -11,23 +11,30 @@ namespace msne {
 #ifndef TRACE_BLOCKS_PER_SM
 #define TRACE_BLOCKS_PER_SM 8   // 64 registers: measured best (profiles/r01_sweeps.md)
 #endif
+#ifndef TRACE8_BLOCKS_PER_SM
+#define TRACE8_BLOCKS_PER_SM 6  // wide-BVH trace kernel
+#endif
+#ifndef MSNE_STACK8
+#define MSNE_STACK8 40          // traversal stack entries (uint2) of the wide-BVH kernels
+#endif
+static const unsigned MSNE_STACK8_HOST = MSNE_STACK8;
 #ifndef SHADE_THREADS
 #define SHADE_THREADS 128
 #endif
 
 void launchGenerate(cudaStream_t st, const DCamera& cam, const DConstants& k, const PathBuffers& pb, Counters* counters, const uint32_t* pixIds,
                     uint32_t nPix, uint32_t nSamples, uint32_t firstSample);
-void launchTrace(cudaStream_t st, int blocks, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf);
+void launchTrace(cudaStream_t st, int blocks, bool wide, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf);
 void launchShade(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf);
 void launchShadeBinned(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf);
-void launchTail(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf);
+void launchTail(cudaStream_t st, int blocks, bool wide, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf);
 void launchAccumulate(cudaStream_t st, const float4* result, float4* image, float4* runState, const uint32_t* pixIds, uint32_t nPix, uint32_t nSamples,
                       uint32_t firstSample, uint32_t spr);
 void launchEnvResample(cudaStream_t st, const float4* src, uint32_t W, uint32_t H, float4* dstRgb, float* dstLum, uint32_t S);
 void launchEnvFold(cudaStream_t st, const float* srcMip, float* dstMip, uint32_t dstSize);
-void launchTraceProbe(cudaStream_t st, const DeviceScene& sc, const float* rays8, uint32_t n, int anyHit, uint32_t* hits5);
+void launchTraceProbe(cudaStream_t st, bool wide, const DeviceScene& sc, const float* rays8, uint32_t n, int anyHit, uint32_t* hits5);
 void launchPrimaryProbe(cudaStream_t st, const DCamera& cam, const DConstants& k, uint32_t sample, float* rays6, uint32_t* rngState);
-int traceOccupancyBlocksPerSm();
+int traceOccupancyBlocksPerSm(bool wide);
 int shadeOccupancyBlocksPerSm();
 
 }  // namespace msne

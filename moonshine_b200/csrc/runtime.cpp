@@ -179,6 +179,9 @@ struct HdMoonshine {
     std::map<std::vector<uint32_t>, uint32_t> blasByKey;
     std::vector<Blas> blases;
     std::vector<BvhNode2> blasNodePool;
+    std::vector<BvhNode8> blasNodePool8;   // bvhWidth == 8: compressed wide nodes instead of blasNodePool
+    uint32_t bvhWidth = 8;                 // MSNE_BVH=2 selects the binary BVH kernels (kept for A/B measurements)
+    uint32_t blasDepthMax = 0, tlasDepth = 0;
     std::vector<TriRec> triPool;
 
     // geomDirty: the set of flattened (identity-transform, visible) instances or the BLAS pool changed -> rebuild BLASes + TLAS.
@@ -186,6 +189,8 @@ struct HdMoonshine {
     bool tablesDirty = true, geomDirty = true, tlasDirty = true, aliasDirty = true;
 
     DevBuf<BvhNode2> dTlasNodes, dBlasNodes;
+    DevBuf<BvhNode8> dTlasNodes8, dBlasNodes8;
+    bool tlasStaticOnly = false;
     DevBuf<uint32_t> dTlasItems;
     DevBuf<TriRec> dTris;
     DevBuf<DInstance> dInstances;
@@ -252,9 +257,11 @@ struct HdMoonshine {
         consts = MsneSpecConstants{1, 1024, 0, 0, 0, 0, 0};
         const float white[4] = {1, 1, 1, 1};
         setBackground(white, 1, 1);   // addDefaultBackground (BackgroundManager.zig:116-126)
+        if (const char* e = getenv("MSNE_BVH")) bvhWidth = atoi(e) == 2 ? 2u : 8u;
         if (const char* e = getenv("MSNE_MAX_LEAF")) maxLeaf = (uint32_t)std::min(8, std::max(1, atoi(e)));
+        if (wide()) maxLeaf = std::min(maxLeaf, 3u);   // a wide node addresses its items through a 24-bit mask: 8 children x 3
         if (const char* e = getenv("MSNE_TAIL_THRESHOLD")) tailThreshold = strtoull(e, nullptr, 10);
-        traceBlocks = smCount * std::max(1, traceOccupancyBlocksPerSm());
+        traceBlocks = smCount * std::max(1, traceOccupancyBlocksPerSm(wide()));
         shadeBlocks = smCount * std::max(1, shadeOccupancyBlocksPerSm());
         CK(cudaStreamSynchronize(stream));
     }
@@ -272,6 +279,7 @@ struct HdMoonshine {
     }
 
     void use() { CK(cudaSetDevice(device)); }
+    bool wide() const { return bvhWidth == 8; }
 
     // ---- environment (BackgroundManager.zig:142-394) -----------------------------------------
     void setBackground(const float* rgba, uint32_t W, uint32_t H) {
@@ -298,6 +306,15 @@ struct HdMoonshine {
     // ---- acceleration structure (replaces Accel.zig:94-184 makeBlases and :440-489 TLAS build) ------
     // pools a host BVH: children become the pre-encoded traversal references of dtypes.h
     uint32_t appendBlas(const BuiltBvh& bvh, const std::vector<TriRec>& tris) {
+        if (wide()) {
+            BuiltBvh8 w;
+            collapseToBvh8(bvh, w);
+            const uint32_t nodeBase = (uint32_t)blasNodePool8.size(), triBase = (uint32_t)triPool.size();
+            for (BvhNode8 n : w.nodes) { n.childBase += nodeBase; n.itemBase += triBase; blasNodePool8.push_back(n); }
+            for (uint32_t i = 0; i < w.order.size(); i++) triPool.push_back(tris[w.order[i]]);
+            blasDepthMax = std::max(blasDepthMax, w.depth);
+            return nodeBase;
+        }
         const uint32_t nodeBase = (uint32_t)blasNodePool.size(), triBase = (uint32_t)triPool.size();
         for (BvhNode2 n : bvh.nodes) {
             for (int s = 0; s < 2; s++) {
@@ -353,7 +370,8 @@ struct HdMoonshine {
     BuildBox staticBounds{};
     uint64_t stats_static_builds = 0, stats_tlas_builds = 0;
     void buildGeometry() {
-        blasNodePool.clear(); triPool.clear(); blasByKey.clear(); blases.clear();
+        blasNodePool.clear(); blasNodePool8.clear(); triPool.clear(); blasByKey.clear(); blases.clear();
+        blasDepthMax = 0;
         const uint32_t nInst = (uint32_t)instances.size();
         std::vector<TriRec> stTris;
         std::vector<BuildBox> stBoxes;
@@ -377,10 +395,15 @@ struct HdMoonshine {
             HostInstance& in = instances[i];
             in.blas = isIdentity(in.transform) ? 0xFFFFFFFFu : getBlas(in.meshKey);   // invisible ones too: toggling visibility stays TLAS-only
         }
-        dBlasNodes.upload(blasNodePool.data(), blasNodePool.size(), stream);
-        dTris.upload(triPool.data(), triPool.size(), stream);
+        uploadBlasPool();
         CK(cudaStreamSynchronize(stream));
         stats_static_builds++;
+    }
+
+    void uploadBlasPool() {
+        if (wide()) dBlasNodes8.upload(blasNodePool8.data(), blasNodePool8.size(), stream);
+        else dBlasNodes.upload(blasNodePool.data(), blasNodePool.size(), stream);
+        dTris.upload(triPool.data(), triPool.size(), stream);
     }
 
     // (2) instance level: device instance records, inverse transforms and the TLAS (Accel.zig:394-489 equivalent)
@@ -392,13 +415,10 @@ struct HdMoonshine {
         di[nInst] = staticRec;
         if (haveStatic) { boxes.push_back(staticBounds); items.push_back(nInst); }
         // transformed instances created since the last BLAS-level build: append their BLAS (or reuse a shared one)
-        const size_t poolNodes = blasNodePool.size();
+        const size_t poolNodes = blasNodePool.size() + blasNodePool8.size();
         for (HostInstance& in : instances)
             if (in.blas == 0xFFFFFFFFu && !isIdentity(in.transform)) in.blas = getBlas(in.meshKey);
-        if (blasNodePool.size() != poolNodes) {
-            dBlasNodes.upload(blasNodePool.data(), blasNodePool.size(), stream);
-            dTris.upload(triPool.data(), triPool.size(), stream);
-        }
+        if (blasNodePool.size() + blasNodePool8.size() != poolNodes) uploadBlasPool();
         for (uint32_t i = 0; i < nInst; i++) {
             const HostInstance& in = instances[i];
             DInstance d{};
@@ -422,7 +442,20 @@ struct HdMoonshine {
         }
         dInstances.upload(di.data(), di.size(), stream);
         hasTlas = !items.empty();
-        if (hasTlas) {
+        tlasStaticOnly = haveStatic && items.size() == 1;
+        if (hasTlas && wide()) {
+            BuiltBvh tl;
+            buildBvh2(boxes.data(), (uint32_t)boxes.size(), 1, tl);
+            BuiltBvh8 w;
+            collapseToBvh8(tl, w);
+            std::vector<uint32_t> slots(w.order.size());
+            for (size_t s = 0; s < w.order.size(); s++) slots[s] = items[w.order[s]];
+            dTlasNodes8.upload(w.nodes.data(), w.nodes.size(), stream);
+            dTlasItems.upload(slots.data(), slots.size(), stream);
+            tlasDepth = w.depth;
+            // every node visit parks at most one group; entering an instance parks two groups and a marker
+            if (tlasDepth + blasDepthMax + 4 > MSNE_STACK8_HOST) fatal("wide BVH deeper than the traversal stack (MSNE_STACK8)");
+        } else if (hasTlas) {
             BuiltBvh tl;
             buildBvh2(boxes.data(), (uint32_t)boxes.size(), 1, tl);
             std::vector<uint32_t> slots(tl.order.size());
@@ -465,7 +498,11 @@ struct HdMoonshine {
 
     DeviceScene deviceScene() const {
         DeviceScene sc{};
-        sc.tlasNodes = hasTlas ? dTlasNodes.p : nullptr;
+        sc.tlasNodes = hasTlas && !wide() ? dTlasNodes.p : nullptr;
+        sc.tlasNodes8 = hasTlas && wide() ? dTlasNodes8.p : nullptr;
+        sc.blasNodes8 = dBlasNodes8.p;
+        sc.staticOnly = tlasStaticOnly ? 1u : 0u;
+        sc.staticRoot = staticRec.blasRoot;
         sc.tlasItems = dTlasItems.p;
         sc.blasNodes = dBlasNodes.p; sc.tris = dTris.p; sc.instances = dInstances.p; sc.geometries = dGeometries.p;
         sc.meshes = dMeshes.p; sc.materials = dMaterials.p; sc.textures = dTextures.p;
@@ -605,7 +642,7 @@ struct HdMoonshine {
             const uint32_t buf = b & 1u;
             const bool prof = profiling && profUsed < kProfEvents;
             if (prof) CK(cudaEventRecord(profEv[profUsed][0], stream));
-            launchTrace(stream, traceBlocks, sc, pb, ws, buf);
+            launchTrace(stream, traceBlocks, wide(), sc, pb, ws, buf);
             if (prof) { CK(cudaEventRecord(profEv[profUsed][1], stream)); profUsed++; }
             // big queues: one material-specialised launch per bin; small queues (tail): one generic launch
             if (lastLive >= binnedThreshold) { launchShadeBinned(stream, shadeBlocks, sc, k, pb, ws, buf); stats.kernel_launches += 6; }
@@ -626,8 +663,8 @@ struct HdMoonshine {
                 // few stragglers left: after the already-queued bounce b+1, trace once more and let k_tail finish
                 // every remaining path in a single launch instead of ~130 launch pairs at the latency floor
                 const uint32_t tb = (b + 2) & 1u;
-                launchTrace(stream, traceBlocks, sc, pb, ws, tb);
-                launchTail(stream, smCount * 4, sc, k, pb, ws, tb);
+                launchTrace(stream, traceBlocks, wide(), sc, pb, ws, tb);
+                launchTail(stream, smCount * 4, wide(), sc, k, pb, ws, tb);
                 stats.kernel_launches += 2;
                 break;
             }
@@ -977,7 +1014,7 @@ bool HdMoonshineExtTraceRays(HdMoonshine* h, const float* rays8, size_t n, bool 
         h->use(); h->syncScene();
         DevBuf<float> dr; DevBuf<uint32_t> dh;
         dr.upload(rays8, 8 * n, h->stream); dh.alloc(5 * n);
-        launchTraceProbe(h->stream, h->deviceScene(), dr.p, (uint32_t)n, anyHit ? 1 : 0, dh.p);
+        launchTraceProbe(h->stream, h->wide(), h->deviceScene(), dr.p, (uint32_t)n, anyHit ? 1 : 0, dh.p);
         h->stats.kernel_launches++;
         CK(cudaMemcpyAsync(hits5, dh.p, 5 * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
