@@ -88,6 +88,17 @@ MSNE_API void HdMoonshineExtSetProfiling(HdMoonshine*, bool per_kernel_events);
 MSNE_API void HdMoonshineExtGetStats(const HdMoonshine*, MsneStats*);
 MSNE_API void HdMoonshineExtResetStats(HdMoonshine*);
 
+/* ---- object picker: ObjectPicker.getClickedObject (engine/hrtsystem/ObjectPicker.zig:89-128) + its ray-generation
+ * program (shaders/hrtsystem/input.hlsl:1-57). `normalized_coords` in [0,1]^2 with the origin at the top left as the
+ * online viewer passes them (online/main.zig:287-305); instance_index is -1 when nothing was hit. ---- */
+typedef struct MsneClickData {
+    int32_t instance_index;
+    uint32_t geometry_index;
+    uint32_t primitive_index;
+    F32x2 barycentrics;
+} MsneClickData;
+MSNE_API bool HdMoonshineExtPick(HdMoonshine*, SensorHandle, LensHandle, F32x2 normalized_coords, MsneClickData* out);
+
 /* ---- debug probes used by tests/ (stage-level parity against the oracle) ---- */
 /* rays: n x {origin.xyz, tmin, dir.xyz, tmax}; hits: n x {u32 instance, u32 geometry, u32 primitive, f32 u, f32 v} */
 MSNE_API bool HdMoonshineExtTraceRays(HdMoonshine*, const float* rays8, size_t n, bool any_hit, uint32_t* hits5);

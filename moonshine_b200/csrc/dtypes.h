@@ -123,6 +123,9 @@ struct DCamera {
     uint32_t width, height;
 };
 
+// ClickData of the object picker (input.hlsl:1-6): instance_index = -1 when nothing was hit
+struct MsneClick { int32_t instance_index; uint32_t geometry_index, primitive_index; float bary[2]; };
+
 // ---- wavefront pool ---------------------------------------------------------------------------
 // One path = six 16-byte lanes per ping-pong buffer (SoA arrays of float4, index q = queue slot):
 //   R0 = (origin.xyz, lastMaterialPdf)      R1 = (dir.xyz, bits: bounce | DELTA<<30 | DEAD<<31)

@@ -225,6 +225,10 @@ struct HdMoonshine {
     int traceBlocks = 0, shadeBlocks = 0;
     uint32_t maxLeaf = 3;   // triangles per BVH leaf (<= 8: 3-bit count in the leaf reference); 2-3 measured best
     uint64_t tailThreshold = 32768;   // survivors below this are finished by k_tail (0 = never)
+    // ray reordering experiment (MSNE_SORT=1): sort each bounce's rays by origin cell + direction cell before tracing
+    bool sortRays = false; uint32_t sortOBits = 5, sortDBits = 5, sortDirFirst = 0, sortTileShift = 0; uint64_t sortMin = 1u << 20;
+    DevBuf<uint32_t> sortKeys[2], sortVals[2]; DevBuf<uint8_t> sortTemp;
+    bool logBounces = false;          // MSNE_LOG_BOUNCES=1: queue sizes after every bounce on stderr
     uint64_t binnedThreshold = 262144;   // survivors below this use the single generic shade launch
 
     // profiling
@@ -260,7 +264,21 @@ struct HdMoonshine {
         if (const char* e = getenv("MSNE_BVH")) bvhWidth = atoi(e) == 2 ? 2u : 8u;
         if (const char* e = getenv("MSNE_MAX_LEAF")) maxLeaf = (uint32_t)std::min(8, std::max(1, atoi(e)));
         if (wide()) maxLeaf = std::min(maxLeaf, 3u);   // a wide node addresses its items through a 24-bit mask: 8 children x 3
+        if (const char* e = getenv("MSNE_LOG_BOUNCES")) logBounces = atoi(e) != 0;
+        if (const char* e = getenv("MSNE_SORT")) sortRays = atoi(e) != 0;
+        if (const char* e = getenv("MSNE_SORT_OBITS")) sortOBits = (uint32_t)atoi(e);
+        if (const char* e = getenv("MSNE_SORT_DBITS")) sortDBits = (uint32_t)atoi(e);
+        if (const char* e = getenv("MSNE_SORT_DIRFIRST")) sortDirFirst = (uint32_t)atoi(e);
+        if (const char* e = getenv("MSNE_SORT_TILE")) sortTileShift = (uint32_t)atoi(e);
+        if (const char* e = getenv("MSNE_SORT_MIN")) sortMin = strtoull(e, nullptr, 10);
         if (const char* e = getenv("MSNE_TAIL_THRESHOLD")) tailThreshold = strtoull(e, nullptr, 10);
+        {
+            int wsOn = 0; uint32_t refillMin = 8, leafMin = 16;
+            if (const char* e = getenv("MSNE_TRACE_WS")) wsOn = atoi(e);
+            if (const char* e = getenv("MSNE_REFILL_MIN")) refillMin = (uint32_t)atoi(e);
+            if (const char* e = getenv("MSNE_LEAF_MIN")) leafMin = (uint32_t)atoi(e);
+            setTraceVariant(wsOn, refillMin, leafMin);
+        }
         traceBlocks = smCount * std::max(1, traceOccupancyBlocksPerSm(wide()));
         shadeBlocks = smCount * std::max(1, shadeOccupancyBlocksPerSm());
         CK(cudaStreamSynchronize(stream));
@@ -367,7 +385,7 @@ struct HdMoonshine {
     //     of the transformed instances. Only needed when that set changes (Accel.zig:94-184 equivalent).
     DInstance staticRec{};
     bool haveStatic = false;
-    BuildBox staticBounds{};
+    BuildBox staticBounds{}, worldBounds{};
     uint64_t stats_static_builds = 0, stats_tlas_builds = 0;
     void buildGeometry() {
         blasNodePool.clear(); blasNodePool8.clear(); triPool.clear(); blasByKey.clear(); blases.clear();
@@ -441,6 +459,8 @@ struct HdMoonshine {
             di[i] = d;
         }
         dInstances.upload(di.data(), di.size(), stream);
+        for (int a = 0; a < 3; a++) { worldBounds.lo[a] = 1e30f; worldBounds.hi[a] = -1e30f; }
+        for (const BuildBox& bb : boxes) for (int a = 0; a < 3; a++) { worldBounds.lo[a] = std::min(worldBounds.lo[a], bb.lo[a]); worldBounds.hi[a] = std::max(worldBounds.hi[a], bb.hi[a]); }
         hasTlas = !items.empty();
         tlasStaticOnly = haveStatic && items.size() == 1;
         if (hasTlas && wide()) {
@@ -496,6 +516,7 @@ struct HdMoonshine {
         }
     }
 
+    BuildBox sceneBounds() const { return worldBounds; }
     DeviceScene deviceScene() const {
         DeviceScene sc{};
         sc.tlasNodes = hasTlas && !wide() ? dTlasNodes.p : nullptr;
@@ -650,13 +671,55 @@ struct HdMoonshine {
             CK(cudaMemcpyAsync(&hostCounters[b & 3u], dCounters.p + (buf ^ 1u), sizeof(Counters), cudaMemcpyDeviceToHost, stream));
             CK(cudaEventRecord(bounceEvents[b & 3u], stream));
         };
-        // keep one bounce queued ahead of the one whose survivor count we wait for
         const uint32_t maxIter = k.max_bounces + 4;
+        if (sortRays && !wide()) {
+            // experiment: synchronous bounces (the sort needs the exact queue size on the host)
+            RaySortParams sp{};
+            BuildBox wb = sceneBounds();
+            for (int a = 0; a < 3; a++) { sp.lo[a] = wb.lo[a]; sp.scale[a] = (float)(1u << sortOBits) / std::max(1e-6f, wb.hi[a] - wb.lo[a]); }
+            sp.obits = sortOBits; sp.dbits = sortDBits; sp.dirFirst = sortDirFirst; sp.tileShift = sortTileShift;
+            const int endBit = sortTileShift ? 32 : (int)(3 * sortOBits + 2 * sortDBits + 1);
+            const uint32_t cap3 = 3u * pb.capacity;
+            if (sortKeys[0].n < cap3) {
+                for (int i = 0; i < 2; i++) { sortKeys[i].alloc(cap3); sortVals[i].alloc(cap3); }
+                sortTemp.alloc(raySortTempBytes(cap3));
+            }
+            uint64_t total = lastLive; bool first = true;
+            for (uint32_t b = 0; b < maxIter; b++) {
+                const uint32_t buf = b & 1u;
+                const uint32_t* perm = nullptr;
+                if (!first && total >= sortMin) {
+                    launchRayKeys(stream, pb, ws, buf, sp, sortKeys[0].p, sortVals[0].p, (uint32_t)total);
+                    raySort(stream, sortTemp.p, sortTemp.n, sortKeys[0].p, sortKeys[1].p, sortVals[0].p, sortVals[1].p, (uint32_t)total, endBit);
+                    perm = sortVals[1].p;
+                }
+                first = false;
+                const bool prof = profiling && profUsed < kProfEvents;
+                if (prof) CK(cudaEventRecord(profEv[profUsed][0], stream));
+                launchTrace(stream, traceBlocks, false, sc, pb, ws, buf, perm);
+                if (prof) { CK(cudaEventRecord(profEv[profUsed][1], stream)); profUsed++; }
+                if (lastLive >= binnedThreshold) launchShadeBinned(stream, shadeBlocks, sc, k, pb, ws, buf);
+                else launchShade(stream, shadeBlocks, sc, k, pb, ws, buf);
+                CK(cudaMemcpyAsync(&hostCounters[0], dCounters.p + (buf ^ 1u), sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+                CK(cudaStreamSynchronize(stream));
+                const Counters c = hostCounters[0];
+                lastLive = c.nLive; total = (uint64_t)c.nLive + c.nShadow;
+                if (c.nLive + c.nDead == 0) break;
+                if ((uint64_t)c.nLive + c.nDead < tailThreshold) {
+                    const uint32_t tb = (b + 1) & 1u;
+                    launchTrace(stream, traceBlocks, false, sc, pb, ws, tb);
+                    launchTail(stream, smCount * 4, false, sc, k, pb, ws, tb);
+                    break;
+                }
+            }
+        } else {
+        // keep one bounce queued ahead of the one whose survivor count we wait for
         enqueueBounce(0);
         for (uint32_t b = 0; b < maxIter; b++) {
             enqueueBounce(b + 1);
             CK(cudaEventSynchronize(bounceEvents[b & 3u]));
             const Counters c = hostCounters[b & 3u];
+            if (logBounces) fprintf(stderr, "libmoonshine: bounce %u -> live %u dead %u shadow %u\n", b, c.nLive, c.nDead, c.nShadow);
             lastLive = c.nLive;
             if (c.nLive + c.nDead == 0) break;   // bounce b+1 then runs on empty queues
             if ((uint64_t)c.nLive + c.nDead < tailThreshold) {
@@ -668,6 +731,7 @@ struct HdMoonshine {
                 stats.kernel_launches += 2;
                 break;
             }
+        }
         }
         launchAccumulate(stream, pb.result, s.image.p, s.runState.p + pixOffset, s.pixIds.p + pixOffset, nPix, nSamples, firstSample, k.samples_per_run);
         stats.kernel_launches++;
@@ -1005,6 +1069,25 @@ void HdMoonshineExtResetStats(HdMoonshine* h) {
         CK(cudaMemsetAsync(h->dScalars.p + 3, 0, sizeof(uint32_t), h->stream));
         CK(cudaStreamSynchronize(h->stream));
     )
+}
+
+// ---- object picker (ObjectPicker.zig:89-128) ---------------------------------------------------------
+bool HdMoonshineExtPick(HdMoonshine* h, SensorHandle s, LensHandle l, F32x2 coords, MsneClickData* out) {
+    LOCK(h);
+    try {
+        h->use(); h->syncScene();
+        const Sensor& se = *h->sensors.at(s);
+        DevBuf<MsneClick> d;
+        d.alloc(1);
+        launchPick(h->stream, h->wide(), h->deviceScene(), HdMoonshine::makeCamera(h->lenses.at(l), se.extent.width, se.extent.height), coords.x, coords.y, d.p);
+        h->stats.kernel_launches++;
+        MsneClick c{};
+        CK(cudaMemcpyAsync(&c, d.p, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        out->instance_index = c.instance_index; out->geometry_index = c.geometry_index; out->primitive_index = c.primitive_index;
+        out->barycentrics.x = c.bary[0]; out->barycentrics.y = c.bary[1];
+        return true;
+    } catch (const std::exception& e) { g_lastError = e.what(); return false; }
 }
 
 // ---- debug probes ----------------------------------------------------------------------------------

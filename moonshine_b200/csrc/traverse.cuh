@@ -269,7 +269,8 @@ struct Traversal {
 
 DI uint32_t signExtendS8x4(uint32_t x) { uint32_t r; asm("prmt.b32 %0, %1, 0x0, 0x0000BA98;" : "=r"(r) : "r"(x)); return r; }
 DI uint32_t highBit(uint32_t x) { return 31u - (uint32_t)__clz((int)x); }
-DI float byteToFloat(uint32_t x, int j) { return (float)((x >> (8 * j)) & 0xFFu); }
+// byte j of x as a float without the (1/8-rate) I2F unit: 0x4B0000bb is the float 2^23 + bb, exactly
+DI float byteToFloat(uint32_t x, int j) { return __uint_as_float(__byte_perm(x, 0x4B000000u, 0x7650u + (uint32_t)j)) - 8388608.0f; }
 
 struct WideRay {
     float3 o, d, idir;

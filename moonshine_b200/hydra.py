@@ -67,6 +67,10 @@ class MsneStats(C.Structure):
                 ("static_blas_builds", C.c_uint64), ("tlas_builds", C.c_uint64)]
 
 
+class MsneClickData(C.Structure):   # input.hlsl:1-6
+    _fields_ = [("instance_index", C.c_int32), ("geometry_index", C.c_uint32), ("primitive_index", C.c_uint32), ("barycentrics", F32x2)]
+
+
 # every symbol include/moonshine.h and include/moonshine_ext.h declare: (restype, argtypes)
 _VP = C.c_void_p
 _U32 = C.c_uint32
@@ -114,6 +118,7 @@ SIGNATURES = {
     "HdMoonshineExtSetProfiling": (None, [_VP, C.c_bool]),
     "HdMoonshineExtGetStats": (None, [_VP, C.POINTER(MsneStats)]),
     "HdMoonshineExtResetStats": (None, [_VP]),
+    "HdMoonshineExtPick": (C.c_bool, [_VP, _U32, _U32, F32x2, _VP]),
     "HdMoonshineExtTraceRays": (C.c_bool, [_VP, _VP, C.c_size_t, C.c_bool, _VP]),
     "HdMoonshineExtPrimaryRays": (C.c_bool, [_VP, _U32, _U32, _U32, _VP, _VP]),
     "HdMoonshineExtGetEnvSize": (_U32, [_VP]),
@@ -322,6 +327,15 @@ class HdMoonshine:
             raise RuntimeError("HdMoonshineExtBuildEmitterTable: " + self.last_error())
 
     def set_constants(self, c): self.SetSpecConstants(c)
+
+    def Pick(self, sensor: int, lens: int, x: float, y: float):
+        """ObjectPicker.getClickedObject (ObjectPicker.zig:89-128): (instance, geometry, primitive, (u, v)) or None."""
+        c = MsneClickData()
+        if not self.L.HdMoonshineExtPick(self.h, sensor, lens, F32x2(x, y), C.byref(c)):
+            raise RuntimeError("HdMoonshineExtPick: " + self.last_error())
+        if c.instance_index < 0:
+            return None
+        return (c.instance_index, c.geometry_index, c.primitive_index, (c.barycentrics.x, c.barycentrics.y))
 
     # -- debug probes ------------------------------------------------------------------------------
     def trace(self, rays8, any_hit=False):

@@ -56,6 +56,7 @@ def lib():
         L.OracleRngFloats.argtypes = [C.c_uint32] * 4 + [C.c_void_p]
         L.OraclePrimaryRays.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p]
         L.OracleTrace.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
+        L.OraclePick.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_void_p]
         L.OracleEnvSize.restype = C.c_uint32
         L.OracleEnvSize.argtypes = [C.c_void_p]
         L.OracleEnvData.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -157,6 +158,16 @@ class Oracle:
         la = lens.as_array()
         self.L.OraclePrimaryRays(self.h, _p(la), width, height, sample, _p(rays), _p(st))
         return rays, st
+
+    def pick(self, lens, width, height, x, y):
+        """input.hlsl:24-57: (instance, geometry, primitive, (u, v)) or None."""
+        out = np.zeros(5, np.uint32)
+        la = lens.as_array()
+        self.L.OraclePick(self.h, _p(la), width, height, float(x), float(y), _p(out))
+        if out[0] == 0xFFFFFFFF:
+            return None
+        uv = out[3:5].view(np.float32)
+        return (int(out[0]), int(out[1]), int(out[2]), (float(uv[0]), float(uv[1])))
 
     def trace(self, rays8, any_hit=False, brute=False):
         r = np.ascontiguousarray(rays8, np.float32).reshape(-1, 8)

@@ -199,6 +199,23 @@ void OracleTrace(Oracle* o, const float* rays8, size_t n, int any_hit, int brute
         std::memcpy(h + 3, &its.barycentrics.x, 4); std::memcpy(h + 4, &its.barycentrics.y, 4);
     }
 }
+// shaders/hrtsystem/input.hlsl:24-57 (object picker): uv = (x, -(y - 1)); the ray comes from the UNMODIFIED push-constant
+// camera (the perfect-focus copy made at :29-31 is never used) with lens sample (0,0); closest hit, FORCE_OPAQUE.
+// out5 = {i32 instance (-1 = miss), u32 geometry, u32 primitive, f32 u, f32 v}
+void OraclePick(Oracle* o, const float* lens12, uint32_t W, uint32_t H, float x, float y, uint32_t* out5) {
+    if (o->dirty) commit(o);
+    Lens lens; std::memcpy(&lens, lens12, 48);
+    float2 uv = {x, y};
+    uv.y -= 1.0f;
+    uv.y *= -1.0f;
+    RayDesc r = generateRay(lens, W, H, uv, {0.0f, 0.0f});
+    Intersection its = o->sc.accel.trace(r.Origin, r.Direction, r.TMin, r.TMax, false, false);
+    out5[0] = its.instanceIndex; out5[1] = 0; out5[2] = 0; out5[3] = 0; out5[4] = 0;
+    if (its.instanceIndex != 0xFFFFFFFFu) {
+        out5[1] = its.geometryIndex; out5[2] = its.primitiveIndex;
+        std::memcpy(out5 + 3, &its.barycentrics.x, 4); std::memcpy(out5 + 4, &its.barycentrics.y, 4);
+    }
+}
 uint32_t OracleEnvSize(Oracle* o) { return o->sc.env.size; }
 void OracleEnvData(Oracle* o, float* rgba, float* lum_all_levels) {
     std::memcpy(rgba, o->sc.env.rgb.data(), o->sc.env.rgb.size() * 16);

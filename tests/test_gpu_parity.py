@@ -289,7 +289,7 @@ def test_wide_and_binary_bvh_agree(maker, center, radius):
     rays[::7, 4] = 0.0      # axis-parallel direction components
     rays[::13, 5] = -0.0
     a, b = m8.trace(rays), m2.trace(rays)
-    assert (a["instance"] != 0xFFFFFFFF).mean() > 0.3
+    assert (a["instance"] != 0xFFFFFFFF).mean() > 0.2
     for f in ("instance", "geometry", "primitive"):
         np.testing.assert_array_equal(a[f], b[f])
     np.testing.assert_array_equal(a["u"].view(np.uint32), b["u"].view(np.uint32))
@@ -302,3 +302,26 @@ def test_wide_and_binary_bvh_agree(maker, center, radius):
         m.RenderLaunches(sensor, lens, 2)
         imgs.append(m.ReadSensor(sensor).copy())
     np.testing.assert_array_equal(imgs[0].view(np.uint32), imgs[1].view(np.uint32))
+
+
+def test_object_picker_matches_oracle():
+    """HdMoonshineExtPick (ObjectPicker.zig:89-128 + input.hlsl) against the oracle: ids exact; barycentrics bit-exact
+    with a pinhole lens, within 1e-5 with the thin lens (cos/sin of the lens sample differ by an ulp between libm and CUDA)."""
+    for maker, exact in ((scenes.single_triangle, True), (scenes.cornell_box, True), (scenes.material_zoo, False)):
+        sc = maker()
+        m, o = _pair(sc)
+        sensor, lens = m.CreateSensor(*sc.extent), m.CreateLens(sc.lens)
+        n_hit = 0
+        for y in np.linspace(0.03, 0.97, 17):
+            for x in np.linspace(0.03, 0.97, 17):
+                g, r = m.Pick(sensor, lens, float(x), float(y)), o.pick(sc.lens, *sc.extent, float(x), float(y))
+                assert (g is None) == (r is None)
+                if g is None:
+                    continue
+                n_hit += 1
+                assert g[:3] == r[:3]
+                if exact:
+                    assert np.array(g[3], np.float32).view(np.uint32).tolist() == np.array(r[3], np.float32).view(np.uint32).tolist()
+                else:
+                    np.testing.assert_allclose(g[3], r[3], atol=1e-5)
+        assert n_hit > 20

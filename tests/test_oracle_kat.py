@@ -223,3 +223,19 @@ def test_bsdf_pbr_sample_pdf_consistency():
         assert abs(pdf - s[3]) <= 2e-4 * max(1.0, abs(pdf))
         checked += 1
     assert checked > 200
+
+
+def test_object_picker_follows_input_hlsl():
+    """input.hlsl:24-57: centre of the sensor through the test lens hits the single triangle; a corner misses;
+    y is flipped (coords origin top-left, uv origin bottom-left)."""
+    from moonshine_b200 import scenes
+    from oracle.binding import Oracle
+    sc = scenes.single_triangle()
+    o = Oracle()
+    scenes.load_scene(o, sc)
+    hit = o.pick(sc.lens, 64, 64, 0.5, 0.5)
+    assert hit is not None and hit[:3] == (0, 0, 0)
+    assert o.pick(sc.lens, 64, 64, 0.01, 0.01) is None
+    # the triangle's apex points up (+z): it is hit near the top of the image (small y) but not near the bottom
+    top, bottom = o.pick(sc.lens, 64, 64, 0.5, 0.3), o.pick(sc.lens, 64, 64, 0.5, 0.95)
+    assert top is not None and bottom is None

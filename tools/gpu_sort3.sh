@@ -1,0 +1,11 @@
+#!/bin/bash
+export MSNE_BVH=2
+run() { echo "== $*"; env "$@" python bench.py --steps 3 --warmup 2 --batch-spp 8 --paths-in-flight 16777216 --no-cpu-baseline --e2e-steps 0 2>&1 | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(round(d['value'],1), round(d['ms_per_step'],2), 'trace avg ms', round(d['roofline']['avg_launch_ms'],3), 'share', round(d['roofline']['kernel_share_of_step'],3))"; }
+run MSNE_SORT=1 MSNE_SORT_OBITS=4 MSNE_SORT_DBITS=3
+run MSNE_SORT=1 MSNE_SORT_OBITS=4 MSNE_SORT_DBITS=3 MSNE_SORT_TILE=12
+run MSNE_SORT=1 MSNE_SORT_OBITS=4 MSNE_SORT_DBITS=3 MSNE_SORT_TILE=13
+run MSNE_SORT=1 MSNE_SORT_OBITS=4 MSNE_SORT_DBITS=3 MSNE_SORT_TILE=14
+run MSNE_SORT=1 MSNE_SORT_OBITS=4 MSNE_SORT_DBITS=3 MSNE_SORT_TILE=16
+run MSNE_SORT=1 MSNE_SORT_OBITS=3 MSNE_SORT_DBITS=4 MSNE_SORT_TILE=13
+run MSNE_SORT=1 MSNE_SORT_OBITS=0 MSNE_SORT_DBITS=5 MSNE_SORT_TILE=13
+run MSNE_SORT=1 MSNE_SORT_OBITS=0 MSNE_SORT_DBITS=4 MSNE_SORT_TILE=10
