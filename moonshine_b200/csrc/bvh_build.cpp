@@ -136,132 +136,4 @@ void buildBvh2(const BuildBox* boxes, uint32_t n, uint32_t maxLeaf, BuiltBvh& ou
     }
 }
 
-
-// ------------------------------------------------------------------------------------------------
-// BVH2 -> compressed BVH8
-// ------------------------------------------------------------------------------------------------
-namespace {
-
-struct Ref8 { int32_t parent, slot; };   // a child of the BVH2: (node, slot)
-
-BuildBox childBox(const BvhNode2& n, int s) {
-    const float* xy = s == 0 ? n.n0 : n.n1;
-    BuildBox b;
-    b.lo[0] = xy[0]; b.hi[0] = xy[1]; b.lo[1] = xy[2]; b.hi[1] = xy[3];
-    b.lo[2] = n.n2[s * 2]; b.hi[2] = n.n2[s * 2 + 1];
-    return b;
-}
-float boxArea(const BuildBox& b) {
-    const float dx = b.hi[0] - b.lo[0], dy = b.hi[1] - b.lo[1], dz = b.hi[2] - b.lo[2];
-    return dx * dy + dy * dz + dz * dx;
-}
-
-}  // namespace
-
-void collapseToBvh8(const BuiltBvh& in, BuiltBvh8& out) {
-    out.nodes.clear(); out.order.clear(); out.bounds = in.bounds; out.depth = 1;
-    out.order.reserve(in.order.size());
-    BvhNode8 blank;
-    std::memset(&blank, 0, sizeof(blank));
-    out.nodes.push_back(blank);
-    struct Work { uint32_t wide; int32_t node2; uint32_t level; };
-    std::vector<Work> queue;
-    queue.push_back({0, 0, 1});
-    auto isEmpty = [&](const Ref8& r) { return in.nodes[r.parent].c[r.slot] < 0 && in.nodes[r.parent].c[2 + r.slot] == 0; };
-    auto isLeaf = [&](const Ref8& r) { return in.nodes[r.parent].c[2 + r.slot] > 0; };
-    for (size_t qi = 0; qi < queue.size(); qi++) {
-        const Work w = queue[qi];
-        out.depth = std::max(out.depth, w.level);
-        // ---- gather up to 8 children ------------------------------------------------------------------
-        Ref8 kids[8]; int nk = 0;
-        for (int s = 0; s < 2; s++) { Ref8 r{w.node2, s}; if (!isEmpty(r)) kids[nk++] = r; }
-        for (;;) {
-            int best = -1; float bestA = -1.0f;
-            for (int i = 0; i < nk; i++) {
-                if (isLeaf(kids[i])) continue;
-                const float a = boxArea(childBox(in.nodes[kids[i].parent], kids[i].slot));
-                if (a > bestA) { bestA = a; best = i; }
-            }
-            if (best < 0) break;
-            const int32_t open = in.nodes[kids[best].parent].c[kids[best].slot];
-            Ref8 sub[2]; int ns = 0;
-            for (int s = 0; s < 2; s++) { Ref8 r{open, s}; if (!isEmpty(r)) sub[ns++] = r; }
-            if (nk - 1 + ns > 8) break;
-            kids[best] = kids[nk - 1]; nk--;
-            for (int s = 0; s < ns; s++) kids[nk++] = sub[s];
-            if (nk == 8) break;
-        }
-        // ---- node frame: origin + per-axis power-of-two cell size ----------------------------------------
-        BuildBox kb[8]; BuildBox nb;
-        for (int a = 0; a < 3; a++) { nb.lo[a] = 1e30f; nb.hi[a] = -1e30f; }
-        for (int i = 0; i < nk; i++) {
-            kb[i] = childBox(in.nodes[kids[i].parent], kids[i].slot);
-            for (int a = 0; a < 3; a++) { nb.lo[a] = std::min(nb.lo[a], kb[i].lo[a]); nb.hi[a] = std::max(nb.hi[a], kb[i].hi[a]); }
-        }
-        if (nk == 0) for (int a = 0; a < 3; a++) nb.lo[a] = nb.hi[a] = 0.0f;
-        BvhNode8 n = blank;
-        double cell[3];
-        for (int a = 0; a < 3; a++) {
-            n.p[a] = nb.lo[a];
-            const double ext = (double)nb.hi[a] - (double)nb.lo[a];
-            int e = ext > 0.0 ? (int)std::ceil(std::log2(ext / 255.0)) : -126;
-            e = std::max(-126, std::min(126, e));
-            while (e < 126 && std::ceil(ext / std::ldexp(1.0, e)) > 255.0) e++;
-            n.e[a] = (uint8_t)(e + 127);
-            cell[a] = std::ldexp(1.0, e);
-        }
-        // ---- slot assignment: greedy maximisation of sum dot(child centre - node centre, slot direction) ---
-        int slotOf[8]; bool slotUsed[8] = {false}; bool kidDone[8] = {false};
-        float cost[8][8];
-        for (int i = 0; i < nk; i++)
-            for (int s = 0; s < 8; s++) {
-                float c = 0.0f;
-                for (int a = 0; a < 3; a++) {
-                    const float d = 0.5f * (kb[i].lo[a] + kb[i].hi[a]) - 0.5f * (nb.lo[a] + nb.hi[a]);
-                    c += ((s >> a) & 1) ? d : -d;
-                }
-                cost[i][s] = c;
-            }
-        for (int it = 0; it < nk; it++) {
-            int bi = -1, bs = -1; float bc = -1e38f;
-            for (int i = 0; i < nk; i++) {
-                if (kidDone[i]) continue;
-                for (int s = 0; s < 8; s++) if (!slotUsed[s] && cost[i][s] > bc) { bc = cost[i][s]; bi = i; bs = s; }
-            }
-            slotOf[bi] = bs; slotUsed[bs] = true; kidDone[bi] = true;
-        }
-        int kidAt[8];
-        for (int s = 0; s < 8; s++) kidAt[s] = -1;
-        for (int i = 0; i < nk; i++) kidAt[slotOf[i]] = i;
-        // ---- emit children in slot order ------------------------------------------------------------------
-        n.childBase = (uint32_t)out.nodes.size();
-        n.itemBase = (uint32_t)out.order.size();
-        for (int s = 0; s < 8; s++) {
-            for (int a = 0; a < 3; a++) { n.qlo[a][s] = 255; n.qhi[a][s] = 0; }   // empty slot: inverted box
-            const int i = kidAt[s];
-            if (i < 0) continue;
-            for (int a = 0; a < 3; a++) {
-                double lo = std::floor(((double)kb[i].lo[a] - (double)n.p[a]) / cell[a]);
-                double hi = std::ceil(((double)kb[i].hi[a] - (double)n.p[a]) / cell[a]);
-                lo = std::max(0.0, std::min(255.0, lo)); hi = std::max(0.0, std::min(255.0, hi));
-                n.qlo[a][s] = (uint8_t)lo; n.qhi[a][s] = (uint8_t)hi;
-            }
-            const BvhNode2& par = in.nodes[kids[i].parent];
-            const int32_t child = par.c[kids[i].slot], count = par.c[2 + kids[i].slot];
-            if (count > 0) {
-                const uint32_t off = (uint32_t)out.order.size() - n.itemBase;
-                n.meta[s] = (uint8_t)((((1u << count) - 1u) << 5) | off);
-                for (int32_t k = 0; k < count; k++) out.order.push_back(in.order[child + k]);
-            } else {
-                n.meta[s] = (uint8_t)(0x20u | (24u + (uint32_t)s));
-                n.imask |= (uint8_t)(1u << s);
-                const uint32_t idx = (uint32_t)out.nodes.size();
-                out.nodes.push_back(blank);
-                queue.push_back({idx, child, w.level + 1});
-            }
-        }
-        out.nodes[w.wide] = n;
-    }
-}
-
 }  // namespace msne

@@ -19,18 +19,6 @@ struct BuiltBvh {
 // `maxLeaf` items per leaf at most. Leaf children reference [first, first+count) in `order`.
 void buildBvh2(const BuildBox* boxes, uint32_t n, uint32_t maxLeaf, BuiltBvh& out);
 
-// Collapses a BVH2 into the compressed 8-wide layout of dtypes.h (greedy: repeatedly open the child with the
-// largest surface area until the node has 8 children). Leaves keep the BVH2 leaves (<= 3 items each, so a node's
-// items fit the 24-bit item mask). `order` maps the new item slots to the caller's item indices; `depth` is the
-// number of node levels (bounds the traversal stack).
-struct BuiltBvh8 {
-    std::vector<BvhNode8> nodes;   // nodes[0] is the root; childBase / itemBase are local to nodes / order
-    std::vector<uint32_t> order;
-    BuildBox bounds;
-    uint32_t depth = 0;
-};
-void collapseToBvh8(const BuiltBvh& in, BuiltBvh8& out);
-
 // outward padding that keeps the FP32 slab test conservative w.r.t. the exact triangle test
 inline void padBox(BuildBox& b) {
     float ext = 1e-3f, mag = 0.0f;

@@ -32,24 +32,6 @@ struct BvhNode2 {
 };
 static_assert(sizeof(BvhNode2) == 64, "BvhNode2 must be 64 B");
 
-// Compressed wide BVH node (8 children, 80 B = five 16-byte loads; after Ylitie, Karras, Laine, "Efficient
-// incoherent ray traversal on GPUs through compressed wide BVHs", HPG 2017):
-//   n0 = (p.xyz, e.x | e.y<<8 | e.z<<16 | imask<<24)   p = node box lo; child planes = p + q * 2^(e-127), q in 0..255
-//   n1 = (childBase, itemBase, meta[0..3], meta[4..7])  imask bit s = slot s holds an inner node; inner children are
-//        nodes[childBase + popc(imask & ((1<<s)-1))]; a leaf child's items are items[itemBase + (meta&31) ...]
-//   n2 = (qlo.x[0..3], qlo.x[4..7], qlo.y[0..3], qlo.y[4..7])  n3 = (qlo.z.., qlo.z.., qhi.x.., qhi.x..)  n4 = (qhi.y.., qhi.y.., qhi.z.., qhi.z..)
-// meta: 0 = empty; inner = 0x20 | (24 + slot); leaf = unary item count (1,3,7) << 5 | first item offset (0..23).
-// Slots are assigned so that visiting them in the order (slot ^ ray octant) is approximately front to back.
-// "items" are triangles (BLAS pool) or TLAS slots (one instance each).
-struct BvhNode8 {
-    float p[3];
-    uint8_t e[3], imask;
-    uint32_t childBase, itemBase;
-    uint8_t meta[8];
-    uint8_t qlo[3][8], qhi[3][8];
-};
-static_assert(sizeof(BvhNode8) == 80, "BvhNode8 must be 80 B");
-
 static const int32_t REF_ITEM = 0x40000000, REF_EMPTY = 0x7FFFFFFD, REF_LEAVE = 0x7FFFFFFE, REF_END = 0x7FFFFFFF;
 
 // Triangle record, 48 B: three vertices in object space + ids (watertight edge test needs all three)
@@ -102,11 +84,6 @@ struct DeviceScene {
     uint32_t envLevels;
     uint32_t envLevelOffset[12];   // float offset of each mip inside envLum
     const float* srgbLut;          // 256 floats
-    // compressed wide BVH (bvhWidth == 8): same two levels, same triangle / instance tables
-    const BvhNode8* tlasNodes8;    // may be null when there are no visible instances
-    const BvhNode8* blasNodes8;
-    uint32_t staticOnly;           // 1: the TLAS holds nothing but the merged static BLAS -> traversal starts at staticRoot
-    uint32_t staticRoot;
 };
 
 // specialization constants (main.hlsl:34-40) as runtime values

@@ -17,7 +17,6 @@
 // order. Compiled with -fmad=false (see device_math.cuh).
 #include "kernels.h"
 #include <cstdlib>
-#include <cub/device/device_radix_sort.cuh>
 #include "shading.cuh"
 #include "traverse.cuh"
 
@@ -108,7 +107,7 @@ DI uint32_t hitBin(const DeviceScene& sc, const HitRec& h) {
 #ifndef DYN_FETCH_MIN
 #define DYN_FETCH_MIN 0   // 0 = off. Measured on cfg3: 12/20/24 were 10-18 % slower than off (profiles/r01_sweeps.md)
 #endif
-__global__ void __launch_bounds__(TRACE_THREADS, TRACE_BLOCKS_PER_SM) k_trace(DeviceScene sc, PathBuffers pb, WaveState ws, uint32_t buf, const uint32_t* __restrict__ perm) {
+__global__ void __launch_bounds__(TRACE_THREADS, TRACE_BLOCKS_PER_SM) k_trace(DeviceScene sc, PathBuffers pb, WaveState ws, uint32_t buf) {
     const Counters cin = ws.counters[buf];
     const uint32_t nLive = cin.nLive, total = cin.nLive + cin.nShadow;
     const uint32_t lane = threadIdx.x & 31;
@@ -131,7 +130,6 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_BLOCKS_PER_SM) k_trace(De
                 idx = base + (uint32_t)__popc(idle & ltMask);
                 if (idx < total) {
                     active = true;
-                    if (perm != nullptr) idx = __ldg(perm + idx);   // coherence-sorted order (k_ray_keys): extension rays still come first
                     if (idx < nLive) {
                         const float4 r0 = pb.R0[buf][idx], r1 = pb.R1[buf][idx];
                         tv.begin(sc, stack, mk3(r0.x, r0.y, r0.z), mk3(r1.x, r1.y, r1.z), 0.0f, MS_INFINITY);
@@ -183,299 +181,16 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_BLOCKS_PER_SM) k_trace(De
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// Warp-synchronous trace kernel (binary BVH). Same per-ray arithmetic and results as k_trace; what changes is how
-// the 32 lanes of a warp are kept busy. ncu on k_trace (profiles/r02_trace_lanes.md): incoherent rays run at 10-15 of
-// 32 lanes because (a) a warp waits for its longest ray and (b) a lane that holds two leaves waits until EVERY lane
-// has left the node loop. Here the whole warp iterates one loop: [retire + refill] -> NODE_STEPS node steps ->
-// triangle phase as soon as `leafMin` lanes hold a leaf (or nobody can descend) -> level changes.
-// Finished lanes are refilled from the ticket counter once `refillMin` of them are idle, so closest-hit and any-hit
-// rays can share a warp (per-lane flag instead of a template parameter).
-// ------------------------------------------------------------------------------------------------
-#ifndef TRACEW_BLOCKS_PER_SM
-#define TRACEW_BLOCKS_PER_SM 8
-#endif
-#ifndef TRACEW_NODE_STEPS
-#define TRACEW_NODE_STEPS 2
-#endif
-__global__ void __launch_bounds__(TRACE_THREADS, TRACEW_BLOCKS_PER_SM) k_trace_ws(DeviceScene sc, PathBuffers pb, WaveState ws, uint32_t buf, const uint32_t* __restrict__ perm,
-                                                                                  uint32_t refillMin, uint32_t leafMin) {
-    const uint32_t FULL = 0xFFFFFFFFu;
-    const Counters cin = ws.counters[buf];
-    const uint32_t nLive = cin.nLive, total = cin.nLive + cin.nShadow;
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t ltMask = (1u << lane) - 1u;
-    int stack[MSNE_STACK];
-    int sp = 0, node = REF_END, leaf = 0;
-    float3 o = mk3(0.f), d = mk3(0.f);
-    float tmax = 0.0f, bestT = 0.0f;
-    SpaceRay ray; ray.set(mk3(0.f), mk3(1.f, 0.f, 0.f));
-    HitRec hit; hit.inst = MISS_ID; hit.tri = 0; hit.u = 0.f; hit.v = 0.f;
-    const BvhNode2* nodes = sc.tlasNodes;
-    uint32_t curInst = MISS_ID, target = 0, idx = 0;
-    bool have = false, anyHit = false;
-    bool more = total > 0 && sc.tlasNodes != nullptr;
-    if (sc.tlasNodes == nullptr && total > 0) {
-        // no geometry: every extension ray misses, no shadow ray is occluded
-        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nLive; i += gridDim.x * blockDim.x) {
-            pb.H[i] = make_uint4(MISS_ID, 0u, 0u, 0u);
-            pb.typeList[(size_t)BIN_MISS * pb.capacity + atomicAdd(ws.typeCount + BIN_MISS, 1u)] = i;
-        }
-    }
-    for (;;) {
-        // ---- retire finished rays, refill idle lanes ----------------------------------------------------------
-        const bool fin = have && node == REF_END && leaf == 0;
-        const uint32_t mFin = __ballot_sync(FULL, fin);
-        const uint32_t mIdle = __ballot_sync(FULL, !have) | mFin;
-        if (mIdle == FULL || (more && (uint32_t)__popc(mIdle) >= refillMin)) {
-            uint32_t bin = 0xFFu;
-            if (fin) {
-                have = false;
-                if (!anyHit) {
-                    pb.H[idx] = make_uint4(hit.inst, hit.tri, __float_as_uint(hit.u), __float_as_uint(hit.v));
-                    bin = hitBin(sc, hit);
-                } else if (hit.inst != MISS_ID) {
-                    float4* n = (target & 1u) ? pb.N1[buf] : pb.N0[buf];
-                    n[target >> 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            }
-            const uint32_t peers = __match_any_sync(FULL, bin);
-            if (bin != 0xFFu) {
-                const int leader = __ffs(peers) - 1;
-                uint32_t slot = 0;
-                if ((int)lane == leader) slot = atomicAdd(ws.typeCount + bin, (uint32_t)__popc(peers));
-                slot = __shfl_sync(peers, slot, leader) + __popc(peers & ltMask);
-                pb.typeList[(size_t)bin * pb.capacity + slot] = idx;
-            }
-            if (more) {
-                const uint32_t n = (uint32_t)__popc(mIdle);
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(ws.traceTicket, n);
-                base = __shfl_sync(FULL, base, 0);
-                more = base + n < total;
-                if (!have) {
-                    const uint32_t pos = base + (uint32_t)__popc(mIdle & ltMask);
-                    if (pos < total) {
-                        idx = perm != nullptr ? __ldg(perm + pos) : pos;
-                        have = true;
-                        float4 a, b;
-                        if (idx < nLive) { a = pb.R0[buf][idx]; b = pb.R1[buf][idx]; anyHit = false; tmax = MS_INFINITY; }
-                        else { a = pb.Q0[idx - nLive]; b = pb.Q1[idx - nLive]; anyHit = true; tmax = a.w; target = __float_as_uint(b.w); }
-                        o = mk3(a.x, a.y, a.z); d = mk3(b.x, b.y, b.z);
-                        bestT = tmax;
-                        hit.inst = MISS_ID; hit.tri = 0; hit.u = 0.0f; hit.v = 0.0f;
-                        ray.set(o, d);
-                        nodes = sc.tlasNodes; curInst = MISS_ID;
-                        sp = 0; stack[sp++] = REF_END;
-                        node = 0; leaf = 0;
-                    }
-                }
-            }
-            if (__ballot_sync(FULL, have) == 0u) break;
-        }
-        // ---- node steps ---------------------------------------------------------------------------------------
-#pragma unroll
-        for (int k = 0; k < TRACEW_NODE_STEPS; k++) {
-            if ((uint32_t)node < (uint32_t)REF_ITEM) {
-                const float4* np = reinterpret_cast<const float4*>(nodes + node);
-                const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
-                const int2 c = __ldg(reinterpret_cast<const int2*>(np + 3));
-                float tn0, tn1;
-                const bool h0 = slab(ray, n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, 0.0f, bestT, tn0) && c.x != REF_EMPTY;
-                const bool h1 = slab(ray, n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, 0.0f, bestT, tn1) && c.y != REF_EMPTY;
-                if (h0 && h1) {
-                    const bool swap = tn1 < tn0;
-                    node = swap ? c.y : c.x;
-                    const int far = swap ? c.x : c.y;
-                    if (sp < MSNE_STACK) stack[sp++] = far;
-                } else if (h0) node = c.x;
-                else if (h1) node = c.y;
-                else node = stack[--sp];
-                if (node < 0 && leaf == 0) { leaf = node; node = stack[--sp]; }
-            }
-        }
-        // ---- triangle phase: when enough lanes hold a leaf, or nobody can descend any further -------------------
-        const uint32_t mLeaf = __ballot_sync(FULL, leaf != 0);
-        const uint32_t mInner = __ballot_sync(FULL, (uint32_t)node < (uint32_t)REF_ITEM);
-        if (mLeaf != 0u && ((uint32_t)__popc(mLeaf) >= leafMin || mInner == 0u)) {
-            if (leaf != 0) {
-                const uint32_t x = ~(uint32_t)leaf;
-                const uint32_t first = x >> 3, count = (x & 7u) + 1u;
-                leaf = 0;
-                for (uint32_t i = 0; i < count; i++) {
-                    const float4* tp = reinterpret_cast<const float4*>(sc.tris + (first + i));
-                    const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
-                    float t, u, v;
-                    if (!triTest(t0, t1, t2, ray, 0.0f, tmax, t, u, v)) continue;
-                    const uint32_t inst = curInst == STATIC_INST ? __float_as_uint(t2.w) : curInst;
-                    if (anyHit) { hit.inst = inst; node = REF_END; sp = 0; break; }
-                    bool better = t < bestT;
-                    if (!better && t == bestT && hit.inst != MISS_ID) {
-                        if (inst != hit.inst) better = inst < hit.inst;
-                        else {
-                            const uint32_t g = __float_as_uint(t0.w), p = __float_as_uint(t1.w);
-                            const uint32_t bg = sc.tris[hit.tri].geom, bp = sc.tris[hit.tri].prim;
-                            better = g != bg ? g < bg : p < bp;
-                        }
-                    }
-                    if (better) { bestT = t; hit.inst = inst; hit.tri = first + i; hit.u = u; hit.v = v; }
-                }
-                if (node < 0) { leaf = node; node = stack[--sp]; }
-            }
-        }
-        // ---- level changes (only with no leaf parked: a parked leaf belongs to the current object space) --------
-        if (leaf == 0 && (uint32_t)node >= (uint32_t)REF_ITEM && node != REF_END) {
-            if (node == REF_LEAVE) {
-                ray.set(o, d); nodes = sc.tlasNodes; curInst = MISS_ID;
-                node = stack[--sp];
-            } else {
-                const uint32_t inst = __ldg(sc.tlasItems + (node & ~REF_ITEM));
-                const DInstance* in = sc.instances + inst;
-                if (__ldg(&in->isStatic)) {
-                    curInst = STATIC_INST;
-                } else {
-                    const float4* mp = reinterpret_cast<const float4*>(in->w2o);
-                    const float4 r0 = __ldg(mp), r1 = __ldg(mp + 1), r2 = __ldg(mp + 2);
-                    const float3 oo = mk3(((r0.x * o.x + r0.y * o.y) + r0.z * o.z) + r0.w, ((r1.x * o.x + r1.y * o.y) + r1.z * o.z) + r1.w,
-                                          ((r2.x * o.x + r2.y * o.y) + r2.z * o.z) + r2.w);
-                    const float3 od = mk3((r0.x * d.x + r0.y * d.y) + r0.z * d.z, (r1.x * d.x + r1.y * d.y) + r1.z * d.z, (r2.x * d.x + r2.y * d.y) + r2.z * d.z);
-                    ray.set(oo, od);
-                    curInst = inst;
-                }
-                nodes = sc.blasNodes;
-                if (sp < MSNE_STACK) stack[sp++] = REF_LEAVE;
-                node = (int)__ldg(&in->blasRoot);
-            }
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const uint32_t done = atomicAdd(ws.traceDone, 1u);
-        if (done == gridDim.x - 1) {
-            *ws.traceTicket = 0; *ws.traceDone = 0;
-            ws.rayCounts[0] += nLive; ws.rayCounts[1] += cin.nShadow;
-            __threadfence();
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// ray reordering: sort key = [shadow | Morton code of the origin cell | Morton code of the octahedral direction cell]
-// ------------------------------------------------------------------------------------------------
-DI uint32_t spread3(uint32_t v) {   // 10 bits -> every third bit
-    v = (v | (v << 16)) & 0x030000FFu; v = (v | (v << 8)) & 0x0300F00Fu; v = (v | (v << 4)) & 0x030C30C3u; v = (v | (v << 2)) & 0x09249249u;
-    return v;
-}
-DI uint32_t spread2(uint32_t v) {   // 16 bits -> every second bit
-    v = (v | (v << 8)) & 0x00FF00FFu; v = (v | (v << 4)) & 0x0F0F0F0Fu; v = (v | (v << 2)) & 0x33333333u; v = (v | (v << 1)) & 0x55555555u;
-    return v;
-}
-__global__ void __launch_bounds__(256) k_ray_keys(PathBuffers pb, WaveState ws, uint32_t buf, RaySortParams sp, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals, uint32_t nMax) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nMax) return;
-    const Counters cin = ws.counters[buf];
-    const uint32_t nLive = cin.nLive, total = cin.nLive + cin.nShadow;
-    vals[i] = i;
-    if (i >= total) { keys[i] = 0xFFFFFFFFu; return; }
-    float4 a, b;
-    if (i < nLive) { a = pb.R0[buf][i]; b = pb.R1[buf][i]; } else { a = pb.Q0[i - nLive]; b = pb.Q1[i - nLive]; }
-    const float omax = (float)((1u << sp.obits) - 1u);
-    const uint32_t qx = (uint32_t)fminf(fmaxf((a.x - sp.lo[0]) * sp.scale[0], 0.0f), omax);
-    const uint32_t qy = (uint32_t)fminf(fmaxf((a.y - sp.lo[1]) * sp.scale[1], 0.0f), omax);
-    const uint32_t qz = (uint32_t)fminf(fmaxf((a.z - sp.lo[2]) * sp.scale[2], 0.0f), omax);
-    const uint32_t mo = spread3(qx) | (spread3(qy) << 1) | (spread3(qz) << 2);
-    // octahedral map of the direction to [0,1]^2
-    const float inv = 1.0f / (fabsf(b.x) + fabsf(b.y) + fabsf(b.z));
-    float u = b.x * inv, v = b.y * inv;
-    if (b.z < 0.0f) { const float uu = (1.0f - fabsf(v)) * (u >= 0.0f ? 1.0f : -1.0f), vv = (1.0f - fabsf(u)) * (v >= 0.0f ? 1.0f : -1.0f); u = uu; v = vv; }
-    const float dmax = (float)((1u << sp.dbits) - 1u);
-    const uint32_t du = (uint32_t)fminf(fmaxf((u * 0.5f + 0.5f) * (dmax + 1.0f), 0.0f), dmax);
-    const uint32_t dv = (uint32_t)fminf(fmaxf((v * 0.5f + 0.5f) * (dmax + 1.0f), 0.0f), dmax);
-    const uint32_t md = spread2(du) | (spread2(dv) << 1);
-    const uint32_t shadowBit = i < nLive ? 0u : 1u;
-    uint32_t key;
-    if (sp.dirFirst) key = (md << (3u * sp.obits)) | mo;
-    else key = (mo << (2u * sp.dbits)) | md;
-    const uint32_t kb = 3u * sp.obits + 2u * sp.dbits;
-    if (sp.tileShift) {
-        // tile-local ordering: rays only move inside their tile of 2^tileShift consecutive queue slots
-        const uint32_t tile = (i < nLive ? i : i - nLive) >> sp.tileShift;
-        keys[i] = (shadowBit << 31) | (tile << kb) | key;
-        return;
-    }
-    keys[i] = key | (shadowBit << kb);
-}
-
-template <bool ANY_HIT, bool WIDE>
-DI bool traceScene(const DeviceScene& sc, const float3 o, const float3 d, const float tmin, const float tmax, HitRec& hit) {
-    if (WIDE) return traceRay8<ANY_HIT>(sc, o, d, tmin, tmax, hit);
-    return traceRay<ANY_HIT>(sc, o, d, tmin, tmax, hit);
-}
-
-// Same contract as k_trace on the compressed wide BVH (traverse.cuh traceRay8): persistent warps pull 32-ray
-// tickets from the joint index space [extension rays | shadow rays], every lane walks its ray to the end, then the
-// warp bins its hits by material type.
-__global__ void __launch_bounds__(TRACE_THREADS, TRACE8_BLOCKS_PER_SM) k_trace8(DeviceScene sc, PathBuffers pb, WaveState ws, uint32_t buf) {
-    const Counters cin = ws.counters[buf];
-    const uint32_t nLive = cin.nLive, total = cin.nLive + cin.nShadow;
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t ltMask = (1u << lane) - 1u;
-    for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(ws.traceTicket, 32u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
-        if (base >= total) break;
-        const uint32_t idx = base + lane;
-        uint32_t bin = 0xFFu;
-        if (idx < nLive) {
-            const float4 r0 = pb.R0[buf][idx], r1 = pb.R1[buf][idx];
-            HitRec h;
-            traceRay8<false>(sc, mk3(r0.x, r0.y, r0.z), mk3(r1.x, r1.y, r1.z), 0.0f, MS_INFINITY, h);
-            pb.H[idx] = make_uint4(h.inst, h.tri, __float_as_uint(h.u), __float_as_uint(h.v));
-            bin = hitBin(sc, h);
-        } else if (idx < total) {
-            const float4 q0 = pb.Q0[idx - nLive], q1 = pb.Q1[idx - nLive];
-            HitRec h;
-            if (traceRay8<true>(sc, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), 0.0f, q0.w, h)) {
-                const uint32_t target = __float_as_uint(q1.w);
-                float4* n = (target & 1u) ? pb.N1[buf] : pb.N0[buf];
-                n[target >> 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
-        // warp-level sort by material id: lanes with the same bin elect a leader that reserves their slots
-        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, bin);
-        if (bin != 0xFFu) {
-            const int leader = __ffs(peers) - 1;
-            uint32_t slot = 0;
-            if ((int)lane == leader) slot = atomicAdd(ws.typeCount + bin, (uint32_t)__popc(peers));
-            slot = __shfl_sync(peers, slot, leader) + __popc(peers & ltMask);
-            pb.typeList[(size_t)bin * pb.capacity + slot] = idx;
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const uint32_t done = atomicAdd(ws.traceDone, 1u);
-        if (done == gridDim.x - 1) {
-            *ws.traceTicket = 0; *ws.traceDone = 0;
-            ws.rayCounts[0] += nLive; ws.rayCounts[1] += cin.nShadow;
-            __threadfence();
-        }
-    }
-}
-
 // debug probe: arbitrary rays (HdMoonshineExtTraceRays); rays8 = {o, tmin, d, tmax}
-template <bool WIDE>
 __global__ void k_trace_probe(DeviceScene sc, const float* __restrict__ rays8, uint32_t n, int anyHit, uint32_t* hits5) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float* r = rays8 + 8 * (size_t)i;
     HitRec h;
     uint32_t geom = 0, prim = 0;
-    if (anyHit) traceScene<true, WIDE>(sc, mk3(r[0], r[1], r[2]), mk3(r[4], r[5], r[6]), r[3], r[7], h);
+    if (anyHit) traceRay<true>(sc, mk3(r[0], r[1], r[2]), mk3(r[4], r[5], r[6]), r[3], r[7], h);
     else {
-        traceScene<false, WIDE>(sc, mk3(r[0], r[1], r[2]), mk3(r[4], r[5], r[6]), r[3], r[7], h);
+        traceRay<false>(sc, mk3(r[0], r[1], r[2]), mk3(r[4], r[5], r[6]), r[3], r[7], h);
         if (h.inst != MISS_ID) { geom = sc.tris[h.tri].geom; prim = sc.tris[h.tri].prim; }
     }
     uint32_t* o = hits5 + 5 * (size_t)i;
@@ -485,7 +200,6 @@ __global__ void k_trace_probe(DeviceScene sc, const float* __restrict__ rays8, u
 // object picker (shaders/hrtsystem/input.hlsl:24-57): one closest-hit query through normalized sensor coordinates
 // with lens sample (0,0). The HLSL edits a local copy of the camera (perfect focus) but then generates the ray
 // from the unmodified push constant (input.hlsl:28-32) - restated as written, i.e. the lens is used as is.
-template <bool WIDE>
 __global__ void k_pick(DeviceScene sc, DCamera cam, float2 coords, MsneClick* out) {
     float2 uv = coords;
     uv.y -= 1.0f;
@@ -493,7 +207,7 @@ __global__ void k_pick(DeviceScene sc, DCamera cam, float2 coords, MsneClick* ou
     float3 o, d;
     cameraRayUV(cam, uv, mk2(0.0f, 0.0f), o, d);
     HitRec h;
-    traceScene<false, WIDE>(sc, o, d, 0.0f, MS_INFINITY, h);
+    traceRay<false>(sc, o, d, 0.0f, MS_INFINITY, h);
     MsneClick c;
     c.instance_index = -1; c.geometry_index = 0; c.primitive_index = 0; c.bary[0] = 0.0f; c.bary[1] = 0.0f;
     if (h.inst != MISS_ID) {
@@ -771,7 +485,6 @@ __global__ void __launch_bounds__(SHADE_THREADS, MIN_BLOCKS) k_shade(DeviceScene
 // path ends. Same device functions, same per-path order of operations -> bit-identical results.
 // Precondition: k_trace has just run on `buf` (H holds this bounce's hits, pending shadow rays are resolved).
 // ------------------------------------------------------------------------------------------------
-template <bool WIDE>
 __global__ void __launch_bounds__(128) k_tail(DeviceScene sc, DConstants k, PathBuffers pb, WaveState ws, uint32_t buf) {
     const Counters cin = ws.counters[buf];
     const uint32_t nLive = cin.nLive, total = cin.nLive + cin.nDead, P = pb.capacity;
@@ -789,19 +502,19 @@ __global__ void __launch_bounds__(128) k_tail(DeviceScene sc, DConstants k, Path
             HitRec h;
             if (out.envRay) {
                 nShadow++;
-                if (traceScene<true, WIDE>(sc, mk3(out.envQ0.x, out.envQ0.y, out.envQ0.z), mk3(out.envQ1.x, out.envQ1.y, out.envQ1.z), 0.0f, out.envQ0.w, h))
+                if (traceRay<true>(sc, mk3(out.envQ0.x, out.envQ0.y, out.envQ0.z), mk3(out.envQ1.x, out.envQ1.y, out.envQ1.z), 0.0f, out.envQ0.w, h))
                     out.N0 = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             if (out.meshRay) {
                 nShadow++;
-                if (traceScene<true, WIDE>(sc, mk3(out.meshQ0.x, out.meshQ0.y, out.meshQ0.z), mk3(out.meshQ1.x, out.meshQ1.y, out.meshQ1.z), 0.0f, out.meshQ0.w, h))
+                if (traceRay<true>(sc, mk3(out.meshQ0.x, out.meshQ0.y, out.meshQ0.z), mk3(out.meshQ1.x, out.meshQ1.y, out.meshQ1.z), 0.0f, out.meshQ0.w, h))
                     out.N1 = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             pb.R0[buf][q] = out.R0; pb.R1[buf][q] = out.R1; pb.S0[buf][q] = out.S0; pb.S1[buf][q] = out.S1;
             pb.N0[buf][q] = out.N0; pb.N1[buf][q] = out.N1;
             if (out.kind == 1) {
                 nClosest++;
-                traceScene<false, WIDE>(sc, mk3(out.R0.x, out.R0.y, out.R0.z), mk3(out.R1.x, out.R1.y, out.R1.z), 0.0f, MS_INFINITY, h);
+                traceRay<false>(sc, mk3(out.R0.x, out.R0.y, out.R0.z), mk3(out.R1.x, out.R1.y, out.R1.z), 0.0f, MS_INFINITY, h);
                 pb.H[q] = make_uint4(h.inst, h.tri, __float_as_uint(h.u), __float_as_uint(h.v));
             }
         }
@@ -901,30 +614,14 @@ __global__ void k_env_fold(const float* __restrict__ srcMip, float* dstMip, uint
 // ------------------------------------------------------------------------------------------------
 // host-callable launch wrappers
 // ------------------------------------------------------------------------------------------------
-static int g_traceWs = 0;
-static uint32_t g_refillMin = 8, g_leafMin = 16;
 static inline dim3 grid1(uint64_t n, uint32_t block) { return dim3((uint32_t)((n + block - 1) / block)); }
 
 void launchGenerate(cudaStream_t st, const DCamera& cam, const DConstants& k, const PathBuffers& pb, Counters* counters, const uint32_t* pixIds,
                     uint32_t nPix, uint32_t nSamples, uint32_t firstSample) {
     k_generate<<<grid1((uint64_t)nPix * nSamples, 256), 256, 0, st>>>(cam, k, pb, counters, pixIds, nPix, nSamples, firstSample);
 }
-void launchTrace(cudaStream_t st, int blocks, bool wide, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const uint32_t* perm) {
-    if (wide) k_trace8<<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf);
-    else if (g_traceWs) k_trace_ws<<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf, perm, g_refillMin, g_leafMin);
-    else k_trace<<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf, perm);
-}
-void setTraceVariant(int warpSync, uint32_t refillMin, uint32_t leafMin) { g_traceWs = warpSync; g_refillMin = refillMin; g_leafMin = leafMin; }
-void launchRayKeys(cudaStream_t st, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const RaySortParams& sp, uint32_t* keys, uint32_t* vals, uint32_t nMax) {
-    k_ray_keys<<<grid1(nMax, 256), 256, 0, st>>>(pb, ws, buf, sp, keys, vals, nMax);
-}
-size_t raySortTempBytes(uint32_t n) {
-    size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, 0, 32, (cudaStream_t)0);
-    return bytes;
-}
-void raySort(cudaStream_t st, void* temp, size_t tempBytes, const uint32_t* keysIn, uint32_t* keysOut, const uint32_t* valsIn, uint32_t* valsOut, uint32_t n, int endBit) {
-    cub::DeviceRadixSort::SortPairs(temp, tempBytes, keysIn, keysOut, valsIn, valsOut, (int)n, 0, endBit, st);
+void launchTrace(cudaStream_t st, int blocks, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf) {
+    k_trace<<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf);
 }
 // Register caps (measured, profiles/r01_sweeps.md): the all-material kernel runs best at 80 registers
 // (6 blocks/SM); the specialised kernels are smaller and take the same cap.
@@ -942,9 +639,8 @@ void launchShadeBinned(cudaStream_t st, int blocks, const DeviceScene& sc, const
     k_shade<2, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, 0u);   // PerfectMirror
     k_shade<4, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, 1u);   // miss + dead
 }
-void launchTail(cudaStream_t st, int blocks, bool wide, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf) {
-    if (wide) k_tail<true><<<blocks, 128, 0, st>>>(sc, k, pb, ws, buf);
-    else k_tail<false><<<blocks, 128, 0, st>>>(sc, k, pb, ws, buf);
+void launchTail(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf) {
+    k_tail<<<blocks, 128, 0, st>>>(sc, k, pb, ws, buf);
 }
 void launchAccumulate(cudaStream_t st, const float4* result, float4* image, float4* runState, const uint32_t* pixIds, uint32_t nPix, uint32_t nSamples,
                       uint32_t firstSample, uint32_t spr) {
@@ -958,22 +654,18 @@ void launchEnvFold(cudaStream_t st, const float* srcMip, float* dstMip, uint32_t
     dim3 b(8, 8), g((dstSize + 7) / 8, (dstSize + 7) / 8);
     k_env_fold<<<g, b, 0, st>>>(srcMip, dstMip, dstSize);
 }
-void launchTraceProbe(cudaStream_t st, bool wide, const DeviceScene& sc, const float* rays8, uint32_t n, int anyHit, uint32_t* hits5) {
-    if (wide) k_trace_probe<true><<<grid1(n, 128), 128, 0, st>>>(sc, rays8, n, anyHit, hits5);
-    else k_trace_probe<false><<<grid1(n, 128), 128, 0, st>>>(sc, rays8, n, anyHit, hits5);
+void launchTraceProbe(cudaStream_t st, const DeviceScene& sc, const float* rays8, uint32_t n, int anyHit, uint32_t* hits5) {
+    k_trace_probe<<<grid1(n, 128), 128, 0, st>>>(sc, rays8, n, anyHit, hits5);
 }
-void launchPick(cudaStream_t st, bool wide, const DeviceScene& sc, const DCamera& cam, float x, float y, MsneClick* out) {
-    if (wide) k_pick<true><<<1, 1, 0, st>>>(sc, cam, make_float2(x, y), out);
-    else k_pick<false><<<1, 1, 0, st>>>(sc, cam, make_float2(x, y), out);
+void launchPick(cudaStream_t st, const DeviceScene& sc, const DCamera& cam, float x, float y, MsneClick* out) {
+    k_pick<<<1, 1, 0, st>>>(sc, cam, make_float2(x, y), out);
 }
 void launchPrimaryProbe(cudaStream_t st, const DCamera& cam, const DConstants& k, uint32_t sample, float* rays6, uint32_t* rngState) {
     k_primary_probe<<<grid1((uint64_t)cam.width * cam.height, 256), 256, 0, st>>>(cam, k, sample, rays6, rngState);
 }
-int traceOccupancyBlocksPerSm(bool wide) {
+int traceOccupancyBlocksPerSm() {
     int n = 0;
-    if (wide) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace8, TRACE_THREADS, 0);
-    else if (g_traceWs) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_ws, TRACE_THREADS, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace, TRACE_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace, TRACE_THREADS, 0);
     return n;
 }
 int shadeOccupancyBlocksPerSm() {

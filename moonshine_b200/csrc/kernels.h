@@ -11,36 +11,24 @@ namespace msne {
 #ifndef TRACE_BLOCKS_PER_SM
 #define TRACE_BLOCKS_PER_SM 8   // 64 registers: measured best (profiles/r01_sweeps.md)
 #endif
-#ifndef TRACE8_BLOCKS_PER_SM
-#define TRACE8_BLOCKS_PER_SM 6  // wide-BVH trace kernel
-#endif
-#ifndef MSNE_STACK8
-#define MSNE_STACK8 40          // traversal stack entries (uint2) of the wide-BVH kernels
-#endif
-static const unsigned MSNE_STACK8_HOST = MSNE_STACK8;
 #ifndef SHADE_THREADS
 #define SHADE_THREADS 128
 #endif
 
 void launchGenerate(cudaStream_t st, const DCamera& cam, const DConstants& k, const PathBuffers& pb, Counters* counters, const uint32_t* pixIds,
                     uint32_t nPix, uint32_t nSamples, uint32_t firstSample);
-void launchTrace(cudaStream_t st, int blocks, bool wide, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const uint32_t* perm = nullptr);
-struct RaySortParams { float lo[3], scale[3]; uint32_t obits, dbits, dirFirst, tileShift; };
-void launchRayKeys(cudaStream_t st, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const RaySortParams& sp, uint32_t* keys, uint32_t* vals, uint32_t nMax);
-size_t raySortTempBytes(uint32_t n);
-void raySort(cudaStream_t st, void* temp, size_t tempBytes, const uint32_t* keysIn, uint32_t* keysOut, const uint32_t* valsIn, uint32_t* valsOut, uint32_t n, int endBit);
+void launchTrace(cudaStream_t st, int blocks, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf);
 void launchShade(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf);
 void launchShadeBinned(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf);
-void launchTail(cudaStream_t st, int blocks, bool wide, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf);
+void launchTail(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf);
 void launchAccumulate(cudaStream_t st, const float4* result, float4* image, float4* runState, const uint32_t* pixIds, uint32_t nPix, uint32_t nSamples,
                       uint32_t firstSample, uint32_t spr);
 void launchEnvResample(cudaStream_t st, const float4* src, uint32_t W, uint32_t H, float4* dstRgb, float* dstLum, uint32_t S);
 void launchEnvFold(cudaStream_t st, const float* srcMip, float* dstMip, uint32_t dstSize);
-void launchTraceProbe(cudaStream_t st, bool wide, const DeviceScene& sc, const float* rays8, uint32_t n, int anyHit, uint32_t* hits5);
-void launchPick(cudaStream_t st, bool wide, const DeviceScene& sc, const DCamera& cam, float x, float y, MsneClick* out);
+void launchTraceProbe(cudaStream_t st, const DeviceScene& sc, const float* rays8, uint32_t n, int anyHit, uint32_t* hits5);
+void launchPick(cudaStream_t st, const DeviceScene& sc, const DCamera& cam, float x, float y, MsneClick* out);
 void launchPrimaryProbe(cudaStream_t st, const DCamera& cam, const DConstants& k, uint32_t sample, float* rays6, uint32_t* rngState);
-void setTraceVariant(int warpSync, uint32_t refillMin, uint32_t leafMin);   // process-wide; call before traceOccupancyBlocksPerSm
-int traceOccupancyBlocksPerSm(bool wide);
+int traceOccupancyBlocksPerSm();
 int shadeOccupancyBlocksPerSm();
 
 }  // namespace msne

@@ -179,9 +179,6 @@ struct HdMoonshine {
     std::map<std::vector<uint32_t>, uint32_t> blasByKey;
     std::vector<Blas> blases;
     std::vector<BvhNode2> blasNodePool;
-    std::vector<BvhNode8> blasNodePool8;   // bvhWidth == 8: compressed wide nodes instead of blasNodePool
-    uint32_t bvhWidth = 8;                 // MSNE_BVH=2 selects the binary BVH kernels (kept for A/B measurements)
-    uint32_t blasDepthMax = 0, tlasDepth = 0;
     std::vector<TriRec> triPool;
 
     // geomDirty: the set of flattened (identity-transform, visible) instances or the BLAS pool changed -> rebuild BLASes + TLAS.
@@ -189,8 +186,6 @@ struct HdMoonshine {
     bool tablesDirty = true, geomDirty = true, tlasDirty = true, aliasDirty = true;
 
     DevBuf<BvhNode2> dTlasNodes, dBlasNodes;
-    DevBuf<BvhNode8> dTlasNodes8, dBlasNodes8;
-    bool tlasStaticOnly = false;
     DevBuf<uint32_t> dTlasItems;
     DevBuf<TriRec> dTris;
     DevBuf<DInstance> dInstances;
@@ -225,9 +220,6 @@ struct HdMoonshine {
     int traceBlocks = 0, shadeBlocks = 0;
     uint32_t maxLeaf = 3;   // triangles per BVH leaf (<= 8: 3-bit count in the leaf reference); 2-3 measured best
     uint64_t tailThreshold = 32768;   // survivors below this are finished by k_tail (0 = never)
-    // ray reordering experiment (MSNE_SORT=1): sort each bounce's rays by origin cell + direction cell before tracing
-    bool sortRays = false; uint32_t sortOBits = 5, sortDBits = 5, sortDirFirst = 0, sortTileShift = 0; uint64_t sortMin = 1u << 20;
-    DevBuf<uint32_t> sortKeys[2], sortVals[2]; DevBuf<uint8_t> sortTemp;
     bool logBounces = false;          // MSNE_LOG_BOUNCES=1: queue sizes after every bounce on stderr
     uint64_t binnedThreshold = 262144;   // survivors below this use the single generic shade launch
 
@@ -261,25 +253,10 @@ struct HdMoonshine {
         consts = MsneSpecConstants{1, 1024, 0, 0, 0, 0, 0};
         const float white[4] = {1, 1, 1, 1};
         setBackground(white, 1, 1);   // addDefaultBackground (BackgroundManager.zig:116-126)
-        if (const char* e = getenv("MSNE_BVH")) bvhWidth = atoi(e) == 2 ? 2u : 8u;
         if (const char* e = getenv("MSNE_MAX_LEAF")) maxLeaf = (uint32_t)std::min(8, std::max(1, atoi(e)));
-        if (wide()) maxLeaf = std::min(maxLeaf, 3u);   // a wide node addresses its items through a 24-bit mask: 8 children x 3
         if (const char* e = getenv("MSNE_LOG_BOUNCES")) logBounces = atoi(e) != 0;
-        if (const char* e = getenv("MSNE_SORT")) sortRays = atoi(e) != 0;
-        if (const char* e = getenv("MSNE_SORT_OBITS")) sortOBits = (uint32_t)atoi(e);
-        if (const char* e = getenv("MSNE_SORT_DBITS")) sortDBits = (uint32_t)atoi(e);
-        if (const char* e = getenv("MSNE_SORT_DIRFIRST")) sortDirFirst = (uint32_t)atoi(e);
-        if (const char* e = getenv("MSNE_SORT_TILE")) sortTileShift = (uint32_t)atoi(e);
-        if (const char* e = getenv("MSNE_SORT_MIN")) sortMin = strtoull(e, nullptr, 10);
         if (const char* e = getenv("MSNE_TAIL_THRESHOLD")) tailThreshold = strtoull(e, nullptr, 10);
-        {
-            int wsOn = 0; uint32_t refillMin = 8, leafMin = 16;
-            if (const char* e = getenv("MSNE_TRACE_WS")) wsOn = atoi(e);
-            if (const char* e = getenv("MSNE_REFILL_MIN")) refillMin = (uint32_t)atoi(e);
-            if (const char* e = getenv("MSNE_LEAF_MIN")) leafMin = (uint32_t)atoi(e);
-            setTraceVariant(wsOn, refillMin, leafMin);
-        }
-        traceBlocks = smCount * std::max(1, traceOccupancyBlocksPerSm(wide()));
+        traceBlocks = smCount * std::max(1, traceOccupancyBlocksPerSm());
         shadeBlocks = smCount * std::max(1, shadeOccupancyBlocksPerSm());
         CK(cudaStreamSynchronize(stream));
     }
@@ -297,7 +274,6 @@ struct HdMoonshine {
     }
 
     void use() { CK(cudaSetDevice(device)); }
-    bool wide() const { return bvhWidth == 8; }
 
     // ---- environment (BackgroundManager.zig:142-394) -----------------------------------------
     void setBackground(const float* rgba, uint32_t W, uint32_t H) {
@@ -324,15 +300,6 @@ struct HdMoonshine {
     // ---- acceleration structure (replaces Accel.zig:94-184 makeBlases and :440-489 TLAS build) ------
     // pools a host BVH: children become the pre-encoded traversal references of dtypes.h
     uint32_t appendBlas(const BuiltBvh& bvh, const std::vector<TriRec>& tris) {
-        if (wide()) {
-            BuiltBvh8 w;
-            collapseToBvh8(bvh, w);
-            const uint32_t nodeBase = (uint32_t)blasNodePool8.size(), triBase = (uint32_t)triPool.size();
-            for (BvhNode8 n : w.nodes) { n.childBase += nodeBase; n.itemBase += triBase; blasNodePool8.push_back(n); }
-            for (uint32_t i = 0; i < w.order.size(); i++) triPool.push_back(tris[w.order[i]]);
-            blasDepthMax = std::max(blasDepthMax, w.depth);
-            return nodeBase;
-        }
         const uint32_t nodeBase = (uint32_t)blasNodePool.size(), triBase = (uint32_t)triPool.size();
         for (BvhNode2 n : bvh.nodes) {
             for (int s = 0; s < 2; s++) {
@@ -385,11 +352,10 @@ struct HdMoonshine {
     //     of the transformed instances. Only needed when that set changes (Accel.zig:94-184 equivalent).
     DInstance staticRec{};
     bool haveStatic = false;
-    BuildBox staticBounds{}, worldBounds{};
+    BuildBox staticBounds{};
     uint64_t stats_static_builds = 0, stats_tlas_builds = 0;
     void buildGeometry() {
-        blasNodePool.clear(); blasNodePool8.clear(); triPool.clear(); blasByKey.clear(); blases.clear();
-        blasDepthMax = 0;
+        blasNodePool.clear(); triPool.clear(); blasByKey.clear(); blases.clear();
         const uint32_t nInst = (uint32_t)instances.size();
         std::vector<TriRec> stTris;
         std::vector<BuildBox> stBoxes;
@@ -413,15 +379,10 @@ struct HdMoonshine {
             HostInstance& in = instances[i];
             in.blas = isIdentity(in.transform) ? 0xFFFFFFFFu : getBlas(in.meshKey);   // invisible ones too: toggling visibility stays TLAS-only
         }
-        uploadBlasPool();
+        dBlasNodes.upload(blasNodePool.data(), blasNodePool.size(), stream);
+        dTris.upload(triPool.data(), triPool.size(), stream);
         CK(cudaStreamSynchronize(stream));
         stats_static_builds++;
-    }
-
-    void uploadBlasPool() {
-        if (wide()) dBlasNodes8.upload(blasNodePool8.data(), blasNodePool8.size(), stream);
-        else dBlasNodes.upload(blasNodePool.data(), blasNodePool.size(), stream);
-        dTris.upload(triPool.data(), triPool.size(), stream);
     }
 
     // (2) instance level: device instance records, inverse transforms and the TLAS (Accel.zig:394-489 equivalent)
@@ -433,10 +394,13 @@ struct HdMoonshine {
         di[nInst] = staticRec;
         if (haveStatic) { boxes.push_back(staticBounds); items.push_back(nInst); }
         // transformed instances created since the last BLAS-level build: append their BLAS (or reuse a shared one)
-        const size_t poolNodes = blasNodePool.size() + blasNodePool8.size();
+        const size_t poolNodes = blasNodePool.size();
         for (HostInstance& in : instances)
             if (in.blas == 0xFFFFFFFFu && !isIdentity(in.transform)) in.blas = getBlas(in.meshKey);
-        if (blasNodePool.size() + blasNodePool8.size() != poolNodes) uploadBlasPool();
+        if (blasNodePool.size() != poolNodes) {
+            dBlasNodes.upload(blasNodePool.data(), blasNodePool.size(), stream);
+            dTris.upload(triPool.data(), triPool.size(), stream);
+        }
         for (uint32_t i = 0; i < nInst; i++) {
             const HostInstance& in = instances[i];
             DInstance d{};
@@ -459,23 +423,8 @@ struct HdMoonshine {
             di[i] = d;
         }
         dInstances.upload(di.data(), di.size(), stream);
-        for (int a = 0; a < 3; a++) { worldBounds.lo[a] = 1e30f; worldBounds.hi[a] = -1e30f; }
-        for (const BuildBox& bb : boxes) for (int a = 0; a < 3; a++) { worldBounds.lo[a] = std::min(worldBounds.lo[a], bb.lo[a]); worldBounds.hi[a] = std::max(worldBounds.hi[a], bb.hi[a]); }
         hasTlas = !items.empty();
-        tlasStaticOnly = haveStatic && items.size() == 1;
-        if (hasTlas && wide()) {
-            BuiltBvh tl;
-            buildBvh2(boxes.data(), (uint32_t)boxes.size(), 1, tl);
-            BuiltBvh8 w;
-            collapseToBvh8(tl, w);
-            std::vector<uint32_t> slots(w.order.size());
-            for (size_t s = 0; s < w.order.size(); s++) slots[s] = items[w.order[s]];
-            dTlasNodes8.upload(w.nodes.data(), w.nodes.size(), stream);
-            dTlasItems.upload(slots.data(), slots.size(), stream);
-            tlasDepth = w.depth;
-            // every node visit parks at most one group; entering an instance parks two groups and a marker
-            if (tlasDepth + blasDepthMax + 4 > MSNE_STACK8_HOST) fatal("wide BVH deeper than the traversal stack (MSNE_STACK8)");
-        } else if (hasTlas) {
+        if (hasTlas) {
             BuiltBvh tl;
             buildBvh2(boxes.data(), (uint32_t)boxes.size(), 1, tl);
             std::vector<uint32_t> slots(tl.order.size());
@@ -516,14 +465,9 @@ struct HdMoonshine {
         }
     }
 
-    BuildBox sceneBounds() const { return worldBounds; }
     DeviceScene deviceScene() const {
         DeviceScene sc{};
-        sc.tlasNodes = hasTlas && !wide() ? dTlasNodes.p : nullptr;
-        sc.tlasNodes8 = hasTlas && wide() ? dTlasNodes8.p : nullptr;
-        sc.blasNodes8 = dBlasNodes8.p;
-        sc.staticOnly = tlasStaticOnly ? 1u : 0u;
-        sc.staticRoot = staticRec.blasRoot;
+        sc.tlasNodes = hasTlas ? dTlasNodes.p : nullptr;
         sc.tlasItems = dTlasItems.p;
         sc.blasNodes = dBlasNodes.p; sc.tris = dTris.p; sc.instances = dInstances.p; sc.geometries = dGeometries.p;
         sc.meshes = dMeshes.p; sc.materials = dMaterials.p; sc.textures = dTextures.p;
@@ -663,7 +607,7 @@ struct HdMoonshine {
             const uint32_t buf = b & 1u;
             const bool prof = profiling && profUsed < kProfEvents;
             if (prof) CK(cudaEventRecord(profEv[profUsed][0], stream));
-            launchTrace(stream, traceBlocks, wide(), sc, pb, ws, buf);
+            launchTrace(stream, traceBlocks, sc, pb, ws, buf);
             if (prof) { CK(cudaEventRecord(profEv[profUsed][1], stream)); profUsed++; }
             // big queues: one material-specialised launch per bin; small queues (tail): one generic launch
             if (lastLive >= binnedThreshold) { launchShadeBinned(stream, shadeBlocks, sc, k, pb, ws, buf); stats.kernel_launches += 6; }
@@ -671,49 +615,8 @@ struct HdMoonshine {
             CK(cudaMemcpyAsync(&hostCounters[b & 3u], dCounters.p + (buf ^ 1u), sizeof(Counters), cudaMemcpyDeviceToHost, stream));
             CK(cudaEventRecord(bounceEvents[b & 3u], stream));
         };
-        const uint32_t maxIter = k.max_bounces + 4;
-        if (sortRays && !wide()) {
-            // experiment: synchronous bounces (the sort needs the exact queue size on the host)
-            RaySortParams sp{};
-            BuildBox wb = sceneBounds();
-            for (int a = 0; a < 3; a++) { sp.lo[a] = wb.lo[a]; sp.scale[a] = (float)(1u << sortOBits) / std::max(1e-6f, wb.hi[a] - wb.lo[a]); }
-            sp.obits = sortOBits; sp.dbits = sortDBits; sp.dirFirst = sortDirFirst; sp.tileShift = sortTileShift;
-            const int endBit = sortTileShift ? 32 : (int)(3 * sortOBits + 2 * sortDBits + 1);
-            const uint32_t cap3 = 3u * pb.capacity;
-            if (sortKeys[0].n < cap3) {
-                for (int i = 0; i < 2; i++) { sortKeys[i].alloc(cap3); sortVals[i].alloc(cap3); }
-                sortTemp.alloc(raySortTempBytes(cap3));
-            }
-            uint64_t total = lastLive; bool first = true;
-            for (uint32_t b = 0; b < maxIter; b++) {
-                const uint32_t buf = b & 1u;
-                const uint32_t* perm = nullptr;
-                if (!first && total >= sortMin) {
-                    launchRayKeys(stream, pb, ws, buf, sp, sortKeys[0].p, sortVals[0].p, (uint32_t)total);
-                    raySort(stream, sortTemp.p, sortTemp.n, sortKeys[0].p, sortKeys[1].p, sortVals[0].p, sortVals[1].p, (uint32_t)total, endBit);
-                    perm = sortVals[1].p;
-                }
-                first = false;
-                const bool prof = profiling && profUsed < kProfEvents;
-                if (prof) CK(cudaEventRecord(profEv[profUsed][0], stream));
-                launchTrace(stream, traceBlocks, false, sc, pb, ws, buf, perm);
-                if (prof) { CK(cudaEventRecord(profEv[profUsed][1], stream)); profUsed++; }
-                if (lastLive >= binnedThreshold) launchShadeBinned(stream, shadeBlocks, sc, k, pb, ws, buf);
-                else launchShade(stream, shadeBlocks, sc, k, pb, ws, buf);
-                CK(cudaMemcpyAsync(&hostCounters[0], dCounters.p + (buf ^ 1u), sizeof(Counters), cudaMemcpyDeviceToHost, stream));
-                CK(cudaStreamSynchronize(stream));
-                const Counters c = hostCounters[0];
-                lastLive = c.nLive; total = (uint64_t)c.nLive + c.nShadow;
-                if (c.nLive + c.nDead == 0) break;
-                if ((uint64_t)c.nLive + c.nDead < tailThreshold) {
-                    const uint32_t tb = (b + 1) & 1u;
-                    launchTrace(stream, traceBlocks, false, sc, pb, ws, tb);
-                    launchTail(stream, smCount * 4, false, sc, k, pb, ws, tb);
-                    break;
-                }
-            }
-        } else {
         // keep one bounce queued ahead of the one whose survivor count we wait for
+        const uint32_t maxIter = k.max_bounces + 4;
         enqueueBounce(0);
         for (uint32_t b = 0; b < maxIter; b++) {
             enqueueBounce(b + 1);
@@ -726,12 +629,11 @@ struct HdMoonshine {
                 // few stragglers left: after the already-queued bounce b+1, trace once more and let k_tail finish
                 // every remaining path in a single launch instead of ~130 launch pairs at the latency floor
                 const uint32_t tb = (b + 2) & 1u;
-                launchTrace(stream, traceBlocks, wide(), sc, pb, ws, tb);
-                launchTail(stream, smCount * 4, wide(), sc, k, pb, ws, tb);
+                launchTrace(stream, traceBlocks, sc, pb, ws, tb);
+                launchTail(stream, smCount * 4, sc, k, pb, ws, tb);
                 stats.kernel_launches += 2;
                 break;
             }
-        }
         }
         launchAccumulate(stream, pb.result, s.image.p, s.runState.p + pixOffset, s.pixIds.p + pixOffset, nPix, nSamples, firstSample, k.samples_per_run);
         stats.kernel_launches++;
@@ -1079,7 +981,7 @@ bool HdMoonshineExtPick(HdMoonshine* h, SensorHandle s, LensHandle l, F32x2 coor
         const Sensor& se = *h->sensors.at(s);
         DevBuf<MsneClick> d;
         d.alloc(1);
-        launchPick(h->stream, h->wide(), h->deviceScene(), HdMoonshine::makeCamera(h->lenses.at(l), se.extent.width, se.extent.height), coords.x, coords.y, d.p);
+        launchPick(h->stream, h->deviceScene(), HdMoonshine::makeCamera(h->lenses.at(l), se.extent.width, se.extent.height), coords.x, coords.y, d.p);
         h->stats.kernel_launches++;
         MsneClick c{};
         CK(cudaMemcpyAsync(&c, d.p, sizeof(c), cudaMemcpyDeviceToHost, h->stream));
@@ -1097,7 +999,7 @@ bool HdMoonshineExtTraceRays(HdMoonshine* h, const float* rays8, size_t n, bool 
         h->use(); h->syncScene();
         DevBuf<float> dr; DevBuf<uint32_t> dh;
         dr.upload(rays8, 8 * n, h->stream); dh.alloc(5 * n);
-        launchTraceProbe(h->stream, h->wide(), h->deviceScene(), dr.p, (uint32_t)n, anyHit ? 1 : 0, dh.p);
+        launchTraceProbe(h->stream, h->deviceScene(), dr.p, (uint32_t)n, anyHit ? 1 : 0, dh.p);
         h->stats.kernel_launches++;
         CK(cudaMemcpyAsync(hits5, dh.p, 5 * n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));

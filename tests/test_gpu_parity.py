@@ -258,52 +258,6 @@ def test_cfg3_full_size_properties():
     assert (sa.rays_closest, sa.rays_shadow) == (sb.rays_closest, sb.rays_shadow)
 
 
-def _with_bvh(width, fn):
-    import os
-    old = os.environ.get("MSNE_BVH")
-    os.environ["MSNE_BVH"] = str(width)
-    try:
-        return fn()
-    finally:
-        if old is None:
-            os.environ.pop("MSNE_BVH", None)
-        else:
-            os.environ["MSNE_BVH"] = old
-
-
-@pytest.mark.parametrize("maker,center,radius", [
-    (lambda: scenes.bathroom(extent=(64, 36), detail=0.25), (0.0, 0.0, 1.2), 1.5),
-    (scenes.material_zoo, (0.0, 0.0, 1.0), 1.2),
-])
-def test_wide_and_binary_bvh_agree(maker, center, radius):
-    """The compressed 8-wide BVH kernels (default) and the binary-BVH kernels (MSNE_BVH=2) must return identical hit
-    records and identical images: hits are defined by the triangle test + tie rule, not by the tree."""
-    sc = maker()
-
-    def make():
-        m = hydra.HdMoonshine()
-        scenes.load_scene(m, sc)
-        return m
-    m8, m2 = _with_bvh(8, make), _with_bvh(2, make)
-    rays = random_rays(11, 400000, np.array(center), radius)
-    rays[::7, 4] = 0.0      # axis-parallel direction components
-    rays[::13, 5] = -0.0
-    a, b = m8.trace(rays), m2.trace(rays)
-    assert (a["instance"] != 0xFFFFFFFF).mean() > 0.2
-    for f in ("instance", "geometry", "primitive"):
-        np.testing.assert_array_equal(a[f], b[f])
-    np.testing.assert_array_equal(a["u"].view(np.uint32), b["u"].view(np.uint32))
-    np.testing.assert_array_equal(a["v"].view(np.uint32), b["v"].view(np.uint32))
-    rays[:, 7] = 0.7
-    np.testing.assert_array_equal(m8.trace(rays, any_hit=True)["instance"] != 0xFFFFFFFF, m2.trace(rays, any_hit=True)["instance"] != 0xFFFFFFFF)
-    imgs = []
-    for m in (m8, m2):
-        sensor, lens = m.CreateSensor(*sc.extent), m.CreateLens(sc.lens)
-        m.RenderLaunches(sensor, lens, 2)
-        imgs.append(m.ReadSensor(sensor).copy())
-    np.testing.assert_array_equal(imgs[0].view(np.uint32), imgs[1].view(np.uint32))
-
-
 def test_object_picker_matches_oracle():
     """HdMoonshineExtPick (ObjectPicker.zig:89-128 + input.hlsl) against the oracle: ids exact; barycentrics bit-exact
     with a pinhole lens, within 1e-5 with the thin lens (cos/sin of the lens sample differ by an ulp between libm and CUDA)."""
