@@ -56,6 +56,7 @@ typedef struct MsneStats {
     uint64_t max_bounce_reached;
     uint64_t static_blas_builds;        /* rebuilds of the BLAS level (merged static BLAS + shared BLASes) */
     uint64_t tlas_builds;               /* rebuilds of the instance level (TLAS + instance records) */
+    uint64_t tlas_refits;               /* transform-only edits served by a bottom-up refit of the existing TLAS */
 } MsneStats;
 
 /* must be called before HdMoonshineCreate; selects the CUDA device of objects created afterwards */
@@ -87,6 +88,12 @@ MSNE_API void HdMoonshineExtSetProfiling(HdMoonshine*, bool per_kernel_events);
 
 MSNE_API void HdMoonshineExtGetStats(const HdMoonshine*, MsneStats*);
 MSNE_API void HdMoonshineExtResetStats(HdMoonshine*);
+
+/* ---- incremental edits beyond the hydra ABI (online/main.zig:225-270) ---- */
+/* Accel.recordUpdateSingleMaterial (Accel.zig:609-627): geometry `geometry` of `instance` switches to `material` */
+MSNE_API void HdMoonshineExtSetGeometryMaterial(HdMoonshine*, InstanceHandle instance, uint32_t geometry, MaterialHandle material);
+/* rebuild the emitter alias table automatically (at the next render) after edits that change it; the reference never does (Accel.zig:187) */
+MSNE_API void HdMoonshineExtSetEmitterTableFollowsEdits(HdMoonshine*, bool on);
 
 /* ---- object picker: ObjectPicker.getClickedObject (engine/hrtsystem/ObjectPicker.zig:89-128) + its ray-generation
  * program (shaders/hrtsystem/input.hlsl:1-57). `normalized_coords` in [0,1]^2 with the origin at the top left as the

@@ -184,6 +184,14 @@ struct HdMoonshine {
     // geomDirty: the set of flattened (identity-transform, visible) instances or the BLAS pool changed -> rebuild BLASes + TLAS.
     // tlasDirty: only transforms / visibility of transformed instances changed -> rebuild the TLAS and instance records.
     bool tablesDirty = true, geomDirty = true, tlasDirty = true, aliasDirty = true;
+    // tlasRefitOk: since the last TLAS build only transforms of transformed, visible instances changed -> the TLAS keeps its
+    // topology and only its boxes are recomputed bottom-up (Accel.zig:629-679 recordRebuild with mode = update_khr).
+    bool tlasRefitOk = false;
+    uint32_t refitsSinceBuild = 0, maxRefits = 32;   // MSNE_TLAS_MAX_REFITS: rebuild after this many consecutive refits
+    std::vector<BvhNode2> tlasHostNodes;             // pre-encoded TLAS as uploaded
+    std::vector<uint32_t> tlasHostSlots;             // TLAS leaf slot -> instance record
+    // emitter alias table: rebuilt by the next render after an edit that changes it, once following is switched on
+    bool emitterFollowsEdits = false, emitterStale = false;
 
     DevBuf<BvhNode2> dTlasNodes, dBlasNodes;
     DevBuf<uint32_t> dTlasItems;
@@ -254,6 +262,7 @@ struct HdMoonshine {
         const float white[4] = {1, 1, 1, 1};
         setBackground(white, 1, 1);   // addDefaultBackground (BackgroundManager.zig:116-126)
         if (const char* e = getenv("MSNE_MAX_LEAF")) maxLeaf = (uint32_t)std::min(8, std::max(1, atoi(e)));
+        if (const char* e = getenv("MSNE_TLAS_MAX_REFITS")) maxRefits = (uint32_t)std::max(0, atoi(e));
         if (const char* e = getenv("MSNE_LOG_BOUNCES")) logBounces = atoi(e) != 0;
         if (const char* e = getenv("MSNE_TAIL_THRESHOLD")) tailThreshold = strtoull(e, nullptr, 10);
         traceBlocks = smCount * std::max(1, traceOccupancyBlocksPerSm());
@@ -353,7 +362,7 @@ struct HdMoonshine {
     DInstance staticRec{};
     bool haveStatic = false;
     BuildBox staticBounds{};
-    uint64_t stats_static_builds = 0, stats_tlas_builds = 0;
+    uint64_t stats_static_builds = 0, stats_tlas_builds = 0, stats_tlas_refits = 0;
     void buildGeometry() {
         blasNodePool.clear(); triPool.clear(); blasByKey.clear(); blases.clear();
         const uint32_t nInst = (uint32_t)instances.size();
@@ -385,6 +394,77 @@ struct HdMoonshine {
         stats_static_builds++;
     }
 
+    BuildBox instanceWorldBox(const HostInstance& in) const {
+        const BuildBox& bb = blases[in.blas].bounds;
+        BuildBox w; for (int a = 0; a < 3; a++) { w.lo[a] = 1e30f; w.hi[a] = -1e30f; }
+        for (int c = 0; c < 8; c++) {
+            const float p[3] = {(c & 1) ? bb.hi[0] : bb.lo[0], (c & 2) ? bb.hi[1] : bb.lo[1], (c & 4) ? bb.hi[2] : bb.lo[2]};
+            for (int r = 0; r < 3; r++) {
+                const float q = ((in.transform[4 * r] * p[0] + in.transform[4 * r + 1] * p[1]) + in.transform[4 * r + 2] * p[2]) + in.transform[4 * r + 3];
+                w.lo[r] = std::min(w.lo[r], q); w.hi[r] = std::max(w.hi[r], q);
+            }
+        }
+        padBox(w);
+        return w;
+    }
+    DInstance instanceRecord(const HostInstance& in) const {
+        DInstance d{};
+        memcpy(d.o2w, in.transform, 48); memcpy(d.w2o, in.inverse, 48);
+        d.customIndex = in.customIndex; d.visible = in.visible ? 1 : 0;
+        if (in.visible && !isIdentity(in.transform)) d.blasRoot = blases[in.blas].rootNode;
+        return d;
+    }
+
+    // (2b) transform-only edits: same TLAS topology, boxes recomputed bottom-up. A node is always created after its
+    //      parent (bvh_build.cpp), so one reverse sweep sees every child before its parent. Hit results do not depend on
+    //      the tree (closest = min t with id tie-break), only traversal cost does; after `maxRefits` refits it is rebuilt.
+    void refitTlas() {
+        const uint32_t nInst = (uint32_t)instances.size();
+        std::vector<DInstance> di(nInst + 1);
+        for (uint32_t i = 0; i < nInst; i++) di[i] = instanceRecord(instances[i]);
+        di[nInst] = staticRec;
+        dInstances.upload(di.data(), di.size(), stream);
+        std::vector<BuildBox> slotBox(tlasHostSlots.size());
+        for (size_t s = 0; s < tlasHostSlots.size(); s++) {
+            const uint32_t rec = tlasHostSlots[s];
+            slotBox[s] = rec == nInst ? staticBounds : instanceWorldBox(instances[rec]);
+        }
+        auto childBoxOf = [&](const BvhNode2& n, int s) {
+            BuildBox b;
+            const float* xy = s == 0 ? n.n0 : n.n1;
+            b.lo[0] = xy[0]; b.hi[0] = xy[1]; b.lo[1] = xy[2]; b.hi[1] = xy[3]; b.lo[2] = n.n2[2 * s]; b.hi[2] = n.n2[2 * s + 1];
+            return b;
+        };
+        for (size_t k = tlasHostNodes.size(); k-- > 0;) {
+            BvhNode2& n = tlasHostNodes[k];
+            for (int s = 0; s < 2; s++) {
+                const int32_t ref = n.c[s];
+                if (ref == REF_EMPTY) continue;
+                BuildBox b;
+                if (ref & REF_ITEM) b = slotBox[(uint32_t)(ref & ~REF_ITEM)];
+                else {
+                    const BvhNode2& ch = tlasHostNodes[(size_t)ref];
+                    bool any = false;
+                    for (int a = 0; a < 3; a++) { b.lo[a] = 1e30f; b.hi[a] = -1e30f; }
+                    for (int cs = 0; cs < 2; cs++) {
+                        if (ch.c[cs] == REF_EMPTY) continue;
+                        const BuildBox cb = childBoxOf(ch, cs);
+                        for (int a = 0; a < 3; a++) { b.lo[a] = std::min(b.lo[a], cb.lo[a]); b.hi[a] = std::max(b.hi[a], cb.hi[a]); }
+                        any = true;
+                    }
+                    if (!any) continue;
+                }
+                float* xy = s == 0 ? n.n0 : n.n1;
+                xy[0] = b.lo[0]; xy[1] = b.hi[0]; xy[2] = b.lo[1]; xy[3] = b.hi[1];
+                n.n2[2 * s] = b.lo[2]; n.n2[2 * s + 1] = b.hi[2];
+            }
+        }
+        dTlasNodes.upload(tlasHostNodes.data(), tlasHostNodes.size(), stream);
+        CK(cudaStreamSynchronize(stream));
+        refitsSinceBuild++;
+        stats_tlas_refits++;
+    }
+
     // (2) instance level: device instance records, inverse transforms and the TLAS (Accel.zig:394-489 equivalent)
     void buildTlas() {
         const uint32_t nInst = (uint32_t)instances.size();
@@ -403,24 +483,8 @@ struct HdMoonshine {
         }
         for (uint32_t i = 0; i < nInst; i++) {
             const HostInstance& in = instances[i];
-            DInstance d{};
-            memcpy(d.o2w, in.transform, 48); memcpy(d.w2o, in.inverse, 48);
-            d.customIndex = in.customIndex; d.visible = in.visible ? 1 : 0;
-            if (in.visible && !isIdentity(in.transform)) {
-                d.blasRoot = blases[in.blas].rootNode;
-                const BuildBox& bb = blases[in.blas].bounds;
-                BuildBox w; for (int a = 0; a < 3; a++) { w.lo[a] = 1e30f; w.hi[a] = -1e30f; }
-                for (int c = 0; c < 8; c++) {
-                    const float p[3] = {(c & 1) ? bb.hi[0] : bb.lo[0], (c & 2) ? bb.hi[1] : bb.lo[1], (c & 4) ? bb.hi[2] : bb.lo[2]};
-                    for (int r = 0; r < 3; r++) {
-                        const float q = ((in.transform[4 * r] * p[0] + in.transform[4 * r + 1] * p[1]) + in.transform[4 * r + 2] * p[2]) + in.transform[4 * r + 3];
-                        w.lo[r] = std::min(w.lo[r], q); w.hi[r] = std::max(w.hi[r], q);
-                    }
-                }
-                padBox(w);
-                boxes.push_back(w); items.push_back(i);
-            }
-            di[i] = d;
+            if (in.visible && !isIdentity(in.transform)) { boxes.push_back(instanceWorldBox(in)); items.push_back(i); }
+            di[i] = instanceRecord(in);
         }
         dInstances.upload(di.data(), di.size(), stream);
         hasTlas = !items.empty();
@@ -438,8 +502,10 @@ struct HdMoonshine {
             for (BvhNode2& n : tl.nodes) n.c[2] = n.c[3] = 0;
             dTlasNodes.upload(tl.nodes.data(), tl.nodes.size(), stream);
             dTlasItems.upload(slots.data(), slots.size(), stream);
-        }
+            tlasHostNodes.swap(tl.nodes); tlasHostSlots.swap(slots);
+        } else { tlasHostNodes.clear(); tlasHostSlots.clear(); }
         CK(cudaStreamSynchronize(stream));
+        refitsSinceBuild = 0;
         stats_tlas_builds++;
     }
 
@@ -456,8 +522,12 @@ struct HdMoonshine {
             CK(cudaStreamSynchronize(stream));   // staging vectors die here
             tablesDirty = false;
         }
-        if (geomDirty) { buildGeometry(); geomDirty = false; tlasDirty = true; }
-        if (tlasDirty) { buildTlas(); tlasDirty = false; }
+        if (geomDirty) { buildGeometry(); geomDirty = false; tlasDirty = true; tlasRefitOk = false; }
+        if (tlasDirty) {
+            if (tlasRefitOk && hasTlas && refitsSinceBuild < maxRefits) refitTlas(); else buildTlas();
+            tlasDirty = false; tlasRefitOk = false;
+        }
+        if (emitterFollowsEdits && emitterStale) { buildEmitterTable(); emitterStale = false; }
         if (aliasDirty) {
             dAlias.upload(alias.data(), alias.size(), stream);
             CK(cudaStreamSynchronize(stream));
@@ -693,7 +763,7 @@ struct HdMoonshine {
         CK(cudaStreamSynchronize(stream));
         out = stats;
         out.rays_closest = rc[0]; out.rays_shadow = rc[1]; out.max_bounce_reached = sc[3];
-        out.static_blas_builds = stats_static_builds; out.tlas_builds = stats_tlas_builds;
+        out.static_blas_builds = stats_static_builds; out.tlas_builds = stats_tlas_builds; out.tlas_refits = stats_tlas_refits;
     }
 };
 
@@ -847,7 +917,8 @@ InstanceHandle HdMoonshineCreateInstance(HdMoonshine* h, Mat3x4 t, const Geometr
         h->instances.push_back(in);
         h->tablesDirty = true;
         if (HdMoonshine::isIdentity(in.transform)) h->geomDirty = true;   // joins the flattened static BLAS
-        else h->tlasDirty = true;                                         // own/shared BLAS appended lazily, TLAS rebuilt
+        else { h->tlasDirty = true; h->tlasRefitOk = false; }             // own/shared BLAS appended lazily, TLAS rebuilt
+        for (size_t i = 0; i < n; i++) if (geoms[i].sampled) h->emitterStale = true;
         h->clearAllSensors();   // hydra.zig:491
         return (uint32_t)h->instances.size() - 1;
     )
@@ -860,7 +931,7 @@ void HdMoonshineSetInstanceVisibility(HdMoonshine* h, InstanceHandle i, bool vis
         if (in.visible != visible) {
             in.visible = visible;
             if (HdMoonshine::isIdentity(in.transform)) h->geomDirty = true;   // member of the flattened static BLAS
-            else h->tlasDirty = true;                                         // transformed instance: TLAS only
+            else { h->tlasDirty = true; h->tlasRefitOk = false; }             // transformed instance: the TLAS item set changes
         }
         h->clearAllSensors();
     )
@@ -876,7 +947,13 @@ void HdMoonshineSetInstanceTransform(HdMoonshine* h, InstanceHandle i, Mat3x4 t)
         inverseAffine(in.transform, in.inverse);
         const bool isStatic = HdMoonshine::isIdentity(in.transform);
         if (wasStatic || isStatic) h->geomDirty = true;   // enters/leaves the flattened static BLAS
-        else h->tlasDirty = true;                         // TLAS + instance records only (hydra.zig:225-311: TLAS update)
+        else {
+            // TLAS + instance records only (Accel.zig:567-602 recordUpdateSingleTransform + :629-679 update-mode rebuild):
+            // the set of TLAS items is unchanged, so the next render refits instead of rebuilding
+            if (!h->tlasDirty) h->tlasRefitOk = true;
+            h->tlasDirty = true;
+        }
+        for (uint32_t g = 0; g < in.geometryCount; g++) if (h->geometries[in.customIndex + g].sampled & 0xFF) h->emitterStale = true;
         h->clearAllSensors();
     )
 }
@@ -971,6 +1048,24 @@ void HdMoonshineExtResetStats(HdMoonshine* h) {
         CK(cudaMemsetAsync(h->dScalars.p + 3, 0, sizeof(uint32_t), h->stream));
         CK(cudaStreamSynchronize(h->stream));
     )
+}
+
+// Accel.recordUpdateSingleMaterial (Accel.zig:609-627; online/main.zig:231): geometry `g` of instance `i` gets another material
+void HdMoonshineExtSetGeometryMaterial(HdMoonshine* h, InstanceHandle i, uint32_t g, MaterialHandle m) {
+    LOCK(h);
+    const HostInstance& in = h->instances.at(i);
+    if (g >= in.geometryCount || m >= h->materials.size()) fatal("HdMoonshineExtSetGeometryMaterial: index out of range");
+    h->geometries[in.customIndex + g].material = m;
+    h->tablesDirty = true;
+    if (h->geometries[in.customIndex + g].sampled & 0xFF) h->emitterStale = true;   // table entries are per triangle, radiance is read at sample time; kept for symmetry
+}
+// The reference builds the emitter alias table only in Accel.create (Accel.zig:491-538); instances added or moved
+// afterwards are never re-sampled (Accel.zig:187). With following on, the table is rebuilt by the next render after any
+// edit that changes it (instance added / moved with a sampled geometry).
+void HdMoonshineExtSetEmitterTableFollowsEdits(HdMoonshine* h, bool on) {
+    LOCK(h);
+    h->emitterFollowsEdits = on;
+    if (on) h->emitterStale = true;
 }
 
 // ---- object picker (ObjectPicker.zig:89-128) ---------------------------------------------------------

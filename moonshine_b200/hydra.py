@@ -64,7 +64,7 @@ class MsneMaterialInfo(C.Structure):
 class MsneStats(C.Structure):
     _fields_ = [("rays_closest", C.c_uint64), ("rays_shadow", C.c_uint64), ("samples", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("device_ms", C.c_double), ("trace_ms", C.c_double), ("trace_launches", C.c_uint64), ("max_bounce_reached", C.c_uint64),
-                ("static_blas_builds", C.c_uint64), ("tlas_builds", C.c_uint64)]
+                ("static_blas_builds", C.c_uint64), ("tlas_builds", C.c_uint64), ("tlas_refits", C.c_uint64)]
 
 
 class MsneClickData(C.Structure):   # input.hlsl:1-6
@@ -118,6 +118,8 @@ SIGNATURES = {
     "HdMoonshineExtSetProfiling": (None, [_VP, C.c_bool]),
     "HdMoonshineExtGetStats": (None, [_VP, C.POINTER(MsneStats)]),
     "HdMoonshineExtResetStats": (None, [_VP]),
+    "HdMoonshineExtSetGeometryMaterial": (None, [_VP, _U32, _U32, _U32]),
+    "HdMoonshineExtSetEmitterTableFollowsEdits": (None, [_VP, C.c_bool]),
     "HdMoonshineExtPick": (C.c_bool, [_VP, _U32, _U32, F32x2, _VP]),
     "HdMoonshineExtTraceRays": (C.c_bool, [_VP, _VP, C.c_size_t, C.c_bool, _VP]),
     "HdMoonshineExtPrimaryRays": (C.c_bool, [_VP, _U32, _U32, _U32, _VP, _VP]),
@@ -327,6 +329,12 @@ class HdMoonshine:
             raise RuntimeError("HdMoonshineExtBuildEmitterTable: " + self.last_error())
 
     def set_constants(self, c): self.SetSpecConstants(c)
+
+    def SetGeometryMaterial(self, instance: int, geometry: int, material: int):
+        self.L.HdMoonshineExtSetGeometryMaterial(self.h, instance, geometry, material)
+
+    def SetEmitterTableFollowsEdits(self, on: bool):
+        self.L.HdMoonshineExtSetEmitterTableFollowsEdits(self.h, bool(on))
 
     def Pick(self, sensor: int, lens: int, x: float, y: float):
         """ObjectPicker.getClickedObject (ObjectPicker.zig:89-128): (instance, geometry, primitive, (u, v)) or None."""

@@ -157,3 +157,100 @@ def test_transform_edits_of_instanced_objects_rebuild_only_the_tlas():
     m.SetInstanceVisibility(insts[0], False)   # the ground plane
     m.RenderLaunches(sensor, lens, 1)
     assert m.GetStats().static_blas_builds == 2
+
+
+def _probe_rays(n, seed, lo, size):
+    rs = np.random.RandomState(seed)
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, 0:3] = rs.rand(n, 3) * np.array(size) + np.array(lo)
+    d = rs.randn(n, 3)
+    rays[:, 4:7] = d / np.linalg.norm(d, axis=1, keepdims=True)
+    rays[:, 7] = 1e12
+    return rays
+
+
+def test_transform_only_edits_refit_the_tlas_and_hits_stay_exact():
+    """§8(f) row 3 (Accel.zig:567-602 + :629-679, TLAS build in update mode): moving transformed instances keeps the TLAS
+    topology and refits its boxes; hit records stay bit-identical to the oracle (which rebuilds from scratch) however far
+    the instances move; after MSNE_TLAS_MAX_REFITS refits the tree is rebuilt."""
+    sc = scenes.mesh_light_stress(8, (64, 64))
+    m = hydra.HdMoonshine()
+    _, _, _, insts = scenes.load_scene(m, sc)
+    o = Oracle()
+    _, _, _, oinsts = scenes.load_scene(o, sc)
+    rays = _probe_rays(6000, 4, (0, 0, 0.2), (8, 8, 3))
+    m.trace(rays)
+    s0 = m.GetStats()
+    assert (s0.tlas_builds, s0.tlas_refits) == (1, 0)
+    rs = np.random.RandomState(9)
+    movable = [i for i in range(len(sc.instances)) if not np.array_equal(sc.instances[i].transform, np.eye(3, 4, dtype=np.float32))]
+    for step in range(3):
+        for i in rs.choice(movable, 12, replace=False):
+            t = sc.instances[i].transform.copy()
+            t[:, 3] += (rs.rand(3).astype(np.float32) - 0.5) * np.array([6.0, 6.0, 1.5], np.float32)   # far from where the tree was built
+            m.SetInstanceTransform(insts[i], t)
+            o.set_instance_transform(oinsts[i], t)
+        g, r = m.trace(rays), o.trace(rays)
+        np.testing.assert_array_equal(g["instance"], r["instance"])
+        hit = r["instance"] != 0xFFFFFFFF
+        assert hit.mean() > 0.2
+        for f in ("geometry", "primitive"):
+            np.testing.assert_array_equal(g[f][hit], r[f][hit])
+        np.testing.assert_array_equal(g["u"][hit].view(np.uint32), r["u"][hit].view(np.uint32))
+        st = m.GetStats()
+        assert (st.static_blas_builds, st.tlas_builds, st.tlas_refits) == (1, 1, step + 1)
+    # a visibility change alters the TLAS item set -> rebuild, not refit
+    m.SetInstanceVisibility(insts[movable[0]], False)
+    m.trace(rays)
+    st = m.GetStats()
+    assert (st.tlas_builds, st.tlas_refits) == (2, 3)
+
+
+def test_emitter_table_follows_edits_when_asked():
+    """The reference samples only the emitters present at Accel.create (Accel.zig:187, :491-538). With
+    HdMoonshineExtSetEmitterTableFollowsEdits the table is rebuilt after an emitter moves (areas change under a
+    non-uniform scale) or a new one is added, and equals the oracle's table built from the edited scene, byte for byte."""
+    sc = scenes.material_zoo()
+    m = hydra.HdMoonshine()
+    _, mats, meshes, insts = scenes.load_scene(m, sc)
+    o = Oracle()
+    _, _, _, oinsts = scenes.load_scene(o, sc)
+    m.SetEmitterTableFollowsEdits(True)
+    emitter = next(i for i, inst in enumerate(sc.instances) if any(g[2] for g in inst.geometries))
+    t = sc.instances[emitter].transform.copy()
+    t[0, 0] *= 2.5
+    t[:, 3] += np.array([0.2, 0.1, 0.3], np.float32)
+    m.SetInstanceTransform(insts[emitter], t)
+    o.set_instance_transform(oinsts[emitter], t)
+    g = sc.instances[emitter].geometries[0]
+    extra = np.array([[0.2, 0, 0, 1.0], [0, 0.4, 0, 1.0], [0, 0, 0.2, 1.5]], np.float32)
+    m.CreateInstance(extra, [(meshes[g[0]], mats[g[1]], True)])
+    o.create_instance(extra, [(g[0], g[1], True)])
+    o.build_emitter_table()
+    sensor, lens = m.CreateSensor(*sc.extent), m.CreateLens(sc.lens)
+    m.RenderLaunches(sensor, lens, 1)   # the rebuild happens here
+    np.testing.assert_array_equal(m.alias_table().view(np.uint8), o.alias_table().view(np.uint8))
+    ref, _ = o.render(sc.lens, *sc.extent)
+    assert within_tol_fraction(m.ReadSensor(sensor), ref) >= 0.995
+
+
+def test_set_geometry_material_equals_building_with_that_material():
+    """Accel.recordUpdateSingleMaterial (Accel.zig:609-627): switching one geometry's material afterwards gives the same
+    image, bit for bit, as creating the instance with it."""
+    sc = scenes.cornell_box((48, 48))
+    a = hydra.HdMoonshine()
+    _, mats, _, insts = scenes.load_scene(a, sc)
+    sensor, lens = a.CreateSensor(*sc.extent), a.CreateLens(sc.lens)
+    a.RenderLaunches(sensor, lens, 1)
+    target, gi = 0, 1                                  # the left (red) wall of the box instance
+    old = sc.instances[target].geometries[gi]
+    new_mat = sc.instances[target].geometries[2][1]    # becomes green like the right wall
+    assert new_mat != old[1]
+    a.SetGeometryMaterial(insts[target], gi, mats[new_mat])
+    a.ClearSensor(sensor)
+    a.RenderLaunches(sensor, lens, 1)
+    img_a = a.ReadSensor(sensor).copy()
+    sc.instances[target].geometries[gi] = (old[0], new_mat, old[2])
+    img_b, _, _ = gpu_render(sc, 1)
+    assert not np.array_equal(img_a, a.GetSensorData(sensor) * 0)
+    np.testing.assert_array_equal(img_a.view(np.uint32), img_b.view(np.uint32))
