@@ -23,6 +23,10 @@ struct Bounds {
 };
 
 constexpr int kBins = 16;
+// Below this depth a range is split by SAH; deeper ranges are halved by index, so the tree is at most
+// kMaxSahDepth + ceil(log2 n) <= 72 levels deep and the single-level traversal (stack of MSNE_STACK = 96 entries, one
+// per level) needs no overflow check.
+constexpr uint32_t kMaxSahDepth = 40;
 
 void setChildBox(BvhNode2& n, int slot, const Bounds& bIn) {
     BuildBox b;
@@ -55,7 +59,7 @@ void buildBvh2(const BuildBox* boxes, uint32_t n, uint32_t maxLeaf, BuiltBvh& ou
     out.nodes.push_back(root);
     if (n == 0) return;
 
-    struct Range { uint32_t first, count; int32_t node; };  // node whose two children are the split of this range
+    struct Range { uint32_t first, count; int32_t node; uint32_t depth; };  // node whose two children are the split of this range
     std::vector<Range> work;
     if (n <= maxLeaf) {
         Bounds b;
@@ -64,7 +68,7 @@ void buildBvh2(const BuildBox* boxes, uint32_t n, uint32_t maxLeaf, BuiltBvh& ou
         out.nodes[0].c[0] = 0; out.nodes[0].c[2] = (int32_t)n;
         return;
     }
-    work.push_back({0, n, 0});
+    work.push_back({0, n, 0, 0});
     while (!work.empty()) {
         Range r = work.back(); work.pop_back();
         uint32_t* ord = out.order.data() + r.first;
@@ -72,7 +76,7 @@ void buildBvh2(const BuildBox* boxes, uint32_t n, uint32_t maxLeaf, BuiltBvh& ou
         Bounds cb;
         for (uint32_t i = 0; i < r.count; i++) cb.growPoint(&cent[(size_t)ord[i] * 3]);
         int bestAxis = -1; int bestBin = -1; float bestCost = 1e38f;
-        for (int a = 0; a < 3; a++) {
+        for (int a = 0; a < 3 && r.depth < kMaxSahDepth; a++) {
             float ext = cb.hi[a] - cb.lo[a];
             if (!(ext > 0.0f)) continue;
             Bounds binB[kBins]; uint32_t binN[kBins] = {0};
@@ -130,7 +134,7 @@ void buildBvh2(const BuildBox* boxes, uint32_t n, uint32_t maxLeaf, BuiltBvh& ou
                 out.nodes.push_back(child);
                 out.nodes[r.node].c[s] = idx;
                 out.nodes[r.node].c[2 + s] = 0;
-                work.push_back({fst[s], cnt[s], idx});
+                work.push_back({fst[s], cnt[s], idx, r.depth + 1});
             }
         }
     }

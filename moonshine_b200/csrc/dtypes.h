@@ -24,13 +24,18 @@ namespace msne {
 //   0 <= ref < REF_ITEM      inner node index in the pooled node array
 //   ref < 0                  BLAS leaf: x = ~ref, first triangle = x >> 3, count = (x & 7) + 1
 //   REF_ITEM | slot          TLAS leaf: one instance, tlasItems[slot]
-//   REF_EMPTY                no child;  REF_LEAVE / REF_END are stack sentinels of the traversal loop
+//   REF_EMPTY                no child: its box is the point (3e38, 3e38, 3e38), which no slab test can reach, so the
+//                            kernels never look at the reference;  REF_LEAVE / REF_END are stack sentinels
 // Every BVH has at least one inner node (the root).
 struct BvhNode2 {
     float n0[4], n1[4], n2[4];
     int32_t c[4];
 };
 static_assert(sizeof(BvhNode2) == 64, "BvhNode2 must be 64 B");
+inline void setEmptyChild(BvhNode2& n, int s) {
+    float* xy = s == 0 ? n.n0 : n.n1;
+    xy[0] = xy[1] = xy[2] = xy[3] = 3e38f; n.n2[2 * s] = n.n2[2 * s + 1] = 3e38f;
+}
 
 static const int32_t REF_ITEM = 0x40000000, REF_EMPTY = 0x7FFFFFFD, REF_LEAVE = 0x7FFFFFFE, REF_END = 0x7FFFFFFF;
 
@@ -84,6 +89,8 @@ struct DeviceScene {
     uint32_t envLevels;
     uint32_t envLevelOffset[12];   // float offset of each mip inside envLum
     const float* srgbLut;          // 256 floats
+    uint32_t staticOnly;           // 1: the TLAS holds nothing but the merged static BLAS -> single-level traversal from staticRoot
+    uint32_t staticRoot;
 };
 
 // specialization constants (main.hlsl:34-40) as runtime values

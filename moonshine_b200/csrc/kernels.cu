@@ -107,7 +107,8 @@ DI uint32_t hitBin(const DeviceScene& sc, const HitRec& h) {
 #ifndef DYN_FETCH_MIN
 #define DYN_FETCH_MIN 0   // 0 = off. Measured on cfg3: 12/20/24 were 10-18 % slower than off (profiles/r01_sweeps.md)
 #endif
-__global__ void __launch_bounds__(TRACE_THREADS, TRACE_BLOCKS_PER_SM) k_trace(DeviceScene sc, PathBuffers pb, WaveState ws, uint32_t buf) {
+template <bool TWO_LEVEL>
+__global__ void __launch_bounds__(TRACE_THREADS, TWO_LEVEL ? TRACE_BLOCKS_PER_SM : TRACE1_BLOCKS_PER_SM) k_trace(DeviceScene sc, PathBuffers pb, WaveState ws, uint32_t buf) {
     const Counters cin = ws.counters[buf];
     const uint32_t nLive = cin.nLive, total = cin.nLive + cin.nShadow;
     const uint32_t lane = threadIdx.x & 31;
@@ -132,10 +133,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_BLOCKS_PER_SM) k_trace(De
                     active = true;
                     if (idx < nLive) {
                         const float4 r0 = pb.R0[buf][idx], r1 = pb.R1[buf][idx];
-                        tv.begin(sc, stack, mk3(r0.x, r0.y, r0.z), mk3(r1.x, r1.y, r1.z), 0.0f, MS_INFINITY);
+                        tv.template begin<TWO_LEVEL>(sc, stack, mk3(r0.x, r0.y, r0.z), mk3(r1.x, r1.y, r1.z), 0.0f, MS_INFINITY);
                     } else {
                         const float4 q0 = pb.Q0[idx - nLive], q1 = pb.Q1[idx - nLive];
-                        tv.begin(sc, stack, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), 0.0f, q0.w);
+                        tv.template begin<TWO_LEVEL>(sc, stack, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), 0.0f, q0.w);
                         tv.target = __float_as_uint(q1.w);
                     }
                 }
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_BLOCKS_PER_SM) k_trace(De
         uint32_t bin = 0xFFu;
         if (active) {
             const bool anyHit = idx >= nLive;
-            const bool done = anyHit ? tv.template run<true>(sc, stack, more) : tv.template run<false>(sc, stack, more);
+            const bool done = anyHit ? tv.template run<true, TWO_LEVEL>(sc, stack, more) : tv.template run<false, TWO_LEVEL>(sc, stack, more);
             if (done) {
                 active = false;
                 if (!anyHit) {
@@ -621,7 +622,8 @@ void launchGenerate(cudaStream_t st, const DCamera& cam, const DConstants& k, co
     k_generate<<<grid1((uint64_t)nPix * nSamples, 256), 256, 0, st>>>(cam, k, pb, counters, pixIds, nPix, nSamples, firstSample);
 }
 void launchTrace(cudaStream_t st, int blocks, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf) {
-    k_trace<<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf);
+    if (sc.staticOnly) k_trace<false><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf);
+    else k_trace<true><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf);
 }
 // Register caps (measured, profiles/r01_sweeps.md): the all-material kernel runs best at 80 registers
 // (6 blocks/SM); the specialised kernels are smaller and take the same cap.
@@ -665,7 +667,10 @@ void launchPrimaryProbe(cudaStream_t st, const DCamera& cam, const DConstants& k
 }
 int traceOccupancyBlocksPerSm() {
     int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace, TRACE_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<true>, TRACE_THREADS, 0);
+    int n1 = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, k_trace<false>, TRACE_THREADS, 0);
+    n = n > n1 ? n : n1;
     return n;
 }
 int shadeOccupancyBlocksPerSm() {

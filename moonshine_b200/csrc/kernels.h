@@ -11,6 +11,9 @@ namespace msne {
 #ifndef TRACE_BLOCKS_PER_SM
 #define TRACE_BLOCKS_PER_SM 8   // 64 registers: measured best (profiles/r01_sweeps.md)
 #endif
+#ifndef TRACE1_BLOCKS_PER_SM
+#define TRACE1_BLOCKS_PER_SM 9  // single-level specialisation (no transformed instances): 56 registers, measured best of 8/9/10
+#endif
 #ifndef SHADE_THREADS
 #define SHADE_THREADS 128
 #endif

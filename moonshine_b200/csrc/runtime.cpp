@@ -206,7 +206,7 @@ struct HdMoonshine {
     DevBuf<float4> dEnvRgb;
     DevBuf<float> dEnvLum;
     uint32_t envSize = 0, envLevels = 0, envLevelOffset[12] = {0};
-    bool hasTlas = false;
+    bool hasTlas = false, tlasStaticOnly = false;
 
     MsneSpecConstants consts{};   // hydra defaults (hydra.zig:97-105)
     std::vector<Lens> lenses;
@@ -228,6 +228,7 @@ struct HdMoonshine {
     int traceBlocks = 0, shadeBlocks = 0;
     uint32_t maxLeaf = 3;   // triangles per BVH leaf (<= 8: 3-bit count in the leaf reference); 2-3 measured best
     uint64_t tailThreshold = 32768;   // survivors below this are finished by k_tail (0 = never)
+    bool forceTwoLevel = false;       // MSNE_TWO_LEVEL=1: never use the single-level trace kernel (A/B measurements)
     bool logBounces = false;          // MSNE_LOG_BOUNCES=1: queue sizes after every bounce on stderr
     uint64_t binnedThreshold = 262144;   // survivors below this use the single generic shade launch
 
@@ -263,6 +264,7 @@ struct HdMoonshine {
         setBackground(white, 1, 1);   // addDefaultBackground (BackgroundManager.zig:116-126)
         if (const char* e = getenv("MSNE_MAX_LEAF")) maxLeaf = (uint32_t)std::min(8, std::max(1, atoi(e)));
         if (const char* e = getenv("MSNE_TLAS_MAX_REFITS")) maxRefits = (uint32_t)std::max(0, atoi(e));
+        if (const char* e = getenv("MSNE_TWO_LEVEL")) forceTwoLevel = atoi(e) != 0;
         if (const char* e = getenv("MSNE_LOG_BOUNCES")) logBounces = atoi(e) != 0;
         if (const char* e = getenv("MSNE_TAIL_THRESHOLD")) tailThreshold = strtoull(e, nullptr, 10);
         traceBlocks = smCount * std::max(1, traceOccupancyBlocksPerSm());
@@ -314,7 +316,7 @@ struct HdMoonshine {
             for (int s = 0; s < 2; s++) {
                 const int32_t child = n.c[s], count = n.c[2 + s];
                 if (count > 0) n.c[s] = (int32_t)~((((uint32_t)child + triBase) << 3) | (uint32_t)(count - 1));
-                else if (child < 0) n.c[s] = REF_EMPTY;
+                else if (child < 0) { n.c[s] = REF_EMPTY; setEmptyChild(n, s); }
                 else n.c[s] = child + (int32_t)nodeBase;
             }
             n.c[2] = n.c[3] = 0;
@@ -488,6 +490,7 @@ struct HdMoonshine {
         }
         dInstances.upload(di.data(), di.size(), stream);
         hasTlas = !items.empty();
+        tlasStaticOnly = haveStatic && items.size() == 1;
         if (hasTlas) {
             BuiltBvh tl;
             buildBvh2(boxes.data(), (uint32_t)boxes.size(), 1, tl);
@@ -497,7 +500,7 @@ struct HdMoonshine {
                 for (int s = 0; s < 2; s++) {
                     const int32_t child = n.c[s], count = n.c[2 + s];
                     if (count > 0) n.c[s] = REF_ITEM | child;   // leaf size is 1: one instance per TLAS leaf
-                    else if (child < 0) n.c[s] = REF_EMPTY;
+                    else if (child < 0) { n.c[s] = REF_EMPTY; setEmptyChild(n, s); }
                 }
             for (BvhNode2& n : tl.nodes) n.c[2] = n.c[3] = 0;
             dTlasNodes.upload(tl.nodes.data(), tl.nodes.size(), stream);
@@ -545,6 +548,7 @@ struct HdMoonshine {
         sc.envRgb = reinterpret_cast<const float*>(dEnvRgb.p); sc.envLum = dEnvLum.p; sc.envSize = envSize; sc.envLevels = envLevels;
         for (int i = 0; i < 12; i++) sc.envLevelOffset[i] = envLevelOffset[i];
         sc.srgbLut = dSrgbLut.p;
+        sc.staticOnly = (tlasStaticOnly && !forceTwoLevel) ? 1u : 0u; sc.staticRoot = staticRec.blasRoot;
         return sc;
     }
     DConstants deviceConstants() const {

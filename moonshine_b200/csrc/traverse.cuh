@@ -91,8 +91,8 @@ DI bool traceRay(const DeviceScene& sc, const float3 o, const float3 d, const fl
             const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
             const int2 c = __ldg(reinterpret_cast<const int2*>(np + 3));
             float tn0, tn1;
-            const bool h0 = slab(ray, n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, tmin, bestT, tn0) && c.x != REF_EMPTY;
-            const bool h1 = slab(ray, n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, tmin, bestT, tn1) && c.y != REF_EMPTY;
+            const bool h0 = slab(ray, n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, tmin, bestT, tn0);   // an empty child's box is unreachable (dtypes.h)
+            const bool h1 = slab(ray, n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, tmin, bestT, tn1);
             if (h0 && h1) {
                 const bool swap = tn1 < tn0;
                 node = swap ? c.y : c.x;
@@ -168,16 +168,21 @@ struct Traversal {
     uint32_t curInst, target;
     int sp, node, leaf;
 
+    // TWO_LEVEL = false: the TLAS holds nothing but the merged static BLAS (DeviceScene::staticOnly), so the walk starts at
+    // its root in world space and the instance-entry / leave code (and the registers that keep the world-space ray) go away.
+    template <bool TWO_LEVEL>
     DI void begin(const DeviceScene& sc, int* stack, float3 o_, float3 d_, float tmin_, float tmax_) {
         o = o_; d = d_; tmin = tmin_; tmax = tmax_; bestT = tmax_;
         hit.inst = MISS_ID; hit.tri = 0; hit.u = 0.0f; hit.v = 0.0f;
         ray.set(o, d);
-        nodes = sc.tlasNodes; curInst = MISS_ID; target = 0;
+        target = 0;
         sp = 0; stack[sp++] = REF_END;
-        node = sc.tlasNodes ? 0 : REF_END; leaf = 0;
+        leaf = 0;
+        if (TWO_LEVEL) { nodes = sc.tlasNodes; curInst = MISS_ID; node = sc.tlasNodes ? 0 : REF_END; }
+        else { nodes = sc.blasNodes; curInst = STATIC_INST; node = (int)sc.staticRoot; }
     }
 
-    template <bool ANY_HIT>
+    template <bool ANY_HIT, bool TWO_LEVEL>
     DI bool run(const DeviceScene& sc, int* stack, bool mayRefill) {
         while (node != REF_END) {
             while ((uint32_t)node < (uint32_t)REF_ITEM) {
@@ -185,13 +190,14 @@ struct Traversal {
                 const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
                 const int2 c = __ldg(reinterpret_cast<const int2*>(np + 3));
                 float tn0, tn1;
-                const bool h0 = slab(ray, n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, tmin, bestT, tn0) && c.x != REF_EMPTY;
-                const bool h1 = slab(ray, n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, tmin, bestT, tn1) && c.y != REF_EMPTY;
+                const bool h0 = slab(ray, n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, tmin, bestT, tn0);   // an empty child's box is unreachable (dtypes.h)
+                const bool h1 = slab(ray, n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, tmin, bestT, tn1);
                 if (h0 && h1) {
                     const bool swap = tn1 < tn0;
                     node = swap ? c.y : c.x;
                     const int far = swap ? c.x : c.y;
-                    if (sp < MSNE_STACK) stack[sp++] = far;
+                    // the single-level walk cannot outgrow the stack: buildBvh2 bounds the depth (bvh_build.cpp kMaxSahDepth)
+                    if (TWO_LEVEL ? sp < MSNE_STACK : true) stack[sp++] = far;
                 } else if (h0) node = c.x;
                 else if (h1) node = c.y;
                 else node = stack[--sp];
@@ -221,7 +227,7 @@ struct Traversal {
                 leaf = 0;
                 if (node < 0) { leaf = node; node = stack[--sp]; }
             }
-            if ((uint32_t)node >= (uint32_t)REF_ITEM && node != REF_END) {
+            if (TWO_LEVEL && (uint32_t)node >= (uint32_t)REF_ITEM && node != REF_END) {
                 if (node == REF_LEAVE) {
                     ray.set(o, d); nodes = sc.tlasNodes; curInst = MISS_ID;
                     node = stack[--sp];
