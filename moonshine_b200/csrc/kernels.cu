@@ -100,63 +100,36 @@ DI uint32_t hitBin(const DeviceScene& sc, const HitRec& h) {
     return __ldg(&sc.materials[mat].type);
 }
 
-// Persistent-threads trace kernel with dynamic ray fetch. Each lane owns a resumable traversal (traverse.cuh
-// `Traversal`); when fewer than DYN_FETCH_MIN lanes of a warp are still walking the BVH, the warp leaves the
-// traversal loop, finished lanes write their results / bin their hit, and idle lanes take new rays from the
-// global ticket counter (ballot + popc compaction of the idle lanes, one atomic per refill).
-#ifndef DYN_FETCH_MIN
-#define DYN_FETCH_MIN 0   // 0 = off. Measured on cfg3: 12/20/24 were 10-18 % slower than off (profiles/r01_sweeps.md)
-#endif
+// Persistent-threads trace kernel: warps pull 32-ray tickets from the joint index space [extension rays | shadow rays]
+// of this bounce, every lane walks its ray to the end (traverse.cuh), then the warp sorts its hits by material type.
+// Refilling idle lanes before the whole ticket is done ("dynamic fetch") was measured in three variants and is not
+// used (profiles/r01_sweeps.md).
 template <bool TWO_LEVEL>
 __global__ void __launch_bounds__(TRACE_THREADS, TWO_LEVEL ? TRACE_BLOCKS_PER_SM : TRACE1_BLOCKS_PER_SM) k_trace(DeviceScene sc, PathBuffers pb, WaveState ws, uint32_t buf) {
     const Counters cin = ws.counters[buf];
     const uint32_t nLive = cin.nLive, total = cin.nLive + cin.nShadow;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t ltMask = (1u << lane) - 1u;
-    int stack[MSNE_STACK];
-    Traversal tv;
-    tv.node = REF_END;
-    bool active = false, more = sc.tlasNodes != nullptr || total > 0;
-    uint32_t idx = 0;
     for (;;) {
-        // ---- refill idle lanes -------------------------------------------------------------------------
-        const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !active);
-        if (more && idle) {
-            const uint32_t n = (uint32_t)__popc(idle);
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(ws.traceTicket, n);
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            more = base + n < total;
-            if (!active) {
-                idx = base + (uint32_t)__popc(idle & ltMask);
-                if (idx < total) {
-                    active = true;
-                    if (idx < nLive) {
-                        const float4 r0 = pb.R0[buf][idx], r1 = pb.R1[buf][idx];
-                        tv.template begin<TWO_LEVEL>(sc, stack, mk3(r0.x, r0.y, r0.z), mk3(r1.x, r1.y, r1.z), 0.0f, MS_INFINITY);
-                    } else {
-                        const float4 q0 = pb.Q0[idx - nLive], q1 = pb.Q1[idx - nLive];
-                        tv.template begin<TWO_LEVEL>(sc, stack, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), 0.0f, q0.w);
-                        tv.target = __float_as_uint(q1.w);
-                    }
-                }
-            }
-        }
-        if (__ballot_sync(0xFFFFFFFFu, active) == 0) break;
-        // ---- traverse ---------------------------------------------------------------------------------------
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(ws.traceTicket, 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= total) break;
+        const uint32_t idx = base + lane;
         uint32_t bin = 0xFFu;
-        if (active) {
-            const bool anyHit = idx >= nLive;
-            const bool done = anyHit ? tv.template run<true, TWO_LEVEL>(sc, stack, more) : tv.template run<false, TWO_LEVEL>(sc, stack, more);
-            if (done) {
-                active = false;
-                if (!anyHit) {
-                    pb.H[idx] = make_uint4(tv.hit.inst, tv.hit.tri, __float_as_uint(tv.hit.u), __float_as_uint(tv.hit.v));
-                    bin = hitBin(sc, tv.hit);
-                } else if (tv.hit.inst != MISS_ID) {
-                    float4* n = (tv.target & 1u) ? pb.N1[buf] : pb.N0[buf];
-                    n[tv.target >> 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+        if (idx < nLive) {
+            const float4 r0 = pb.R0[buf][idx], r1 = pb.R1[buf][idx];
+            HitRec h;
+            traceRay<false, TWO_LEVEL>(sc, mk3(r0.x, r0.y, r0.z), mk3(r1.x, r1.y, r1.z), 0.0f, MS_INFINITY, h);
+            pb.H[idx] = make_uint4(h.inst, h.tri, __float_as_uint(h.u), __float_as_uint(h.v));
+            bin = hitBin(sc, h);
+        } else if (idx < total) {
+            const float4 q0 = pb.Q0[idx - nLive], q1 = pb.Q1[idx - nLive];
+            HitRec h;
+            if (traceRay<true, TWO_LEVEL>(sc, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), 0.0f, q0.w, h)) {
+                const uint32_t target = __float_as_uint(q1.w);
+                float4* n = (target & 1u) ? pb.N1[buf] : pb.N0[buf];
+                n[target >> 1] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
         // ---- warp-level sort by material id: lanes with the same bin elect a leader that reserves their slots
@@ -189,9 +162,9 @@ __global__ void k_trace_probe(DeviceScene sc, const float* __restrict__ rays8, u
     const float* r = rays8 + 8 * (size_t)i;
     HitRec h;
     uint32_t geom = 0, prim = 0;
-    if (anyHit) traceRay<true>(sc, mk3(r[0], r[1], r[2]), mk3(r[4], r[5], r[6]), r[3], r[7], h);
+    if (anyHit) traceRay<true, true>(sc, mk3(r[0], r[1], r[2]), mk3(r[4], r[5], r[6]), r[3], r[7], h);
     else {
-        traceRay<false>(sc, mk3(r[0], r[1], r[2]), mk3(r[4], r[5], r[6]), r[3], r[7], h);
+        traceRay<false, true>(sc, mk3(r[0], r[1], r[2]), mk3(r[4], r[5], r[6]), r[3], r[7], h);
         if (h.inst != MISS_ID) { geom = sc.tris[h.tri].geom; prim = sc.tris[h.tri].prim; }
     }
     uint32_t* o = hits5 + 5 * (size_t)i;
@@ -208,7 +181,7 @@ __global__ void k_pick(DeviceScene sc, DCamera cam, float2 coords, MsneClick* ou
     float3 o, d;
     cameraRayUV(cam, uv, mk2(0.0f, 0.0f), o, d);
     HitRec h;
-    traceRay<false>(sc, o, d, 0.0f, MS_INFINITY, h);
+    traceRay<false, true>(sc, o, d, 0.0f, MS_INFINITY, h);
     MsneClick c;
     c.instance_index = -1; c.geometry_index = 0; c.primitive_index = 0; c.bary[0] = 0.0f; c.bary[1] = 0.0f;
     if (h.inst != MISS_ID) {
@@ -503,19 +476,19 @@ __global__ void __launch_bounds__(128) k_tail(DeviceScene sc, DConstants k, Path
             HitRec h;
             if (out.envRay) {
                 nShadow++;
-                if (traceRay<true>(sc, mk3(out.envQ0.x, out.envQ0.y, out.envQ0.z), mk3(out.envQ1.x, out.envQ1.y, out.envQ1.z), 0.0f, out.envQ0.w, h))
+                if (traceRay<true, true>(sc, mk3(out.envQ0.x, out.envQ0.y, out.envQ0.z), mk3(out.envQ1.x, out.envQ1.y, out.envQ1.z), 0.0f, out.envQ0.w, h))
                     out.N0 = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             if (out.meshRay) {
                 nShadow++;
-                if (traceRay<true>(sc, mk3(out.meshQ0.x, out.meshQ0.y, out.meshQ0.z), mk3(out.meshQ1.x, out.meshQ1.y, out.meshQ1.z), 0.0f, out.meshQ0.w, h))
+                if (traceRay<true, true>(sc, mk3(out.meshQ0.x, out.meshQ0.y, out.meshQ0.z), mk3(out.meshQ1.x, out.meshQ1.y, out.meshQ1.z), 0.0f, out.meshQ0.w, h))
                     out.N1 = make_float4(0.f, 0.f, 0.f, 0.f);
             }
             pb.R0[buf][q] = out.R0; pb.R1[buf][q] = out.R1; pb.S0[buf][q] = out.S0; pb.S1[buf][q] = out.S1;
             pb.N0[buf][q] = out.N0; pb.N1[buf][q] = out.N1;
             if (out.kind == 1) {
                 nClosest++;
-                traceRay<false>(sc, mk3(out.R0.x, out.R0.y, out.R0.z), mk3(out.R1.x, out.R1.y, out.R1.z), 0.0f, MS_INFINITY, h);
+                traceRay<false, true>(sc, mk3(out.R0.x, out.R0.y, out.R0.z), mk3(out.R1.x, out.R1.y, out.R1.z), 0.0f, MS_INFINITY, h);
                 pb.H[q] = make_uint4(h.inst, h.tri, __float_as_uint(h.u), __float_as_uint(h.v));
             }
         }

@@ -11,13 +11,15 @@
 //   closest = min t, ties -> smallest (instance, geometry, primitive); no culling; mask 0 skipped.
 // The slab test is only required to be conservative (boxes are padded at build time, bvh_build.h).
 //
-// Loop structure ("while-while with postponed leaves"): a lane walks inner nodes until it holds a leaf,
-// parks it and keeps descending until a second leaf shows up; only then does it run triangle tests. Lanes
-// of a warp therefore meet in the triangle loop instead of executing it one lane at a time (the v1 kernel
-// ran at 4.8/32 active lanes per instruction, profiles/r01a_ncu_summary_baseline.txt).
-// All visible identity-transform instances live in ONE world-space BLAS (runtime.cpp buildAccel): an identity
+// Loop structure: classic while-while. A lane walks inner nodes until it reaches a leaf, tests the leaf's triangles at
+// once (so the next slab tests already see the shorter ray), pops, and goes back to walking. Postponing leaves (park one
+// or two and keep descending) was measured: parking one costs 2 %, parking two 12 % (profiles/r01_sweeps.md) - the extra
+// speculative node visits outweigh the fuller triangle loop.
+// All visible identity-transform instances live in ONE world-space BLAS (runtime.cpp buildGeometry): an identity
 // transform leaves the ray bit-identical, so flattening changes no result, and their triangles carry the
-// instance index.
+// instance index. TWO_LEVEL = false is the specialisation for scenes whose TLAS holds nothing else
+// (DeviceScene::staticOnly): the walk starts at that BLAS root and the instance entry / leave code, the registers that
+// keep the world-space ray, and the stack-overflow test (bvh_build.cpp bounds the depth) go away.
 #pragma once
 #include "device_math.cuh"
 
@@ -25,9 +27,6 @@ namespace msne {
 
 #ifndef MSNE_STACK
 #define MSNE_STACK 96
-#endif
-#ifndef DYN_FETCH_MIN
-#define DYN_FETCH_MIN 0   // 0 = off. Measured on cfg3: 12/20/24 were 10-18 % slower than off (profiles/r01_sweeps.md)
 #endif
 
 struct HitRec { uint32_t inst, tri; float u, v; };
@@ -71,7 +70,7 @@ DI bool triTest(const float4 t0, const float4 t1, const float4 t2, const SpaceRa
     return tmin < t && t < tmax;
 }
 
-template <bool ANY_HIT>
+template <bool ANY_HIT, bool TWO_LEVEL>
 DI bool traceRay(const DeviceScene& sc, const float3 o, const float3 d, const float tmin, const float tmax, HitRec& hit) {
     hit.inst = MISS_ID; hit.tri = 0; hit.u = 0.0f; hit.v = 0.0f;
     if (sc.tlasNodes == nullptr) return false;
@@ -80,12 +79,11 @@ DI bool traceRay(const DeviceScene& sc, const float3 o, const float3 d, const fl
     int sp = 0;
     stack[sp++] = REF_END;
     SpaceRay ray; ray.set(o, d);
-    const BvhNode2* nodes = sc.tlasNodes;
-    uint32_t curInst = MISS_ID;
-    int node = 0;   // current reference (see dtypes.h): inner node, leaf (<0), TLAS item, or sentinel
-    int leaf = 0;   // parked leaf reference (0 = none; 0 is never a leaf code)
+    const BvhNode2* nodes = TWO_LEVEL ? sc.tlasNodes : sc.blasNodes;
+    uint32_t curInst = TWO_LEVEL ? MISS_ID : STATIC_INST;
+    int node = TWO_LEVEL ? 0 : (int)sc.staticRoot;   // current reference (dtypes.h): inner node, leaf (<0), TLAS item, or sentinel
     while (node != REF_END) {
-        // ---- inner nodes: descend until two leaves are pending (or the stack yields a non-inner entry) ----
+        // ---- inner nodes: descend until a leaf (or a TLAS item / sentinel) comes up ------------------------------
         while ((uint32_t)node < (uint32_t)REF_ITEM) {
             const float4* np = reinterpret_cast<const float4*>(nodes + node);
             const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
@@ -97,15 +95,14 @@ DI bool traceRay(const DeviceScene& sc, const float3 o, const float3 d, const fl
                 const bool swap = tn1 < tn0;
                 node = swap ? c.y : c.x;
                 const int far = swap ? c.x : c.y;
-                if (sp < MSNE_STACK) stack[sp++] = far;
+                if (TWO_LEVEL ? sp < MSNE_STACK : true) stack[sp++] = far;
             } else if (h0) node = c.x;
             else if (h1) node = c.y;
             else node = stack[--sp];
-            if (node < 0 && leaf == 0) { leaf = node; node = stack[--sp]; }   // park the first leaf, keep walking
         }
-        // ---- triangles of the parked leaf, then of `node` if that is a leaf too --------------------------
-        while (leaf != 0) {
-            const uint32_t x = ~(uint32_t)leaf;
+        // ---- leaves ---------------------------------------------------------------------------------------------
+        while (node < 0) {
+            const uint32_t x = ~(uint32_t)node;
             const uint32_t first = x >> 3, count = (x & 7u) + 1u;
             for (uint32_t i = 0; i < count; i++) {
                 const float4* tp = reinterpret_cast<const float4*>(sc.tris + (first + i));
@@ -113,7 +110,9 @@ DI bool traceRay(const DeviceScene& sc, const float3 o, const float3 d, const fl
                 float t, u, v;
                 if (!triTest(t0, t1, t2, ray, tmin, tmax, t, u, v)) continue;
                 const uint32_t inst = curInst == STATIC_INST ? __float_as_uint(t2.w) : curInst;
-                if (ANY_HIT) { hit.inst = inst; return true; }
+                // structured exit (no `return` from inside the loops): with an early return ptxas gives up the convergence
+                // barriers of the whole any-hit walk and its lanes never re-join (-15 % on k_trace, profiles/r01_sweeps.md)
+                if (ANY_HIT) { hit.inst = inst; node = REF_END; break; }
                 bool better = t < bestT;
                 if (!better && t == bestT && hit.inst != MISS_ID) {
                     if (inst != hit.inst) better = inst < hit.inst;
@@ -125,11 +124,10 @@ DI bool traceRay(const DeviceScene& sc, const float3 o, const float3 d, const fl
                 }
                 if (better) { bestT = t; hit.inst = inst; hit.tri = first + i; hit.u = u; hit.v = v; }
             }
-            leaf = 0;
-            if (node < 0) { leaf = node; node = stack[--sp]; }
+            if (!(ANY_HIT && node == REF_END)) node = stack[--sp];
         }
-        // ---- level changes (rare relative to node steps) -------------------------------------------------
-        if ((uint32_t)node >= (uint32_t)REF_ITEM && node != REF_END) {
+        // ---- level changes (rare relative to node steps) -----------------------------------------------------------
+        if (TWO_LEVEL && (uint32_t)node >= (uint32_t)REF_ITEM && node != REF_END) {
             if (node == REF_LEAVE) {
                 ray.set(o, d); nodes = sc.tlasNodes; curInst = MISS_ID;
                 node = stack[--sp];
@@ -155,106 +153,5 @@ DI bool traceRay(const DeviceScene& sc, const float3 o, const float3 d, const fl
     }
     return hit.inst != MISS_ID;
 }
-
-
-// Resumable form of traceRay for the persistent kernel: the same loop, with its state in a struct so a lane can
-// leave the loop (dynamic fetch) and continue later. `run` returns true when the ray is finished.
-struct Traversal {
-    float3 o, d;
-    float tmin, tmax, bestT;
-    SpaceRay ray;
-    HitRec hit;
-    const BvhNode2* nodes;
-    uint32_t curInst, target;
-    int sp, node, leaf;
-
-    // TWO_LEVEL = false: the TLAS holds nothing but the merged static BLAS (DeviceScene::staticOnly), so the walk starts at
-    // its root in world space and the instance-entry / leave code (and the registers that keep the world-space ray) go away.
-    template <bool TWO_LEVEL>
-    DI void begin(const DeviceScene& sc, int* stack, float3 o_, float3 d_, float tmin_, float tmax_) {
-        o = o_; d = d_; tmin = tmin_; tmax = tmax_; bestT = tmax_;
-        hit.inst = MISS_ID; hit.tri = 0; hit.u = 0.0f; hit.v = 0.0f;
-        ray.set(o, d);
-        target = 0;
-        sp = 0; stack[sp++] = REF_END;
-        leaf = 0;
-        if (TWO_LEVEL) { nodes = sc.tlasNodes; curInst = MISS_ID; node = sc.tlasNodes ? 0 : REF_END; }
-        else { nodes = sc.blasNodes; curInst = STATIC_INST; node = (int)sc.staticRoot; }
-    }
-
-    template <bool ANY_HIT, bool TWO_LEVEL>
-    DI bool run(const DeviceScene& sc, int* stack, bool mayRefill) {
-        while (node != REF_END) {
-            while ((uint32_t)node < (uint32_t)REF_ITEM) {
-                const float4* np = reinterpret_cast<const float4*>(nodes + node);
-                const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
-                const int2 c = __ldg(reinterpret_cast<const int2*>(np + 3));
-                float tn0, tn1;
-                const bool h0 = slab(ray, n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, tmin, bestT, tn0);   // an empty child's box is unreachable (dtypes.h)
-                const bool h1 = slab(ray, n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, tmin, bestT, tn1);
-                if (h0 && h1) {
-                    const bool swap = tn1 < tn0;
-                    node = swap ? c.y : c.x;
-                    const int far = swap ? c.x : c.y;
-                    // the single-level walk cannot outgrow the stack: buildBvh2 bounds the depth (bvh_build.cpp kMaxSahDepth)
-                    if (TWO_LEVEL ? sp < MSNE_STACK : true) stack[sp++] = far;
-                } else if (h0) node = c.x;
-                else if (h1) node = c.y;
-                else node = stack[--sp];
-                if (node < 0 && leaf == 0) { leaf = node; node = stack[--sp]; }
-            }
-            while (leaf != 0) {
-                const uint32_t x = ~(uint32_t)leaf;
-                const uint32_t first = x >> 3, count = (x & 7u) + 1u;
-                for (uint32_t i = 0; i < count; i++) {
-                    const float4* tp = reinterpret_cast<const float4*>(sc.tris + (first + i));
-                    const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
-                    float t, u, v;
-                    if (!triTest(t0, t1, t2, ray, tmin, tmax, t, u, v)) continue;
-                    const uint32_t inst = curInst == STATIC_INST ? __float_as_uint(t2.w) : curInst;
-                    if (ANY_HIT) { hit.inst = inst; node = REF_END; leaf = 0; return true; }
-                    bool better = t < bestT;
-                    if (!better && t == bestT && hit.inst != MISS_ID) {
-                        if (inst != hit.inst) better = inst < hit.inst;
-                        else {
-                            const uint32_t g = __float_as_uint(t0.w), p = __float_as_uint(t1.w);
-                            const uint32_t bg = sc.tris[hit.tri].geom, bp = sc.tris[hit.tri].prim;
-                            better = g != bg ? g < bg : p < bp;
-                        }
-                    }
-                    if (better) { bestT = t; hit.inst = inst; hit.tri = first + i; hit.u = u; hit.v = v; }
-                }
-                leaf = 0;
-                if (node < 0) { leaf = node; node = stack[--sp]; }
-            }
-            if (TWO_LEVEL && (uint32_t)node >= (uint32_t)REF_ITEM && node != REF_END) {
-                if (node == REF_LEAVE) {
-                    ray.set(o, d); nodes = sc.tlasNodes; curInst = MISS_ID;
-                    node = stack[--sp];
-                } else {
-                    const uint32_t inst = __ldg(sc.tlasItems + (node & ~REF_ITEM));
-                    const DInstance* in = sc.instances + inst;
-                    if (__ldg(&in->isStatic)) {
-                        curInst = STATIC_INST;
-                    } else {
-                        const float4* mp = reinterpret_cast<const float4*>(in->w2o);
-                        const float4 r0 = __ldg(mp), r1 = __ldg(mp + 1), r2 = __ldg(mp + 2);
-                        const float3 oo = mk3(((r0.x * o.x + r0.y * o.y) + r0.z * o.z) + r0.w, ((r1.x * o.x + r1.y * o.y) + r1.z * o.z) + r1.w,
-                                              ((r2.x * o.x + r2.y * o.y) + r2.z * o.z) + r2.w);
-                        const float3 od = mk3((r0.x * d.x + r0.y * d.y) + r0.z * d.z, (r1.x * d.x + r1.y * d.y) + r1.z * d.z, (r2.x * d.x + r2.y * d.y) + r2.z * d.z);
-                        ray.set(oo, od);
-                        curInst = inst;
-                    }
-                    nodes = sc.blasNodes;
-                    if (sp < MSNE_STACK) stack[sp++] = REF_LEAVE;
-                    node = (int)__ldg(&in->blasRoot);
-                }
-            }
-            // dynamic fetch: too few lanes of this warp are still traversing -> go refill the idle ones
-            if (mayRefill && __popc(__activemask()) < DYN_FETCH_MIN) break;
-        }
-        return node == REF_END;
-    }
-};
 
 }  // namespace msne
