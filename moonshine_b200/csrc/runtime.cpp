@@ -396,9 +396,28 @@ struct HdMoonshine {
         stats_static_builds++;
     }
 
+    // World-space bounds of a transformed instance (TLAS item). Small meshes (<= kHullVertices vertices): bounds of the
+    // transformed vertices - for a rotated object up to 2x tighter than the transformed object-space box, which is what
+    // decides how many instances a ray has to enter in instance-heavy scenes (cfg5: 10^6 icosahedra). Larger ones: the
+    // eight corners of the (padded) BLAS bounds. Either way padded again in world space.
+    static constexpr size_t kHullVertices = 4096;
     BuildBox instanceWorldBox(const HostInstance& in) const {
         const BuildBox& bb = blases[in.blas].bounds;
         BuildBox w; for (int a = 0; a < 3; a++) { w.lo[a] = 1e30f; w.hi[a] = -1e30f; }
+        size_t nVerts = 0;
+        for (uint32_t mk : in.meshKey) nVerts += meshes[mk]->pos.size() / 3;
+        if (nVerts > 0 && nVerts <= kHullVertices) {
+            for (uint32_t mk : in.meshKey) {
+                const std::vector<float>& pos = meshes[mk]->pos;
+                for (size_t v = 0; v + 2 < pos.size(); v += 3)
+                    for (int r = 0; r < 3; r++) {
+                        const float q = ((in.transform[4 * r] * pos[v] + in.transform[4 * r + 1] * pos[v + 1]) + in.transform[4 * r + 2] * pos[v + 2]) + in.transform[4 * r + 3];
+                        w.lo[r] = std::min(w.lo[r], q); w.hi[r] = std::max(w.hi[r], q);
+                    }
+            }
+            padBox(w); padBox(w);   // the object-space padding of the BLAS bounds is not inherited on this path
+            return w;
+        }
         for (int c = 0; c < 8; c++) {
             const float p[3] = {(c & 1) ? bb.hi[0] : bb.lo[0], (c & 2) ? bb.hi[1] : bb.lo[1], (c & 4) ? bb.hi[2] : bb.lo[2]};
             for (int r = 0; r < 3; r++) {
