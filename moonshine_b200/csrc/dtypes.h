@@ -88,7 +88,7 @@ struct DeviceScene {
     uint32_t envSize;
     uint32_t envLevels;
     uint32_t envLevelOffset[12];   // float offset of each mip inside envLum
-    const float* srgbLut;          // 256 floats
+    const float* texLuts;          // 512 floats: [0,256) sRGB -> linear, [256,512) c / 255 (shading.cuh)
     uint32_t staticOnly;           // 1: the TLAS holds nothing but the merged static BLAS -> single-level traversal from staticRoot
     uint32_t staticRoot;
 };

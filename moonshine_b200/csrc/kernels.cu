@@ -290,6 +290,7 @@ DI void shadeOne(const DeviceScene& sc, const DConstants& k, const PathBuffers& 
         throughput = throughput / pSurvive;
     }
 
+    prepareMaterial(material, outgoingDirSs);
     const bool isCurrentMaterialDelta = matIsDelta(material.type);
     float3 neeEnv = mk3(0.0f), neeMesh = mk3(0.0f);
     if (!isCurrentMaterialDelta) {

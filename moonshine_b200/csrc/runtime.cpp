@@ -254,9 +254,9 @@ struct HdMoonshine {
         CK(cudaMemsetAsync(dCounters.p, 0, 2 * sizeof(Counters), stream));
         CK(cudaMemsetAsync(dScalars.p, 0, 16 * sizeof(uint32_t), stream));
         CK(cudaMemsetAsync(dRayCounts.p, 0, 2 * sizeof(unsigned long long), stream));
-        float lut[256];
-        for (int i = 0; i < 256; i++) lut[i] = srgbToLinear(i);
-        dSrgbLut.upload(lut, 256, stream);
+        float lut[512];
+        for (int i = 0; i < 256; i++) { lut[i] = srgbToLinear(i); lut[256 + i] = (float)i / 255.0f; }   // UNORM: the same IEEE division a texel fetch would do
+        dSrgbLut.upload(lut, 512, stream);
         alias.assign(1, DAlias{0, 0.0f, 0, 0, 0});
         // hydra.zig:97-105
         consts = MsneSpecConstants{1, 1024, 0, 0, 0, 0, 0};
@@ -566,7 +566,7 @@ struct HdMoonshine {
         sc.alias = dAlias.p; sc.aliasEntries = (uint32_t)alias.size();
         sc.envRgb = reinterpret_cast<const float*>(dEnvRgb.p); sc.envLum = dEnvLum.p; sc.envSize = envSize; sc.envLevels = envLevels;
         for (int i = 0; i < 12; i++) sc.envLevelOffset[i] = envLevelOffset[i];
-        sc.srgbLut = dSrgbLut.p;
+        sc.texLuts = dSrgbLut.p;
         sc.staticOnly = (tlasStaticOnly && !forceTwoLevel) ? 1u : 0u; sc.staticRoot = staticRec.blasRoot;
         return sc;
     }

@@ -13,17 +13,22 @@
 namespace msne {
 
 // ---- textures ------------------------------------------------------------------------------------
-DI float4 fetchTexel(const DeviceScene& sc, const DTexture& t, uint32_t x, uint32_t y) {
+// `luts`: 512 floats, [0,256) = sRGB -> linear (IEC formula in double, rounded once), [256,512) = c / 255.0f (UNORM), both
+// tabulated on the host with the same IEEE operations the per-texel arithmetic would do, so values are identical and
+// the kernels do a cached load instead of a pow / an IEEE division per channel.
+DI float unorm8(const float* __restrict__ luts, uint32_t c) { return __ldg(luts + 256 + c); }
+DI float srgb8(const float* __restrict__ luts, uint32_t c) { return __ldg(luts + c); }
+DI float4 fetchTexel(const float* __restrict__ luts, const DTexture& t, uint32_t x, uint32_t y) {
     const size_t i = (size_t)y * t.w + x;
     switch (t.fmt) {
         case TEX_R32F: return make_float4(__ldg((const float*)t.data + i), 0.f, 0.f, 1.f);
         case TEX_RG32F: { float2 v = __ldg((const float2*)t.data + i); return make_float4(v.x, v.y, 0.f, 1.f); }
         case TEX_RGBA32F: return __ldg((const float4*)t.data + i);
-        case TEX_R8_UNORM: return make_float4((float)__ldg((const uint8_t*)t.data + i) / 255.0f, 0.f, 0.f, 1.f);
-        case TEX_RG8_UNORM: { uchar2 v = __ldg((const uchar2*)t.data + i); return make_float4((float)v.x / 255.0f, (float)v.y / 255.0f, 0.f, 1.f); }
+        case TEX_R8_UNORM: return make_float4(unorm8(luts, __ldg((const uint8_t*)t.data + i)), 0.f, 0.f, 1.f);
+        case TEX_RG8_UNORM: { uchar2 v = __ldg((const uchar2*)t.data + i); return make_float4(unorm8(luts, v.x), unorm8(luts, v.y), 0.f, 1.f); }
         case TEX_RGBA8_SRGB: {
             uchar4 v = __ldg((const uchar4*)t.data + i);
-            return make_float4(__ldg(sc.srgbLut + v.x), __ldg(sc.srgbLut + v.y), __ldg(sc.srgbLut + v.z), (float)v.w / 255.0f);
+            return make_float4(srgb8(luts, v.x), srgb8(luts, v.y), srgb8(luts, v.z), unorm8(luts, v.w));
         }
         default: {  // TEX_RGBA16F
             uint2 raw = __ldg((const uint2*)t.data + i);
@@ -32,7 +37,11 @@ DI float4 fetchTexel(const DeviceScene& sc, const DTexture& t, uint32_t x, uint3
         }
     }
 }
-DI int wrapRepeat(int i, int n) { int m = i % n; return m < 0 ? m + n : m; }
+// REPEAT addressing; power-of-two sizes (the common case) take the mask instead of the ~20-instruction integer modulo
+DI int wrapRepeat(int i, int n) {
+    if ((n & (n - 1)) == 0) return i & (n - 1);
+    int m = i % n; return m < 0 ? m + n : m;
+}
 DI int wrapMirror(int i, int n) {
     int m = i % (2 * n); if (m < 0) m += 2 * n;
     const int k = m - n;
@@ -40,28 +49,65 @@ DI int wrapMirror(int i, int n) {
     return (n - 1) - mir;
 }
 DI float4 lerp4(float4 a, float4 b, float t) { return make_float4(a.x + t * (b.x - a.x), a.y + t * (b.y - a.y), a.z + t * (b.z - a.z), a.w + t * (b.w - a.w)); }
+DI float bilerp1(float t00, float t10, float t01, float t11, float a, float b) {
+    const float top = t00 + a * (t10 - t00), bot = t01 + a * (t11 - t01);
+    return top + b * (bot - top);
+}
 
-// dTextures[idx].SampleLevel(dTextureSampler, uv, 0).
-// Deliberately NOT inlined: it is used ~6x per hit and each copy carries five 7-way format switches; inlined,
-// k_shade was 189 KB of SASS and stalled on instruction fetch (profiles/r01b). Arguments/return are scalars in
-// registers, so the call costs no local-memory traffic.
+// dTextures[idx].SampleLevel(dTextureSampler, uv, 0): exact FP32 bilinear lerp(lerp(t00,t10,a),lerp(t01,t11,a),b).
+// The format switch runs once per sample (not per texel) and each case filters only the channels the format has; the
+// constant channels (0, 0, 1) are what filtering them would give for finite weights (0 + a*(0-0), 1 + a*(1-1)).
+// Deliberately NOT inlined: it is used ~6x per hit; inlined, k_shade was 189 KB of SASS and stalled on instruction
+// fetch (profiles/r01b). Arguments/return are scalars in registers, so the call costs no local-memory traffic.
 #ifndef MSNE_INLINE_TEX
 __device__ __noinline__
 #else
 DI
 #endif
-float4 sampleTextureImpl(const DTexture* __restrict__ textures, const float* __restrict__ srgbLut, uint32_t idx, float u_, float v_) {
-    DeviceScene sc; sc.srgbLut = srgbLut;
+float4 sampleTextureImpl(const DTexture* __restrict__ textures, const float* __restrict__ luts, uint32_t idx, float u_, float v_) {
     const DTexture t = textures[idx];
-    if (t.w == 1 && t.h == 1) return fetchTexel(sc, t, 0, 0);
+    if (t.w == 1 && t.h == 1) return fetchTexel(luts, t, 0, 0);
     const float u = u_ * (float)t.w - 0.5f, v = v_ * (float)t.h - 0.5f;
     const float fu = floorf(u), fv = floorf(v);
     const float a = u - fu, b = v - fv;
     const int i0 = wrapRepeat((int)fu, t.w), i1 = wrapRepeat((int)fu + 1, t.w), j0 = wrapRepeat((int)fv, t.h), j1 = wrapRepeat((int)fv + 1, t.h);
-    const float4 t00 = fetchTexel(sc, t, i0, j0), t10 = fetchTexel(sc, t, i1, j0), t01 = fetchTexel(sc, t, i0, j1), t11 = fetchTexel(sc, t, i1, j1);
-    return lerp4(lerp4(t00, t10, a), lerp4(t01, t11, a), b);
+    const size_t o00 = (size_t)j0 * t.w + i0, o10 = (size_t)j0 * t.w + i1, o01 = (size_t)j1 * t.w + i0, o11 = (size_t)j1 * t.w + i1;
+    switch (t.fmt) {
+        case TEX_R8_UNORM: {
+            const uint8_t* d = (const uint8_t*)t.data;
+            const uint32_t c00 = __ldg(d + o00), c10 = __ldg(d + o10), c01 = __ldg(d + o01), c11 = __ldg(d + o11);
+            return make_float4(bilerp1(unorm8(luts, c00), unorm8(luts, c10), unorm8(luts, c01), unorm8(luts, c11), a, b), 0.f, 0.f, 1.f);
+        }
+        case TEX_RG8_UNORM: {
+            const uchar2* d = (const uchar2*)t.data;
+            const uchar2 c00 = __ldg(d + o00), c10 = __ldg(d + o10), c01 = __ldg(d + o01), c11 = __ldg(d + o11);
+            return make_float4(bilerp1(unorm8(luts, c00.x), unorm8(luts, c10.x), unorm8(luts, c01.x), unorm8(luts, c11.x), a, b),
+                               bilerp1(unorm8(luts, c00.y), unorm8(luts, c10.y), unorm8(luts, c01.y), unorm8(luts, c11.y), a, b), 0.f, 1.f);
+        }
+        case TEX_RGBA8_SRGB: {
+            const uchar4* d = (const uchar4*)t.data;
+            const uchar4 c00 = __ldg(d + o00), c10 = __ldg(d + o10), c01 = __ldg(d + o01), c11 = __ldg(d + o11);
+            return make_float4(bilerp1(srgb8(luts, c00.x), srgb8(luts, c10.x), srgb8(luts, c01.x), srgb8(luts, c11.x), a, b),
+                               bilerp1(srgb8(luts, c00.y), srgb8(luts, c10.y), srgb8(luts, c01.y), srgb8(luts, c11.y), a, b),
+                               bilerp1(srgb8(luts, c00.z), srgb8(luts, c10.z), srgb8(luts, c01.z), srgb8(luts, c11.z), a, b),
+                               bilerp1(unorm8(luts, c00.w), unorm8(luts, c10.w), unorm8(luts, c01.w), unorm8(luts, c11.w), a, b));
+        }
+        case TEX_R32F: {
+            const float* d = (const float*)t.data;
+            return make_float4(bilerp1(__ldg(d + o00), __ldg(d + o10), __ldg(d + o01), __ldg(d + o11), a, b), 0.f, 0.f, 1.f);
+        }
+        case TEX_RG32F: {
+            const float2* d = (const float2*)t.data;
+            const float2 c00 = __ldg(d + o00), c10 = __ldg(d + o10), c01 = __ldg(d + o01), c11 = __ldg(d + o11);
+            return make_float4(bilerp1(c00.x, c10.x, c01.x, c11.x, a, b), bilerp1(c00.y, c10.y, c01.y, c11.y, a, b), 0.f, 1.f);
+        }
+        default: {  // TEX_RGBA32F, TEX_RGBA16F
+            const float4 t00 = fetchTexel(luts, t, i0, j0), t10 = fetchTexel(luts, t, i1, j0), t01 = fetchTexel(luts, t, i0, j1), t11 = fetchTexel(luts, t, i1, j1);
+            return lerp4(lerp4(t00, t10, a), lerp4(t01, t11, a), b);
+        }
+    }
 }
-DI float4 sampleTexture(const DeviceScene& sc, uint32_t idx, float2 uv) { return sampleTextureImpl(sc.textures, sc.srgbLut, idx, uv.x, uv.y); }
+DI float4 sampleTexture(const DeviceScene& sc, uint32_t idx, float2 uv) { return sampleTextureImpl(sc.textures, sc.texLuts, idx, uv.x, uv.y); }
 
 // ---- reflection_frame.hlsl:3-85 ------------------------------------------------------------------
 struct Frame {
@@ -134,6 +180,11 @@ struct MaterialParams {
     float metalness;
     float alpha;      // GGX α = max(roughness², 0.001)
     float ior;        // StandardPBR.ior / Glass.intIOR
+    // per-hit invariants of pdf/eval/sample, evaluated once by prepareMaterial with the operations the HLSL repeats in
+    // every call (same operands -> same bits): color/π (:264, :153), p_spec (:218, :241), Λ(w_o) (:37-41 inside G)
+    float3 diffuse;
+    float pSpec;
+    float lambdaO;
 };
 
 DI float lambertPdf(float3 w_i, float3 w_o) { return sameHemisphere(w_i, w_o) ? fabsf(cosTheta(w_i)) / MS_PI : 0.0f; }   // :157-159
@@ -149,22 +200,20 @@ DI float microfacetPdf(const MaterialParams& m, float3 w_i, float3 w_o) {       
     return ggxPdf(m.alpha, h) / (4.0f * dot(w_o, h));
 }
 DI float pbrPdf(const MaterialParams& m, float3 w_i, float3 w_o) {                        // :240-249
-    const float pSpec = 1.0f / (1.0f + (1 - m.metalness));
-    return lerp1(lambertPdf(w_i, w_o), microfacetPdf(m, w_i, w_o), pSpec);
+    return lerp1(lambertPdf(w_i, w_o), microfacetPdf(m, w_i, w_o), m.pSpec);
 }
 DI float3 pbrEval(const MaterialParams& m, float3 w_i, float3 w_o) {                      // :251-266
     const float3 h = normalize(w_i + w_o);
     const float fD = fresnelDielectric(dot(w_i, h), MS_AIR_IOR, m.ior);
     const float3 fMetallic = schlick3(dot(w_i, h), m.color);
     const float3 F = lerp3(mk3(fD), fMetallic, m.metalness);
-    const float G = ggxG(m.alpha, w_i, w_o);
+    const float G = 1.0f / (1.0f + ggxLambda(m.alpha, w_i) + m.lambdaO);   // ggxG (:44-46) with the cached Λ(w_o)
     const float D = ggxD(m.alpha, h);
     const float3 specular = sameHemisphere(w_o, w_i) ? (F * G * D) / (4.0f * fabsf(cosTheta(w_i)) * fabsf(cosTheta(w_o))) : mk3(0.0f);
-    const float3 diffuse = m.color / MS_PI;
-    return specular + (1.0f - m.metalness) * diffuse;
+    return specular + (1.0f - m.metalness) * m.diffuse;
 }
 DI MatSample pbrSample(const MaterialParams& m, float3 w_o, float2 sq) {                  // :217-238 (+ :207-215)
-    const float pSpec = 1.0f / (1.0f + (1 - m.metalness));
+    const float pSpec = m.pSpec;
     MatSample s;
     if (coinFlipRemap(pSpec, sq.x)) {
         const float3 h = ggxSample(m.alpha, w_o, sq);
@@ -219,7 +268,7 @@ DI float matPdf(const MaterialParams& m, float3 w_i, float3 w_o) {
 }
 DI float3 matEval(const MaterialParams& m, float3 w_i, float3 w_o) {
     if (m.type == MAT_STANDARD_PBR) return pbrEval(m, w_i, w_o);
-    if (m.type == MAT_LAMBERT) return m.color / MS_PI;
+    if (m.type == MAT_LAMBERT) return m.diffuse;
     if (m.type == MAT_PERFECT_MIRROR) return mk3(1.0f / fabsf(cosTheta(w_i)));
     return glassEval(m.ior, w_i, w_o);
 }
@@ -241,6 +290,12 @@ DI MaterialParams loadMaterial(const DeviceScene& sc, const DMaterial& dm, float
         m.color = xyz(sampleTexture(sc, dm.color, uv));
     }
     return m;
+}
+// w_o = the outgoing direction in the shading frame, the same for every pdf/eval/sample call of this hit
+DI void prepareMaterial(MaterialParams& m, float3 w_o) {
+    m.diffuse = m.color / MS_PI;
+    m.pSpec = 1.0f / (1.0f + (1 - m.metalness));
+    m.lambdaO = m.type == MAT_STANDARD_PBR ? ggxLambda(m.alpha, w_o) : 0.0f;
 }
 DI float3 decodeNormal(float2 rg) {                                                       // :489-492
     rg = 2.0f * rg - mk2(1.0f, 1.0f);
