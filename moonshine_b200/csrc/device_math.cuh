@@ -141,10 +141,15 @@ DI float2 squareToEqualAreaSphereInverse(float3 dir) {                          
     uv = uv * mk2(signf(dir.x), signf(dir.y));
     return (uv + mk2(1.0f, 1.0f)) / 2.0f;
 }
+// Same two quotients as the HLSL's branches (rand/p or (rand-p)/(1-p)), selected per lane and divided ONCE: in a warp
+// both branches are always taken by somebody, so the branchy form executes two IEEE divisions per call (20 calls per
+// env-map sample).
 DI bool coinFlipRemap(float p, float& rand) {                                             // :103-111
-    if (rand < p) { rand /= p; return true; }
-    rand = (rand - p) / (1.0f - p);
-    return false;
+    const bool heads = rand < p;
+    const float num = heads ? rand : rand - p;
+    const float den = heads ? p : 1.0f - p;
+    rand = num / den;
+    return heads;
 }
 // float -> uint conversion with defined behaviour for negative / NaN / huge inputs (-> 0 / 0 / max)
 DI uint32_t floatToUint(float f) { return f >= 0.0f ? (f < 4294967040.0f ? (uint32_t)f : 0xFFFFFFFFu) : 0u; }
