@@ -140,4 +140,26 @@ void buildBvh2(const BuildBox* boxes, uint32_t n, uint32_t maxLeaf, BuiltBvh& ou
     }
 }
 
+void reorderTopBfs(BuiltBvh& bvh, uint32_t k) {
+    const uint32_t n = (uint32_t)bvh.nodes.size();
+    if (k == 0 || n <= 1) return;
+    std::vector<uint32_t> newOf(n, 0xFFFFFFFFu), bfs;
+    bfs.reserve(std::min(k, n));
+    bfs.push_back(0); newOf[0] = 0;
+    for (size_t head = 0; head < bfs.size() && bfs.size() < k; head++) {
+        const BvhNode2& nd = bvh.nodes[bfs[head]];
+        for (int s = 0; s < 2 && bfs.size() < k; s++)
+            if (nd.c[2 + s] == 0 && nd.c[s] >= 0) { newOf[(uint32_t)nd.c[s]] = (uint32_t)bfs.size(); bfs.push_back((uint32_t)nd.c[s]); }
+    }
+    uint32_t next = (uint32_t)bfs.size();
+    for (uint32_t i = 0; i < n; i++) if (newOf[i] == 0xFFFFFFFFu) newOf[i] = next++;
+    std::vector<BvhNode2> out(n);
+    for (uint32_t i = 0; i < n; i++) {
+        BvhNode2 nd = bvh.nodes[i];
+        for (int s = 0; s < 2; s++) if (nd.c[2 + s] == 0 && nd.c[s] >= 0) nd.c[s] = (int32_t)newOf[(uint32_t)nd.c[s]];
+        out[newOf[i]] = nd;
+    }
+    bvh.nodes.swap(out);
+}
+
 }  // namespace msne

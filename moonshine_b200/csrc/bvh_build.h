@@ -19,6 +19,10 @@ struct BuiltBvh {
 // `maxLeaf` items per leaf at most. Leaf children reference [first, first+count) in `order`.
 void buildBvh2(const BuildBox* boxes, uint32_t n, uint32_t maxLeaf, BuiltBvh& out);
 
+// Renumbers the nodes so that the first min(k, n) are the top of the tree in breadth-first order (the rest keep their
+// relative order). Pure relabelling: boxes, leaves and `order` are untouched.
+void reorderTopBfs(BuiltBvh& bvh, uint32_t k);
+
 // outward padding that keeps the FP32 slab test conservative w.r.t. the exact triangle test
 inline void padBox(BuildBox& b) {
     float ext = 1e-3f, mag = 0.0f;

@@ -88,9 +88,12 @@ struct DeviceScene {
     uint32_t envSize;
     uint32_t envLevels;
     uint32_t envLevelOffset[12];   // float offset of each mip inside envLum
+    const float4* envQuads;        // the same pyramid, quad-major: for mip L the 2x2 texels under texel (x, y) of mip L+1 as ONE float4
+    uint32_t envQuadOffset[12];    // (l00, l10, l01, l11) at envQuads[envQuadOffset[L] + y * (size >> (L+1)) + x]: one 16-byte load per level of EnvMap::sample
     const float* texLuts;          // 512 floats: [0,256) sRGB -> linear, [256,512) c / 255 (shading.cuh)
     uint32_t staticOnly;           // 1: the TLAS holds nothing but the merged static BLAS -> single-level traversal from staticRoot
     uint32_t staticRoot;
+    uint32_t staticTop;            // MSNE_TRACE_SMEM_NODES experiment: the first `staticTop` nodes from staticRoot are the top of the tree in BFS order
 };
 
 // specialization constants (main.hlsl:34-40) as runtime values

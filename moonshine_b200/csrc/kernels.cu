@@ -22,6 +22,43 @@
 
 namespace msne {
 
+// Queue traffic (path state, hit records, shadow rays, bin lists) is written once and read once, a whole wave (GBs) apart:
+// MSNE_STREAM_HINTS = 1 marks it evict-first (ld/st.global.cs) so that it does not displace the scene data in L2.
+#ifndef MSNE_STREAM_HINTS
+#define MSNE_STREAM_HINTS 1
+#endif
+// MSNE_SHADE_PREFETCH = 1 (L2) / 2 (L1): k_shade prefetches the path state of its NEXT grid-stride item while it shades the
+// current one (the slot index is fetched two items ahead so that the prefetch never waits for it).
+#ifndef MSNE_SHADE_PREFETCH
+#define MSNE_SHADE_PREFETCH 0
+#endif
+// (2 = loads only, 3 = stores only: measurement variants)
+#if MSNE_STREAM_HINTS == 1 || MSNE_STREAM_HINTS == 2
+DI float4 qld(const float4* p) { return __ldcs(p); }
+DI uint4 qld(const uint4* p) { return __ldcs(p); }
+DI uint32_t qld(const uint32_t* p) { return __ldcs(p); }
+#else
+DI float4 qld(const float4* p) { return *p; }
+DI uint4 qld(const uint4* p) { return *p; }
+DI uint32_t qld(const uint32_t* p) { return __ldg(p); }
+#endif
+#if MSNE_STREAM_HINTS == 1 || MSNE_STREAM_HINTS == 3
+DI void qst(float4* p, float4 v) { __stcs(p, v); }
+DI void qst(uint4* p, uint4 v) { __stcs(p, v); }
+DI void qst(uint32_t* p, uint32_t v) { __stcs(p, v); }
+#else
+DI void qst(float4* p, float4 v) { *p = v; }
+DI void qst(uint4* p, uint4 v) { *p = v; }
+DI void qst(uint32_t* p, uint32_t v) { *p = v; }
+#endif
+DI void prefetchQueue(const void* p) {
+#if MSNE_SHADE_PREFETCH == 2
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
+
 // ------------------------------------------------------------------------------------------------
 // generate
 // ------------------------------------------------------------------------------------------------
@@ -110,6 +147,30 @@ __global__ void __launch_bounds__(TRACE_THREADS, TWO_LEVEL ? TRACE_BLOCKS_PER_SM
     const uint32_t nLive = cin.nLive, total = cin.nLive + cin.nShadow;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t ltMask = (1u << lane) - 1u;
+    const BvhNode2* smemTop = nullptr;
+#if MSNE_TRACE_SMEM_NODES > 0
+    // TMA staging of the top of the tree: one bulk copy (cp.async.bulk, the 1-D TMA path) per block, completion through an
+    // mbarrier transaction count; every thread then waits on phase 0 of the barrier.
+    extern __shared__ __align__(128) unsigned char smemRaw[];
+    if (!TWO_LEVEL && sc.staticTop > 0) {
+        const uint32_t bytes = sc.staticTop * (uint32_t)sizeof(BvhNode2);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smemRaw);
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(smemRaw + MSNE_TRACE_SMEM_NODES * sizeof(BvhNode2));
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(sc.blasNodes + sc.staticRoot), "r"(bytes), "r"(bar) : "memory");
+        }
+        __syncthreads();
+        uint32_t ok = 0;
+        while (!ok) {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(bar) : "memory");
+        }
+        smemTop = reinterpret_cast<const BvhNode2*>(smemRaw);
+    }
+#endif
     for (;;) {
         uint32_t base = 0;
         if (lane == 0) base = atomicAdd(ws.traceTicket, 32u);
@@ -118,15 +179,15 @@ __global__ void __launch_bounds__(TRACE_THREADS, TWO_LEVEL ? TRACE_BLOCKS_PER_SM
         const uint32_t idx = base + lane;
         uint32_t bin = 0xFFu;
         if (idx < nLive) {
-            const float4 r0 = pb.R0[buf][idx], r1 = pb.R1[buf][idx];
+            const float4 r0 = qld(pb.R0[buf] + idx), r1 = qld(pb.R1[buf] + idx);
             HitRec h;
-            traceRay<false, TWO_LEVEL>(sc, mk3(r0.x, r0.y, r0.z), mk3(r1.x, r1.y, r1.z), 0.0f, MS_INFINITY, h);
-            pb.H[idx] = make_uint4(h.inst, h.tri, __float_as_uint(h.u), __float_as_uint(h.v));
+            traceRay<false, TWO_LEVEL>(sc, mk3(r0.x, r0.y, r0.z), mk3(r1.x, r1.y, r1.z), 0.0f, MS_INFINITY, h, smemTop);
+            qst(pb.H + idx, make_uint4(h.inst, h.tri, __float_as_uint(h.u), __float_as_uint(h.v)));
             bin = hitBin(sc, h);
         } else if (idx < total) {
-            const float4 q0 = pb.Q0[idx - nLive], q1 = pb.Q1[idx - nLive];
+            const float4 q0 = qld(pb.Q0 + (idx - nLive)), q1 = qld(pb.Q1 + (idx - nLive));
             HitRec h;
-            if (traceRay<true, TWO_LEVEL>(sc, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), 0.0f, q0.w, h)) {
+            if (traceRay<true, TWO_LEVEL>(sc, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), 0.0f, q0.w, h, smemTop)) {
                 const uint32_t target = __float_as_uint(q1.w);
                 float4* n = (target & 1u) ? pb.N1[buf] : pb.N0[buf];
                 n[target >> 1] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -139,7 +200,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TWO_LEVEL ? TRACE_BLOCKS_PER_SM
             uint32_t slot = 0;
             if ((int)lane == leader) slot = atomicAdd(ws.typeCount + bin, (uint32_t)__popc(peers));
             slot = __shfl_sync(peers, slot, leader) + __popc(peers & ltMask);
-            pb.typeList[(size_t)bin * pb.capacity + slot] = idx;
+            qst(pb.typeList + ((size_t)bin * pb.capacity + slot), idx);
         }
     }
     // last block out: re-arm the ticket for the next launch and publish ray counts
@@ -204,8 +265,8 @@ struct ShadeOut {
 // MT: -1 = any (runtime dispatch), 0..3 = MaterialType known at compile time, 4 = miss / dead paths only
 template <int MT>
 DI void shadeOne(const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, uint32_t buf, uint32_t q, ShadeOut& out, uint32_t& bounceOut) {
-    const float4 R0 = pb.R0[buf][q], R1 = pb.R1[buf][q], S0 = pb.S0[buf][q], S1 = pb.S1[buf][q];
-    const float4 N0 = pb.N0[buf][q], N1 = pb.N1[buf][q];
+    const float4 R0 = qld(pb.R0[buf] + q), R1 = qld(pb.R1[buf] + q), S0 = qld(pb.S0[buf] + q), S1 = qld(pb.S1[buf] + q);
+    const float4 N0 = qld(pb.N0[buf] + q), N1 = qld(pb.N1[buf] + q);
     const uint32_t flags = __float_as_uint(R1.w);
     const uint32_t bounceCount = flags & BOUNCE_MASK;
     const uint32_t slot = __float_as_uint(S1.w);
@@ -227,7 +288,7 @@ DI void shadeOne(const DeviceScene& sc, const DConstants& k, const PathBuffers& 
     float3 throughput = mk3(S0.x, S0.y, S0.z);
     Rng rng; rng.state = __float_as_uint(S0.w);
 
-    const uint4 H = pb.H[q];
+    const uint4 H = qld(pb.H + q);
     if ((MT < 0 || MT == (int)BIN_MISS) && H.x == MISS_ID) {
         // integrator.hlsl:169-180
         if (k.env_samples == 0 || bounceCount == 0 || isLastMaterialDelta) {
@@ -253,7 +314,7 @@ DI void shadeOne(const DeviceScene& sc, const DConstants& k, const PathBuffers& 
     const uint32_t instanceID = __ldg(&sc.instances[instanceIndex].customIndex);
     const DGeometry geometry = sc.geometries[instanceID + geometryIndex];
     const bool geomSampled = (geometry.sampled & 0xFFu) != 0;   // only the low byte is defined (Accel.zig:40-44)
-    const MeshAttributes attrs = lookupAttributes(sc, k, instanceIndex, geometry.mesh, primitiveIndex, bary);
+    const MeshAttributes attrs = lookupAttributes(sc, k, instanceIndex, geometry.mesh, primitiveIndex, bary, tr);
     const DMaterial dm = sc.materials[geometry.material];
     const Frame textureFrame = getTextureFrame(sc, k, dm, attrs.texcoord, attrs.frame);
     const float3 emissiveLight = xyz(sampleTexture(sc, dm.emissive, attrs.texcoord));
@@ -396,12 +457,31 @@ __global__ void __launch_bounds__(SHADE_THREADS, MIN_BLOCKS) k_shade(DeviceScene
     uint32_t localMaxBounce = 0;
     const uint32_t stride = gridDim.x * blockDim.x;
     // every lane of a warp runs the same number of iterations so the ballots below are convergent
+    // queue slot of grid-stride item i: list entry, or the dead range filled from the top of the buffer
+    auto slotOf = [&](uint32_t i) -> uint32_t { return i < nList ? (BIN < 0 ? i : qld(list + i)) : (P - 1u - (i - nList)); };
+#if MSNE_SHADE_PREFETCH
+    const uint32_t first = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t qCur = first < total ? slotOf(first) : 0u;                      // this item
+    uint32_t qNext = first + stride < total ? slotOf(first + stride) : 0u;   // next item: its path state is prefetched below
+#endif
     for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < total; base += stride) {
         const uint32_t i = base + lane;
         ShadeOut out;
         out.kind = 0; out.envRay = false; out.meshRay = false;
+#if MSNE_SHADE_PREFETCH
+        const uint32_t q = qCur;
+        qCur = qNext;
+        if (i + stride < total) {
+            prefetchQueue(pb.R0[buf] + qNext); prefetchQueue(pb.R1[buf] + qNext); prefetchQueue(pb.S0[buf] + qNext); prefetchQueue(pb.S1[buf] + qNext);
+            prefetchQueue(pb.N0[buf] + qNext); prefetchQueue(pb.N1[buf] + qNext); prefetchQueue(pb.H + qNext);
+        }
+        // issued now, consumed by the prefetch of the next iteration
+        qNext = i + 2u * stride < total ? slotOf(i + 2u * stride) : 0u;   // total <= 2 P < 2^31: no wrap
+#endif
         if (i < total) {
-            const uint32_t q = i < nList ? (BIN < 0 ? i : __ldg(list + i)) : (P - 1u - (i - nList));
+#if !MSNE_SHADE_PREFETCH
+            const uint32_t q = slotOf(i);
+#endif
             uint32_t b;
             shadeOne<BIN>(sc, k, pb, buf, q, out, b);
             localMaxBounce = max(localMaxBounce, b);
@@ -422,17 +502,17 @@ __global__ void __launch_bounds__(SHADE_THREADS, MIN_BLOCKS) k_shade(DeviceScene
         shadowBase = __shfl_sync(0xFFFFFFFFu, shadowBase, 0);
         if (out.kind != 0) {
             const uint32_t oq = out.kind == 1 ? liveBase + __popc(liveMask & ltMask) : P - 1u - (deadBase + __popc(deadMask & ltMask));
-            pb.R0[ob][oq] = out.R0; pb.R1[ob][oq] = out.R1; pb.S0[ob][oq] = out.S0; pb.S1[ob][oq] = out.S1;
-            pb.N0[ob][oq] = out.N0; pb.N1[ob][oq] = out.N1;
+            qst(pb.R0[ob] + oq, out.R0); qst(pb.R1[ob] + oq, out.R1); qst(pb.S0[ob] + oq, out.S0); qst(pb.S1[ob] + oq, out.S1);
+            qst(pb.N0[ob] + oq, out.N0); qst(pb.N1[ob] + oq, out.N1);
             if (out.envRay) {
                 const uint32_t si = shadowBase + __popc(envMask & ltMask);
                 out.envQ1.w = __uint_as_float(oq * 2u + 0u);
-                pb.Q0[si] = out.envQ0; pb.Q1[si] = out.envQ1;
+                qst(pb.Q0 + si, out.envQ0); qst(pb.Q1 + si, out.envQ1);
             }
             if (out.meshRay) {
                 const uint32_t si = shadowBase + __popc(envMask) + __popc(meshMask & ltMask);
                 out.meshQ1.w = __uint_as_float(oq * 2u + 1u);
-                pb.Q0[si] = out.meshQ0; pb.Q1[si] = out.meshQ1;
+                qst(pb.Q0 + si, out.meshQ0); qst(pb.Q1 + si, out.meshQ1);
             }
         }
     }
@@ -578,12 +658,16 @@ __global__ void k_env_resample(const float4* __restrict__ src, uint32_t W, uint3
     dstRgb[(size_t)y * S + x] = make_float4(c.x, c.y, c.z, 1.0f);
     dstLum[(size_t)y * S + x] = luminance(c);
 }
-__global__ void k_env_fold(const float* __restrict__ srcMip, float* dstMip, uint32_t dstSize) {
+// fold.hlsl: one mip of the SUM pyramid; also emits the four source texels as one float4 (quad-major copy of the source mip
+// that EnvMap::sample walks with a single 16-byte load per level, shading.cuh envSample)
+__global__ void k_env_fold(const float* __restrict__ srcMip, float* dstMip, float4* srcQuads, uint32_t dstSize) {
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= dstSize || y >= dstSize) return;
     const uint32_t ps = dstSize * 2;
-    dstMip[(size_t)y * dstSize + x] = srcMip[(size_t)(2 * y) * ps + 2 * x] + srcMip[(size_t)(2 * y) * ps + 2 * x + 1] +
-                                      srcMip[(size_t)(2 * y + 1) * ps + 2 * x] + srcMip[(size_t)(2 * y + 1) * ps + 2 * x + 1];
+    const float l00 = srcMip[(size_t)(2 * y) * ps + 2 * x], l10 = srcMip[(size_t)(2 * y) * ps + 2 * x + 1];
+    const float l01 = srcMip[(size_t)(2 * y + 1) * ps + 2 * x], l11 = srcMip[(size_t)(2 * y + 1) * ps + 2 * x + 1];
+    dstMip[(size_t)y * dstSize + x] = l00 + l10 + l01 + l11;
+    srcQuads[(size_t)y * dstSize + x] = make_float4(l00, l10, l01, l11);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -596,7 +680,14 @@ void launchGenerate(cudaStream_t st, const DCamera& cam, const DConstants& k, co
     k_generate<<<grid1((uint64_t)nPix * nSamples, 256), 256, 0, st>>>(cam, k, pb, counters, pixIds, nPix, nSamples, firstSample);
 }
 void launchTrace(cudaStream_t st, int blocks, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf) {
+#if MSNE_TRACE_SMEM_NODES > 0
+    static const size_t smemBytes = MSNE_TRACE_SMEM_NODES * sizeof(BvhNode2) + 16;
+    static const cudaError_t attr = cudaFuncSetAttribute(k_trace<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
+    (void)attr;
+    if (sc.staticOnly) k_trace<false><<<blocks, TRACE_THREADS, smemBytes, st>>>(sc, pb, ws, buf);
+#else
     if (sc.staticOnly) k_trace<false><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf);
+#endif
     else k_trace<true><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf);
 }
 // Register caps (measured, profiles/r01_sweeps.md): the all-material kernel runs best at 80 registers
@@ -626,9 +717,9 @@ void launchEnvResample(cudaStream_t st, const float4* src, uint32_t W, uint32_t 
     dim3 b(8, 8), g((S + 7) / 8, (S + 7) / 8);
     k_env_resample<<<g, b, 0, st>>>(src, W, H, dstRgb, dstLum, S);
 }
-void launchEnvFold(cudaStream_t st, const float* srcMip, float* dstMip, uint32_t dstSize) {
+void launchEnvFold(cudaStream_t st, const float* srcMip, float* dstMip, float4* srcQuads, uint32_t dstSize) {
     dim3 b(8, 8), g((dstSize + 7) / 8, (dstSize + 7) / 8);
-    k_env_fold<<<g, b, 0, st>>>(srcMip, dstMip, dstSize);
+    k_env_fold<<<g, b, 0, st>>>(srcMip, dstMip, srcQuads, dstSize);
 }
 void launchTraceProbe(cudaStream_t st, const DeviceScene& sc, const float* rays8, uint32_t n, int anyHit, uint32_t* hits5) {
     k_trace_probe<<<grid1(n, 128), 128, 0, st>>>(sc, rays8, n, anyHit, hits5);
@@ -643,7 +734,12 @@ int traceOccupancyBlocksPerSm() {
     int n = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<true>, TRACE_THREADS, 0);
     int n1 = 0;
+#if MSNE_TRACE_SMEM_NODES > 0
+    cudaFuncSetAttribute(k_trace<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MSNE_TRACE_SMEM_NODES * sizeof(BvhNode2) + 16));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, k_trace<false>, TRACE_THREADS, MSNE_TRACE_SMEM_NODES * sizeof(BvhNode2) + 16);
+#else
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, k_trace<false>, TRACE_THREADS, 0);
+#endif
     n = n > n1 ? n : n1;
     return n;
 }

@@ -14,6 +14,12 @@ namespace msne {
 #ifndef TRACE1_BLOCKS_PER_SM
 #define TRACE1_BLOCKS_PER_SM 9  // single-level specialisation (no transformed instances): 56 registers, measured best of 8/9/10
 #endif
+// Experiment (profiles/r01_sweeps.md "TMA-staged top of the tree"): k_trace<false> copies the first N nodes of the static BLAS
+// (BFS order, bvh_build.cpp reorderTopBfs) into shared memory with one cp.async.bulk per block and walks them from there.
+// 0 = off (default: the top of the tree is L1-resident anyway and shared memory is carved out of the same SRAM).
+#ifndef MSNE_TRACE_SMEM_NODES
+#define MSNE_TRACE_SMEM_NODES 0
+#endif
 #ifndef SHADE_THREADS
 #define SHADE_THREADS 128
 #endif
@@ -27,7 +33,7 @@ void launchTail(cudaStream_t st, int blocks, const DeviceScene& sc, const DConst
 void launchAccumulate(cudaStream_t st, const float4* result, float4* image, float4* runState, const uint32_t* pixIds, uint32_t nPix, uint32_t nSamples,
                       uint32_t firstSample, uint32_t spr);
 void launchEnvResample(cudaStream_t st, const float4* src, uint32_t W, uint32_t H, float4* dstRgb, float* dstLum, uint32_t S);
-void launchEnvFold(cudaStream_t st, const float* srcMip, float* dstMip, uint32_t dstSize);
+void launchEnvFold(cudaStream_t st, const float* srcMip, float* dstMip, float4* srcQuads, uint32_t dstSize);
 void launchTraceProbe(cudaStream_t st, const DeviceScene& sc, const float* rays8, uint32_t n, int anyHit, uint32_t* hits5);
 void launchPick(cudaStream_t st, const DeviceScene& sc, const DCamera& cam, float x, float y, MsneClick* out);
 void launchPrimaryProbe(cudaStream_t st, const DCamera& cam, const DConstants& k, uint32_t sample, float* rays6, uint32_t* rngState);

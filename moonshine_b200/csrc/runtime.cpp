@@ -205,7 +205,8 @@ struct HdMoonshine {
     DevBuf<float> dSrgbLut;
     DevBuf<float4> dEnvRgb;
     DevBuf<float> dEnvLum;
-    uint32_t envSize = 0, envLevels = 0, envLevelOffset[12] = {0};
+    DevBuf<float4> dEnvQuads;
+    uint32_t envSize = 0, envLevels = 0, envLevelOffset[12] = {0}, envQuadOffset[12] = {0};
     bool hasTlas = false, tlasStaticOnly = false;
 
     MsneSpecConstants consts{};   // hydra defaults (hydra.zig:97-105)
@@ -299,10 +300,13 @@ struct HdMoonshine {
         for (uint32_t s = S; s >= 1; s >>= 1) { envLevelOffset[envLevels++] = (uint32_t)total; total += (size_t)s * s; if (s == 1) break; }
         dEnvRgb.ensure((size_t)S * S);
         dEnvLum.ensure(total);
+        size_t quads = 0;
+        for (uint32_t l = 1; l < envLevels; l++) { envQuadOffset[l - 1] = (uint32_t)quads; quads += (size_t)(S >> l) * (S >> l); }
+        dEnvQuads.ensure(std::max<size_t>(quads, 1));
         launchEnvResample(stream, src.p, W, H, dEnvRgb.p, dEnvLum.p, S);
         stats.kernel_launches++;
         for (uint32_t l = 1; l < envLevels; l++) {
-            launchEnvFold(stream, dEnvLum.p + envLevelOffset[l - 1], dEnvLum.p + envLevelOffset[l], S >> l);
+            launchEnvFold(stream, dEnvLum.p + envLevelOffset[l - 1], dEnvLum.p + envLevelOffset[l], dEnvQuads.p + envQuadOffset[l - 1], S >> l);
             stats.kernel_launches++;
         }
         CK(cudaStreamSynchronize(stream));   // src is freed on return
@@ -362,6 +366,7 @@ struct HdMoonshine {
     // (1) BLAS level: merged static BLAS over every visible identity-transform instance + one shared BLAS per mesh-key
     //     of the transformed instances. Only needed when that set changes (Accel.zig:94-184 equivalent).
     DInstance staticRec{};
+    uint32_t staticTop = 0;
     bool haveStatic = false;
     BuildBox staticBounds{};
     uint64_t stats_static_builds = 0, stats_tlas_builds = 0, stats_tlas_refits = 0;
@@ -383,6 +388,11 @@ struct HdMoonshine {
         if (haveStatic) {
             BuiltBvh bvh;
             buildBvh2(stBoxes.data(), (uint32_t)stBoxes.size(), maxLeaf, bvh);
+            staticTop = 0;
+#if MSNE_TRACE_SMEM_NODES > 0
+            reorderTopBfs(bvh, MSNE_TRACE_SMEM_NODES);
+            staticTop = (uint32_t)std::min<size_t>(MSNE_TRACE_SMEM_NODES, bvh.nodes.size());
+#endif
             staticRec.blasRoot = appendBlas(bvh, stTris);
             staticBounds = bvh.bounds;
         }
@@ -565,9 +575,11 @@ struct HdMoonshine {
         sc.meshes = dMeshes.p; sc.materials = dMaterials.p; sc.textures = dTextures.p;
         sc.alias = dAlias.p; sc.aliasEntries = (uint32_t)alias.size();
         sc.envRgb = reinterpret_cast<const float*>(dEnvRgb.p); sc.envLum = dEnvLum.p; sc.envSize = envSize; sc.envLevels = envLevels;
-        for (int i = 0; i < 12; i++) sc.envLevelOffset[i] = envLevelOffset[i];
+        for (int i = 0; i < 12; i++) { sc.envLevelOffset[i] = envLevelOffset[i]; sc.envQuadOffset[i] = envQuadOffset[i]; }
+        sc.envQuads = dEnvQuads.p;
         sc.texLuts = dSrgbLut.p;
         sc.staticOnly = (tlasStaticOnly && !forceTwoLevel) ? 1u : 0u; sc.staticRoot = staticRec.blasRoot;
+        sc.staticTop = haveStatic ? staticTop : 0u;
         return sc;
     }
     DConstants deviceConstants() const {

@@ -10,6 +10,13 @@
 #include <cuda_fp16.h>
 #include "device_math.cuh"
 
+#ifndef MSNE_POS_FROM_TRIREC
+#define MSNE_POS_FROM_TRIREC 1
+#endif
+#ifndef MSNE_ENV_QUADS
+#define MSNE_ENV_QUADS 1   // EnvMap::sample reads the quad-major pyramid (one LDG.128 per level instead of four scalar loads)
+#endif
+
 namespace msne {
 
 // ---- textures ------------------------------------------------------------------------------------
@@ -331,12 +338,23 @@ DI void getTangentBitangent(float3 p0, float3 p1, float3 p2, float2 t0, float2 t
 }
 
 // MeshAttributes::lookupAndInterpolate(...).inWorld(...)  (world.hlsl:114-176)
-DI MeshAttributes lookupAttributes(const DeviceScene& sc, const DConstants& k, uint32_t instanceIndex, uint32_t meshIdx, uint32_t primitiveIndex, float2 attribs) {
+// `tri`: the pooled triangle record of a traced hit (nullptr for light samples). Its vertices are the mesh's object-space
+// positions copied verbatim (runtime.cpp meshTriangles), so the hit path takes them from the 48-byte record the trace
+// kernel just touched instead of chasing index -> position (same bits, one dependent hop and nine scalar loads less).
+DI MeshAttributes lookupAttributes(const DeviceScene& sc, const DConstants& k, uint32_t instanceIndex, uint32_t meshIdx, uint32_t primitiveIndex, float2 attribs,
+                                   const TriRec* tri = nullptr) {
     const DMesh mesh = sc.meshes[meshIdx];
     const float3 bary = mk3(1.0f - attribs.x - attribs.y, attribs.x, attribs.y);
     MeshAttributes a;
     const uint32_t ix = __ldg(mesh.idx + 3 * (size_t)primitiveIndex), iy = __ldg(mesh.idx + 3 * (size_t)primitiveIndex + 1), iz = __ldg(mesh.idx + 3 * (size_t)primitiveIndex + 2);
-    const float3 p0 = ld3(mesh.pos, ix), p1 = ld3(mesh.pos, iy), p2 = ld3(mesh.pos, iz);
+    float3 p0, p1, p2;
+    if (MSNE_POS_FROM_TRIREC && tri != nullptr) {
+        const float4* tp = reinterpret_cast<const float4*>(tri);
+        const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+        p0 = mk3(t0.x, t0.y, t0.z); p1 = mk3(t1.x, t1.y, t1.z); p2 = mk3(t2.x, t2.y, t2.z);
+    } else {
+        p0 = ld3(mesh.pos, ix); p1 = ld3(mesh.pos, iy); p2 = ld3(mesh.pos, iz);
+    }
     a.position = interp3(bary, p0, p1, p2);
     // :130 — `cond ? uint3 : float3` promotes both arms to float3 before converting back to uint3
     uint32_t ax, ay, az;
@@ -404,10 +422,16 @@ DI LightSample envSample(const DeviceScene& sc, float2 rand) {
     uint32_t ix = 0, iy = 0;
     for (uint32_t level = mipCount - 1; level-- > 0;) {
         ix *= 2; iy *= 2;
+#if MSNE_ENV_QUADS
+        // quad-major copy of the mip (k_env_fold): the four texels under the parent texel are one 16-byte load
+        const float4 qd = __ldg(sc.envQuads + sc.envQuadOffset[level] + (iy >> 1) * (size >> (level + 1)) + (ix >> 1));
+        const float l00 = qd.x, l10 = qd.y, l01 = qd.z, l11 = qd.w;
+#else
         const uint32_t sz = size >> level;
         const float* mip = sc.envLum + sc.envLevelOffset[level];
         const float l00 = __ldg(mip + (size_t)iy * sz + ix), l10 = __ldg(mip + (size_t)iy * sz + ix + 1);
         const float l01 = __ldg(mip + (size_t)(iy + 1) * sz + ix), l11 = __ldg(mip + (size_t)(iy + 1) * sz + ix + 1);
+#endif
         const float px0 = l00 + l01;
         const float px1 = l10 + l11;
         const bool right = coinFlipRemap(px1 / (px0 + px1), rand.x);

@@ -22,6 +22,7 @@
 // keep the world-space ray, and the stack-overflow test (bvh_build.cpp bounds the depth) go away.
 #pragma once
 #include "device_math.cuh"
+#include "kernels.h"
 
 namespace msne {
 
@@ -70,8 +71,10 @@ DI bool triTest(const float4 t0, const float4 t1, const float4 t2, const SpaceRa
     return tmin < t && t < tmax;
 }
 
+// `smemTop` (MSNE_TRACE_SMEM_NODES experiment, single-level only): generic pointer to a shared-memory copy of the first
+// sc.staticTop nodes from sc.staticRoot, or nullptr.
 template <bool ANY_HIT, bool TWO_LEVEL>
-DI bool traceRay(const DeviceScene& sc, const float3 o, const float3 d, const float tmin, const float tmax, HitRec& hit) {
+DI bool traceRay(const DeviceScene& sc, const float3 o, const float3 d, const float tmin, const float tmax, HitRec& hit, const BvhNode2* smemTop = nullptr) {
     hit.inst = MISS_ID; hit.tri = 0; hit.u = 0.0f; hit.v = 0.0f;
     if (sc.tlasNodes == nullptr) return false;
     float bestT = tmax;
@@ -85,9 +88,22 @@ DI bool traceRay(const DeviceScene& sc, const float3 o, const float3 d, const fl
     while (node != REF_END) {
         // ---- inner nodes: descend until a leaf (or a TLAS item / sentinel) comes up ------------------------------
         while ((uint32_t)node < (uint32_t)REF_ITEM) {
+#if MSNE_TRACE_SMEM_NODES > 0
+            float4 n0, n1, n2; int2 c;
+            if (!TWO_LEVEL) {
+                // one generic load path: the pointer selects the shared-memory copy for the top of the tree
+                const uint32_t rel = (uint32_t)node - sc.staticRoot;
+                const float4* np = reinterpret_cast<const float4*>(rel < sc.staticTop ? smemTop + rel : nodes + node);
+                n0 = np[0]; n1 = np[1]; n2 = np[2]; c = *reinterpret_cast<const int2*>(np + 3);
+            } else {
+                const float4* np = reinterpret_cast<const float4*>(nodes + node);
+                n0 = __ldg(np); n1 = __ldg(np + 1); n2 = __ldg(np + 2); c = __ldg(reinterpret_cast<const int2*>(np + 3));
+            }
+#else
             const float4* np = reinterpret_cast<const float4*>(nodes + node);
             const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
             const int2 c = __ldg(reinterpret_cast<const int2*>(np + 3));
+#endif
             float tn0, tn1;
             const bool h0 = slab(ray, n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, tmin, bestT, tn0);   // an empty child's box is unreachable (dtypes.h)
             const bool h1 = slab(ray, n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, tmin, bestT, tn1);
