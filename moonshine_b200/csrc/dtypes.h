@@ -82,6 +82,8 @@ struct DeviceScene {
     const DTexture* textures;
     const DAlias* alias;           // [0] = header {alias = count, select = sum of areas}
     uint32_t aliasEntries;         // 0 when no table was built
+    const float4* emitterTris;     // per alias entry i (alias[1 + i]) 64 B: (p0, uv0.x) (p1, uv0.y) (p2, uv1.x) (uv1.y, uv2.x, uv2.y, -): the object-space
+                                   // vertices + texcoords MeshLights::sample would fetch through instance -> geometry -> mesh -> index
     // environment (BackgroundManager.zig:154-163)
     const float* envRgb;           // S*S float4
     const float* envLum;           // mip 0 .. log2(S), tightly packed, SUM pyramid

@@ -391,7 +391,12 @@ DI void shadeOne(const DeviceScene& sc, const DConstants& k, const PathBuffers& 
                     const uint32_t lInstanceID = __ldg(&sc.instances[e.inst].customIndex);
                     const DGeometry lg = sc.geometries[lInstanceID + e.geom];
                     const float2 lbary = squareToTriangle(rand);
+#if MSNE_EMITTER_RECORDS
+                    const LightPoint lp = emitterPoint(sc, idx, e.inst, lbary);
+                    struct { float3 position; float2 texcoord; struct { float3 n; } triangleFrame; } la = {lp.position, lp.texcoord, {lp.n}};
+#else
                     const MeshAttributes la = lookupAttributes(sc, k, e.inst, lg.mesh, e.prim, lbary);
+#endif
                     const float3 radiance = xyz(sampleTexture(sc, sc.materials[lg.material].emissive, la.texcoord));
                     const float3 dirWs = normalize(la.position - attrs.position);
                     const float pdf = areaMeasureToSolidAngleMeasure(la.position, attrs.position, dirWs, la.triangleFrame.n) / sum;

@@ -560,8 +560,9 @@ struct HdMoonshine {
             tlasDirty = false; tlasRefitOk = false;
         }
         if (emitterFollowsEdits && emitterStale) { buildEmitterTable(); emitterStale = false; }
-        if (aliasDirty) {
+        if (aliasDirty || emitterRecIndexed != (consts.indexed_attributes != 0)) {
             dAlias.upload(alias.data(), alias.size(), stream);
+            uploadEmitterRecords();
             CK(cudaStreamSynchronize(stream));
             aliasDirty = false;
         }
@@ -573,7 +574,7 @@ struct HdMoonshine {
         sc.tlasItems = dTlasItems.p;
         sc.blasNodes = dBlasNodes.p; sc.tris = dTris.p; sc.instances = dInstances.p; sc.geometries = dGeometries.p;
         sc.meshes = dMeshes.p; sc.materials = dMaterials.p; sc.textures = dTextures.p;
-        sc.alias = dAlias.p; sc.aliasEntries = (uint32_t)alias.size();
+        sc.alias = dAlias.p; sc.aliasEntries = (uint32_t)alias.size(); sc.emitterTris = dEmitterTris.p;
         sc.envRgb = reinterpret_cast<const float*>(dEnvRgb.p); sc.envLum = dEnvLum.p; sc.envSize = envSize; sc.envLevels = envLevels;
         for (int i = 0; i < 12; i++) { sc.envLevelOffset[i] = envLevelOffset[i]; sc.envQuadOffset[i] = envQuadOffset[i]; }
         sc.envQuads = dEnvQuads.p;
@@ -618,6 +619,35 @@ struct HdMoonshine {
         alias.push_back(DAlias{(uint32_t)entries.size(), sum, 0, 0, 0});
         alias.insert(alias.end(), entries.begin(), entries.end());
         aliasDirty = true;
+    }
+
+    // Per alias entry: the triangle's object-space vertices and texcoords exactly as MeshAttributes::lookupAndInterpolate
+    // (world.hlsl:114-136) would fetch them for (instance, geometry, primitive) - including the float round trip of the
+    // attribute indices (:130) and the default texcoords of a mesh without uvs - packed into 64 B (dtypes.h emitterTris).
+    DevBuf<float4> dEmitterTris;
+    bool emitterRecIndexed = false;
+    void uploadEmitterRecords() {
+        emitterRecIndexed = consts.indexed_attributes != 0;
+        const size_t n = alias.empty() ? 0 : alias.size() - 1;
+        std::vector<float4> rec(4 * std::max<size_t>(n, 1), float4{0, 0, 0, 0});
+        for (size_t e = 0; e < n; e++) {
+            const DAlias& a = alias[1 + e];
+            const HostInstance& in = instances[a.inst];
+            const HostMesh& m = *meshes[geometries[in.customIndex + a.geom].mesh];
+            float p[3][3] = {{0}}, t[3][2] = {{0, 0}, {1, 0}, {1, 1}};
+            for (int v = 0; v < 3; v++) {
+                const uint32_t vi = m.idx[3 * (size_t)a.prim + v];
+                memcpy(p[v], &m.pos[3 * (size_t)vi], 12);
+                const uint32_t ai = emitterRecIndexed ? (uint32_t)(float)vi : (uint32_t)(float)(a.prim * 3u + (uint32_t)v);
+                if (!m.uv.empty()) { t[v][0] = t[v][1] = 0.0f; if (2 * (size_t)ai + 1 < m.uv.size()) { t[v][0] = m.uv[2 * (size_t)ai]; t[v][1] = m.uv[2 * (size_t)ai + 1]; } }
+            }
+            rec[4 * e + 0] = float4{p[0][0], p[0][1], p[0][2], t[0][0]};
+            rec[4 * e + 1] = float4{p[1][0], p[1][1], p[1][2], t[0][1]};
+            rec[4 * e + 2] = float4{p[2][0], p[2][1], p[2][2], t[1][0]};
+            rec[4 * e + 3] = float4{t[1][1], t[2][0], t[2][1], 0.0f};
+        }
+        dEmitterTris.upload(rec.data(), rec.size(), stream);
+        CK(cudaStreamSynchronize(stream));   // rec dies here
     }
 
     // ---- camera (camera.hlsl:14-30 hoisted) ----------------------------------------------------
