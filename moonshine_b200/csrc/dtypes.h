@@ -121,7 +121,7 @@ struct MsneClick { int32_t instance_index; uint32_t geometry_index, primitive_in
 //   S0 = (throughput.xyz, rng state bits)   S1 = (accumulated.xyz, result-slot bits)
 //   N0 = pending env-NEE contribution       N1 = pending mesh-NEE contribution (zeroed by the trace
 //        kernel when the shadow ray is occluded; folded into `accumulated` by the next shade pass)
-//   H  = hit record written by the trace kernel: (instanceIndex, triangle index, u bits, v bits)
+//   H  = hit record written by the trace kernel: (instanceIndex, triangle index | bin << 29, u bits, v bits)
 // Shadow queue: Q0 = (origin.xyz, tmax)  Q1 = (dir.xyz, bits: target q*2 + light)
 struct Counters { uint32_t nLive, nDead, nShadow, pad; };
 
@@ -151,6 +151,8 @@ static const uint32_t FLAG_DEAD = 0x80000000u;
 static const uint32_t FLAG_DELTA = 0x40000000u;
 static const uint32_t BOUNCE_MASK = 0x3FFFFFFFu;
 static const uint32_t MISS_ID = 0xFFFFFFFFu;
+// H.y = pooled triangle index (< 2^29) | material bin << 29 (written by k_trace, read back by k_bin; shading masks it off)
+static const uint32_t H_BIN_SHIFT = 29, H_TRI_MASK = (1u << 29) - 1u;
 static const uint32_t STATIC_INST = 0xFFFFFFFEu;
 
 enum TexFormat : uint32_t { TEX_R32F = 0, TEX_RG32F, TEX_RGBA32F, TEX_R8_UNORM, TEX_RG8_UNORM, TEX_RGBA8_SRGB, TEX_RGBA16F };

@@ -17,6 +17,7 @@
 // order. Compiled with -fmad=false (see device_math.cuh).
 #include "kernels.h"
 #include <cstdlib>
+#include <cub/device/device_radix_sort.cuh>
 #include "shading.cuh"
 #include "traverse.cuh"
 
@@ -29,6 +30,9 @@ namespace msne {
 #endif
 // MSNE_SHADE_PREFETCH = 1 (L2) / 2 (L1): k_shade prefetches the path state of its NEXT grid-stride item while it shades the
 // current one (the slot index is fetched two items ahead so that the prefetch never waits for it).
+#ifndef MSNE_SORT_KEY
+#define MSNE_SORT_KEY 0   // 0: octant-major key, 1: origin-cell-major key (measurement variant)
+#endif
 #ifndef MSNE_SHADE_PREFETCH
 #define MSNE_SHADE_PREFETCH 0
 #endif
@@ -141,8 +145,12 @@ DI uint32_t hitBin(const DeviceScene& sc, const HitRec& h) {
 // of this bounce, every lane walks its ray to the end (traverse.cuh), then the warp sorts its hits by material type.
 // Refilling idle lanes before the whole ticket is done ("dynamic fetch") was measured in three variants and is not
 // used (profiles/r01_sweeps.md).
-template <bool TWO_LEVEL>
-__global__ void __launch_bounds__(TRACE_THREADS, TWO_LEVEL ? TRACE_BLOCKS_PER_SM : TRACE1_BLOCKS_PER_SM) k_trace(DeviceScene sc, PathBuffers pb, WaveState ws, uint32_t buf) {
+// SORTED: the tickets walk `perm` (k_sort_keys + radix sort: rays ordered by direction octant and origin cell, extension rays
+// first) instead of the queue order, so the 32 rays of a warp visit the same part of the tree; the material binning is then
+// done by k_bin in queue order (the shade kernels keep reading contiguous path state).
+template <bool TWO_LEVEL, bool SORTED>
+__global__ void __launch_bounds__(TRACE_THREADS, TWO_LEVEL ? TRACE_BLOCKS_PER_SM : TRACE1_BLOCKS_PER_SM) k_trace(DeviceScene sc, PathBuffers pb, WaveState ws, uint32_t buf,
+                                                                                                               const uint32_t* __restrict__ perm) {
     const Counters cin = ws.counters[buf];
     const uint32_t nLive = cin.nLive, total = cin.nLive + cin.nShadow;
     const uint32_t lane = threadIdx.x & 31;
@@ -176,14 +184,16 @@ __global__ void __launch_bounds__(TRACE_THREADS, TWO_LEVEL ? TRACE_BLOCKS_PER_SM
         if (lane == 0) base = atomicAdd(ws.traceTicket, 32u);
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (base >= total) break;
-        const uint32_t idx = base + lane;
+        const uint32_t idx = !SORTED ? base + lane : (base + lane < total ? __ldg(perm + base + lane) : 0xFFFFFFFFu);
         uint32_t bin = 0xFFu;
         if (idx < nLive) {
             const float4 r0 = qld(pb.R0[buf] + idx), r1 = qld(pb.R1[buf] + idx);
             HitRec h;
             traceRay<false, TWO_LEVEL>(sc, mk3(r0.x, r0.y, r0.z), mk3(r1.x, r1.y, r1.z), 0.0f, MS_INFINITY, h, smemTop);
-            qst(pb.H + idx, make_uint4(h.inst, h.tri, __float_as_uint(h.u), __float_as_uint(h.v)));
             bin = hitBin(sc, h);
+            // the material bin rides in the top bits of the triangle index (H_TRI_MASK, dtypes.h): k_bin reads it back without
+            // repeating the instance -> geometry -> material chain
+            qst(pb.H + idx, make_uint4(h.inst, h.tri | (bin << H_BIN_SHIFT), __float_as_uint(h.u), __float_as_uint(h.v)));
         } else if (idx < total) {
             const float4 q0 = qld(pb.Q0 + (idx - nLive)), q1 = qld(pb.Q1 + (idx - nLive));
             HitRec h;
@@ -194,6 +204,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TWO_LEVEL ? TRACE_BLOCKS_PER_SM
             }
         }
         // ---- warp-level sort by material id: lanes with the same bin elect a leader that reserves their slots
+        if (SORTED) continue;
         const uint32_t peers = __match_any_sync(0xFFFFFFFFu, bin);
         if (bin != 0xFFu) {
             const int leader = __ffs(peers) - 1;
@@ -212,6 +223,76 @@ __global__ void __launch_bounds__(TRACE_THREADS, TWO_LEVEL ? TRACE_BLOCKS_PER_SM
             *ws.traceTicket = 0; *ws.traceDone = 0;
             ws.rayCounts[0] += nLive; ws.rayCounts[1] += cin.nShadow;
             __threadfence();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ray reordering for incoherent bounces (runtime.cpp: only queues above the sort threshold)
+// ------------------------------------------------------------------------------------------------
+// 16-bit key per ray of the joint index space: [15] shadow ray, [14:12] direction octant, [11:0] Morton code of the origin
+// in a 16^3 grid over the scene bounds. Only the ORDER in which rays are traced depends on it - never a result.
+DI uint32_t spread4(uint32_t v) { v &= 0xFu; v = (v | (v << 4)) & 0x0C3u; v = (v | (v << 2)) & 0x249u; return v; }
+__global__ void __launch_bounds__(256) k_sort_keys(PathBuffers pb, WaveState ws, uint32_t buf, SortFrame f, uint16_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const Counters cin = ws.counters[buf];
+    const uint32_t nLive = cin.nLive, total = cin.nLive + cin.nShadow;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const bool shadow = i >= nLive;
+        const float4 o = shadow ? pb.Q0[i - nLive] : pb.R0[buf][i];
+        const float4 d = shadow ? pb.Q1[i - nLive] : pb.R1[buf][i];
+        const uint32_t cx = (uint32_t)fminf(fmaxf((o.x - f.lo[0]) * f.scale[0], 0.0f), 15.0f);
+        const uint32_t cy = (uint32_t)fminf(fmaxf((o.y - f.lo[1]) * f.scale[1], 0.0f), 15.0f);
+        const uint32_t cz = (uint32_t)fminf(fmaxf((o.z - f.lo[2]) * f.scale[2], 0.0f), 15.0f);
+        const uint32_t oct = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
+#if MSNE_SORT_KEY == 1
+        keys[i] = (uint16_t)((shadow ? 0x8000u : 0u) | ((spread4(cx) | (spread4(cy) << 1) | (spread4(cz) << 2)) << 3) | oct);
+#else
+        keys[i] = (uint16_t)((shadow ? 0x8000u : 0u) | (oct << 12) | spread4(cx) | (spread4(cy) << 1) | (spread4(cz) << 2));
+#endif
+        vals[i] = i;
+    }
+}
+// Material binning in queue order for sorted bounces (the epilogue of the unsorted k_trace as a streaming pass over the bins
+// k_trace left in H.y). A warp owns 512 consecutive slots: it counts its bins first, reserves each bin's range with ONE atomic
+// (per-warp-iteration atomics on the five counters made this pass contention-bound), then writes the slots in queue order.
+__global__ void __launch_bounds__(256) k_bin(PathBuffers pb, WaveState ws, uint32_t buf) {
+    const uint32_t nLive = ws.counters[buf].nLive;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t ltMask = (1u << lane) - 1u;
+    const uint32_t warpsTotal = gridDim.x * (blockDim.x >> 5), warpId = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    constexpr uint32_t ITERS = 16, CHUNK = 32 * ITERS;
+    for (uint64_t chunk = (uint64_t)warpId * CHUNK; chunk < nLive; chunk += (uint64_t)warpsTotal * CHUNK) {
+        unsigned long long packed = 0;   // this lane's 16 bins, 4 bits each (0xF = past the end)
+        uint32_t cnt[NUM_BINS];
+#pragma unroll
+        for (uint32_t b = 0; b < NUM_BINS; b++) cnt[b] = 0;
+#pragma unroll
+        for (uint32_t it = 0; it < ITERS; it++) {
+            const uint64_t idx = chunk + it * 32u + lane;
+            const uint32_t bin = idx < nLive ? (qld(&pb.H[idx].y) >> H_BIN_SHIFT) : 0xFu;
+            packed |= (unsigned long long)bin << (4u * it);
+#pragma unroll
+            for (uint32_t b = 0; b < NUM_BINS; b++) cnt[b] += (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, bin == b));
+        }
+        uint32_t mine = 0;
+#pragma unroll
+        for (uint32_t b = 0; b < NUM_BINS; b++) if (lane == b) mine = cnt[b];
+        uint32_t reserved = 0;
+        if (lane < NUM_BINS && mine) reserved = atomicAdd(ws.typeCount + lane, mine);
+        uint32_t next[NUM_BINS];
+#pragma unroll
+        for (uint32_t b = 0; b < NUM_BINS; b++) next[b] = __shfl_sync(0xFFFFFFFFu, reserved, (int)b);
+#pragma unroll
+        for (uint32_t it = 0; it < ITERS; it++) {
+            const uint32_t bin = (uint32_t)(packed >> (4u * it)) & 0xFu;
+            uint32_t slot = 0;
+#pragma unroll
+            for (uint32_t b = 0; b < NUM_BINS; b++) {
+                const uint32_t m = __ballot_sync(0xFFFFFFFFu, bin == b);
+                if (bin == b) slot = next[b] + (uint32_t)__popc(m & ltMask);
+                next[b] += (uint32_t)__popc(m);
+            }
+            if (bin != 0xFu) qst(pb.typeList + ((size_t)bin * pb.capacity + slot), (uint32_t)(chunk + it * 32u + lane));
         }
     }
 }
@@ -308,7 +389,7 @@ DI void shadeOne(const DeviceScene& sc, const DConstants& k, const PathBuffers& 
 
     // decode hit (integrator.hlsl:82-88)
     const uint32_t instanceIndex = H.x;
-    const TriRec* tr = sc.tris + H.y;
+    const TriRec* tr = sc.tris + (H.y & H_TRI_MASK);
     const uint32_t geometryIndex = __ldg(&tr->geom), primitiveIndex = __ldg(&tr->prim);
     const float2 bary = mk2(__uint_as_float(H.z), __uint_as_float(H.w));
     const uint32_t instanceID = __ldg(&sc.instances[instanceIndex].customIndex);
@@ -687,13 +768,32 @@ void launchGenerate(cudaStream_t st, const DCamera& cam, const DConstants& k, co
 void launchTrace(cudaStream_t st, int blocks, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf) {
 #if MSNE_TRACE_SMEM_NODES > 0
     static const size_t smemBytes = MSNE_TRACE_SMEM_NODES * sizeof(BvhNode2) + 16;
-    static const cudaError_t attr = cudaFuncSetAttribute(k_trace<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
+    static const cudaError_t attr = cudaFuncSetAttribute(k_trace<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
     (void)attr;
-    if (sc.staticOnly) k_trace<false><<<blocks, TRACE_THREADS, smemBytes, st>>>(sc, pb, ws, buf);
+    if (sc.staticOnly) k_trace<false, false><<<blocks, TRACE_THREADS, smemBytes, st>>>(sc, pb, ws, buf, nullptr);
 #else
-    if (sc.staticOnly) k_trace<false><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf);
+    if (sc.staticOnly) k_trace<false, false><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf, nullptr);
 #endif
-    else k_trace<true><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf);
+    else k_trace<true, false><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf, nullptr);
+}
+// sorted bounce: keys -> radix sort (16-bit keys, queue index as value) -> trace through the permutation -> binning pass
+size_t sortTempBytes(size_t maxItems) {
+    size_t bytes = 0;
+    cub::DoubleBuffer<uint16_t> k(nullptr, nullptr);
+    cub::DoubleBuffer<uint32_t> v(nullptr, nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, k, v, (uint64_t)maxItems, 0, 16);
+    return bytes;
+}
+void launchTraceSorted(cudaStream_t st, int blocks, int smCount, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const SortFrame& frame,
+                       uint32_t nItems, uint16_t* keys0, uint16_t* keys1, uint32_t* vals0, uint32_t* vals1, void* temp, size_t tempBytes) {
+    k_sort_keys<<<smCount * 8, 256, 0, st>>>(pb, ws, buf, frame, keys0, vals0);
+    cub::DoubleBuffer<uint16_t> k(keys0, keys1);
+    cub::DoubleBuffer<uint32_t> v(vals0, vals1);
+    cub::DeviceRadixSort::SortPairs(temp, tempBytes, k, v, (uint64_t)nItems, 0, 16, st);
+    const uint32_t* perm = v.Current();
+    if (sc.staticOnly) k_trace<false, true><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf, perm);
+    else k_trace<true, true><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf, perm);
+    k_bin<<<smCount * 8, 256, 0, st>>>(pb, ws, buf);
 }
 // Register caps (measured, profiles/r01_sweeps.md): the all-material kernel runs best at 80 registers
 // (6 blocks/SM); the specialised kernels are smaller and take the same cap.
@@ -737,13 +837,13 @@ void launchPrimaryProbe(cudaStream_t st, const DCamera& cam, const DConstants& k
 }
 int traceOccupancyBlocksPerSm() {
     int n = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<true>, TRACE_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<true, false>, TRACE_THREADS, 0);
     int n1 = 0;
 #if MSNE_TRACE_SMEM_NODES > 0
-    cudaFuncSetAttribute(k_trace<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MSNE_TRACE_SMEM_NODES * sizeof(BvhNode2) + 16));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, k_trace<false>, TRACE_THREADS, MSNE_TRACE_SMEM_NODES * sizeof(BvhNode2) + 16);
+    cudaFuncSetAttribute(k_trace<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MSNE_TRACE_SMEM_NODES * sizeof(BvhNode2) + 16));
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, k_trace<false, false>, TRACE_THREADS, MSNE_TRACE_SMEM_NODES * sizeof(BvhNode2) + 16);
 #else
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, k_trace<false>, TRACE_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, k_trace<false, false>, TRACE_THREADS, 0);
 #endif
     n = n > n1 ? n : n1;
     return n;

@@ -222,6 +222,12 @@ struct HdMoonshine {
     DevBuf<Counters> dCounters;
     DevBuf<uint32_t> dScalars;       // [0] traceTicket [1] traceDone [2] shadeDone [3] maxBounce [4..8] typeCount [9..13] binDone
     DevBuf<uint32_t> poolTypeList;
+    // ray reordering (kernels.cu k_sort_keys): double-buffered 16-bit keys + queue indices over the joint index space (<= 3 P items)
+    DevBuf<uint16_t> sortKeys[2];
+    DevBuf<uint32_t> sortVals[2];
+    DevBuf<uint8_t> sortTemp;
+    uint64_t sortThreshold = 0;      // extension-ray queues at least this long are traced in sorted order (0 = never)
+    SortFrame sortFrame{};           // scene bounds for the origin cells (buildTlas)
     DevBuf<unsigned long long> dRayCounts;
     Counters* hostCounters = nullptr;   // pinned ring of 4
     cudaEvent_t bounceEvents[4]{};
@@ -268,6 +274,7 @@ struct HdMoonshine {
         if (const char* e = getenv("MSNE_TWO_LEVEL")) forceTwoLevel = atoi(e) != 0;
         if (const char* e = getenv("MSNE_LOG_BOUNCES")) logBounces = atoi(e) != 0;
         if (const char* e = getenv("MSNE_TAIL_THRESHOLD")) tailThreshold = strtoull(e, nullptr, 10);
+        if (const char* e = getenv("MSNE_SORT_THRESHOLD")) sortThreshold = strtoull(e, nullptr, 10);
         traceBlocks = smCount * std::max(1, traceOccupancyBlocksPerSm());
         shadeBlocks = smCount * std::max(1, shadeOccupancyBlocksPerSm());
         CK(cudaStreamSynchronize(stream));
@@ -518,6 +525,14 @@ struct HdMoonshine {
             di[i] = instanceRecord(in);
         }
         dInstances.upload(di.data(), di.size(), stream);
+        {   // bounds of everything visible: the 16^3 grid of the ray-sorting keys (ordering only, never a result)
+            BuildBox all; for (int a = 0; a < 3; a++) { all.lo[a] = 1e30f; all.hi[a] = -1e30f; }
+            for (const BuildBox& b : boxes) for (int a = 0; a < 3; a++) { all.lo[a] = std::min(all.lo[a], b.lo[a]); all.hi[a] = std::max(all.hi[a], b.hi[a]); }
+            for (int a = 0; a < 3; a++) {
+                const float ext = boxes.empty() ? 1.0f : std::max(all.hi[a] - all.lo[a], 1e-20f);
+                sortFrame.lo[a] = boxes.empty() ? 0.0f : all.lo[a]; sortFrame.scale[a] = 16.0f / ext;
+            }
+        }
         hasTlas = !items.empty();
         tlasStaticOnly = haveStatic && items.size() == 1;
         if (hasTlas) {
@@ -718,6 +733,10 @@ struct HdMoonshine {
         poolBufs[14].alloc(P);
         poolH.alloc(P);
         poolTypeList.alloc((size_t)NUM_BINS * P);
+        if (sortThreshold) {
+            for (int i = 0; i < 2; i++) { sortKeys[i].alloc((size_t)3 * P); sortVals[i].alloc((size_t)3 * P); }
+            sortTemp.alloc(sortTempBytes((size_t)3 * P));
+        }
         for (int b = 0; b < 2; b++) {
             pb.R0[b] = poolBufs[0 + b].p; pb.R1[b] = poolBufs[2 + b].p; pb.S0[b] = poolBufs[4 + b].p; pb.S1[b] = poolBufs[6 + b].p;
             pb.N0[b] = poolBufs[8 + b].p; pb.N1[b] = poolBufs[10 + b].p;
@@ -738,11 +757,18 @@ struct HdMoonshine {
         stats.kernel_launches++;
         int profUsed = 0;
         uint64_t lastLive = (uint64_t)nPix * nSamples;   // most recent survivor count known to the host
-        auto enqueueBounce = [&](uint32_t b) {
+        // `in`: exact input counts of the bounce when the host already knows them (sorted bounces), else nullptr
+        auto enqueueBounce = [&](uint32_t b, const Counters* in) {
             const uint32_t buf = b & 1u;
             const bool prof = profiling && profUsed < kProfEvents;
             if (prof) CK(cudaEventRecord(profEv[profUsed][0], stream));
-            launchTrace(stream, traceBlocks, sc, pb, ws, buf);
+            if (in != nullptr && sortThreshold && in->nLive >= sortThreshold) {
+                launchTraceSorted(stream, traceBlocks, smCount, sc, pb, ws, buf, sortFrame, in->nLive + in->nShadow, sortKeys[0].p, sortKeys[1].p, sortVals[0].p, sortVals[1].p,
+                                  sortTemp.p, sortTemp.n);
+                stats.kernel_launches += 6;   // keys, CUB histogram + exclusive sum + 2 onesweep passes, binning
+            } else {
+                launchTrace(stream, traceBlocks, sc, pb, ws, buf);
+            }
             if (prof) { CK(cudaEventRecord(profEv[profUsed][1], stream)); profUsed++; }
             // big queues: one material-specialised launch per bin; small queues (tail): one generic launch
             if (lastLive >= binnedThreshold) { launchShadeBinned(stream, shadeBlocks, sc, k, pb, ws, buf); stats.kernel_launches += 6; }
@@ -752,14 +778,19 @@ struct HdMoonshine {
         };
         // keep one bounce queued ahead of the one whose survivor count we wait for
         const uint32_t maxIter = k.max_bounces + 4;
-        enqueueBounce(0);
+        enqueueBounce(0, nullptr);   // primary rays are coherent as generated (8x4 pixel blocks per warp)
         for (uint32_t b = 0; b < maxIter; b++) {
-            enqueueBounce(b + 1);
+            // Long queues (sorted bounces): the radix sort needs the exact item count on the host, so the next bounce is queued
+            // only after this one's counts arrived - a ~20 us bubble against milliseconds of work. Short queues keep one bounce
+            // queued ahead of the count the host waits for.
+            const bool ahead = !(sortThreshold && lastLive >= sortThreshold);
+            if (ahead) enqueueBounce(b + 1, nullptr);
             CK(cudaEventSynchronize(bounceEvents[b & 3u]));
             const Counters c = hostCounters[b & 3u];
             if (logBounces) fprintf(stderr, "libmoonshine: bounce %u -> live %u dead %u shadow %u\n", b, c.nLive, c.nDead, c.nShadow);
             lastLive = c.nLive;
-            if (c.nLive + c.nDead == 0) break;   // bounce b+1 then runs on empty queues
+            if (c.nLive + c.nDead == 0) break;   // a bounce b+1 queued ahead then runs on empty queues
+            if (!ahead) enqueueBounce(b + 1, &c);
             if ((uint64_t)c.nLive + c.nDead < tailThreshold) {
                 // few stragglers left: after the already-queued bounce b+1, trace once more and let k_tail finish
                 // every remaining path in a single launch instead of ~130 launch pairs at the latency floor

@@ -206,6 +206,32 @@ int main(int argc, char** argv) {
         totalCost += cost; totalRays += rays.size();
     };
     char nm[32];
+    // optional ray reordering before the warps are formed (MSNE_SIM_SORT): 1 = stable by direction octant, 2 = octant then
+    // origin cell (4 bits per axis, Morton), 3 = origin cell then octant, 4 = origin cell (5 bits) + octahedral direction (4x4)
+    const int sortMode = getenv("MSNE_SIM_SORT") ? atoi(getenv("MSNE_SIM_SORT")) : 0;
+    if (sortMode) {
+        auto part = [](uint32_t v) { v &= 1023; v = (v | (v << 16)) & 0x30000FF; v = (v | (v << 8)) & 0x300F00F; v = (v | (v << 4)) & 0x30C30C3; v = (v | (v << 2)) & 0x9249249; return v; };
+        auto key = [&](const Ray& r) -> uint64_t {
+            const uint32_t oct = (r.d.x < 0) | ((r.d.y < 0) << 1) | ((r.d.z < 0) << 2);
+            auto cell = [&](int bits) {
+                const float sc[3] = {(r.o.x - bvh.bounds.lo[0]) / (bvh.bounds.hi[0] - bvh.bounds.lo[0]), (r.o.y - bvh.bounds.lo[1]) / (bvh.bounds.hi[1] - bvh.bounds.lo[1]),
+                                     (r.o.z - bvh.bounds.lo[2]) / (bvh.bounds.hi[2] - bvh.bounds.lo[2])};
+                uint32_t c[3];
+                for (int a = 0; a < 3; a++) c[a] = (uint32_t)std::min<float>((1 << bits) - 1, std::max(0.0f, sc[a] * (1 << bits)));
+                return (uint64_t)(part(c[0]) | (part(c[1]) << 1) | (part(c[2]) << 2));
+            };
+            if (sortMode == 1) return oct;
+            if (sortMode == 2) return ((uint64_t)oct << 32) | cell(4);
+            if (sortMode == 3) return (cell(4) << 3) | oct;
+            const float an = std::fabs(r.d.x) + std::fabs(r.d.y) + std::fabs(r.d.z);
+            const float u = r.d.x / an, v = r.d.y / an;
+            const uint32_t du = (uint32_t)std::min(3.0f, (u * 0.5f + 0.5f) * 4), dv = (uint32_t)std::min(3.0f, (v * 0.5f + 0.5f) * 4);
+            return (cell(5) << 8) | (oct << 4) | (du << 2) | dv;
+        };
+        for (int b = 1; b < maxB; b++)
+            for (auto* v : {&byBounce[b], &shadowBy[b]})
+                std::stable_sort(v->begin(), v->end(), [&](const Ray& a, const Ray& c) { return key(a) < key(c); });
+    }
     for (int b = 0; b < maxB; b++) { snprintf(nm, sizeof nm, "ext b%d", b); measure(nm, byBounce[b]); }
     for (int b = 0; b < maxB; b++) { snprintf(nm, sizeof nm, "shadow b%d", b); measure(nm, shadowBy[b]); }
     printf("TOTAL warp cost per ray %.1f over %llu rays\n", totalCost / totalRays, (unsigned long long)totalRays);
