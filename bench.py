@@ -4,7 +4,7 @@
 Workload (config.workload): cfg3, the procedural "Salle-de-bain-class" bathroom (moonshine_b200/scenes.py
 `bathroom`, ~1.4 M triangles, 34 materials, sun+sky env map) at 1920x1080, offline constants
 (offline/main.zig:106-111). One STEP = one wave batch of `batch_spp` samples per pixel over every pixel this
-rank owns (default 32 spp; the default 32 timed steps are the full 1024 spp of the metric config). With N
+rank owns (default 64 spp = one 128 Mi-path wave at 1080p; the default 16 timed steps are the full 1024 spp of the metric config). With N
 GPUs the image is sharded into 32x32 tiles round-robin over ranks and each step renders batch_spp*N samples
 of the rank's tiles (weak scaling: per-GPU work fixed), followed by ONE NCCL reduce of the RGBA32F radiance
 buffer to rank 0 inside the timed region.
@@ -14,7 +14,9 @@ buffer to rank 0 inside the timed region.
   e2e      same metric through the reference-facing call HdMoonshineRender (hydra/moonshine.h:74): per step
            one launch of samples_per_run = batch_spp samples + the D2H copy of the sensor into the host buffer,
            wall-clock, host<->device copies inside the timed region.
-  roofline dominant kernel k_trace: algorithmic bytes (48 B per traced ray) / CUDA-event duration.
+  roofline dominant kernel k_trace: algorithmic bytes (48 B per traced ray) / CUDA-event duration of the k_trace
+           launches alone; the ray-reordering passes of sorted bounces (keys, radix sort, binning) are timed separately
+           (roofline.reorder_share_of_step).
   cpu_baseline / --impl reference: the CPU oracle (line-by-line restatement of the reference shaders; the
            reference itself has no CPU path and cannot be built here) on the host cores, bounded pixel sample.
 """
@@ -171,7 +173,7 @@ def config_dict(args, scene, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=32)
+    ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg3")
@@ -179,8 +181,8 @@ def main():
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--detail", type=float, default=1.0)
     ap.add_argument("--n-side", type=int, default=1000, help="cfg5: instances per side (1000 = 10^6 instances)")
-    ap.add_argument("--batch-spp", type=int, default=32)
-    ap.add_argument("--paths-in-flight", type=int, default=0, help="wavefront pool size in paths (0 = library default, 64 Mi)")
+    ap.add_argument("--batch-spp", type=int, default=64)
+    ap.add_argument("--paths-in-flight", type=int, default=0, help="wavefront pool size in paths (0 = library default, 128 Mi)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps (capped at 32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -271,6 +273,7 @@ def main():
                 "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
                 "peak_source": peak_src, "launches": int(st.trace_launches), "avg_launch_ms": st.trace_ms / max(1, st.trace_launches),
                 "kernel_share_of_step": st.trace_ms / max(st.device_ms, 1e-9),
+                "reorder_share_of_step": st.sort_ms / max(st.device_ms, 1e-9),
                 "algorithmic_bytes_per_launch": trace_bytes / max(1, st.trace_launches),
                 "note": "software BVH traversal is L2-latency bound, not streaming bound: see DESIGN.md and profiles/"}
     roofline_step = {"bytes_formula": "224*N_ext + 112*N_shadow + 32*N_samples (SURVEY.md 8d)", "achieved": step_bytes / (st.device_ms / 1e3) / 1e9,

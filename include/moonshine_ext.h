@@ -57,6 +57,7 @@ typedef struct MsneStats {
     uint64_t static_blas_builds;        /* rebuilds of the BLAS level (merged static BLAS + shared BLASes) */
     uint64_t tlas_builds;               /* rebuilds of the instance level (TLAS + instance records) */
     uint64_t tlas_refits;               /* transform-only edits served by a bottom-up refit of the existing TLAS */
+    double   sort_ms;                   /* CUDA-event time of the ray-reordering passes (keys + radix sort + binning; profiling on) */
 } MsneStats;
 
 /* must be called before HdMoonshineCreate; selects the CUDA device of objects created afterwards */
@@ -84,6 +85,10 @@ MSNE_API void* HdMoonshineExtGetSensorDevicePtr(const HdMoonshine*, SensorHandle
 /* multi-GPU: this object renders only the pixels of 32x32 tiles t with t % world == rank; the rest stay 0 */
 MSNE_API bool HdMoonshineExtSetTileShard(HdMoonshine*, uint32_t rank, uint32_t world);
 MSNE_API void HdMoonshineExtSetPathsInFlight(HdMoonshine*, uint64_t max_paths);   /* wavefront pool size (0 = default) */
+/* extension-ray queues of at least `min_rays` are traced in sorted order (direction octant + origin cell); 0 = never,
+ * UINT64_MAX = library default (262144, and only for scenes whose BVHs hold >= 2048 nodes). Ordering only: images are
+ * bitwise identical either way. */
+MSNE_API void HdMoonshineExtSetRaySorting(HdMoonshine*, uint64_t min_rays);
 MSNE_API void HdMoonshineExtSetProfiling(HdMoonshine*, bool per_kernel_events);
 
 MSNE_API void HdMoonshineExtGetStats(const HdMoonshine*, MsneStats*);

@@ -230,24 +230,26 @@ __global__ void __launch_bounds__(TRACE_THREADS, TWO_LEVEL ? TRACE_BLOCKS_PER_SM
 // ------------------------------------------------------------------------------------------------
 // ray reordering for incoherent bounces (runtime.cpp: only queues above the sort threshold)
 // ------------------------------------------------------------------------------------------------
-// 16-bit key per ray of the joint index space: [15] shadow ray, [14:12] direction octant, [11:0] Morton code of the origin
-// in a 16^3 grid over the scene bounds. Only the ORDER in which rays are traced depends on it - never a result.
-DI uint32_t spread4(uint32_t v) { v &= 0xFu; v = (v | (v << 4)) & 0x0C3u; v = (v | (v << 2)) & 0x249u; return v; }
+// 16-bit key per ray of the joint index space: [15] shadow ray, [14:12] direction octant, [11:0] origin cell (z, y, x cell
+// coordinates concatenated; thousands of rays share a key, so the order BETWEEN cells is immaterial). Only the order in which
+// rays are traced depends on it - never a result.
 __global__ void __launch_bounds__(256) k_sort_keys(PathBuffers pb, WaveState ws, uint32_t buf, SortFrame f, uint16_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     const Counters cin = ws.counters[buf];
     const uint32_t nLive = cin.nLive, total = cin.nLive + cin.nShadow;
+    const float mx = (float)((1u << f.bits[0]) - 1u), my = (float)((1u << f.bits[1]) - 1u), mz = (float)((1u << f.bits[2]) - 1u);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const bool shadow = i >= nLive;
         const float4 o = shadow ? pb.Q0[i - nLive] : pb.R0[buf][i];
         const float4 d = shadow ? pb.Q1[i - nLive] : pb.R1[buf][i];
-        const uint32_t cx = (uint32_t)fminf(fmaxf((o.x - f.lo[0]) * f.scale[0], 0.0f), 15.0f);
-        const uint32_t cy = (uint32_t)fminf(fmaxf((o.y - f.lo[1]) * f.scale[1], 0.0f), 15.0f);
-        const uint32_t cz = (uint32_t)fminf(fmaxf((o.z - f.lo[2]) * f.scale[2], 0.0f), 15.0f);
+        const uint32_t cx = (uint32_t)fminf(fmaxf((o.x - f.lo[0]) * f.scale[0], 0.0f), mx);
+        const uint32_t cy = (uint32_t)fminf(fmaxf((o.y - f.lo[1]) * f.scale[1], 0.0f), my);
+        const uint32_t cz = (uint32_t)fminf(fmaxf((o.z - f.lo[2]) * f.scale[2], 0.0f), mz);
         const uint32_t oct = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
+        const uint32_t cell = (((cz << f.bits[1]) | cy) << f.bits[0]) | cx;
 #if MSNE_SORT_KEY == 1
-        keys[i] = (uint16_t)((shadow ? 0x8000u : 0u) | ((spread4(cx) | (spread4(cy) << 1) | (spread4(cz) << 2)) << 3) | oct);
+        keys[i] = (uint16_t)((shadow ? 0x8000u : 0u) | (cell << 3) | oct);
 #else
-        keys[i] = (uint16_t)((shadow ? 0x8000u : 0u) | (oct << 12) | spread4(cx) | (spread4(cy) << 1) | (spread4(cz) << 2));
+        keys[i] = (uint16_t)((shadow ? 0x8000u : 0u) | (oct << 12) | cell);
 #endif
         vals[i] = i;
     }
@@ -784,17 +786,19 @@ size_t sortTempBytes(size_t maxItems) {
     cub::DeviceRadixSort::SortPairs(nullptr, bytes, k, v, (uint64_t)maxItems, 0, 16);
     return bytes;
 }
-void launchTraceSorted(cudaStream_t st, int blocks, int smCount, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const SortFrame& frame,
-                       uint32_t nItems, uint16_t* keys0, uint16_t* keys1, uint32_t* vals0, uint32_t* vals1, void* temp, size_t tempBytes) {
+const uint32_t* launchSortRays(cudaStream_t st, int smCount, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const SortFrame& frame, uint32_t nItems,
+                               uint16_t* keys0, uint16_t* keys1, uint32_t* vals0, uint32_t* vals1, void* temp, size_t tempBytes) {
     k_sort_keys<<<smCount * 8, 256, 0, st>>>(pb, ws, buf, frame, keys0, vals0);
     cub::DoubleBuffer<uint16_t> k(keys0, keys1);
     cub::DoubleBuffer<uint32_t> v(vals0, vals1);
     cub::DeviceRadixSort::SortPairs(temp, tempBytes, k, v, (uint64_t)nItems, 0, 16, st);
-    const uint32_t* perm = v.Current();
+    return v.Current();
+}
+void launchTraceSorted(cudaStream_t st, int blocks, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const uint32_t* perm) {
     if (sc.staticOnly) k_trace<false, true><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf, perm);
     else k_trace<true, true><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf, perm);
-    k_bin<<<smCount * 8, 256, 0, st>>>(pb, ws, buf);
 }
+void launchBin(cudaStream_t st, int smCount, const PathBuffers& pb, const WaveState& ws, uint32_t buf) { k_bin<<<smCount * 8, 256, 0, st>>>(pb, ws, buf); }
 // Register caps (measured, profiles/r01_sweeps.md): the all-material kernel runs best at 80 registers
 // (6 blocks/SM); the specialised kernels are smaller and take the same cap.
 #ifndef SHADE_MINB

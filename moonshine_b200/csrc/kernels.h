@@ -27,11 +27,15 @@ namespace msne {
 void launchGenerate(cudaStream_t st, const DCamera& cam, const DConstants& k, const PathBuffers& pb, Counters* counters, const uint32_t* pixIds,
                     uint32_t nPix, uint32_t nSamples, uint32_t firstSample);
 void launchTrace(cudaStream_t st, int blocks, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf);
-// ray reordering (kernels.cu k_sort_keys / k_bin): origin cell = (o - lo) * scale in a 16^3 grid over the scene bounds
-struct SortFrame { float lo[3], scale[3]; };
+// ray reordering (kernels.cu k_sort_keys / k_bin): origin cell = (o - lo) * scale in a grid of 2^bits[a] cells per axis over the
+// scene bounds; 3 bits per axis + 3 dealt out to the axes with the longest cells (runtime.cpp buildTlas)
+struct SortFrame { float lo[3], scale[3]; uint32_t bits[3]; };
 size_t sortTempBytes(size_t maxItems);
-void launchTraceSorted(cudaStream_t st, int blocks, int smCount, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const SortFrame& frame,
-                       uint32_t nItems, uint16_t* keys0, uint16_t* keys1, uint32_t* vals0, uint32_t* vals1, void* temp, size_t tempBytes);
+// sorted bounce = launchSortRays (keys + 16-bit radix sort; returns the permutation) -> launchTraceSorted -> launchBin
+const uint32_t* launchSortRays(cudaStream_t st, int smCount, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const SortFrame& frame, uint32_t nItems,
+                               uint16_t* keys0, uint16_t* keys1, uint32_t* vals0, uint32_t* vals1, void* temp, size_t tempBytes);
+void launchTraceSorted(cudaStream_t st, int blocks, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const uint32_t* perm);
+void launchBin(cudaStream_t st, int smCount, const PathBuffers& pb, const WaveState& ws, uint32_t buf);
 void launchShade(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf);
 void launchShadeBinned(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf);
 void launchTail(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf);

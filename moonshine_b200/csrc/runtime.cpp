@@ -215,7 +215,7 @@ struct HdMoonshine {
     uint32_t shardRank = 0, shardWorld = 1;
 
     // wavefront pool
-    uint64_t pathsInFlight = 1ull << 26;   // 64 Mi paths x 288 B = 18 GiB of the 180 GB HBM; amortises the Russian-roulette tail
+    uint64_t pathsInFlight = 1ull << 27;   // 128 Mi paths x 308 B = 39 GiB (+ 5 GiB of sort buffers) of the 180 GB HBM; amortises the ~8 ms Russian-roulette tail of a wave
     PathBuffers pb{};
     std::vector<DevBuf<float4>> poolBufs;
     DevBuf<uint4> poolH;
@@ -226,7 +226,10 @@ struct HdMoonshine {
     DevBuf<uint16_t> sortKeys[2];
     DevBuf<uint32_t> sortVals[2];
     DevBuf<uint8_t> sortTemp;
-    uint64_t sortThreshold = 0;      // extension-ray queues at least this long are traced in sorted order (0 = never)
+    uint64_t sortThreshold = 262144; // extension-ray queues at least this long are traced in sorted order (0 = never)
+    bool sortAnyScene = false;       // false: only scenes with >= kSortMinNodes BVH nodes (a 36-triangle Cornell box loses 4 % to the sort)
+    static constexpr size_t kSortMinNodes = 2048;
+    bool sortActive = false;         // decided per render (renderLaunches)
     SortFrame sortFrame{};           // scene bounds for the origin cells (buildTlas)
     DevBuf<unsigned long long> dRayCounts;
     Counters* hostCounters = nullptr;   // pinned ring of 4
@@ -242,7 +245,8 @@ struct HdMoonshine {
     // profiling
     bool profiling = false;
     static const int kProfEvents = 96;
-    cudaEvent_t profEv[kProfEvents][2]{};
+    cudaEvent_t profEv[kProfEvents][4]{};   // [0],[1] around k_trace; sorted bounces: [2] before the sort, [3] after the binning pass
+    bool profSorted[kProfEvents]{};
     MsneStats stats{};
 
     // ---- lifecycle ---------------------------------------------------------------------------
@@ -255,7 +259,7 @@ struct HdMoonshine {
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         for (auto& e : bounceEvents) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CK(cudaEventCreate(&evStart)); CK(cudaEventCreate(&evStop));
-        for (auto& p : profEv) { CK(cudaEventCreate(&p[0])); CK(cudaEventCreate(&p[1])); }
+        for (auto& p : profEv) for (auto& e : p) CK(cudaEventCreate(&e));
         CK(cudaMallocHost((void**)&hostCounters, 4 * sizeof(Counters)));
         dCounters.alloc(2); dScalars.alloc(16); dRayCounts.alloc(2);
         CK(cudaMemsetAsync(dCounters.p, 0, 2 * sizeof(Counters), stream));
@@ -274,7 +278,7 @@ struct HdMoonshine {
         if (const char* e = getenv("MSNE_TWO_LEVEL")) forceTwoLevel = atoi(e) != 0;
         if (const char* e = getenv("MSNE_LOG_BOUNCES")) logBounces = atoi(e) != 0;
         if (const char* e = getenv("MSNE_TAIL_THRESHOLD")) tailThreshold = strtoull(e, nullptr, 10);
-        if (const char* e = getenv("MSNE_SORT_THRESHOLD")) sortThreshold = strtoull(e, nullptr, 10);
+        if (const char* e = getenv("MSNE_SORT_THRESHOLD")) { sortThreshold = strtoull(e, nullptr, 10); sortAnyScene = true; }
         traceBlocks = smCount * std::max(1, traceOccupancyBlocksPerSm());
         shadeBlocks = smCount * std::max(1, shadeOccupancyBlocksPerSm());
         CK(cudaStreamSynchronize(stream));
@@ -288,7 +292,7 @@ struct HdMoonshine {
         for (auto& e : bounceEvents) if (e) cudaEventDestroy(e);
         if (evStart) cudaEventDestroy(evStart);
         if (evStop) cudaEventDestroy(evStop);
-        for (auto& p : profEv) { if (p[0]) cudaEventDestroy(p[0]); if (p[1]) cudaEventDestroy(p[1]); }
+        for (auto& p : profEv) for (auto& e : p) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
     }
 
@@ -528,10 +532,16 @@ struct HdMoonshine {
         {   // bounds of everything visible: the 16^3 grid of the ray-sorting keys (ordering only, never a result)
             BuildBox all; for (int a = 0; a < 3; a++) { all.lo[a] = 1e30f; all.hi[a] = -1e30f; }
             for (const BuildBox& b : boxes) for (int a = 0; a < 3; a++) { all.lo[a] = std::min(all.lo[a], b.lo[a]); all.hi[a] = std::max(all.hi[a], b.hi[a]); }
-            for (int a = 0; a < 3; a++) {
-                const float ext = boxes.empty() ? 1.0f : std::max(all.hi[a] - all.lo[a], 1e-20f);
-                sortFrame.lo[a] = boxes.empty() ? 0.0f : all.lo[a]; sortFrame.scale[a] = 16.0f / ext;
+            float ext[3];
+            for (int a = 0; a < 3; a++) { ext[a] = boxes.empty() ? 1.0f : std::max(all.hi[a] - all.lo[a], 1e-20f); sortFrame.lo[a] = boxes.empty() ? 0.0f : all.lo[a]; sortFrame.bits[a] = 3; }
+            // 3 bits per axis (even the thin axis of a flat scene separates ray populations: cfg5 loses 3 % without them), then
+            // the remaining 3 bits go to the axes whose cells are still the longest
+            for (int n = 0; n < 3; n++) {
+                int best = 0;
+                for (int a = 1; a < 3; a++) if (ext[a] / float(1u << sortFrame.bits[a]) > ext[best] / float(1u << sortFrame.bits[best])) best = a;
+                sortFrame.bits[best]++;
             }
+            for (int a = 0; a < 3; a++) sortFrame.scale[a] = float(1u << sortFrame.bits[a]) / ext[a];
         }
         hasTlas = !items.empty();
         tlasStaticOnly = haveStatic && items.size() == 1;
@@ -733,15 +743,18 @@ struct HdMoonshine {
         poolBufs[14].alloc(P);
         poolH.alloc(P);
         poolTypeList.alloc((size_t)NUM_BINS * P);
-        if (sortThreshold) {
-            for (int i = 0; i < 2; i++) { sortKeys[i].alloc((size_t)3 * P); sortVals[i].alloc((size_t)3 * P); }
-            sortTemp.alloc(sortTempBytes((size_t)3 * P));
-        }
+        sortKeys[0].release();   // sized with the pool (ensureSortBuffers)
         for (int b = 0; b < 2; b++) {
             pb.R0[b] = poolBufs[0 + b].p; pb.R1[b] = poolBufs[2 + b].p; pb.S0[b] = poolBufs[4 + b].p; pb.S1[b] = poolBufs[6 + b].p;
             pb.N0[b] = poolBufs[8 + b].p; pb.N1[b] = poolBufs[10 + b].p;
         }
         pb.Q0 = poolBufs[12].p; pb.Q1 = poolBufs[13].p; pb.result = poolBufs[14].p; pb.H = poolH.p; pb.typeList = poolTypeList.p; pb.capacity = P;
+    }
+    void ensureSortBuffers() {
+        const size_t items = (size_t)3 * pb.capacity;
+        if (sortKeys[0].n >= items) return;
+        for (int i = 0; i < 2; i++) { sortKeys[i].alloc(items); sortVals[i].alloc(items); }
+        sortTemp.alloc(sortTempBytes(items));
     }
     WaveState waveState() const {
         WaveState ws{};
@@ -761,15 +774,23 @@ struct HdMoonshine {
         auto enqueueBounce = [&](uint32_t b, const Counters* in) {
             const uint32_t buf = b & 1u;
             const bool prof = profiling && profUsed < kProfEvents;
-            if (prof) CK(cudaEventRecord(profEv[profUsed][0], stream));
-            if (in != nullptr && sortThreshold && in->nLive >= sortThreshold) {
-                launchTraceSorted(stream, traceBlocks, smCount, sc, pb, ws, buf, sortFrame, in->nLive + in->nShadow, sortKeys[0].p, sortKeys[1].p, sortVals[0].p, sortVals[1].p,
-                                  sortTemp.p, sortTemp.n);
+            const bool sorted = in != nullptr && sortActive && in->nLive >= sortThreshold;
+            if (prof) profSorted[profUsed] = sorted;
+            if (sorted) {
+                if (prof) CK(cudaEventRecord(profEv[profUsed][2], stream));
+                const uint32_t* perm = launchSortRays(stream, smCount, pb, ws, buf, sortFrame, in->nLive + in->nShadow, sortKeys[0].p, sortKeys[1].p, sortVals[0].p, sortVals[1].p,
+                                                      sortTemp.p, sortTemp.n);
+                if (prof) CK(cudaEventRecord(profEv[profUsed][0], stream));
+                launchTraceSorted(stream, traceBlocks, sc, pb, ws, buf, perm);
+                if (prof) CK(cudaEventRecord(profEv[profUsed][1], stream));
+                launchBin(stream, smCount, pb, ws, buf);
+                if (prof) { CK(cudaEventRecord(profEv[profUsed][3], stream)); profUsed++; }
                 stats.kernel_launches += 6;   // keys, CUB histogram + exclusive sum + 2 onesweep passes, binning
             } else {
+                if (prof) CK(cudaEventRecord(profEv[profUsed][0], stream));
                 launchTrace(stream, traceBlocks, sc, pb, ws, buf);
+                if (prof) { CK(cudaEventRecord(profEv[profUsed][1], stream)); profUsed++; }
             }
-            if (prof) { CK(cudaEventRecord(profEv[profUsed][1], stream)); profUsed++; }
             // big queues: one material-specialised launch per bin; small queues (tail): one generic launch
             if (lastLive >= binnedThreshold) { launchShadeBinned(stream, shadeBlocks, sc, k, pb, ws, buf); stats.kernel_launches += 6; }
             else { launchShade(stream, shadeBlocks, sc, k, pb, ws, buf); stats.kernel_launches += 2; }
@@ -783,7 +804,7 @@ struct HdMoonshine {
             // Long queues (sorted bounces): the radix sort needs the exact item count on the host, so the next bounce is queued
             // only after this one's counts arrived - a ~20 us bubble against milliseconds of work. Short queues keep one bounce
             // queued ahead of the count the host waits for.
-            const bool ahead = !(sortThreshold && lastLive >= sortThreshold);
+            const bool ahead = !(sortActive && lastLive >= sortThreshold);
             if (ahead) enqueueBounce(b + 1, nullptr);
             CK(cudaEventSynchronize(bounceEvents[b & 3u]));
             const Counters c = hostCounters[b & 3u];
@@ -809,6 +830,10 @@ struct HdMoonshine {
                 float ms = 0;
                 CK(cudaEventElapsedTime(&ms, profEv[i][0], profEv[i][1]));
                 stats.trace_ms += ms; stats.trace_launches++;
+                if (profSorted[i]) {
+                    CK(cudaEventElapsedTime(&ms, profEv[i][2], profEv[i][0])); stats.sort_ms += ms;
+                    CK(cudaEventElapsedTime(&ms, profEv[i][1], profEv[i][3])); stats.sort_ms += ms;
+                }
             }
         }
     }
@@ -824,6 +849,8 @@ struct HdMoonshine {
         const uint64_t totalSamples = (uint64_t)nLaunches * k.samples_per_run;
         if (s.nPix == 0 || totalSamples == 0) { s.sample_count += (uint32_t)totalSamples; return; }
         ensurePool(std::min<uint64_t>(pathsInFlight, (uint64_t)s.nPix * totalSamples));
+        sortActive = sortThreshold != 0 && pb.capacity >= sortThreshold && (sortAnyScene || blasNodePool.size() + tlasHostNodes.size() >= kSortMinNodes);
+        if (sortActive) ensureSortBuffers();
         const uint32_t P = pb.capacity;
         CK(cudaEventRecord(evStart, stream));
         const uint32_t pixChunk = std::min(s.nPix, P);
@@ -1127,7 +1154,12 @@ bool HdMoonshineExtSetTileShard(HdMoonshine* h, uint32_t rank, uint32_t world) {
         return true;
     } catch (const std::exception& e) { g_lastError = e.what(); return false; }
 }
-void HdMoonshineExtSetPathsInFlight(HdMoonshine* h, uint64_t n) { LOCK(h); h->pathsInFlight = n ? n : (1ull << 26); h->pb.capacity = 0; }
+void HdMoonshineExtSetRaySorting(HdMoonshine* h, uint64_t minRays) {
+    LOCK(h);
+    if (minRays == UINT64_MAX) { h->sortThreshold = 262144; h->sortAnyScene = false; }
+    else { h->sortThreshold = minRays; h->sortAnyScene = true; }
+}
+void HdMoonshineExtSetPathsInFlight(HdMoonshine* h, uint64_t n) { LOCK(h); h->pathsInFlight = n ? n : (1ull << 27); h->pb.capacity = 0; }
 void HdMoonshineExtSetProfiling(HdMoonshine* h, bool on) { LOCK(h); h->profiling = on; }
 void HdMoonshineExtGetStats(const HdMoonshine* h, MsneStats* out) {
     HdMoonshine* m = const_cast<HdMoonshine*>(h);

@@ -64,7 +64,7 @@ class MsneMaterialInfo(C.Structure):
 class MsneStats(C.Structure):
     _fields_ = [("rays_closest", C.c_uint64), ("rays_shadow", C.c_uint64), ("samples", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("device_ms", C.c_double), ("trace_ms", C.c_double), ("trace_launches", C.c_uint64), ("max_bounce_reached", C.c_uint64),
-                ("static_blas_builds", C.c_uint64), ("tlas_builds", C.c_uint64), ("tlas_refits", C.c_uint64)]
+                ("static_blas_builds", C.c_uint64), ("tlas_builds", C.c_uint64), ("tlas_refits", C.c_uint64), ("sort_ms", C.c_double)]
 
 
 class MsneClickData(C.Structure):   # input.hlsl:1-6
@@ -115,6 +115,7 @@ SIGNATURES = {
     "HdMoonshineExtGetSensorDevicePtr": (_VP, [_VP, _U32]),
     "HdMoonshineExtSetTileShard": (C.c_bool, [_VP, _U32, _U32]),
     "HdMoonshineExtSetPathsInFlight": (None, [_VP, C.c_uint64]),
+    "HdMoonshineExtSetRaySorting": (None, [_VP, C.c_uint64]),
     "HdMoonshineExtSetProfiling": (None, [_VP, C.c_bool]),
     "HdMoonshineExtGetStats": (None, [_VP, C.POINTER(MsneStats)]),
     "HdMoonshineExtResetStats": (None, [_VP]),
@@ -286,6 +287,7 @@ class HdMoonshine:
             raise ValueError("HdMoonshineExtSetTileShard: " + self.last_error())
 
     def SetPathsInFlight(self, n: int): self.L.HdMoonshineExtSetPathsInFlight(self.h, n)
+    def SetRaySorting(self, min_rays: int): self.L.HdMoonshineExtSetRaySorting(self.h, min_rays)
     def SetProfiling(self, on: bool): self.L.HdMoonshineExtSetProfiling(self.h, bool(on))
 
     def GetStats(self) -> MsneStats:
@@ -378,12 +380,14 @@ class HdMoonshine:
         return a
 
 
-def render_scene(scene, n_launches: int = 1, device: int = 0, paths_in_flight: Optional[int] = None, shard=None):
+def render_scene(scene, n_launches: int = 1, device: int = 0, paths_in_flight: Optional[int] = None, shard=None, ray_sorting: Optional[int] = None):
     """Load a scenes.Scene into a fresh HdMoonshine, render `n_launches` launches, return (image HxWx4, stats, obj)."""
     from . import scenes as _sc
     m = HdMoonshine(device)
     if paths_in_flight:
         m.SetPathsInFlight(paths_in_flight)
+    if ray_sorting is not None:
+        m.SetRaySorting(ray_sorting)
     _sc.load_scene(m, scene)
     if shard:
         m.SetTileShard(*shard)

@@ -133,6 +133,17 @@ def test_wave_chunking_is_bitwise_invariant():
     np.testing.assert_array_equal(a.view(np.uint32), c.view(np.uint32))
 
 
+def test_ray_sorting_is_bitwise_invariant():
+    """Sorted bounces (radix sort by direction octant + origin cell, k_bin) change the order rays are traced in, never a
+    result: every bounce sorted == never sorted, bit for bit, with transformed instances (two-level) and without."""
+    for sc in (scenes.material_zoo((48, 32)), scenes.cornell_box((40, 40)), scenes.mesh_light_stress(6, (32, 32))):
+        a, sa, _ = gpu_render(sc, 4, ray_sorting=0)
+        b, sb, _ = gpu_render(sc, 4, ray_sorting=1)
+        np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))
+        assert (sa.rays_closest, sa.rays_shadow) == (sb.rays_closest, sb.rays_shadow)
+        assert sb.kernel_launches > sa.kernel_launches   # the sort really ran
+
+
 def test_tile_shards_sum_to_the_unsharded_image():
     sc = scenes.material_zoo((96, 64))
     full, _, _ = gpu_render(sc, 3)
