@@ -28,13 +28,8 @@ namespace msne {
 #ifndef MSNE_STREAM_HINTS
 #define MSNE_STREAM_HINTS 1
 #endif
-// MSNE_SHADE_PREFETCH = 1 (L2) / 2 (L1): k_shade prefetches the path state of its NEXT grid-stride item while it shades the
-// current one (the slot index is fetched two items ahead so that the prefetch never waits for it).
 #ifndef MSNE_SORT_KEY
 #define MSNE_SORT_KEY 0   // 0: octant-major key, 1: origin-cell-major key (measurement variant)
-#endif
-#ifndef MSNE_SHADE_PREFETCH
-#define MSNE_SHADE_PREFETCH 0
 #endif
 // (2 = loads only, 3 = stores only: measurement variants)
 #if MSNE_STREAM_HINTS == 1 || MSNE_STREAM_HINTS == 2
@@ -55,13 +50,6 @@ DI void qst(float4* p, float4 v) { *p = v; }
 DI void qst(uint4* p, uint4 v) { *p = v; }
 DI void qst(uint32_t* p, uint32_t v) { *p = v; }
 #endif
-DI void prefetchQueue(const void* p) {
-#if MSNE_SHADE_PREFETCH == 2
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#else
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#endif
-}
 
 // ------------------------------------------------------------------------------------------------
 // generate
@@ -145,12 +133,13 @@ DI uint32_t hitBin(const DeviceScene& sc, const HitRec& h) {
 // of this bounce, every lane walks its ray to the end (traverse.cuh), then the warp sorts its hits by material type.
 // Refilling idle lanes before the whole ticket is done ("dynamic fetch") was measured in three variants and is not
 // used (profiles/r01_sweeps.md).
-// SORTED: the tickets walk `perm` (k_sort_keys + radix sort: rays ordered by direction octant and origin cell, extension rays
-// first) instead of the queue order, so the 32 rays of a warp visit the same part of the tree; the material binning is then
+// SORTED: the tickets walk the permutations of the extension and the shadow queue (radix sort of the keys the shade pass wrote:
+// rays ordered by direction octant and origin cell) instead of the queue order, so the 32 rays of a warp visit the same part of the tree; the material binning is then
 // done by k_bin in queue order (the shade kernels keep reading contiguous path state).
 template <bool TWO_LEVEL, bool SORTED>
 __global__ void __launch_bounds__(TRACE_THREADS, TWO_LEVEL ? TRACE_BLOCKS_PER_SM : TRACE1_BLOCKS_PER_SM) k_trace(DeviceScene sc, PathBuffers pb, WaveState ws, uint32_t buf,
-                                                                                                               const uint32_t* __restrict__ perm) {
+                                                                                                               const uint32_t* __restrict__ permExt,
+                                                                                                               const uint32_t* __restrict__ permShadow) {
     const Counters cin = ws.counters[buf];
     const uint32_t nLive = cin.nLive, total = cin.nLive + cin.nShadow;
     const uint32_t lane = threadIdx.x & 31;
@@ -184,7 +173,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, TWO_LEVEL ? TRACE_BLOCKS_PER_SM
         if (lane == 0) base = atomicAdd(ws.traceTicket, 32u);
         base = __shfl_sync(0xFFFFFFFFu, base, 0);
         if (base >= total) break;
-        const uint32_t idx = !SORTED ? base + lane : (base + lane < total ? __ldg(perm + base + lane) : 0xFFFFFFFFu);
+        uint32_t idx = base + lane;
+        if (SORTED) idx = idx < nLive ? __ldg(permExt + idx) : (idx < total ? nLive + __ldg(permShadow + (idx - nLive)) : 0xFFFFFFFFu);
         uint32_t bin = 0xFFu;
         if (idx < nLive) {
             const float4 r0 = qld(pb.R0[buf] + idx), r1 = qld(pb.R1[buf] + idx);
@@ -230,29 +220,23 @@ __global__ void __launch_bounds__(TRACE_THREADS, TWO_LEVEL ? TRACE_BLOCKS_PER_SM
 // ------------------------------------------------------------------------------------------------
 // ray reordering for incoherent bounces (runtime.cpp: only queues above the sort threshold)
 // ------------------------------------------------------------------------------------------------
-// 16-bit key per ray of the joint index space: [15] shadow ray, [14:12] direction octant, [11:0] origin cell (z, y, x cell
-// coordinates concatenated; thousands of rays share a key, so the order BETWEEN cells is immaterial). Only the order in which
-// rays are traced depends on it - never a result.
-__global__ void __launch_bounds__(256) k_sort_keys(PathBuffers pb, WaveState ws, uint32_t buf, SortFrame f, uint16_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-    const Counters cin = ws.counters[buf];
-    const uint32_t nLive = cin.nLive, total = cin.nLive + cin.nShadow;
-    const float mx = (float)((1u << f.bits[0]) - 1u), my = (float)((1u << f.bits[1]) - 1u), mz = (float)((1u << f.bits[2]) - 1u);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const bool shadow = i >= nLive;
-        const float4 o = shadow ? pb.Q0[i - nLive] : pb.R0[buf][i];
-        const float4 d = shadow ? pb.Q1[i - nLive] : pb.R1[buf][i];
-        const uint32_t cx = (uint32_t)fminf(fmaxf((o.x - f.lo[0]) * f.scale[0], 0.0f), mx);
-        const uint32_t cy = (uint32_t)fminf(fmaxf((o.y - f.lo[1]) * f.scale[1], 0.0f), my);
-        const uint32_t cz = (uint32_t)fminf(fmaxf((o.z - f.lo[2]) * f.scale[2], 0.0f), mz);
-        const uint32_t oct = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
-        const uint32_t cell = (((cz << f.bits[1]) | cy) << f.bits[0]) | cx;
+// 16-bit key of a queued ray: [14:12] direction octant, [11:0] origin cell (z, y, x cell coordinates concatenated; thousands of
+// rays share a key, so the order BETWEEN cells is immaterial). Only the order in which rays are traced depends on it - never
+// a result. Written by the shade kernels next to the ray itself (2 B per ray instead of a pass that re-reads 32 B per ray).
+DI uint16_t rayKey(const SortFrame& f, float4 o, float4 d) {
+    const uint32_t cx = (uint32_t)fminf(fmaxf((o.x - f.lo[0]) * f.scale[0], 0.0f), (float)((1u << f.bits[0]) - 1u));
+    const uint32_t cy = (uint32_t)fminf(fmaxf((o.y - f.lo[1]) * f.scale[1], 0.0f), (float)((1u << f.bits[1]) - 1u));
+    const uint32_t cz = (uint32_t)fminf(fmaxf((o.z - f.lo[2]) * f.scale[2], 0.0f), (float)((1u << f.bits[2]) - 1u));
+    const uint32_t oct = (d.x < 0.0f ? 1u : 0u) | (d.y < 0.0f ? 2u : 0u) | (d.z < 0.0f ? 4u : 0u);
+    const uint32_t cell = (((cz << f.bits[1]) | cy) << f.bits[0]) | cx;
 #if MSNE_SORT_KEY == 1
-        keys[i] = (uint16_t)((shadow ? 0x8000u : 0u) | (cell << 3) | oct);
+    return (uint16_t)((cell << 3) | oct);
 #else
-        keys[i] = (uint16_t)((shadow ? 0x8000u : 0u) | (oct << 12) | cell);
+    return (uint16_t)((oct << 12) | cell);
 #endif
-        vals[i] = i;
-    }
+}
+__global__ void k_iota(uint32_t* dst, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = (uint32_t)i;
 }
 // Material binning in queue order for sorted bounces (the epilogue of the unsorted k_trace as a streaming pass over the bins
 // k_trace left in H.y). A warp owns 512 consecutive slots: it counts its bins first, reserves each bin's range with ONE atomic
@@ -531,7 +515,7 @@ DI void shadeOne(const DeviceScene& sc, const DConstants& k, const PathBuffers& 
 // small queues, one launch per bounce). BIN = 0..4: only the slots the trace kernel binned under that material type
 // (4 = misses + the dead range); five such launches cover a bounce with material-specialised, convergent code.
 template <int BIN, int MIN_BLOCKS>
-__global__ void __launch_bounds__(SHADE_THREADS, MIN_BLOCKS) k_shade(DeviceScene sc, DConstants k, PathBuffers pb, WaveState ws, uint32_t buf, uint32_t lastOfBounce) {
+__global__ void __launch_bounds__(SHADE_THREADS, MIN_BLOCKS) k_shade(DeviceScene sc, DConstants k, PathBuffers pb, WaveState ws, uint32_t buf, uint32_t lastOfBounce, SortKeys keys) {
     const Counters cin = ws.counters[buf];
     Counters* cout = ws.counters + (buf ^ 1u);
     const uint32_t P = pb.capacity;
@@ -547,29 +531,12 @@ __global__ void __launch_bounds__(SHADE_THREADS, MIN_BLOCKS) k_shade(DeviceScene
     // every lane of a warp runs the same number of iterations so the ballots below are convergent
     // queue slot of grid-stride item i: list entry, or the dead range filled from the top of the buffer
     auto slotOf = [&](uint32_t i) -> uint32_t { return i < nList ? (BIN < 0 ? i : qld(list + i)) : (P - 1u - (i - nList)); };
-#if MSNE_SHADE_PREFETCH
-    const uint32_t first = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t qCur = first < total ? slotOf(first) : 0u;                      // this item
-    uint32_t qNext = first + stride < total ? slotOf(first + stride) : 0u;   // next item: its path state is prefetched below
-#endif
     for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < total; base += stride) {
         const uint32_t i = base + lane;
         ShadeOut out;
         out.kind = 0; out.envRay = false; out.meshRay = false;
-#if MSNE_SHADE_PREFETCH
-        const uint32_t q = qCur;
-        qCur = qNext;
-        if (i + stride < total) {
-            prefetchQueue(pb.R0[buf] + qNext); prefetchQueue(pb.R1[buf] + qNext); prefetchQueue(pb.S0[buf] + qNext); prefetchQueue(pb.S1[buf] + qNext);
-            prefetchQueue(pb.N0[buf] + qNext); prefetchQueue(pb.N1[buf] + qNext); prefetchQueue(pb.H + qNext);
-        }
-        // issued now, consumed by the prefetch of the next iteration
-        qNext = i + 2u * stride < total ? slotOf(i + 2u * stride) : 0u;   // total <= 2 P < 2^31: no wrap
-#endif
         if (i < total) {
-#if !MSNE_SHADE_PREFETCH
             const uint32_t q = slotOf(i);
-#endif
             uint32_t b;
             shadeOne<BIN>(sc, k, pb, buf, q, out, b);
             localMaxBounce = max(localMaxBounce, b);
@@ -592,15 +559,18 @@ __global__ void __launch_bounds__(SHADE_THREADS, MIN_BLOCKS) k_shade(DeviceScene
             const uint32_t oq = out.kind == 1 ? liveBase + __popc(liveMask & ltMask) : P - 1u - (deadBase + __popc(deadMask & ltMask));
             qst(pb.R0[ob] + oq, out.R0); qst(pb.R1[ob] + oq, out.R1); qst(pb.S0[ob] + oq, out.S0); qst(pb.S1[ob] + oq, out.S1);
             qst(pb.N0[ob] + oq, out.N0); qst(pb.N1[ob] + oq, out.N1);
+            if (keys.ext != nullptr && out.kind == 1) keys.ext[oq] = rayKey(keys.frame, out.R0, out.R1);
             if (out.envRay) {
                 const uint32_t si = shadowBase + __popc(envMask & ltMask);
                 out.envQ1.w = __uint_as_float(oq * 2u + 0u);
                 qst(pb.Q0 + si, out.envQ0); qst(pb.Q1 + si, out.envQ1);
+                if (keys.ext != nullptr) keys.shadow[si] = rayKey(keys.frame, out.envQ0, out.envQ1);
             }
             if (out.meshRay) {
                 const uint32_t si = shadowBase + __popc(envMask) + __popc(meshMask & ltMask);
                 out.meshQ1.w = __uint_as_float(oq * 2u + 1u);
                 qst(pb.Q0 + si, out.meshQ0); qst(pb.Q1 + si, out.meshQ1);
+                if (keys.ext != nullptr) keys.shadow[si] = rayKey(keys.frame, out.meshQ0, out.meshQ1);
             }
         }
     }
@@ -772,31 +742,29 @@ void launchTrace(cudaStream_t st, int blocks, const DeviceScene& sc, const PathB
     static const size_t smemBytes = MSNE_TRACE_SMEM_NODES * sizeof(BvhNode2) + 16;
     static const cudaError_t attr = cudaFuncSetAttribute(k_trace<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
     (void)attr;
-    if (sc.staticOnly) k_trace<false, false><<<blocks, TRACE_THREADS, smemBytes, st>>>(sc, pb, ws, buf, nullptr);
+    if (sc.staticOnly) k_trace<false, false><<<blocks, TRACE_THREADS, smemBytes, st>>>(sc, pb, ws, buf, nullptr, nullptr);
 #else
-    if (sc.staticOnly) k_trace<false, false><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf, nullptr);
+    if (sc.staticOnly) k_trace<false, false><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf, nullptr, nullptr);
 #endif
-    else k_trace<true, false><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf, nullptr);
+    else k_trace<true, false><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf, nullptr, nullptr);
 }
-// sorted bounce: keys -> radix sort (16-bit keys, queue index as value) -> trace through the permutation -> binning pass
+// sorted bounce: radix sort of the keys the previous shade pass wrote (16-bit keys, queue index as value; extension and
+// shadow queue separately) -> trace through the permutations -> binning pass
 size_t sortTempBytes(size_t maxItems) {
     size_t bytes = 0;
-    cub::DoubleBuffer<uint16_t> k(nullptr, nullptr);
-    cub::DoubleBuffer<uint32_t> v(nullptr, nullptr);
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, k, v, (uint64_t)maxItems, 0, 16);
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint16_t*)nullptr, (uint16_t*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, (uint64_t)maxItems, 0, 16);
     return bytes;
 }
-const uint32_t* launchSortRays(cudaStream_t st, int smCount, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const SortFrame& frame, uint32_t nItems,
-                               uint16_t* keys0, uint16_t* keys1, uint32_t* vals0, uint32_t* vals1, void* temp, size_t tempBytes) {
-    k_sort_keys<<<smCount * 8, 256, 0, st>>>(pb, ws, buf, frame, keys0, vals0);
-    cub::DoubleBuffer<uint16_t> k(keys0, keys1);
-    cub::DoubleBuffer<uint32_t> v(vals0, vals1);
-    cub::DeviceRadixSort::SortPairs(temp, tempBytes, k, v, (uint64_t)nItems, 0, 16, st);
-    return v.Current();
+void launchIota(cudaStream_t st, uint32_t* dst, size_t n) { k_iota<<<1024, 256, 0, st>>>(dst, n); }
+void launchSortRays(cudaStream_t st, const SortBuffers& sb, uint32_t nExt, uint32_t nShadow) {
+    size_t bytes = sb.tempBytes;
+    if (nExt) cub::DeviceRadixSort::SortPairs(sb.temp, bytes, (const uint16_t*)sb.keysExt, sb.keysTmp, sb.iota, sb.permExt, (uint64_t)nExt, 0, 15, st);
+    bytes = sb.tempBytes;
+    if (nShadow) cub::DeviceRadixSort::SortPairs(sb.temp, bytes, (const uint16_t*)sb.keysShadow, sb.keysTmp, sb.iota, sb.permShadow, (uint64_t)nShadow, 0, 15, st);
 }
-void launchTraceSorted(cudaStream_t st, int blocks, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const uint32_t* perm) {
-    if (sc.staticOnly) k_trace<false, true><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf, perm);
-    else k_trace<true, true><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf, perm);
+void launchTraceSorted(cudaStream_t st, int blocks, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const uint32_t* permExt, const uint32_t* permShadow) {
+    if (sc.staticOnly) k_trace<false, true><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf, permExt, permShadow);
+    else k_trace<true, true><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf, permExt, permShadow);
 }
 void launchBin(cudaStream_t st, int smCount, const PathBuffers& pb, const WaveState& ws, uint32_t buf) { k_bin<<<smCount * 8, 256, 0, st>>>(pb, ws, buf); }
 // Register caps (measured, profiles/r01_sweeps.md): the all-material kernel runs best at 80 registers
@@ -804,16 +772,16 @@ void launchBin(cudaStream_t st, int smCount, const PathBuffers& pb, const WaveSt
 #ifndef SHADE_MINB
 #define SHADE_MINB 6
 #endif
-void launchShade(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf) {
-    k_shade<-1, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, 1u);
+void launchShade(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const SortKeys& keys) {
+    k_shade<-1, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, 1u, keys);
 }
 // one launch per material bin; the miss/dead bin goes last and clears the bounce's counters
-void launchShadeBinned(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf) {
-    k_shade<3, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, 0u);   // StandardPBR
-    k_shade<1, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, 0u);   // Lambert
-    k_shade<0, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, 0u);   // Glass
-    k_shade<2, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, 0u);   // PerfectMirror
-    k_shade<4, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, 1u);   // miss + dead
+void launchShadeBinned(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const SortKeys& keys) {
+    k_shade<3, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, 0u, keys);   // StandardPBR
+    k_shade<1, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, 0u, keys);   // Lambert
+    k_shade<0, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, 0u, keys);   // Glass
+    k_shade<2, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, 0u, keys);   // PerfectMirror
+    k_shade<4, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, 1u, keys);   // miss + dead
 }
 void launchTail(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf) {
     k_tail<<<blocks, 128, 0, st>>>(sc, k, pb, ws, buf);

@@ -27,17 +27,25 @@ namespace msne {
 void launchGenerate(cudaStream_t st, const DCamera& cam, const DConstants& k, const PathBuffers& pb, Counters* counters, const uint32_t* pixIds,
                     uint32_t nPix, uint32_t nSamples, uint32_t firstSample);
 void launchTrace(cudaStream_t st, int blocks, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf);
-// ray reordering (kernels.cu k_sort_keys / k_bin): origin cell = (o - lo) * scale in a grid of 2^bits[a] cells per axis over the
-// scene bounds; 3 bits per axis + 3 dealt out to the axes with the longest cells (runtime.cpp buildTlas)
+// Ray reordering for incoherent bounces. The shade kernels emit a 16-bit key per ray they queue (kernels.cu rayKey: origin cell
+// = (o - lo) * scale in a grid of 2^bits[a] cells per axis over the scene bounds, 3 bits per axis + 3 dealt out to the axes with
+// the longest cells, runtime.cpp buildTlas); launchSortRays radix-sorts extension and shadow rays, k_trace walks the two
+// permutations and k_bin re-lists the hits per material in queue order.
 struct SortFrame { float lo[3], scale[3]; uint32_t bits[3]; };
+struct SortKeys { uint16_t* ext; uint16_t* shadow; SortFrame frame; };   // ext == nullptr: the shade pass writes no keys
+struct SortBuffers {          // sized for P extension + 2 P shadow rays (runtime.cpp ensureSortBuffers)
+    uint16_t* keysExt; uint16_t* keysShadow; uint16_t* keysTmp;
+    const uint32_t* iota;     // 0, 1, 2, ... (2 P entries)
+    uint32_t* permExt; uint32_t* permShadow;
+    void* temp; size_t tempBytes;
+};
 size_t sortTempBytes(size_t maxItems);
-// sorted bounce = launchSortRays (keys + 16-bit radix sort; returns the permutation) -> launchTraceSorted -> launchBin
-const uint32_t* launchSortRays(cudaStream_t st, int smCount, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const SortFrame& frame, uint32_t nItems,
-                               uint16_t* keys0, uint16_t* keys1, uint32_t* vals0, uint32_t* vals1, void* temp, size_t tempBytes);
-void launchTraceSorted(cudaStream_t st, int blocks, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const uint32_t* perm);
+void launchIota(cudaStream_t st, uint32_t* dst, size_t n);
+void launchSortRays(cudaStream_t st, const SortBuffers& sb, uint32_t nExt, uint32_t nShadow);
+void launchTraceSorted(cudaStream_t st, int blocks, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const uint32_t* permExt, const uint32_t* permShadow);
 void launchBin(cudaStream_t st, int smCount, const PathBuffers& pb, const WaveState& ws, uint32_t buf);
-void launchShade(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf);
-void launchShadeBinned(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf);
+void launchShade(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const SortKeys& keys);
+void launchShadeBinned(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const SortKeys& keys);
 void launchTail(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf);
 void launchAccumulate(cudaStream_t st, const float4* result, float4* image, float4* runState, const uint32_t* pixIds, uint32_t nPix, uint32_t nSamples,
                       uint32_t firstSample, uint32_t spr);

@@ -222,9 +222,10 @@ struct HdMoonshine {
     DevBuf<Counters> dCounters;
     DevBuf<uint32_t> dScalars;       // [0] traceTicket [1] traceDone [2] shadeDone [3] maxBounce [4..8] typeCount [9..13] binDone
     DevBuf<uint32_t> poolTypeList;
-    // ray reordering (kernels.cu k_sort_keys): double-buffered 16-bit keys + queue indices over the joint index space (<= 3 P items)
-    DevBuf<uint16_t> sortKeys[2];
-    DevBuf<uint32_t> sortVals[2];
+    // ray reordering (kernels.h SortBuffers): keys of the extension (P) and the shadow queue (2 P), a scratch key buffer, the
+    // identity values and the two permutations
+    DevBuf<uint16_t> sortKeysExt, sortKeysShadow, sortKeysTmp;
+    DevBuf<uint32_t> sortIota, sortPermExt, sortPermShadow;
     DevBuf<uint8_t> sortTemp;
     uint64_t sortThreshold = 262144; // extension-ray queues at least this long are traced in sorted order (0 = never)
     bool sortAnyScene = false;       // false: only scenes with >= kSortMinNodes BVH nodes (a 36-triangle Cornell box loses 4 % to the sort)
@@ -743,7 +744,7 @@ struct HdMoonshine {
         poolBufs[14].alloc(P);
         poolH.alloc(P);
         poolTypeList.alloc((size_t)NUM_BINS * P);
-        sortKeys[0].release();   // sized with the pool (ensureSortBuffers)
+        sortKeysExt.release();   // sized with the pool (ensureSortBuffers)
         for (int b = 0; b < 2; b++) {
             pb.R0[b] = poolBufs[0 + b].p; pb.R1[b] = poolBufs[2 + b].p; pb.S0[b] = poolBufs[4 + b].p; pb.S1[b] = poolBufs[6 + b].p;
             pb.N0[b] = poolBufs[8 + b].p; pb.N1[b] = poolBufs[10 + b].p;
@@ -751,10 +752,16 @@ struct HdMoonshine {
         pb.Q0 = poolBufs[12].p; pb.Q1 = poolBufs[13].p; pb.result = poolBufs[14].p; pb.H = poolH.p; pb.typeList = poolTypeList.p; pb.capacity = P;
     }
     void ensureSortBuffers() {
-        const size_t items = (size_t)3 * pb.capacity;
-        if (sortKeys[0].n >= items) return;
-        for (int i = 0; i < 2; i++) { sortKeys[i].alloc(items); sortVals[i].alloc(items); }
-        sortTemp.alloc(sortTempBytes(items));
+        const size_t P = pb.capacity;
+        if (sortKeysExt.n >= P) return;
+        sortKeysExt.alloc(P); sortKeysShadow.alloc(2 * P); sortKeysTmp.alloc(2 * P);
+        sortIota.alloc(2 * P); sortPermExt.alloc(P); sortPermShadow.alloc(2 * P);
+        sortTemp.alloc(sortTempBytes(2 * P));
+        launchIota(stream, sortIota.p, 2 * P);
+        stats.kernel_launches++;
+    }
+    SortBuffers sortBuffers() const {
+        return SortBuffers{sortKeysExt.p, sortKeysShadow.p, sortKeysTmp.p, sortIota.p, sortPermExt.p, sortPermShadow.p, sortTemp.p, sortTemp.n};
     }
     WaveState waveState() const {
         WaveState ws{};
@@ -778,22 +785,24 @@ struct HdMoonshine {
             if (prof) profSorted[profUsed] = sorted;
             if (sorted) {
                 if (prof) CK(cudaEventRecord(profEv[profUsed][2], stream));
-                const uint32_t* perm = launchSortRays(stream, smCount, pb, ws, buf, sortFrame, in->nLive + in->nShadow, sortKeys[0].p, sortKeys[1].p, sortVals[0].p, sortVals[1].p,
-                                                      sortTemp.p, sortTemp.n);
+                launchSortRays(stream, sortBuffers(), in->nLive, in->nShadow);
                 if (prof) CK(cudaEventRecord(profEv[profUsed][0], stream));
-                launchTraceSorted(stream, traceBlocks, sc, pb, ws, buf, perm);
+                launchTraceSorted(stream, traceBlocks, sc, pb, ws, buf, sortPermExt.p, sortPermShadow.p);
                 if (prof) CK(cudaEventRecord(profEv[profUsed][1], stream));
                 launchBin(stream, smCount, pb, ws, buf);
                 if (prof) { CK(cudaEventRecord(profEv[profUsed][3], stream)); profUsed++; }
-                stats.kernel_launches += 6;   // keys, CUB histogram + exclusive sum + 2 onesweep passes, binning
+                stats.kernel_launches += (in->nLive ? 4 : 0) + (in->nShadow ? 4 : 0) + 1;   // per sort: CUB histogram + exclusive sum + 2 onesweep passes; binning
             } else {
                 if (prof) CK(cudaEventRecord(profEv[profUsed][0], stream));
                 launchTrace(stream, traceBlocks, sc, pb, ws, buf);
                 if (prof) { CK(cudaEventRecord(profEv[profUsed][1], stream)); profUsed++; }
             }
             // big queues: one material-specialised launch per bin; small queues (tail): one generic launch
-            if (lastLive >= binnedThreshold) { launchShadeBinned(stream, shadeBlocks, sc, k, pb, ws, buf); stats.kernel_launches += 6; }
-            else { launchShade(stream, shadeBlocks, sc, k, pb, ws, buf); stats.kernel_launches += 2; }
+            // the rays this pass queues get their sort keys from it when the next bounce may still be long enough to be sorted
+            SortKeys keys{};
+            if (sortActive && lastLive >= sortThreshold) { keys.ext = sortKeysExt.p; keys.shadow = sortKeysShadow.p; keys.frame = sortFrame; }
+            if (lastLive >= binnedThreshold) { launchShadeBinned(stream, shadeBlocks, sc, k, pb, ws, buf, keys); stats.kernel_launches += 6; }
+            else { launchShade(stream, shadeBlocks, sc, k, pb, ws, buf, keys); stats.kernel_launches += 2; }
             CK(cudaMemcpyAsync(&hostCounters[b & 3u], dCounters.p + (buf ^ 1u), sizeof(Counters), cudaMemcpyDeviceToHost, stream));
             CK(cudaEventRecord(bounceEvents[b & 3u], stream));
         };

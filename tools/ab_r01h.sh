@@ -1,15 +1,13 @@
 #!/bin/bash
-# Session-3: defaults (sorting on for big scenes, 128 Mi-path waves), adaptive sort grid
 mkdir -p gpurun_out
 ( timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 ) > gpurun_out/ab_tests.log
+( MSNE_SORT_THRESHOLD=1 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 ) >> gpurun_out/ab_tests.log
 cat gpurun_out/ab_tests.log
 {
 run() { echo "== $*"; env "$@" python bench.py --no-cpu-baseline --e2e-steps 0 $EXTRA 2>/dev/null | tail -1 | \
     python -c "import json,sys; d=json.loads(sys.stdin.read()); print(round(d['value'],1), 'Mrays/s', round(d['ms_per_step'],2), 'ms/step; k_trace avg launch', round(d['roofline']['avg_launch_ms'],3), 'ms, share', round(d['roofline']['kernel_share_of_step'],3), 'reorder', round(d['roofline']['reorder_share_of_step'],3), 'launches', d['gpu_launches'])"; }
-EXTRA="--workload cfg2 --batch-spp 64 --steps 8 --warmup 3" run A=cfg2
+EXTRA="--steps 4 --warmup 3" run A=cfg3
 EXTRA="--workload cfg5 --batch-spp 8 --steps 4 --warmup 3" run A=cfg5
-EXTRA="--workload cfg5 --batch-spp 8 --steps 4 --warmup 3" run MSNE_SORT_THRESHOLD=0
-EXTRA="--workload cfg5 --batch-spp 32 --steps 3 --warmup 3" run A=cfg5_128Mi
+EXTRA="--steps 4 --warmup 3" run A=cfg3again
 } > gpurun_out/ab_r01h.log 2>&1
 cat gpurun_out/ab_r01h.log
-python bench.py > gpurun_out/bench_cfg3_1gpu.json 2> gpurun_out/bench_cfg3_1gpu.err; tail -c 2500 gpurun_out/bench_cfg3_1gpu.json
