@@ -117,12 +117,17 @@ struct MsneClick { int32_t instance_index; uint32_t geometry_index, primitive_in
 
 // ---- wavefront pool ---------------------------------------------------------------------------
 // One path = six 16-byte lanes per ping-pong buffer (SoA arrays of float4, index q = queue slot):
-//   R0 = (origin.xyz, lastMaterialPdf)      R1 = (dir.xyz, bits: bounce | DELTA<<30 | DEAD<<31)
+//   R0 = (origin.xyz, lastMaterialPdf)      R1 = (dir.xyz, bits: bounce | DELTA<<30 | DEAD<<31)   (interleaved, RAY_STRIDE)
 //   S0 = (throughput.xyz, rng state bits)   S1 = (accumulated.xyz, result-slot bits)
 //   N0 = pending env-NEE contribution       N1 = pending mesh-NEE contribution (zeroed by the trace
 //        kernel when the shadow ray is occluded; folded into `accumulated` by the next shade pass)
 //   H  = hit record written by the trace kernel: (instanceIndex, triangle index | bin << 29, u bits, v bits)
 // Shadow queue: Q0 = (origin.xyz, tmax)  Q1 = (dir.xyz, bits: target q*2 + light)
+// The two lanes of a ray (R0/R1, and Q0/Q1 of a shadow ray) are interleaved in ONE array - R1 = R0 + 1, element q at index
+// RAY_STRIDE * q - so that a ray is one aligned 32-byte sector: sorted bounces gather rays by queue index, and a gathered
+// sector costs the same DRAM access whether 16 or 32 of its bytes are used. Streaming passes touch the same sectors as with
+// separate arrays.
+static const uint32_t RAY_STRIDE = 2;
 struct Counters { uint32_t nLive, nDead, nShadow, pad; };
 
 struct PathBuffers {

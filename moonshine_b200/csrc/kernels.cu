@@ -93,8 +93,8 @@ __global__ void __launch_bounds__(256) k_generate(DCamera cam, DConstants k, Pat
     const float2 r1 = rng.getFloat2();
     float3 o, d;
     cameraRay(cam, k, px, py, r0, r1, o, d);
-    pb.R0[0][p] = make_float4(o.x, o.y, o.z, 0.0f);
-    pb.R1[0][p] = make_float4(d.x, d.y, d.z, __uint_as_float(0u));
+    pb.R0[0][RAY_STRIDE * (size_t)p] = make_float4(o.x, o.y, o.z, 0.0f);
+    pb.R1[0][RAY_STRIDE * (size_t)p] = make_float4(d.x, d.y, d.z, __uint_as_float(0u));
     pb.S0[0][p] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(rng.state));
     pb.S1[0][p] = make_float4(0.0f, 0.0f, 0.0f, __uint_as_float(p));
     pb.N0[0][p] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TWO_LEVEL ? TRACE_BLOCKS_PER_SM
         if (SORTED) idx = idx < nLive ? __ldg(permExt + idx) : (idx < total ? nLive + __ldg(permShadow + (idx - nLive)) : 0xFFFFFFFFu);
         uint32_t bin = 0xFFu;
         if (idx < nLive) {
-            const float4 r0 = qld(pb.R0[buf] + idx), r1 = qld(pb.R1[buf] + idx);
+            const float4 r0 = qld(pb.R0[buf] + RAY_STRIDE * (size_t)idx), r1 = qld(pb.R1[buf] + RAY_STRIDE * (size_t)idx);
             HitRec h;
             traceRay<false, TWO_LEVEL>(sc, mk3(r0.x, r0.y, r0.z), mk3(r1.x, r1.y, r1.z), 0.0f, MS_INFINITY, h, smemTop);
             bin = hitBin(sc, h);
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TWO_LEVEL ? TRACE_BLOCKS_PER_SM
             // repeating the instance -> geometry -> material chain
             qst(pb.H + idx, make_uint4(h.inst, h.tri | (bin << H_BIN_SHIFT), __float_as_uint(h.u), __float_as_uint(h.v)));
         } else if (idx < total) {
-            const float4 q0 = qld(pb.Q0 + (idx - nLive)), q1 = qld(pb.Q1 + (idx - nLive));
+            const float4 q0 = qld(pb.Q0 + RAY_STRIDE * (size_t)(idx - nLive)), q1 = qld(pb.Q1 + RAY_STRIDE * (size_t)(idx - nLive));
             HitRec h;
             if (traceRay<true, TWO_LEVEL>(sc, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), 0.0f, q0.w, h, smemTop)) {
                 const uint32_t target = __float_as_uint(q1.w);
@@ -332,7 +332,7 @@ struct ShadeOut {
 // MT: -1 = any (runtime dispatch), 0..3 = MaterialType known at compile time, 4 = miss / dead paths only
 template <int MT>
 DI void shadeOne(const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, uint32_t buf, uint32_t q, ShadeOut& out, uint32_t& bounceOut) {
-    const float4 R0 = qld(pb.R0[buf] + q), R1 = qld(pb.R1[buf] + q), S0 = qld(pb.S0[buf] + q), S1 = qld(pb.S1[buf] + q);
+    const float4 R0 = qld(pb.R0[buf] + RAY_STRIDE * (size_t)q), R1 = qld(pb.R1[buf] + RAY_STRIDE * (size_t)q), S0 = qld(pb.S0[buf] + q), S1 = qld(pb.S1[buf] + q);
     const float4 N0 = qld(pb.N0[buf] + q), N1 = qld(pb.N1[buf] + q);
     const uint32_t flags = __float_as_uint(R1.w);
     const uint32_t bounceCount = flags & BOUNCE_MASK;
@@ -557,19 +557,19 @@ __global__ void __launch_bounds__(SHADE_THREADS, MIN_BLOCKS) k_shade(DeviceScene
         shadowBase = __shfl_sync(0xFFFFFFFFu, shadowBase, 0);
         if (out.kind != 0) {
             const uint32_t oq = out.kind == 1 ? liveBase + __popc(liveMask & ltMask) : P - 1u - (deadBase + __popc(deadMask & ltMask));
-            qst(pb.R0[ob] + oq, out.R0); qst(pb.R1[ob] + oq, out.R1); qst(pb.S0[ob] + oq, out.S0); qst(pb.S1[ob] + oq, out.S1);
+            qst(pb.R0[ob] + RAY_STRIDE * (size_t)oq, out.R0); qst(pb.R1[ob] + RAY_STRIDE * (size_t)oq, out.R1); qst(pb.S0[ob] + oq, out.S0); qst(pb.S1[ob] + oq, out.S1);
             qst(pb.N0[ob] + oq, out.N0); qst(pb.N1[ob] + oq, out.N1);
             if (keys.ext != nullptr && out.kind == 1) keys.ext[oq] = rayKey(keys.frame, out.R0, out.R1);
             if (out.envRay) {
                 const uint32_t si = shadowBase + __popc(envMask & ltMask);
                 out.envQ1.w = __uint_as_float(oq * 2u + 0u);
-                qst(pb.Q0 + si, out.envQ0); qst(pb.Q1 + si, out.envQ1);
+                qst(pb.Q0 + RAY_STRIDE * (size_t)si, out.envQ0); qst(pb.Q1 + RAY_STRIDE * (size_t)si, out.envQ1);
                 if (keys.ext != nullptr) keys.shadow[si] = rayKey(keys.frame, out.envQ0, out.envQ1);
             }
             if (out.meshRay) {
                 const uint32_t si = shadowBase + __popc(envMask) + __popc(meshMask & ltMask);
                 out.meshQ1.w = __uint_as_float(oq * 2u + 1u);
-                qst(pb.Q0 + si, out.meshQ0); qst(pb.Q1 + si, out.meshQ1);
+                qst(pb.Q0 + RAY_STRIDE * (size_t)si, out.meshQ0); qst(pb.Q1 + RAY_STRIDE * (size_t)si, out.meshQ1);
                 if (keys.ext != nullptr) keys.shadow[si] = rayKey(keys.frame, out.meshQ0, out.meshQ1);
             }
         }
@@ -623,7 +623,7 @@ __global__ void __launch_bounds__(128) k_tail(DeviceScene sc, DConstants k, Path
                 if (traceRay<true, true>(sc, mk3(out.meshQ0.x, out.meshQ0.y, out.meshQ0.z), mk3(out.meshQ1.x, out.meshQ1.y, out.meshQ1.z), 0.0f, out.meshQ0.w, h))
                     out.N1 = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            pb.R0[buf][q] = out.R0; pb.R1[buf][q] = out.R1; pb.S0[buf][q] = out.S0; pb.S1[buf][q] = out.S1;
+            pb.R0[buf][RAY_STRIDE * (size_t)q] = out.R0; pb.R1[buf][RAY_STRIDE * (size_t)q] = out.R1; pb.S0[buf][q] = out.S0; pb.S1[buf][q] = out.S1;
             pb.N0[buf][q] = out.N0; pb.N1[buf][q] = out.N1;
             if (out.kind == 1) {
                 nClosest++;
