@@ -31,8 +31,19 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: NCCL's own log (e.g. the version banner under NCCL_DEBUG=VERSION) goes to stderr
+# stdout carries exactly ONE JSON line. Native libraries write there too (NCCL prints its version banner with printf when
+# NCCL_DEBUG is set in the environment), so file descriptor 1 is pointed at stderr for the whole run and the JSON line goes
+# to the saved descriptor (emit()).
 os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+sys.stdout.flush()
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 import numpy as np  # noqa: E402
 
@@ -157,7 +168,7 @@ def run_reference(args):
             "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "reference has no CPU path and cannot be built here (Zig/DXC/Vulkan-RT absent): this is the CPU oracle, a line-by-line restatement of its shaders"}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -317,7 +328,7 @@ def main():
                 "cpu_baseline": cpu, "rays": {"closest": int(st.rays_closest), "shadow": int(st.rays_shadow), "samples": int(st.samples), "max_bounce": max_bounce,
                                               "total_all_ranks": rays_total},
                 "reduce_ms": reduce_ms}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     m.Destroy()
