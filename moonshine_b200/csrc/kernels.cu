@@ -756,11 +756,14 @@ size_t sortTempBytes(size_t maxItems) {
     return bytes;
 }
 void launchIota(cudaStream_t st, uint32_t* dst, size_t n) { k_iota<<<1024, 256, 0, st>>>(dst, n); }
-void launchSortRays(cudaStream_t st, const SortBuffers& sb, uint32_t nExt, uint32_t nShadow) {
+cudaError_t launchSortRays(cudaStream_t st, const SortBuffers& sb, uint32_t nExt, uint32_t nShadow) {
+    cudaError_t err = cudaSuccess;
     size_t bytes = sb.tempBytes;
-    if (nExt) cub::DeviceRadixSort::SortPairs(sb.temp, bytes, (const uint16_t*)sb.keysExt, sb.keysTmp, sb.iota, sb.permExt, (uint64_t)nExt, 0, 15, st);
+    if (nExt) err = cub::DeviceRadixSort::SortPairs(sb.temp, bytes, (const uint16_t*)sb.keysExt, sb.keysTmp, sb.iota, sb.permExt, (uint64_t)nExt, 0, 15, st);
     bytes = sb.tempBytes;
-    if (nShadow) cub::DeviceRadixSort::SortPairs(sb.temp, bytes, (const uint16_t*)sb.keysShadow, sb.keysTmp, sb.iota, sb.permShadow, (uint64_t)nShadow, 0, 15, st);
+    if (nShadow && err == cudaSuccess)
+        err = cub::DeviceRadixSort::SortPairs(sb.temp, bytes, (const uint16_t*)sb.keysShadow, sb.keysTmp, sb.iota, sb.permShadow, (uint64_t)nShadow, 0, 15, st);
+    return err;
 }
 void launchTraceSorted(cudaStream_t st, int blocks, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const uint32_t* permExt, const uint32_t* permShadow) {
     if (sc.staticOnly) k_trace<false, true><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf, permExt, permShadow);

@@ -41,7 +41,7 @@ struct SortBuffers {          // sized for P extension + 2 P shadow rays (runtim
 };
 size_t sortTempBytes(size_t maxItems);
 void launchIota(cudaStream_t st, uint32_t* dst, size_t n);
-void launchSortRays(cudaStream_t st, const SortBuffers& sb, uint32_t nExt, uint32_t nShadow);
+cudaError_t launchSortRays(cudaStream_t st, const SortBuffers& sb, uint32_t nExt, uint32_t nShadow);
 void launchTraceSorted(cudaStream_t st, int blocks, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const uint32_t* permExt, const uint32_t* permShadow);
 void launchBin(cudaStream_t st, int smCount, const PathBuffers& pb, const WaveState& ws, uint32_t buf);
 void launchShade(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const SortKeys& keys);

@@ -788,7 +788,7 @@ struct HdMoonshine {
             if (prof) profSorted[profUsed] = sorted;
             if (sorted) {
                 if (prof) CK(cudaEventRecord(profEv[profUsed][2], stream));
-                launchSortRays(stream, sortBuffers(), in->nLive, in->nShadow);
+                CK(launchSortRays(stream, sortBuffers(), in->nLive, in->nShadow));
                 if (prof) CK(cudaEventRecord(profEv[profUsed][0], stream));
                 launchTraceSorted(stream, traceBlocks, sc, pb, ws, buf, sortPermExt.p, sortPermShadow.p);
                 if (prof) CK(cudaEventRecord(profEv[profUsed][1], stream));
