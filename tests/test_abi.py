@@ -35,6 +35,16 @@ def test_struct_layouts_match_reference_header():
     assert C.sizeof(hydra.MsneSpecConstants) == 28  # pipeline.zig:319-327
 
 
+def test_stats_struct_matches_the_header_field_for_field():
+    """MsneStats grows with the library: the ctypes mirror must list the header's fields in the header's order and width."""
+    txt = open(os.path.join(ROOT, "include", "moonshine_ext.h")).read()
+    body = re.search(r"typedef struct MsneStats \{(.*?)\} MsneStats;", txt, re.S).group(1)
+    declared = re.findall(r"^\s*(uint64_t|double)\s+(\w+);", body, re.M)
+    ctype = {"uint64_t": C.c_uint64, "double": C.c_double}
+    assert [(n, ctype[t]) for t, n in declared] == list(hydra.MsneStats._fields_)
+    assert C.sizeof(hydra.MsneStats) == 8 * len(declared)
+
+
 def test_no_gpu_means_loud_failure():
     import torch
     if torch.cuda.is_available():
