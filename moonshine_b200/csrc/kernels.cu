@@ -2,16 +2,19 @@
 // pipeline (shaders/hrtsystem/main.hlsl raygen/closesthit/miss/shadowmiss driven by vkCmdTraceRaysKHR,
 // engine/hrtsystem/pipeline.zig:269-271).
 //
-// One camera sample of one pixel = one path. Paths live in SoA float4 queues in HBM (dtypes.h) and move
+// One camera sample of one pixel = one path. Paths live in float4 queues in HBM (dtypes.h) and move
 // through two kernels per bounce:
 //
 //   k_trace  persistent threads; warps pull 32-ray tickets from ONE index space that holds this bounce's
 //            extension rays (closest hit -> H[q]) followed by the previous bounce's shadow rays (any hit ->
-//            zero the pending NEE contribution of path q when occluded).
+//            zero the pending NEE contribution of path q when occluded). Long queues are traced in sorted
+//            order (radix sort of the 15-bit direction-octant + origin-cell keys the shade pass wrote), and
+//            k_bin then re-lists the hits per material in queue order.
 //   k_shade  integrator.hlsl:68-183 for one bounce: fold pending NEE, emission (+MIS), termination /
 //            Russian roulette, env + mesh NEE sample generation (-> shadow queue), BSDF sample -> next
 //            extension ray; survivors are compacted into the other ping-pong buffer with warp-ballot
-//            aggregated atomics, finished paths write their radiance to result[slot].
+//            aggregated atomics, finished paths write their radiance to result[slot]. One launch per
+//            material bin (specialised code), one generic launch for short queues, k_tail for stragglers.
 //
 // k_generate starts a wave (main.hlsl:85-88), k_accumulate applies storeColor (main.hlsl:43-51) in sample
 // order. Compiled with -fmad=false (see device_math.cuh).

@@ -737,22 +737,22 @@ struct HdMoonshine {
     void ensurePool(uint64_t wanted) {
         const uint32_t P = (uint32_t)std::min<uint64_t>(wanted, 0x7FFFFFFFull / 4);
         if (pb.capacity >= P && pb.capacity != 0) return;
+        // poolBufs: [0],[1] interleaved ray lanes R0/R1 of the two ping-pong buffers (dtypes.h RAY_STRIDE), [2..9] S0,S1,N0,N1 x 2,
+        // [10] interleaved shadow-ray lanes Q0/Q1 (2 P rays), [11] result
         poolBufs.clear();
-        poolBufs.resize(12 + 2 + 1);
-        // [0],[1]: interleaved ray lanes R0/R1 of the two ping-pong buffers (2 P float4 each, dtypes.h RAY_STRIDE); [2],[3] unused;
-        // [12]: interleaved shadow-ray lanes Q0/Q1 (2 P rays x 2); [13] unused
+        poolBufs.resize(12);
         for (int i = 0; i < 2; i++) poolBufs[i].alloc((size_t)RAY_STRIDE * P);
-        for (int i = 4; i < 12; i++) poolBufs[i].alloc(P);
-        poolBufs[12].alloc((size_t)RAY_STRIDE * 2 * P);
-        poolBufs[14].alloc(P);
+        for (int i = 2; i < 10; i++) poolBufs[i].alloc(P);
+        poolBufs[10].alloc((size_t)RAY_STRIDE * 2 * P);
+        poolBufs[11].alloc(P);
         poolH.alloc(P);
         poolTypeList.alloc((size_t)NUM_BINS * P);
         sortKeysExt.release();   // sized with the pool (ensureSortBuffers)
         for (int b = 0; b < 2; b++) {
-            pb.R0[b] = poolBufs[0 + b].p; pb.R1[b] = poolBufs[0 + b].p + 1; pb.S0[b] = poolBufs[4 + b].p; pb.S1[b] = poolBufs[6 + b].p;
-            pb.N0[b] = poolBufs[8 + b].p; pb.N1[b] = poolBufs[10 + b].p;
+            pb.R0[b] = poolBufs[b].p; pb.R1[b] = poolBufs[b].p + 1; pb.S0[b] = poolBufs[2 + b].p; pb.S1[b] = poolBufs[4 + b].p;
+            pb.N0[b] = poolBufs[6 + b].p; pb.N1[b] = poolBufs[8 + b].p;
         }
-        pb.Q0 = poolBufs[12].p; pb.Q1 = poolBufs[12].p + 1; pb.result = poolBufs[14].p; pb.H = poolH.p; pb.typeList = poolTypeList.p; pb.capacity = P;
+        pb.Q0 = poolBufs[10].p; pb.Q1 = poolBufs[10].p + 1; pb.result = poolBufs[11].p; pb.H = poolH.p; pb.typeList = poolTypeList.p; pb.capacity = P;
     }
     void ensureSortBuffers() {
         const size_t P = pb.capacity;
