@@ -64,8 +64,15 @@ struct DMaterial {                                                            //
     uint32_t normal, emissive, type;
     uint32_t color, metalness, roughness;                                     // material.hlsl:186-190 / :146-147
     float ior;                                                                // material.hlsl:189 / :348-351
-    uint32_t pad;
+    // Resolved on the host (runtime.cpp resolveMaterials): bit s of constMask = texture slot s (MAT_SLOT_*) is a 1x1 image, whose
+    // SampleLevel is its only texel whatever the uv - that texel, decoded exactly as the sampler would, sits in constant[s].
+    // Most materials are built from solid textures (hydra's defaults, glTF factors), so a hit costs one 112-byte record instead
+    // of five descriptor -> texel -> table chains.
+    uint32_t constMask;
+    float constant[5][4];
 };
+static_assert(sizeof(DMaterial) == 112, "DMaterial is 112 B");
+enum MatSlot : uint32_t { MAT_SLOT_NORMAL = 0, MAT_SLOT_EMISSIVE, MAT_SLOT_COLOR, MAT_SLOT_METALNESS, MAT_SLOT_ROUGHNESS };
 struct DTexture { const void* data; uint32_t w, h, fmt, pad; };               // bindless dTextures[] (material.hlsl:3)
 struct DAlias { uint32_t alias; float select; uint32_t inst, geom, prim; };   // light.hlsl:17-22,105-109
 static_assert(sizeof(DAlias) == 20, "alias entry is 20 B (Accel.zig:51-55)");

@@ -385,9 +385,9 @@ DI void shadeOne(const DeviceScene& sc, const DConstants& k, const PathBuffers& 
     const DGeometry geometry = sc.geometries[instanceID + geometryIndex];
     const bool geomSampled = (geometry.sampled & 0xFFu) != 0;   // only the low byte is defined (Accel.zig:40-44)
     const MeshAttributes attrs = lookupAttributes(sc, k, instanceIndex, geometry.mesh, primitiveIndex, bary, tr);
-    const DMaterial dm = sc.materials[geometry.material];
+    const DMaterial& dm = sc.materials[geometry.material];   // read in place (112 B: header + resolved constants), field by field
     const Frame textureFrame = getTextureFrame(sc, k, dm, attrs.texcoord, attrs.frame);
-    const float3 emissiveLight = xyz(sampleTexture(sc, dm.emissive, attrs.texcoord));
+    const float3 emissiveLight = xyz(sampleMaterialSlot(sc, dm, MAT_SLOT_EMISSIVE, dm.emissive, attrs.texcoord));
     MaterialParams material = loadMaterial(sc, dm, attrs.texcoord);
     if (MT >= 0) material.type = (uint32_t)MT;   // compile-time constant: the other variants' code is pruned
 
@@ -467,7 +467,11 @@ DI void shadeOne(const DeviceScene& sc, const DConstants& k, const PathBuffers& 
 #else
                     const MeshAttributes la = lookupAttributes(sc, k, e.inst, lg.mesh, e.prim, lbary);
 #endif
-                    const float3 radiance = xyz(sampleTexture(sc, sc.materials[lg.material].emissive, la.texcoord));
+                    const DMaterial* lm = sc.materials + lg.material;
+                    float3 radiance;
+                    if (MSNE_MATERIAL_CONSTANTS && (__ldg(&lm->constMask) >> MAT_SLOT_EMISSIVE) & 1u)
+                        radiance = mk3(__ldg(&lm->constant[MAT_SLOT_EMISSIVE][0]), __ldg(&lm->constant[MAT_SLOT_EMISSIVE][1]), __ldg(&lm->constant[MAT_SLOT_EMISSIVE][2]));
+                    else radiance = xyz(sampleTexture(sc, __ldg(&lm->emissive), la.texcoord));
                     const float3 dirWs = normalize(la.position - attrs.position);
                     const float pdf = areaMeasureToSolidAngleMeasure(la.position, attrs.position, dirWs, la.triangleFrame.n) / sum;
                     if (pdf > 0.0f) {

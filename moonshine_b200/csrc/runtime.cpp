@@ -80,7 +80,7 @@ struct HostMesh {
     DevBuf<uint32_t> dIdx;
 };
 
-struct HostTexture { DevBuf<uint8_t> data; uint32_t w, h, fmt; };
+struct HostTexture { DevBuf<uint8_t> data; uint32_t w, h, fmt; uint8_t first[16]; };   // first = host copy of texel (0,0)
 
 struct HostInstance {
     float transform[12];
@@ -567,6 +567,47 @@ struct HdMoonshine {
         stats_tlas_builds++;
     }
 
+    // fetchTexel (shading.cuh) of texel (0,0) on the host: same table values, same conversions -> the bits the sampler returns
+    static void decodeFirstTexel(const HostTexture& t, float out[4]) {
+        auto unorm = [](uint8_t c) { return (float)c / 255.0f; };
+        auto half = [](uint16_t h) {
+            const uint32_t sign = (uint32_t)(h >> 15) << 31, e = (h >> 10) & 31u, m = h & 1023u;
+            uint32_t bits;
+            if (e == 0) {
+                if (m == 0) bits = sign;
+                else { int sh = 0; uint32_t mm = m; while (!(mm & 1024u)) { mm <<= 1; sh++; } bits = sign | ((uint32_t)(113 - sh) << 23) | ((mm & 1023u) << 13); }
+            } else if (e == 31) bits = sign | 0x7F800000u | (m << 13);
+            else bits = sign | ((e + 112u) << 23) | (m << 13);
+            float f; memcpy(&f, &bits, 4); return f;
+        };
+        float f[4] = {0, 0, 0, 0}; memcpy(f, t.first, 16);
+        uint16_t hh[4]; memcpy(hh, t.first, 8);
+        out[0] = out[1] = out[2] = 0.0f; out[3] = 1.0f;
+        switch (t.fmt) {
+            case TEX_R32F: out[0] = f[0]; break;
+            case TEX_RG32F: out[0] = f[0]; out[1] = f[1]; break;
+            case TEX_RGBA32F: out[0] = f[0]; out[1] = f[1]; out[2] = f[2]; out[3] = f[3]; break;
+            case TEX_R8_UNORM: out[0] = unorm(t.first[0]); break;
+            case TEX_RG8_UNORM: out[0] = unorm(t.first[0]); out[1] = unorm(t.first[1]); break;
+            case TEX_RGBA8_SRGB: out[0] = srgbToLinear(t.first[0]); out[1] = srgbToLinear(t.first[1]); out[2] = srgbToLinear(t.first[2]); out[3] = unorm(t.first[3]); break;
+            default: for (int i = 0; i < 4; i++) out[i] = half(hh[i]); break;   // TEX_RGBA16F
+        }
+    }
+    void resolveMaterials() {
+        for (DMaterial& m : materials) {
+            const uint32_t slots[5] = {m.normal, m.emissive, m.color, m.metalness, m.roughness};
+            m.constMask = 0;
+            for (int s = 0; s < 5; s++) {
+                for (int c = 0; c < 4; c++) m.constant[s][c] = 0.0f;
+                if (slots[s] >= textures.size()) continue;
+                const HostTexture& t = *textures[slots[s]];
+                if (t.w != 1 || t.h != 1) continue;
+                decodeFirstTexel(t, m.constant[s]);
+                m.constMask |= 1u << s;
+            }
+        }
+    }
+
     void syncScene() {
         if (tablesDirty) {
             std::vector<DMesh> dm(meshes.size());
@@ -575,6 +616,7 @@ struct HdMoonshine {
             std::vector<DTexture> dt(textures.size());
             for (size_t i = 0; i < textures.size(); i++) dt[i] = DTexture{textures[i]->data.p, textures[i]->w, textures[i]->h, textures[i]->fmt, 0};
             dTextures.upload(dt.data(), dt.size(), stream);
+            resolveMaterials();
             dMaterials.upload(materials.data(), materials.size(), stream);
             dGeometries.upload(geometries.data(), geometries.size(), stream);
             CK(cudaStreamSynchronize(stream));   // staging vectors die here
@@ -914,6 +956,8 @@ static uint32_t uploadTexture(HdMoonshine* h, const void* data, uint32_t w, uint
     auto t = std::make_unique<HostTexture>();
     t->w = w; t->h = hgt; t->fmt = fmt;
     const size_t bytes = (size_t)w * hgt * texelBytes(fmt);
+    memset(t->first, 0, sizeof(t->first));
+    if (bytes) memcpy(t->first, data, std::min<size_t>(texelBytes(fmt), sizeof(t->first)));
     t->data.alloc(bytes);
     CK(cudaMemcpyAsync(t->data.p, data, bytes, cudaMemcpyHostToDevice, h->stream));
     CK(cudaStreamSynchronize(h->stream));   // `data` is borrowed for the duration of the call

@@ -13,6 +13,9 @@
 #ifndef MSNE_POS_FROM_TRIREC
 #define MSNE_POS_FROM_TRIREC 1
 #endif
+#ifndef MSNE_MATERIAL_CONSTANTS
+#define MSNE_MATERIAL_CONSTANTS 1   // 1x1 material textures are read as constants of the material record (sampleMaterialSlot)
+#endif
 #ifndef MSNE_EMITTER_RECORDS
 #define MSNE_EMITTER_RECORDS 1   // mesh-light samples read the 64-byte per-entry record (emitterPoint) instead of the attribute chain
 #endif
@@ -118,6 +121,11 @@ float4 sampleTextureImpl(const DTexture* __restrict__ textures, const float* __r
     }
 }
 DI float4 sampleTexture(const DeviceScene& sc, uint32_t idx, float2 uv) { return sampleTextureImpl(sc.textures, sc.texLuts, idx, uv.x, uv.y); }
+// texture slot `slot` of a material: the host-resolved constant when the image is 1x1 (same bits as the sampler's result)
+DI float4 sampleMaterialSlot(const DeviceScene& sc, const DMaterial& dm, uint32_t slot, uint32_t idx, float2 uv) {
+    if (MSNE_MATERIAL_CONSTANTS && (__ldg(&dm.constMask) >> slot) & 1u) return __ldg(reinterpret_cast<const float4*>(dm.constant[slot]));
+    return sampleTexture(sc, idx, uv);
+}
 
 // ---- reflection_frame.hlsl:3-85 ------------------------------------------------------------------
 struct Frame {
@@ -292,12 +300,12 @@ DI MaterialParams loadMaterial(const DeviceScene& sc, const DMaterial& dm, float
     MaterialParams m;
     m.type = dm.type; m.color = mk3(0.0f); m.metalness = 0.0f; m.alpha = 0.001f; m.ior = dm.ior;
     if (dm.type == MAT_STANDARD_PBR) {                                                    // :192-199
-        m.color = xyz(sampleTexture(sc, dm.color, uv));
-        m.metalness = sampleTexture(sc, dm.metalness, uv).x;
-        const float roughness = sampleTexture(sc, dm.roughness, uv).x;
+        m.color = xyz(sampleMaterialSlot(sc, dm, MAT_SLOT_COLOR, dm.color, uv));
+        m.metalness = sampleMaterialSlot(sc, dm, MAT_SLOT_METALNESS, dm.metalness, uv).x;
+        const float roughness = sampleMaterialSlot(sc, dm, MAT_SLOT_ROUGHNESS, dm.roughness, uv).x;
         m.alpha = fmaxf(roughness * roughness, 0.001f);
     } else if (dm.type == MAT_LAMBERT) {                                                  // :149-155
-        m.color = xyz(sampleTexture(sc, dm.color, uv));
+        m.color = xyz(sampleMaterialSlot(sc, dm, MAT_SLOT_COLOR, dm.color, uv));
     }
     return m;
 }
@@ -312,7 +320,7 @@ DI float3 decodeNormal(float2 rg) {                                             
     return mk3(rg.x, rg.y, sqrtf(1.0f - clampf(dot(rg, rg), 0.0f, 1.0f)));
 }
 DI Frame getTextureFrame(const DeviceScene& sc, const DConstants& k, const DMaterial& dm, float2 uv, const Frame& tangentFrame) {   // :506-517
-    const float4 s = sampleTexture(sc, dm.normal, uv);
+    const float4 s = sampleMaterialSlot(sc, dm, MAT_SLOT_NORMAL, dm.normal, uv);
     const float3 nTs = k.two_component_normal ? decodeNormal(mk2(s.x, s.y)) : mk3(s.x, s.y, s.z);
     Frame f = tangentFrame;
     f.n = normalize(tangentFrame.frameToWorld(nTs));
