@@ -195,6 +195,30 @@ def test_hydra_per_corner_attributes_mode():
     assert within_tol_fraction(g, r) >= 0.998
 
 
+@pytest.mark.parametrize("indexed", [True, False])
+def test_textured_mesh_light_in_both_attribute_modes(indexed):
+    """Mesh-light samples read the per-alias-entry emitter record (vertices + texcoords): a Cornell box whose emitter has a
+    NON-constant emissive texture and explicit texcoords, looked up through the index buffer and per triangle corner."""
+    sc = scenes.cornell_box((40, 40))
+    light_mat = sc.materials[3]
+    tex = np.array([[[30, 2, 2, 1], [2, 30, 2, 1]], [[2, 2, 30, 1], [20, 20, 20, 1]]], np.float32)
+    light_mat.emissive = sc.raw_texture(tex, scenes.TEX_RGBA32F)
+    lm = sc.meshes[sc.instances[1].geometries[0][0]]
+    lm.texcoords = np.array([[0.1, 0.2], [0.9, 0.15], [0.8, 0.85], [0.2, 0.9]], np.float32)
+    sc.constants = scenes.Constants(indexed_attributes=indexed)
+    if not indexed:
+        for mesh in sc.meshes:
+            flat = mesh.indices.reshape(-1)
+            if mesh.normals is not None:
+                mesh.normals = mesh.normals[flat]
+            if mesh.texcoords is not None:
+                mesh.texcoords = mesh.texcoords[flat]
+    g, sg, _ = gpu_render(sc, 2)
+    r, _, _ = oracle_render(sc, 2)
+    assert sg.rays_shadow > 0
+    assert within_tol_fraction(g, r) >= 0.998
+
+
 def test_spec_constant_limits_are_rejected():
     m = hydra.HdMoonshine()
     c = scenes.Constants(env_samples_per_bounce=2)
