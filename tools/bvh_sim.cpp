@@ -185,6 +185,7 @@ int main(int argc, char** argv) {
     double totalCost = 0; uint64_t totalRays = 0;
     auto measure = [&](const char* name, const std::vector<Ray>& rays) {
         uint64_t nodes = 0, leaves = 0, tris = 0, warpNode = 0, warpTri = 0, warps = 0;
+        uint64_t laneHist[33] = {0};
         std::vector<Lane> L(32);
         for (size_t base = 0; base < rays.size(); base += 32) {
             const size_t cnt = std::min<size_t>(32, rays.size() - base);
@@ -192,12 +193,21 @@ int main(int argc, char** argv) {
             warps++;
             for (;;) {
                 int mN = 0, mT = 0; bool any = false;
-                for (size_t i = 0; i < cnt; i++) if (L[i].node != END) { any = true; mN = std::max(mN, innerPhase(L[i], sc)); }
+                int steps[32]; int nAct = 0;
+                for (size_t i = 0; i < cnt; i++) { steps[i] = 0; if (L[i].node != END) { any = true; steps[i] = innerPhase(L[i], sc); mN = std::max(mN, steps[i]); nAct++; } }
                 if (!any) break;
+                // active-lane histogram of the node steps of this phase: step k of the phase is executed by the lanes with steps > k
+                for (int k = 0; k < mN; k++) { int a = 0; for (size_t i = 0; i < cnt; i++) a += steps[i] > k; laneHist[a]++; }
                 for (size_t i = 0; i < cnt; i++) if (L[i].node != END) mT = std::max(mT, leafPhase(L[i], sc));
                 warpNode += mN; warpTri += mT;
             }
             for (size_t i = 0; i < cnt; i++) { nodes += L[i].nodes; leaves += L[i].leaves; tris += L[i].tris; }
+        }
+        if (getenv("MSNE_SIM_HIST")) {
+            uint64_t tot = 0; for (int a = 0; a <= 32; a++) tot += laneHist[a];
+            uint64_t acc = 0; printf("   node steps by active lanes (cumulative %%):");
+            for (int a = 1; a <= 32; a++) { acc += laneHist[a]; if (a == 1 || a == 2 || a == 4 || a == 8 || a == 16 || a == 24 || a == 32) printf(" <=%d: %.0f", a, 100.0 * acc / tot); }
+            printf("\n");
         }
         const double nr = (double)rays.size();
         const double cost = (warpNode * CN + warpTri * CT);
