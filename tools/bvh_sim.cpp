@@ -113,8 +113,94 @@ static void walk(Lane& L, const Scene& sc) { while (L.node != END) { innerPhase(
 
 struct Rng { uint32_t s; float f() { s = s * 747796405u + 2891336453u; uint32_t w = ((s >> ((s >> 28) + 4)) ^ s) * 277803737u; return float(((w >> 22) ^ w) >> 8) * 0x1p-24f; } };
 
+// --selftest: builder invariants on a random triangle soup (run by tests/test_bvh_host.py, no GPU involved)
+//   every item sits in exactly one leaf, leaves hold 1..maxLeaf items, every child box contains its items, depth <= 72 (the
+//   single-level kernel's stack needs no overflow test), the while-while walk finds the brute-force closest hit for random
+//   rays, and reorderTopBfs is a pure relabelling (same hits, first k nodes in breadth-first order).
+static int selftest() {
+    Rng rng{4242};
+    int failures = 0;
+    for (uint32_t maxLeaf : {1u, 3u, 8u}) {
+        for (uint32_t n : {1u, 2u, 7u, 500u, 20000u}) {
+            std::vector<float> tri((size_t)n * 9);
+            for (uint32_t i = 0; i < n; i++) {
+                const float c[3] = {rng.f() * 10 - 5, rng.f() * 10 - 5, rng.f() * 2 - 1};
+                const float sz = i % 97 == 0 ? 3.0f : 0.15f;   // a few large triangles among many small ones
+                for (int v = 0; v < 3; v++) for (int a = 0; a < 3; a++) tri[(size_t)i * 9 + v * 3 + a] = c[a] + (rng.f() - 0.5f) * sz;
+            }
+            if (n >= 500) for (int a = 0; a < 9; a++) tri[9 * 5 + a] = tri[9 * 4 + a];   // an exact duplicate (coinciding centroids)
+            std::vector<BuildBox> boxes(n);
+            for (uint32_t i = 0; i < n; i++) for (int a = 0; a < 3; a++) {
+                const float* v = &tri[(size_t)i * 9];
+                boxes[i].lo[a] = std::min(v[a], std::min(v[3 + a], v[6 + a]));
+                boxes[i].hi[a] = std::max(v[a], std::max(v[3 + a], v[6 + a]));
+            }
+            BuiltBvh bvh;
+            buildBvh2(boxes.data(), n, maxLeaf, bvh);
+            // structure
+            std::vector<int> seen(n, 0);
+            uint32_t maxDepth = 0;
+            std::vector<std::pair<int, uint32_t>> st{{0, 1u}};
+            while (!st.empty()) {
+                auto [ni, depth] = st.back(); st.pop_back();
+                maxDepth = std::max(maxDepth, depth);
+                const BvhNode2& nd = bvh.nodes[ni];
+                for (int s2 = 0; s2 < 2; s2++) {
+                    const float* xy = s2 == 0 ? nd.n0 : nd.n1;
+                    const float lo[3] = {xy[0], xy[2], nd.n2[2 * s2]}, hi[3] = {xy[1], xy[3], nd.n2[2 * s2 + 1]};
+                    if (nd.c[2 + s2] > 0) {
+                        if ((uint32_t)nd.c[2 + s2] > maxLeaf) { printf("leaf of %d items > maxLeaf %u\n", nd.c[2 + s2], maxLeaf); failures++; }
+                        for (int k = 0; k < nd.c[2 + s2]; k++) {
+                            const uint32_t id = bvh.order[nd.c[s2] + k];
+                            seen[id]++;
+                            for (int a = 0; a < 3; a++) if (boxes[id].lo[a] < lo[a] || boxes[id].hi[a] > hi[a]) { printf("item %u outside its leaf box\n", id); failures++; }
+                        }
+                    } else if (nd.c[s2] >= 0) st.push_back({nd.c[s2], depth + 1});
+                }
+            }
+            for (uint32_t i = 0; i < n; i++) if (seen[i] != 1) { printf("n=%u leaf=%u: item %u referenced %d times\n", n, maxLeaf, i, seen[i]); failures++; break; }
+            if (maxDepth > 72) { printf("depth %u > 72\n", maxDepth); failures++; }
+            // traversal == brute force, before and after the breadth-first relabelling
+            std::vector<Ray> rays;
+            for (int r = 0; r < 300; r++) {
+                const V3 o{rng.f() * 12 - 6, rng.f() * 12 - 6, rng.f() * 6 - 3};
+                rays.push_back(Ray{o, norm(V3{rng.f() - 0.5f, rng.f() - 0.5f, rng.f() - 0.5f}), 3e38f, false});
+            }
+            std::vector<int> want(rays.size());
+            for (size_t r = 0; r < rays.size(); r++) {
+                const SpaceRay sr = mk(rays[r]);
+                float best = 3e38f; int hit = -1;
+                for (uint32_t i = 0; i < n; i++) { float t; if (triTest(&tri[(size_t)i * 9], sr, 0.0f, 3e38f, t) && (t < best || (t == best && (int)i < hit))) { best = t; hit = (int)i; } }
+                want[r] = hit;
+            }
+            for (int pass = 0; pass < 2; pass++) {
+                if (pass == 1) {
+                    const std::vector<BvhNode2> before = bvh.nodes;
+                    reorderTopBfs(bvh, 63);
+                    if (bvh.nodes.size() != before.size()) { printf("reorderTopBfs changed the node count\n"); failures++; }
+                    // breadth-first prefix: children of node i (i < k) that are inner nodes carry increasing indices > i
+                    int last = 0;
+                    for (size_t i = 0; i < std::min<size_t>(63, bvh.nodes.size()); i++)
+                        for (int s2 = 0; s2 < 2; s2++) if (bvh.nodes[i].c[2 + s2] == 0 && bvh.nodes[i].c[s2] >= 0 && (size_t)bvh.nodes[i].c[s2] < std::min<size_t>(63, bvh.nodes.size())) {
+                            if (bvh.nodes[i].c[s2] <= last) { printf("top of the tree is not in breadth-first order\n"); failures++; }
+                            last = bvh.nodes[i].c[s2];
+                        }
+                }
+                Scene sc{&bvh, tri.data()};
+                for (size_t r = 0; r < rays.size(); r++) {
+                    Lane L; start(L, rays[r]); walk(L, sc);
+                    if (L.hitTri != want[r]) { printf("n=%u leaf=%u pass=%d ray %zu: bvh hit %d, brute force %d\n", n, maxLeaf, pass, r, L.hitTri, want[r]); failures++; break; }
+                }
+            }
+        }
+    }
+    printf(failures ? "SELFTEST FAILED (%d)\n" : "selftest ok\n", failures);
+    return failures ? 1 : 0;
+}
+
 int main(int argc, char** argv) {
-    if (argc < 2) { fprintf(stderr, "usage: bvh_sim tris.bin [maxLeaf] [paths]\n"); return 2; }
+    if (argc >= 2 && strcmp(argv[1], "--selftest") == 0) return selftest();
+    if (argc < 2) { fprintf(stderr, "usage: bvh_sim tris.bin [maxLeaf] [paths] | bvh_sim --selftest\n"); return 2; }
     const uint32_t maxLeaf = argc > 2 ? atoi(argv[2]) : 3;
     const uint32_t nPaths = argc > 3 ? atoi(argv[3]) : 65536;
     FILE* f = fopen(argv[1], "rb"); if (!f) { perror("open"); return 1; }
