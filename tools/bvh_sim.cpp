@@ -331,5 +331,89 @@ int main(int argc, char** argv) {
     for (int b = 0; b < maxB; b++) { snprintf(nm, sizeof nm, "ext b%d", b); measure(nm, byBounce[b]); }
     for (int b = 0; b < maxB; b++) { snprintf(nm, sizeof nm, "shadow b%d", b); measure(nm, shadowBy[b]); }
     printf("TOTAL warp cost per ray %.1f over %llu rays\n", totalCost / totalRays, (unsigned long long)totalRays);
+    // MSNE_SIM_VOTE: model of a vote-scheduled loop - every iteration the warp runs EITHER one node step (for the lanes that
+    // hold an inner node) OR one leaf visit (for the lanes that hold a leaf), chosen by lane counts: leaf visit when
+    // nLeaf >= T or no lane holds an inner node. T = 33: today's while-while (leaves only when nobody can step).
+    if (getenv("MSNE_SIM_VOTE")) {
+        const double CB = 6;   // ballots + branch of the vote
+        for (int b = 2; b <= 3; b++) {
+            const std::vector<Ray>& rays = byBounce[b];
+            for (int T : {33, 24, 16, 12, 8, 4, 1}) {
+                uint64_t nodeIt = 0, triIt = 0, its = 0;
+                std::vector<Lane> L(32);
+                for (size_t base = 0; base < rays.size(); base += 32) {
+                    const size_t cnt = std::min<size_t>(32, rays.size() - base);
+                    for (size_t i = 0; i < cnt; i++) start(L[i], rays[base + i]);
+                    for (;;) {
+                        int nI = 0, nL = 0;
+                        for (size_t i = 0; i < cnt; i++) if (L[i].node != END) { if (L[i].node >= 0) nI++; else nL++; }
+                        if (nI + nL == 0) break;
+                        its++;
+                        if (nL >= T || nI == 0) {
+                            int mT = 0;
+                            for (size_t i = 0; i < cnt; i++) if (L[i].node != END && L[i].node < 0) {
+                                // one leaf visit: the body of leafPhase for a single leaf
+                                Lane& l = L[i];
+                                const uint32_t x = (uint32_t)(-(l.node + 1)), first = x >> 3, count = (x & 7u) + 1;
+                                int tests = 0; bool stop = false;
+                                for (uint32_t k = 0; k < count; k++) {
+                                    tests++; float t; const uint32_t id = sc.bvh->order[first + k];
+                                    if (!triTest(sc.tri + 9 * (size_t)id, l.r, 0.0f, l.any ? l.bestT : 3e38f, t)) continue;
+                                    if (l.any) { l.hitTri = (int)id; stop = true; break; }
+                                    if (t < l.bestT || (t == l.bestT && (int)id < l.hitTri)) { l.bestT = t; l.hitTri = (int)id; }
+                                }
+                                l.node = stop ? END : l.stack[--l.sp];
+                                mT = std::max(mT, tests);
+                            }
+                            triIt += mT;
+                        } else {
+                            for (size_t i = 0; i < cnt; i++) if (L[i].node != END && L[i].node >= 0) {
+                                Lane& l = L[i];
+                                const BvhNode2& n = sc.bvh->nodes[l.node];
+                                float t0, t1;
+                                const bool h0 = n.c[0] != -1 || n.c[2] != 0 ? slab(l.r, n, 0, 0.0f, l.bestT, t0) : false;
+                                const bool h1 = n.c[1] != -1 || n.c[3] != 0 ? slab(l.r, n, 1, 0.0f, l.bestT, t1) : false;
+                                auto ref = [&](int s2) { return n.c[2 + s2] > 0 ? -(1 + ((n.c[s2] << 3) | (n.c[2 + s2] - 1))) : n.c[s2]; };
+                                if (h0 && h1) { const bool sw = t1 < t0; l.node = sw ? ref(1) : ref(0); l.stack[l.sp++] = sw ? ref(0) : ref(1); }
+                                else if (h0) l.node = ref(0);
+                                else if (h1) l.node = ref(1);
+                                else l.node = l.stack[--l.sp];
+                            }
+                            nodeIt++;
+                        }
+                    }
+                }
+                printf("vote b%d T=%2d: cost/ray %6.1f (+%.1f with the vote) node-its %.2f tri-its %.2f per ray\n", b, T, (nodeIt * CN + triIt * CT) / rays.size(),
+                       its * CB / rays.size(), (double)nodeIt / rays.size(), (double)triIt / rays.size());
+            }
+        }
+    }
+    // MSNE_SIM_REFILL=R: model of dynamic fetch - at the top of an outer iteration, when at least R lanes are idle, the idle
+    // lanes take the next rays of the (sorted) stream instead of waiting for the whole ticket (R = 32: today's kernel).
+    if (getenv("MSNE_SIM_REFILL")) {
+        const double CF = 40;   // warp instructions of one fetch (ticket atomic, ray loads, setup)
+        for (int b = 2; b <= 3; b++) {
+            const std::vector<Ray>& rays = byBounce[b];
+            for (int R : {32, 24, 16, 8, 4, 1}) {
+                std::vector<Lane> L(32);
+                for (auto& l : L) l.node = END;
+                size_t next = 0; uint64_t warpNode = 0, warpTri = 0, fetches = 0;
+                for (;;) {
+                    int idle = 0; for (auto& l : L) idle += l.node == END;
+                    if (idle == 32 && next >= rays.size()) break;
+                    if ((idle >= R || idle == 32) && next < rays.size()) {
+                        for (auto& l : L) if (l.node == END && next < rays.size()) start(l, rays[next++]);
+                        fetches++;
+                    }
+                    int mN = 0, mT = 0;
+                    for (auto& l : L) if (l.node != END) mN = std::max(mN, innerPhase(l, sc));
+                    for (auto& l : L) if (l.node != END) mT = std::max(mT, leafPhase(l, sc));
+                    warpNode += mN; warpTri += mT;
+                }
+                printf("refill b%d R=%2d: cost/ray %6.1f (node-steps %.2f, tri-steps %.2f, fetches %.3f per ray)\n", b, R,
+                       (warpNode * CN + warpTri * CT + fetches * CF) / rays.size(), (double)warpNode / rays.size(), (double)warpTri / rays.size(), (double)fetches / rays.size());
+            }
+        }
+    }
     return 0;
 }
