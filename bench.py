@@ -315,6 +315,27 @@ def main():
            "steps": e2e_steps, "ms_per_step": e2e_wall / e2e_steps * 1e3,
            "call": "HdMoonshineRender(sensor, lens) with samples_per_run = batch spp; sensor copied to the pinned host buffer every call"}
 
+    # ---- e2e_interactive: the call pattern of the Hydra delegate (hydra/hydra.zig:316-329: ONE sample per HdMoonshineRender,
+    # sensor copied to the host after every call), same scene and constants as above -------------------------------------------
+    m.SetSpecConstants(scenes.Constants(samples_per_run=world))   # weak scaling: every rank still renders 1 spp of the full frame's worth of paths
+    m.Render(sensor, lens)
+    m.Render(sensor, lens)
+    barrier()
+    m.ResetStats()
+    n_int = 48
+    t0 = time.perf_counter()
+    for _ in range(n_int):
+        if not m.Render(sensor, lens):
+            raise SystemExit("HdMoonshineRender failed: " + m.last_error())
+    barrier()
+    int_wall = time.perf_counter() - t0
+    st3 = m.GetStats()
+    int_rays = allreduce(float(st3.rays_closest + st3.rays_shadow), dist.ReduceOp.SUM if world > 1 else None)
+    int_wall = allreduce(int_wall, dist.ReduceOp.MAX if world > 1 else None)
+    e2e_interactive = {"value": int_rays / int_wall / 1e6, "unit": UNIT, "calls": n_int, "ms_per_call": int_wall / n_int * 1e3,
+                       "device_ms_per_call": st3.device_ms / n_int, "launches_per_call": st3.kernel_launches / n_int,
+                       "call": "HdMoonshineRender(sensor, lens), samples_per_run = 1 per GPU-frame, sensor read back every call"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         r = cpu_oracle_run(scene, 4, 1, target_seconds=20.0)
@@ -324,7 +345,7 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
                 "ms_per_step": dev_ms_max / args.steps, "wall_ms_per_step": wall_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args, scene, world),
-                "clocks": clk, "e2e": e2e, "gpu_launches": timed_launches, "roofline": roofline, "roofline_step": roofline_step,
+                "clocks": clk, "e2e": e2e, "e2e_interactive": e2e_interactive, "gpu_launches": timed_launches, "roofline": roofline, "roofline_step": roofline_step,
                 "cpu_baseline": cpu, "rays": {"closest": int(st.rays_closest), "shadow": int(st.rays_shadow), "samples": int(st.samples), "max_bounce": max_bounce,
                                               "total_all_ranks": rays_total},
                 "reduce_ms": reduce_ms}

@@ -1,7 +1,7 @@
 /* moonshine.h — the reference's C ABI, re-exported by the B200-native libmoonshine.so.
  *
  * This header restates /root/reference/hydra/moonshine.h:10-95 (types :10-69, entry points :71-95)
- * so that the reference's USD Hydra delegate (hydra/*.cpp) links against the replacement library
+ * so that the reference's USD Hydra delegate (hydra/ *.cpp) links against the replacement library
  * unchanged. Semantics of every entry point follow the Zig implementation it replaces,
  * hydra/hydra.zig:107-558 (cited per function below). Differences are limited to what is behind the
  * boundary: CUDA (sm_100a) instead of Vulkan ray tracing.

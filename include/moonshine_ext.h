@@ -116,6 +116,13 @@ MSNE_API bool HdMoonshineExtPick(HdMoonshine*, SensorHandle, LensHandle, F32x2 n
 MSNE_API bool HdMoonshineExtTraceRays(HdMoonshine*, const float* rays8, size_t n, bool any_hit, uint32_t* hits5);
 /* primary rays of launch sample `sample`: rays6 = W*H x {origin, dir}; rng_state = W*H (after the 4 camera draws) */
 MSNE_API bool HdMoonshineExtPrimaryRays(HdMoonshine*, SensorHandle, LensHandle, uint32_t sample, float* rays6, uint32_t* rng_state);
+/* material.hlsl MaterialVariant::{eval,pdf,sample} on caller-supplied inputs: queries = n x 14 floats
+ * {type, color r,g,b, metalness, roughness, ior, op, a.x,a.y,a.z, w_o.x,w_o.y,w_o.z}; op 0 = eval(w_i = a, w_o) -> rgb, 1 = pdf(a, w_o) -> x,
+ * 2 = sample(w_o, square = a.xy) -> {dir.xyz, pdf}; directions in the shading frame. out = n x 4 floats. */
+MSNE_API bool HdMoonshineExtBsdfProbe(HdMoonshine*, const float* queries14, size_t n, float* out4);
+/* light.hlsl EnvMap against the current background: op 0 = sample(rand = in.xy) -> {dir.xyz, radiance.rgb, pdf} (no shadow ray),
+ * 1 = eval(dir = in.xyz) -> {radiance.rgb, pdf}, 2 = incomingRadiance(dir) -> {rgb}. in = n x 3 floats, out = n x 7 floats. */
+MSNE_API bool HdMoonshineExtEnvProbe(HdMoonshine*, int op, const float* in3, size_t n, float* out7);
 MSNE_API uint32_t HdMoonshineExtGetEnvSize(const HdMoonshine*);
 MSNE_API bool HdMoonshineExtGetEnvData(HdMoonshine*, float* rgba, float* lum_all_levels);
 MSNE_API uint32_t HdMoonshineExtGetEmitterTableSize(const HdMoonshine*);            /* entries incl. header */

@@ -23,10 +23,6 @@ struct Bounds {
 };
 
 constexpr int kBins = 16;
-// Below this depth a range is split by SAH; deeper ranges are halved by index, so the tree is at most
-// kMaxSahDepth + ceil(log2 n) <= 72 levels deep and the single-level traversal (stack of MSNE_STACK = 96 entries, one
-// per level) needs no overflow check.
-constexpr uint32_t kMaxSahDepth = 40;
 
 void setChildBox(BvhNode2& n, int slot, const Bounds& bIn) {
     BuildBox b;
@@ -39,8 +35,9 @@ void setChildBox(BvhNode2& n, int slot, const Bounds& bIn) {
 
 }  // namespace
 
-void buildBvh2(const BuildBox* boxes, uint32_t n, uint32_t maxLeaf, BuiltBvh& out) {
+void buildBvh2(const BuildBox* boxes, uint32_t n, uint32_t maxLeaf, BuiltBvh& out, uint32_t kMaxSahDepth) {
     out.nodes.clear();
+    out.depth = 1;
     out.order.resize(n);
     for (uint32_t i = 0; i < n; i++) out.order[i] = i;
     std::vector<float> cent((size_t)n * 3);
@@ -71,6 +68,7 @@ void buildBvh2(const BuildBox* boxes, uint32_t n, uint32_t maxLeaf, BuiltBvh& ou
     work.push_back({0, n, 0, 0});
     while (!work.empty()) {
         Range r = work.back(); work.pop_back();
+        out.depth = std::max(out.depth, r.depth + 1);
         uint32_t* ord = out.order.data() + r.first;
         // centroid bounds
         Bounds cb;

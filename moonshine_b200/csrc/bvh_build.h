@@ -14,10 +14,14 @@ struct BuiltBvh {
     std::vector<BvhNode2> nodes;   // nodes[0] is the root; child indices are local to this array
     std::vector<uint32_t> order;   // item index for each leaf slot
     BuildBox bounds;               // padded root bounds
+    uint32_t depth = 0;            // inner-node levels on the longest root-to-leaf walk (1 = root only)
 };
 
 // `maxLeaf` items per leaf at most. Leaf children reference [first, first+count) in `order`.
-void buildBvh2(const BuildBox* boxes, uint32_t n, uint32_t maxLeaf, BuiltBvh& out);
+// Ranges deeper than `maxSahDepth` levels are halved by index instead of split by SAH, which bounds the depth by
+// maxSahDepth + ceil(log2 n): the traversal stack (MSNE_STACK entries, one per level) is sized against it (runtime.cpp).
+constexpr uint32_t kDefaultMaxSahDepth = 40;
+void buildBvh2(const BuildBox* boxes, uint32_t n, uint32_t maxLeaf, BuiltBvh& out, uint32_t maxSahDepth = kDefaultMaxSahDepth);
 
 // Renumbers the nodes so that the first min(k, n) are the top of the tree in breadth-first order (the rest keep their
 // relative order). Pure relabelling: boxes, leaves and `order` are untouched.

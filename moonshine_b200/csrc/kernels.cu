@@ -293,13 +293,56 @@ __global__ void k_trace_probe(DeviceScene sc, const float* __restrict__ rays8, u
     const float* r = rays8 + 8 * (size_t)i;
     HitRec h;
     uint32_t geom = 0, prim = 0;
-    if (anyHit) traceRay<true, true>(sc, mk3(r[0], r[1], r[2]), mk3(r[4], r[5], r[6]), r[3], r[7], h);
+    // the renderer only ever traces [0, INFINITY = 1e12] (math.hlsl:5); a caller's +inf would make the slab test accept the
+    // unreachable point box of an empty child (dtypes.h)
+    const float tmin = fmaxf(r[3], 0.0f), tmax = fminf(r[7], MS_INFINITY);
+    if (anyHit) traceRay<true, true>(sc, mk3(r[0], r[1], r[2]), mk3(r[4], r[5], r[6]), tmin, tmax, h);
     else {
-        traceRay<false, true>(sc, mk3(r[0], r[1], r[2]), mk3(r[4], r[5], r[6]), r[3], r[7], h);
+        traceRay<false, true>(sc, mk3(r[0], r[1], r[2]), mk3(r[4], r[5], r[6]), tmin, tmax, h);
         if (h.inst != MISS_ID) { geom = sc.tris[h.tri].geom; prim = sc.tris[h.tri].prim; }
     }
     uint32_t* o = hits5 + 5 * (size_t)i;
     o[0] = h.inst; o[1] = geom; o[2] = prim; o[3] = __float_as_uint(h.u); o[4] = __float_as_uint(h.v);
+}
+
+// debug probes: the BSDF and environment-map device functions on caller-supplied inputs (HdMoonshineExtBsdfProbe / EnvProbe),
+// so the tests can pin material.hlsl / light.hlsl function by function against the oracle instead of only through images.
+// query = {type, color rgb, metalness, roughness, ior, op, a.xyz, w_o.xyz}: op 0 eval(a, w_o), 1 pdf(a, w_o), 2 sample(w_o, square = a.xy)
+__global__ void k_bsdf_probe(const float* __restrict__ q14, uint32_t n, float* out4) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* q = q14 + 14 * (size_t)i;
+    MaterialParams m;
+    m.type = (uint32_t)q[0]; m.color = mk3(q[1], q[2], q[3]); m.metalness = q[4];
+    m.alpha = fmaxf(q[5] * q[5], 0.001f);   // StandardPBR::load (material.hlsl:196)
+    m.ior = q[6];
+    const int op = (int)q[7];
+    const float3 a = mk3(q[8], q[9], q[10]), w_o = mk3(q[11], q[12], q[13]);
+    prepareMaterial(m, w_o);
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (op == 0) { const float3 e = matEval(m, a, w_o); r = make_float4(e.x, e.y, e.z, 0.f); }
+    else if (op == 1) r.x = matPdf(m, a, w_o);
+    else { const MatSample sm = matSample(m, w_o, mk2(a.x, a.y)); r = make_float4(sm.dirFs.x, sm.dirFs.y, sm.dirFs.z, sm.pdf); }
+    reinterpret_cast<float4*>(out4)[i] = r;
+}
+// op 0: EnvMap::sample(rand = in.xy) -> {dir, radiance, pdf}; 1: EnvMap::eval(dir) -> {radiance, pdf}; 2: incomingRadiance(dir) -> {rgb}
+__global__ void k_env_probe(DeviceScene sc, int op, const float* __restrict__ in3, uint32_t n, float* out7) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* a = in3 + 3 * (size_t)i;
+    float* r = out7 + 7 * (size_t)i;
+    for (int k = 0; k < 7; k++) r[k] = 0.0f;
+    if (op == 0) {
+        const LightSample ls = envSample(sc, mk2(a[0], a[1]));
+        r[0] = ls.dirWs.x; r[1] = ls.dirWs.y; r[2] = ls.dirWs.z; r[3] = ls.radiance.x; r[4] = ls.radiance.y; r[5] = ls.radiance.z; r[6] = ls.pdf;
+    } else if (op == 1) {
+        float3 rad; float pdf;
+        envEval(sc, mk3(a[0], a[1], a[2]), rad, pdf);
+        r[0] = rad.x; r[1] = rad.y; r[2] = rad.z; r[3] = pdf;
+    } else {
+        const float3 c = envIncomingRadiance(sc, mk3(a[0], a[1], a[2]));
+        r[0] = c.x; r[1] = c.y; r[2] = c.z;
+    }
 }
 
 // object picker (shaders/hrtsystem/input.hlsl:24-57): one closest-hit query through normalized sensor coordinates
@@ -810,6 +853,10 @@ void launchEnvFold(cudaStream_t st, const float* srcMip, float* dstMip, float4* 
 }
 void launchTraceProbe(cudaStream_t st, const DeviceScene& sc, const float* rays8, uint32_t n, int anyHit, uint32_t* hits5) {
     k_trace_probe<<<grid1(n, 128), 128, 0, st>>>(sc, rays8, n, anyHit, hits5);
+}
+void launchBsdfProbe(cudaStream_t st, const float* q14, uint32_t n, float* out4) { k_bsdf_probe<<<grid1(n, 128), 128, 0, st>>>(q14, n, out4); }
+void launchEnvProbe(cudaStream_t st, const DeviceScene& sc, int op, const float* in3, uint32_t n, float* out7) {
+    k_env_probe<<<grid1(n, 128), 128, 0, st>>>(sc, op, in3, n, out7);
 }
 void launchPick(cudaStream_t st, const DeviceScene& sc, const DCamera& cam, float x, float y, MsneClick* out) {
     k_pick<<<1, 1, 0, st>>>(sc, cam, make_float2(x, y), out);

@@ -20,6 +20,11 @@ namespace msne {
 #ifndef MSNE_TRACE_SMEM_NODES
 #define MSNE_TRACE_SMEM_NODES 0
 #endif
+// Entries of the per-ray traversal stack (traverse.cuh): one per tree level (the far child) + the REF_END / REF_LEAVE sentinels.
+// runtime.cpp holds depth(TLAS) + depth(BLAS) + 2 below it at build time.
+#ifndef MSNE_STACK
+#define MSNE_STACK 96
+#endif
 #ifndef SHADE_THREADS
 #define SHADE_THREADS 128
 #endif
@@ -52,6 +57,8 @@ void launchAccumulate(cudaStream_t st, const float4* result, float4* image, floa
 void launchEnvResample(cudaStream_t st, const float4* src, uint32_t W, uint32_t H, float4* dstRgb, float* dstLum, uint32_t S);
 void launchEnvFold(cudaStream_t st, const float* srcMip, float* dstMip, float4* srcQuads, uint32_t dstSize);
 void launchTraceProbe(cudaStream_t st, const DeviceScene& sc, const float* rays8, uint32_t n, int anyHit, uint32_t* hits5);
+void launchBsdfProbe(cudaStream_t st, const float* q14, uint32_t n, float* out4);
+void launchEnvProbe(cudaStream_t st, const DeviceScene& sc, int op, const float* in3, uint32_t n, float* out7);
 void launchPick(cudaStream_t st, const DeviceScene& sc, const DCamera& cam, float x, float y, MsneClick* out);
 void launchPrimaryProbe(cudaStream_t st, const DCamera& cam, const DConstants& k, uint32_t sample, float* rays6, uint32_t* rngState);
 int traceOccupancyBlocksPerSm();

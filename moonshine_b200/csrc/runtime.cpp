@@ -34,7 +34,9 @@ using namespace msne;
 namespace {
 
 thread_local std::string g_lastError;
-int g_device = 0;
+// Selected per calling thread (HdMoonshineExtSetDevice -> HdMoonshineCreate on the same thread): two threads that bring up
+// renderers on different GPUs do not race on it.
+thread_local int g_device = 0;
 
 struct CudaError : std::runtime_error { using std::runtime_error::runtime_error; };
 
@@ -91,7 +93,7 @@ struct HostInstance {
     uint32_t blas;                   // index into blases
 };
 
-struct Blas { uint32_t rootNode; BuildBox bounds; };
+struct Blas { uint32_t rootNode; BuildBox bounds; uint32_t depth; };
 
 struct Sensor {
     Extent2D extent{};
@@ -327,6 +329,10 @@ struct HdMoonshine {
     // ---- acceleration structure (replaces Accel.zig:94-184 makeBlases and :440-489 TLAS build) ------
     // pools a host BVH: children become the pre-encoded traversal references of dtypes.h
     uint32_t appendBlas(const BuiltBvh& bvh, const std::vector<TriRec>& tris) {
+        // leaf references hold the pooled triangle index in 28 bits (dtypes.h), hit records in 29 (H_TRI_MASK); inner references must
+        // stay below REF_ITEM. The merged static BLAS duplicates triangles per identity instance, so the pools can grow quickly.
+        if (triPool.size() + tris.size() >= (1ull << 28)) throw std::runtime_error("acceleration structure: more than 2^28 pooled triangles");
+        if (blasNodePool.size() + bvh.nodes.size() >= (size_t)REF_ITEM) throw std::runtime_error("acceleration structure: more than 2^30 pooled BVH nodes");
         const uint32_t nodeBase = (uint32_t)blasNodePool.size(), triBase = (uint32_t)triPool.size();
         for (BvhNode2 n : bvh.nodes) {
             for (int s = 0; s < 2; s++) {
@@ -356,6 +362,21 @@ struct HdMoonshine {
             tris.push_back(t); boxes.push_back(b);
         }
     }
+    // The traversal stack holds one entry per level of the walk (far child), plus the REF_END and REF_LEAVE sentinels:
+    // depth(TLAS) + depth(BLAS) + 2 <= MSNE_STACK. The builder's own bound (SAH cap + log2 n per tree) does not guarantee that for
+    // two degenerate trees stacked on each other, so BLASes are held to kMaxBlasDepth levels and the TLAS to what is left
+    // (buildTlas); a tree over the limit is rebuilt with a tighter SAH cap (median splits below it).
+    static constexpr uint32_t kMaxBlasDepth = 64;
+    uint32_t maxBlasDepth = 1;
+    static uint32_t ceilLog2(uint32_t n) { uint32_t l = 0; while ((1ull << l) < n) l++; return l; }
+    static void buildDepthLimited(const std::vector<BuildBox>& boxes, uint32_t maxLeaf, uint32_t depthLimit, BuiltBvh& out) {
+        buildBvh2(boxes.data(), (uint32_t)boxes.size(), maxLeaf, out);
+        if (out.depth <= depthLimit) return;
+        const uint32_t lg = ceilLog2((uint32_t)boxes.size());
+        if (depthLimit <= lg + 1) throw std::runtime_error("acceleration structure: hierarchy too deep for the traversal stack");
+        buildBvh2(boxes.data(), (uint32_t)boxes.size(), maxLeaf, out, depthLimit - lg - 1);
+        if (out.depth > depthLimit) throw std::runtime_error("acceleration structure: depth limit not met");
+    }
     uint32_t getBlas(const std::vector<uint32_t>& key) {
         auto it = blasByKey.find(key);
         if (it != blasByKey.end()) return it->second;
@@ -363,8 +384,9 @@ struct HdMoonshine {
         std::vector<TriRec> tris;
         for (uint32_t g = 0; g < key.size(); g++) meshTriangles(*meshes[key[g]], g, 0, tris, boxes);
         BuiltBvh bvh;
-        buildBvh2(boxes.data(), (uint32_t)boxes.size(), maxLeaf, bvh);
-        Blas b; b.rootNode = appendBlas(bvh, tris); b.bounds = bvh.bounds;
+        buildDepthLimited(boxes, maxLeaf, kMaxBlasDepth, bvh);
+        maxBlasDepth = std::max(maxBlasDepth, bvh.depth);
+        Blas b; b.rootNode = appendBlas(bvh, tris); b.bounds = bvh.bounds; b.depth = bvh.depth;
         blases.push_back(b);
         const uint32_t id = (uint32_t)blases.size() - 1;
         blasByKey[key] = id;
@@ -382,8 +404,10 @@ struct HdMoonshine {
     bool haveStatic = false;
     BuildBox staticBounds{};
     uint64_t stats_static_builds = 0, stats_tlas_builds = 0, stats_tlas_refits = 0;
+    uint32_t tlasDepth = 0;
     void buildGeometry() {
         blasNodePool.clear(); triPool.clear(); blasByKey.clear(); blases.clear();
+        maxBlasDepth = 1;
         const uint32_t nInst = (uint32_t)instances.size();
         std::vector<TriRec> stTris;
         std::vector<BuildBox> stBoxes;
@@ -399,7 +423,8 @@ struct HdMoonshine {
         haveStatic = !stTris.empty();
         if (haveStatic) {
             BuiltBvh bvh;
-            buildBvh2(stBoxes.data(), (uint32_t)stBoxes.size(), maxLeaf, bvh);
+            buildDepthLimited(stBoxes, maxLeaf, kMaxBlasDepth, bvh);
+            maxBlasDepth = std::max(maxBlasDepth, bvh.depth);
             staticTop = 0;
 #if MSNE_TRACE_SMEM_NODES > 0
             reorderTopBfs(bvh, MSNE_TRACE_SMEM_NODES);
@@ -548,7 +573,8 @@ struct HdMoonshine {
         tlasStaticOnly = haveStatic && items.size() == 1;
         if (hasTlas) {
             BuiltBvh tl;
-            buildBvh2(boxes.data(), (uint32_t)boxes.size(), 1, tl);
+            buildDepthLimited(boxes, 1, (uint32_t)MSNE_STACK - 2u - maxBlasDepth, tl);
+            tlasDepth = tl.depth;
             std::vector<uint32_t> slots(tl.order.size());
             for (size_t s = 0; s < tl.order.size(); s++) slots[s] = items[tl.order[s]];
             for (BvhNode2& n : tl.nodes)
@@ -971,6 +997,7 @@ static uint32_t createMesh(HdMoonshine* h, const F32x3* pos, const F32x3* nrm, c
     auto m = std::make_unique<HostMesh>();
     m->pos.assign((const float*)pos, (const float*)pos + 3 * nPos);
     m->idx.assign((const uint32_t*)idx, (const uint32_t*)idx + 3 * nTri);
+    for (uint32_t v : m->idx) if (v >= nPos) throw std::runtime_error("CreateMesh: vertex index out of range");
     m->dPos.upload(m->pos.data(), m->pos.size(), h->stream);
     m->dIdx.upload(m->idx.data(), m->idx.size(), h->stream);
     if (nrm) { m->nrm.assign((const float*)nrm, (const float*)nrm + 3 * nAttr); m->dNrm.upload(m->nrm.data(), m->nrm.size(), h->stream); }
@@ -1006,7 +1033,11 @@ HdMoonshine* HdMoonshineCreate(void) {
     }
 }
 
-void HdMoonshineDestroy(HdMoonshine* h) { delete h; }
+void HdMoonshineDestroy(HdMoonshine* h) {
+    if (!h) return;
+    { LOCK(h); }   // hydra.zig:542-558 takes no lock; here an entry point still running on another thread finishes first
+    delete h;
+}
 
 bool HdMoonshineRender(HdMoonshine* h, SensorHandle sensor, LensHandle lens) {
     LOCK(h);
@@ -1058,25 +1089,41 @@ ImageHandle HdMoonshineExtCreateTexture(HdMoonshine* h, const void* data, Extent
 
 MaterialHandle HdMoonshineCreateMaterial(HdMoonshine* h, Material m) {
     LOCK(h);
-    h->materials.push_back(DMaterial{m.normal, m.emissive, MAT_STANDARD_PBR, m.color, m.metalness, m.roughness, m.ior, 0});
-    h->tablesDirty = true;
-    return (uint32_t)h->materials.size() - 1;
+    ABORT_ON_THROW(
+        h->materials.push_back(DMaterial{m.normal, m.emissive, MAT_STANDARD_PBR, m.color, m.metalness, m.roughness, m.ior, 0});
+        h->tablesDirty = true;
+        return (uint32_t)h->materials.size() - 1;
+    )
 }
 MaterialHandle HdMoonshineExtCreateMaterial(HdMoonshine* h, const MsneMaterialInfo* m) {
     LOCK(h);
     if (m->type > MAT_STANDARD_PBR) fatal("HdMoonshineExtCreateMaterial: bad material type");
-    h->materials.push_back(DMaterial{m->normal, m->emissive, m->type, m->color, m->metalness, m->roughness, m->ior, 0});
-    h->tablesDirty = true;
-    return (uint32_t)h->materials.size() - 1;
+    ABORT_ON_THROW(
+        h->materials.push_back(DMaterial{m->normal, m->emissive, m->type, m->color, m->metalness, m->roughness, m->ior, 0});
+        h->tablesDirty = true;
+        return (uint32_t)h->materials.size() - 1;
+    )
 }
 // hydra.zig:435-481: queued in the reference and flushed by the next Render; applied to the host table
 // here and uploaded by the next render — same observable order. (No sensor clear, as in the reference.)
-void HdMoonshineSetMaterialNormal(HdMoonshine* h, MaterialHandle m, ImageHandle i) { LOCK(h); h->materials.at(m).normal = i; h->tablesDirty = true; }
-void HdMoonshineSetMaterialEmissive(HdMoonshine* h, MaterialHandle m, ImageHandle i) { LOCK(h); h->materials.at(m).emissive = i; h->tablesDirty = true; }
-void HdMoonshineSetMaterialColor(HdMoonshine* h, MaterialHandle m, ImageHandle i) { LOCK(h); h->materials.at(m).color = i; h->tablesDirty = true; }
-void HdMoonshineSetMaterialMetalness(HdMoonshine* h, MaterialHandle m, ImageHandle i) { LOCK(h); h->materials.at(m).metalness = i; h->tablesDirty = true; }
-void HdMoonshineSetMaterialRoughness(HdMoonshine* h, MaterialHandle m, ImageHandle i) { LOCK(h); h->materials.at(m).roughness = i; h->tablesDirty = true; }
-void HdMoonshineSetMaterialIOR(HdMoonshine* h, MaterialHandle m, float ior) { LOCK(h); h->materials.at(m).ior = ior; h->tablesDirty = true; }
+// A handle that was never returned by Create* is a caller bug; like the reference's `catch unreachable` it aborts, but with a message
+// (no exception may cross the C boundary).
+static void setMaterialSlot(HdMoonshine* h, MaterialHandle m, ImageHandle i, uint32_t DMaterial::*slot, const char* what) {
+    LOCK(h);
+    if (m >= h->materials.size()) fatal(what);
+    h->materials[m].*slot = i;
+    h->tablesDirty = true;
+}
+void HdMoonshineSetMaterialNormal(HdMoonshine* h, MaterialHandle m, ImageHandle i) { setMaterialSlot(h, m, i, &DMaterial::normal, "HdMoonshineSetMaterialNormal: no such material"); }
+void HdMoonshineSetMaterialEmissive(HdMoonshine* h, MaterialHandle m, ImageHandle i) { setMaterialSlot(h, m, i, &DMaterial::emissive, "HdMoonshineSetMaterialEmissive: no such material"); }
+void HdMoonshineSetMaterialColor(HdMoonshine* h, MaterialHandle m, ImageHandle i) { setMaterialSlot(h, m, i, &DMaterial::color, "HdMoonshineSetMaterialColor: no such material"); }
+void HdMoonshineSetMaterialMetalness(HdMoonshine* h, MaterialHandle m, ImageHandle i) { setMaterialSlot(h, m, i, &DMaterial::metalness, "HdMoonshineSetMaterialMetalness: no such material"); }
+void HdMoonshineSetMaterialRoughness(HdMoonshine* h, MaterialHandle m, ImageHandle i) { setMaterialSlot(h, m, i, &DMaterial::roughness, "HdMoonshineSetMaterialRoughness: no such material"); }
+void HdMoonshineSetMaterialIOR(HdMoonshine* h, MaterialHandle m, float ior) {
+    LOCK(h);
+    if (m >= h->materials.size()) fatal("HdMoonshineSetMaterialIOR: no such material");
+    h->materials[m].ior = ior; h->tablesDirty = true;
+}
 
 InstanceHandle HdMoonshineCreateInstance(HdMoonshine* h, Mat3x4 t, const Geometry* geoms, size_t n, bool visible) {
     LOCK(h);
@@ -1153,9 +1200,16 @@ SensorHandle HdMoonshineCreateSensor(HdMoonshine* h, Extent2D e) {
         return (uint32_t)h->sensors.size() - 1;
     )
 }
-float* HdMoonshineGetSensorData(const HdMoonshine* h, SensorHandle s) { return h->sensors.at(s)->host; }   // no lock (hydra.zig:522-524)
+float* HdMoonshineGetSensorData(const HdMoonshine* h, SensorHandle s) {
+    // hydra.zig:522-524 takes no lock (its sensor list is a fixed-capacity array); ours is a growing vector, so the lookup is
+    // serialised with CreateSensor. The returned buffer itself is stable from CreateSensor until Destroy.
+    HdMoonshine* m = const_cast<HdMoonshine*>(h);
+    std::lock_guard<std::mutex> lock_(m->mutex);
+    if (s >= m->sensors.size()) fatal("HdMoonshineGetSensorData: no such sensor");
+    return m->sensors[s]->host;
+}
 
-LensHandle HdMoonshineCreateLens(HdMoonshine* h, Lens l) { LOCK(h); h->lenses.push_back(l); return (uint32_t)h->lenses.size() - 1; }
+LensHandle HdMoonshineCreateLens(HdMoonshine* h, Lens l) { LOCK(h); ABORT_ON_THROW(h->lenses.push_back(l); return (uint32_t)h->lenses.size() - 1;) }
 void HdMoonshineSetLens(HdMoonshine* h, LensHandle i, Lens l) {
     LOCK(h);
     ABORT_ON_THROW(h->use(); h->lenses.at(i) = l; h->clearAllSensors();)
@@ -1170,7 +1224,11 @@ bool HdMoonshineExtSetSpecConstants(HdMoonshine* h, const MsneSpecConstants* c) 
     }
     try { h->use(); h->consts = *c; h->clearAllSensors(); return true; } catch (const std::exception& e) { g_lastError = e.what(); return false; }
 }
-void HdMoonshineExtGetSpecConstants(const HdMoonshine* h, MsneSpecConstants* c) { *c = h->consts; }
+void HdMoonshineExtGetSpecConstants(const HdMoonshine* h, MsneSpecConstants* c) {
+    HdMoonshine* m = const_cast<HdMoonshine*>(h);
+    std::lock_guard<std::mutex> lock_(m->mutex);
+    *c = m->consts;
+}
 
 bool HdMoonshineExtSetBackground(HdMoonshine* h, const float* rgba, Extent2D e) {
     LOCK(h);
@@ -1192,8 +1250,18 @@ void HdMoonshineExtClearSensor(HdMoonshine* h, SensorHandle s) {
     LOCK(h);
     ABORT_ON_THROW(h->use(); h->clearSensor(*h->sensors.at(s));)
 }
-uint32_t HdMoonshineExtGetSensorSampleCount(const HdMoonshine* h, SensorHandle s) { return h->sensors.at(s)->sample_count; }
-void* HdMoonshineExtGetSensorDevicePtr(const HdMoonshine* h, SensorHandle s) { return h->sensors.at(s)->image.p; }
+uint32_t HdMoonshineExtGetSensorSampleCount(const HdMoonshine* h, SensorHandle s) {
+    HdMoonshine* m = const_cast<HdMoonshine*>(h);
+    std::lock_guard<std::mutex> lock_(m->mutex);
+    if (s >= m->sensors.size()) fatal("HdMoonshineExtGetSensorSampleCount: no such sensor");
+    return m->sensors[s]->sample_count;
+}
+void* HdMoonshineExtGetSensorDevicePtr(const HdMoonshine* h, SensorHandle s) {
+    HdMoonshine* m = const_cast<HdMoonshine*>(h);
+    std::lock_guard<std::mutex> lock_(m->mutex);
+    if (s >= m->sensors.size()) fatal("HdMoonshineExtGetSensorDevicePtr: no such sensor");
+    return m->sensors[s]->image.p;
+}
 
 bool HdMoonshineExtSetTileShard(HdMoonshine* h, uint32_t rank, uint32_t world) {
     LOCK(h);
@@ -1237,7 +1305,8 @@ void HdMoonshineExtResetStats(HdMoonshine* h) {
 // Accel.recordUpdateSingleMaterial (Accel.zig:609-627; online/main.zig:231): geometry `g` of instance `i` gets another material
 void HdMoonshineExtSetGeometryMaterial(HdMoonshine* h, InstanceHandle i, uint32_t g, MaterialHandle m) {
     LOCK(h);
-    const HostInstance& in = h->instances.at(i);
+    if (i >= h->instances.size()) fatal("HdMoonshineExtSetGeometryMaterial: no such instance");
+    const HostInstance& in = h->instances[i];
     if (g >= in.geometryCount || m >= h->materials.size()) fatal("HdMoonshineExtSetGeometryMaterial: index out of range");
     h->geometries[in.customIndex + g].material = m;
     h->tablesDirty = true;
@@ -1297,6 +1366,32 @@ bool HdMoonshineExtPrimaryRays(HdMoonshine* h, SensorHandle s, LensHandle l, uin
         h->stats.kernel_launches++;
         CK(cudaMemcpyAsync(rays6, dr.p, 6 * n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaMemcpyAsync(rngState, ds.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return true;
+    } catch (const std::exception& e) { g_lastError = e.what(); return false; }
+}
+bool HdMoonshineExtBsdfProbe(HdMoonshine* h, const float* queries14, size_t n, float* out4) {
+    LOCK(h);
+    try {
+        h->use();
+        DevBuf<float> dq, dout;
+        dq.upload(queries14, 14 * n, h->stream); dout.alloc(4 * n);
+        launchBsdfProbe(h->stream, dq.p, (uint32_t)n, dout.p);
+        h->stats.kernel_launches++;
+        CK(cudaMemcpyAsync(out4, dout.p, 4 * n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return true;
+    } catch (const std::exception& e) { g_lastError = e.what(); return false; }
+}
+bool HdMoonshineExtEnvProbe(HdMoonshine* h, int op, const float* in3, size_t n, float* out7) {
+    LOCK(h);
+    try {
+        h->use(); h->syncScene();
+        DevBuf<float> din, dout;
+        din.upload(in3, 3 * n, h->stream); dout.alloc(7 * n);
+        launchEnvProbe(h->stream, h->deviceScene(), op, din.p, (uint32_t)n, dout.p);
+        h->stats.kernel_launches++;
+        CK(cudaMemcpyAsync(out7, dout.p, 7 * n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         return true;
     } catch (const std::exception& e) { g_lastError = e.what(); return false; }

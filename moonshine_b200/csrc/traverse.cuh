@@ -26,10 +26,6 @@
 
 namespace msne {
 
-#ifndef MSNE_STACK
-#define MSNE_STACK 96
-#endif
-
 struct HitRec { uint32_t inst, tri; float u, v; };
 
 struct SpaceRay {
@@ -146,6 +142,10 @@ DI bool traceRay(const DeviceScene& sc, const float3 o, const float3 d, const fl
         if (TWO_LEVEL && (uint32_t)node >= (uint32_t)REF_ITEM && node != REF_END) {
             if (node == REF_LEAVE) {
                 ray.set(o, d); nodes = sc.tlasNodes; curInst = MISS_ID;
+                node = stack[--sp];
+            } else if (node == REF_EMPTY) {
+                // only reachable from the probes (caller-supplied tmax / direction scale can make the slab test accept the
+                // far-away point box of an empty child, dtypes.h): nothing there
                 node = stack[--sp];
             } else {
                 const uint32_t inst = __ldg(sc.tlasItems + (node & ~REF_ITEM));

@@ -124,6 +124,8 @@ SIGNATURES = {
     "HdMoonshineExtPick": (C.c_bool, [_VP, _U32, _U32, F32x2, _VP]),
     "HdMoonshineExtTraceRays": (C.c_bool, [_VP, _VP, C.c_size_t, C.c_bool, _VP]),
     "HdMoonshineExtPrimaryRays": (C.c_bool, [_VP, _U32, _U32, _U32, _VP, _VP]),
+    "HdMoonshineExtBsdfProbe": (C.c_bool, [_VP, _VP, C.c_size_t, _VP]),
+    "HdMoonshineExtEnvProbe": (C.c_bool, [_VP, C.c_int, _VP, C.c_size_t, _VP]),
     "HdMoonshineExtGetEnvSize": (_U32, [_VP]),
     "HdMoonshineExtGetEnvData": (C.c_bool, [_VP, _VP, _VP]),
     "HdMoonshineExtGetEmitterTableSize": (_U32, [_VP]),
@@ -362,6 +364,20 @@ class HdMoonshine:
         if not self.L.HdMoonshineExtPrimaryRays(self.h, sensor, lens, sample, _p(rays), _p(st)):
             raise RuntimeError("HdMoonshineExtPrimaryRays: " + self.last_error())
         return rays, st
+
+    def bsdf_batch(self, queries14):
+        q = np.ascontiguousarray(queries14, np.float32).reshape(-1, 14)
+        out = np.zeros((len(q), 4), np.float32)
+        if not self.L.HdMoonshineExtBsdfProbe(self.h, _p(q), len(q), _p(out)):
+            raise RuntimeError("HdMoonshineExtBsdfProbe: " + self.last_error())
+        return out
+
+    def env_probe(self, op, inputs3):
+        a = np.ascontiguousarray(inputs3, np.float32).reshape(-1, 3)
+        out = np.zeros((len(a), 7), np.float32)
+        if not self.L.HdMoonshineExtEnvProbe(self.h, op, _p(a), len(a), _p(out)):
+            raise RuntimeError("HdMoonshineExtEnvProbe: " + self.last_error())
+        return out
 
     def env_data(self):
         s = self.L.HdMoonshineExtGetEnvSize(self.h)

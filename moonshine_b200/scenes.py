@@ -248,6 +248,31 @@ def furnace_white_sphere(env_samples: int, spr: int = 512, order: int = 5, exten
     return s
 
 
+def furnace_material_sphere(kind: str, spr: int = 256, env_samples: int = 0, order: int = 4, extent=(32, 32)) -> Scene:
+    """White-furnace variants of engine/tests.zig:257-364 for the BSDFs the reference's own tests never exercise:
+    kind = "mirror" (PerfectMirror), "glass" (Glass, ior 1.5), "metal" (StandardPBR white, metalness 1, roughness 0.5),
+    "dielectric" (StandardPBR white, metalness 0, roughness 0.5). Mirror and glass neither absorb nor gain (radiance 1);
+    single-scattering GGX metal can only lose energy (radiance <= 1)."""
+    s = Scene(f"furnace-{kind}-sphere", extent=extent, lens=test_lens())
+    n, e, white = s.solid2(0.5, 0.5), s.solid3(0, 0, 0), s.solid3(1, 1, 1)
+    if kind == "mirror":
+        m = s.add_material(type=MAT_PERFECT_MIRROR, normal=n, emissive=e)
+    elif kind == "glass":
+        m = s.add_material(type=MAT_GLASS, normal=n, emissive=e, ior=1.5)
+    elif kind == "metal":
+        m = s.add_material(type=MAT_STANDARD_PBR, normal=n, emissive=e, color=white, metalness=s.solid1(1.0), roughness=s.solid1(0.5), ior=1.5)
+    elif kind == "dielectric":
+        m = s.add_material(type=MAT_STANDARD_PBR, normal=n, emissive=e, color=white, metalness=s.solid1(0.0), roughness=s.solid1(0.5), ior=1.5)
+    else:
+        raise ValueError(kind)
+    p, i = icosphere(order, False)
+    s.add_instance([(s.add_mesh(p, i), m, False)])
+    s.background = np.ones((1, 1, 4), np.float32)
+    s.constants = Constants(samples_per_run=spr, max_bounces=1024, env_samples_per_bounce=env_samples, mesh_samples_per_bounce=0)
+    s.build_emitter_table = False
+    return s
+
+
 def furnace_emissive_interior(mesh_samples: int = 0, spr: int = 1024, order: int = 5, extent=(32, 32)) -> Scene:
     """engine/tests.zig:366-455 — "inside illuminating sphere is white" (mesh_samples=1 revives :457-487)."""
     s = Scene("furnace-emissive-interior", extent=extent, lens=Lens((0, 0, 0), (1, 0, 0), (0, 0, 1), math.pi / 3.0, 0.0, 1.0))

@@ -47,6 +47,9 @@ def lib():
         L.OracleSetConstants.argtypes = [C.c_void_p] + [C.c_uint32] * 4 + [C.c_int] * 3
         L.OracleSetBruteForce.argtypes = [C.c_void_p, C.c_int]
         L.OracleRender.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p]
+        L.OracleRenderDiag.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.OracleEnvProbe.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.OracleBsdfBatch.argtypes = [C.c_size_t, C.c_void_p, C.c_void_p]
         L.OracleHashPcg.restype = C.c_uint32
         L.OracleHashPcg.argtypes = [C.c_uint32]
         L.OracleHashLcg.restype = C.c_uint32
@@ -152,6 +155,23 @@ class Oracle:
         self.L.OracleRender(self.h, _p(la), width, height, _p(image), sample_count, n_launches, threads, pixel_stride, _p(counts))
         return image, counts
 
+    def render_diag(self, lens, width, height, n_launches=1, sample_count=0, threads=0, pixel_stride=1):
+        """render() plus the per-pixel diagnostic: smallest GGX alpha the pixel's paths touched (1e30 = none)."""
+        image = np.zeros((height, width, 4), np.float32)
+        min_alpha = np.full((height, width), 1e30, np.float32)
+        counts = np.zeros(2, np.uint64)
+        la = lens.as_array()
+        self.L.OracleSetBruteForce(self.h, 0)
+        self.L.OracleRenderDiag(self.h, _p(la), width, height, _p(image), sample_count, n_launches, threads, pixel_stride, _p(counts), _p(min_alpha))
+        return image, counts, min_alpha
+
+    def env_probe(self, op, inputs3):
+        """EnvMap::sample (op 0, rand in columns 0-1), ::eval (op 1, direction), ::incomingRadiance (op 2) -> (n, 7)."""
+        a = np.ascontiguousarray(inputs3, np.float32).reshape(-1, 3)
+        out = np.zeros((len(a), 7), np.float32)
+        self.L.OracleEnvProbe(self.h, op, len(a), _p(a), _p(out))
+        return out
+
     def primary_rays(self, lens, width, height, sample):
         rays = np.zeros((height, width, 6), np.float32)
         st = np.zeros((height, width), np.uint32)
@@ -199,6 +219,14 @@ class Oracle:
 def rng_floats(s, x, y, n):
     out = np.zeros(n, np.float32)
     lib().OracleRngFloats(s, x, y, n, _p(out))
+    return out
+
+
+def bsdf_batch(queries14):
+    """n x {type, color rgb, metalness, roughness, ior, op, a.xyz, w_o.xyz} -> n x 4 (see OracleBsdf)."""
+    q = np.ascontiguousarray(queries14, np.float32).reshape(-1, 14)
+    out = np.zeros((len(q), 4), np.float32)
+    lib().OracleBsdfBatch(len(q), _p(q), _p(out))
     return out
 
 

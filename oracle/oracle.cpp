@@ -137,8 +137,15 @@ void OracleSetBruteForce(Oracle* o, int brute) { o->sc.brute = brute != 0; }
 // [y0,y1) x [0,W) with `stride`-interleaved pixel subsampling (stride 1 = every pixel) on `threads`
 // host threads. image = W*H RGBA32F, read-modify-written exactly like storeColor.
 // counts[0] += closest-hit TraceRay calls, counts[1] += shadow TraceRay calls.
+// min_alpha (optional, W*H floats): per pixel the smallest GGX alpha its paths touched (1e30 = none) - a diagnostic for the tests.
+void OracleRenderDiag(Oracle* o, const float* lens12, uint32_t W, uint32_t H, float* image, uint32_t sample_count, uint32_t n_launches,
+                      int threads, uint32_t pixel_stride, uint64_t* counts, float* min_alpha);
 void OracleRender(Oracle* o, const float* lens12, uint32_t W, uint32_t H, float* image, uint32_t sample_count, uint32_t n_launches,
                   int threads, uint32_t pixel_stride, uint64_t* counts) {
+    OracleRenderDiag(o, lens12, W, H, image, sample_count, n_launches, threads, pixel_stride, counts, nullptr);
+}
+void OracleRenderDiag(Oracle* o, const float* lens12, uint32_t W, uint32_t H, float* image, uint32_t sample_count, uint32_t n_launches,
+                      int threads, uint32_t pixel_stride, uint64_t* counts, float* min_alpha) {
     if (o->dirty) commit(o);
     Lens lens; std::memcpy(&lens, lens12, 48);
     if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
@@ -154,8 +161,10 @@ void OracleRender(Oracle* o, const float* lens12, uint32_t W, uint32_t H, float*
             for (uint32_t x = 0; x < W; x++) {
                 if (((size_t)y * W + x) % pixel_stride) continue;
                 float* texel = image + 4 * ((size_t)y * W + x);
+                tc.minAlpha = 1e30f;
                 for (uint32_t l = 0; l < n_launches; l++)
                     raygenPixel(sc, tc, lens, W, H, x, y, sample_count + l * sc.consts.samples_per_run, texel);
+                if (min_alpha) min_alpha[(size_t)y * W + x] = tc.minAlpha;
             }
         }
         nc += tc.closest; ns += tc.shadow;
@@ -222,6 +231,31 @@ void OracleEnvData(Oracle* o, float* rgba, float* lum_all_levels) {
     size_t off = 0;
     for (auto& l : o->sc.env.lum) { std::memcpy(lum_all_levels + off, l.data(), l.size() * 4); off += l.size(); }
 }
+// EnvMap probes against the CURRENT background (light.hlsl:47-103). op 0: sample(rand = in[0..1]) with nothing to occlude ->
+// out7 = {dir.xyz, radiance.rgb, pdf};  op 1: eval(dir = in[0..2]) -> {radiance.rgb, pdf, 0,0,0};  op 2: incomingRadiance(dir) -> {rgb, 0...}
+void OracleEnvProbe(Oracle* o, int op, size_t n, const float* in3, float* out7) {
+    SceneData empty;            // no instances: the shadow ray of EnvMap::sample finds nothing
+    empty.accel.instances = &empty.instances;
+    empty.accel.buildTlas();
+    EnvMap env{&o->sc.env};
+    TraceCounters tc;
+    for (size_t i = 0; i < n; i++) {
+        const float* a = in3 + 3 * i; float* r = out7 + 7 * i;
+        for (int k = 0; k < 7; k++) r[k] = 0.0f;
+        if (op == 0) {
+            LightSample ls = env.sample(empty, tc, {0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 1.0f}, {a[0], a[1]});
+            r[0] = ls.dirWs.x; r[1] = ls.dirWs.y; r[2] = ls.dirWs.z; r[3] = ls.radiance.x; r[4] = ls.radiance.y; r[5] = ls.radiance.z; r[6] = ls.pdf;
+        } else if (op == 1) {
+            LightEval l = env.eval({a[0], a[1], a[2]});
+            r[0] = l.radiance.x; r[1] = l.radiance.y; r[2] = l.radiance.z; r[3] = l.pdf;
+        } else {
+            float3 c = env.incomingRadiance({a[0], a[1], a[2]});
+            r[0] = c.x; r[1] = c.y; r[2] = c.z;
+        }
+    }
+}
+// batched OracleBsdf: queries = n x {type, color rgb, metalness, roughness, ior, op, a.xyz, w_o.xyz} (14 floats; type/op as floats)
+void OracleBsdfBatch(size_t n, const float* q14, float* out4);
 uint32_t OracleAliasCount(Oracle* o) { return (uint32_t)o->sc.aliasTable.size(); }
 void OracleAliasData(Oracle* o, void* out20) { std::memcpy(out20, o->sc.aliasTable.data(), o->sc.aliasTable.size() * sizeof(AliasEntry)); }
 void OracleWorldToInstance(Oracle* o, uint32_t inst, float* out12) { std::memcpy(out12, o->sc.instances[inst].worldToInstance.m, 48); }
@@ -239,6 +273,13 @@ void OracleBsdf(uint32_t type, const float* params6, int op, const float* w_i, c
     if (op == 0) { float3 e = v.eval(wi, wo); out4[0] = e.x; out4[1] = e.y; out4[2] = e.z; out4[3] = 0; }
     else if (op == 1) { out4[0] = v.pdf(wi, wo); out4[1] = out4[2] = out4[3] = 0; }
     else { MaterialSample s = v.sample(wo, {w_i[0], w_i[1]}); out4[0] = s.dirFs.x; out4[1] = s.dirFs.y; out4[2] = s.dirFs.z; out4[3] = s.pdf; }
+}
+
+void OracleBsdfBatch(size_t n, const float* q14, float* out4) {
+    for (size_t i = 0; i < n; i++) {
+        const float* q = q14 + 14 * i;
+        OracleBsdf((uint32_t)q[0], q + 1, (int)q[7], q + 8, q + 11, out4 + 4 * i);
+    }
 }
 
 }  // extern "C"

@@ -325,7 +325,9 @@ struct MeshAttributes {
 struct LightSample { float3 dirWs, radiance; float pdf; };
 struct LightEval { float3 radiance; float pdf; };
 
-struct TraceCounters { uint64_t closest = 0, shadow = 0; };
+// minAlpha: diagnostic only (never feeds a result) - the smallest GGX alpha of any StandardPBR surface the paths counted here
+// touched; tests use it to tell pixels whose value went through a near-singular D(m) (material.hlsl:31-35) from the rest.
+struct TraceCounters { uint64_t closest = 0, shadow = 0; float minAlpha = 1e30f; };
 
 inline bool shadowHit(const SceneData& sc, TraceCounters& tc, float3 origin, float3 dir, float tmax) {  // intersection.hlsl:34-47
     tc.shadow++;
@@ -501,6 +503,7 @@ inline float3 incomingRadiance(const SceneData& sc, TraceCounters& tc, RayDesc i
         Frame textureFrame = getTextureFrame(sc, geometry.material, attrs.texcoord, attrs.frame);
         float3 emissiveLight = getEmissive(sc, geometry.material, attrs.texcoord);
         MaterialVariant material = MaterialVariant::load(sc, sc.materials[geometry.material], attrs.texcoord);
+        if (material.type == MAT_STANDARD_PBR && material.pbr.distr.a < tc.minAlpha) tc.minAlpha = material.pbr.distr.a;   // diagnostic
 
         float3 outgoingDirWs = -ray.Direction;
 

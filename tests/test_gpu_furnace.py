@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 from moonshine_b200 import scenes
-from gpu_common import gpu_render
+from gpu_common import gpu_render, oracle_render, within_tol_fraction
 
 pytestmark = pytest.mark.gpu
 
@@ -30,3 +30,24 @@ def test_inside_illuminating_sphere_with_mesh_nee_is_white():
     img, stats, _ = gpu_render(scenes.furnace_emissive_interior(mesh_samples=1, spr=512))
     assert np.abs(img[..., :3] - 1.0).max() <= 0.1  # tests.zig:457-487 (commented out in the reference)
     assert stats.rays_shadow > 0
+
+
+def test_mirror_and_glass_furnace_conserve_energy():
+    """Same bounds as tests/test_oracle_furnace.py on the CUDA path (PerfectMirror / Glass, material.hlsl:313-393)."""
+    img, _, _ = gpu_render(scenes.furnace_material_sphere("mirror"))
+    assert np.abs(img[..., :3] - 1.0).max() <= 1e-5
+    img, _, _ = gpu_render(scenes.furnace_material_sphere("glass"))
+    assert np.abs(img[..., :3] - 1.0).max() <= 0.25
+    assert abs(float(img[..., :3].mean()) - 1.0) <= 5e-3
+
+
+@pytest.mark.parametrize("kind,env", [("metal", 0), ("metal", 1), ("dielectric", 1), ("glass", 1), ("mirror", 1)])
+def test_material_furnaces_match_the_oracle(kind, env):
+    """Each non-Lambert BSDF alone on a sphere, 64 spp: the GPU image against the oracle's, pixel by pixel, and the energy bound."""
+    sc = scenes.furnace_material_sphere(kind, spr=64, env_samples=env)
+    g, _, _ = gpu_render(sc)
+    r, _, _ = oracle_render(sc)
+    assert within_tol_fraction(g, r, rel=2e-4) >= 0.99
+    assert abs(float(g[..., :3].mean()) - float(r[..., :3].mean())) <= 1e-3
+    if kind == "metal":
+        assert float(g[..., :3].mean()) <= 1.0 + 5e-3

@@ -1,0 +1,106 @@
+"""GPU-vs-oracle parity at the REAL sizes of BASELINE.json's configs (cfg2 512x512, cfg3 1920x1080 / 1.4 M triangles, cfg5 10^6
+instances / 2*10^7 alias entries at 2048x2048) - every pixel where the oracle affords it, a strided pixel set where it does not.
+
+Bars as in test_gpu_parity.py: integer / index work bit-exact, radiance within 1e-4*max(1,|x|) per pixel component at 1 spp.
+The residual is characterised, not just tolerated: `render_diag` gives, per pixel, the smallest GGX alpha its paths touched, and
+the tests state separately what holds for pixels that never went through a near-singular D(m) (material.hlsl:31-35, alpha < 0.01:
+a 1-ulp change of the half vector moves D by ~1 %) and for all pixels.
+"""
+import numpy as np
+import pytest
+
+from moonshine_b200 import hydra, scenes
+from oracle.binding import Oracle
+from gpu_common import gpu_render, random_rays, within_tol_fraction
+
+pytestmark = pytest.mark.gpu
+
+
+def _ok_mask(g, r, rel=1e-4):
+    d = np.abs(g[..., :3].astype(np.float64) - r[..., :3].astype(np.float64))
+    return (d <= rel * np.maximum(1.0, np.abs(r[..., :3]))).all(axis=-1)
+
+
+def test_cfg2_cornell_512_every_pixel():
+    """BASELINE cfg2 at size: 512x512, 2 launches (running mean), every pixel."""
+    sc = scenes.cornell_box((512, 512))
+    g, stats, _ = gpu_render(sc, 2)
+    o = Oracle()
+    scenes.load_scene(o, sc)
+    r, counts = o.render(sc.lens, 512, 512, n_launches=2)
+    ok = _ok_mask(g, r)
+    print(f"cfg2 512x512x2: pixels within 1e-4: {ok.mean():.6f}; closest rays gpu {stats.rays_closest} oracle {int(counts[0])}")
+    assert ok.mean() >= 0.999
+    np.testing.assert_array_equal(g[..., 3], 2.0)
+    assert abs(int(stats.rays_closest) - int(counts[0])) <= counts[0] * 1e-3
+    assert np.isfinite(g).all()
+
+
+def test_cfg3_full_size_every_pixel():
+    """BASELINE cfg3 at size: the 1.4 M-triangle bathroom at 1920x1080, 1 spp, all 2 073 600 pixels against the oracle."""
+    sc = scenes.bathroom()
+    assert sc.extent == (1920, 1080) and sc.triangle_count() > 1_400_000
+    g, stats, m = gpu_render(sc, 1)
+    o = Oracle()
+    scenes.load_scene(o, sc)
+    r, counts, min_alpha = o.render_diag(sc.lens, 1920, 1080)
+    ok = _ok_mask(g, r)
+    ok5 = _ok_mask(g, r, rel=5e-2)
+    sharp = min_alpha < 0.01          # some bounce of the pixel's path hit GGX with alpha < 0.01 (chrome, polished ceramic)
+    print(f"cfg3 full: all pixels within 1e-4: {ok.mean():.6f}, within 5e-2: {ok5.mean():.6f}; "
+          f"pixels touching alpha<0.01: {sharp.mean():.4f} (within 1e-4: {ok[sharp].mean():.4f}); "
+          f"others within 1e-4: {ok[~sharp].mean():.6f}; closest rays gpu {stats.rays_closest} oracle {int(counts[0])}, "
+          f"shadow gpu {stats.rays_shadow} oracle {int(counts[1])}")
+    # the statement the reduced-size test could not make: away from near-singular GGX lobes the image meets the 1e-4 bar
+    assert ok[~sharp].mean() >= 0.999
+    assert ok.mean() >= 0.995
+    assert ok5.mean() >= 0.999
+    assert abs(int(stats.rays_closest) - int(counts[0])) <= counts[0] * 1e-3
+    assert stats.rays_shadow <= counts[1]
+    np.testing.assert_array_equal(g[..., 3], 1.0)
+    assert np.isfinite(g).all()
+    # probe rays against the 1.4 M-triangle BVH: hit ids and barycentric bit patterns
+    rays = random_rays(11, 20000, np.array([0.0, 0.0, 1.3]), 1.5)
+    gh, rh = m.trace(rays), o.trace(rays)
+    np.testing.assert_array_equal(gh["instance"], rh["instance"])
+    hit = rh["instance"] != 0xFFFFFFFF
+    assert hit.mean() > 0.3
+    for f in ("geometry", "primitive"):
+        np.testing.assert_array_equal(gh[f][hit], rh[f][hit])
+    np.testing.assert_array_equal(gh["u"][hit].view(np.uint32), rh["u"][hit].view(np.uint32))
+    np.testing.assert_array_equal(gh["v"][hit].view(np.uint32), rh["v"][hit].view(np.uint32))
+
+
+def test_cfg5_million_instances():
+    """BASELINE cfg5 at size: 10^6 transformed instances of one shared BLAS, every triangle a sampled emitter.
+    Alias table (2*10^7 entries, 400 MB) byte-exact, 20 000 probe rays bit-exact, image on every 4th pixel of 2048x2048."""
+    sc = scenes.mesh_light_stress(1000, (2048, 2048))
+    assert len(sc.instances) >= 1_000_000
+    m = hydra.HdMoonshine()
+    scenes.load_scene(m, sc)
+    o = Oracle()
+    scenes.load_scene(o, sc)
+    g_tab, r_tab = m.alias_table(), o.alias_table()
+    assert len(g_tab) == len(r_tab) == 1 + 20_000_000
+    assert g_tab.tobytes() == r_tab.tobytes()
+    del g_tab, r_tab
+    rays = random_rays(9, 20000, np.array([500.0, 500.0, 1.0]), 60.0)
+    gh, rh = m.trace(rays), o.trace(rays)
+    np.testing.assert_array_equal(gh["instance"], rh["instance"])
+    hit = rh["instance"] != 0xFFFFFFFF
+    assert hit.mean() > 0.1
+    np.testing.assert_array_equal(gh["primitive"][hit], rh["primitive"][hit])
+    np.testing.assert_array_equal(gh["u"][hit].view(np.uint32), rh["u"][hit].view(np.uint32))
+    np.testing.assert_array_equal(gh["v"][hit].view(np.uint32), rh["v"][hit].view(np.uint32))
+    sensor, lens = m.CreateSensor(2048, 2048), m.CreateLens(sc.lens)
+    m.RenderLaunches(sensor, lens, 1)
+    g = m.ReadSensor(sensor).copy()
+    stride = 4
+    r, counts = o.render(sc.lens, 2048, 2048, pixel_stride=stride)
+    sel = (np.arange(2048 * 2048) % stride == 0).reshape(2048, 2048)
+    ok = _ok_mask(g, r)[sel]
+    print(f"cfg5 10^6 instances: {sel.sum()} pixels compared, within 1e-4: {ok.mean():.6f}")
+    assert ok.mean() >= 0.998
+    assert np.isfinite(g).all()
+    st = m.GetStats()
+    assert st.rays_closest >= 2048 * 2048

@@ -43,6 +43,38 @@ def test_inside_illuminating_sphere_with_mesh_nee_is_white():
     assert counts[1] > 0
 
 
+def _sphere_mask(img):
+    """pixels whose primary ray hits the unit sphere of the test lens (origin (-3,0,0), vfov pi/4), away from the silhouette"""
+    h, w = img.shape[:2]
+    y, x = np.mgrid[0:h, 0:w]
+    u, v = (x + 0.5) / w * 2 - 1, (y + 0.5) / h * 2 - 1
+    t = np.tan(np.pi / 8)
+    return (u * t) ** 2 + (v * t) ** 2 < (0.8 / 3.0) ** 2
+
+
+def test_mirror_and_glass_furnace_conserve_energy():
+    """Delta BSDFs (material.hlsl:313-393) neither absorb nor gain: a mirror / glass sphere in a white furnace is white.
+    Not pinned by any reference test - this ties PerfectMirror/Glass eval*|cos|/pdf == 1 to the analytic expectation."""
+    img, _ = _render(scenes.furnace_material_sphere("mirror"))
+    assert np.abs(img[..., :3] - 1.0).max() <= 1e-5
+    img, _ = _render(scenes.furnace_material_sphere("glass"))
+    assert np.abs(img[..., :3] - 1.0).max() <= 0.25         # Russian roulette after bounce 3 (p = 0.95) adds variance, not bias
+    assert abs(float(img[..., :3].mean()) - 1.0) <= 5e-3
+
+
+def test_ggx_metal_furnace_never_gains_energy():
+    """StandardPBR (material.hlsl:179-270), white metal, roughness 0.5: single-scattering GGX with the Smith G term can only lose
+    energy, so the sphere is at most white - with and without env NEE (MIS must not change the expectation)."""
+    means = []
+    for env in (0, 1):
+        img, _ = _render(scenes.furnace_material_sphere("metal", env_samples=env))
+        on = _sphere_mask(img)
+        means.append(float(img[on][:, :3].mean()))
+        assert 0.7 <= means[-1] <= 1.0 + 5e-3, means
+        np.testing.assert_allclose(img[~on & (img[..., 0] == 1.0)][:, :3], 1.0)   # background pixels stay exactly white
+    assert abs(means[0] - means[1]) <= 0.02                  # BSDF sampling alone == MIS of BSDF + env sampling
+
+
 def test_running_mean_matches_batch_mean():
     """storeColor (main.hlsl:43-51): N launches of spr=1 give the running mean of the N per-sample colours."""
     sc = scenes.single_triangle(extent=(16, 16))
