@@ -21,8 +21,8 @@
 typedef struct MsneSpecConstants {      /* pipeline.zig:319-327 — identical field order */
     uint32_t samples_per_run;
     uint32_t max_bounces;
-    uint32_t env_samples_per_bounce;    /* 0 or 1 (values >1 are rejected: returns false) */
-    uint32_t mesh_samples_per_bounce;   /* 0 or 1 */
+    uint32_t env_samples_per_bounce;    /* any count (integrator.hlsl:141-144); 0 and 1 take the queued-shadow-ray fast path, */
+    uint32_t mesh_samples_per_bounce;   /* larger counts trace their shadow rays inside the shade pass (integrator.hlsl:147-150) */
     uint32_t flip_image;                /* Bool32 */
     uint32_t indexed_attributes;        /* Bool32 */
     uint32_t two_component_normal_texture; /* Bool32 */
@@ -57,7 +57,10 @@ typedef struct MsneStats {
     uint64_t static_blas_builds;        /* rebuilds of the BLAS level (merged static BLAS + shared BLASes) */
     uint64_t tlas_builds;               /* rebuilds of the instance level (TLAS + instance records) */
     uint64_t tlas_refits;               /* transform-only edits served by a bottom-up refit of the existing TLAS */
-    double   sort_ms;                   /* CUDA-event time of the ray-reordering passes (keys + radix sort + binning; profiling on) */
+    double   sort_ms;                   /* CUDA-event time of the ray-reordering passes (counting sort + binning; profiling on) */
+    uint64_t waves;                     /* waves rendered (generate .. accumulate); two are in flight at a time */
+    uint64_t host_syncs;                /* host<->device synchronisations inside render loops (one per render call, none per bounce) */
+    uint64_t tail_paths;                /* paths left to k_tail after the wavefront bounces, summed over waves */
 } MsneStats;
 
 /* must be called before HdMoonshineCreate; selects the CUDA device of objects created afterwards */
@@ -116,6 +119,8 @@ MSNE_API bool HdMoonshineExtPick(HdMoonshine*, SensorHandle, LensHandle, F32x2 n
 MSNE_API bool HdMoonshineExtTraceRays(HdMoonshine*, const float* rays8, size_t n, bool any_hit, uint32_t* hits5);
 /* primary rays of launch sample `sample`: rays6 = W*H x {origin, dir}; rng_state = W*H (after the 4 camera draws) */
 MSNE_API bool HdMoonshineExtPrimaryRays(HdMoonshine*, SensorHandle, LensHandle, uint32_t sample, float* rays6, uint32_t* rng_state);
+/* the renderer's DEFINED binary32 transcendentals: fn 0 sin(a), 1 cos(a), 2 log(a), 3 atan2(a, b), 4 acos(a); n floats each */
+MSNE_API bool HdMoonshineExtMathProbe(HdMoonshine*, int fn, const float* a, const float* b, size_t n, float* out);
 /* material.hlsl MaterialVariant::{eval,pdf,sample} on caller-supplied inputs: queries = n x 14 floats
  * {type, color r,g,b, metalness, roughness, ior, op, a.x,a.y,a.z, w_o.x,w_o.y,w_o.z}; op 0 = eval(w_i = a, w_o) -> rgb, 1 = pdf(a, w_o) -> x,
  * 2 = sample(w_o, square = a.xy) -> {dir.xyz, pdf}; directions in the shading frame. out = n x 4 floats. */

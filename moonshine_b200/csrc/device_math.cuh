@@ -93,13 +93,70 @@ DI void coordinateSystem(float3 v1, float3& v2, float3& v3) {                   
     v3 = cross(v2, v1);
 }
 
+// ---- defined binary32 transcendentals -------------------------------------------------------------
+// HLSL's sin / cos / log / atan2 / acos have implementation-defined precision. Here they are DEFINED as
+// fixed sequences of correctly rounded IEEE binary32 operations - Cody-Waite reduction + the Cephes single-precision minimax
+// polynomials - instead of CUDA's libdevice, so that any conforming implementation of the same sequences (the CPU oracle states
+// them independently) returns the same bits: with them the whole renderer is reproducible bit for bit across host and device.
+// Accuracy against float64: sin/cos <= 1.5 ulp, log <= 1 ulp, atan2 <= 3.1 ulp, acos <= 4.1 ulp (tests/test_oracle_kat.py).
+DI void sinCosDef(float x, float& s, float& c) {
+    const float q = rintf(x * 0.636619772367581343f);                   // round to nearest, ties to even
+    float r = x - q * 1.5703125f;                                        // pi/2 in three parts: the products are exact for |x| < 1e5
+    r = r - q * 4.837512969970703125e-4f;
+    r = r - q * 7.54978995489188216e-8f;
+    const float z = r * r;
+    const float sp = ((-1.9515295891e-4f * z + 8.3321608736e-3f) * z - 1.6666654611e-1f) * z * r + r;
+    float cp = ((2.443315711809948e-5f * z - 1.388731625493765e-3f) * z + 4.166664568298827e-2f) * z * z;
+    cp = cp - 0.5f * z;
+    cp = cp + 1.0f;
+    const int n = (int)q & 3;
+    const float ss = (n & 1) ? cp : sp, cc = (n & 1) ? sp : cp;
+    s = (n & 2) ? -ss : ss;
+    c = (n == 1 || n == 2) ? -cc : cc;
+}
+DI float sinDef(float x) { float s, c; sinCosDef(x, s, c); return s; }
+DI float cosDef(float x) { float s, c; sinCosDef(x, s, c); return c; }
+DI float logDef(float x) {                                               // x positive and normal
+    const int bits = __float_as_int(x);
+    int e = ((bits >> 23) & 0xFF) - 126;
+    float m = __int_as_float((bits & 0x007FFFFF) | 0x3F000000);          // [0.5, 1)
+    if (m < 0.707106781186547524f) { e -= 1; m = (m + m) - 1.0f; } else { m = m - 1.0f; }
+    const float z = m * m;
+    float y = ((((((((7.0376836292e-2f * m - 1.1514610310e-1f) * m + 1.1676998740e-1f) * m - 1.2420140846e-1f) * m + 1.4249322787e-1f) * m
+                 - 1.6668057665e-1f) * m + 2.0000714765e-1f) * m - 2.4999993993e-1f) * m + 3.3333331174e-1f) * m * z;
+    const float fe = (float)e;
+    y = y + -2.12194440e-4f * fe;
+    y = y - 0.5f * z;
+    float r = m + y;
+    r = r + 0.693359375f * fe;
+    return r;
+}
+DI float atanPosDef(float x) {                                           // x >= 0
+    float y0 = 0.0f;
+    if (x > 2.414213562373095f) { y0 = 1.5707963267948966f; x = -(1.0f / x); }
+    else if (x > 0.4142135623730950f) { y0 = 0.7853981633974483f; x = (x - 1.0f) / (x + 1.0f); }
+    const float z = x * x;
+    const float p = (((8.05374449538e-2f * z - 1.38776856032e-1f) * z + 1.99777106478e-1f) * z - 3.33329491539e-1f) * z * x + x;
+    return y0 + p;
+}
+DI float atan2Def(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    float a;
+    if (ax == 0.0f) a = ay == 0.0f ? 0.0f : 1.5707963267948966f;
+    else a = atanPosDef(ay / ax);
+    if (x < 0.0f) a = 3.14159265358979323846f - a;
+    return y < 0.0f ? -a : a;
+}
+DI float acosDef(float z) { return 2.0f * atan2Def(sqrtf(1.0f - z), sqrtf(1.0f + z)); }
+
 // ---- utils/mappings.hlsl -----------------------------------------------------------------------
 DI float2 squareToTriangle(float2 sq) { float a = 1 - sqrtf(1 - sq.x); float b = sq.y * sqrtf(1 - sq.x); return mk2(a, b); }  // :5-9
 DI float2 squareToGaussian(float2 sq) {                                                   // :11-17
     const float u1 = 1.0f - sq.x, u2 = sq.y;
-    const float r = sqrtf(-2.0f * logf(u1));
+    const float r = sqrtf(-2.0f * logDef(u1));
     const float theta = 2 * MS_PI * u2;
-    return r * mk2(cosf(theta), sinf(theta));
+    float sn, cs; sinCosDef(theta, sn, cs);
+    return r * mk2(cs, sn);
 }
 DI float2 squareToUniformDiskConcentric(float2 sq) {                                      // :19-37
     float2 uO = 2.0f * sq - mk2(1.0f, 1.0f);
@@ -107,18 +164,19 @@ DI float2 squareToUniformDiskConcentric(float2 sq) {                            
     float theta, r;
     if (fabsf(uO.x) > fabsf(uO.y)) { r = uO.x; theta = (MS_PI / 4) * (uO.y / uO.x); }
     else { r = uO.y; theta = (MS_PI / 2) - (MS_PI / 4) * (uO.x / uO.y); }
-    return r * mk2(cosf(theta), sinf(theta));
+    float sn, cs; sinCosDef(theta, sn, cs);
+    return r * mk2(cs, sn);
 }
 DI float3 squareToCosineHemisphere(float2 sq) {                                           // :39-44
     float2 d = squareToUniformDiskConcentric(sq);
     float z = sqrtf(fmaxf(0.0f, 1.0f - dot(d, d)));
     return mk3(d.x, d.y, z);
 }
-DI float3 sphericalToCartesian(float sinTheta, float cosTheta, float phi) { return mk3(sinTheta * cosf(phi), sinTheta * sinf(phi), cosTheta); }  // :53-55
+DI float3 sphericalToCartesian(float sinTheta, float cosTheta, float phi) { float sn, cs; sinCosDef(phi, sn, cs); return mk3(sinTheta * cs, sinTheta * sn, cosTheta); }  // :53-55
 DI float2 cartesianToSpherical(float3 v) {                                                // :59-64
-    float p = atan2f(v.y, v.x);
+    float p = atan2Def(v.y, v.x);
     float phi = (p < 0) ? (p + 2 * MS_PI) : p;
-    float theta = acosf(v.z);
+    float theta = acosDef(v.z);
     return mk2(phi, theta);
 }
 DI float3 squareToEqualAreaSphere(float2 sq) {                                            // :67-83
@@ -129,12 +187,13 @@ DI float3 squareToEqualAreaSphere(float2 sq) {                                  
     const float r = 1.0f - d;
     const float phi = (r == 0.0f ? 1.0f : (uvp.y - uvp.x) / r + 1.0f) * MS_PI / 4.0f;
     const float3 signs = mk3(signf(uv.x), signf(uv.y), signf(signedDistance));
-    return signs * mk3(cosf(phi) * r * sqrtf(2.0f - r * r), sinf(phi) * r * sqrtf(2.0f - r * r), 1.0f - r * r);
+    float sn, cs; sinCosDef(phi, sn, cs);
+    return signs * mk3(cs * r * sqrtf(2.0f - r * r), sn * r * sqrtf(2.0f - r * r), 1.0f - r * r);
 }
 DI float2 squareToEqualAreaSphereInverse(float3 dir) {                                    // :85-99
     const float3 a = mk3(fabsf(dir.x), fabsf(dir.y), fabsf(dir.z));
     const float r = sqrtf(1.0f - a.z);
-    float phi = (a.x == 0.0f && a.y == 0.0f) ? 0.0f : atan2f(fminf(a.x, a.y), fmaxf(a.x, a.y)) * 2.0f / MS_PI;
+    float phi = (a.x == 0.0f && a.y == 0.0f) ? 0.0f : atan2Def(fminf(a.x, a.y), fmaxf(a.x, a.y)) * 2.0f / MS_PI;
     if (a.x < a.y) phi = 1.0f - phi;
     float2 uv = mk2(r - phi * r, phi * r);
     if (dir.z < 0) uv = mk2(1.0f, 1.0f) - mk2(uv.y, uv.x);

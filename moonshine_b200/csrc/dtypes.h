@@ -155,6 +155,7 @@ struct WaveState {
     uint32_t* maxBounce;
     uint32_t* typeCount;       // [NUM_BINS] entries in typeList bins (reset by the shade kernel that consumes the bin)
     uint32_t* binDone;         // [NUM_BINS] finished-block counters of the specialised shade kernels
+    Counters* history;         // [bounce] queue sizes each bounce produced, logged by its last shade launch (read by the host after the wave)
 };
 
 static const uint32_t NUM_BINS = 5;   // MaterialType 0..3 + 4 = miss (and dead paths)

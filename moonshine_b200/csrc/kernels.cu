@@ -20,7 +20,6 @@
 // order. Compiled with -fmad=false (see device_math.cuh).
 #include "kernels.h"
 #include <cstdlib>
-#include <cub/device/device_radix_sort.cuh>
 #include "shading.cuh"
 #include "traverse.cuh"
 
@@ -238,8 +237,101 @@ DI uint16_t rayKey(const SortFrame& f, float4 o, float4 d) {
     return (uint16_t)((oct << 12) | cell);
 #endif
 }
-__global__ void k_iota(uint32_t* dst, size_t n) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = (uint32_t)i;
+// ------------------------------------------------------------------------------------------------
+// Counting sort of the 15-bit ray keys -> permutation (queue indices grouped by key). Hand-written instead of a library radix
+// sort because (a) it takes its item counts from DEVICE memory (the counters the shade pass just wrote), so a bounce needs no
+// host round trip, (b) the values are the identity, so nothing but 2-byte keys is read, and (c) the order inside a key - and in
+// fact any order - is immaterial to the results: only traversal coherence depends on it, so the scatter can use atomics.
+//   k_sort_count    every block histograms its contiguous slice of the keys in shared memory (2^15 bins, 128 KB; lanes with equal
+//                   keys are aggregated with __match_any_sync first: coherent rays share keys) and adds its non-zero bins to the
+//                   global histogram
+//   k_sort_scan     exclusive prefix sum of the global histogram -> global bin cursors; the histogram is re-zeroed for the next sort
+//   k_sort_scatter  every block counts its slice again, reserves its run in every bin with one atomic on the bin cursor, then
+//                   writes the queue indices of its slice into its runs
+// blockIdx.y = 0: extension rays of `buf`, 1: shadow rays. Keys are read three times (6 B per ray), the permutation written once.
+// ------------------------------------------------------------------------------------------------
+static constexpr uint32_t SORT_BINS = 1u << 15;
+static constexpr uint32_t SORT_THREADS = 1024;
+struct SortJob {
+    const uint16_t* keys[2]; uint32_t* perm[2];
+    uint32_t* hist;      // [2][SORT_BINS], zero between sorts
+    uint32_t* cursor;    // [2][SORT_BINS]
+    const Counters* counters;   // this bounce's input counts
+};
+DI void sortSlice(const SortJob& j, uint32_t& lo, uint32_t& hi) {
+    const uint32_t n = blockIdx.y == 0 ? j.counters->nLive : j.counters->nShadow;
+    const uint32_t per = ((n + gridDim.x - 1) / gridDim.x + 31u) & ~31u;
+    const uint64_t l = (uint64_t)blockIdx.x * per;
+    lo = (uint32_t)(l < n ? l : n);
+    hi = (uint32_t)(l + per < n ? l + per : n);
+}
+// shared histogram of keys[lo, hi): every lane of a warp stays in the loop until the whole warp is done (full-mask match)
+DI void sortCountSlice(const uint16_t* __restrict__ keys, uint32_t lo, uint32_t hi, uint32_t* hist) {
+    for (uint32_t b = threadIdx.x; b < SORT_BINS; b += SORT_THREADS) hist[b] = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t base = lo + (threadIdx.x & ~31u); base < hi; base += SORT_THREADS) {
+        const uint32_t i = base + lane;
+        const uint32_t key = i < hi ? (uint32_t)__ldg(keys + i) & (SORT_BINS - 1u) : 0xFFFFFFFFu;
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+        if (i < hi && (int)lane == __ffs(peers) - 1) atomicAdd(hist + key, (uint32_t)__popc(peers));
+    }
+    __syncthreads();
+}
+__global__ void __launch_bounds__(SORT_THREADS, 1) k_sort_count(SortJob j) {
+    extern __shared__ uint32_t sortHist[];
+    uint32_t lo, hi;
+    sortSlice(j, lo, hi);
+    if (lo >= hi) return;
+    sortCountSlice(j.keys[blockIdx.y], lo, hi, sortHist);
+    uint32_t* g = j.hist + blockIdx.y * SORT_BINS;
+    for (uint32_t b = threadIdx.x; b < SORT_BINS; b += SORT_THREADS) { const uint32_t c = sortHist[b]; if (c) atomicAdd(g + b, c); }
+}
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_scan(SortJob j) {
+    __shared__ uint32_t warpSum[32];
+    uint32_t* g = j.hist + blockIdx.x * SORT_BINS;
+    uint32_t* cur = j.cursor + blockIdx.x * SORT_BINS;
+    constexpr uint32_t PER = SORT_BINS / SORT_THREADS;   // 32 consecutive bins per thread
+    uint32_t v[PER], sum = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < PER; k++) { v[k] = g[threadIdx.x * PER + k]; sum += v[k]; }
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t incl = sum;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((int)lane >= o) incl += t; }
+    if (lane == 31) warpSum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = warpSum[lane], wi = w;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, o); if ((int)lane >= o) wi += t; }
+        warpSum[lane] = wi - w;
+    }
+    __syncthreads();
+    uint32_t run = warpSum[warp] + incl - sum;
+#pragma unroll
+    for (uint32_t k = 0; k < PER; k++) { cur[threadIdx.x * PER + k] = run; run += v[k]; g[threadIdx.x * PER + k] = 0; }
+}
+__global__ void __launch_bounds__(SORT_THREADS, 1) k_sort_scatter(SortJob j) {
+    extern __shared__ uint32_t sortHist[];
+    uint32_t lo, hi;
+    sortSlice(j, lo, hi);
+    if (lo >= hi) return;
+    const uint16_t* __restrict__ keys = j.keys[blockIdx.y];
+    sortCountSlice(keys, lo, hi, sortHist);
+    uint32_t* cur = j.cursor + blockIdx.y * SORT_BINS;
+    for (uint32_t b = threadIdx.x; b < SORT_BINS; b += SORT_THREADS) { const uint32_t c = sortHist[b]; if (c) sortHist[b] = atomicAdd(cur + b, c); }
+    __syncthreads();
+    uint32_t* __restrict__ perm = j.perm[blockIdx.y];
+    const uint32_t lane = threadIdx.x & 31u, ltMask = (1u << lane) - 1u;
+    for (uint32_t base = lo + (threadIdx.x & ~31u); base < hi; base += SORT_THREADS) {
+        const uint32_t i = base + lane;
+        const uint32_t key = i < hi ? (uint32_t)__ldg(keys + i) & (SORT_BINS - 1u) : 0xFFFFFFFFu;
+        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, key);
+        const int leader = __ffs(peers) - 1;
+        uint32_t pos = 0;
+        if (i < hi && (int)lane == leader) pos = atomicAdd(sortHist + key, (uint32_t)__popc(peers));
+        pos = __shfl_sync(0xFFFFFFFFu, pos, leader) + (uint32_t)__popc(peers & ltMask);
+        if (i < hi) perm[pos] = i;
+    }
 }
 // Material binning in queue order for sorted bounces (the epilogue of the unsorted k_trace as a streaming pass over the bins
 // k_trace left in H.y). A warp owns 512 consecutive slots: it counts its bins first, reserves each bin's range with ONE atomic
@@ -325,6 +417,20 @@ __global__ void k_bsdf_probe(const float* __restrict__ q14, uint32_t n, float* o
     else { const MatSample sm = matSample(m, w_o, mk2(a.x, a.y)); r = make_float4(sm.dirFs.x, sm.dirFs.y, sm.dirFs.z, sm.pdf); }
     reinterpret_cast<float4*>(out4)[i] = r;
 }
+// the defined transcendentals (device_math.cuh): fn 0 sin(a), 1 cos(a), 2 log(a), 3 atan2(a, b), 4 acos(a)
+__global__ void k_math_probe(int fn, const float* __restrict__ a, const float* __restrict__ b, uint32_t n, float* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float r;
+    switch (fn) {
+        case 0: r = sinDef(a[i]); break;
+        case 1: r = cosDef(a[i]); break;
+        case 2: r = logDef(a[i]); break;
+        case 3: r = atan2Def(a[i], b[i]); break;
+        default: r = acosDef(a[i]); break;
+    }
+    out[i] = r;
+}
 // op 0: EnvMap::sample(rand = in.xy) -> {dir, radiance, pdf}; 1: EnvMap::eval(dir) -> {radiance, pdf}; 2: incomingRadiance(dir) -> {rgb}
 __global__ void k_env_probe(DeviceScene sc, int op, const float* __restrict__ in3, uint32_t n, float* out7) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -373,10 +479,82 @@ struct ShadeOut {
     float4 R0, R1, S0, S1, N0, N1;
     bool envRay, meshRay;
     float4 envQ0, envQ1, meshQ0, meshQ1;   // Q1.w (target) filled in after the slot is known
+    uint32_t inlineShadow;                  // INLINE_NEE: shadow rays traced inside shadeOne
 };
 
+// One light sample of estimateDirectMISLight (integrator.hlsl:20-35) up to, but not including, the occlusion test: the
+// contribution throughput * L * f * |cos| * w / p_light / n as the integrator adds it when the shadow ray finds nothing, and that
+// shadow ray. Returns false when the sample contributes nothing whatever the ray finds (light pdf or BSDF response zero: no ray).
+DI bool neeEnvSample(const DeviceScene& sc, const DConstants& k, const MaterialParams& material, const Frame& shadingFrame, float3 outgoingDirSs,
+                     float3 position, float3 triangleNormal, float3 throughput, float2 rand, float3& contribution, float4& q0, float4& q1) {
+    // EnvMap::sample (light.hlsl:47-80)
+    const LightSample ls = envSample(sc, rand);
+    if (!(ls.pdf > 0.0f)) return false;
+    const float3 lightDirFs = shadingFrame.worldToFrame(ls.dirWs);
+    const float scatteringPdf = matPdf(material, lightDirFs, outgoingDirSs);
+    if (!(scatteringPdf > 0.0f)) return false;
+    const float3 brdf = matEval(material, lightDirFs, outgoingDirSs);
+    const float weight = powerHeuristic(k.env_samples, ls.pdf, 1, scatteringPdf);
+    const float3 est = ls.radiance * brdf * fabsf(cosTheta(lightDirFs)) * weight / ls.pdf;
+    contribution = (throughput * est) / (float)k.env_samples;
+    const float3 so = offsetAlongNormal(position, faceForward(triangleNormal, ls.dirWs));
+    q0 = make_float4(so.x, so.y, so.z, MS_INFINITY);
+    q1 = make_float4(ls.dirWs.x, ls.dirWs.y, ls.dirWs.z, 0.0f);
+    return true;
+}
+DI bool neeMeshSample(const DeviceScene& sc, const DConstants& k, const MaterialParams& material, const Frame& shadingFrame, float3 outgoingDirSs,
+                      float3 position, float3 triangleNormal, float3 throughput, float2 rand, float3& contribution, float4& q0, float4& q1) {
+    // MeshLights::sample (light.hlsl:130-158)
+    if (!(sc.aliasEntries > 1)) return false;
+    const uint32_t entryCount = __ldg(&sc.alias[0].alias);
+    const float sum = __ldg(&sc.alias[0].select);
+    if (entryCount == 0 || sum == 0) return false;
+    // sampleAlias (mappings.hlsl:114-126), offset 1
+    const float scaled = rand.x * (float)entryCount;
+    uint32_t idx = (uint32_t)scaled;
+    if (idx >= entryCount) idx = entryCount - 1;   // hazard: float rounding past the table end
+    rand.x = scaled - floorf(scaled);
+    DAlias e = sc.alias[1 + idx];
+    if (!coinFlipRemap(e.select, rand.x)) { idx = e.alias; e = sc.alias[1 + idx]; }
+    const uint32_t lInstanceID = __ldg(&sc.instances[e.inst].customIndex);
+    const DGeometry lg = sc.geometries[lInstanceID + e.geom];
+    const float2 lbary = squareToTriangle(rand);
+#if MSNE_EMITTER_RECORDS
+    const LightPoint lp = emitterPoint(sc, idx, e.inst, lbary);
+    struct { float3 position; float2 texcoord; struct { float3 n; } triangleFrame; } la = {lp.position, lp.texcoord, {lp.n}};
+#else
+    const MeshAttributes la = lookupAttributes(sc, k, e.inst, lg.mesh, e.prim, lbary);
+#endif
+    const DMaterial* lm = sc.materials + lg.material;
+    float3 radiance;
+    if (MSNE_MATERIAL_CONSTANTS && (__ldg(&lm->constMask) >> MAT_SLOT_EMISSIVE) & 1u)
+        radiance = mk3(__ldg(&lm->constant[MAT_SLOT_EMISSIVE][0]), __ldg(&lm->constant[MAT_SLOT_EMISSIVE][1]), __ldg(&lm->constant[MAT_SLOT_EMISSIVE][2]));
+    else radiance = xyz(sampleTexture(sc, __ldg(&lm->emissive), la.texcoord));
+    const float3 dirWs = normalize(la.position - position);
+    const float pdf = areaMeasureToSolidAngleMeasure(la.position, position, dirWs, la.triangleFrame.n) / sum;
+    if (!(pdf > 0.0f)) return false;
+    const float3 lightDirFs = shadingFrame.worldToFrame(dirWs);
+    const float scatteringPdf = matPdf(material, lightDirFs, outgoingDirSs);
+    if (!(scatteringPdf > 0.0f)) return false;
+    const float3 brdf = matEval(material, lightDirFs, outgoingDirSs);
+    const float weight = powerHeuristic(k.mesh_samples, pdf, 1, scatteringPdf);
+    const float3 est = radiance * brdf * fabsf(cosTheta(lightDirFs)) * weight / pdf;
+    contribution = (throughput * est) / (float)k.mesh_samples;
+    const float3 offL = offsetAlongNormal(la.position, la.triangleFrame.n);
+    const float3 offS = offsetAlongNormal(position, faceForward(triangleNormal, dirWs));
+    const float tmax = length(offL - offS);
+    const float3 sd = normalize(offL - offS);
+    q0 = make_float4(offS.x, offS.y, offS.z, tmax);
+    q1 = make_float4(sd.x, sd.y, sd.z, 0.0f);
+    return true;
+}
+
 // MT: -1 = any (runtime dispatch), 0..3 = MaterialType known at compile time, 4 = miss / dead paths only
-template <int MT>
+// INLINE_NEE = false: at most one env and one mesh light sample per bounce (the offline and Hydra constants); their shadow rays are
+// queued (out.envRay / out.meshRay) and the contributions wait in N0 / N1 for the next trace pass.
+// INLINE_NEE = true: any env_samples_per_bounce / mesh_samples_per_bounce (integrator.hlsl:141-150 loops over them): every light
+// sample's shadow ray is traced right here and its contribution added in the reference's order, so nothing is pending afterwards.
+template <int MT, bool INLINE_NEE = false>
 DI void shadeOne(const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, uint32_t buf, uint32_t q, ShadeOut& out, uint32_t& bounceOut) {
     const float4 R0 = qld(pb.R0[buf] + RAY_STRIDE * (size_t)q), R1 = qld(pb.R1[buf] + RAY_STRIDE * (size_t)q), S0 = qld(pb.S0[buf] + q), S1 = qld(pb.S1[buf] + q);
     const float4 N0 = qld(pb.N0[buf] + q), N1 = qld(pb.N1[buf] + q);
@@ -384,7 +562,7 @@ DI void shadeOne(const DeviceScene& sc, const DConstants& k, const PathBuffers& 
     const uint32_t bounceCount = flags & BOUNCE_MASK;
     const uint32_t slot = __float_as_uint(S1.w);
     bounceOut = bounceCount;
-    out.kind = 0; out.envRay = false; out.meshRay = false;
+    out.kind = 0; out.envRay = false; out.meshRay = false; out.inlineShadow = 0;
 
     float3 acc = mk3(S1.x, S1.y, S1.z);
     // NEE of the previous bounce, in the reference's order: env first, then mesh (integrator.hlsl:141-150)
@@ -468,73 +646,33 @@ DI void shadeOne(const DeviceScene& sc, const DConstants& k, const PathBuffers& 
     const bool isCurrentMaterialDelta = matIsDelta(material.type);
     float3 neeEnv = mk3(0.0f), neeMesh = mk3(0.0f);
     if (!isCurrentMaterialDelta) {
-        // env NEE (integrator.hlsl:141-144 -> estimateDirectMISLight :20-35 -> EnvMap::sample light.hlsl:47-80)
-        if (k.env_samples) {
-            const float2 rand = rng.getFloat2();
-            const LightSample ls = envSample(sc, rand);
-            if (ls.pdf > 0.0f) {
-                const float3 lightDirFs = shadingFrame.worldToFrame(ls.dirWs);
-                const float scatteringPdf = matPdf(material, lightDirFs, outgoingDirSs);
-                if (scatteringPdf > 0.0f) {
-                    const float3 brdf = matEval(material, lightDirFs, outgoingDirSs);
-                    const float weight = powerHeuristic(k.env_samples, ls.pdf, 1, scatteringPdf);
-                    const float3 est = ls.radiance * brdf * fabsf(cosTheta(lightDirFs)) * weight / ls.pdf;
-                    neeEnv = (throughput * est) / (float)k.env_samples;
-                    const float3 so = offsetAlongNormal(attrs.position, faceForward(attrs.triangleFrame.n, ls.dirWs));
-                    out.envRay = true;
-                    out.envQ0 = make_float4(so.x, so.y, so.z, MS_INFINITY);
-                    out.envQ1 = make_float4(ls.dirWs.x, ls.dirWs.y, ls.dirWs.z, 0.0f);
-                }
+        if (INLINE_NEE) {
+            // integrator.hlsl:141-150 with any sample counts: draw, sample, occlusion test, add - in that order
+            float3 c; float4 q0, q1; HitRec sh;
+            for (uint32_t i = 0; i < k.env_samples; i++) {
+                const float2 rand = rng.getFloat2();
+                if (!neeEnvSample(sc, k, material, shadingFrame, outgoingDirSs, attrs.position, attrs.triangleFrame.n, throughput, rand, c, q0, q1)) continue;
+                out.inlineShadow++;
+                if (!traceRay<true, true>(sc, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), 0.0f, q0.w, sh)) acc = acc + c;
             }
-        }
-        // mesh NEE (integrator.hlsl:147-150 -> MeshLights::sample light.hlsl:130-158)
-        if (k.mesh_samples) {
-            float2 rand = rng.getFloat2();
-            if (sc.aliasEntries > 1) {
-                const uint32_t entryCount = __ldg(&sc.alias[0].alias);
-                const float sum = __ldg(&sc.alias[0].select);
-                if (entryCount != 0 && sum != 0) {
-                    // sampleAlias (mappings.hlsl:114-126), offset 1
-                    const float scaled = rand.x * (float)entryCount;
-                    uint32_t idx = (uint32_t)scaled;
-                    if (idx >= entryCount) idx = entryCount - 1;   // hazard: float rounding past the table end
-                    rand.x = scaled - floorf(scaled);
-                    DAlias e = sc.alias[1 + idx];
-                    if (!coinFlipRemap(e.select, rand.x)) { idx = e.alias; e = sc.alias[1 + idx]; }
-                    const uint32_t lInstanceID = __ldg(&sc.instances[e.inst].customIndex);
-                    const DGeometry lg = sc.geometries[lInstanceID + e.geom];
-                    const float2 lbary = squareToTriangle(rand);
-#if MSNE_EMITTER_RECORDS
-                    const LightPoint lp = emitterPoint(sc, idx, e.inst, lbary);
-                    struct { float3 position; float2 texcoord; struct { float3 n; } triangleFrame; } la = {lp.position, lp.texcoord, {lp.n}};
-#else
-                    const MeshAttributes la = lookupAttributes(sc, k, e.inst, lg.mesh, e.prim, lbary);
-#endif
-                    const DMaterial* lm = sc.materials + lg.material;
-                    float3 radiance;
-                    if (MSNE_MATERIAL_CONSTANTS && (__ldg(&lm->constMask) >> MAT_SLOT_EMISSIVE) & 1u)
-                        radiance = mk3(__ldg(&lm->constant[MAT_SLOT_EMISSIVE][0]), __ldg(&lm->constant[MAT_SLOT_EMISSIVE][1]), __ldg(&lm->constant[MAT_SLOT_EMISSIVE][2]));
-                    else radiance = xyz(sampleTexture(sc, __ldg(&lm->emissive), la.texcoord));
-                    const float3 dirWs = normalize(la.position - attrs.position);
-                    const float pdf = areaMeasureToSolidAngleMeasure(la.position, attrs.position, dirWs, la.triangleFrame.n) / sum;
-                    if (pdf > 0.0f) {
-                        const float3 lightDirFs = shadingFrame.worldToFrame(dirWs);
-                        const float scatteringPdf = matPdf(material, lightDirFs, outgoingDirSs);
-                        if (scatteringPdf > 0.0f) {
-                            const float3 brdf = matEval(material, lightDirFs, outgoingDirSs);
-                            const float weight = powerHeuristic(k.mesh_samples, pdf, 1, scatteringPdf);
-                            const float3 est = radiance * brdf * fabsf(cosTheta(lightDirFs)) * weight / pdf;
-                            neeMesh = (throughput * est) / (float)k.mesh_samples;
-                            const float3 offL = offsetAlongNormal(la.position, la.triangleFrame.n);
-                            const float3 offS = offsetAlongNormal(attrs.position, faceForward(attrs.triangleFrame.n, dirWs));
-                            const float tmax = length(offL - offS);
-                            const float3 sd = normalize(offL - offS);
-                            out.meshRay = true;
-                            out.meshQ0 = make_float4(offS.x, offS.y, offS.z, tmax);
-                            out.meshQ1 = make_float4(sd.x, sd.y, sd.z, 0.0f);
-                        }
-                    }
-                }
+            for (uint32_t i = 0; i < k.mesh_samples; i++) {
+                const float2 rand = rng.getFloat2();
+                if (!neeMeshSample(sc, k, material, shadingFrame, outgoingDirSs, attrs.position, attrs.triangleFrame.n, throughput, rand, c, q0, q1)) continue;
+                out.inlineShadow++;
+                if (!traceRay<true, true>(sc, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), 0.0f, q0.w, sh)) acc = acc + c;
+            }
+        } else {
+            // env NEE (integrator.hlsl:141-144 -> estimateDirectMISLight :20-35 -> EnvMap::sample light.hlsl:47-80)
+            if (k.env_samples) {
+                const float2 rand = rng.getFloat2();
+                out.envRay = neeEnvSample(sc, k, material, shadingFrame, outgoingDirSs, attrs.position, attrs.triangleFrame.n, throughput, rand, neeEnv, out.envQ0, out.envQ1);
+                if (!out.envRay) neeEnv = mk3(0.0f);
+            }
+            // mesh NEE (integrator.hlsl:147-150 -> MeshLights::sample light.hlsl:130-158)
+            if (k.mesh_samples) {
+                const float2 rand = rng.getFloat2();
+                out.meshRay = neeMeshSample(sc, k, material, shadingFrame, outgoingDirSs, attrs.position, attrs.triangleFrame.n, throughput, rand, neeMesh, out.meshQ0, out.meshQ1);
+                if (!out.meshRay) neeMesh = mk3(0.0f);
             }
         }
     }
@@ -564,8 +702,8 @@ DI void shadeOne(const DeviceScene& sc, const DConstants& k, const PathBuffers& 
 // Shared body of the shade kernels. BIN = -1: every queue slot [0, nLive) + the dead range, any material (used for
 // small queues, one launch per bounce). BIN = 0..4: only the slots the trace kernel binned under that material type
 // (4 = misses + the dead range); five such launches cover a bounce with material-specialised, convergent code.
-template <int BIN, int MIN_BLOCKS>
-__global__ void __launch_bounds__(SHADE_THREADS, MIN_BLOCKS) k_shade(DeviceScene sc, DConstants k, PathBuffers pb, WaveState ws, uint32_t buf, uint32_t lastOfBounce, SortKeys keys) {
+template <int BIN, int MIN_BLOCKS, bool INLINE_NEE = false>
+__global__ void __launch_bounds__(SHADE_THREADS, MIN_BLOCKS) k_shade(DeviceScene sc, DConstants k, PathBuffers pb, WaveState ws, uint32_t buf, int32_t historySlot, SortKeys keys) {
     const Counters cin = ws.counters[buf];
     Counters* cout = ws.counters + (buf ^ 1u);
     const uint32_t P = pb.capacity;
@@ -577,6 +715,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, MIN_BLOCKS) k_shade(DeviceScene
     const uint32_t ltMask = (1u << lane) - 1u;
     const uint32_t ob = buf ^ 1u;
     uint32_t localMaxBounce = 0;
+    uint32_t nInline = 0;
     const uint32_t stride = gridDim.x * blockDim.x;
     // every lane of a warp runs the same number of iterations so the ballots below are convergent
     // queue slot of grid-stride item i: list entry, or the dead range filled from the top of the buffer
@@ -584,12 +723,13 @@ __global__ void __launch_bounds__(SHADE_THREADS, MIN_BLOCKS) k_shade(DeviceScene
     for (uint32_t base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < total; base += stride) {
         const uint32_t i = base + lane;
         ShadeOut out;
-        out.kind = 0; out.envRay = false; out.meshRay = false;
+        out.kind = 0; out.envRay = false; out.meshRay = false; out.inlineShadow = 0;
         if (i < total) {
             const uint32_t q = slotOf(i);
             uint32_t b;
-            shadeOne<BIN>(sc, k, pb, buf, q, out, b);
+            shadeOne<BIN, INLINE_NEE>(sc, k, pb, buf, q, out, b);
             localMaxBounce = max(localMaxBounce, b);
+            if (INLINE_NEE) nInline += out.inlineShadow;
         }
         // ---- warp-ballot compaction into the other ping-pong buffer -----------------------------
         const uint32_t liveMask = __ballot_sync(0xFFFFFFFFu, out.kind == 1);
@@ -626,6 +766,10 @@ __global__ void __launch_bounds__(SHADE_THREADS, MIN_BLOCKS) k_shade(DeviceScene
     }
     // last block out: clear what this launch consumed, publish the deepest bounce seen
     if (localMaxBounce) atomicMax(ws.maxBounce, localMaxBounce);
+    if (INLINE_NEE) {
+        for (int o = 16; o > 0; o >>= 1) nInline += __shfl_down_sync(0xFFFFFFFFu, nInline, o);
+        if (lane == 0 && nInline) atomicAdd(ws.rayCounts + 1, (unsigned long long)nInline);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -634,7 +778,12 @@ __global__ void __launch_bounds__(SHADE_THREADS, MIN_BLOCKS) k_shade(DeviceScene
         if (done == gridDim.x - 1) {
             if (BIN < 0) { for (uint32_t b = 0; b < NUM_BINS; b++) ws.typeCount[b] = 0; }
             else ws.typeCount[BIN] = 0;
-            if (lastOfBounce) { ws.counters[buf].nLive = 0; ws.counters[buf].nDead = 0; ws.counters[buf].nShadow = 0; }
+            // historySlot >= 0: this is the bounce's last shade launch - log what the bounce produced (the host reads the log after
+            // the wave, never during it) and clear what it consumed
+            if (historySlot >= 0) {
+                ws.history[historySlot] = *cout;
+                ws.counters[buf].nLive = 0; ws.counters[buf].nDead = 0; ws.counters[buf].nShadow = 0;
+            }
             *doneCtr = 0;
             __threadfence();
         }
@@ -648,6 +797,7 @@ __global__ void __launch_bounds__(SHADE_THREADS, MIN_BLOCKS) k_shade(DeviceScene
 // path ends. Same device functions, same per-path order of operations -> bit-identical results.
 // Precondition: k_trace has just run on `buf` (H holds this bounce's hits, pending shadow rays are resolved).
 // ------------------------------------------------------------------------------------------------
+template <bool INLINE_NEE>
 __global__ void __launch_bounds__(128) k_tail(DeviceScene sc, DConstants k, PathBuffers pb, WaveState ws, uint32_t buf) {
     const Counters cin = ws.counters[buf];
     const uint32_t nLive = cin.nLive, total = cin.nLive + cin.nDead, P = pb.capacity;
@@ -657,10 +807,11 @@ __global__ void __launch_bounds__(128) k_tail(DeviceScene sc, DConstants k, Path
         const uint32_t q = i < nLive ? i : (P - 1u - (i - nLive));
         for (;;) {
             ShadeOut out;
-            out.kind = 0; out.envRay = false; out.meshRay = false;
+            out.kind = 0; out.envRay = false; out.meshRay = false; out.inlineShadow = 0;
             uint32_t b;
-            shadeOne<-1>(sc, k, pb, buf, q, out, b);
+            shadeOne<-1, INLINE_NEE>(sc, k, pb, buf, q, out, b);
             localMaxBounce = max(localMaxBounce, b);
+            if (INLINE_NEE) nShadow += out.inlineShadow;
             if (out.kind == 0) break;
             HitRec h;
             if (out.envRay) {
@@ -798,22 +949,19 @@ void launchTrace(cudaStream_t st, int blocks, const DeviceScene& sc, const PathB
 #endif
     else k_trace<true, false><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf, nullptr, nullptr);
 }
-// sorted bounce: radix sort of the keys the previous shade pass wrote (16-bit keys, queue index as value; extension and
-// shadow queue separately) -> trace through the permutations -> binning pass
-size_t sortTempBytes(size_t maxItems) {
-    size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint16_t*)nullptr, (uint16_t*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, (uint64_t)maxItems, 0, 16);
-    return bytes;
-}
-void launchIota(cudaStream_t st, uint32_t* dst, size_t n) { k_iota<<<1024, 256, 0, st>>>(dst, n); }
-cudaError_t launchSortRays(cudaStream_t st, const SortBuffers& sb, uint32_t nExt, uint32_t nShadow) {
-    cudaError_t err = cudaSuccess;
-    size_t bytes = sb.tempBytes;
-    if (nExt) err = cub::DeviceRadixSort::SortPairs(sb.temp, bytes, (const uint16_t*)sb.keysExt, sb.keysTmp, sb.iota, sb.permExt, (uint64_t)nExt, 0, 15, st);
-    bytes = sb.tempBytes;
-    if (nShadow && err == cudaSuccess)
-        err = cub::DeviceRadixSort::SortPairs(sb.temp, bytes, (const uint16_t*)sb.keysShadow, sb.keysTmp, sb.iota, sb.permShadow, (uint64_t)nShadow, 0, 15, st);
-    return err;
+// sorted bounce: counting sort of the keys the previous shade pass wrote (extension and shadow queue in one set of launches,
+// item counts read on the device) -> trace through the permutations -> binning pass
+void launchSortRays(cudaStream_t st, int smCount, const SortBuffers& sb, const Counters* counters) {
+    static const size_t smemBytes = SORT_BINS * sizeof(uint32_t);
+    static const cudaError_t a0 = cudaFuncSetAttribute(k_sort_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
+    static const cudaError_t a1 = cudaFuncSetAttribute(k_sort_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
+    (void)a0; (void)a1;
+    SortJob j;
+    j.keys[0] = sb.keysExt; j.keys[1] = sb.keysShadow; j.perm[0] = sb.permExt; j.perm[1] = sb.permShadow;
+    j.hist = sb.hist; j.cursor = sb.cursor; j.counters = counters;
+    k_sort_count<<<dim3(smCount, 2), SORT_THREADS, smemBytes, st>>>(j);
+    k_sort_scan<<<2, SORT_THREADS, 0, st>>>(j);
+    k_sort_scatter<<<dim3(smCount, 2), SORT_THREADS, smemBytes, st>>>(j);
 }
 void launchTraceSorted(cudaStream_t st, int blocks, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const uint32_t* permExt, const uint32_t* permShadow) {
     if (sc.staticOnly) k_trace<false, true><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf, permExt, permShadow);
@@ -825,19 +973,25 @@ void launchBin(cudaStream_t st, int smCount, const PathBuffers& pb, const WaveSt
 #ifndef SHADE_MINB
 #define SHADE_MINB 6
 #endif
-void launchShade(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const SortKeys& keys) {
-    k_shade<-1, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, 1u, keys);
+void launchShade(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf, int32_t slot, const SortKeys& keys) {
+    k_shade<-1, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, slot, keys);
+}
+// env/mesh_samples_per_bounce > 1: one generic launch per bounce whose light samples trace their shadow rays in place (4 blocks/SM:
+// the traversal stack and the shading state are live at the same time)
+void launchShadeInlineNee(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf, int32_t slot, const SortKeys& keys) {
+    k_shade<-1, 4, true><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, slot, keys);
 }
 // one launch per material bin; the miss/dead bin goes last and clears the bounce's counters
-void launchShadeBinned(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const SortKeys& keys) {
-    k_shade<3, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, 0u, keys);   // StandardPBR
-    k_shade<1, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, 0u, keys);   // Lambert
-    k_shade<0, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, 0u, keys);   // Glass
-    k_shade<2, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, 0u, keys);   // PerfectMirror
-    k_shade<4, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, 1u, keys);   // miss + dead
+void launchShadeBinned(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf, int32_t slot, const SortKeys& keys) {
+    k_shade<3, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, -1, keys);   // StandardPBR
+    k_shade<1, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, -1, keys);   // Lambert
+    k_shade<0, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, -1, keys);   // Glass
+    k_shade<2, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, -1, keys);   // PerfectMirror
+    k_shade<4, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, slot, keys);   // miss + dead
 }
-void launchTail(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf) {
-    k_tail<<<blocks, 128, 0, st>>>(sc, k, pb, ws, buf);
+void launchTail(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf, bool inlineNee) {
+    if (inlineNee) k_tail<true><<<blocks, 128, 0, st>>>(sc, k, pb, ws, buf);
+    else k_tail<false><<<blocks, 128, 0, st>>>(sc, k, pb, ws, buf);
 }
 void launchAccumulate(cudaStream_t st, const float4* result, float4* image, float4* runState, const uint32_t* pixIds, uint32_t nPix, uint32_t nSamples,
                       uint32_t firstSample, uint32_t spr) {
@@ -854,6 +1008,7 @@ void launchEnvFold(cudaStream_t st, const float* srcMip, float* dstMip, float4* 
 void launchTraceProbe(cudaStream_t st, const DeviceScene& sc, const float* rays8, uint32_t n, int anyHit, uint32_t* hits5) {
     k_trace_probe<<<grid1(n, 128), 128, 0, st>>>(sc, rays8, n, anyHit, hits5);
 }
+void launchMathProbe(cudaStream_t st, int fn, const float* a, const float* b, uint32_t n, float* out) { k_math_probe<<<grid1(n, 256), 256, 0, st>>>(fn, a, b, n, out); }
 void launchBsdfProbe(cudaStream_t st, const float* q14, uint32_t n, float* out4) { k_bsdf_probe<<<grid1(n, 128), 128, 0, st>>>(q14, n, out4); }
 void launchEnvProbe(cudaStream_t st, const DeviceScene& sc, int op, const float* in3, uint32_t n, float* out7) {
     k_env_probe<<<grid1(n, 128), 128, 0, st>>>(sc, op, in3, n, out7);
@@ -880,6 +1035,11 @@ int traceOccupancyBlocksPerSm() {
 int shadeOccupancyBlocksPerSm() {
     int n = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade<-1, SHADE_MINB>, SHADE_THREADS, 0);
+    return n;
+}
+int shadeInlineOccupancyBlocksPerSm() {
+    int n = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade<-1, 4, true>, SHADE_THREADS, 0);
     return n;
 }
 

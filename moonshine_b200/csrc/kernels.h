@@ -39,29 +39,31 @@ void launchTrace(cudaStream_t st, int blocks, const DeviceScene& sc, const PathB
 struct SortFrame { float lo[3], scale[3]; uint32_t bits[3]; };
 struct SortKeys { uint16_t* ext; uint16_t* shadow; SortFrame frame; };   // ext == nullptr: the shade pass writes no keys
 struct SortBuffers {          // sized for P extension + 2 P shadow rays (runtime.cpp ensureSortBuffers)
-    uint16_t* keysExt; uint16_t* keysShadow; uint16_t* keysTmp;
-    const uint32_t* iota;     // 0, 1, 2, ... (2 P entries)
+    uint16_t* keysExt; uint16_t* keysShadow;
     uint32_t* permExt; uint32_t* permShadow;
-    void* temp; size_t tempBytes;
+    uint32_t* hist; uint32_t* cursor;   // [2][2^15] each; hist is zero between sorts
 };
-size_t sortTempBytes(size_t maxItems);
-void launchIota(cudaStream_t st, uint32_t* dst, size_t n);
-cudaError_t launchSortRays(cudaStream_t st, const SortBuffers& sb, uint32_t nExt, uint32_t nShadow);
+// three launches (count, scan, scatter); the item counts are read from `counters` (device memory) when the kernels run
+void launchSortRays(cudaStream_t st, int smCount, const SortBuffers& sb, const Counters* counters);
 void launchTraceSorted(cudaStream_t st, int blocks, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const uint32_t* permExt, const uint32_t* permShadow);
 void launchBin(cudaStream_t st, int smCount, const PathBuffers& pb, const WaveState& ws, uint32_t buf);
-void launchShade(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const SortKeys& keys);
-void launchShadeBinned(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const SortKeys& keys);
-void launchTail(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf);
+// `slot` >= 0 on the launch that ends a bounce: the bounce's output counts are logged in ws.history[slot]
+void launchShade(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf, int32_t slot, const SortKeys& keys);
+void launchShadeBinned(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf, int32_t slot, const SortKeys& keys);
+void launchShadeInlineNee(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf, int32_t slot, const SortKeys& keys);
+void launchTail(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf, bool inlineNee);
 void launchAccumulate(cudaStream_t st, const float4* result, float4* image, float4* runState, const uint32_t* pixIds, uint32_t nPix, uint32_t nSamples,
                       uint32_t firstSample, uint32_t spr);
 void launchEnvResample(cudaStream_t st, const float4* src, uint32_t W, uint32_t H, float4* dstRgb, float* dstLum, uint32_t S);
 void launchEnvFold(cudaStream_t st, const float* srcMip, float* dstMip, float4* srcQuads, uint32_t dstSize);
 void launchTraceProbe(cudaStream_t st, const DeviceScene& sc, const float* rays8, uint32_t n, int anyHit, uint32_t* hits5);
+void launchMathProbe(cudaStream_t st, int fn, const float* a, const float* b, uint32_t n, float* out);
 void launchBsdfProbe(cudaStream_t st, const float* q14, uint32_t n, float* out4);
 void launchEnvProbe(cudaStream_t st, const DeviceScene& sc, int op, const float* in3, uint32_t n, float* out7);
 void launchPick(cudaStream_t st, const DeviceScene& sc, const DCamera& cam, float x, float y, MsneClick* out);
 void launchPrimaryProbe(cudaStream_t st, const DCamera& cam, const DConstants& k, uint32_t sample, float* rays6, uint32_t* rngState);
 int traceOccupancyBlocksPerSm();
 int shadeOccupancyBlocksPerSm();
+int shadeInlineOccupancyBlocksPerSm();
 
 }  // namespace msne

@@ -216,40 +216,60 @@ struct HdMoonshine {
     std::vector<std::unique_ptr<Sensor>> sensors;
     uint32_t shardRank = 0, shardWorld = 1;
 
-    // wavefront pool
-    uint64_t pathsInFlight = 1ull << 27;   // 128 Mi paths x 308 B = 39 GiB (+ 5 GiB of sort buffers) of the 180 GB HBM; amortises the ~8 ms Russian-roulette tail of a wave
-    PathBuffers pb{};
-    std::vector<DevBuf<float4>> poolBufs;
-    DevBuf<uint4> poolH;
-    DevBuf<Counters> dCounters;
-    DevBuf<uint32_t> dScalars;       // [0] traceTicket [1] traceDone [2] shadeDone [3] maxBounce [4..8] typeCount [9..13] binDone
-    DevBuf<uint32_t> poolTypeList;
-    // ray reordering (kernels.h SortBuffers): keys of the extension (P) and the shadow queue (2 P), a scratch key buffer, the
-    // identity values and the two permutations
-    DevBuf<uint16_t> sortKeysExt, sortKeysShadow, sortKeysTmp;
-    DevBuf<uint32_t> sortIota, sortPermExt, sortPermShadow;
-    DevBuf<uint8_t> sortTemp;
+    // ---- wavefront execution ---------------------------------------------------------------------------------------------
+    // A WAVE = up to P paths (consecutive samples of a chunk of owned pixels) carried from k_generate to k_accumulate. The host
+    // enqueues a whole wave - every bounce's sort / trace / bin / shade launches, then k_tail - WITHOUT waiting for the device:
+    // queue sizes live in device counters that the kernels read, and which launches a bounce gets (sorted or not, binned or
+    // generic shading, how many wavefront bounces before k_tail) is a performance HINT taken from the survival profile of the
+    // last finished wave. Whatever the hint, the image is the same bits (tests assert it). Two wave contexts (own stream, pool,
+    // counters) alternate, so the latency-bound Russian-roulette tail of one wave (k_tail: a few thousand paths, ~150 bounces
+    // deep) runs under the bandwidth-bound head of the next; accumulates are chained by events to stay in sample order.
+    static constexpr int kWaveContexts = 2;
+    static constexpr uint32_t kMaxHistory = 192;   // wavefront bounces logged / scheduled per wave at most (k_tail finishes the rest)
+    static const int kProfEvents = 96;
+    struct WaveCtx {
+        cudaStream_t stream = nullptr;
+        PathBuffers pb{};
+        std::vector<DevBuf<float4>> poolBufs;
+        DevBuf<uint4> poolH;
+        DevBuf<uint32_t> poolTypeList;
+        DevBuf<Counters> dCounters;        // [2] ping-pong
+        DevBuf<uint32_t> dScalars;         // [0] traceTicket [1] traceDone [2] shadeDone [3] maxBounce [4..8] typeCount [9..13] binDone
+        DevBuf<unsigned long long> dRayCounts;
+        DevBuf<Counters> dHistory;         // [kMaxHistory] queue sizes every bounce produced
+        Counters* hostHistory = nullptr;   // pinned copy, valid once evDone has fired
+        // ray reordering (kernels.h SortBuffers): keys of the extension (P) and the shadow queue (2 P), the two permutations,
+        // global histogram + bin cursors of the counting sort
+        DevBuf<uint16_t> sortKeysExt, sortKeysShadow;
+        DevBuf<uint32_t> sortPermExt, sortPermShadow, sortHist, sortCursor;
+        cudaEvent_t evDone = nullptr;      // recorded after the wave's k_accumulate
+        bool pending = false;              // a wave was enqueued and its log not read yet
+        uint32_t bounces = 0;              // wavefront bounces that wave scheduled
+        uint64_t paths = 0;
+        int profUsed = 0;
+        cudaEvent_t profEv[kProfEvents][4]{};   // [0],[1] around k_trace; sorted bounces: [2] before the sort, [3] after the binning pass
+        bool profSorted[kProfEvents]{};
+    };
+    WaveCtx ctx[kWaveContexts];
+    uint64_t pathsInFlight = 1ull << 27;   // over both contexts: 2 x 64 Mi paths x (308 + 18) B = 41 GiB of the 180 GB HBM
     uint64_t sortThreshold = 262144; // extension-ray queues at least this long are traced in sorted order (0 = never)
     bool sortAnyScene = false;       // false: only scenes with >= kSortMinNodes BVH nodes (a 36-triangle Cornell box loses 4 % to the sort)
     static constexpr size_t kSortMinNodes = 2048;
     bool sortActive = false;         // decided per render (renderLaunches)
     SortFrame sortFrame{};           // scene bounds for the origin cells (buildTlas)
-    DevBuf<unsigned long long> dRayCounts;
-    Counters* hostCounters = nullptr;   // pinned ring of 4
-    cudaEvent_t bounceEvents[4]{};
-    cudaEvent_t evStart = nullptr, evStop = nullptr;
-    int traceBlocks = 0, shadeBlocks = 0;
+    cudaEvent_t evStart = nullptr, evStop = nullptr, evAccum[kWaveContexts]{};
+    int traceBlocks = 0, shadeBlocks = 0, shadeInlineBlocks = 0;
     uint32_t maxLeaf = 3;   // triangles per BVH leaf (<= 8: 3-bit count in the leaf reference); 2-3 measured best
-    uint64_t tailThreshold = 32768;   // survivors below this are finished by k_tail (0 = never)
+    uint64_t tailThreshold = 32768;   // once fewer paths than this are expected to survive, k_tail finishes the wave
     bool forceTwoLevel = false;       // MSNE_TWO_LEVEL=1: never use the single-level trace kernel (A/B measurements)
-    bool logBounces = false;          // MSNE_LOG_BOUNCES=1: queue sizes after every bounce on stderr
-    uint64_t binnedThreshold = 262144;   // survivors below this use the single generic shade launch
+    bool logBounces = false;          // MSNE_LOG_BOUNCES=1: queue sizes after every bounce on stderr (printed when the wave's log is read)
+    uint64_t binnedThreshold = 262144;   // bounces expected to shade fewer paths than this use the single generic shade launch
+    int waveContextsInUse = kWaveContexts;   // MSNE_WAVE_CONTEXTS=1: one wave at a time (A/B measurements)
+    // survival profile of the last finished wave: survivalIn[b] = live paths entering bounce b / paths of the wave (b = 0: 1)
+    std::vector<double> survivalIn;
 
     // profiling
     bool profiling = false;
-    static const int kProfEvents = 96;
-    cudaEvent_t profEv[kProfEvents][4]{};   // [0],[1] around k_trace; sorted bounces: [2] before the sort, [3] after the binning pass
-    bool profSorted[kProfEvents]{};
     MsneStats stats{};
 
     // ---- lifecycle ---------------------------------------------------------------------------
@@ -260,14 +280,21 @@ struct HdMoonshine {
         CK(cudaGetDeviceProperties(&prop, device));
         smCount = prop.multiProcessorCount;
         CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-        for (auto& e : bounceEvents) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         CK(cudaEventCreate(&evStart)); CK(cudaEventCreate(&evStop));
-        for (auto& p : profEv) for (auto& e : p) CK(cudaEventCreate(&e));
-        CK(cudaMallocHost((void**)&hostCounters, 4 * sizeof(Counters)));
-        dCounters.alloc(2); dScalars.alloc(16); dRayCounts.alloc(2);
-        CK(cudaMemsetAsync(dCounters.p, 0, 2 * sizeof(Counters), stream));
-        CK(cudaMemsetAsync(dScalars.p, 0, 16 * sizeof(uint32_t), stream));
-        CK(cudaMemsetAsync(dRayCounts.p, 0, 2 * sizeof(unsigned long long), stream));
+        for (auto& e : evAccum) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        for (WaveCtx& c : ctx) {
+            CK(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&c.evDone, cudaEventDisableTiming));
+            for (auto& p : c.profEv) for (auto& e : p) CK(cudaEventCreate(&e));
+            CK(cudaMallocHost((void**)&c.hostHistory, kMaxHistory * sizeof(Counters)));
+            c.dCounters.alloc(2); c.dScalars.alloc(16); c.dRayCounts.alloc(2); c.dHistory.alloc(kMaxHistory);
+            c.sortHist.alloc(2 * 32768); c.sortCursor.alloc(2 * 32768);
+            CK(cudaMemsetAsync(c.dCounters.p, 0, 2 * sizeof(Counters), stream));
+            CK(cudaMemsetAsync(c.dScalars.p, 0, 16 * sizeof(uint32_t), stream));
+            CK(cudaMemsetAsync(c.dRayCounts.p, 0, 2 * sizeof(unsigned long long), stream));
+            CK(cudaMemsetAsync(c.dHistory.p, 0, kMaxHistory * sizeof(Counters), stream));
+            CK(cudaMemsetAsync(c.sortHist.p, 0, 2 * 32768 * sizeof(uint32_t), stream));
+        }
         float lut[512];
         for (int i = 0; i < 256; i++) { lut[i] = srgbToLinear(i); lut[256 + i] = (float)i / 255.0f; }   // UNORM: the same IEEE division a texel fetch would do
         dSrgbLut.upload(lut, 512, stream);
@@ -282,20 +309,27 @@ struct HdMoonshine {
         if (const char* e = getenv("MSNE_LOG_BOUNCES")) logBounces = atoi(e) != 0;
         if (const char* e = getenv("MSNE_TAIL_THRESHOLD")) tailThreshold = strtoull(e, nullptr, 10);
         if (const char* e = getenv("MSNE_SORT_THRESHOLD")) { sortThreshold = strtoull(e, nullptr, 10); sortAnyScene = true; }
+        if (const char* e = getenv("MSNE_WAVE_CONTEXTS")) waveContextsInUse = std::min(kWaveContexts, std::max(1, atoi(e)));
+        if (const char* e = getenv("MSNE_BINNED_THRESHOLD")) binnedThreshold = strtoull(e, nullptr, 10);
         traceBlocks = smCount * std::max(1, traceOccupancyBlocksPerSm());
         shadeBlocks = smCount * std::max(1, shadeOccupancyBlocksPerSm());
+        shadeInlineBlocks = smCount * std::max(1, shadeInlineOccupancyBlocksPerSm());
         CK(cudaStreamSynchronize(stream));
     }
 
     ~HdMoonshine() {
         cudaSetDevice(device);
         if (stream) cudaStreamSynchronize(stream);
+        for (WaveCtx& c : ctx) {
+            if (c.stream) { cudaStreamSynchronize(c.stream); cudaStreamDestroy(c.stream); }
+            if (c.evDone) cudaEventDestroy(c.evDone);
+            for (auto& p : c.profEv) for (auto& e : p) if (e) cudaEventDestroy(e);
+            if (c.hostHistory) cudaFreeHost(c.hostHistory);
+        }
         for (auto& s : sensors) if (s && s->host) cudaFreeHost(s->host);
-        if (hostCounters) cudaFreeHost(hostCounters);
-        for (auto& e : bounceEvents) if (e) cudaEventDestroy(e);
+        for (auto& e : evAccum) if (e) cudaEventDestroy(e);
         if (evStart) cudaEventDestroy(evStart);
         if (evStop) cudaEventDestroy(evStop);
-        for (auto& p : profEv) for (auto& e : p) if (e) cudaEventDestroy(e);
         if (stream) cudaStreamDestroy(stream);
     }
 
@@ -802,120 +836,138 @@ struct HdMoonshine {
     void clearAllSensors() { for (auto& s : sensors) clearSensor(*s); }
 
     // ---- wavefront pool --------------------------------------------------------------------------
-    void ensurePool(uint64_t wanted) {
+    void ensurePool(WaveCtx& c, uint64_t wanted) {
         const uint32_t P = (uint32_t)std::min<uint64_t>(wanted, 0x7FFFFFFFull / 4);
-        if (pb.capacity >= P && pb.capacity != 0) return;
+        if (c.pb.capacity >= P && c.pb.capacity != 0) return;
         // poolBufs: [0],[1] interleaved ray lanes R0/R1 of the two ping-pong buffers (dtypes.h RAY_STRIDE), [2..9] S0,S1,N0,N1 x 2,
         // [10] interleaved shadow-ray lanes Q0/Q1 (2 P rays), [11] result
-        poolBufs.clear();
-        poolBufs.resize(12);
-        for (int i = 0; i < 2; i++) poolBufs[i].alloc((size_t)RAY_STRIDE * P);
-        for (int i = 2; i < 10; i++) poolBufs[i].alloc(P);
-        poolBufs[10].alloc((size_t)RAY_STRIDE * 2 * P);
-        poolBufs[11].alloc(P);
-        poolH.alloc(P);
-        poolTypeList.alloc((size_t)NUM_BINS * P);
-        sortKeysExt.release();   // sized with the pool (ensureSortBuffers)
+        CK(cudaStreamSynchronize(c.stream));
+        c.poolBufs.clear();
+        c.poolBufs.resize(12);
+        for (int i = 0; i < 2; i++) c.poolBufs[i].alloc((size_t)RAY_STRIDE * P);
+        for (int i = 2; i < 10; i++) c.poolBufs[i].alloc(P);
+        c.poolBufs[10].alloc((size_t)RAY_STRIDE * 2 * P);
+        c.poolBufs[11].alloc(P);
+        c.poolH.alloc(P);
+        c.poolTypeList.alloc((size_t)NUM_BINS * P);
+        c.sortKeysExt.release();   // sized with the pool (ensureSortBuffers)
+        PathBuffers& pb = c.pb;
         for (int b = 0; b < 2; b++) {
-            pb.R0[b] = poolBufs[b].p; pb.R1[b] = poolBufs[b].p + 1; pb.S0[b] = poolBufs[2 + b].p; pb.S1[b] = poolBufs[4 + b].p;
-            pb.N0[b] = poolBufs[6 + b].p; pb.N1[b] = poolBufs[8 + b].p;
+            pb.R0[b] = c.poolBufs[b].p; pb.R1[b] = c.poolBufs[b].p + 1; pb.S0[b] = c.poolBufs[2 + b].p; pb.S1[b] = c.poolBufs[4 + b].p;
+            pb.N0[b] = c.poolBufs[6 + b].p; pb.N1[b] = c.poolBufs[8 + b].p;
         }
-        pb.Q0 = poolBufs[10].p; pb.Q1 = poolBufs[10].p + 1; pb.result = poolBufs[11].p; pb.H = poolH.p; pb.typeList = poolTypeList.p; pb.capacity = P;
+        pb.Q0 = c.poolBufs[10].p; pb.Q1 = c.poolBufs[10].p + 1; pb.result = c.poolBufs[11].p; pb.H = c.poolH.p; pb.typeList = c.poolTypeList.p; pb.capacity = P;
     }
-    void ensureSortBuffers() {
-        const size_t P = pb.capacity;
-        if (sortKeysExt.n >= P) return;
-        sortKeysExt.alloc(P); sortKeysShadow.alloc(2 * P); sortKeysTmp.alloc(2 * P);
-        sortIota.alloc(2 * P); sortPermExt.alloc(P); sortPermShadow.alloc(2 * P);
-        sortTemp.alloc(sortTempBytes(2 * P));
-        launchIota(stream, sortIota.p, 2 * P);
-        stats.kernel_launches++;
+    void ensureSortBuffers(WaveCtx& c) {
+        const size_t P = c.pb.capacity;
+        if (c.sortKeysExt.n >= P) return;
+        c.sortKeysExt.alloc(P); c.sortKeysShadow.alloc(2 * P);
+        c.sortPermExt.alloc(P); c.sortPermShadow.alloc(2 * P);
     }
-    SortBuffers sortBuffers() const {
-        return SortBuffers{sortKeysExt.p, sortKeysShadow.p, sortKeysTmp.p, sortIota.p, sortPermExt.p, sortPermShadow.p, sortTemp.p, sortTemp.n};
+    static SortBuffers sortBuffers(const WaveCtx& c) {
+        return SortBuffers{c.sortKeysExt.p, c.sortKeysShadow.p, c.sortPermExt.p, c.sortPermShadow.p, c.sortHist.p, c.sortCursor.p};
     }
-    WaveState waveState() const {
+    static WaveState waveState(const WaveCtx& c) {
         WaveState ws{};
-        ws.counters = dCounters.p; ws.traceTicket = dScalars.p + 0; ws.traceDone = dScalars.p + 1; ws.shadeDone = dScalars.p + 2;
-        ws.maxBounce = dScalars.p + 3; ws.rayCounts = dRayCounts.p; ws.typeCount = dScalars.p + 4; ws.binDone = dScalars.p + 9;
+        uint32_t* sc = c.dScalars.p;
+        ws.counters = c.dCounters.p; ws.traceTicket = sc + 0; ws.traceDone = sc + 1; ws.shadeDone = sc + 2;
+        ws.maxBounce = sc + 3; ws.rayCounts = c.dRayCounts.p; ws.typeCount = sc + 4; ws.binDone = sc + 9; ws.history = c.dHistory.p;
         return ws;
     }
 
-    // one wave: `nSamples` consecutive samples of `nPix` owned pixels starting at pixIds + pixOffset
-    void runWave(Sensor& s, const DCamera& cam, const DeviceScene& sc, const DConstants& k, uint32_t pixOffset, uint32_t nPix, uint32_t firstSample, uint32_t nSamples) {
-        const WaveState ws = waveState();
-        launchGenerate(stream, cam, k, pb, dCounters.p, s.pixIds.p + pixOffset, nPix, nSamples, firstSample);
+    // live paths expected to ENTER bounce b of a wave of n paths, from the last finished wave's log; with no log yet: everything
+    // survives the first four bounces (Russian roulette starts after bounce 3, integrator.hlsl:130), then 72 % per bounce
+    double expectedIn(uint32_t b, uint64_t n) const {
+        if (b == 0) return (double)n;
+        if (b < survivalIn.size()) return survivalIn[b] * (double)n;
+        if (survivalIn.size() > 1) return survivalIn.back() * std::pow(0.8, (double)(b - (survivalIn.size() - 1))) * (double)n;
+        return (double)n * (b < 4 ? 1.0 : std::pow(0.72, (double)(b - 3)));
+    }
+
+    // reads the log of the wave last enqueued on `c` (blocks until that wave is done): survival profile, per-kernel timings
+    void harvest(WaveCtx& c) {
+        if (!c.pending) return;
+        CK(cudaEventSynchronize(c.evDone));
+        c.pending = false;
+        stats.waves++;
+        if (c.bounces && c.paths) {
+            survivalIn.assign(1, 1.0);
+            for (uint32_t b = 0; b < c.bounces; b++) survivalIn.push_back((double)c.hostHistory[b].nLive / (double)c.paths);
+            const Counters& last = c.hostHistory[c.bounces - 1];
+            stats.tail_paths += (uint64_t)last.nLive + last.nDead;
+        }
+        if (logBounces)
+            for (uint32_t b = 0; b < c.bounces; b++)
+                fprintf(stderr, "libmoonshine: bounce %u -> live %u dead %u shadow %u\n", b, c.hostHistory[b].nLive, c.hostHistory[b].nDead, c.hostHistory[b].nShadow);
+        for (int i = 0; i < c.profUsed; i++) {
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, c.profEv[i][0], c.profEv[i][1]));
+            stats.trace_ms += ms; stats.trace_launches++;
+            if (c.profSorted[i]) {
+                CK(cudaEventElapsedTime(&ms, c.profEv[i][2], c.profEv[i][0])); stats.sort_ms += ms;
+                CK(cudaEventElapsedTime(&ms, c.profEv[i][1], c.profEv[i][3])); stats.sort_ms += ms;
+            }
+        }
+        c.profUsed = 0;
+    }
+
+    // one wave: `nSamples` consecutive samples of `nPix` owned pixels starting at pixIds + pixOffset, enqueued on c.stream without
+    // any host synchronisation; `afterAccum` (may be null): the previous wave's accumulate, which this wave's must follow
+    void enqueueWave(WaveCtx& c, Sensor& s, const DCamera& cam, const DeviceScene& sc, const DConstants& k, uint32_t pixOffset, uint32_t nPix,
+                     uint32_t firstSample, uint32_t nSamples, cudaEvent_t afterAccum) {
+        const WaveState ws = waveState(c);
+        const PathBuffers& pb = c.pb;
+        cudaStream_t st = c.stream;
+        const uint64_t nPaths = (uint64_t)nPix * nSamples;
+        const bool inlineNee = k.env_samples > 1 || k.mesh_samples > 1;
+        launchGenerate(st, cam, k, pb, c.dCounters.p, s.pixIds.p + pixOffset, nPix, nSamples, firstSample);
         stats.kernel_launches++;
-        int profUsed = 0;
-        uint64_t lastLive = (uint64_t)nPix * nSamples;   // most recent survivor count known to the host
-        // `in`: exact input counts of the bounce when the host already knows them (sorted bounces), else nullptr
-        auto enqueueBounce = [&](uint32_t b, const Counters* in) {
+        // how many bounces run as wavefront launches before k_tail finishes the stragglers
+        const double tailAt = (double)std::max<uint64_t>(tailThreshold, 1);
+        uint32_t K = 1;
+        const uint32_t kCap = (uint32_t)std::min<uint64_t>((uint64_t)k.max_bounces + 2, kMaxHistory);
+        while (K < kCap && expectedIn(K, nPaths) >= tailAt) K++;
+        auto sortedAt = [&](uint32_t b) { return b >= 1 && sortActive && expectedIn(b, nPaths) >= (double)sortThreshold; };
+        c.profUsed = 0;
+        for (uint32_t b = 0; b < K; b++) {
             const uint32_t buf = b & 1u;
-            const bool prof = profiling && profUsed < kProfEvents;
-            const bool sorted = in != nullptr && sortActive && in->nLive >= sortThreshold;
-            if (prof) profSorted[profUsed] = sorted;
+            const bool prof = profiling && c.profUsed < kProfEvents;
+            const bool sorted = sortedAt(b);
+            if (prof) c.profSorted[c.profUsed] = sorted;
             if (sorted) {
-                if (prof) CK(cudaEventRecord(profEv[profUsed][2], stream));
-                CK(launchSortRays(stream, sortBuffers(), in->nLive, in->nShadow));
-                if (prof) CK(cudaEventRecord(profEv[profUsed][0], stream));
-                launchTraceSorted(stream, traceBlocks, sc, pb, ws, buf, sortPermExt.p, sortPermShadow.p);
-                if (prof) CK(cudaEventRecord(profEv[profUsed][1], stream));
-                launchBin(stream, smCount, pb, ws, buf);
-                if (prof) { CK(cudaEventRecord(profEv[profUsed][3], stream)); profUsed++; }
-                stats.kernel_launches += (in->nLive ? 4 : 0) + (in->nShadow ? 4 : 0) + 1;   // per sort: CUB histogram + exclusive sum + 2 onesweep passes; binning
+                if (prof) CK(cudaEventRecord(c.profEv[c.profUsed][2], st));
+                launchSortRays(st, smCount, sortBuffers(c), c.dCounters.p + buf);
+                if (prof) CK(cudaEventRecord(c.profEv[c.profUsed][0], st));
+                launchTraceSorted(st, traceBlocks, sc, pb, ws, buf, c.sortPermExt.p, c.sortPermShadow.p);
+                if (prof) CK(cudaEventRecord(c.profEv[c.profUsed][1], st));
+                launchBin(st, smCount, pb, ws, buf);
+                if (prof) { CK(cudaEventRecord(c.profEv[c.profUsed][3], st)); c.profUsed++; }
+                stats.kernel_launches += 5;   // count, scan, scatter, trace, bin
             } else {
-                if (prof) CK(cudaEventRecord(profEv[profUsed][0], stream));
-                launchTrace(stream, traceBlocks, sc, pb, ws, buf);
-                if (prof) { CK(cudaEventRecord(profEv[profUsed][1], stream)); profUsed++; }
+                if (prof) CK(cudaEventRecord(c.profEv[c.profUsed][0], st));
+                launchTrace(st, traceBlocks, sc, pb, ws, buf);
+                if (prof) { CK(cudaEventRecord(c.profEv[c.profUsed][1], st)); c.profUsed++; }
+                stats.kernel_launches += 1;
             }
-            // big queues: one material-specialised launch per bin; small queues (tail): one generic launch
-            // the rays this pass queues get their sort keys from it when the next bounce may still be long enough to be sorted
+            // the rays this pass queues get their sort keys from it when the next bounce is going to be traced in sorted order
             SortKeys keys{};
-            if (sortActive && lastLive >= sortThreshold) { keys.ext = sortKeysExt.p; keys.shadow = sortKeysShadow.p; keys.frame = sortFrame; }
-            if (lastLive >= binnedThreshold) { launchShadeBinned(stream, shadeBlocks, sc, k, pb, ws, buf, keys); stats.kernel_launches += 6; }
-            else { launchShade(stream, shadeBlocks, sc, k, pb, ws, buf, keys); stats.kernel_launches += 2; }
-            CK(cudaMemcpyAsync(&hostCounters[b & 3u], dCounters.p + (buf ^ 1u), sizeof(Counters), cudaMemcpyDeviceToHost, stream));
-            CK(cudaEventRecord(bounceEvents[b & 3u], stream));
-        };
-        // keep one bounce queued ahead of the one whose survivor count we wait for
-        const uint32_t maxIter = k.max_bounces + 4;
-        enqueueBounce(0, nullptr);   // primary rays are coherent as generated (8x4 pixel blocks per warp)
-        for (uint32_t b = 0; b < maxIter; b++) {
-            // Long queues (sorted bounces): the radix sort needs the exact item count on the host, so the next bounce is queued
-            // only after this one's counts arrived - a ~20 us bubble against milliseconds of work. Short queues keep one bounce
-            // queued ahead of the count the host waits for.
-            const bool ahead = !(sortActive && lastLive >= sortThreshold);
-            if (ahead) enqueueBounce(b + 1, nullptr);
-            CK(cudaEventSynchronize(bounceEvents[b & 3u]));
-            const Counters c = hostCounters[b & 3u];
-            if (logBounces) fprintf(stderr, "libmoonshine: bounce %u -> live %u dead %u shadow %u\n", b, c.nLive, c.nDead, c.nShadow);
-            lastLive = c.nLive;
-            if (c.nLive + c.nDead == 0) break;   // a bounce b+1 queued ahead then runs on empty queues
-            if (!ahead) enqueueBounce(b + 1, &c);
-            if ((uint64_t)c.nLive + c.nDead < tailThreshold) {
-                // few stragglers left: after the already-queued bounce b+1, trace once more and let k_tail finish
-                // every remaining path in a single launch instead of ~130 launch pairs at the latency floor
-                const uint32_t tb = (b + 2) & 1u;
-                launchTrace(stream, traceBlocks, sc, pb, ws, tb);
-                launchTail(stream, smCount * 4, sc, k, pb, ws, tb);
-                stats.kernel_launches += 2;
-                break;
-            }
+            if (b + 1 < K && sortedAt(b + 1)) { keys.ext = c.sortKeysExt.p; keys.shadow = c.sortKeysShadow.p; keys.frame = sortFrame; }
+            // big queues: one material-specialised launch per bin; small queues: one generic launch
+            if (inlineNee) { launchShadeInlineNee(st, shadeInlineBlocks, sc, k, pb, ws, buf, (int32_t)b, keys); stats.kernel_launches += 1; }
+            else if (expectedIn(b, nPaths) >= (double)binnedThreshold) { launchShadeBinned(st, shadeBlocks, sc, k, pb, ws, buf, (int32_t)b, keys); stats.kernel_launches += 5; }
+            else { launchShade(st, shadeBlocks, sc, k, pb, ws, buf, (int32_t)b, keys); stats.kernel_launches += 1; }
         }
-        launchAccumulate(stream, pb.result, s.image.p, s.runState.p + pixOffset, s.pixIds.p + pixOffset, nPix, nSamples, firstSample, k.samples_per_run);
+        // whatever is still alive (normally < tailThreshold paths; more only when the profile was off): trace once more and let
+        // k_tail finish every remaining path in a single launch instead of ~130 launch pairs at the latency floor
+        launchTrace(st, traceBlocks, sc, pb, ws, K & 1u);
+        launchTail(st, smCount * 4, sc, k, pb, ws, K & 1u, inlineNee);
+        stats.kernel_launches += 2;
+        CK(cudaMemcpyAsync(c.hostHistory, c.dHistory.p, K * sizeof(Counters), cudaMemcpyDeviceToHost, st));
+        if (afterAccum) CK(cudaStreamWaitEvent(st, afterAccum, 0));
+        launchAccumulate(st, pb.result, s.image.p, s.runState.p + pixOffset, s.pixIds.p + pixOffset, nPix, nSamples, firstSample, k.samples_per_run);
         stats.kernel_launches++;
-        if (profUsed) {
-            CK(cudaStreamSynchronize(stream));
-            for (int i = 0; i < profUsed; i++) {
-                float ms = 0;
-                CK(cudaEventElapsedTime(&ms, profEv[i][0], profEv[i][1]));
-                stats.trace_ms += ms; stats.trace_launches++;
-                if (profSorted[i]) {
-                    CK(cudaEventElapsedTime(&ms, profEv[i][2], profEv[i][0])); stats.sort_ms += ms;
-                    CK(cudaEventElapsedTime(&ms, profEv[i][1], profEv[i][3])); stats.sort_ms += ms;
-                }
-            }
-        }
+        CK(cudaEventRecord(c.evDone, st));
+        c.pending = true; c.bounces = K; c.paths = nPaths;
     }
 
     // offline/main.zig:131-165: n launches of samples_per_run samples each; sensor.sample_count advances
@@ -928,26 +980,48 @@ struct HdMoonshine {
         const DCamera cam = makeCamera(lens, s.extent.width, s.extent.height);
         const uint64_t totalSamples = (uint64_t)nLaunches * k.samples_per_run;
         if (s.nPix == 0 || totalSamples == 0) { s.sample_count += (uint32_t)totalSamples; return; }
-        ensurePool(std::min<uint64_t>(pathsInFlight, (uint64_t)s.nPix * totalSamples));
-        sortActive = sortThreshold != 0 && pb.capacity >= sortThreshold && (sortAnyScene || blasNodePool.size() + tlasHostNodes.size() >= kSortMinNodes);
-        if (sortActive) ensureSortBuffers();
-        const uint32_t P = pb.capacity;
-        CK(cudaEventRecord(evStart, stream));
+        const uint64_t totalPaths = (uint64_t)s.nPix * totalSamples;
+        // pool per context: half of the paths in flight; a render that fits one context uses only that one
+        const int nCtx = waveContextsInUse;
+        const uint64_t perCtx = std::max<uint64_t>(1, pathsInFlight / (uint64_t)nCtx);
+        const uint64_t wantP = std::min<uint64_t>(perCtx, totalPaths);
+        ensurePool(ctx[0], wantP);
+        const uint32_t P = (uint32_t)std::min<uint64_t>(ctx[0].pb.capacity, wantP);
         const uint32_t pixChunk = std::min(s.nPix, P);
         const uint32_t samplesPerWave = std::max(1u, P / pixChunk);
+        const uint64_t nWaves = (uint64_t)((s.nPix + pixChunk - 1) / pixChunk) * ((totalSamples + samplesPerWave - 1) / samplesPerWave);
+        const int used = nWaves > 1 ? nCtx : 1;
+        for (int i = 1; i < used; i++) ensurePool(ctx[i], P);
+        size_t bvhNodes = blasNodePool.size() + tlasHostNodes.size();
+        sortActive = sortThreshold != 0 && P >= sortThreshold && (sortAnyScene || bvhNodes >= kSortMinNodes);
+        if (sortActive) for (int i = 0; i < used; i++) ensureSortBuffers(ctx[i]);
+        // everything queued on the main stream so far (uploads, sensor clears) precedes the waves; the waves' streams start at evStart
+        CK(cudaEventRecord(evStart, stream));
+        for (int i = 0; i < used; i++) CK(cudaStreamWaitEvent(ctx[i].stream, evStart, 0));
+        uint64_t wave = 0;
+        cudaEvent_t lastAccum = nullptr;
         for (uint32_t p0 = 0; p0 < s.nPix; p0 += pixChunk) {
             const uint32_t np = std::min(pixChunk, s.nPix - p0);
             for (uint64_t s0 = 0; s0 < totalSamples; s0 += samplesPerWave) {
                 const uint32_t ns = (uint32_t)std::min<uint64_t>(samplesPerWave, totalSamples - s0);
-                runWave(s, cam, sc, k, p0, np, s.sample_count + (uint32_t)s0, ns);
+                WaveCtx& c = ctx[wave % (uint64_t)used];
+                harvest(c);   // the wave before last: its log feeds this wave's schedule while the last one keeps the GPU busy
+                enqueueWave(c, s, cam, sc, k, p0, np, s.sample_count + (uint32_t)s0, ns, lastAccum);
+                cudaEvent_t ev = evAccum[wave % (uint64_t)kWaveContexts];
+                CK(cudaEventRecord(ev, c.stream));
+                lastAccum = ev;
+                wave++;
             }
         }
+        for (int i = 0; i < used; i++) CK(cudaStreamWaitEvent(stream, ctx[i].evDone, 0));
         CK(cudaEventRecord(evStop, stream));
         CK(cudaStreamSynchronize(stream));
+        stats.host_syncs++;
+        for (int i = 0; i < used; i++) harvest(ctx[i]);
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, evStart, evStop));
         stats.device_ms += ms;
-        stats.samples += (uint64_t)s.nPix * totalSamples;
+        stats.samples += totalPaths;
         s.sample_count += (uint32_t)totalSamples;
     }
 
@@ -959,13 +1033,17 @@ struct HdMoonshine {
 
     void fetchStats(MsneStats& out) {
         use();
-        unsigned long long rc[2] = {0, 0};
-        uint32_t sc[4] = {0, 0, 0, 0};
-        CK(cudaMemcpyAsync(rc, dRayCounts.p, sizeof(rc), cudaMemcpyDeviceToHost, stream));
-        CK(cudaMemcpyAsync(sc, dScalars.p, sizeof(sc), cudaMemcpyDeviceToHost, stream));
-        CK(cudaStreamSynchronize(stream));
         out = stats;
-        out.rays_closest = rc[0]; out.rays_shadow = rc[1]; out.max_bounce_reached = sc[3];
+        out.rays_closest = 0; out.rays_shadow = 0; out.max_bounce_reached = 0;
+        for (WaveCtx& c : ctx) {
+            unsigned long long rc[2] = {0, 0};
+            uint32_t scal[4] = {0, 0, 0, 0};
+            CK(cudaMemcpyAsync(rc, c.dRayCounts.p, sizeof(rc), cudaMemcpyDeviceToHost, c.stream));
+            CK(cudaMemcpyAsync(scal, c.dScalars.p, sizeof(scal), cudaMemcpyDeviceToHost, c.stream));
+            CK(cudaStreamSynchronize(c.stream));
+            out.rays_closest += rc[0]; out.rays_shadow += rc[1];
+            out.max_bounce_reached = std::max<uint64_t>(out.max_bounce_reached, scal[3]);
+        }
         out.static_blas_builds = stats_static_builds; out.tlas_builds = stats_tlas_builds; out.tlas_refits = stats_tlas_refits;
     }
 };
@@ -1218,10 +1296,7 @@ void HdMoonshineSetLens(HdMoonshine* h, LensHandle i, Lens l) {
 // ---- extensions ------------------------------------------------------------------------------------
 bool HdMoonshineExtSetSpecConstants(HdMoonshine* h, const MsneSpecConstants* c) {
     LOCK(h);
-    if (c->env_samples_per_bounce > 1 || c->mesh_samples_per_bounce > 1 || c->samples_per_run == 0) {
-        g_lastError = "env/mesh samples per bounce must be 0 or 1 and samples_per_run >= 1";
-        return false;
-    }
+    if (c->samples_per_run == 0) { g_lastError = "samples_per_run must be >= 1"; return false; }
     try { h->use(); h->consts = *c; h->clearAllSensors(); return true; } catch (const std::exception& e) { g_lastError = e.what(); return false; }
 }
 void HdMoonshineExtGetSpecConstants(const HdMoonshine* h, MsneSpecConstants* c) {
@@ -1283,7 +1358,11 @@ void HdMoonshineExtSetRaySorting(HdMoonshine* h, uint64_t minRays) {
     if (minRays == UINT64_MAX) { h->sortThreshold = 262144; h->sortAnyScene = false; }
     else { h->sortThreshold = minRays; h->sortAnyScene = true; }
 }
-void HdMoonshineExtSetPathsInFlight(HdMoonshine* h, uint64_t n) { LOCK(h); h->pathsInFlight = n ? n : (1ull << 27); h->pb.capacity = 0; }
+void HdMoonshineExtSetPathsInFlight(HdMoonshine* h, uint64_t n) {
+    LOCK(h);
+    h->pathsInFlight = n ? n : (1ull << 27);
+    for (HdMoonshine::WaveCtx& c : h->ctx) c.pb.capacity = 0;   // pools are re-sized by the next render
+}
 void HdMoonshineExtSetProfiling(HdMoonshine* h, bool on) { LOCK(h); h->profiling = on; }
 void HdMoonshineExtGetStats(const HdMoonshine* h, MsneStats* out) {
     HdMoonshine* m = const_cast<HdMoonshine*>(h);
@@ -1295,10 +1374,11 @@ void HdMoonshineExtResetStats(HdMoonshine* h) {
     ABORT_ON_THROW(
         h->use();
         h->stats = MsneStats{};
-        if (const char* e = getenv("MSNE_BINNED_THRESHOLD")) h->binnedThreshold = strtoull(e, nullptr, 10);
-        CK(cudaMemsetAsync(h->dRayCounts.p, 0, 2 * sizeof(unsigned long long), h->stream));
-        CK(cudaMemsetAsync(h->dScalars.p + 3, 0, sizeof(uint32_t), h->stream));
-        CK(cudaStreamSynchronize(h->stream));
+        for (HdMoonshine::WaveCtx& c : h->ctx) {
+            CK(cudaMemsetAsync(c.dRayCounts.p, 0, 2 * sizeof(unsigned long long), c.stream));
+            CK(cudaMemsetAsync(c.dScalars.p + 3, 0, sizeof(uint32_t), c.stream));
+            CK(cudaStreamSynchronize(c.stream));
+        }
     )
 }
 
@@ -1366,6 +1446,19 @@ bool HdMoonshineExtPrimaryRays(HdMoonshine* h, SensorHandle s, LensHandle l, uin
         h->stats.kernel_launches++;
         CK(cudaMemcpyAsync(rays6, dr.p, 6 * n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaMemcpyAsync(rngState, ds.p, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return true;
+    } catch (const std::exception& e) { g_lastError = e.what(); return false; }
+}
+bool HdMoonshineExtMathProbe(HdMoonshine* h, int fn, const float* a, const float* b, size_t n, float* out) {
+    LOCK(h);
+    try {
+        h->use();
+        DevBuf<float> da, db, dout;
+        da.upload(a, n, h->stream); db.upload(b, n, h->stream); dout.alloc(n);
+        launchMathProbe(h->stream, fn, da.p, db.p, (uint32_t)n, dout.p);
+        h->stats.kernel_launches++;
+        CK(cudaMemcpyAsync(out, dout.p, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
         CK(cudaStreamSynchronize(h->stream));
         return true;
     } catch (const std::exception& e) { g_lastError = e.what(); return false; }

@@ -64,7 +64,8 @@ class MsneMaterialInfo(C.Structure):
 class MsneStats(C.Structure):
     _fields_ = [("rays_closest", C.c_uint64), ("rays_shadow", C.c_uint64), ("samples", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("device_ms", C.c_double), ("trace_ms", C.c_double), ("trace_launches", C.c_uint64), ("max_bounce_reached", C.c_uint64),
-                ("static_blas_builds", C.c_uint64), ("tlas_builds", C.c_uint64), ("tlas_refits", C.c_uint64), ("sort_ms", C.c_double)]
+                ("static_blas_builds", C.c_uint64), ("tlas_builds", C.c_uint64), ("tlas_refits", C.c_uint64), ("sort_ms", C.c_double),
+                ("waves", C.c_uint64), ("host_syncs", C.c_uint64), ("tail_paths", C.c_uint64)]
 
 
 class MsneClickData(C.Structure):   # input.hlsl:1-6
@@ -124,6 +125,7 @@ SIGNATURES = {
     "HdMoonshineExtPick": (C.c_bool, [_VP, _U32, _U32, F32x2, _VP]),
     "HdMoonshineExtTraceRays": (C.c_bool, [_VP, _VP, C.c_size_t, C.c_bool, _VP]),
     "HdMoonshineExtPrimaryRays": (C.c_bool, [_VP, _U32, _U32, _U32, _VP, _VP]),
+    "HdMoonshineExtMathProbe": (C.c_bool, [_VP, C.c_int, _VP, _VP, C.c_size_t, _VP]),
     "HdMoonshineExtBsdfProbe": (C.c_bool, [_VP, _VP, C.c_size_t, _VP]),
     "HdMoonshineExtEnvProbe": (C.c_bool, [_VP, C.c_int, _VP, C.c_size_t, _VP]),
     "HdMoonshineExtGetEnvSize": (_U32, [_VP]),
@@ -364,6 +366,14 @@ class HdMoonshine:
         if not self.L.HdMoonshineExtPrimaryRays(self.h, sensor, lens, sample, _p(rays), _p(st)):
             raise RuntimeError("HdMoonshineExtPrimaryRays: " + self.last_error())
         return rays, st
+
+    def math_probe(self, fn, a, b=None):
+        a = np.ascontiguousarray(a, np.float32)
+        b = np.zeros_like(a) if b is None else np.ascontiguousarray(b, np.float32)
+        out = np.zeros_like(a)
+        if not self.L.HdMoonshineExtMathProbe(self.h, fn, _p(a), _p(b), a.size, _p(out)):
+            raise RuntimeError("HdMoonshineExtMathProbe: " + self.last_error())
+        return out
 
     def bsdf_batch(self, queries14):
         q = np.ascontiguousarray(queries14, np.float32).reshape(-1, 14)

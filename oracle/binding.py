@@ -50,6 +50,7 @@ def lib():
         L.OracleRenderDiag.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p]
         L.OracleEnvProbe.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p]
         L.OracleBsdfBatch.argtypes = [C.c_size_t, C.c_void_p, C.c_void_p]
+        L.OracleMathProbe.argtypes = [C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
         L.OracleHashPcg.restype = C.c_uint32
         L.OracleHashPcg.argtypes = [C.c_uint32]
         L.OracleHashLcg.restype = C.c_uint32
@@ -219,6 +220,15 @@ class Oracle:
 def rng_floats(s, x, y, n):
     out = np.zeros(n, np.float32)
     lib().OracleRngFloats(s, x, y, n, _p(out))
+    return out
+
+
+def math_probe(fn, a, b=None):
+    """The defined transcendentals of oracle/utils.h: fn 0 sin, 1 cos, 2 log, 3 atan2(a, b), 4 acos."""
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.zeros_like(a) if b is None else np.ascontiguousarray(b, np.float32)
+    out = np.zeros_like(a)
+    lib().OracleMathProbe(fn, a.size, _p(a), _p(b), _p(out))
     return out
 
 

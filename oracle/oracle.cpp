@@ -256,6 +256,7 @@ void OracleEnvProbe(Oracle* o, int op, size_t n, const float* in3, float* out7) 
 }
 // batched OracleBsdf: queries = n x {type, color rgb, metalness, roughness, ior, op, a.xyz, w_o.xyz} (14 floats; type/op as floats)
 void OracleBsdfBatch(size_t n, const float* q14, float* out4);
+void OracleMathProbe(int fn, size_t n, const float* a, const float* b, float* out);
 uint32_t OracleAliasCount(Oracle* o) { return (uint32_t)o->sc.aliasTable.size(); }
 void OracleAliasData(Oracle* o, void* out20) { std::memcpy(out20, o->sc.aliasTable.data(), o->sc.aliasTable.size() * sizeof(AliasEntry)); }
 void OracleWorldToInstance(Oracle* o, uint32_t inst, float* out12) { std::memcpy(out12, o->sc.instances[inst].worldToInstance.m, 48); }
@@ -275,6 +276,18 @@ void OracleBsdf(uint32_t type, const float* params6, int op, const float* w_i, c
     else { MaterialSample s = v.sample(wo, {w_i[0], w_i[1]}); out4[0] = s.dirFs.x; out4[1] = s.dirFs.y; out4[2] = s.dirFs.z; out4[3] = s.pdf; }
 }
 
+// the defined transcendentals (utils.h): fn 0 sin(a), 1 cos(a), 2 log(a), 3 atan2(a, b), 4 acos(a)
+void OracleMathProbe(int fn, size_t n, const float* a, const float* b, float* out) {
+    for (size_t i = 0; i < n; i++) {
+        switch (fn) {
+            case 0: out[i] = sinDef(a[i]); break;
+            case 1: out[i] = cosDef(a[i]); break;
+            case 2: out[i] = logDef(a[i]); break;
+            case 3: out[i] = atan2Def(a[i], b[i]); break;
+            default: out[i] = acosDef(a[i]); break;
+        }
+    }
+}
 void OracleBsdfBatch(size_t n, const float* q14, float* out4) {
     for (size_t i = 0; i < n; i++) {
         const float* q = q14 + 14 * i;

@@ -1,7 +1,9 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see vec.h).
 // CPU restatement of /root/reference/shaders/utils/{random,math,mappings}.hlsl.
 // Every function cites the HLSL lines it follows. pow(x,2)/pow(x,5) are restated as explicit
-// multiplications; sin/cos/log/atan2/acos are libm's binary32 versions.
+// multiplications. sin/cos/log/atan2/acos: the HLSL intrinsics have implementation-defined
+// precision, so they are DEFINED here (sinDef ... acosDef below) as fixed sequences of IEEE binary32
+// operations; the CUDA path states the same sequences independently (device_math.cuh) and must agree bit for bit.
 #pragma once
 #include "vec.h"
 
@@ -69,6 +71,66 @@ inline void coordinateSystem(float3 v1, float3& v2, float3& v3) {               
     v3 = cross(v2, v1);
 }
 
+// ---- defined binary32 transcendentals ------------------------------------------------------
+// Every operation is a correctly rounded IEEE binary32 +, -, *, / or sqrt in the order written (no FMA contraction), so any
+// conforming implementation returns the same bits. Accuracy (tests/test_oracle_kat.py, against float64): sin/cos <= 2 ulp on
+// [-2 pi, 4 pi], log <= 2 ulp on [2^-24, 1], atan2 <= 3 ulp, acos <= 4 ulp away from +-1 - the class of a GPU's own intrinsics.
+// sin/cos: Cody-Waite reduction by multiples of pi/2 (three-part constant; exact products for |x| < 1e5), then the Cephes
+// single-precision minimax polynomials on [-pi/4, pi/4].
+inline void sinCosDef(float x, float& s, float& c) {
+    const float q = std::nearbyint(x * 0.636619772367581343f);          // round to nearest, ties to even
+    float r = x - q * 1.5703125f;
+    r = r - q * 4.837512969970703125e-4f;
+    r = r - q * 7.54978995489188216e-8f;
+    const float z = r * r;
+    const float sp = ((-1.9515295891e-4f * z + 8.3321608736e-3f) * z - 1.6666654611e-1f) * z * r + r;
+    float cp = ((2.443315711809948e-5f * z - 1.388731625493765e-3f) * z + 4.166664568298827e-2f) * z * z;
+    cp = cp - 0.5f * z;
+    cp = cp + 1.0f;
+    switch ((int32_t)q & 3) {
+        case 0: s = sp; c = cp; break;
+        case 1: s = cp; c = -sp; break;
+        case 2: s = -sp; c = -cp; break;
+        default: s = -cp; c = sp; break;
+    }
+}
+inline float sinDef(float x) { float s, c; sinCosDef(x, s, c); return s; }
+inline float cosDef(float x) { float s, c; sinCosDef(x, s, c); return c; }
+// log of a positive normal number: x = m 2^e with m in [sqrt(1/2), sqrt(2)), Cephes logf polynomial in m - 1
+inline float logDef(float x) {
+    const int32_t bits = as_int(x);
+    int32_t e = ((bits >> 23) & 0xFF) - 126;
+    float m = as_float((bits & 0x007FFFFF) | 0x3F000000);                // [0.5, 1)
+    if (m < 0.707106781186547524f) { e -= 1; m = (m + m) - 1.0f; } else { m = m - 1.0f; }
+    const float z = m * m;
+    float y = ((((((((7.0376836292e-2f * m - 1.1514610310e-1f) * m + 1.1676998740e-1f) * m - 1.2420140846e-1f) * m + 1.4249322787e-1f) * m
+                 - 1.6668057665e-1f) * m + 2.0000714765e-1f) * m - 2.4999993993e-1f) * m + 3.3333331174e-1f) * m * z;
+    const float fe = (float)e;
+    y = y + -2.12194440e-4f * fe;
+    y = y - 0.5f * z;
+    float r = m + y;
+    r = r + 0.693359375f * fe;
+    return r;
+}
+// atan of x >= 0 (Cephes atanf: two argument reductions, degree-4 polynomial in x^2)
+inline float atanPosDef(float x) {
+    float y0 = 0.0f;
+    if (x > 2.414213562373095f) { y0 = 1.5707963267948966f; x = -(1.0f / x); }
+    else if (x > 0.4142135623730950f) { y0 = 0.7853981633974483f; x = (x - 1.0f) / (x + 1.0f); }
+    const float z = x * x;
+    const float p = (((8.05374449538e-2f * z - 1.38776856032e-1f) * z + 1.99777106478e-1f) * z - 3.33329491539e-1f) * z * x + x;
+    return y0 + p;
+}
+inline float atan2Def(float y, float x) {
+    const float ax = std::fabs(x), ay = std::fabs(y);
+    float a;
+    if (ax == 0.0f) a = ay == 0.0f ? 0.0f : 1.5707963267948966f;
+    else a = atanPosDef(ay / ax);
+    if (x < 0.0f) a = 3.14159265358979323846f - a;
+    return y < 0.0f ? -a : a;
+}
+inline float acosDef(float z) { return 2.0f * atan2Def(std::sqrt(1.0f - z), std::sqrt(1.0f + z)); }
+
 // ---- mappings.hlsl ----------------------------------------------------------------------
 inline float2 squareToTriangle(float2 sq) {                                        // :5-9
     float a = 1 - std::sqrt(1 - sq.x);
@@ -78,9 +140,9 @@ inline float2 squareToTriangle(float2 sq) {                                     
 inline float2 squareToGaussian(float2 sq) {                                        // :11-17
     const float u1 = 1.0f - sq.x;
     const float u2 = sq.y;
-    const float r = std::sqrt(-2.0f * std::log(u1));
+    const float r = std::sqrt(-2.0f * logDef(u1));
     const float theta = 2 * PI * u2;
-    return r * f2(std::cos(theta), std::sin(theta));
+    return r * f2(cosDef(theta), sinDef(theta));
 }
 inline float2 squareToUniformDiskConcentric(float2 sq) {                           // :19-37
     float2 uOffset = 2.0f * sq - f2(1.0f, 1.0f);
@@ -93,7 +155,7 @@ inline float2 squareToUniformDiskConcentric(float2 sq) {                        
         r = uOffset.y;
         theta = (PI / 2) - (PI / 4) * (uOffset.x / uOffset.y);
     }
-    return r * f2(std::cos(theta), std::sin(theta));
+    return r * f2(cosDef(theta), sinDef(theta));
 }
 inline float3 squareToCosineHemisphere(float2 sq) {                                // :39-44
     float2 d = squareToUniformDiskConcentric(sq);
@@ -101,12 +163,12 @@ inline float3 squareToCosineHemisphere(float2 sq) {                             
     return {d.x, d.y, z};
 }
 inline float3 sphericalToCartesian(float sinTheta, float cosTheta, float phi) {    // :53-55
-    return {sinTheta * std::cos(phi), sinTheta * std::sin(phi), cosTheta};
+    return {sinTheta * cosDef(phi), sinTheta * sinDef(phi), cosTheta};
 }
 inline float2 cartesianToSpherical(float3 v) {                                     // :59-64
-    float p = std::atan2(v.y, v.x);
+    float p = atan2Def(v.y, v.x);
     float phi = (p < 0) ? (p + 2 * PI) : p;
-    float theta = std::acos(v.z);
+    float theta = acosDef(v.z);
     return {phi, theta};
 }
 inline float3 squareToEqualAreaSphere(float2 sq) {                                 // :67-83
@@ -117,8 +179,8 @@ inline float3 squareToEqualAreaSphere(float2 sq) {                              
     const float r = 1.0f - d;
     const float phi = (r == 0.0f ? 1.0f : (uvp.y - uvp.x) / r + 1.0f) * PI / 4.0f;
     const float3 signs = {signf(uv.x), signf(uv.y), signf(signedDistance)};
-    return signs * f3(std::cos(phi) * r * std::sqrt(2.0f - r * r),
-                      std::sin(phi) * r * std::sqrt(2.0f - r * r),
+    return signs * f3(cosDef(phi) * r * std::sqrt(2.0f - r * r),
+                      sinDef(phi) * r * std::sqrt(2.0f - r * r),
                       1.0f - r * r);
 }
 inline float2 squareToEqualAreaSphereInverse(float3 dir) {                         // :85-99
@@ -126,7 +188,7 @@ inline float2 squareToEqualAreaSphereInverse(float3 dir) {                      
     const float r = std::sqrt(1.0f - xyz.z);
     float phi = (xyz.x == 0.0f && xyz.y == 0.0f)
                     ? 0.0f
-                    : std::atan2(std::fmin(xyz.x, xyz.y), std::fmax(xyz.x, xyz.y)) * 2.0f / PI;
+                    : atan2Def(std::fmin(xyz.x, xyz.y), std::fmax(xyz.x, xyz.y)) * 2.0f / PI;
     if (xyz.x < xyz.y) phi = 1.0f - phi;
     float2 uv = {r - phi * r, phi * r};
     if (dir.z < 0) uv = f2(1.0f, 1.0f) - f2(uv.y, uv.x);

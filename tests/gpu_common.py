@@ -32,3 +32,8 @@ def random_rays(seed, n, center, radius, tmax=1e12):
     rays[:, 4:7] = d
     rays[:, 7] = tmax
     return rays
+
+
+def identical_fraction(a, b):
+    """fraction of pixels whose four components are the same bits"""
+    return float((a.view(np.uint32) == b.view(np.uint32)).all(axis=-1).mean())

@@ -221,9 +221,33 @@ def test_textured_mesh_light_in_both_attribute_modes(indexed):
 
 def test_spec_constant_limits_are_rejected():
     m = hydra.HdMoonshine()
-    c = scenes.Constants(env_samples_per_bounce=2)
+    c = scenes.Constants(samples_per_run=0)
     with pytest.raises(ValueError):
         m.SetSpecConstants(c)
+
+
+@pytest.mark.parametrize("maker,env,mesh", [
+    (scenes.material_zoo, 2, 3),
+    (lambda: scenes.cornell_box((64, 64)), 0, 4),
+    (lambda: scenes.mesh_light_stress(6, (48, 48)), 3, 2),
+    (lambda: scenes.bathroom((96, 54), detail=0.03), 2, 2),
+])
+def test_more_than_one_light_sample_per_bounce(maker, env, mesh):
+    """integrator.hlsl:141-150 loops env_samples_per_bounce / mesh_samples_per_bounce times (pipeline.zig:319-327 lets any count
+    through): RNG draw order of SURVEY appendix B, contributions added sample by sample, each divided by its count."""
+    sc = maker()
+    sc.constants.env_samples_per_bounce, sc.constants.mesh_samples_per_bounce = env, mesh
+    g, stats, _ = gpu_render(sc, 2)
+    r, counts, _ = oracle_render(sc, 2)
+    assert within_tol_fraction(g, r, rel=2e-4) >= 0.99
+    assert abs(int(stats.rays_closest) - int(counts[0])) <= max(4, counts[0] * 3e-3)
+    assert 0 < stats.rays_shadow <= counts[1]
+    assert stats.rays_shadow > 1.2 * stats.rays_closest or env + mesh < 3   # really more than one shadow ray per hit
+    np.testing.assert_array_equal(g[..., 3], 2.0)
+    # same image whatever the wave size (one sample per wave vs everything in one wave)
+    b, sb, _ = gpu_render(sc, 2, paths_in_flight=sc.extent[0] * sc.extent[1])
+    np.testing.assert_array_equal(g.view(np.uint32), b.view(np.uint32))
+    assert (stats.rays_closest, stats.rays_shadow) == (sb.rays_closest, sb.rays_shadow)
 
 
 def test_library_tile_ownership_matches_python_mirror():

@@ -11,7 +11,7 @@ import pytest
 
 from moonshine_b200 import hydra, scenes
 from oracle.binding import Oracle
-from gpu_common import gpu_render, random_rays, within_tol_fraction
+from gpu_common import gpu_render, identical_fraction, random_rays, within_tol_fraction
 
 pytestmark = pytest.mark.gpu
 
@@ -29,7 +29,7 @@ def test_cfg2_cornell_512_every_pixel():
     scenes.load_scene(o, sc)
     r, counts = o.render(sc.lens, 512, 512, n_launches=2)
     ok = _ok_mask(g, r)
-    print(f"cfg2 512x512x2: pixels within 1e-4: {ok.mean():.6f}; closest rays gpu {stats.rays_closest} oracle {int(counts[0])}")
+    print(f"cfg2 512x512x2: bit-identical pixels {identical_fraction(g, r):.6f}; pixels within 1e-4: {ok.mean():.6f}; closest rays gpu {stats.rays_closest} oracle {int(counts[0])}")
     assert ok.mean() >= 0.999
     np.testing.assert_array_equal(g[..., 3], 2.0)
     assert abs(int(stats.rays_closest) - int(counts[0])) <= counts[0] * 1e-3
@@ -47,7 +47,7 @@ def test_cfg3_full_size_every_pixel():
     ok = _ok_mask(g, r)
     ok5 = _ok_mask(g, r, rel=5e-2)
     sharp = min_alpha < 0.01          # some bounce of the pixel's path hit GGX with alpha < 0.01 (chrome, polished ceramic)
-    print(f"cfg3 full: all pixels within 1e-4: {ok.mean():.6f}, within 5e-2: {ok5.mean():.6f}; "
+    print(f"cfg3 full: bit-identical pixels {identical_fraction(g, r):.6f}; all pixels within 1e-4: {ok.mean():.6f}, within 5e-2: {ok5.mean():.6f}; "
           f"pixels touching alpha<0.01: {sharp.mean():.4f} (within 1e-4: {ok[sharp].mean():.4f}); "
           f"others within 1e-4: {ok[~sharp].mean():.6f}; closest rays gpu {stats.rays_closest} oracle {int(counts[0])}, "
           f"shadow gpu {stats.rays_shadow} oracle {int(counts[1])}")
@@ -99,7 +99,8 @@ def test_cfg5_million_instances():
     r, counts = o.render(sc.lens, 2048, 2048, pixel_stride=stride)
     sel = (np.arange(2048 * 2048) % stride == 0).reshape(2048, 2048)
     ok = _ok_mask(g, r)[sel]
-    print(f"cfg5 10^6 instances: {sel.sum()} pixels compared, within 1e-4: {ok.mean():.6f}")
+    same = (g.view(np.uint32) == r.view(np.uint32)).all(axis=-1)[sel]
+    print(f"cfg5 10^6 instances: {sel.sum()} pixels compared, bit-identical {same.mean():.6f}, within 1e-4: {ok.mean():.6f}")
     assert ok.mean() >= 0.998
     assert np.isfinite(g).all()
     st = m.GetStats()

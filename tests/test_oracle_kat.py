@@ -239,3 +239,33 @@ def test_object_picker_follows_input_hlsl():
     # the triangle's apex points up (+z): it is hit near the top of the image (small y) but not near the bottom
     top, bottom = o.pick(sc.lens, 64, 64, 0.5, 0.3), o.pick(sc.lens, 64, 64, 0.5, 0.95)
     assert top is not None and bottom is None
+
+
+def _ulp_err(got, ref64):
+    ulp = np.maximum(np.spacing(np.abs(ref64.astype(np.float32))).astype(np.float64), np.finfo(np.float32).tiny)
+    return np.abs(got.astype(np.float64) - ref64) / ulp
+
+
+def test_defined_transcendentals_accuracy():
+    """sin/cos/log/atan2/acos are DEFINED as fixed IEEE binary32 operation sequences (oracle/utils.h) because the
+    HLSL intrinsics they stand for have implementation-defined precision. They must still BE those functions: error against
+    float64 in the class of a GPU's intrinsics, over the ranges the shaders use (mappings.hlsl:11-99)."""
+    from oracle import binding as ob
+    rs = np.random.RandomState(0)
+    x = np.concatenate([rs.uniform(-2 * np.pi, 4 * np.pi, 400_000), np.linspace(0, 2 * np.pi, 50_001)]).astype(np.float32)
+    for fn, f in ((0, np.sin), (1, np.cos)):
+        g, ref = ob.math_probe(fn, x), f(x.astype(np.float64))
+        assert np.abs(g - ref).max() <= 1.2e-7                                  # absolute: 1 ulp of 1.0
+        assert _ulp_err(g, ref)[np.abs(ref) > 1e-3].max() <= 2.0
+    u = np.concatenate([rs.uniform(2.0 ** -24, 1, 400_000), 1 - np.arange(1, 5000) * 2.0 ** -24, np.arange(1, 5000) * 2.0 ** -24]).astype(np.float32)
+    g, ref = ob.math_probe(2, u), np.log(u.astype(np.float64))
+    assert _ulp_err(g, ref)[np.abs(ref) > 1e-3].max() <= 2.0 and np.abs(g - ref)[np.abs(ref) <= 1e-3].max() <= 1e-9
+    y, xx = rs.uniform(-1, 1, 400_000).astype(np.float32), rs.uniform(-1, 1, 400_000).astype(np.float32)
+    assert _ulp_err(ob.math_probe(3, y, xx), np.arctan2(y.astype(np.float64), xx.astype(np.float64))).max() <= 3.5
+    z = rs.uniform(-1, 1, 400_000).astype(np.float32)
+    assert _ulp_err(ob.math_probe(4, z), np.arccos(z.astype(np.float64))).max() <= 4.5
+    # exact anchors
+    np.testing.assert_array_equal(ob.math_probe(0, np.array([0.0], np.float32)), [0.0])
+    np.testing.assert_array_equal(ob.math_probe(1, np.array([0.0], np.float32)), [1.0])
+    np.testing.assert_array_equal(ob.math_probe(2, np.array([1.0], np.float32)), [0.0])
+    np.testing.assert_array_equal(ob.math_probe(3, np.array([0.0, 1.0], np.float32), np.array([1.0, 0.0], np.float32)), np.array([0.0, np.pi / 2], np.float32))
