@@ -7,7 +7,7 @@ Workload (config.workload): cfg3, the procedural "Salle-de-bain-class" bathroom 
 rank owns (default 64 spp = one 128 Mi-path wave at 1080p; the default 16 timed steps are the full 1024 spp of the metric config). With N
 GPUs the image is sharded into 32x32 tiles round-robin over ranks and each step renders batch_spp*N samples
 of the rank's tiles (weak scaling: per-GPU work fixed), followed by ONE NCCL reduce of the RGBA32F radiance
-buffer to rank 0 inside the timed region.
+buffer to rank 0 inside the timed region - issued by the library itself (HdMoonshineExtCommInit / CommReduceSensor).
 
   value    Mrays/s = (closest-hit + shadow rays traced by all ranks) / max-over-ranks device time (CUDA events
            on the library's stream around each step, first k_generate .. last k_accumulate).
@@ -217,15 +217,14 @@ def main():
     if args.paths_in_flight:
         m.SetPathsInFlight(args.paths_in_flight)
     scenes.load_scene(m, scene)
-    m.SetTileShard(rank, world)
+    if world > 1:
+        # the product's own multi-GPU path: the library holds the NCCL communicator (HdMoonshineExtCommInit shards the pixel tiles by
+        # rank; HdMoonshineRender / CommReduceSensor end with one ncclReduce of the frame to rank 0). torch.distributed is only the
+        # harness plumbing here (barrier, max/sum of the timings).
+        m.CommInit(hydra.exchange_unique_id(rank, world, "bench_" + os.environ.get("MASTER_PORT", "0")), rank, world)
     sensor, lens = m.CreateSensor(W, H), m.CreateLens(scene.lens)
     m.SetProfiling(True)
     batch = args.batch_spp * world
-
-    class _Dev:  # zero-copy view of the library-owned radiance buffer for torch.distributed
-        def __init__(self, ptr, n):
-            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
-    radiance = torch.as_tensor(_Dev(m.SensorDevicePtr(sensor), W * H * 4), device=f"cuda:{local_rank}")
 
     def barrier():
         if world > 1:
@@ -235,25 +234,21 @@ def main():
     for _ in range(max(3, args.warmup)):
         m.RenderLaunches(sensor, lens, batch)
     if world > 1:
-        warm = radiance.clone()
-        dist.reduce(warm, dst=0)
+        m.CommReduceSensor(sensor, 0)
 
     # ---- timed region: K steps, inputs resident in HBM ------------------------------------------------
     barrier()
     m.ResetStats()
     clocks = ClockSampler(local_rank)
     clocks.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         m.RenderLaunches(sensor, lens, batch)
     reduce_ms = 0.0
     if world > 1:
-        ev0.record()
-        dist.reduce(radiance, dst=0)
-        ev1.record()
-        torch.cuda.synchronize()
-        reduce_ms = ev0.elapsed_time(ev1)
+        tr = time.perf_counter()
+        m.CommReduceSensor(sensor, 0)   # ncclReduce on the library's stream + the root's copy to its host buffer; includes the wait for the slowest rank
+        reduce_ms = (time.perf_counter() - tr) * 1e3
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     clk = clocks.stop()
@@ -313,7 +308,8 @@ def main():
     e2e_wall = allreduce(e2e_wall, dist.ReduceOp.MAX if world > 1 else None)
     e2e = {"value": e2e_rays / e2e_wall / 1e6, "unit": UNIT, "h2d_bytes_per_step": 52, "d2h_bytes_per_step": W * H * 16,
            "steps": e2e_steps, "ms_per_step": e2e_wall / e2e_steps * 1e3,
-           "call": "HdMoonshineRender(sensor, lens) with samples_per_run = batch spp; sensor copied to the pinned host buffer every call"}
+           "call": "HdMoonshineRender(sensor, lens) with samples_per_run = batch spp; every call ends with the assembled frame in rank 0's pinned host "
+                   "buffer (N > 1: ncclReduce of the tiles to rank 0 inside the call, then the copy to the host)"}
 
     # ---- e2e_interactive: the call pattern of the Hydra delegate (hydra/hydra.zig:316-329: ONE sample per HdMoonshineRender,
     # sensor copied to the host after every call), same scene and constants as above -------------------------------------------

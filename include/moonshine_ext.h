@@ -85,14 +85,32 @@ MSNE_API void HdMoonshineExtClearSensor(HdMoonshine*, SensorHandle);     /* Sens
 MSNE_API uint32_t HdMoonshineExtGetSensorSampleCount(const HdMoonshine*, SensorHandle);
 MSNE_API void* HdMoonshineExtGetSensorDevicePtr(const HdMoonshine*, SensorHandle);  /* RGBA32F W*H, for NCCL */
 
-/* multi-GPU: this object renders only the pixels of 32x32 tiles t with t % world == rank; the rest stay 0 */
+/* multi-GPU: this object renders only the pixels of the 16x16 tiles (cx, cy) with (cx + s cy) % world == rank, s = the smallest
+ * number >= 2 coprime to world (3 for 2, 4, 8 ranks); the rest of its frame stays 0 */
 MSNE_API bool HdMoonshineExtSetTileShard(HdMoonshine*, uint32_t rank, uint32_t world);
+/* One rank per GPU over NCCL (the reference is single-GPU, so this has no reference twin). Rank 0 calls
+ * CommGetUniqueId and hands the 128 bytes to the other ranks by any channel (file, socket, MPI, torch.distributed); every rank
+ * then calls CommInit, which also shards the pixel tiles by rank. From then on HdMoonshineRender renders the rank's tiles and ends
+ * with one ncclReduce(sum) of the RGBA32F frame to rank 0, whose GetSensorData buffer receives the assembled frame (exact: every
+ * texel has one non-zero contributor). CommReduceSensor does the same after HdMoonshineExtRenderLaunches. Collective calls: every
+ * rank must make them in the same order. */
+#define MSNE_COMM_ID_BYTES 128
+MSNE_API bool HdMoonshineExtCommGetUniqueId(void* id128);
+MSNE_API bool HdMoonshineExtCommInit(HdMoonshine*, const void* id128, uint32_t rank, uint32_t world);
+MSNE_API bool HdMoonshineExtCommReduceSensor(HdMoonshine*, SensorHandle, uint32_t root);
+MSNE_API bool HdMoonshineExtCommAllReduceU64(HdMoonshine*, uint64_t* values, size_t n);   /* sum over ranks, in place (ray counters) */
+MSNE_API void HdMoonshineExtCommDestroy(HdMoonshine*);
 MSNE_API void HdMoonshineExtSetPathsInFlight(HdMoonshine*, uint64_t max_paths);   /* wavefront pool size (0 = default) */
 /* extension-ray queues of at least `min_rays` are traced in sorted order (direction octant + origin cell); 0 = never,
  * UINT64_MAX = library default (262144, and only for scenes whose BVHs hold >= 2048 nodes). Ordering only: images are
  * bitwise identical either way. */
 MSNE_API void HdMoonshineExtSetRaySorting(HdMoonshine*, uint64_t min_rays);
 MSNE_API void HdMoonshineExtSetProfiling(HdMoonshine*, bool per_kernel_events);
+/* Scheduling hints (performance only - the image is the same bits for any values): k_tail finishes a wave once fewer than
+ * `tail_paths` paths are expected to survive; bounces expected to shade fewer than `binned_paths` paths use one generic shade
+ * launch instead of one per material; `wave_contexts` = waves in flight (1 or 2). UINT64_MAX / 0 = library defaults
+ * (32768, 262144, 2). Also forgets the survival profile learnt from earlier waves. */
+MSNE_API void HdMoonshineExtSetSchedule(HdMoonshine*, uint64_t tail_paths, uint64_t binned_paths, uint32_t wave_contexts);
 
 MSNE_API void HdMoonshineExtGetStats(const HdMoonshine*, MsneStats*);
 MSNE_API void HdMoonshineExtResetStats(HdMoonshine*);

@@ -8,5 +8,5 @@ NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 OUT=${OUT:-../libmoonshine.so}
 $NVCC -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo -fmad=false \
       -Xcompiler -fPIC,-ffp-contract=off,-fno-fast-math,-Wall,-Wno-unused-function \
-      -shared kernels.cu runtime.cpp bvh_build.cpp -o $OUT "$@"
+      -shared kernels.cu runtime.cpp bvh_build.cpp -ldl -o $OUT "$@"
 echo "built $(realpath $OUT)"

@@ -23,6 +23,8 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types and prototypes only: the library itself is dlopen'ed on first use (HdMoonshineExtComm*)
 
 #include "../../include/moonshine_ext.h"
 #include "bvh_build.h"
@@ -104,6 +106,7 @@ struct Sensor {
     DevBuf<float4> runState;
     uint32_t nPix = 0;
     uint32_t shardRank = 0, shardWorld = 0;   // shard the pixIds were built for
+    DevBuf<float4> reduced;          // root rank of a communicator: the frame assembled from every rank's tiles
 };
 
 // engine/vector.zig:350-362 (inverse_affine) on row-major 3x4
@@ -155,6 +158,44 @@ float srgbToLinear(int c) {
     const double s = c / 255.0;
     return (float)(s <= 0.04045 ? s / 12.92 : std::pow((s + 0.055) / 1.055, 2.4));
 }
+
+// NCCL entry points, resolved at run time: a single-GPU deployment needs no NCCL installed, and inside a process that already
+// loaded a libnccl.so.2 (e.g. under torch.distributed) the loader hands back that same copy.
+struct NcclApi {
+    void* lib = nullptr;
+    decltype(&ncclGetUniqueId) getUniqueId = nullptr;
+    decltype(&ncclCommInitRank) commInitRank = nullptr;
+    decltype(&ncclCommDestroy) commDestroy = nullptr;
+    decltype(&ncclReduce) reduce = nullptr;
+    decltype(&ncclAllReduce) allReduce = nullptr;
+    decltype(&ncclGetErrorString) getErrorString = nullptr;
+};
+NcclApi& ncclApi() {
+    static NcclApi api = [] {
+        NcclApi a;
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) { a.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (a.lib) break; }
+        if (!a.lib) return a;
+        a.getUniqueId = (decltype(a.getUniqueId))dlsym(a.lib, "ncclGetUniqueId");
+        a.commInitRank = (decltype(a.commInitRank))dlsym(a.lib, "ncclCommInitRank");
+        a.commDestroy = (decltype(a.commDestroy))dlsym(a.lib, "ncclCommDestroy");
+        a.reduce = (decltype(a.reduce))dlsym(a.lib, "ncclReduce");
+        a.allReduce = (decltype(a.allReduce))dlsym(a.lib, "ncclAllReduce");
+        a.getErrorString = (decltype(a.getErrorString))dlsym(a.lib, "ncclGetErrorString");
+        return a;
+    }();
+    if (!api.lib || !api.getUniqueId || !api.commInitRank || !api.commDestroy || !api.reduce || !api.allReduce || !api.getErrorString)
+        throw std::runtime_error("NCCL (libnccl.so.2) is not available in this process");
+    return api;
+}
+#define NK(expr)                                                                                         \
+    do {                                                                                                 \
+        ncclResult_t r_ = (expr);                                                                        \
+        if (r_ != ncclSuccess) {                                                                         \
+            char buf_[512];                                                                              \
+            snprintf(buf_, sizeof(buf_), "%s failed: %s (%s:%d)", #expr, ncclApi().getErrorString(r_), __FILE__, __LINE__); \
+            throw CudaError(buf_);                                                                       \
+        }                                                                                                \
+    } while (0)
 
 size_t texelBytes(uint32_t fmt) {
     switch (fmt) {
@@ -215,6 +256,9 @@ struct HdMoonshine {
     std::vector<Lens> lenses;
     std::vector<std::unique_ptr<Sensor>> sensors;
     uint32_t shardRank = 0, shardWorld = 1;
+    uint32_t tileEdge = 16;          // pixel tiles of tileEdge x tileEdge are dealt round-robin to the ranks (MSNE_TILE_EDGE)
+    ncclComm_t comm = nullptr;       // HdMoonshineExtCommInit: one rank per GPU, tiles sharded by rank, frames assembled with ncclReduce
+    uint32_t commRank = 0, commWorld = 1;
 
     // ---- wavefront execution ---------------------------------------------------------------------------------------------
     // A WAVE = up to P paths (consecutive samples of a chunk of owned pixels) carried from k_generate to k_accumulate. The host
@@ -309,6 +353,7 @@ struct HdMoonshine {
         if (const char* e = getenv("MSNE_LOG_BOUNCES")) logBounces = atoi(e) != 0;
         if (const char* e = getenv("MSNE_TAIL_THRESHOLD")) tailThreshold = strtoull(e, nullptr, 10);
         if (const char* e = getenv("MSNE_SORT_THRESHOLD")) { sortThreshold = strtoull(e, nullptr, 10); sortAnyScene = true; }
+        if (const char* e = getenv("MSNE_TILE_EDGE")) tileEdge = (uint32_t)std::min(256, std::max(8, atoi(e) / 8 * 8));
         if (const char* e = getenv("MSNE_WAVE_CONTEXTS")) waveContextsInUse = std::min(kWaveContexts, std::max(1, atoi(e)));
         if (const char* e = getenv("MSNE_BINNED_THRESHOLD")) binnedThreshold = strtoull(e, nullptr, 10);
         traceBlocks = smCount * std::max(1, traceOccupancyBlocksPerSm());
@@ -320,6 +365,7 @@ struct HdMoonshine {
     ~HdMoonshine() {
         cudaSetDevice(device);
         if (stream) cudaStreamSynchronize(stream);
+        if (comm) { try { ncclApi().commDestroy(comm); } catch (...) {} comm = nullptr; }
         for (WaveCtx& c : ctx) {
             if (c.stream) { cudaStreamSynchronize(c.stream); cudaStreamDestroy(c.stream); }
             if (c.evDone) cudaEventDestroy(c.evDone);
@@ -804,18 +850,29 @@ struct HdMoonshine {
     }
 
     // ---- sensors -------------------------------------------------------------------------------
+    // owner of pixel tile (cx, cy): consecutive tiles of a row go to consecutive ranks, and every row starts `stagger` ranks
+    // further, stagger = the smallest number >= 2 coprime to the world size (3 for 2, 4 and 8 ranks): neither a tile column
+    // nor a tile row is served by one rank
+    static uint32_t tileStagger(uint32_t world) {
+        auto gcd = [](uint32_t a, uint32_t b) { while (b) { const uint32_t t = a % b; a = b; b = t; } return a; };
+        uint32_t s = 2;
+        while (world > 1 && gcd(s, world) != 1) s++;
+        return world == 2 ? 3u : s;
+    }
+    static uint32_t tileOwner(uint32_t cx, uint32_t cy, uint32_t world) { return (cx + tileStagger(world) * cy) % world; }
     void buildPixIds(Sensor& s) {
-        // 32x32 tiles, round-robin over ranks; inside a tile 8x4 blocks so a warp of 32
-        // consecutive queue slots is a compact 8x4 pixel block (coherent primary rays)
-        const uint32_t W = s.extent.width, H = s.extent.height;
-        const uint32_t tx = (W + 31) / 32, ty = (H + 31) / 32;
+        // tileEdge x tileEdge pixel tiles dealt round-robin over ranks; inside a tile 8x4 blocks so that a warp of 32
+        // consecutive queue slots is a compact 8x4 pixel block (coherent primary rays). Small tiles even out the per-rank work
+        // (a 32-pixel tile can be all sky or all chrome); the edge stays a multiple of 8 so the 8x4 blocks are never split.
+        const uint32_t W = s.extent.width, H = s.extent.height, E = tileEdge;
+        const uint32_t tx = (W + E - 1) / E, ty = (H + E - 1) / E;
         std::vector<uint32_t> ids;
         ids.reserve((size_t)W * H / std::max(1u, shardWorld) + 1024);
         for (uint32_t t = 0; t < tx * ty; t++) {
-            if (t % shardWorld != shardRank) continue;
-            const uint32_t x0 = (t % tx) * 32, y0 = (t / tx) * 32;
-            for (uint32_t by = 0; by < 32; by += 4)
-                for (uint32_t bx = 0; bx < 32; bx += 8)
+            if (tileOwner(t % tx, t / tx, shardWorld) != shardRank) continue;
+            const uint32_t x0 = (t % tx) * E, y0 = (t / tx) * E;
+            for (uint32_t by = 0; by < E; by += 4)
+                for (uint32_t bx = 0; bx < E; bx += 8)
                     for (uint32_t y = 0; y < 4; y++)
                         for (uint32_t x = 0; x < 8; x++) {
                             const uint32_t px = x0 + bx + x, py = y0 + by + y;
@@ -1031,6 +1088,20 @@ struct HdMoonshine {
         CK(cudaStreamSynchronize(stream));
     }
 
+    // every rank holds a full-frame buffer that is zero outside its own tiles, so one ncclReduce(sum) assembles the
+    // frame exactly (x + 0 + ... + 0). The root receives into a separate buffer - its own sensor keeps accumulating its tiles -
+    // and copies the assembled frame to the host buffer of GetSensorData.
+    void reduceSensor(Sensor& s, uint32_t root) {
+        use();
+        if (!comm) throw std::runtime_error("no communicator: call HdMoonshineExtCommInit first");
+        const size_t n = (size_t)s.extent.width * s.extent.height;
+        const bool isRoot = commRank == root;
+        if (isRoot) s.reduced.ensure(std::max<size_t>(1, n));
+        NK(ncclApi().reduce(s.image.p, isRoot ? (void*)s.reduced.p : nullptr, n * 4, ncclFloat, ncclSum, (int)root, comm, stream));
+        if (isRoot) CK(cudaMemcpyAsync(s.host, s.reduced.p, n * sizeof(float4), cudaMemcpyDeviceToHost, stream));
+        CK(cudaStreamSynchronize(stream));
+    }
+
     void fetchStats(MsneStats& out) {
         use();
         out = stats;
@@ -1122,7 +1193,8 @@ bool HdMoonshineRender(HdMoonshine* h, SensorHandle sensor, LensHandle lens) {
     try {
         Sensor& s = *h->sensors.at(sensor);
         h->renderLaunches(s, h->lenses.at(lens), 1);   // hydra.zig:316-329: one traceRays per call
-        h->readSensor(s);                              // hydra.zig:332-358: copy to the persistent host buffer, wait idle
+        if (h->comm) h->reduceSensor(s, 0);            // one rank per GPU: assemble the tiles on rank 0, whose host buffer gets the frame
+        else h->readSensor(s);                         // hydra.zig:332-358: copy to the persistent host buffer, wait idle
         return true;
     } catch (const std::exception& e) { g_lastError = e.what(); return false; }
 }
@@ -1353,6 +1425,58 @@ bool HdMoonshineExtSetTileShard(HdMoonshine* h, uint32_t rank, uint32_t world) {
         return true;
     } catch (const std::exception& e) { g_lastError = e.what(); return false; }
 }
+// ---- multi-GPU: one process (or thread) per GPU, NCCL over NVLink ----------------------------------------------------
+bool HdMoonshineExtCommGetUniqueId(void* id128) {
+    try {
+        ncclUniqueId id;
+        NK(ncclApi().getUniqueId(&id));
+        static_assert(sizeof(id) == MSNE_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+        memcpy(id128, &id, sizeof(id));
+        return true;
+    } catch (const std::exception& e) { g_lastError = e.what(); return false; }
+}
+bool HdMoonshineExtCommInit(HdMoonshine* h, const void* id128, uint32_t rank, uint32_t world) {
+    LOCK(h);
+    if (world == 0 || rank >= world) { g_lastError = "bad rank / world size"; return false; }
+    try {
+        h->use();
+        if (h->comm) { ncclApi().commDestroy(h->comm); h->comm = nullptr; }
+        ncclUniqueId id;
+        memcpy(&id, id128, sizeof(id));
+        NK(ncclApi().commInitRank(&h->comm, (int)world, id, (int)rank));
+        h->commRank = rank; h->commWorld = world;
+        h->shardRank = rank; h->shardWorld = world;
+        for (auto& s : h->sensors) {
+            h->buildPixIds(*s);
+            CK(cudaMemsetAsync(s->image.p, 0, (size_t)s->extent.width * s->extent.height * sizeof(float4), h->stream));
+            h->clearSensor(*s);
+        }
+        CK(cudaStreamSynchronize(h->stream));
+        return true;
+    } catch (const std::exception& e) { g_lastError = e.what(); return false; }
+}
+bool HdMoonshineExtCommReduceSensor(HdMoonshine* h, SensorHandle s, uint32_t root) {
+    LOCK(h);
+    try { h->reduceSensor(*h->sensors.at(s), root); return true; } catch (const std::exception& e) { g_lastError = e.what(); return false; }
+}
+bool HdMoonshineExtCommAllReduceU64(HdMoonshine* h, uint64_t* values, size_t n) {
+    LOCK(h);
+    try {
+        h->use();
+        if (!h->comm) throw std::runtime_error("no communicator: call HdMoonshineExtCommInit first");
+        DevBuf<unsigned long long> d;
+        d.upload(reinterpret_cast<const unsigned long long*>(values), n, h->stream);
+        NK(ncclApi().allReduce(d.p, d.p, n, ncclUint64, ncclSum, h->comm, h->stream));
+        CK(cudaMemcpyAsync(values, d.p, n * sizeof(uint64_t), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+        return true;
+    } catch (const std::exception& e) { g_lastError = e.what(); return false; }
+}
+void HdMoonshineExtCommDestroy(HdMoonshine* h) {
+    LOCK(h);
+    if (h->comm) { try { h->use(); ncclApi().commDestroy(h->comm); } catch (...) {} h->comm = nullptr; }
+}
+
 void HdMoonshineExtSetRaySorting(HdMoonshine* h, uint64_t minRays) {
     LOCK(h);
     if (minRays == UINT64_MAX) { h->sortThreshold = 262144; h->sortAnyScene = false; }
@@ -1364,6 +1488,13 @@ void HdMoonshineExtSetPathsInFlight(HdMoonshine* h, uint64_t n) {
     for (HdMoonshine::WaveCtx& c : h->ctx) c.pb.capacity = 0;   // pools are re-sized by the next render
 }
 void HdMoonshineExtSetProfiling(HdMoonshine* h, bool on) { LOCK(h); h->profiling = on; }
+void HdMoonshineExtSetSchedule(HdMoonshine* h, uint64_t tailPaths, uint64_t binnedPaths, uint32_t waveContexts) {
+    LOCK(h);
+    h->tailThreshold = tailPaths == UINT64_MAX ? 32768 : tailPaths;
+    h->binnedThreshold = binnedPaths == UINT64_MAX ? 262144 : binnedPaths;
+    h->waveContextsInUse = waveContexts == 0 ? HdMoonshine::kWaveContexts : (int)std::min<uint32_t>(waveContexts, HdMoonshine::kWaveContexts);
+    h->survivalIn.clear();
+}
 void HdMoonshineExtGetStats(const HdMoonshine* h, MsneStats* out) {
     HdMoonshine* m = const_cast<HdMoonshine*>(h);
     std::lock_guard<std::mutex> lock_(m->mutex);

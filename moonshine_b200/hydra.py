@@ -115,9 +115,15 @@ SIGNATURES = {
     "HdMoonshineExtGetSensorSampleCount": (_U32, [_VP, _U32]),
     "HdMoonshineExtGetSensorDevicePtr": (_VP, [_VP, _U32]),
     "HdMoonshineExtSetTileShard": (C.c_bool, [_VP, _U32, _U32]),
+    "HdMoonshineExtCommGetUniqueId": (C.c_bool, [_VP]),
+    "HdMoonshineExtCommInit": (C.c_bool, [_VP, _VP, _U32, _U32]),
+    "HdMoonshineExtCommReduceSensor": (C.c_bool, [_VP, _U32, _U32]),
+    "HdMoonshineExtCommAllReduceU64": (C.c_bool, [_VP, _VP, C.c_size_t]),
+    "HdMoonshineExtCommDestroy": (None, [_VP]),
     "HdMoonshineExtSetPathsInFlight": (None, [_VP, C.c_uint64]),
     "HdMoonshineExtSetRaySorting": (None, [_VP, C.c_uint64]),
     "HdMoonshineExtSetProfiling": (None, [_VP, C.c_bool]),
+    "HdMoonshineExtSetSchedule": (None, [_VP, C.c_uint64, C.c_uint64, _U32]),
     "HdMoonshineExtGetStats": (None, [_VP, C.POINTER(MsneStats)]),
     "HdMoonshineExtResetStats": (None, [_VP]),
     "HdMoonshineExtSetGeometryMaterial": (None, [_VP, _U32, _U32, _U32]),
@@ -290,9 +296,33 @@ class HdMoonshine:
         if not self.L.HdMoonshineExtSetTileShard(self.h, rank, world):
             raise ValueError("HdMoonshineExtSetTileShard: " + self.last_error())
 
+    # one rank per GPU over NCCL (include/moonshine_ext.h "multi-GPU")
+    def CommInit(self, unique_id: bytes, rank: int, world: int):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        if not self.L.HdMoonshineExtCommInit(self.h, buf, rank, world):
+            raise RuntimeError("HdMoonshineExtCommInit: " + self.last_error())
+
+    def CommReduceSensor(self, sensor: int, root: int = 0):
+        if not self.L.HdMoonshineExtCommReduceSensor(self.h, sensor, root):
+            raise RuntimeError("HdMoonshineExtCommReduceSensor: " + self.last_error())
+
+    def CommAllReduceU64(self, values):
+        a = np.ascontiguousarray(values, np.uint64)
+        if not self.L.HdMoonshineExtCommAllReduceU64(self.h, _p(a), a.size):
+            raise RuntimeError("HdMoonshineExtCommAllReduceU64: " + self.last_error())
+        return a
+
+    def CommDestroy(self):
+        self.L.HdMoonshineExtCommDestroy(self.h)
+
     def SetPathsInFlight(self, n: int): self.L.HdMoonshineExtSetPathsInFlight(self.h, n)
     def SetRaySorting(self, min_rays: int): self.L.HdMoonshineExtSetRaySorting(self.h, min_rays)
     def SetProfiling(self, on: bool): self.L.HdMoonshineExtSetProfiling(self.h, bool(on))
+
+    def SetSchedule(self, tail_paths: Optional[int] = None, binned_paths: Optional[int] = None, wave_contexts: int = 0):
+        """Scheduling hints (never change a result); None = library default."""
+        big = 0xFFFFFFFFFFFFFFFF
+        self.L.HdMoonshineExtSetSchedule(self.h, big if tail_paths is None else tail_paths, big if binned_paths is None else binned_paths, wave_contexts)
 
     def GetStats(self) -> MsneStats:
         st = MsneStats()
@@ -406,7 +436,36 @@ class HdMoonshine:
         return a
 
 
-def render_scene(scene, n_launches: int = 1, device: int = 0, paths_in_flight: Optional[int] = None, shard=None, ray_sorting: Optional[int] = None):
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the library (rank 0 calls it and hands the 128 bytes to the other ranks)."""
+    buf = C.create_string_buffer(128)
+    if not load_library().HdMoonshineExtCommGetUniqueId(buf):
+        raise RuntimeError("HdMoonshineExtCommGetUniqueId: " + (load_library().HdMoonshineExtLastError() or b"").decode())
+    return buf.raw
+
+
+def exchange_unique_id(rank: int, world: int, tag: str, timeout_s: float = 120.0) -> bytes:
+    """File rendezvous for the NCCL id between the ranks of ONE node (no torch, no MPI): rank 0 writes, the others poll.
+    `tag` must be the same on every rank and unique per job (e.g. MASTER_PORT)."""
+    import tempfile
+    import time
+    path = os.path.join(tempfile.gettempdir(), f"msne_nccl_id_{tag}")
+    if rank == 0:
+        uid = comm_unique_id()
+        with open(path + ".tmp", "wb") as f:
+            f.write(uid)
+        os.replace(path + ".tmp", path)
+        return uid
+    t0 = time.time()
+    while time.time() - t0 < timeout_s:
+        if os.path.exists(path) and os.path.getsize(path) == 128:
+            return open(path, "rb").read()
+        time.sleep(0.02)
+    raise RuntimeError(f"rank {rank}: no NCCL id from rank 0 at {path}")
+
+
+def render_scene(scene, n_launches: int = 1, device: int = 0, paths_in_flight: Optional[int] = None, shard=None, ray_sorting: Optional[int] = None,
+                 tail_paths: Optional[int] = None, binned_paths: Optional[int] = None, wave_contexts: int = 0):
     """Load a scenes.Scene into a fresh HdMoonshine, render `n_launches` launches, return (image HxWx4, stats, obj)."""
     from . import scenes as _sc
     m = HdMoonshine(device)
@@ -414,6 +473,8 @@ def render_scene(scene, n_launches: int = 1, device: int = 0, paths_in_flight: O
         m.SetPathsInFlight(paths_in_flight)
     if ray_sorting is not None:
         m.SetRaySorting(ray_sorting)
+    if tail_paths is not None or binned_paths is not None or wave_contexts:
+        m.SetSchedule(tail_paths, binned_paths, wave_contexts)
     _sc.load_scene(m, scene)
     if shard:
         m.SetTileShard(*shard)

@@ -17,6 +17,7 @@ from __future__ import annotations
 import io
 import json
 import math
+import os
 import struct
 import sys
 import zlib
@@ -423,15 +424,23 @@ def write_glb(scene: S.Scene, path: str) -> None:
 # CLI (offline/main.zig:27-50)
 # ---------------------------------------------------------------------------------------------------------------
 def main(argv: Optional[List[str]] = None) -> int:
+    """offline <in.glb> <skybox.exr> <out.exr> [spp=16] (offline/main.zig:27-50) [--extent WxH] [--device N] [--gpus N].
+
+    --gpus N (one node): the process re-launches itself as N ranks (RANK / WORLD_SIZE / LOCAL_RANK, the torchrun convention, so
+    `torchrun --nproc-per-node N -m moonshine_b200.offline ...` works as well); every rank loads the scene, renders all samples
+    of its own pixel tiles on its own GPU, and one ncclReduce inside the library assembles the frame on rank 0, which writes it.
+    """
     import time
     argv = list(sys.argv[1:] if argv is None else argv)
-    extent, device = (1280, 720), 0
+    extent, device, gpus = (1280, 720), None, 1
     while "--extent" in argv:
         i = argv.index("--extent"); w, h = argv[i + 1].lower().split("x"); extent = (int(w), int(h)); del argv[i:i + 2]
     while "--device" in argv:
         i = argv.index("--device"); device = int(argv[i + 1]); del argv[i:i + 2]
+    while "--gpus" in argv:
+        i = argv.index("--gpus"); gpus = int(argv[i + 1]); del argv[i:i + 2]
     if len(argv) < 3:
-        print("usage: offline <in.glb> <skybox.exr> <out.exr> [spp=16] [--extent WxH] [--device N]", file=sys.stderr)
+        print("usage: offline <in.glb> <skybox.exr> <out.exr> [spp=16] [--extent WxH] [--device N] [--gpus N]", file=sys.stderr)
         return 2  # error.BadArgs
     in_path, sky_path, out_path = argv[:3]
     if not in_path.endswith(".glb"):
@@ -441,22 +450,52 @@ def main(argv: Optional[List[str]] = None) -> int:
     if not out_path.endswith(".exr"):
         raise SystemExit("OnlySupportsExrOutput")
     spp = int(argv[3]) if len(argv) > 3 else 16
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    if gpus > 1 and world == 1:
+        return _launch_ranks(gpus, [in_path, sky_path, out_path, str(spp), "--extent", f"{extent[0]}x{extent[1]}"])
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", 0))
     from . import hydra
     t0 = time.perf_counter()
     scene = load_glb(in_path, extent)
     scene.background = read_exr(sky_path)
     m = hydra.HdMoonshine(device)
     S.load_scene(m, scene)
+    if world > 1:
+        m.CommInit(hydra.exchange_unique_id(rank, world, os.environ.get("MSNE_JOB_TAG", os.environ.get("MASTER_PORT", "0"))), rank, world)
     sensor, lens = m.CreateSensor(*extent), m.CreateLens(scene.lens)
-    print(f"{time.perf_counter() - t0:.3f} seconds to load world")
+    if rank == 0:
+        print(f"{time.perf_counter() - t0:.3f} seconds to load world")
     t0 = time.perf_counter()
     m.RenderLaunches(sensor, lens, spp)
-    img = m.ReadSensor(sensor)
+    if world > 1:
+        m.CommReduceSensor(sensor, 0)     # rank 0's host buffer receives the assembled frame
+        img = m.GetSensorData(sensor)
+    else:
+        img = m.ReadSensor(sensor)
     st = m.GetStats()
-    print(f"{time.perf_counter() - t0:.3f} seconds to render ({(st.rays_closest + st.rays_shadow) / max(st.device_ms, 1e-9) / 1e3:.1f} Mrays/s)")
-    write_exr(out_path, img)
+    rays = int(st.rays_closest + st.rays_shadow)
+    if world > 1:
+        rays = int(m.CommAllReduceU64([rays])[0])
+    if rank == 0:
+        print(f"{time.perf_counter() - t0:.3f} seconds to render ({rays / max(st.device_ms, 1e-9) / 1e3:.1f} Mrays/s on {world} GPU{'s' if world > 1 else ''})")
+        write_exr(out_path, img)
     m.Destroy()
     return 0
+
+
+def _launch_ranks(n: int, args: List[str]) -> int:
+    """One process per GPU on this node (the torchrun environment convention, without needing torch)."""
+    import subprocess
+    import uuid
+    tag = uuid.uuid4().hex[:12]
+    procs = []
+    for r in range(n):
+        env = dict(os.environ, RANK=str(r), LOCAL_RANK=str(r), WORLD_SIZE=str(n), MSNE_JOB_TAG=tag)
+        procs.append(subprocess.Popen([sys.executable, "-m", "moonshine_b200.offline"] + args, env=env,
+                                      cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    codes = [p.wait() for p in procs]
+    return max(codes)
 
 
 if __name__ == "__main__":

@@ -17,10 +17,13 @@ def test_every_pixel_has_exactly_one_owner(w, h, world):
     assert om.shape == (h, w) and om.min() >= 0 and om.max() < world
     counts = [shard.owned_pixel_count(w, h, r, world) for r in range(world)]
     assert sum(counts) == w * h
-    if w * h >= 32 * 32 * world * 4:
-        assert max(counts) - min(counts) <= 4 * 32 * 32  # round-robin keeps ranks balanced to a few tiles
-    # tiles are 32x32 and never split between ranks
-    assert (om[:32, :32] == om[0, 0]).all()
+    T = shard.TILE
+    if w * h >= T * T * world * 4:
+        assert max(counts) - min(counts) <= 4 * T * T  # dealing tiles keeps ranks balanced to a few tiles
+    # tiles are never split between ranks, and neither a tile row nor a tile column belongs to one rank
+    assert (om[:T, :T] == om[0, 0]).all()
+    if world > 1 and w >= 2 * T and h >= 2 * T:
+        assert om[0, 0] != om[0, T] and om[0, 0] != om[T, 0]
 
 
 def _worker(rank, world, port, w, h, out_path):
