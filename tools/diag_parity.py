@@ -21,5 +21,9 @@ for name, maker, launches in cases:
     g, st, _ = gpu_render(sc, launches)
     r, counts, _ = oracle_render(sc, launches)
     d = np.abs(g[..., :3].astype(np.float64) - r[..., :3]) / np.maximum(1.0, np.abs(r[..., :3]))
+    if name == "cfg3-full":
+        bad = np.argwhere(~(g.view(np.uint32) == r.view(np.uint32)).all(axis=-1))
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        np.savez(os.path.join(ROOT, "gpurun_out", "cfg3_full_diff.npz"), yx=bad, gpu=g[bad[:, 0], bad[:, 1]], oracle=r[bad[:, 0], bad[:, 1]])
     print(f"{name:12s} identical {identical_fraction(g, r):.6f}  within1e-4 {within_tol_fraction(g, r):.6f}  max rel diff {d.max():.3g}  "
           f"closest {st.rays_closest}/{int(counts[0])}  shadow {st.rays_shadow}/{int(counts[1])}", flush=True)
