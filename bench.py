@@ -223,7 +223,6 @@ def main():
         # harness plumbing here (barrier, max/sum of the timings).
         m.CommInit(hydra.exchange_unique_id(rank, world, "bench_" + os.environ.get("MASTER_PORT", "0")), rank, world)
     sensor, lens = m.CreateSensor(W, H), m.CreateLens(scene.lens)
-    m.SetProfiling(True)
     batch = args.batch_spp * world
 
     def barrier():
@@ -268,20 +267,40 @@ def main():
     wall_ms_max = allreduce(wall_ms, dist.ReduceOp.MAX if world > 1 else None)
     value = rays_total / (dev_ms_max / 1e3) / 1e6
 
-    # ---- roofline of the dominant kernel (k_trace), from CUDA events recorded on the library's stream ----
+    # ---- roofline of the dominant kernel (k_trace): CUDA events on the launching stream around every k_trace launch -------------
+    # The timed loop above keeps two waves in flight on two streams, so an event interval around one stream's kernel also spans
+    # the other stream's work. The per-kernel figures therefore come from a second pass over the same workload with ONE wave in
+    # flight (same kernels, same data, same launch population), measured right here, live.
+    prof_steps = max(1, min(args.steps, 4))
+    m.SetSchedule(wave_contexts=1)
+    m.RenderLaunches(sensor, lens, batch)          # untimed: re-learns the survival profile for this wave size
+    m.SetProfiling(True)
+    barrier()
+    m.ResetStats()
+    for _ in range(prof_steps):
+        m.RenderLaunches(sensor, lens, batch)
+    stp = m.GetStats()
+    m.SetProfiling(False)
+    m.SetSchedule()
     peak, peak_src = hbm_peak()
-    trace_bytes = 48.0 * rays_local  # 32 B ray read + 16 B hit write / conditional NEE clear
-    trace_s = st.trace_ms / 1e3 if st.trace_ms > 0 else float("nan")
+    # rays the k_trace launches themselves traced (k_tail traces its stragglers inline): 48 B each = 32 B ray read + 16 B hit
+    # write / conditional NEE clear
+    trace_bytes = 48.0 * float(stp.rays_closest + stp.rays_shadow)
+    trace_s = stp.trace_ms / 1e3 if stp.trace_ms > 0 else float("nan")
     achieved = trace_bytes / trace_s / 1e9
     traffic = ncu_traffic()
     step_bytes = 224.0 * st.rays_closest + 112.0 * st.rays_shadow + 32.0 * st.samples
     roofline = {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
-                "peak_source": peak_src, "launches": int(st.trace_launches), "avg_launch_ms": st.trace_ms / max(1, st.trace_launches),
-                "kernel_share_of_step": st.trace_ms / max(st.device_ms, 1e-9),
-                "reorder_share_of_step": st.sort_ms / max(st.device_ms, 1e-9),
-                "algorithmic_bytes_per_launch": trace_bytes / max(1, st.trace_launches),
-                "note": "software BVH traversal is L2-latency bound, not streaming bound: see DESIGN.md and profiles/"}
+                "traffic_source": (traffic or {}).get("source"),
+                "peak_source": peak_src, "launches": int(stp.trace_launches), "avg_launch_ms": stp.trace_ms / max(1, stp.trace_launches),
+                "kernel_share_of_step": stp.trace_ms / max(stp.device_ms, 1e-9),
+                "reorder_share_of_step": stp.sort_ms / max(stp.device_ms, 1e-9),
+                "algorithmic_bytes_per_launch": trace_bytes / max(1, stp.trace_launches),
+                "measured_in": f"{prof_steps} extra steps of the same workload with one wave in flight ({stp.device_ms / prof_steps:.1f} ms per step); "
+                               "the timed steps overlap two waves on two streams, which makes per-kernel event intervals overlap",
+                "l2": (traffic or {}).get("l2"), "simt": (traffic or {}).get("simt"),
+                "note": "software BVH traversal is latency / SIMT-efficiency bound, not streaming bound: see DESIGN.md and profiles/"}
     roofline_step = {"bytes_formula": "224*N_ext + 112*N_shadow + 32*N_samples (SURVEY.md 8d)", "achieved": step_bytes / (st.device_ms / 1e3) / 1e9,
                      "peak": peak, "unit": "GB/s", "frac": step_bytes / (st.device_ms / 1e3) / 1e9 / peak}
     timed_launches = int(st.kernel_launches)

@@ -56,11 +56,12 @@ typedef struct MsneStats {
     uint64_t max_bounce_reached;
     uint64_t static_blas_builds;        /* rebuilds of the BLAS level (merged static BLAS + shared BLASes) */
     uint64_t tlas_builds;               /* rebuilds of the instance level (TLAS + instance records) */
-    uint64_t tlas_refits;               /* transform-only edits served by a bottom-up refit of the existing TLAS */
+    uint64_t tlas_refits;               /* transform-only edits served by a refit of the existing TLAS on the device */
     double   sort_ms;                   /* CUDA-event time of the ray-reordering passes (counting sort + binning; profiling on) */
     uint64_t waves;                     /* waves rendered (generate .. accumulate); two are in flight at a time */
     uint64_t host_syncs;                /* host<->device synchronisations inside render loops (one per render call, none per bounce) */
     uint64_t tail_paths;                /* paths left to k_tail after the wavefront bounces, summed over waves */
+    double   accel_sync_ms;             /* host wall time spent bringing the acceleration structure up to date after edits (builds, refits, record uploads) */
 } MsneStats;
 
 /* must be called before HdMoonshineCreate; selects the CUDA device of objects created afterwards */

@@ -54,7 +54,7 @@ struct DInstance {
     uint32_t blasRoot;     // index of the BLAS root in the pooled node array
     uint32_t visible;      // mask != 0
     uint32_t isStatic;     // 1: pseudo-instance holding the merged static BLAS (no transform; hit.inst comes from TriRec.inst)
-    uint32_t pad[4];
+    uint32_t pad[4];       // [0] BLAS id, [1] TLAS leaf slot or 0xFFFFFFFF (device-side refit, kernels.cu k_tlas_boxes)
 };
 static_assert(sizeof(DInstance) == 128, "DInstance must be 128 B");
 
@@ -102,6 +102,7 @@ struct DeviceScene {
     const float* texLuts;          // 512 floats: [0,256) sRGB -> linear, [256,512) c / 255 (shading.cuh)
     uint32_t staticOnly;           // 1: the TLAS holds nothing but the merged static BLAS -> single-level traversal from staticRoot
     uint32_t staticRoot;
+    uint32_t staticHidden;         // 1: some member of the merged static BLAS is hidden (checked per candidate hit, traverse.cuh)
     uint32_t staticTop;            // MSNE_TRACE_SMEM_NODES experiment: the first `staticTop` nodes from staticRoot are the top of the tree in BFS order
 };
 

@@ -246,9 +246,9 @@ DI uint16_t rayKey(const SortFrame& f, float4 o, float4 d) {
 //                   keys are aggregated with __match_any_sync first: coherent rays share keys) and adds its non-zero bins to the
 //                   global histogram
 //   k_sort_scan     exclusive prefix sum of the global histogram -> global bin cursors; the histogram is re-zeroed for the next sort
-//   k_sort_scatter  every block counts its slice again, reserves its run in every bin with one atomic on the bin cursor, then
-//                   writes the queue indices of its slice into its runs
-// blockIdx.y = 0: extension rays of `buf`, 1: shadow rays. Keys are read three times (6 B per ray), the permutation written once.
+//   k_sort_scatter  every block reserves its run in every bin (its own histogram, kept by the count pass) with one atomic on the
+//                   bin cursor, then writes the queue indices of its slice into its runs
+// blockIdx.y = 0: extension rays of `buf`, 1: shadow rays. Keys are read twice (4 B per ray), the permutation written once.
 // ------------------------------------------------------------------------------------------------
 static constexpr uint32_t SORT_BINS = 1u << 15;
 static constexpr uint32_t SORT_THREADS = 1024;
@@ -256,6 +256,7 @@ struct SortJob {
     const uint16_t* keys[2]; uint32_t* perm[2];
     uint32_t* hist;      // [2][SORT_BINS], zero between sorts
     uint32_t* cursor;    // [2][SORT_BINS]
+    uint32_t* blockHist; // [2][gridDim.x][SORT_BINS]: every block's histogram of its slice, kept from the count to the scatter pass
     const Counters* counters;   // this bounce's input counts
 };
 DI void sortSlice(const SortJob& j, uint32_t& lo, uint32_t& hi) {
@@ -285,30 +286,38 @@ __global__ void __launch_bounds__(SORT_THREADS, 1) k_sort_count(SortJob j) {
     if (lo >= hi) return;
     sortCountSlice(j.keys[blockIdx.y], lo, hi, sortHist);
     uint32_t* g = j.hist + blockIdx.y * SORT_BINS;
-    for (uint32_t b = threadIdx.x; b < SORT_BINS; b += SORT_THREADS) { const uint32_t c = sortHist[b]; if (c) atomicAdd(g + b, c); }
+    uint32_t* mine = j.blockHist + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * SORT_BINS;
+    for (uint32_t b = threadIdx.x; b < SORT_BINS; b += SORT_THREADS) { const uint32_t c = sortHist[b]; mine[b] = c; if (c) atomicAdd(g + b, c); }
 }
 __global__ void __launch_bounds__(SORT_THREADS) k_sort_scan(SortJob j) {
-    __shared__ uint32_t warpSum[32];
+    // one block per queue; warp w owns bins [1024 w, 1024 w + 1024) and walks them 32 at a time (coalesced)
+    __shared__ uint32_t warpBase[32];
     uint32_t* g = j.hist + blockIdx.x * SORT_BINS;
     uint32_t* cur = j.cursor + blockIdx.x * SORT_BINS;
-    constexpr uint32_t PER = SORT_BINS / SORT_THREADS;   // 32 consecutive bins per thread
-    uint32_t v[PER], sum = 0;
-#pragma unroll
-    for (uint32_t k = 0; k < PER; k++) { v[k] = g[threadIdx.x * PER + k]; sum += v[k]; }
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    uint32_t incl = sum;
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((int)lane >= o) incl += t; }
-    if (lane == 31) warpSum[warp] = incl;
+    uint32_t v[32], total = 0;
+#pragma unroll
+    for (uint32_t p = 0; p < 32; p++) { v[p] = g[warp * 1024u + p * 32u + lane]; total += v[p]; }
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
+    if (lane == 0) warpBase[warp] = total;
     __syncthreads();
     if (warp == 0) {
-        uint32_t w = warpSum[lane], wi = w;
+        const uint32_t w = warpBase[lane];
+        uint32_t wi = w;
         for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, wi, o); if ((int)lane >= o) wi += t; }
-        warpSum[lane] = wi - w;
+        warpBase[lane] = wi - w;
     }
     __syncthreads();
-    uint32_t run = warpSum[warp] + incl - sum;
+    uint32_t carry = warpBase[warp];
 #pragma unroll
-    for (uint32_t k = 0; k < PER; k++) { cur[threadIdx.x * PER + k] = run; run += v[k]; g[threadIdx.x * PER + k] = 0; }
+    for (uint32_t p = 0; p < 32; p++) {
+        uint32_t incl = v[p];
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o); if ((int)lane >= o) incl += t; }
+        const uint32_t idx = warp * 1024u + p * 32u + lane;
+        cur[idx] = carry + incl - v[p];
+        g[idx] = 0;
+        carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+    }
 }
 __global__ void __launch_bounds__(SORT_THREADS, 1) k_sort_scatter(SortJob j) {
     extern __shared__ uint32_t sortHist[];
@@ -316,9 +325,9 @@ __global__ void __launch_bounds__(SORT_THREADS, 1) k_sort_scatter(SortJob j) {
     sortSlice(j, lo, hi);
     if (lo >= hi) return;
     const uint16_t* __restrict__ keys = j.keys[blockIdx.y];
-    sortCountSlice(keys, lo, hi, sortHist);
     uint32_t* cur = j.cursor + blockIdx.y * SORT_BINS;
-    for (uint32_t b = threadIdx.x; b < SORT_BINS; b += SORT_THREADS) { const uint32_t c = sortHist[b]; if (c) sortHist[b] = atomicAdd(cur + b, c); }
+    const uint32_t* mine = j.blockHist + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * SORT_BINS;
+    for (uint32_t b = threadIdx.x; b < SORT_BINS; b += SORT_THREADS) { const uint32_t c = mine[b]; sortHist[b] = c ? atomicAdd(cur + b, c) : 0u; }
     __syncthreads();
     uint32_t* __restrict__ perm = j.perm[blockIdx.y];
     const uint32_t lane = threadIdx.x & 31u, ltMask = (1u << lane) - 1u;
@@ -930,6 +939,70 @@ __global__ void k_env_fold(const float* __restrict__ srcMip, float* dstMip, floa
 }
 
 // ------------------------------------------------------------------------------------------------
+// TLAS refit on the device (Accel.zig:629-679: recordRebuild with mode = update_khr): after transform edits the instance
+// level keeps its topology and only boxes change. k_tlas_boxes recomputes the world-space box of every edited instance from
+// its (already uploaded) new transform and the object-space bounds of its BLAS and writes it into the instance's TLAS leaf;
+// k_tlas_propagate then carries boxes upwards: one walker per TLAS leaf, the SECOND walker to arrive at an inner node (the
+// first one stops) re-unites the node's child boxes and writes the union into the parent. Counters reset themselves.
+// ------------------------------------------------------------------------------------------------
+DI void writeChildBox(BvhNode2* nodes, uint32_t packed, const float lo[3], const float hi[3]) {
+    BvhNode2* n = nodes + (packed >> 1);
+    const uint32_t s = packed & 1u;
+    float* xy = s == 0 ? n->n0 : n->n1;
+    xy[0] = lo[0]; xy[1] = hi[0]; xy[2] = lo[1]; xy[3] = hi[1];
+    n->n2[2 * s] = lo[2]; n->n2[2 * s + 1] = hi[2];
+}
+__global__ void k_tlas_boxes(TlasRefit r, const uint32_t* __restrict__ dirty, uint32_t nDirty) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nDirty) return;
+    const DInstance* in = r.instances + dirty[k];
+    const uint32_t slot = in->pad[1];
+    if (slot == 0xFFFFFFFFu) return;   // not a TLAS item (identity or hidden at build time)
+    const float* bb = r.blasBounds + 6 * (size_t)in->pad[0];
+    float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+    for (int c = 0; c < 8; c++) {
+        const float p[3] = {(c & 1) ? bb[3] : bb[0], (c & 2) ? bb[4] : bb[1], (c & 4) ? bb[5] : bb[2]};
+        for (int a = 0; a < 3; a++) {
+            const float q = ((in->o2w[4 * a] * p[0] + in->o2w[4 * a + 1] * p[1]) + in->o2w[4 * a + 2] * p[2]) + in->o2w[4 * a + 3];
+            lo[a] = fminf(lo[a], q); hi[a] = fmaxf(hi[a], q);
+        }
+    }
+    // bvh_build.h padBox: keeps the FP32 slab test conservative
+    float ext = 1e-3f, mag = 0.0f;
+    for (int a = 0; a < 3; a++) { ext = fmaxf(ext, hi[a] - lo[a]); mag = fmaxf(mag, fmaxf(fabsf(lo[a]), fabsf(hi[a]))); }
+    const float pad = 1e-5f * ext + 1e-6f * mag;
+    for (int a = 0; a < 3; a++) { lo[a] -= pad; hi[a] += pad; }
+    writeChildBox(r.nodes, r.slotNode[slot], lo, hi);
+}
+__global__ void k_tlas_propagate(TlasRefit r, uint32_t nSlots) {
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= nSlots) return;
+    uint32_t node = r.slotNode[slot] >> 1;
+    for (;;) {
+        __threadfence();
+        const uint32_t expected = r.expected[node];
+        if (expected > 1u) {
+            const uint32_t arrived = atomicAdd(r.arrived + node, 1u);
+            if (arrived + 1u < expected) return;     // the other child's walker carries on from here
+            r.arrived[node] = 0;
+            __threadfence();
+        }
+        const uint32_t parent = r.parent[node];
+        if (parent == 0xFFFFFFFFu) return;           // root
+        const volatile BvhNode2* n = r.nodes + node;
+        float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+        for (int s = 0; s < 2; s++) {
+            if (n->c[s] == REF_EMPTY) continue;
+            const volatile float* xy = s == 0 ? n->n0 : n->n1;
+            lo[0] = fminf(lo[0], xy[0]); hi[0] = fmaxf(hi[0], xy[1]); lo[1] = fminf(lo[1], xy[2]); hi[1] = fmaxf(hi[1], xy[3]);
+            lo[2] = fminf(lo[2], n->n2[2 * s]); hi[2] = fmaxf(hi[2], n->n2[2 * s + 1]);
+        }
+        writeChildBox(r.nodes, parent, lo, hi);
+        node = parent >> 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // host-callable launch wrappers
 // ------------------------------------------------------------------------------------------------
 static inline dim3 grid1(uint64_t n, uint32_t block) { return dim3((uint32_t)((n + block - 1) / block)); }
@@ -958,7 +1031,7 @@ void launchSortRays(cudaStream_t st, int smCount, const SortBuffers& sb, const C
     (void)a0; (void)a1;
     SortJob j;
     j.keys[0] = sb.keysExt; j.keys[1] = sb.keysShadow; j.perm[0] = sb.permExt; j.perm[1] = sb.permShadow;
-    j.hist = sb.hist; j.cursor = sb.cursor; j.counters = counters;
+    j.hist = sb.hist; j.cursor = sb.cursor; j.blockHist = sb.blockHist; j.counters = counters;
     k_sort_count<<<dim3(smCount, 2), SORT_THREADS, smemBytes, st>>>(j);
     k_sort_scan<<<2, SORT_THREADS, 0, st>>>(j);
     k_sort_scatter<<<dim3(smCount, 2), SORT_THREADS, smemBytes, st>>>(j);
@@ -1012,6 +1085,10 @@ void launchMathProbe(cudaStream_t st, int fn, const float* a, const float* b, ui
 void launchBsdfProbe(cudaStream_t st, const float* q14, uint32_t n, float* out4) { k_bsdf_probe<<<grid1(n, 128), 128, 0, st>>>(q14, n, out4); }
 void launchEnvProbe(cudaStream_t st, const DeviceScene& sc, int op, const float* in3, uint32_t n, float* out7) {
     k_env_probe<<<grid1(n, 128), 128, 0, st>>>(sc, op, in3, n, out7);
+}
+void launchTlasRefit(cudaStream_t st, const TlasRefit& r, const uint32_t* dirty, uint32_t nDirty, uint32_t nSlots) {
+    if (nDirty) k_tlas_boxes<<<grid1(nDirty, 128), 128, 0, st>>>(r, dirty, nDirty);
+    if (nSlots) k_tlas_propagate<<<grid1(nSlots, 128), 128, 0, st>>>(r, nSlots);
 }
 void launchPick(cudaStream_t st, const DeviceScene& sc, const DCamera& cam, float x, float y, MsneClick* out) {
     k_pick<<<1, 1, 0, st>>>(sc, cam, make_float2(x, y), out);

@@ -42,6 +42,7 @@ struct SortBuffers {          // sized for P extension + 2 P shadow rays (runtim
     uint16_t* keysExt; uint16_t* keysShadow;
     uint32_t* permExt; uint32_t* permShadow;
     uint32_t* hist; uint32_t* cursor;   // [2][2^15] each; hist is zero between sorts
+    uint32_t* blockHist;                // [2][SM count][2^15]
 };
 // three launches (count, scan, scatter); the item counts are read from `counters` (device memory) when the kernels run
 void launchSortRays(cudaStream_t st, int smCount, const SortBuffers& sb, const Counters* counters);
@@ -60,6 +61,17 @@ void launchTraceProbe(cudaStream_t st, const DeviceScene& sc, const float* rays8
 void launchMathProbe(cudaStream_t st, int fn, const float* a, const float* b, uint32_t n, float* out);
 void launchBsdfProbe(cudaStream_t st, const float* q14, uint32_t n, float* out4);
 void launchEnvProbe(cudaStream_t st, const DeviceScene& sc, int op, const float* in3, uint32_t n, float* out7);
+// TLAS refit on the device (kernels.cu k_tlas_boxes / k_tlas_propagate)
+struct TlasRefit {
+    BvhNode2* nodes;              // TLAS nodes (boxes rewritten in place)
+    const DInstance* instances;   // pad[0] = BLAS id, pad[1] = TLAS leaf slot (0xFFFFFFFF: none)
+    const float* blasBounds;      // per BLAS: lo.xyz, hi.xyz (object space, padded)
+    const uint32_t* slotNode;     // per TLAS leaf slot: node * 2 + child
+    const uint32_t* parent;       // per node: parent * 2 + child, 0xFFFFFFFF for the root
+    const uint32_t* expected;     // per node: non-empty children (1 or 2)
+    uint32_t* arrived;            // per node, zero between refits
+};
+void launchTlasRefit(cudaStream_t st, const TlasRefit& r, const uint32_t* dirty, uint32_t nDirty, uint32_t nSlots);
 void launchPick(cudaStream_t st, const DeviceScene& sc, const DCamera& cam, float x, float y, MsneClick* out);
 void launchPrimaryProbe(cudaStream_t st, const DCamera& cam, const DConstants& k, uint32_t sample, float* rays6, uint32_t* rngState);
 int traceOccupancyBlocksPerSm();

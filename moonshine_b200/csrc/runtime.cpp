@@ -11,6 +11,7 @@
 // areas) is compiled with -ffp-contract=off and follows the reference's operation order
 // (engine/vector.zig:350-362,501-521; engine/hrtsystem/alias_table.zig:28-91; Accel.zig:503-521).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -93,6 +94,9 @@ struct HostInstance {
     uint32_t customIndex, geometryCount;
     std::vector<uint32_t> meshKey;   // BLAS dedupe key: the mesh ids of the geometry list (Accel.zig:315-343)
     uint32_t blas;                   // index into blases
+    bool inStatic = false;           // its triangles are part of the current merged static BLAS
+    uint32_t tlasSlot = 0xFFFFFFFFu; // its leaf in the current TLAS (transformed instances that were visible when it was built)
+    uint32_t triCount = 0;
 };
 
 struct Blas { uint32_t rootNode; BuildBox bounds; uint32_t depth; };
@@ -231,6 +235,15 @@ struct HdMoonshine {
     // topology and only its boxes are recomputed bottom-up (Accel.zig:629-679 recordRebuild with mode = update_khr).
     bool tlasRefitOk = false;
     uint32_t refitsSinceBuild = 0, maxRefits = 32;   // MSNE_TLAS_MAX_REFITS: rebuild after this many consecutive refits
+    // Edits that only touch instance RECORDS (transform of a TLAS member, visibility of a member of either level) are served
+    // without rebuilding anything: the records of `dirtyInstances` are re-uploaded (128 B each), transforms additionally refit
+    // the TLAS boxes on the device. Hidden members stay in their tree (skipped at traversal time) until they make up a quarter
+    // of it, then the next sync rebuilds without them.
+    std::vector<uint32_t> dirtyInstances;
+    uint64_t staticTris = 0, hiddenStaticTris = 0;
+    uint32_t tlasItemCount = 0, hiddenTlasItems = 0;
+    DevBuf<uint32_t> dSlotNode, dNodeParent, dNodeExpected, dNodeArrived, dDirty;
+    DevBuf<float> dBlasBounds;
     std::vector<BvhNode2> tlasHostNodes;             // pre-encoded TLAS as uploaded
     std::vector<uint32_t> tlasHostSlots;             // TLAS leaf slot -> instance record
     // emitter alias table: rebuilt by the next render after an edit that changes it, once following is switched on
@@ -268,7 +281,9 @@ struct HdMoonshine {
     // last finished wave. Whatever the hint, the image is the same bits (tests assert it). Two wave contexts (own stream, pool,
     // counters) alternate, so the latency-bound Russian-roulette tail of one wave (k_tail: a few thousand paths, ~150 bounces
     // deep) runs under the bandwidth-bound head of the next; accumulates are chained by events to stay in sample order.
-    static constexpr int kWaveContexts = 2;
+    static constexpr int kWaveContexts = 4;
+    static constexpr int kDefaultWaveContexts = 2;
+    static constexpr uint64_t kMinSplitWave = 131072;   // paths: smaller renders stay one wave
     static constexpr uint32_t kMaxHistory = 192;   // wavefront bounces logged / scheduled per wave at most (k_tail finishes the rest)
     static const int kProfEvents = 96;
     struct WaveCtx {
@@ -285,7 +300,7 @@ struct HdMoonshine {
         // ray reordering (kernels.h SortBuffers): keys of the extension (P) and the shadow queue (2 P), the two permutations,
         // global histogram + bin cursors of the counting sort
         DevBuf<uint16_t> sortKeysExt, sortKeysShadow;
-        DevBuf<uint32_t> sortPermExt, sortPermShadow, sortHist, sortCursor;
+        DevBuf<uint32_t> sortPermExt, sortPermShadow, sortHist, sortCursor, sortBlockHist;
         cudaEvent_t evDone = nullptr;      // recorded after the wave's k_accumulate
         bool pending = false;              // a wave was enqueued and its log not read yet
         uint32_t bounces = 0;              // wavefront bounces that wave scheduled
@@ -308,7 +323,7 @@ struct HdMoonshine {
     bool forceTwoLevel = false;       // MSNE_TWO_LEVEL=1: never use the single-level trace kernel (A/B measurements)
     bool logBounces = false;          // MSNE_LOG_BOUNCES=1: queue sizes after every bounce on stderr (printed when the wave's log is read)
     uint64_t binnedThreshold = 262144;   // bounces expected to shade fewer paths than this use the single generic shade launch
-    int waveContextsInUse = kWaveContexts;   // MSNE_WAVE_CONTEXTS=1: one wave at a time (A/B measurements)
+    int waveContextsInUse = kDefaultWaveContexts;   // MSNE_WAVE_CONTEXTS=1: one wave at a time (A/B measurements)
     // survival profile of the last finished wave: survivalIn[b] = live paths entering bounce b / paths of the wave (b = 0: 1)
     std::vector<double> survivalIn;
 
@@ -492,10 +507,12 @@ struct HdMoonshine {
         std::vector<TriRec> stTris;
         std::vector<BuildBox> stBoxes;
         for (uint32_t i = 0; i < nInst; i++) {
-            const HostInstance& in = instances[i];
-            if (!in.visible || !isIdentity(in.transform)) continue;
+            HostInstance& in = instances[i];
+            in.inStatic = in.visible && isIdentity(in.transform);
+            if (!in.inStatic) continue;
             for (uint32_t g = 0; g < in.meshKey.size(); g++) meshTriangles(*meshes[in.meshKey[g]], g, i, stTris, stBoxes);
         }
+        staticTris = stTris.size(); hiddenStaticTris = 0;
         staticRec = DInstance{};
         const float I[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
         memcpy(staticRec.o2w, I, 48); memcpy(staticRec.w2o, I, 48);
@@ -559,55 +576,41 @@ struct HdMoonshine {
         DInstance d{};
         memcpy(d.o2w, in.transform, 48); memcpy(d.w2o, in.inverse, 48);
         d.customIndex = in.customIndex; d.visible = in.visible ? 1 : 0;
-        if (in.visible && !isIdentity(in.transform)) d.blasRoot = blases[in.blas].rootNode;
+        if (!isIdentity(in.transform) && in.blas != 0xFFFFFFFFu) { d.blasRoot = blases[in.blas].rootNode; d.pad[0] = in.blas; }
+        d.pad[1] = in.tlasSlot;
         return d;
     }
 
-    // (2b) transform-only edits: same TLAS topology, boxes recomputed bottom-up. A node is always created after its
-    //      parent (bvh_build.cpp), so one reverse sweep sees every child before its parent. Hit results do not depend on
-    //      the tree (closest = min t with id tie-break), only traversal cost does; after `maxRefits` refits it is rebuilt.
-    void refitTlas() {
+    // re-uploads the device records of the edited instances (one 128-byte copy each; everything when there are many)
+    void uploadDirtyRecords() {
+        std::sort(dirtyInstances.begin(), dirtyInstances.end());
+        dirtyInstances.erase(std::unique(dirtyInstances.begin(), dirtyInstances.end()), dirtyInstances.end());
         const uint32_t nInst = (uint32_t)instances.size();
-        std::vector<DInstance> di(nInst + 1);
-        for (uint32_t i = 0; i < nInst; i++) di[i] = instanceRecord(instances[i]);
-        di[nInst] = staticRec;
-        dInstances.upload(di.data(), di.size(), stream);
-        std::vector<BuildBox> slotBox(tlasHostSlots.size());
-        for (size_t s = 0; s < tlasHostSlots.size(); s++) {
-            const uint32_t rec = tlasHostSlots[s];
-            slotBox[s] = rec == nInst ? staticBounds : instanceWorldBox(instances[rec]);
-        }
-        auto childBoxOf = [&](const BvhNode2& n, int s) {
-            BuildBox b;
-            const float* xy = s == 0 ? n.n0 : n.n1;
-            b.lo[0] = xy[0]; b.hi[0] = xy[1]; b.lo[1] = xy[2]; b.hi[1] = xy[3]; b.lo[2] = n.n2[2 * s]; b.hi[2] = n.n2[2 * s + 1];
-            return b;
-        };
-        for (size_t k = tlasHostNodes.size(); k-- > 0;) {
-            BvhNode2& n = tlasHostNodes[k];
-            for (int s = 0; s < 2; s++) {
-                const int32_t ref = n.c[s];
-                if (ref == REF_EMPTY) continue;
-                BuildBox b;
-                if (ref & REF_ITEM) b = slotBox[(uint32_t)(ref & ~REF_ITEM)];
-                else {
-                    const BvhNode2& ch = tlasHostNodes[(size_t)ref];
-                    bool any = false;
-                    for (int a = 0; a < 3; a++) { b.lo[a] = 1e30f; b.hi[a] = -1e30f; }
-                    for (int cs = 0; cs < 2; cs++) {
-                        if (ch.c[cs] == REF_EMPTY) continue;
-                        const BuildBox cb = childBoxOf(ch, cs);
-                        for (int a = 0; a < 3; a++) { b.lo[a] = std::min(b.lo[a], cb.lo[a]); b.hi[a] = std::max(b.hi[a], cb.hi[a]); }
-                        any = true;
-                    }
-                    if (!any) continue;
-                }
-                float* xy = s == 0 ? n.n0 : n.n1;
-                xy[0] = b.lo[0]; xy[1] = b.hi[0]; xy[2] = b.lo[1]; xy[3] = b.hi[1];
-                n.n2[2 * s] = b.lo[2]; n.n2[2 * s + 1] = b.hi[2];
+        if (dirtyInstances.size() > 4096) {
+            std::vector<DInstance> di(nInst + 1);
+            for (uint32_t i = 0; i < nInst; i++) di[i] = instanceRecord(instances[i]);
+            di[nInst] = staticRec;
+            dInstances.upload(di.data(), di.size(), stream);
+            CK(cudaStreamSynchronize(stream));
+        } else {
+            std::vector<DInstance> recs(dirtyInstances.size());
+            for (size_t k = 0; k < dirtyInstances.size(); k++) {
+                recs[k] = instanceRecord(instances[dirtyInstances[k]]);
+                CK(cudaMemcpyAsync(dInstances.p + dirtyInstances[k], &recs[k], sizeof(DInstance), cudaMemcpyHostToDevice, stream));
             }
+            CK(cudaStreamSynchronize(stream));   // recs die here
         }
-        dTlasNodes.upload(tlasHostNodes.data(), tlasHostNodes.size(), stream);
+    }
+    // (2b) transform-only edits: same TLAS topology; the edited instances' boxes are recomputed and carried up the tree ON THE
+    //      DEVICE (kernels.cu k_tlas_boxes / k_tlas_propagate) - what crosses the bus is 132 B per edited instance, whatever the
+    //      size of the scene. Hit results do not depend on the tree (closest = min t with id tie-break), only traversal cost
+    //      does; after `maxRefits` refits the TLAS is rebuilt.
+    void refitTlas() {
+        uploadDirtyRecords();
+        dDirty.upload(dirtyInstances.data(), dirtyInstances.size(), stream);
+        TlasRefit r{dTlasNodes.p, dInstances.p, dBlasBounds.p, dSlotNode.p, dNodeParent.p, dNodeExpected.p, dNodeArrived.p};
+        launchTlasRefit(stream, r, dDirty.p, (uint32_t)dirtyInstances.size(), (uint32_t)tlasHostSlots.size());
+        stats.kernel_launches += 2;
         CK(cudaStreamSynchronize(stream));
         refitsSinceBuild++;
         stats_tlas_refits++;
@@ -630,11 +633,11 @@ struct HdMoonshine {
             dTris.upload(triPool.data(), triPool.size(), stream);
         }
         for (uint32_t i = 0; i < nInst; i++) {
-            const HostInstance& in = instances[i];
+            HostInstance& in = instances[i];
+            in.tlasSlot = 0xFFFFFFFFu;
             if (in.visible && !isIdentity(in.transform)) { boxes.push_back(instanceWorldBox(in)); items.push_back(i); }
-            di[i] = instanceRecord(in);
         }
-        dInstances.upload(di.data(), di.size(), stream);
+        tlasItemCount = (uint32_t)items.size(); hiddenTlasItems = 0;
         {   // bounds of everything visible: the 16^3 grid of the ray-sorting keys (ordering only, never a result)
             BuildBox all; for (int a = 0; a < 3; a++) { all.lo[a] = 1e30f; all.hi[a] = -1e30f; }
             for (const BuildBox& b : boxes) for (int a = 0; a < 3; a++) { all.lo[a] = std::min(all.lo[a], b.lo[a]); all.hi[a] = std::max(all.hi[a], b.hi[a]); }
@@ -656,19 +659,36 @@ struct HdMoonshine {
             buildDepthLimited(boxes, 1, (uint32_t)MSNE_STACK - 2u - maxBlasDepth, tl);
             tlasDepth = tl.depth;
             std::vector<uint32_t> slots(tl.order.size());
-            for (size_t s = 0; s < tl.order.size(); s++) slots[s] = items[tl.order[s]];
-            for (BvhNode2& n : tl.nodes)
+            for (size_t s = 0; s < tl.order.size(); s++) { slots[s] = items[tl.order[s]]; if (slots[s] < nInst) instances[slots[s]].tlasSlot = (uint32_t)s; }
+            // what the device-side refit needs: where every leaf slot lives, every node's parent, how many children it has
+            std::vector<uint32_t> slotNode(slots.size(), 0), parent(tl.nodes.size(), 0xFFFFFFFFu), expected(tl.nodes.size(), 0);
+            for (size_t k = 0; k < tl.nodes.size(); k++) {
+                BvhNode2& n = tl.nodes[k];
                 for (int s = 0; s < 2; s++) {
                     const int32_t child = n.c[s], count = n.c[2 + s];
-                    if (count > 0) n.c[s] = REF_ITEM | child;   // leaf size is 1: one instance per TLAS leaf
+                    if (count > 0) { n.c[s] = REF_ITEM | child; slotNode[(size_t)child] = (uint32_t)(2 * k + s); expected[k]++; }   // leaf size is 1: one instance per TLAS leaf
                     else if (child < 0) { n.c[s] = REF_EMPTY; setEmptyChild(n, s); }
+                    else { parent[(size_t)child] = (uint32_t)(2 * k + s); expected[k]++; }
                 }
+            }
             for (BvhNode2& n : tl.nodes) n.c[2] = n.c[3] = 0;
             dTlasNodes.upload(tl.nodes.data(), tl.nodes.size(), stream);
             dTlasItems.upload(slots.data(), slots.size(), stream);
+            dSlotNode.upload(slotNode.data(), slotNode.size(), stream);
+            dNodeParent.upload(parent.data(), parent.size(), stream);
+            dNodeExpected.upload(expected.data(), expected.size(), stream);
+            dNodeArrived.ensure(tl.nodes.size());
+            CK(cudaMemsetAsync(dNodeArrived.p, 0, tl.nodes.size() * sizeof(uint32_t), stream));
+            std::vector<float> bb(6 * std::max<size_t>(1, blases.size()), 0.0f);
+            for (size_t b = 0; b < blases.size(); b++) for (int a = 0; a < 3; a++) { bb[6 * b + a] = blases[b].bounds.lo[a]; bb[6 * b + 3 + a] = blases[b].bounds.hi[a]; }
+            dBlasBounds.upload(bb.data(), bb.size(), stream);
+            CK(cudaStreamSynchronize(stream));   // the staging vectors die here
             tlasHostNodes.swap(tl.nodes); tlasHostSlots.swap(slots);
         } else { tlasHostNodes.clear(); tlasHostSlots.clear(); }
+        for (uint32_t i = 0; i < nInst; i++) di[i] = instanceRecord(instances[i]);   // after the slots are known
+        dInstances.upload(di.data(), di.size(), stream);
         CK(cudaStreamSynchronize(stream));
+        dirtyInstances.clear();
         refitsSinceBuild = 0;
         stats_tlas_builds++;
     }
@@ -728,11 +748,15 @@ struct HdMoonshine {
             CK(cudaStreamSynchronize(stream));   // staging vectors die here
             tablesDirty = false;
         }
+        const auto t0 = std::chrono::steady_clock::now();
+        const bool accelWork = geomDirty || tlasDirty || !dirtyInstances.empty();
         if (geomDirty) { buildGeometry(); geomDirty = false; tlasDirty = true; tlasRefitOk = false; }
         if (tlasDirty) {
             if (tlasRefitOk && hasTlas && refitsSinceBuild < maxRefits) refitTlas(); else buildTlas();
             tlasDirty = false; tlasRefitOk = false;
-        }
+        } else if (!dirtyInstances.empty()) uploadDirtyRecords();   // visibility toggles: records only
+        dirtyInstances.clear();
+        if (accelWork) stats.accel_sync_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         if (emitterFollowsEdits && emitterStale) { buildEmitterTable(); emitterStale = false; }
         if (aliasDirty || emitterRecIndexed != (consts.indexed_attributes != 0)) {
             dAlias.upload(alias.data(), alias.size(), stream);
@@ -754,6 +778,7 @@ struct HdMoonshine {
         sc.envQuads = dEnvQuads.p;
         sc.texLuts = dSrgbLut.p;
         sc.staticOnly = (tlasStaticOnly && !forceTwoLevel) ? 1u : 0u; sc.staticRoot = staticRec.blasRoot;
+        sc.staticHidden = hiddenStaticTris ? 1u : 0u;
         sc.staticTop = haveStatic ? staticTop : 0u;
         return sc;
     }
@@ -920,9 +945,10 @@ struct HdMoonshine {
         if (c.sortKeysExt.n >= P) return;
         c.sortKeysExt.alloc(P); c.sortKeysShadow.alloc(2 * P);
         c.sortPermExt.alloc(P); c.sortPermShadow.alloc(2 * P);
+        c.sortBlockHist.ensure((size_t)2 * smCount * 32768);
     }
     static SortBuffers sortBuffers(const WaveCtx& c) {
-        return SortBuffers{c.sortKeysExt.p, c.sortKeysShadow.p, c.sortPermExt.p, c.sortPermShadow.p, c.sortHist.p, c.sortCursor.p};
+        return SortBuffers{c.sortKeysExt.p, c.sortKeysShadow.p, c.sortPermExt.p, c.sortPermShadow.p, c.sortHist.p, c.sortCursor.p, c.sortBlockHist.p};
     }
     static WaveState waveState(const WaveCtx& c) {
         WaveState ws{};
@@ -1041,7 +1067,11 @@ struct HdMoonshine {
         // pool per context: half of the paths in flight; a render that fits one context uses only that one
         const int nCtx = waveContextsInUse;
         const uint64_t perCtx = std::max<uint64_t>(1, pathsInFlight / (uint64_t)nCtx);
-        const uint64_t wantP = std::min<uint64_t>(perCtx, totalPaths);
+        // A render that would fit one wave is still cut into one wave per context (when there is enough of it): the contexts'
+        // streams run concurrently, so the latency-bound end of every wave - a handful of long paths - overlaps the others'
+        // instead of being waited for in full. This is what a one-sample HdMoonshineRender call (hydra.zig:316-329) gets.
+        const uint64_t split = totalPaths >= (uint64_t)nCtx * kMinSplitWave ? (totalPaths + (uint64_t)nCtx - 1) / (uint64_t)nCtx : totalPaths;
+        const uint64_t wantP = std::min<uint64_t>(perCtx, (split + 31) & ~31ull);
         ensurePool(ctx[0], wantP);
         const uint32_t P = (uint32_t)std::min<uint64_t>(ctx[0].pb.capacity, wantP);
         const uint32_t pixChunk = std::min(s.nPix, P);
@@ -1290,6 +1320,7 @@ InstanceHandle HdMoonshineCreateInstance(HdMoonshine* h, Mat3x4 t, const Geometr
             in.meshKey.push_back(geoms[i].mesh);
         }
         in.blas = 0xFFFFFFFFu;
+        for (uint32_t mk : in.meshKey) in.triCount += (uint32_t)(h->meshes.at(mk)->idx.size() / 3);
         h->instances.push_back(in);
         h->tablesDirty = true;
         if (HdMoonshine::isIdentity(in.transform)) h->geomDirty = true;   // joins the flattened static BLAS
@@ -1306,8 +1337,21 @@ void HdMoonshineSetInstanceVisibility(HdMoonshine* h, InstanceHandle i, bool vis
         HostInstance& in = h->instances.at(i);
         if (in.visible != visible) {
             in.visible = visible;
-            if (HdMoonshine::isIdentity(in.transform)) h->geomDirty = true;   // member of the flattened static BLAS
-            else { h->tlasDirty = true; h->tlasRefitOk = false; }             // transformed instance: the TLAS item set changes
+            // A member of the merged static BLAS or of the TLAS keeps its place in the tree: only its record changes (traversal
+            // skips hidden members). Rebuild only to INSERT something the tree does not hold, or once a quarter of it is hidden.
+            if (HdMoonshine::isIdentity(in.transform)) {
+                if (in.inStatic) {
+                    h->dirtyInstances.push_back(i);
+                    if (visible) h->hiddenStaticTris -= in.triCount; else h->hiddenStaticTris += in.triCount;
+                    if (h->hiddenStaticTris * 4 > h->staticTris) h->geomDirty = true;
+                } else if (visible) h->geomDirty = true;
+            } else {
+                if (in.tlasSlot != 0xFFFFFFFFu) {
+                    h->dirtyInstances.push_back(i);
+                    if (visible) h->hiddenTlasItems--; else h->hiddenTlasItems++;
+                    if (h->hiddenTlasItems * 4 > h->tlasItemCount) { h->tlasDirty = true; h->tlasRefitOk = false; }
+                } else if (visible) { h->tlasDirty = true; h->tlasRefitOk = false; }
+            }
         }
         h->clearAllSensors();
     )
@@ -1322,13 +1366,16 @@ void HdMoonshineSetInstanceTransform(HdMoonshine* h, InstanceHandle i, Mat3x4 t)
         memcpy(in.transform, &t, 48);
         inverseAffine(in.transform, in.inverse);
         const bool isStatic = HdMoonshine::isIdentity(in.transform);
-        if (wasStatic || isStatic) h->geomDirty = true;   // enters/leaves the flattened static BLAS
-        else {
+        if (wasStatic || isStatic) {
+            // enters / leaves the flattened static BLAS (an invisible identity instance that was never part of it: nothing to do)
+            if (in.inStatic || (isStatic && in.visible) || (!isStatic && in.visible)) h->geomDirty = true;
+        } else if (in.tlasSlot != 0xFFFFFFFFu) {
             // TLAS + instance records only (Accel.zig:567-602 recordUpdateSingleTransform + :629-679 update-mode rebuild):
-            // the set of TLAS items is unchanged, so the next render refits instead of rebuilding
+            // the set of TLAS items is unchanged, so the next render refits - on the device - instead of rebuilding
+            h->dirtyInstances.push_back(i);
             if (!h->tlasDirty) h->tlasRefitOk = true;
             h->tlasDirty = true;
-        }
+        } else if (in.visible) { h->tlasDirty = true; h->tlasRefitOk = false; }   // visible but not in the tree yet
         for (uint32_t g = 0; g < in.geometryCount; g++) if (h->geometries[in.customIndex + g].sampled & 0xFF) h->emitterStale = true;
         h->clearAllSensors();
     )
@@ -1492,7 +1539,7 @@ void HdMoonshineExtSetSchedule(HdMoonshine* h, uint64_t tailPaths, uint64_t binn
     LOCK(h);
     h->tailThreshold = tailPaths == UINT64_MAX ? 32768 : tailPaths;
     h->binnedThreshold = binnedPaths == UINT64_MAX ? 262144 : binnedPaths;
-    h->waveContextsInUse = waveContexts == 0 ? HdMoonshine::kWaveContexts : (int)std::min<uint32_t>(waveContexts, HdMoonshine::kWaveContexts);
+    h->waveContextsInUse = waveContexts == 0 ? HdMoonshine::kDefaultWaveContexts : (int)std::min<uint32_t>(waveContexts, HdMoonshine::kWaveContexts);
     h->survivalIn.clear();
 }
 void HdMoonshineExtGetStats(const HdMoonshine* h, MsneStats* out) {

@@ -122,6 +122,9 @@ DI bool traceRay(const DeviceScene& sc, const float3 o, const float3 d, const fl
                 float t, u, v;
                 if (!triTest(t0, t1, t2, ray, tmin, tmax, t, u, v)) continue;
                 const uint32_t inst = curInst == STATIC_INST ? __float_as_uint(t2.w) : curInst;
+                // a member of the flattened static BLAS that was hidden after the BLAS was built (runtime.cpp: no rebuild for a
+                // visibility toggle); sc.staticHidden is a launch-uniform flag, 0 in every scene that never hides one
+                if (sc.staticHidden && curInst == STATIC_INST && !__ldg(&sc.instances[inst].visible)) continue;
                 // structured exit (no `return` from inside the loops): with an early return ptxas gives up the convergence
                 // barriers of the whole any-hit walk and its lanes never re-join (-15 % on k_trace, profiles/r01_sweeps.md)
                 if (ANY_HIT) { hit.inst = inst; node = REF_END; break; }
@@ -150,6 +153,10 @@ DI bool traceRay(const DeviceScene& sc, const float3 o, const float3 d, const fl
             } else {
                 const uint32_t inst = __ldg(sc.tlasItems + (node & ~REF_ITEM));
                 const DInstance* in = sc.instances + inst;
+                if (!__ldg(&in->visible)) {
+                    node = stack[--sp];          // hidden after the TLAS was built: mask 0 (Accel.zig:401), nothing to enter
+                    continue;
+                }
                 if (__ldg(&in->isStatic)) {
                     curInst = STATIC_INST;   // world space == object space
                 } else {

@@ -65,7 +65,7 @@ class MsneStats(C.Structure):
     _fields_ = [("rays_closest", C.c_uint64), ("rays_shadow", C.c_uint64), ("samples", C.c_uint64), ("kernel_launches", C.c_uint64),
                 ("device_ms", C.c_double), ("trace_ms", C.c_double), ("trace_launches", C.c_uint64), ("max_bounce_reached", C.c_uint64),
                 ("static_blas_builds", C.c_uint64), ("tlas_builds", C.c_uint64), ("tlas_refits", C.c_uint64), ("sort_ms", C.c_double),
-                ("waves", C.c_uint64), ("host_syncs", C.c_uint64), ("tail_paths", C.c_uint64)]
+                ("waves", C.c_uint64), ("host_syncs", C.c_uint64), ("tail_paths", C.c_uint64), ("accel_sync_ms", C.c_double)]
 
 
 class MsneClickData(C.Structure):   # input.hlsl:1-6

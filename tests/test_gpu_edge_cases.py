@@ -153,8 +153,20 @@ def test_transform_edits_of_instanced_objects_rebuild_only_the_tlas():
     hit = r["instance"] != 0xFFFFFFFF
     np.testing.assert_array_equal(g["primitive"][hit], r["primitive"][hit])
     assert not (g["instance"] == insts[9]).any()
-    # an edit of a flattened (identity) instance does rebuild the BLAS level
-    m.SetInstanceVisibility(insts[0], False)   # the ground plane
+    # hiding a member of the flattened static BLAS (the ground plane, 2 of its 770 triangles) rebuilds nothing either: the
+    # member stays in the tree and traversal skips it
+    m.SetInstanceVisibility(insts[0], False)
+    o.set_instance_visibility(oinsts[0], False)
+    g, r = m.trace(rays), o.trace(rays)
+    np.testing.assert_array_equal(g["instance"], r["instance"])
+    assert not (g["instance"] == insts[0]).any()
+    s2 = m.GetStats()
+    assert (s2.static_blas_builds, s2.tlas_builds) == (1, 2)
+    # a TRANSFORM edit of a flattened instance changes the BLAS level and does rebuild it
+    lifted = np.eye(3, 4, dtype=np.float32)
+    lifted[2, 3] = 0.5
+    m.SetInstanceVisibility(insts[0], True)
+    m.SetInstanceTransform(insts[0], lifted)
     m.RenderLaunches(sensor, lens, 1)
     assert m.GetStats().static_blas_builds == 2
 
@@ -199,11 +211,34 @@ def test_transform_only_edits_refit_the_tlas_and_hits_stay_exact():
         np.testing.assert_array_equal(g["u"][hit].view(np.uint32), r["u"][hit].view(np.uint32))
         st = m.GetStats()
         assert (st.static_blas_builds, st.tlas_builds, st.tlas_refits) == (1, 1, step + 1)
-    # a visibility change alters the TLAS item set -> rebuild, not refit
+    # a visibility change rebuilds nothing: the instance keeps its TLAS leaf and traversal skips it (mask 0, Accel.zig:401)
     m.SetInstanceVisibility(insts[movable[0]], False)
-    m.trace(rays)
+    o.set_instance_visibility(oinsts[movable[0]], False)
+    g, r = m.trace(rays), o.trace(rays)
+    np.testing.assert_array_equal(g["instance"], r["instance"])
+    assert not (g["instance"] == insts[movable[0]]).any()
     st = m.GetStats()
-    assert (st.tlas_builds, st.tlas_refits) == (2, 3)
+    assert (st.tlas_builds, st.tlas_refits) == (1, 3)
+    # moving a hidden instance and showing it again: still no rebuild, and it is found at its new place
+    t = sc.instances[movable[0]].transform.copy()
+    t[:, 3] += np.array([1.0, -1.0, 0.3], np.float32)
+    m.SetInstanceTransform(insts[movable[0]], t)
+    o.set_instance_transform(oinsts[movable[0]], t)
+    m.SetInstanceVisibility(insts[movable[0]], True)
+    o.set_instance_visibility(oinsts[movable[0]], True)
+    g, r = m.trace(rays), o.trace(rays)
+    np.testing.assert_array_equal(g["instance"], r["instance"])
+    hit = r["instance"] != 0xFFFFFFFF
+    np.testing.assert_array_equal(g["u"][hit].view(np.uint32), r["u"][hit].view(np.uint32))
+    st = m.GetStats()
+    assert (st.static_blas_builds, st.tlas_builds, st.tlas_refits) == (1, 1, 4)
+    # once a quarter of the TLAS leaves are hidden the next sync rebuilds without them
+    for i in movable[: len(movable) // 4 + 2]:
+        m.SetInstanceVisibility(insts[i], False)
+        o.set_instance_visibility(oinsts[i], False)
+    g, r = m.trace(rays), o.trace(rays)
+    np.testing.assert_array_equal(g["instance"], r["instance"])
+    assert m.GetStats().tlas_builds == 2
 
 
 def test_emitter_table_follows_edits_when_asked():

@@ -105,3 +105,21 @@ def test_cfg5_million_instances():
     assert np.isfinite(g).all()
     st = m.GetStats()
     assert st.rays_closest >= 2048 * 2048
+    # Accel.zig:567-602 + :629-679 at this scale: moving 16 of the 10^6 instances is served by re-uploading 16 records and a
+    # refit of the TLAS on the device - no rebuild, and far below the ~seconds a rebuild of the instance level costs
+    rs = np.random.RandomState(3)
+    _, _, _, insts = None, None, None, list(range(len(sc.instances)))   # handles are dense indices in creation order
+    for i in rs.choice(np.arange(1, 1_000_001), 16, replace=False):
+        t = sc.instances[i].transform.copy()
+        t[:, 3] += np.array([0.4, -0.3, 0.2], np.float32)
+        m.SetInstanceTransform(int(i), t)
+        o.set_instance_transform(int(i), t)
+    before = st.accel_sync_ms
+    gh, rh = m.trace(rays), o.trace(rays)
+    st2 = m.GetStats()
+    print(f"cfg5: 16 moved instances -> refit in {st2.accel_sync_ms - before:.2f} ms (first build of the scene: {before:.0f} ms)")
+    assert (st2.tlas_builds, st2.tlas_refits, st2.static_blas_builds) == (st.tlas_builds, st.tlas_refits + 1, st.static_blas_builds)
+    assert st2.accel_sync_ms - before < 50.0
+    np.testing.assert_array_equal(gh["instance"], rh["instance"])
+    hit = rh["instance"] != 0xFFFFFFFF
+    np.testing.assert_array_equal(gh["u"][hit].view(np.uint32), rh["u"][hit].view(np.uint32))

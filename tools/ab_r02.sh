@@ -10,6 +10,10 @@ for v in "$@"; do
     ctx2big) $B --paths-in-flight 268435456 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
     ctx2small) $B --paths-in-flight 67108864 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
     ctx1big) MSNE_WAVE_CONTEXTS=1 $B --paths-in-flight 268435456 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
+    ctx4) MSNE_WAVE_CONTEXTS=4 $B 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
+    ctx4small) MSNE_WAVE_CONTEXTS=4 $B --paths-in-flight 67108864 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
+    ctx2tail128k) MSNE_TAIL_THRESHOLD=131072 $B 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
+    ctx4tail128k) MSNE_WAVE_CONTEXTS=4 MSNE_TAIL_THRESHOLD=131072 $B 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
     nosort) MSNE_SORT_THRESHOLD=0 $B 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
     tail8k) MSNE_TAIL_THRESHOLD=8192 $B 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
     tail128k) MSNE_TAIL_THRESHOLD=131072 $B 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
