@@ -103,7 +103,6 @@ struct DeviceScene {
     uint32_t staticOnly;           // 1: the TLAS holds nothing but the merged static BLAS -> single-level traversal from staticRoot
     uint32_t staticRoot;
     uint32_t staticHidden;         // 1: some member of the merged static BLAS is hidden (checked per candidate hit, traverse.cuh)
-    uint32_t staticTop;            // MSNE_TRACE_SMEM_NODES experiment: the first `staticTop` nodes from staticRoot are the top of the tree in BFS order
 };
 
 // specialization constants (main.hlsl:34-40) as runtime values

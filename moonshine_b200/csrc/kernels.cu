@@ -135,77 +135,157 @@ DI uint32_t hitBin(const DeviceScene& sc, const HitRec& h) {
 // of this bounce, every lane walks its ray to the end (traverse.cuh), then the warp sorts its hits by material type.
 // Refilling idle lanes before the whole ticket is done ("dynamic fetch") was measured in three variants and is not
 // used (profiles/r01_sweeps.md).
-// SORTED: the tickets walk the permutations of the extension and the shadow queue (radix sort of the keys the shade pass wrote:
-// rays ordered by direction octant and origin cell) instead of the queue order, so the 32 rays of a warp visit the same part of the tree; the material binning is then
-// done by k_bin in queue order (the shade kernels keep reading contiguous path state).
+// SORTED: the tickets walk the permutations of the extension and the shadow queue (counting sort of the keys the shade pass wrote:
+// rays ordered by direction octant and origin cell) instead of the queue order, so the 32 rays of a warp visit the same part of
+// the tree; the material binning is then done by k_bin in queue order (the shade kernels keep reading contiguous path state).
+//
+// Ticket staging (MSNE_TRACE_STAGING): the rays of a warp's NEXT ticket are copied into shared memory while the warp traverses the
+// current one, so no ticket starts with every lane waiting a DRAM round trip for its ray (queues are streamed evict-first: always
+// a miss), and without holding the next ray in registers - registers are what bounds this kernel's occupancy.
+//   queue order: a ticket is 32 consecutive rays = ONE contiguous kilobyte -> one bulk tensor-memory-accelerator copy per ticket
+//                (cp.async.bulk.shared.global, completion counted in bytes on a per-warp mbarrier; SASS: UBLKCP + SYNCS);
+//   sorted:      the rays are gathered through the permutation -> two 16-byte cp.async (LDGSTS) per lane, the permutation entries
+//                themselves fetched one ticket further ahead into a register.
+// The index space is padded so that a ticket never straddles the two queues: extension tickets cover [0, roundup32(nLive)), shadow
+// tickets follow.
+#ifndef MSNE_TRACE_STAGING
+#define MSNE_TRACE_STAGING 1
+#endif
+DI uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+DI void mbarInit(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+DI void mbarExpectTx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+DI void mbarWait(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+}
+DI void bulkCopyG2S(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+DI void cpAsync16(uint32_t dst, const void* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
+DI void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+DI void cpAsyncWaitAll() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 template <bool TWO_LEVEL, bool SORTED>
 __global__ void __launch_bounds__(TRACE_THREADS, TWO_LEVEL ? TRACE_BLOCKS_PER_SM : TRACE1_BLOCKS_PER_SM) k_trace(DeviceScene sc, PathBuffers pb, WaveState ws, uint32_t buf,
                                                                                                                const uint32_t* __restrict__ permExt,
                                                                                                                const uint32_t* __restrict__ permShadow) {
     const Counters cin = ws.counters[buf];
-    const uint32_t nLive = cin.nLive, total = cin.nLive + cin.nShadow;
+    const uint32_t nLive = cin.nLive, nShadow = cin.nShadow;
+    const uint32_t live32 = (nLive + 31u) & ~31u;          // shadow tickets start at a ticket boundary
+    const uint32_t total = live32 + nShadow;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t ltMask = (1u << lane) - 1u;
-    const BvhNode2* smemTop = nullptr;
-#if MSNE_TRACE_SMEM_NODES > 0
-    // TMA staging of the top of the tree: one bulk copy (cp.async.bulk, the 1-D TMA path) per block, completion through an
-    // mbarrier transaction count; every thread then waits on phase 0 of the barrier.
-    extern __shared__ __align__(128) unsigned char smemRaw[];
-    if (!TWO_LEVEL && sc.staticTop > 0) {
-        const uint32_t bytes = sc.staticTop * (uint32_t)sizeof(BvhNode2);
-        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smemRaw);
-        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(smemRaw + MSNE_TRACE_SMEM_NODES * sizeof(BvhNode2));
-        if (threadIdx.x == 0) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(dst), "l"(sc.blasNodes + sc.staticRoot), "r"(bytes), "r"(bar) : "memory");
-        }
-        __syncthreads();
-        uint32_t ok = 0;
-        while (!ok) {
-            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(bar) : "memory");
-        }
-        smemTop = reinterpret_cast<const BvhNode2*>(smemRaw);
+    const float4* __restrict__ extRays = pb.R0[buf];       // ray q = the two float4 lanes at [2 q], [2 q + 1] (dtypes.h RAY_STRIDE)
+    const float4* __restrict__ shadowRays = pb.Q0;
+    // queue slot of index-space position i (0xFFFFFFFF: padding / past the end), and whether it is an extension ray
+    auto slotOf = [&](uint32_t i, uint32_t permEntry) -> uint32_t {
+        if (i < live32) return i < nLive ? (SORTED ? permEntry : i) : 0xFFFFFFFFu;
+        return i < total ? (SORTED ? permEntry : i - live32) : 0xFFFFFFFFu;
+    };
+    auto permLoad = [&](uint32_t i) -> uint32_t {
+        if (!SORTED) return 0u;
+        if (i < nLive) return __ldg(permExt + i);
+        if (i >= live32 && i < total) return __ldg(permShadow + (i - live32));
+        return 0u;
+    };
+    auto grab = [&]() -> uint32_t {
+        uint32_t b = 0;
+        if (lane == 0) b = atomicAdd(ws.traceTicket, 32u);
+        return __shfl_sync(0xFFFFFFFFu, b, 0);
+    };
+#if MSNE_TRACE_STAGING
+    __shared__ __align__(128) float4 stage[TRACE_THREADS / 32][64];   // one kilobyte per warp: the next ticket's 32 rays
+    __shared__ __align__(8) unsigned long long stageBar[TRACE_THREADS / 32];
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t myStage = smemAddr(&stage[warp][0]), myBar = smemAddr(&stageBar[warp]);
+    uint32_t parity = 0;
+    if (!SORTED) {
+        if (lane == 0) { mbarInit(myBar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+        __syncwarp();
     }
-#endif
+    // starts the copy of ticket `b` (its rays' queue slots: `slot` per lane) into this warp's stage
+    auto stageTicket = [&](uint32_t b, uint32_t slot) {
+        if (b >= total) return;
+        const bool ext = b < live32;
+        if (SORTED) {
+            if (slot != 0xFFFFFFFFu) {
+                const float4* src = (ext ? extRays : shadowRays) + RAY_STRIDE * (size_t)slot;
+                cpAsync16(myStage + lane * 32u, src);
+                cpAsync16(myStage + lane * 32u + 16u, src + 1);
+            }
+            cpAsyncCommit();
+        } else if (lane == 0) {
+            const uint32_t first = ext ? b : b - live32, n = ext ? nLive : nShadow;
+            const uint32_t count = n - first < 32u ? n - first : 32u;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the stage was last read through the generic proxy
+            mbarExpectTx(myBar, count * 32u);
+            bulkCopyG2S(myStage, (ext ? extRays : shadowRays) + RAY_STRIDE * (size_t)first, count * 32u, myBar);
+        }
+    };
+    // software pipeline: ticket k is traversed while ticket k+1's rays are in flight to shared memory and (SORTED) ticket k+2's
+    // permutation entries are in flight to a register
+    uint32_t base = grab();
+    uint32_t baseNext = base < total ? grab() : total;
+    uint32_t perm = permLoad(base + lane), permNext = permLoad(baseNext + lane);
+    stageTicket(base, slotOf(base + lane, perm));
+    while (base < total) {
+        const uint32_t baseAfter = baseNext < total ? grab() : total;
+        const uint32_t permAfter = permLoad(baseAfter + lane);
+        const uint32_t idx = slotOf(base + lane, perm);
+        const bool ext = base < live32;
+        // this ticket's rays have landed
+        if (SORTED) cpAsyncWaitAll(); else { mbarWait(myBar, parity); parity ^= 1u; }
+        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+        if (idx != 0xFFFFFFFFu) { r0 = stage[warp][2 * lane]; r1 = stage[warp][2 * lane + 1]; }
+        __syncwarp();
+        stageTicket(baseNext, slotOf(baseNext + lane, permNext));
+#else
+    {
+    uint32_t base = 0, baseNext = 0, perm = 0, permNext = 0;
     for (;;) {
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(ws.traceTicket, 32u);
-        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        base = grab();
         if (base >= total) break;
-        uint32_t idx = base + lane;
-        if (SORTED) idx = idx < nLive ? __ldg(permExt + idx) : (idx < total ? nLive + __ldg(permShadow + (idx - nLive)) : 0xFFFFFFFFu);
+        perm = permLoad(base + lane);
+        const uint32_t idx = slotOf(base + lane, perm);
+        const bool ext = base < live32;
+        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+        if (idx != 0xFFFFFFFFu) {
+            const float4* src = (ext ? extRays : shadowRays) + RAY_STRIDE * (size_t)idx;
+            r0 = qld(src); r1 = qld(src + 1);
+        }
+        const uint32_t baseAfter = 0, permAfter = 0;
+#endif
         uint32_t bin = 0xFFu;
-        if (idx < nLive) {
-            const float4 r0 = qld(pb.R0[buf] + RAY_STRIDE * (size_t)idx), r1 = qld(pb.R1[buf] + RAY_STRIDE * (size_t)idx);
+        if (idx != 0xFFFFFFFFu) {
             HitRec h;
-            traceRay<false, TWO_LEVEL>(sc, mk3(r0.x, r0.y, r0.z), mk3(r1.x, r1.y, r1.z), 0.0f, MS_INFINITY, h, smemTop);
-            bin = hitBin(sc, h);
-            // the material bin rides in the top bits of the triangle index (H_TRI_MASK, dtypes.h): k_bin reads it back without
-            // repeating the instance -> geometry -> material chain
-            qst(pb.H + idx, make_uint4(h.inst, h.tri | (bin << H_BIN_SHIFT), __float_as_uint(h.u), __float_as_uint(h.v)));
-        } else if (idx < total) {
-            const float4 q0 = qld(pb.Q0 + RAY_STRIDE * (size_t)(idx - nLive)), q1 = qld(pb.Q1 + RAY_STRIDE * (size_t)(idx - nLive));
-            HitRec h;
-            if (traceRay<true, TWO_LEVEL>(sc, mk3(q0.x, q0.y, q0.z), mk3(q1.x, q1.y, q1.z), 0.0f, q0.w, h, smemTop)) {
-                const uint32_t target = __float_as_uint(q1.w);
+            if (ext) {
+                traceRay<false, TWO_LEVEL>(sc, mk3(r0.x, r0.y, r0.z), mk3(r1.x, r1.y, r1.z), 0.0f, MS_INFINITY, h);
+                bin = hitBin(sc, h);
+                // the material bin rides in the top bits of the triangle index (H_TRI_MASK, dtypes.h): k_bin reads it back without
+                // repeating the instance -> geometry -> material chain
+                qst(pb.H + idx, make_uint4(h.inst, h.tri | (bin << H_BIN_SHIFT), __float_as_uint(h.u), __float_as_uint(h.v)));
+            } else if (traceRay<true, TWO_LEVEL>(sc, mk3(r0.x, r0.y, r0.z), mk3(r1.x, r1.y, r1.z), 0.0f, r0.w, h)) {
+                const uint32_t target = __float_as_uint(r1.w);
                 float4* n = (target & 1u) ? pb.N1[buf] : pb.N0[buf];
                 n[target >> 1] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
         // ---- warp-level sort by material id: lanes with the same bin elect a leader that reserves their slots
-        if (SORTED) continue;
-        const uint32_t peers = __match_any_sync(0xFFFFFFFFu, bin);
-        if (bin != 0xFFu) {
-            const int leader = __ffs(peers) - 1;
-            uint32_t slot = 0;
-            if ((int)lane == leader) slot = atomicAdd(ws.typeCount + bin, (uint32_t)__popc(peers));
-            slot = __shfl_sync(peers, slot, leader) + __popc(peers & ltMask);
-            qst(pb.typeList + ((size_t)bin * pb.capacity + slot), idx);
+        if (!SORTED) {
+            const uint32_t peers = __match_any_sync(0xFFFFFFFFu, bin);
+            if (bin != 0xFFu) {
+                const int leader = __ffs(peers) - 1;
+                uint32_t slot = 0;
+                if ((int)lane == leader) slot = atomicAdd(ws.typeCount + bin, (uint32_t)__popc(peers));
+                slot = __shfl_sync(peers, slot, leader) + __popc(peers & ltMask);
+                qst(pb.typeList + ((size_t)bin * pb.capacity + slot), idx);
+            }
         }
+        base = baseNext; baseNext = baseAfter; perm = permNext; permNext = permAfter;
     }
+#if !MSNE_TRACE_STAGING
+    }
+#endif
     // last block out: re-arm the ticket for the next launch and publish ray counts
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -213,7 +293,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TWO_LEVEL ? TRACE_BLOCKS_PER_SM
         const uint32_t done = atomicAdd(ws.traceDone, 1u);
         if (done == gridDim.x - 1) {
             *ws.traceTicket = 0; *ws.traceDone = 0;
-            ws.rayCounts[0] += nLive; ws.rayCounts[1] += cin.nShadow;
+            ws.rayCounts[0] += nLive; ws.rayCounts[1] += nShadow;
             __threadfence();
         }
     }
@@ -1012,14 +1092,7 @@ void launchGenerate(cudaStream_t st, const DCamera& cam, const DConstants& k, co
     k_generate<<<grid1((uint64_t)nPix * nSamples, 256), 256, 0, st>>>(cam, k, pb, counters, pixIds, nPix, nSamples, firstSample);
 }
 void launchTrace(cudaStream_t st, int blocks, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf) {
-#if MSNE_TRACE_SMEM_NODES > 0
-    static const size_t smemBytes = MSNE_TRACE_SMEM_NODES * sizeof(BvhNode2) + 16;
-    static const cudaError_t attr = cudaFuncSetAttribute(k_trace<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
-    (void)attr;
-    if (sc.staticOnly) k_trace<false, false><<<blocks, TRACE_THREADS, smemBytes, st>>>(sc, pb, ws, buf, nullptr, nullptr);
-#else
     if (sc.staticOnly) k_trace<false, false><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf, nullptr, nullptr);
-#endif
     else k_trace<true, false><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf, nullptr, nullptr);
 }
 // sorted bounce: counting sort of the keys the previous shade pass wrote (extension and shadow queue in one set of launches,
@@ -1097,17 +1170,10 @@ void launchPrimaryProbe(cudaStream_t st, const DCamera& cam, const DConstants& k
     k_primary_probe<<<grid1((uint64_t)cam.width * cam.height, 256), 256, 0, st>>>(cam, k, sample, rays6, rngState);
 }
 int traceOccupancyBlocksPerSm() {
-    int n = 0;
+    int n = 0, n1 = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace<true, false>, TRACE_THREADS, 0);
-    int n1 = 0;
-#if MSNE_TRACE_SMEM_NODES > 0
-    cudaFuncSetAttribute(k_trace<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MSNE_TRACE_SMEM_NODES * sizeof(BvhNode2) + 16));
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, k_trace<false, false>, TRACE_THREADS, MSNE_TRACE_SMEM_NODES * sizeof(BvhNode2) + 16);
-#else
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n1, k_trace<false, false>, TRACE_THREADS, 0);
-#endif
-    n = n > n1 ? n : n1;
-    return n;
+    return n > n1 ? n : n1;
 }
 int shadeOccupancyBlocksPerSm() {
     int n = 0;

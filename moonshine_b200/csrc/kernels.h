@@ -14,12 +14,6 @@ namespace msne {
 #ifndef TRACE1_BLOCKS_PER_SM
 #define TRACE1_BLOCKS_PER_SM 9  // single-level specialisation (no transformed instances): 56 registers, measured best of 8/9/10
 #endif
-// Experiment (profiles/r01_sweeps.md "TMA-staged top of the tree"): k_trace<false> copies the first N nodes of the static BLAS
-// (BFS order, bvh_build.cpp reorderTopBfs) into shared memory with one cp.async.bulk per block and walks them from there.
-// 0 = off (default: the top of the tree is L1-resident anyway and shared memory is carved out of the same SRAM).
-#ifndef MSNE_TRACE_SMEM_NODES
-#define MSNE_TRACE_SMEM_NODES 0
-#endif
 // Entries of the per-ray traversal stack (traverse.cuh): one per tree level (the far child) + the REF_END / REF_LEAVE sentinels.
 // runtime.cpp holds depth(TLAS) + depth(BLAS) + 2 below it at build time.
 #ifndef MSNE_STACK

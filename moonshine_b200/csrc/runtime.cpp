@@ -495,7 +495,6 @@ struct HdMoonshine {
     // (1) BLAS level: merged static BLAS over every visible identity-transform instance + one shared BLAS per mesh-key
     //     of the transformed instances. Only needed when that set changes (Accel.zig:94-184 equivalent).
     DInstance staticRec{};
-    uint32_t staticTop = 0;
     bool haveStatic = false;
     BuildBox staticBounds{};
     uint64_t stats_static_builds = 0, stats_tlas_builds = 0, stats_tlas_refits = 0;
@@ -522,11 +521,6 @@ struct HdMoonshine {
             BuiltBvh bvh;
             buildDepthLimited(stBoxes, maxLeaf, kMaxBlasDepth, bvh);
             maxBlasDepth = std::max(maxBlasDepth, bvh.depth);
-            staticTop = 0;
-#if MSNE_TRACE_SMEM_NODES > 0
-            reorderTopBfs(bvh, MSNE_TRACE_SMEM_NODES);
-            staticTop = (uint32_t)std::min<size_t>(MSNE_TRACE_SMEM_NODES, bvh.nodes.size());
-#endif
             staticRec.blasRoot = appendBlas(bvh, stTris);
             staticBounds = bvh.bounds;
         }
@@ -779,7 +773,6 @@ struct HdMoonshine {
         sc.texLuts = dSrgbLut.p;
         sc.staticOnly = (tlasStaticOnly && !forceTwoLevel) ? 1u : 0u; sc.staticRoot = staticRec.blasRoot;
         sc.staticHidden = hiddenStaticTris ? 1u : 0u;
-        sc.staticTop = haveStatic ? staticTop : 0u;
         return sc;
     }
     DConstants deviceConstants() const {

@@ -30,7 +30,7 @@ struct HitRec { uint32_t inst, tri; float u, v; };
 
 struct SpaceRay {
     float3 o, d, idir, ood;
-    float rdd;
+    float rdd, eps;
     DI void set(float3 o_, float3 d_) {
         o = o_; d = d_;
         idir.x = fabsf(d.x) > 1e-20f ? 1.0f / d.x : copysignf(1e20f, d.x);
@@ -38,6 +38,12 @@ struct SpaceRay {
         idir.z = fabsf(d.z) > 1e-20f ? 1.0f / d.z : copysignf(1e20f, d.z);
         ood = mk3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
         rdd = 1.0f / dot(d, d);
+        // The slab distances are lo * idir - ood: their ABSOLUTE error is a few ulp of |ood| = |o / d| (the two products cancel), which
+        // for a ray that starts far from the box, or runs nearly parallel to a slab, exceeds any fixed padding of the box. The
+        // triangle test has no such cancellation (vertices are translated by o first) and accepts rays within a few ulp of |o| of an
+        // edge. eps (16 ulp of the largest |ood|) widens the slab comparison by both, so a box is never skipped that holds a
+        // triangle the exact-as-written triangle test would accept: traversal finds what testing every triangle would find.
+        eps = 1e-6f * fmaxf(fmaxf(fabsf(ood.x), fabsf(ood.y)), fabsf(ood.z));
     }
 };
 
@@ -48,7 +54,7 @@ DI bool slab(const SpaceRay& r, float lox, float hix, float loy, float hiy, floa
     const float tz0 = fmaf(loz, r.idir.z, -r.ood.z), tz1 = fmaf(hiz, r.idir.z, -r.ood.z);
     tnear = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), tmin));
     const float tfar = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), tmax));
-    return tnear <= tfar * 1.0000004f;
+    return tnear <= fmaf(tfar, 1.0000004f, r.eps);
 }
 
 DI bool triTest(const float4 t0, const float4 t1, const float4 t2, const SpaceRay& r, float tmin, float tmax, float& t, float& u, float& v) {
@@ -67,10 +73,8 @@ DI bool triTest(const float4 t0, const float4 t1, const float4 t2, const SpaceRa
     return tmin < t && t < tmax;
 }
 
-// `smemTop` (MSNE_TRACE_SMEM_NODES experiment, single-level only): generic pointer to a shared-memory copy of the first
-// sc.staticTop nodes from sc.staticRoot, or nullptr.
 template <bool ANY_HIT, bool TWO_LEVEL>
-DI bool traceRay(const DeviceScene& sc, const float3 o, const float3 d, const float tmin, const float tmax, HitRec& hit, const BvhNode2* smemTop = nullptr) {
+DI bool traceRay(const DeviceScene& sc, const float3 o, const float3 d, const float tmin, const float tmax, HitRec& hit) {
     hit.inst = MISS_ID; hit.tri = 0; hit.u = 0.0f; hit.v = 0.0f;
     if (sc.tlasNodes == nullptr) return false;
     float bestT = tmax;
@@ -84,22 +88,9 @@ DI bool traceRay(const DeviceScene& sc, const float3 o, const float3 d, const fl
     while (node != REF_END) {
         // ---- inner nodes: descend until a leaf (or a TLAS item / sentinel) comes up ------------------------------
         while ((uint32_t)node < (uint32_t)REF_ITEM) {
-#if MSNE_TRACE_SMEM_NODES > 0
-            float4 n0, n1, n2; int2 c;
-            if (!TWO_LEVEL) {
-                // one generic load path: the pointer selects the shared-memory copy for the top of the tree
-                const uint32_t rel = (uint32_t)node - sc.staticRoot;
-                const float4* np = reinterpret_cast<const float4*>(rel < sc.staticTop ? smemTop + rel : nodes + node);
-                n0 = np[0]; n1 = np[1]; n2 = np[2]; c = *reinterpret_cast<const int2*>(np + 3);
-            } else {
-                const float4* np = reinterpret_cast<const float4*>(nodes + node);
-                n0 = __ldg(np); n1 = __ldg(np + 1); n2 = __ldg(np + 2); c = __ldg(reinterpret_cast<const int2*>(np + 3));
-            }
-#else
             const float4* np = reinterpret_cast<const float4*>(nodes + node);
             const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
             const int2 c = __ldg(reinterpret_cast<const int2*>(np + 3));
-#endif
             float tn0, tn1;
             const bool h0 = slab(ray, n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, tmin, bestT, tn0);   // an empty child's box is unreachable (dtypes.h)
             const bool h1 = slab(ray, n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, tmin, bestT, tn1);

@@ -46,8 +46,12 @@ def lib():
         L.OracleBuildEmitterTable.argtypes = [C.c_void_p]
         L.OracleSetConstants.argtypes = [C.c_void_p] + [C.c_uint32] * 4 + [C.c_int] * 3
         L.OracleSetBruteForce.argtypes = [C.c_void_p, C.c_int]
+        L.OracleSetCrossCheck.argtypes = [C.c_void_p, C.c_int]
+        L.OracleCrossCheckMismatches.restype = C.c_uint64
+        L.OracleCrossCheckMismatches.argtypes = [C.c_void_p]
         L.OracleRender.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p]
         L.OracleRenderDiag.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.OracleRenderPixels.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.OracleEnvProbe.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p]
         L.OracleBsdfBatch.argtypes = [C.c_size_t, C.c_void_p, C.c_void_p]
         L.OracleMathProbe.argtypes = [C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -165,6 +169,21 @@ class Oracle:
         self.L.OracleSetBruteForce(self.h, 0)
         self.L.OracleRenderDiag(self.h, _p(la), width, height, _p(image), sample_count, n_launches, threads, pixel_stride, _p(counts), _p(min_alpha))
         return image, counts, min_alpha
+
+    def render_pixels(self, lens, width, height, xy, sample_count=0, brute=False, threads=0):
+        """One launch of the listed pixels (n x {x, y}) -> n x RGBA; brute = no BVH (every triangle tested)."""
+        p = np.ascontiguousarray(xy, np.uint32).reshape(-1, 2)
+        out = np.zeros((len(p), 4), np.float32)
+        la = lens.as_array()
+        self.L.OracleRenderPixels(self.h, _p(la), width, height, sample_count, len(p), _p(p), _p(out), int(brute), threads)
+        return out
+
+    def set_cross_check(self, on=True):
+        """Diagnostics: every ray query is answered by the BVH walk and by testing all triangles; mismatches are counted."""
+        self.L.OracleSetCrossCheck(self.h, int(on))
+
+    def cross_check_mismatches(self):
+        return int(self.L.OracleCrossCheckMismatches(self.h))
 
     def env_probe(self, op, inputs3):
         """EnvMap::sample (op 0, rand in columns 0-1), ::eval (op 1, direction), ::incomingRadiance (op 2) -> (n, 7)."""

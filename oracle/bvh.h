@@ -28,6 +28,8 @@
 // The BVH itself (median split, float boxes padded outward) only has to be conservative; a
 // brute-force path (`brute=true`) bypasses it so tests can check that it is.
 #pragma once
+#include <atomic>
+#include <cstdio>
 #include <algorithm>
 #include <limits>
 #include "scene.h"
@@ -98,9 +100,15 @@ struct Bvh {
     }
 };
 
-// conservative slab test evaluated in double precision
+// Conservative slab test evaluated in double precision. The boxes bound the triangles geometrically, but the FP32 triangle test
+// (tri_test, the definition of a hit) accepts rays within a few ulp of |o| of an edge and reports t with a few ulp of error, so
+// the comparison is widened relatively (1e-6) and absolutely (1e-6 of the largest |o / d|, the scale of those errors in t):
+// the walk then returns exactly what testing every triangle returns (`brute`), which is what "closest hit" means here.
 inline bool ray_box(const AABB& b, const double o[3], const double inv[3], double tmax) {
     double t0 = 0.0, t1 = tmax;
+    double eps = 0.0;
+    for (int a = 0; a < 3; a++) { const double m = std::fabs(o[a] * inv[a]); if (m == m && m < 1e300 && m > eps) eps = m; }
+    eps *= 1e-6;
     const float lo[3] = {b.lo.x, b.lo.y, b.lo.z}, hi[3] = {b.hi.x, b.hi.y, b.hi.z};
     for (int a = 0; a < 3; a++) {
         double ta = (lo[a] - o[a]) * inv[a], tb = (hi[a] - o[a]) * inv[a];
@@ -108,7 +116,7 @@ inline bool ray_box(const AABB& b, const double o[3], const double inv[3], doubl
         if (ta > tb) std::swap(ta, tb);
         t0 = std::max(t0, ta); t1 = std::min(t1, tb);
     }
-    return t0 <= t1 * 1.0000001 + 1e-30;
+    return t0 <= t1 * 1.000001 + eps + 1e-30;
 }
 
 struct Blas {
@@ -165,8 +173,21 @@ struct Accel {
         tlas.build(boxes, 1);
     }
 
-    // closest hit when anyHit==false; returns true/false occlusion in its.instanceIndex!=MAX when anyHit
+    // diagnostic: every query is answered by the walk AND by testing every triangle; disagreements are counted and the first few printed
+    mutable std::atomic<uint64_t> crossCheckMismatches{0};
+    bool crossCheck = false;
     Intersection trace(float3 o, float3 d, float tmin, float tmax, bool anyHit, bool brute) const {
+        if (!crossCheck) return traceImpl(o, d, tmin, tmax, anyHit, brute);
+        const Intersection a = traceImpl(o, d, tmin, tmax, anyHit, false), b = traceImpl(o, d, tmin, tmax, anyHit, true);
+        const bool same = anyHit ? (a.instanceIndex != MAX_UINT) == (b.instanceIndex != MAX_UINT)
+                                 : (a.instanceIndex == b.instanceIndex && (a.instanceIndex == MAX_UINT || (a.geometryIndex == b.geometryIndex && a.primitiveIndex == b.primitiveIndex)));
+        if (!same && crossCheckMismatches.fetch_add(1) < 8)
+            fprintf(stderr, "oracle cross-check: %s ray o=(%.9g %.9g %.9g) d=(%.9g %.9g %.9g) tmax=%.9g  walk -> inst %u geom %u prim %u | all triangles -> inst %u geom %u prim %u\n",
+                    anyHit ? "any-hit" : "closest", o.x, o.y, o.z, d.x, d.y, d.z, tmax, a.instanceIndex, a.geometryIndex, a.primitiveIndex, b.instanceIndex, b.geometryIndex, b.primitiveIndex);
+        return b;
+    }
+    // closest hit when anyHit==false; returns true/false occlusion in its.instanceIndex!=MAX when anyHit
+    Intersection traceImpl(float3 o, float3 d, float tmin, float tmax, bool anyHit, bool brute) const {
         Intersection best; best.instanceIndex = MAX_UINT; best.geometryIndex = best.primitiveIndex = 0; best.barycentrics = {0, 0};
         float bestT = tmax;
         auto consider = [&](uint32_t inst, const Tri& tr, float3 oo, float3 od) -> bool {

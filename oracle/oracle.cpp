@@ -132,6 +132,9 @@ void OracleSetConstants(Oracle* o, uint32_t spr, uint32_t max_bounces, uint32_t 
     o->sc.consts = {spr, max_bounces, env, mesh, flip != 0, indexed != 0, two_comp != 0};
 }
 void OracleSetBruteForce(Oracle* o, int brute) { o->sc.brute = brute != 0; }
+// diagnostics: answer every query both ways (BVH walk and all triangles), count disagreements
+void OracleSetCrossCheck(Oracle* o, int on) { o->sc.accel.crossCheck = on != 0; o->sc.accel.crossCheckMismatches = 0; }
+uint64_t OracleCrossCheckMismatches(Oracle* o) { return o->sc.accel.crossCheckMismatches.load(); }
 
 // Runs `n_launches` consecutive raygen launches (offline/main.zig:131-165 loop) over the pixels
 // [y0,y1) x [0,W) with `stride`-interleaved pixel subsampling (stride 1 = every pixel) on `threads`
@@ -174,6 +177,33 @@ void OracleRenderDiag(Oracle* o, const float* lens12, uint32_t W, uint32_t H, fl
     work();
     for (auto& t : pool) t.join();
     if (counts) { counts[0] += nc; counts[1] += ns; }
+}
+
+// One launch (sample index `sample_count`) of a LIST of pixels: xy = n x {x, y}, out = n x RGBA. `brute` = 1 intersects every
+// triangle of every instance instead of walking the BVHs (diagnostics: tells a traversal problem from a shading one).
+void OracleRenderPixels(Oracle* o, const float* lens12, uint32_t W, uint32_t H, uint32_t sample_count, size_t n, const uint32_t* xy, float* out, int brute, int threads) {
+    if (o->dirty) commit(o);
+    Lens lens; std::memcpy(&lens, lens12, 48);
+    if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+    SceneData& sc = o->sc;
+    const bool saved = sc.brute;
+    sc.brute = brute != 0;
+    std::atomic<size_t> next{0};
+    auto work = [&]() {
+        TraceCounters tc;
+        for (;;) {
+            const size_t i = next.fetch_add(1);
+            if (i >= n) break;
+            float texel[4] = {0, 0, 0, 0};
+            raygenPixel(sc, tc, lens, W, H, xy[2 * i], xy[2 * i + 1], sample_count, texel);
+            std::memcpy(out + 4 * i, texel, 16);
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; t++) pool.emplace_back(work);
+    work();
+    for (auto& t : pool) t.join();
+    sc.brute = saved;
 }
 
 // ---- per-function entry points for known-answer / stage tests ---------------------------
