@@ -223,14 +223,19 @@ __global__ void __launch_bounds__(TRACE_THREADS, TWO_LEVEL ? TRACE_BLOCKS_PER_SM
         }
     };
     // software pipeline: ticket k is traversed while ticket k+1's rays are in flight to shared memory and (SORTED) ticket k+2's
-    // permutation entries are in flight to a register
-    uint32_t base = grab();
-    uint32_t baseNext = base < total ? grab() : total;
-    uint32_t perm = permLoad(base + lane), permNext = permLoad(baseNext + lane);
-    stageTicket(base, slotOf(base + lane, perm));
+    // permutation entries are in flight to a register. Holding tickets ahead costs load balance at the end of a queue (a warp
+    // then works through its two or three tickets while others idle), so a warp only grabs ahead while every warp of the grid
+    // still has several tickets to come; short queues and queue ends run one ticket at a time.
+    constexpr uint32_t NONE = 0xFFFFFFFEu;
+    const uint32_t margin = gridDim.x * (TRACE_THREADS / 32u) * 32u * 4u;
+    uint32_t base = grab(), perm = permLoad(base + lane);
+    bool staged = false;
+    uint32_t baseNext = NONE, permNext = 0, baseAfter = NONE, permAfter = 0;
     while (base < total) {
-        const uint32_t baseAfter = baseNext < total ? grab() : total;
-        const uint32_t permAfter = permLoad(baseAfter + lane);
+        const bool ahead = base + margin < total && base + margin > base;
+        if (!staged) stageTicket(base, slotOf(base + lane, perm));
+        if (ahead && baseNext == NONE) { baseNext = grab(); permNext = permLoad(baseNext + lane); }
+        if (SORTED && ahead && baseAfter == NONE) { baseAfter = grab(); permAfter = permLoad(baseAfter + lane); }
         const uint32_t idx = slotOf(base + lane, perm);
         const bool ext = base < live32;
         // this ticket's rays have landed
@@ -238,10 +243,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, TWO_LEVEL ? TRACE_BLOCKS_PER_SM
         float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
         if (idx != 0xFFFFFFFFu) { r0 = stage[warp][2 * lane]; r1 = stage[warp][2 * lane + 1]; }
         __syncwarp();
-        stageTicket(baseNext, slotOf(baseNext + lane, permNext));
+        bool nextStaged = false;
+        if (baseNext != NONE && baseNext < total) { stageTicket(baseNext, slotOf(baseNext + lane, permNext)); nextStaged = true; }
 #else
     {
-    uint32_t base = 0, baseNext = 0, perm = 0, permNext = 0;
+    uint32_t base = 0, perm = 0;
     for (;;) {
         base = grab();
         if (base >= total) break;
@@ -253,7 +259,6 @@ __global__ void __launch_bounds__(TRACE_THREADS, TWO_LEVEL ? TRACE_BLOCKS_PER_SM
             const float4* src = (ext ? extRays : shadowRays) + RAY_STRIDE * (size_t)idx;
             r0 = qld(src); r1 = qld(src + 1);
         }
-        const uint32_t baseAfter = 0, permAfter = 0;
 #endif
         uint32_t bin = 0xFFu;
         if (idx != 0xFFFFFFFFu) {
@@ -281,9 +286,12 @@ __global__ void __launch_bounds__(TRACE_THREADS, TWO_LEVEL ? TRACE_BLOCKS_PER_SM
                 qst(pb.typeList + ((size_t)bin * pb.capacity + slot), idx);
             }
         }
-        base = baseNext; baseNext = baseAfter; perm = permNext; permNext = permAfter;
+#if MSNE_TRACE_STAGING
+        if (baseNext != NONE) { base = baseNext; perm = permNext; staged = nextStaged; baseNext = baseAfter; permNext = permAfter; baseAfter = NONE; }
+        else { base = grab(); perm = permLoad(base + lane); staged = false; }
     }
-#if !MSNE_TRACE_STAGING
+#else
+    }
     }
 #endif
     // last block out: re-arm the ticket for the next launch and publish ray counts

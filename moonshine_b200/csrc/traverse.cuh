@@ -5,7 +5,8 @@
 // reference behaviour and is stated in DESIGN.md §"Intersection"; the CPU oracle implements the same
 // definition independently (oracle/bvh.h):
 //   object-space ray   o' = mulPoint(w2o, o), d' = mulVec(w2o, d)   (t shared between spaces)
-//   A=v0-o, B=v1-o, C=v2-o;  U=dot(d,cross(C,B)), V=dot(d,cross(A,C)), W=dot(d,cross(B,A))
+//   A=v0-o, B=v1-o, C=v2-o;  U=dot(d,cross(C,B)), V=dot(d,cross(A,C)), W=dot(d,cross(B,A)), each with a rounding-error bound;
+//   any |value| <= its bound -> all three (and u, v, t) are recomputed in binary64 (exact products): signs are the EXACT signs
 //   miss if mixed signs; det=(U+V)+W, det==0 -> miss; rdet=1/det; u=V*rdet; v=W*rdet
 //   T=(U*dot(A,d)+V*dot(B,d))+W*dot(C,d);  t=(T*rdet)*(1/dot(d,d));  hit iff tmin<t<tmax
 //   closest = min t, ties -> smallest (instance, geometry, primitive); no culling; mask 0 skipped.
@@ -43,7 +44,7 @@ struct SpaceRay {
         // triangle test has no such cancellation (vertices are translated by o first) and accepts rays within a few ulp of |o| of an
         // edge. eps (16 ulp of the largest |ood|) widens the slab comparison by both, so a box is never skipped that holds a
         // triangle the exact-as-written triangle test would accept: traversal finds what testing every triangle would find.
-        eps = 1e-6f * fmaxf(fmaxf(fabsf(ood.x), fabsf(ood.y)), fabsf(ood.z));
+        eps = 4e-7f * fmaxf(fmaxf(fabsf(ood.x), fabsf(ood.y)), fabsf(ood.z));
     }
 };
 
@@ -57,20 +58,58 @@ DI bool slab(const SpaceRay& r, float lox, float hix, float loy, float hiy, floa
     return tnear <= fmaf(tfar, 1.0000004f, r.eps);
 }
 
+// Edge function d . (P x Q) in binary32 with a bound of its rounding error (8 * 2^-24 times the sum of the magnitudes of its six
+// products): when |value| > bound, the sign is that of the exact value.
+DI float edgeFn(const float3 d, const float3 P, const float3 Q, float& bound) {
+    const float px = P.y * Q.z, qx = P.z * Q.y, py = P.z * Q.x, qy = P.x * Q.z, pz = P.x * Q.y, qz = P.y * Q.x;
+    const float cx = px - qx, cy = py - qy, cz = pz - qz;
+    const float tx = d.x * cx, ty = d.y * cy, tz = d.z * cz;
+    const float mag = (fabsf(d.x) * (fabsf(px) + fabsf(qx)) + fabsf(d.y) * (fabsf(py) + fabsf(qy))) + fabsf(d.z) * (fabsf(pz) + fabsf(qz));
+    bound = mag * 4.7683716e-07f;
+    return (tx + ty) + tz;
+}
+DI double edgeFnExact(const float3 d, const float3 P, const float3 Q) {
+    const double cx = (double)P.y * (double)Q.z - (double)P.z * (double)Q.y;
+    const double cy = (double)P.z * (double)Q.x - (double)P.x * (double)Q.z;
+    const double cz = (double)P.x * (double)Q.y - (double)P.y * (double)Q.x;
+    return ((double)d.x * cx + (double)d.y * cy) + (double)d.z * cz;
+}
+DI double dotExact(const float3 a, const float3 b) { return ((double)a.x * (double)b.x + (double)a.y * (double)b.y) + (double)a.z * (double)b.z; }
+// The rare path of triTest (a few per cent of the tests): the ray grazes the triangle's plane or passes within rounding distance of
+// an edge, so binary32 cannot tell the signs of the edge functions. In binary64 every product of two binary32 numbers is exact
+// and the sums are good to 1e-15: the decision is the exact one. Out of line: it must not cost the traversal loop registers.
+// Returns (t, u, v, hit ? 1 : 0) in registers.
+__device__ __noinline__ float4 triTestExact(const float3 A, const float3 B, const float3 C, const float3 d) {
+    const double Ud = edgeFnExact(d, C, B), Vd = edgeFnExact(d, A, C), Wd = edgeFnExact(d, B, A);
+    if ((Ud < 0.0 || Vd < 0.0 || Wd < 0.0) && (Ud > 0.0 || Vd > 0.0 || Wd > 0.0)) return make_float4(0.f, 0.f, 0.f, 0.f);
+    const double det = (Ud + Vd) + Wd;
+    if (det == 0.0) return make_float4(0.f, 0.f, 0.f, 0.f);
+    const double T = (Ud * dotExact(A, d) + Vd * dotExact(B, d)) + Wd * dotExact(C, d);
+    return make_float4((float)((T / det) / dotExact(d, d)), (float)(Vd / det), (float)(Wd / det), 1.0f);
+}
+// A triangle is hit iff the ray passes through the translated triangle (A, B, C = v - o rounded to binary32) EXACTLY: the signs of
+// the three edge functions are certified in binary32 or decided in binary64. No ray can slip between two triangles that share an
+// edge (X x Y = -(Y x X) holds exactly in both precisions), and none is accepted by a triangle it does not pass through - so
+// walking any conservative BVH finds exactly what testing every triangle would find (oracle/bvh.h states the same test).
 DI bool triTest(const float4 t0, const float4 t1, const float4 t2, const SpaceRay& r, float tmin, float tmax, float& t, float& u, float& v) {
     const float3 A = mk3(t0.x, t0.y, t0.z) - r.o, B = mk3(t1.x, t1.y, t1.z) - r.o, C = mk3(t2.x, t2.y, t2.z) - r.o;
-    const float U = dot(r.d, cross(C, B));
-    const float V = dot(r.d, cross(A, C));
-    const float W = dot(r.d, cross(B, A));
-    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
-    const float det = (U + V) + W;
-    if (det == 0.0f) return false;
-    const float rdet = 1.0f / det;
-    u = V * rdet;
-    v = W * rdet;
-    const float T = (U * dot(A, r.d) + V * dot(B, r.d)) + W * dot(C, r.d);
-    t = (T * rdet) * r.rdd;
-    return tmin < t && t < tmax;
+    float eU, eV, eW;
+    const float U = edgeFn(r.d, C, B, eU);
+    const float V = edgeFn(r.d, A, C, eV);
+    const float W = edgeFn(r.d, B, A, eW);
+    if (fabsf(U) > eU && fabsf(V) > eV && fabsf(W) > eW) {
+        if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+        const float det = (U + V) + W;
+        const float rdet = 1.0f / det;
+        u = V * rdet;
+        v = W * rdet;
+        const float T = (U * dot(A, r.d) + V * dot(B, r.d)) + W * dot(C, r.d);
+        t = (T * rdet) * r.rdd;
+        return tmin < t && t < tmax;
+    }
+    const float4 e = triTestExact(A, B, C, r.d);
+    t = e.x; u = e.y; v = e.z;
+    return e.w != 0.0f && tmin < t && t < tmax;
 }
 
 template <bool ANY_HIT, bool TWO_LEVEL>

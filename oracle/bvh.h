@@ -124,19 +124,52 @@ struct Blas {
     Bvh bvh;
 };
 
+// Edge functions U = d.(C x B), V = d.(A x C), W = d.(B x A) of the translated triangle (A, B, C = v - o, rounded to binary32: that
+// IS the triangle the ray is tested against). Each is evaluated in binary32 together with a bound of its rounding error (a few
+// ulp of the sum of the magnitudes of its six products). When all three are further from zero than their bounds, their signs are
+// those of the exact values and the binary32 results are used. Otherwise - the ray grazes the triangle's plane or passes within
+// rounding distance of an edge - the three are re-evaluated in binary64, where every product of two binary32 numbers is exact and
+// the sums are good to 1e-15: the decision is then the exact one. Hence a triangle is accepted only if the ray really passes
+// through it, whichever boxes led to it: walking any conservative BVH returns what testing every triangle returns.
+inline float edgeFn(float3 d, float3 P, float3 Q, float& bound) {   // d . (P x Q), bound >= its rounding error
+    const float px = P.y * Q.z, qx = P.z * Q.y, py = P.z * Q.x, qy = P.x * Q.z, pz = P.x * Q.y, qz = P.y * Q.x;
+    const float cx = px - qx, cy = py - qy, cz = pz - qz;
+    const float tx = d.x * cx, ty = d.y * cy, tz = d.z * cz;
+    const float mag = (std::fabs(d.x) * (std::fabs(px) + std::fabs(qx)) + std::fabs(d.y) * (std::fabs(py) + std::fabs(qy))) + std::fabs(d.z) * (std::fabs(pz) + std::fabs(qz));
+    bound = mag * 4.7683716e-07f;   // 8 * 2^-24: products, differences, the dot's products and its two sums
+    return (tx + ty) + tz;
+}
+inline double edgeFnExact(float3 d, float3 P, float3 Q) {
+    const double cx = (double)P.y * (double)Q.z - (double)P.z * (double)Q.y;
+    const double cy = (double)P.z * (double)Q.x - (double)P.x * (double)Q.z;
+    const double cz = (double)P.x * (double)Q.y - (double)P.y * (double)Q.x;
+    return ((double)d.x * cx + (double)d.y * cy) + (double)d.z * cz;
+}
 inline bool tri_test(const Tri& tr, float3 o, float3 d, float tmin, float tmax, float& t, float& u, float& v) {
     const float3 A = tr.v0 - o, B = tr.v1 - o, C = tr.v2 - o;
-    const float U = dot(d, cross(C, B));
-    const float V = dot(d, cross(A, C));
-    const float W = dot(d, cross(B, A));
-    if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
-    const float det = (U + V) + W;
-    if (det == 0.0f) return false;
-    const float rdet = 1.0f / det;
-    u = V * rdet;
-    v = W * rdet;
-    const float T = (U * dot(A, d) + V * dot(B, d)) + W * dot(C, d);
-    t = (T * rdet) * (1.0f / dot(d, d));
+    float eU, eV, eW;
+    const float U = edgeFn(d, C, B, eU);
+    const float V = edgeFn(d, A, C, eV);
+    const float W = edgeFn(d, B, A, eW);
+    if (std::fabs(U) > eU && std::fabs(V) > eV && std::fabs(W) > eW) {
+        if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+        const float det = (U + V) + W;
+        const float rdet = 1.0f / det;
+        u = V * rdet;
+        v = W * rdet;
+        const float T = (U * dot(A, d) + V * dot(B, d)) + W * dot(C, d);
+        t = (T * rdet) * (1.0f / dot(d, d));
+        return tmin < t && t < tmax;
+    }
+    const double Ud = edgeFnExact(d, C, B), Vd = edgeFnExact(d, A, C), Wd = edgeFnExact(d, B, A);
+    if ((Ud < 0.0 || Vd < 0.0 || Wd < 0.0) && (Ud > 0.0 || Vd > 0.0 || Wd > 0.0)) return false;
+    const double det = (Ud + Vd) + Wd;
+    if (det == 0.0) return false;
+    auto dotd = [](float3 a, float3 b) { return ((double)a.x * (double)b.x + (double)a.y * (double)b.y) + (double)a.z * (double)b.z; };
+    u = (float)(Vd / det);
+    v = (float)(Wd / det);
+    const double T = (Ud * dotd(A, d) + Vd * dotd(B, d)) + Wd * dotd(C, d);
+    t = (float)((T / det) / dotd(d, d));
     return tmin < t && t < tmax;
 }
 
