@@ -2,8 +2,10 @@
 #include "bvh_build.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
+#include <thread>
 
 namespace msne {
 
@@ -35,6 +37,161 @@ void setChildBox(BvhNode2& n, int slot, const Bounds& bIn) {
 
 }  // namespace
 
+namespace {
+
+struct Range { uint32_t first, count; int32_t node; uint32_t depth; };  // node whose two children are the split of this range
+
+struct BuildCtx {
+    const BuildBox* boxes;
+    const float* cent;
+    uint32_t* order;
+    uint32_t maxLeaf, maxSahDepth;
+};
+
+// Splits range `r` (binned SAH, median by index past maxSahDepth), fills the two child boxes of nodes[r.node] and either makes a
+// child a leaf or appends a new inner node to `nodes` and pushes its range on `work`. Touches only order[r.first, r.first + r.count).
+// runs fn(begin, end, slot) over [0, count) on up to `maxThreads` threads (slot < maxThreads identifies the caller's scratch)
+template <class F>
+void parallelChunks(uint32_t count, unsigned maxThreads, F fn) {
+    const unsigned nT = (unsigned)std::min<uint64_t>(maxThreads, (count + 65535u) / 65536u);
+    if (nT <= 1) { fn(0u, count, 0u); return; }
+    std::vector<std::thread> pool;
+    const uint32_t per = (count + nT - 1) / nT;
+    for (unsigned t = 0; t < nT; t++) {
+        const uint32_t b0 = std::min(count, t * per), e0 = std::min(count, b0 + per);
+        pool.emplace_back([=] { fn(b0, e0, t); });
+    }
+    for (auto& th : pool) th.join();
+}
+
+struct Bins { Bounds box[3][kBins]; uint32_t n[3][kBins]; Bounds cent; };
+
+// Splits range `r` (binned SAH over the three axes in one pass, median by index past maxSahDepth), fills the two child boxes of
+// nodes[r.node] and either makes a child a leaf or appends a new inner node to `nodes` and pushes its range on `work`. Touches only
+// order[r.first, r.first + r.count). `threads` > 1: the passes over the items of a big range run on that many threads (used for the
+// top of the tree); the result is the same for any thread count (min / max / counts are order-independent, the partition is stable
+// per chunk and chunks are concatenated in order... except that item order INSIDE the two halves may differ, which never changes
+// a split: bins and bounds depend on the set, not the order).
+void splitRange(const BuildCtx& c, const Range& r, std::vector<BvhNode2>& nodes, std::vector<Range>& work, unsigned threads = 1, std::vector<uint32_t>* scratch = nullptr) {
+    uint32_t* ord = c.order + r.first;
+    // centroid bounds
+    constexpr unsigned kMaxT = 16;
+    threads = std::min(threads, kMaxT);
+    Bounds cbT[kMaxT];
+    parallelChunks(r.count, threads, [&](uint32_t b0, uint32_t e0, unsigned t) {
+        Bounds cb; for (uint32_t i = b0; i < e0; i++) cb.growPoint(&c.cent[(size_t)ord[i] * 3]);
+        cbT[t] = cb;
+    });
+    Bounds cb;
+    for (unsigned t = 0; t < kMaxT; t++) if (cbT[t].lo[0] <= cbT[t].hi[0]) cb.grow(cbT[t].lo, cbT[t].hi);
+    int bestAxis = -1; int bestBin = -1; float bestCost = 1e38f;
+    Bounds bestL, bestR;
+    if (r.depth < c.maxSahDepth) {
+        float scale[3]; bool use[3];
+        for (int a = 0; a < 3; a++) { const float ext = cb.hi[a] - cb.lo[a]; use[a] = ext > 0.0f; scale[a] = use[a] ? (float)kBins / ext : 0.0f; }
+        std::vector<Bins> binsT(std::max(1u, threads));
+        for (Bins& bt : binsT) std::memset(bt.n, 0, sizeof(bt.n));
+        parallelChunks(r.count, threads, [&](uint32_t b0, uint32_t e0, unsigned t) {
+            Bins& bt = binsT[t];
+            for (uint32_t i = b0; i < e0; i++) {
+                const uint32_t it = ord[i];
+                for (int a = 0; a < 3; a++) {
+                    if (!use[a]) continue;
+                    int bi = (int)((c.cent[(size_t)it * 3 + a] - cb.lo[a]) * scale[a]);
+                    bi = bi < 0 ? 0 : (bi >= kBins ? kBins - 1 : bi);
+                    bt.n[a][bi]++; bt.box[a][bi].grow(c.boxes[it].lo, c.boxes[it].hi);
+                }
+            }
+        });
+        for (int a = 0; a < 3; a++) {
+            if (!use[a]) continue;
+            Bounds binB[kBins]; uint32_t binN[kBins] = {0};
+            for (const Bins& bt : binsT)
+                for (int bb = 0; bb < kBins; bb++) if (bt.n[a][bb]) { binN[bb] += bt.n[a][bb]; binB[bb].grow(bt.box[a][bb].lo, bt.box[a][bb].hi); }
+            Bounds rightB[kBins]; float rightArea[kBins]; uint32_t rightN[kBins];
+            Bounds acc; uint32_t cnt = 0;
+            for (int bb = kBins - 1; bb > 0; bb--) {
+                if (binN[bb]) acc.grow(binB[bb].lo, binB[bb].hi);
+                cnt += binN[bb];
+                rightB[bb] = acc; rightArea[bb] = acc.halfArea(); rightN[bb] = cnt;
+            }
+            Bounds accL; uint32_t cntL = 0;
+            for (int bb = 0; bb < kBins - 1; bb++) {
+                if (binN[bb]) accL.grow(binB[bb].lo, binB[bb].hi);
+                cntL += binN[bb];
+                if (cntL == 0 || rightN[bb + 1] == 0) continue;
+                float cost = accL.halfArea() * (float)cntL + rightArea[bb + 1] * (float)rightN[bb + 1];
+                if (cost < bestCost) { bestCost = cost; bestAxis = a; bestBin = bb; bestL = accL; bestR = rightB[bb + 1]; }
+            }
+        }
+    }
+    uint32_t mid;
+    bool boundsKnown = false;
+    if (bestAxis >= 0) {
+        const float scale = (float)kBins / (cb.hi[bestAxis] - cb.lo[bestAxis]);
+        const float lo = cb.lo[bestAxis];
+        const int a = bestAxis, bb = bestBin;
+        auto left = [&](uint32_t it) {
+            int bi = (int)((c.cent[(size_t)it * 3 + a] - lo) * scale);
+            bi = bi < 0 ? 0 : (bi >= kBins ? kBins - 1 : bi);
+            return bi <= bb;
+        };
+        if (threads > 1 && scratch != nullptr && r.count >= (1u << 18)) {
+            // parallel partition: every chunk counts its left items, then scatters into `scratch` at the chunk's offsets
+            scratch->resize(r.count);
+            uint32_t leftN[kMaxT + 1] = {0}, rightN[kMaxT + 1] = {0}, bounds[kMaxT + 1] = {0};
+            unsigned used = 0;
+            parallelChunks(r.count, threads, [&](uint32_t b0, uint32_t e0, unsigned t) {
+                uint32_t l = 0; for (uint32_t i = b0; i < e0; i++) l += left(ord[i]) ? 1u : 0u;
+                leftN[t] = l; rightN[t] = (e0 - b0) - l; bounds[t] = b0;
+            });
+            for (unsigned t = 0; t < kMaxT; t++) if (leftN[t] + rightN[t]) used = t + 1;
+            uint32_t lOff[kMaxT], rOff[kMaxT], totalL = 0;
+            for (unsigned t = 0; t < used; t++) { lOff[t] = totalL; totalL += leftN[t]; }
+            uint32_t run = totalL;
+            for (unsigned t = 0; t < used; t++) { rOff[t] = run; run += rightN[t]; }
+            uint32_t* tmp = scratch->data();
+            parallelChunks(r.count, threads, [&](uint32_t b0, uint32_t e0, unsigned t) {
+                uint32_t l = lOff[t], rr = rOff[t];
+                for (uint32_t i = b0; i < e0; i++) { const uint32_t it = ord[i]; if (left(it)) tmp[l++] = it; else tmp[rr++] = it; }
+            });
+            std::memcpy(ord, tmp, (size_t)r.count * sizeof(uint32_t));
+            mid = totalL;
+        } else {
+            uint32_t* m = std::partition(ord, ord + r.count, left);
+            mid = (uint32_t)(m - ord);
+        }
+        boundsKnown = mid != 0 && mid != r.count;   // the bins hold exactly the two halves' boxes
+    } else {
+        mid = r.count / 2;  // all centroids coincide (or past the SAH depth cap): split by index
+    }
+    if (mid == 0 || mid == r.count) mid = r.count / 2;
+    const uint32_t cnt[2] = {mid, r.count - mid};
+    const uint32_t fst[2] = {r.first, r.first + mid};
+    for (int s = 0; s < 2; s++) {
+        Bounds bnd;
+        if (boundsKnown) bnd = s == 0 ? bestL : bestR;
+        else for (uint32_t i = 0; i < cnt[s]; i++) bnd.grow(c.boxes[c.order[fst[s] + i]].lo, c.boxes[c.order[fst[s] + i]].hi);
+        setChildBox(nodes[r.node], s, bnd);
+        if (cnt[s] <= c.maxLeaf) {
+            nodes[r.node].c[s] = (int32_t)fst[s];
+            nodes[r.node].c[2 + s] = (int32_t)cnt[s];
+        } else {
+            BvhNode2 child; std::memset(&child, 0, sizeof(child)); child.c[0] = child.c[1] = -1;
+            int32_t idx = (int32_t)nodes.size();
+            nodes.push_back(child);
+            nodes[r.node].c[s] = idx;
+            nodes[r.node].c[2 + s] = 0;
+            work.push_back({fst[s], cnt[s], idx, r.depth + 1});
+        }
+    }
+}
+
+}  // namespace
+
+// Top-down build. The top of the tree is split on the calling thread until there are enough independent ranges; every such range
+// is then a subtree built by one of the worker threads into its own node array (ranges own disjoint slices of `order`), and the
+// subtrees are appended to the node array in range order - so the result does not depend on the number of threads.
 void buildBvh2(const BuildBox* boxes, uint32_t n, uint32_t maxLeaf, BuiltBvh& out, uint32_t kMaxSahDepth) {
     out.nodes.clear();
     out.depth = 1;
@@ -55,9 +212,6 @@ void buildBvh2(const BuildBox* boxes, uint32_t n, uint32_t maxLeaf, BuiltBvh& ou
     root.c[0] = root.c[1] = -1;
     out.nodes.push_back(root);
     if (n == 0) return;
-
-    struct Range { uint32_t first, count; int32_t node; uint32_t depth; };  // node whose two children are the split of this range
-    std::vector<Range> work;
     if (n <= maxLeaf) {
         Bounds b;
         for (uint32_t i = 0; i < n; i++) b.grow(boxes[i].lo, boxes[i].hi);
@@ -65,76 +219,58 @@ void buildBvh2(const BuildBox* boxes, uint32_t n, uint32_t maxLeaf, BuiltBvh& ou
         out.nodes[0].c[0] = 0; out.nodes[0].c[2] = (int32_t)n;
         return;
     }
-    work.push_back({0, n, 0, 0});
-    while (!work.empty()) {
-        Range r = work.back(); work.pop_back();
-        out.depth = std::max(out.depth, r.depth + 1);
-        uint32_t* ord = out.order.data() + r.first;
-        // centroid bounds
-        Bounds cb;
-        for (uint32_t i = 0; i < r.count; i++) cb.growPoint(&cent[(size_t)ord[i] * 3]);
-        int bestAxis = -1; int bestBin = -1; float bestCost = 1e38f;
-        for (int a = 0; a < 3 && r.depth < kMaxSahDepth; a++) {
-            float ext = cb.hi[a] - cb.lo[a];
-            if (!(ext > 0.0f)) continue;
-            Bounds binB[kBins]; uint32_t binN[kBins] = {0};
-            float scale = (float)kBins / ext;
-            for (uint32_t i = 0; i < r.count; i++) {
-                uint32_t it = ord[i];
-                int bi = (int)((cent[(size_t)it * 3 + a] - cb.lo[a]) * scale);
-                bi = bi < 0 ? 0 : (bi >= kBins ? kBins - 1 : bi);
-                binN[bi]++; binB[bi].grow(boxes[it].lo, boxes[it].hi);
-            }
-            float rightArea[kBins]; uint32_t rightN[kBins];
-            Bounds acc; uint32_t cnt = 0;
-            for (int b = kBins - 1; b > 0; b--) {
-                if (binN[b]) acc.grow(binB[b].lo, binB[b].hi);
-                cnt += binN[b];
-                rightArea[b] = acc.halfArea(); rightN[b] = cnt;
-            }
-            Bounds accL; uint32_t cntL = 0;
-            for (int b = 0; b < kBins - 1; b++) {
-                if (binN[b]) accL.grow(binB[b].lo, binB[b].hi);
-                cntL += binN[b];
-                if (cntL == 0 || rightN[b + 1] == 0) continue;
-                float cost = accL.halfArea() * (float)cntL + rightArea[b + 1] * (float)rightN[b + 1];
-                if (cost < bestCost) { bestCost = cost; bestAxis = a; bestBin = b; }
-            }
+    const BuildCtx ctx{boxes, cent.data(), out.order.data(), maxLeaf, kMaxSahDepth};
+    // ---- top of the tree, breadth first, until every open range is small enough to be one task -------------------------
+    constexpr uint32_t kParallelMin = 1u << 16;            // below this many items the whole build is one task
+    const uint32_t taskSize = std::max<uint32_t>(4096, n / 128);
+    std::vector<Range> open{{0, n, 0, 0}}, tasks;
+    if (n < kParallelMin) { tasks = open; open.clear(); }
+    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    std::vector<uint32_t> scratch;
+    while (!open.empty()) {
+        std::vector<Range> next;
+        for (const Range& r : open) {
+            out.depth = std::max(out.depth, r.depth + 1);
+            std::vector<Range> kids;
+            splitRange(ctx, r, out.nodes, kids, hw, &scratch);
+            for (const Range& k : kids) (k.count <= taskSize ? tasks : next).push_back(k);
         }
-        uint32_t mid;
-        if (bestAxis >= 0) {
-            float ext = cb.hi[bestAxis] - cb.lo[bestAxis];
-            float scale = (float)kBins / ext;
-            float lo = cb.lo[bestAxis];
-            int a = bestAxis; int bb = bestBin;
-            uint32_t* m = std::partition(ord, ord + r.count, [&](uint32_t it) {
-                int bi = (int)((cent[(size_t)it * 3 + a] - lo) * scale);
-                bi = bi < 0 ? 0 : (bi >= kBins ? kBins - 1 : bi);
-                return bi <= bb;
-            });
-            mid = (uint32_t)(m - ord);
-        } else {
-            mid = r.count / 2;  // all centroids coincide: split by index
+        open.swap(next);
+    }
+    std::sort(tasks.begin(), tasks.end(), [](const Range& a, const Range& b) { return a.first < b.first; });
+    // ---- subtrees: one task each, local node arrays (local node 0 stands for the task's root in the main array) ------------
+    struct Sub { std::vector<BvhNode2> nodes; uint32_t depth = 0; };
+    std::vector<Sub> subs(tasks.size());
+    auto runTask = [&](size_t t) {
+        Sub& sub = subs[t];
+        sub.nodes.push_back(out.nodes[(size_t)tasks[t].node]);
+        std::vector<Range> work{{tasks[t].first, tasks[t].count, 0, tasks[t].depth}};
+        while (!work.empty()) {
+            const Range r = work.back(); work.pop_back();
+            sub.depth = std::max(sub.depth, r.depth + 1);
+            splitRange(ctx, r, sub.nodes, work);
         }
-        if (mid == 0 || mid == r.count) mid = r.count / 2;
-        const uint32_t cnt[2] = {mid, r.count - mid};
-        const uint32_t fst[2] = {r.first, r.first + mid};
-        for (int s = 0; s < 2; s++) {
-            Bounds b;
-            for (uint32_t i = 0; i < cnt[s]; i++) b.grow(boxes[out.order[fst[s] + i]].lo, boxes[out.order[fst[s] + i]].hi);
-            setChildBox(out.nodes[r.node], s, b);
-            if (cnt[s] <= maxLeaf) {
-                out.nodes[r.node].c[s] = (int32_t)fst[s];
-                out.nodes[r.node].c[2 + s] = (int32_t)cnt[s];
-            } else {
-                BvhNode2 child; std::memset(&child, 0, sizeof(child)); child.c[0] = child.c[1] = -1;
-                int32_t idx = (int32_t)out.nodes.size();
-                out.nodes.push_back(child);
-                out.nodes[r.node].c[s] = idx;
-                out.nodes[r.node].c[2 + s] = 0;
-                work.push_back({fst[s], cnt[s], idx, r.depth + 1});
-            }
-        }
+    };
+    const unsigned nThreads = (unsigned)std::min<size_t>(hw, tasks.size());
+    if (nThreads <= 1) for (size_t t = 0; t < tasks.size(); t++) runTask(t);
+    else {
+        std::atomic<size_t> nextTask{0};
+        std::vector<std::thread> pool;
+        for (unsigned w = 0; w < nThreads; w++)
+            pool.emplace_back([&] { for (;;) { const size_t t = nextTask.fetch_add(1); if (t >= tasks.size()) break; runTask(t); } });
+        for (auto& th : pool) th.join();
+    }
+    // ---- stitch: local node k >= 1 of task t becomes main node base_t + k - 1 -------------------------------------------------
+    for (size_t t = 0; t < tasks.size(); t++) {
+        const Sub& sub = subs[t];
+        const int32_t base = (int32_t)out.nodes.size();
+        auto remap = [&](BvhNode2 nd) {
+            for (int s = 0; s < 2; s++) if (nd.c[2 + s] == 0 && nd.c[s] >= 1) nd.c[s] = base + nd.c[s] - 1;
+            return nd;
+        };
+        out.nodes[(size_t)tasks[t].node] = remap(sub.nodes[0]);
+        for (size_t k = 1; k < sub.nodes.size(); k++) out.nodes.push_back(remap(sub.nodes[k]));
+        out.depth = std::max(out.depth, sub.depth);
     }
 }
 

@@ -5,10 +5,11 @@
 // reference behaviour and is stated in DESIGN.md §"Intersection"; the CPU oracle implements the same
 // definition independently (oracle/bvh.h):
 //   object-space ray   o' = mulPoint(w2o, o), d' = mulVec(w2o, d)   (t shared between spaces)
-//   A=v0-o, B=v1-o, C=v2-o;  U=dot(d,cross(C,B)), V=dot(d,cross(A,C)), W=dot(d,cross(B,A)), each with a rounding-error bound;
-//   any |value| <= its bound -> all three (and u, v, t) are recomputed in binary64 (exact products): signs are the EXACT signs
-//   miss if mixed signs; det=(U+V)+W, det==0 -> miss; rdet=1/det; u=V*rdet; v=W*rdet
-//   T=(U*dot(A,d)+V*dot(B,d))+W*dot(C,d);  t=(T*rdet)*(1/dot(d,d));  hit iff tmin<t<tmax
+//   kz = dominant axis of d, (kx, ky) the other two in cyclic order (swapped if d[kz] < 0); Sx=d[kx]/d[kz], Sy=d[ky]/d[kz], Sz=1/d[kz]
+//   A=v0-o, B=v1-o, C=v2-o;  Ax=A[kx]-Sx*A[kz], Ay=A[ky]-Sy*A[kz] (same for B, C);  Az=Sz*A[kz] ...
+//   U=Cx*By-Cy*Bx, V=Ax*Cy-Ay*Cx, W=Bx*Ay-By*Ax; any |value| <= 2^-22 (|p|+|q|) of its two products -> U, V, W, u, v, t are
+//   recomputed in binary64 (exact products, exact sign of the difference): signs are the EXACT signs of the 2-D edge functions
+//   miss if mixed signs; det=(U+V)+W, det==0 -> miss; rdet=1/det; u=V*rdet; v=W*rdet; t=((U*Az+V*Bz)+W*Cz)*rdet; hit iff tmin<t<tmax
 //   closest = min t, ties -> smallest (instance, geometry, primitive); no culling; mask 0 skipped.
 // The slab test is only required to be conservative (boxes are padded at build time, bvh_build.h).
 //
@@ -29,22 +30,38 @@ namespace msne {
 
 struct HitRec { uint32_t inst, tri; float u, v; };
 
+#ifndef MSNE_SLAB_EPS
+#define MSNE_SLAB_EPS 4e-7f   // measurement variants only; 0 makes the slab test unsafe for far / axis-parallel rays
+#endif
+#ifndef MSNE_TRI_FALLBACK_INLINE
+#define MSNE_TRI_FALLBACK_INLINE 0
+#endif
+
 struct SpaceRay {
-    float3 o, d, idir, ood;
-    float rdd, eps;
-    DI void set(float3 o_, float3 d_) {
-        o = o_; d = d_;
+    float3 o, idir, ood;
+    float eps;
+    float Sx, Sy, Sz;      // shear of the ray onto its dominant axis (triTest)
+    uint32_t k;            // kx | ky << 2 | kz << 4: the axis permutation of that shear
+    DI void set(float3 o_, float3 d) {
+        o = o_;
         idir.x = fabsf(d.x) > 1e-20f ? 1.0f / d.x : copysignf(1e20f, d.x);
         idir.y = fabsf(d.y) > 1e-20f ? 1.0f / d.y : copysignf(1e20f, d.y);
         idir.z = fabsf(d.z) > 1e-20f ? 1.0f / d.z : copysignf(1e20f, d.z);
         ood = mk3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
-        rdd = 1.0f / dot(d, d);
         // The slab distances are lo * idir - ood: their ABSOLUTE error is a few ulp of |ood| = |o / d| (the two products cancel), which
-        // for a ray that starts far from the box, or runs nearly parallel to a slab, exceeds any fixed padding of the box. The
-        // triangle test has no such cancellation (vertices are translated by o first) and accepts rays within a few ulp of |o| of an
-        // edge. eps (16 ulp of the largest |ood|) widens the slab comparison by both, so a box is never skipped that holds a
-        // triangle the exact-as-written triangle test would accept: traversal finds what testing every triangle would find.
-        eps = 4e-7f * fmaxf(fmaxf(fabsf(ood.x), fabsf(ood.y)), fabsf(ood.z));
+        // for a ray that starts far from the box, or runs nearly parallel to a slab, exceeds any fixed padding of the box. eps (~7 ulp
+        // of the largest |ood|) widens the slab comparison accordingly, so a box is never skipped that holds a triangle the ray
+        // passes through: traversal finds what testing every triangle would find.
+        eps = MSNE_SLAB_EPS * fmaxf(fmaxf(fabsf(ood.x), fabsf(ood.y)), fabsf(ood.z));
+        // dominant axis kz, the other two in cyclic order, swapped when d[kz] < 0 so that the winding is preserved
+        const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+        const uint32_t kz = ax > ay ? (ax > az ? 0u : 2u) : (ay > az ? 1u : 2u);
+        uint32_t kx = kz == 2u ? 0u : kz + 1u, ky = kx == 2u ? 0u : kx + 1u;
+        const float dz = kz == 0u ? d.x : (kz == 1u ? d.y : d.z);
+        if (dz < 0.0f) { const uint32_t tmp = kx; kx = ky; ky = tmp; }
+        const float dx = kx == 0u ? d.x : (kx == 1u ? d.y : d.z), dy = ky == 0u ? d.x : (ky == 1u ? d.y : d.z);
+        Sx = dx / dz; Sy = dy / dz; Sz = 1.0f / dz;
+        k = kx | (ky << 2) | (kz << 4);
     }
 };
 
@@ -58,56 +75,54 @@ DI bool slab(const SpaceRay& r, float lox, float hix, float loy, float hiy, floa
     return tnear <= fmaf(tfar, 1.0000004f, r.eps);
 }
 
-// Edge function d . (P x Q) in binary32 with a bound of its rounding error (8 * 2^-24 times the sum of the magnitudes of its six
-// products): when |value| > bound, the sign is that of the exact value.
-DI float edgeFn(const float3 d, const float3 P, const float3 Q, float& bound) {
-    const float px = P.y * Q.z, qx = P.z * Q.y, py = P.z * Q.x, qy = P.x * Q.z, pz = P.x * Q.y, qz = P.y * Q.x;
-    const float cx = px - qx, cy = py - qy, cz = pz - qz;
-    const float tx = d.x * cx, ty = d.y * cy, tz = d.z * cz;
-    const float mag = (fabsf(d.x) * (fabsf(px) + fabsf(qx)) + fabsf(d.y) * (fabsf(py) + fabsf(qy))) + fabsf(d.z) * (fabsf(pz) + fabsf(qz));
-    bound = mag * 4.7683716e-07f;
-    return (tx + ty) + tz;
-}
-DI double edgeFnExact(const float3 d, const float3 P, const float3 Q) {
-    const double cx = (double)P.y * (double)Q.z - (double)P.z * (double)Q.y;
-    const double cy = (double)P.z * (double)Q.x - (double)P.x * (double)Q.z;
-    const double cz = (double)P.x * (double)Q.y - (double)P.y * (double)Q.x;
-    return ((double)d.x * cx + (double)d.y * cy) + (double)d.z * cz;
-}
-DI double dotExact(const float3 a, const float3 b) { return ((double)a.x * (double)b.x + (double)a.y * (double)b.y) + (double)a.z * (double)b.z; }
-// The rare path of triTest (a few per cent of the tests): the ray grazes the triangle's plane or passes within rounding distance of
-// an edge, so binary32 cannot tell the signs of the edge functions. In binary64 every product of two binary32 numbers is exact
-// and the sums are good to 1e-15: the decision is the exact one. Out of line: it must not cost the traversal loop registers.
-// Returns (t, u, v, hit ? 1 : 0) in registers.
-__device__ __noinline__ float4 triTestExact(const float3 A, const float3 B, const float3 C, const float3 d) {
-    const double Ud = edgeFnExact(d, C, B), Vd = edgeFnExact(d, A, C), Wd = edgeFnExact(d, B, A);
-    if ((Ud < 0.0 || Vd < 0.0 || Wd < 0.0) && (Ud > 0.0 || Vd > 0.0 || Wd > 0.0)) return make_float4(0.f, 0.f, 0.f, 0.f);
-    const double det = (Ud + Vd) + Wd;
+DI float pick(const float3 v, uint32_t k) { return k == 0u ? v.x : (k == 1u ? v.y : v.z); }
+// The rare path of triTest: binary32 cannot certify the sign of an edge function (the ray passes within rounding distance of an
+// edge line). In binary64 the two products of an edge function are exact and their difference, rounded once, has the exact sign.
+// Returns (t, u, v, hit ? 1 : 0) in registers; out of line so that it costs the traversal loop no registers.
+#if MSNE_TRI_FALLBACK_INLINE
+DI
+#else
+__device__ __noinline__
+#endif
+float4 triTestExact(float Ax, float Ay, float Bx, float By, float Cx, float Cy, float Az, float Bz, float Cz) {
+    const double U = (double)Cx * (double)By - (double)Cy * (double)Bx;
+    const double V = (double)Ax * (double)Cy - (double)Ay * (double)Cx;
+    const double W = (double)Bx * (double)Ay - (double)By * (double)Ax;
+    if ((U < 0.0 || V < 0.0 || W < 0.0) && (U > 0.0 || V > 0.0 || W > 0.0)) return make_float4(0.f, 0.f, 0.f, 0.f);
+    const double det = (U + V) + W;
     if (det == 0.0) return make_float4(0.f, 0.f, 0.f, 0.f);
-    const double T = (Ud * dotExact(A, d) + Vd * dotExact(B, d)) + Wd * dotExact(C, d);
-    return make_float4((float)((T / det) / dotExact(d, d)), (float)(Vd / det), (float)(Wd / det), 1.0f);
+    const double T = (U * (double)Az + V * (double)Bz) + W * (double)Cz;
+    return make_float4((float)(T / det), (float)(V / det), (float)(W / det), 1.0f);
 }
-// A triangle is hit iff the ray passes through the translated triangle (A, B, C = v - o rounded to binary32) EXACTLY: the signs of
-// the three edge functions are certified in binary32 or decided in binary64. No ray can slip between two triangles that share an
-// edge (X x Y = -(Y x X) holds exactly in both precisions), and none is accepted by a triangle it does not pass through - so
-// walking any conservative BVH finds exactly what testing every triangle would find (oracle/bvh.h states the same test).
+// Ray/triangle test: the project's definition of the driver-opaque reference behaviour; the CPU checker
+// states the same test independently (oracle/bvh.h). The triangle is translated to the ray origin and sheared onto the ray's dominant axis, which
+// turns the test into three 2-D edge functions of the projected vertices (Woop, Benthin, Wald 2013). Their SIGNS are exact: each is
+// certified in binary32 (|value| above the rounding bound of its two products) or decided in binary64. Consequences:
+//  * two triangles that share an edge see the same projected end points and opposite edge functions, exactly: no ray slips between;
+//  * a triangle is accepted only if the ray passes through its projection, so a conservative BVH walk returns exactly what testing
+//    every triangle returns - results do not depend on the tree, on traversal order, or on which boxes happened to be visited.
 DI bool triTest(const float4 t0, const float4 t1, const float4 t2, const SpaceRay& r, float tmin, float tmax, float& t, float& u, float& v) {
     const float3 A = mk3(t0.x, t0.y, t0.z) - r.o, B = mk3(t1.x, t1.y, t1.z) - r.o, C = mk3(t2.x, t2.y, t2.z) - r.o;
-    float eU, eV, eW;
-    const float U = edgeFn(r.d, C, B, eU);
-    const float V = edgeFn(r.d, A, C, eV);
-    const float W = edgeFn(r.d, B, A, eW);
-    if (fabsf(U) > eU && fabsf(V) > eV && fabsf(W) > eW) {
+    const uint32_t kx = r.k & 3u, ky = (r.k >> 2) & 3u, kz = r.k >> 4;
+    const float Akz = pick(A, kz), Bkz = pick(B, kz), Ckz = pick(C, kz);
+    const float Ax = pick(A, kx) - r.Sx * Akz, Ay = pick(A, ky) - r.Sy * Akz;
+    const float Bx = pick(B, kx) - r.Sx * Bkz, By = pick(B, ky) - r.Sy * Bkz;
+    const float Cx = pick(C, kx) - r.Sx * Ckz, Cy = pick(C, ky) - r.Sy * Ckz;
+    const float u0 = Cx * By, u1 = Cy * Bx, v0 = Ax * Cy, v1 = Ay * Cx, w0 = Bx * Ay, w1 = By * Ax;
+    const float U = u0 - u1, V = v0 - v1, W = w0 - w1;
+    const float Az = r.Sz * Akz, Bz = r.Sz * Bkz, Cz = r.Sz * Ckz;
+    constexpr float kBound = 2.3841858e-07f;   // 2^-22 > 3 ulp: two rounded products and their rounded difference
+    if (fabsf(U) > kBound * (fabsf(u0) + fabsf(u1)) && fabsf(V) > kBound * (fabsf(v0) + fabsf(v1)) && fabsf(W) > kBound * (fabsf(w0) + fabsf(w1))) {
         if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
         const float det = (U + V) + W;
         const float rdet = 1.0f / det;
         u = V * rdet;
         v = W * rdet;
-        const float T = (U * dot(A, r.d) + V * dot(B, r.d)) + W * dot(C, r.d);
-        t = (T * rdet) * r.rdd;
+        const float T = (U * Az + V * Bz) + W * Cz;
+        t = T * rdet;
         return tmin < t && t < tmax;
     }
-    const float4 e = triTestExact(A, B, C, r.d);
+    const float4 e = triTestExact(Ax, Ay, Bx, By, Cx, Cy, Az, Bz, Cz);
     t = e.x; u = e.y; v = e.z;
     return e.w != 0.0f && tmin < t && t < tmax;
 }

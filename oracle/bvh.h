@@ -124,52 +124,55 @@ struct Blas {
     Bvh bvh;
 };
 
-// Edge functions U = d.(C x B), V = d.(A x C), W = d.(B x A) of the translated triangle (A, B, C = v - o, rounded to binary32: that
-// IS the triangle the ray is tested against). Each is evaluated in binary32 together with a bound of its rounding error (a few
-// ulp of the sum of the magnitudes of its six products). When all three are further from zero than their bounds, their signs are
-// those of the exact values and the binary32 results are used. Otherwise - the ray grazes the triangle's plane or passes within
-// rounding distance of an edge - the three are re-evaluated in binary64, where every product of two binary32 numbers is exact and
-// the sums are good to 1e-15: the decision is then the exact one. Hence a triangle is accepted only if the ray really passes
-// through it, whichever boxes led to it: walking any conservative BVH returns what testing every triangle returns.
-inline float edgeFn(float3 d, float3 P, float3 Q, float& bound) {   // d . (P x Q), bound >= its rounding error
-    const float px = P.y * Q.z, qx = P.z * Q.y, py = P.z * Q.x, qy = P.x * Q.z, pz = P.x * Q.y, qz = P.y * Q.x;
-    const float cx = px - qx, cy = py - qy, cz = pz - qz;
-    const float tx = d.x * cx, ty = d.y * cy, tz = d.z * cz;
-    const float mag = (std::fabs(d.x) * (std::fabs(px) + std::fabs(qx)) + std::fabs(d.y) * (std::fabs(py) + std::fabs(qy))) + std::fabs(d.z) * (std::fabs(pz) + std::fabs(qz));
-    bound = mag * 4.7683716e-07f;   // 8 * 2^-24: products, differences, the dot's products and its two sums
-    return (tx + ty) + tz;
-}
-inline double edgeFnExact(float3 d, float3 P, float3 Q) {
-    const double cx = (double)P.y * (double)Q.z - (double)P.z * (double)Q.y;
-    const double cy = (double)P.z * (double)Q.x - (double)P.x * (double)Q.z;
-    const double cz = (double)P.x * (double)Q.y - (double)P.y * (double)Q.x;
-    return ((double)d.x * cx + (double)d.y * cy) + (double)d.z * cz;
+// Ray/triangle test = the definition of a hit. The triangle is translated to the ray origin (A, B, C = v - o,
+// rounded to binary32) and sheared onto the ray's dominant axis, which leaves three 2-D edge functions of the projected vertices
+// (Woop, Benthin, Wald 2013). Their signs are EXACT: each is certified in binary32 (|value| above the rounding bound of its two
+// products) or decided in binary64, where both products are exact and their difference, rounded once, has the exact sign. So two
+// triangles sharing an edge decide consistently (no ray slips between them) and a triangle is accepted only if the ray passes
+// through its projection: walking any conservative BVH returns what testing every triangle returns (`brute`, cross-check mode).
+struct RayShear { uint32_t kx, ky, kz; float Sx, Sy, Sz; };
+inline RayShear ray_shear(float3 d) {
+    const float ax = std::fabs(d.x), ay = std::fabs(d.y), az = std::fabs(d.z);
+    RayShear r;
+    r.kz = ax > ay ? (ax > az ? 0u : 2u) : (ay > az ? 1u : 2u);
+    r.kx = r.kz == 2u ? 0u : r.kz + 1u; r.ky = r.kx == 2u ? 0u : r.kx + 1u;
+    const float dv[3] = {d.x, d.y, d.z};
+    if (dv[r.kz] < 0.0f) std::swap(r.kx, r.ky);
+    r.Sx = dv[r.kx] / dv[r.kz]; r.Sy = dv[r.ky] / dv[r.kz]; r.Sz = 1.0f / dv[r.kz];
+    return r;
 }
 inline bool tri_test(const Tri& tr, float3 o, float3 d, float tmin, float tmax, float& t, float& u, float& v) {
-    const float3 A = tr.v0 - o, B = tr.v1 - o, C = tr.v2 - o;
-    float eU, eV, eW;
-    const float U = edgeFn(d, C, B, eU);
-    const float V = edgeFn(d, A, C, eV);
-    const float W = edgeFn(d, B, A, eW);
-    if (std::fabs(U) > eU && std::fabs(V) > eV && std::fabs(W) > eW) {
+    const RayShear r = ray_shear(d);
+    const float3 A3 = tr.v0 - o, B3 = tr.v1 - o, C3 = tr.v2 - o;
+    const float A[3] = {A3.x, A3.y, A3.z}, B[3] = {B3.x, B3.y, B3.z}, C[3] = {C3.x, C3.y, C3.z};
+    const float Ax = A[r.kx] - r.Sx * A[r.kz], Ay = A[r.ky] - r.Sy * A[r.kz];
+    const float Bx = B[r.kx] - r.Sx * B[r.kz], By = B[r.ky] - r.Sy * B[r.kz];
+    const float Cx = C[r.kx] - r.Sx * C[r.kz], Cy = C[r.ky] - r.Sy * C[r.kz];
+    const float u0 = Cx * By, u1 = Cy * Bx, v0 = Ax * Cy, v1 = Ay * Cx, w0 = Bx * Ay, w1 = By * Ax;
+    const float U = u0 - u1, V = v0 - v1, W = w0 - w1;
+    const float Az = r.Sz * A[r.kz], Bz = r.Sz * B[r.kz], Cz = r.Sz * C[r.kz];
+    const float kBound = 2.3841858e-07f;   // 2^-22
+    if (std::fabs(U) > kBound * (std::fabs(u0) + std::fabs(u1)) && std::fabs(V) > kBound * (std::fabs(v0) + std::fabs(v1)) &&
+        std::fabs(W) > kBound * (std::fabs(w0) + std::fabs(w1))) {
         if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
         const float det = (U + V) + W;
         const float rdet = 1.0f / det;
         u = V * rdet;
         v = W * rdet;
-        const float T = (U * dot(A, d) + V * dot(B, d)) + W * dot(C, d);
-        t = (T * rdet) * (1.0f / dot(d, d));
+        const float T = (U * Az + V * Bz) + W * Cz;
+        t = T * rdet;
         return tmin < t && t < tmax;
     }
-    const double Ud = edgeFnExact(d, C, B), Vd = edgeFnExact(d, A, C), Wd = edgeFnExact(d, B, A);
+    const double Ud = (double)Cx * (double)By - (double)Cy * (double)Bx;
+    const double Vd = (double)Ax * (double)Cy - (double)Ay * (double)Cx;
+    const double Wd = (double)Bx * (double)Ay - (double)By * (double)Ax;
     if ((Ud < 0.0 || Vd < 0.0 || Wd < 0.0) && (Ud > 0.0 || Vd > 0.0 || Wd > 0.0)) return false;
     const double det = (Ud + Vd) + Wd;
     if (det == 0.0) return false;
-    auto dotd = [](float3 a, float3 b) { return ((double)a.x * (double)b.x + (double)a.y * (double)b.y) + (double)a.z * (double)b.z; };
+    const double T = (Ud * (double)Az + Vd * (double)Bz) + Wd * (double)Cz;
+    t = (float)(T / det);
     u = (float)(Vd / det);
     v = (float)(Wd / det);
-    const double T = (Ud * dotd(A, d) + Vd * dotd(B, d)) + Wd * dotd(C, d);
-    t = (float)((T / det) / dotd(d, d));
     return tmin < t && t < tmax;
 }
 
