@@ -89,8 +89,12 @@ void splitRange(const BuildCtx& c, const Range& r, std::vector<BvhNode2>& nodes,
     if (r.depth < c.maxSahDepth) {
         float scale[3]; bool use[3];
         for (int a = 0; a < 3; a++) { const float ext = cb.hi[a] - cb.lo[a]; use[a] = ext > 0.0f; scale[a] = use[a] ? (float)kBins / ext : 0.0f; }
-        std::vector<Bins> binsT(std::max(1u, threads));
-        for (Bins& bt : binsT) std::memset(bt.n, 0, sizeof(bt.n));
+        Bins oneBins;                       // ranges handled by one thread (nearly all of them) stay off the heap
+        std::vector<Bins> manyBins;
+        Bins* binsT = &oneBins;
+        const unsigned nBins = std::max(1u, threads);
+        if (nBins > 1) { manyBins.resize(nBins); binsT = manyBins.data(); }
+        for (unsigned t = 0; t < nBins; t++) std::memset(binsT[t].n, 0, sizeof(binsT[t].n));
         parallelChunks(r.count, threads, [&](uint32_t b0, uint32_t e0, unsigned t) {
             Bins& bt = binsT[t];
             for (uint32_t i = b0; i < e0; i++) {
@@ -106,8 +110,10 @@ void splitRange(const BuildCtx& c, const Range& r, std::vector<BvhNode2>& nodes,
         for (int a = 0; a < 3; a++) {
             if (!use[a]) continue;
             Bounds binB[kBins]; uint32_t binN[kBins] = {0};
-            for (const Bins& bt : binsT)
+            for (unsigned t = 0; t < nBins; t++) {
+                const Bins& bt = binsT[t];
                 for (int bb = 0; bb < kBins; bb++) if (bt.n[a][bb]) { binN[bb] += bt.n[a][bb]; binB[bb].grow(bt.box[a][bb].lo, bt.box[a][bb].hi); }
+            }
             Bounds rightB[kBins]; float rightArea[kBins]; uint32_t rightN[kBins];
             Bounds acc; uint32_t cnt = 0;
             for (int bb = kBins - 1; bb > 0; bb--) {

@@ -149,7 +149,7 @@ DI uint32_t hitBin(const DeviceScene& sc, const HitRec& h) {
 // The index space is padded so that a ticket never straddles the two queues: extension tickets cover [0, roundup32(nLive)), shadow
 // tickets follow.
 #ifndef MSNE_TRACE_STAGING
-#define MSNE_TRACE_STAGING 1
+#define MSNE_TRACE_STAGING 0
 #endif
 DI uint32_t smemAddr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 DI void mbarInit(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }

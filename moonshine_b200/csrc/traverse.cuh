@@ -38,8 +38,8 @@ struct HitRec { uint32_t inst, tri; float u, v; };
 #endif
 
 struct SpaceRay {
-    float3 o, idir, ood;
-    float eps;
+    float3 o, idir;
+    float3 oodLo, oodHi;   // o * idir, pushed outwards per axis: subtracted from lo * idir / hi * idir respectively (slab)
     float Sx, Sy, Sz;      // shear of the ray onto its dominant axis (triTest)
     uint32_t k;            // kx | ky << 2 | kz << 4: the axis permutation of that shear
     DI void set(float3 o_, float3 d) {
@@ -47,12 +47,16 @@ struct SpaceRay {
         idir.x = fabsf(d.x) > 1e-20f ? 1.0f / d.x : copysignf(1e20f, d.x);
         idir.y = fabsf(d.y) > 1e-20f ? 1.0f / d.y : copysignf(1e20f, d.y);
         idir.z = fabsf(d.z) > 1e-20f ? 1.0f / d.z : copysignf(1e20f, d.z);
-        ood = mk3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
-        // The slab distances are lo * idir - ood: their ABSOLUTE error is a few ulp of |ood| = |o / d| (the two products cancel), which
-        // for a ray that starts far from the box, or runs nearly parallel to a slab, exceeds any fixed padding of the box. eps (~7 ulp
-        // of the largest |ood|) widens the slab comparison accordingly, so a box is never skipped that holds a triangle the ray
-        // passes through: traversal finds what testing every triangle would find.
-        eps = MSNE_SLAB_EPS * fmaxf(fmaxf(fabsf(ood.x), fabsf(ood.y)), fabsf(ood.z));
+        // The slab distances are plane * idir - o * idir: the two products cancel, so the ABSOLUTE error of a distance is a few ulp of
+        // |o * idir| - which, for a ray that starts far from the box or runs nearly parallel to the slab, exceeds any fixed padding of
+        // the box. Each axis therefore carries its own margin (MSNE_SLAB_EPS ~ 7 ulp of |o * idir|), applied outwards: the plane the
+        // ray enters through moves towards the ray, the one it leaves through away from it. No box is skipped that holds a triangle
+        // the ray passes through - traversal finds what testing every triangle would find - and the margin costs no instruction.
+        const float3 ood = mk3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
+        const float3 e = mk3(MSNE_SLAB_EPS * fabsf(ood.x), MSNE_SLAB_EPS * fabsf(ood.y), MSNE_SLAB_EPS * fabsf(ood.z));
+        // idir > 0: lo is the entry plane (distance must not come out too late: subtract MORE), hi the exit plane (subtract LESS)
+        oodLo = mk3(idir.x > 0.0f ? ood.x + e.x : ood.x - e.x, idir.y > 0.0f ? ood.y + e.y : ood.y - e.y, idir.z > 0.0f ? ood.z + e.z : ood.z - e.z);
+        oodHi = mk3(idir.x > 0.0f ? ood.x - e.x : ood.x + e.x, idir.y > 0.0f ? ood.y - e.y : ood.y + e.y, idir.z > 0.0f ? ood.z - e.z : ood.z + e.z);
         // dominant axis kz, the other two in cyclic order, swapped when d[kz] < 0 so that the winding is preserved
         const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
         const uint32_t kz = ax > ay ? (ax > az ? 0u : 2u) : (ay > az ? 1u : 2u);
@@ -67,12 +71,12 @@ struct SpaceRay {
 
 // returns true when the child's box overlaps [tmin, tmax] along the ray (conservative)
 DI bool slab(const SpaceRay& r, float lox, float hix, float loy, float hiy, float loz, float hiz, float tmin, float tmax, float& tnear) {
-    const float tx0 = fmaf(lox, r.idir.x, -r.ood.x), tx1 = fmaf(hix, r.idir.x, -r.ood.x);
-    const float ty0 = fmaf(loy, r.idir.y, -r.ood.y), ty1 = fmaf(hiy, r.idir.y, -r.ood.y);
-    const float tz0 = fmaf(loz, r.idir.z, -r.ood.z), tz1 = fmaf(hiz, r.idir.z, -r.ood.z);
+    const float tx0 = fmaf(lox, r.idir.x, -r.oodLo.x), tx1 = fmaf(hix, r.idir.x, -r.oodHi.x);
+    const float ty0 = fmaf(loy, r.idir.y, -r.oodLo.y), ty1 = fmaf(hiy, r.idir.y, -r.oodHi.y);
+    const float tz0 = fmaf(loz, r.idir.z, -r.oodLo.z), tz1 = fmaf(hiz, r.idir.z, -r.oodHi.z);
     tnear = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), tmin));
     const float tfar = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), tmax));
-    return tnear <= fmaf(tfar, 1.0000004f, r.eps);
+    return tnear <= tfar * 1.0000004f;
 }
 
 DI float pick(const float3 v, uint32_t k) { return k == 0u ? v.x : (k == 1u ? v.y : v.z); }
