@@ -12,7 +12,7 @@ namespace msne {
 #define TRACE_BLOCKS_PER_SM 8   // 64 registers: measured best (profiles/r01_sweeps.md)
 #endif
 #ifndef TRACE1_BLOCKS_PER_SM
-#define TRACE1_BLOCKS_PER_SM 9  // single-level specialisation (no transformed instances): 56 registers, measured best of 8/9/10
+#define TRACE1_BLOCKS_PER_SM 8  // single-level specialisation (no transformed instances): 64 registers; 8 vs 9 blocks: +2 % since the exact triangle test (profiles/r02_sweeps.md)
 #endif
 // Entries of the per-ray traversal stack (traverse.cuh): one per tree level (the far child) + the REF_END / REF_LEAVE sentinels.
 // runtime.cpp holds depth(TLAS) + depth(BLAS) + 2 below it at build time.

@@ -510,8 +510,10 @@ def _tile_textures(n=1024, tiles=8, base=(225, 228, 230), grout=(120, 118, 115),
     h = g + 0.004 * rs.rand(n, n)
     gx, gy = np.gradient(h, axis=1), np.gradient(h, axis=0)
     nrm = np.zeros((n, n, 2), np.uint8)
-    nrm[..., 0] = np.clip(127.5 - gx * 900, 0, 255).astype(np.uint8)
-    nrm[..., 1] = np.clip(127.5 - gy * 900, 0, 255).astype(np.uint8)
+    # tangent-space xy kept inside the unit disk (|x|, |y| <= 0.56): a texel on its rim decodes to z = 0, a normal lying IN the
+    # surface, for which Frame::reorthogonalize (reflection_frame.hlsl:31-35) divides 0 by 0 whenever it lines up with the tangent
+    nrm[..., 0] = np.clip(127.5 - gx * 900, 56, 199).astype(np.uint8)
+    nrm[..., 1] = np.clip(127.5 - gy * 900, 56, 199).astype(np.uint8)
     rough = np.clip(60 + (1 - g) * 150 + rs.rand(n, n) * 12, 0, 255).astype(np.uint8)
     return rgba, nrm, rough
 

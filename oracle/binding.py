@@ -52,6 +52,7 @@ def lib():
         L.OracleRender.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p]
         L.OracleRenderDiag.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p]
         L.OracleRenderPixels.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.OracleDebugPath.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
         L.OracleEnvProbe.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p]
         L.OracleBsdfBatch.argtypes = [C.c_size_t, C.c_void_p, C.c_void_p]
         L.OracleMathProbe.argtypes = [C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -184,6 +185,13 @@ class Oracle:
 
     def cross_check_mismatches(self):
         return int(self.L.OracleCrossCheckMismatches(self.h))
+
+    def debug_path(self, lens, width, height, x, y, sample=0):
+        """Diagnostics: prints every bounce of one path on stderr, returns its RGBA."""
+        out = np.zeros(4, np.float32)
+        la = lens.as_array()
+        self.L.OracleDebugPath(self.h, _p(la), width, height, x, y, sample, _p(out))
+        return out
 
     def env_probe(self, op, inputs3):
         """EnvMap::sample (op 0, rand in columns 0-1), ::eval (op 1, direction), ::incomingRadiance (op 2) -> (n, 7)."""

@@ -206,6 +206,18 @@ void OracleRenderPixels(Oracle* o, const float* lens12, uint32_t W, uint32_t H, 
     sc.brute = saved;
 }
 
+// diagnostics: one path (pixel x, y, sample index) with every bounce printed on stderr; out = its radiance
+void OracleDebugPath(Oracle* o, const float* lens12, uint32_t W, uint32_t H, uint32_t x, uint32_t y, uint32_t sample, float* out4) {
+    if (o->dirty) commit(o);
+    Lens lens; std::memcpy(&lens, lens12, 48);
+    TraceCounters tc;
+    float texel[4] = {0, 0, 0, 0};
+    g_debugPath = true;
+    raygenPixel(o->sc, tc, lens, W, H, x, y, sample, texel);
+    g_debugPath = false;
+    std::memcpy(out4, texel, 16);
+}
+
 // ---- per-function entry points for known-answer / stage tests ---------------------------
 uint32_t OracleHashPcg(uint32_t a) { return Hash::pcg(a); }
 uint32_t OracleHashLcg(uint32_t a) { return Hash::lcg(a); }

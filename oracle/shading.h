@@ -6,6 +6,7 @@
 //   integrator.hlsl -> PathTracingIntegrator::incomingRadiance;  main.hlsl -> raygen/storeColor.
 // All paths relative to /root/reference/shaders/hrtsystem/.
 #pragma once
+#include <cstdio>
 #include "bvh.h"
 
 namespace orc {
@@ -481,6 +482,7 @@ inline float3 estimateDirectMISLight(const SceneData& sc, TraceCounters& tc, con
     return f3(0.0f);
 }
 
+static thread_local bool g_debugPath = false;   // diagnostics: OracleDebugPath prints every bounce of one path
 inline float3 incomingRadiance(const SceneData& sc, TraceCounters& tc, RayDesc initialRay, Rng& rng) {   // :68-183
     const Constants& k = sc.consts;
     EnvMap envMap{&sc.env};
@@ -499,6 +501,11 @@ inline float3 incomingRadiance(const SceneData& sc, TraceCounters& tc, RayDesc i
 
         uint32_t instanceID = sc.instances[its.instanceIndex].customIndex;
         const GeometryRec& geometry = sc.geometries[instanceID + its.geometryIndex];
+        if (g_debugPath)
+            fprintf(stderr, "bounce %u: o=(%.9g %.9g %.9g) d=(%.9g %.9g %.9g) -> inst %u geom %u prim %u bary (%.9g %.9g) material %u type %u | throughput (%g %g %g) acc (%g %g %g)\n",
+                    bounceCount, ray.Origin.x, ray.Origin.y, ray.Origin.z, ray.Direction.x, ray.Direction.y, ray.Direction.z, its.instanceIndex, its.geometryIndex,
+                    its.primitiveIndex, its.barycentrics.x, its.barycentrics.y, geometry.material, sc.materials[geometry.material].type, throughput.x, throughput.y, throughput.z,
+                    accumulatedColor.x, accumulatedColor.y, accumulatedColor.z);
         MeshAttributes attrs = MeshAttributes::lookupAndInterpolate(sc, its.instanceIndex, its.geometryIndex, its.primitiveIndex, its.barycentrics).inWorld(sc, its.instanceIndex);
         Frame textureFrame = getTextureFrame(sc, geometry.material, attrs.texcoord, attrs.frame);
         float3 emissiveLight = getEmissive(sc, geometry.material, attrs.texcoord);
@@ -547,6 +554,11 @@ inline float3 incomingRadiance(const SceneData& sc, TraceCounters& tc, RayDesc i
         }
 
         MaterialSample sample = material.sample(outgoingDirSs, rng.getFloat2());   // :154-163
+        if (g_debugPath)
+            fprintf(stderr, "          position (%.9g %.9g %.9g) n_tri (%g %g %g) n_shade (%g %g %g) w_o (%g %g %g) sample dir (%g %g %g) pdf %g acc (%g %g %g)\n",
+                    attrs.position.x, attrs.position.y, attrs.position.z, attrs.triangleFrame.n.x, attrs.triangleFrame.n.y, attrs.triangleFrame.n.z,
+                    shadingFrame.n.x, shadingFrame.n.y, shadingFrame.n.z, outgoingDirSs.x, outgoingDirSs.y, outgoingDirSs.z, sample.dirFs.x, sample.dirFs.y, sample.dirFs.z,
+                    sample.pdf, accumulatedColor.x, accumulatedColor.y, accumulatedColor.z);
         if (sample.pdf == 0.0f) return accumulatedColor;
         lastMaterialPdf = sample.pdf;
         ray.Direction = shadingFrame.frameToWorld(sample.dirFs);

@@ -16,6 +16,9 @@ for v in "$@"; do
     ctx4tail128k) MSNE_WAVE_CONTEXTS=4 MSNE_TAIL_THRESHOLD=131072 $B 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
     nostage) MSNE_LIB=$PWD/moonshine_b200/libmoonshine_nostage.so $B 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
     lib_*) MSNE_LIB=$PWD/moonshine_b200/libmoonshine_${v#lib_}.so $B 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
+    cfg5) python bench.py --workload cfg5 --steps 3 --warmup 3 --batch-spp 8 --no-cpu-baseline 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
+    cfg5_*) MSNE_LIB=$PWD/moonshine_b200/libmoonshine_${v#cfg5_}.so python bench.py --workload cfg5 --steps 3 --warmup 3 --batch-spp 8 --no-cpu-baseline 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
+    cfg2) python bench.py --workload cfg2 --steps 6 --warmup 3 --no-cpu-baseline 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
     nosort) MSNE_SORT_THRESHOLD=0 $B 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
     tail8k) MSNE_TAIL_THRESHOLD=8192 $B 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
     tail128k) MSNE_TAIL_THRESHOLD=131072 $B 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
