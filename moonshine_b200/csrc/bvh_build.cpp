@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstring>
+#include <mutex>
 #include <thread>
 
 namespace msne {
@@ -72,7 +73,8 @@ struct Bins { Bounds box[3][kBins]; uint32_t n[3][kBins]; Bounds cent; };
 // top of the tree); the result is the same for any thread count (min / max / counts are order-independent, the partition is stable
 // per chunk and chunks are concatenated in order... except that item order INSIDE the two halves may differ, which never changes
 // a split: bins and bounds depend on the set, not the order).
-void splitRange(const BuildCtx& c, const Range& r, std::vector<BvhNode2>& nodes, std::vector<Range>& work, unsigned threads = 1, std::vector<uint32_t>* scratch = nullptr) {
+struct Split { uint32_t mid; Bounds box[2]; };
+Split splitRange(const BuildCtx& c, const Range& r, unsigned threads = 1, std::vector<uint32_t>* scratch = nullptr) {
     uint32_t* ord = c.order + r.first;
     // centroid bounds
     constexpr unsigned kMaxT = 16;
@@ -172,32 +174,26 @@ void splitRange(const BuildCtx& c, const Range& r, std::vector<BvhNode2>& nodes,
         mid = r.count / 2;  // all centroids coincide (or past the SAH depth cap): split by index
     }
     if (mid == 0 || mid == r.count) mid = r.count / 2;
+    Split out;
+    out.mid = mid;
     const uint32_t cnt[2] = {mid, r.count - mid};
     const uint32_t fst[2] = {r.first, r.first + mid};
     for (int s = 0; s < 2; s++) {
         Bounds bnd;
         if (boundsKnown) bnd = s == 0 ? bestL : bestR;
         else for (uint32_t i = 0; i < cnt[s]; i++) bnd.grow(c.boxes[c.order[fst[s] + i]].lo, c.boxes[c.order[fst[s] + i]].hi);
-        setChildBox(nodes[r.node], s, bnd);
-        if (cnt[s] <= c.maxLeaf) {
-            nodes[r.node].c[s] = (int32_t)fst[s];
-            nodes[r.node].c[2 + s] = (int32_t)cnt[s];
-        } else {
-            BvhNode2 child; std::memset(&child, 0, sizeof(child)); child.c[0] = child.c[1] = -1;
-            int32_t idx = (int32_t)nodes.size();
-            nodes.push_back(child);
-            nodes[r.node].c[s] = idx;
-            nodes[r.node].c[2 + s] = 0;
-            work.push_back({fst[s], cnt[s], idx, r.depth + 1});
-        }
+        out.box[s] = bnd;
     }
+    return out;
 }
 
 }  // namespace
 
-// Top-down build. The top of the tree is split on the calling thread until there are enough independent ranges; every such range
-// is then a subtree built by one of the worker threads into its own node array (ranges own disjoint slices of `order`), and the
-// subtrees are appended to the node array in range order - so the result does not depend on the number of threads.
+// Top-down build on all host cores. Nodes come from one pre-sized array through an atomic cursor; ranges are tasks in a shared
+// queue (a worker keeps small children on its own stack and shares big ones); the few ranges at the top that are too big to be
+// one task are split on the calling thread with the passes over their items spread over the workers. Which thread builds what is
+// timing dependent, so the node array is renumbered depth first at the end: the result (tree AND layout) does not depend on the
+// number of threads or on scheduling.
 void buildBvh2(const BuildBox* boxes, uint32_t n, uint32_t maxLeaf, BuiltBvh& out, uint32_t kMaxSahDepth) {
     out.nodes.clear();
     out.depth = 1;
@@ -213,12 +209,12 @@ void buildBvh2(const BuildBox* boxes, uint32_t n, uint32_t maxLeaf, BuiltBvh& ou
     padBox(out.bounds);
 
     // root is always an inner node; an empty child has c = -1, count = 0
-    BvhNode2 root;
-    std::memset(&root, 0, sizeof(root));
-    root.c[0] = root.c[1] = -1;
-    out.nodes.push_back(root);
-    if (n == 0) return;
+    BvhNode2 blank;
+    std::memset(&blank, 0, sizeof(blank));
+    blank.c[0] = blank.c[1] = -1;
     if (n <= maxLeaf) {
+        out.nodes.push_back(blank);
+        if (n == 0) return;
         Bounds b;
         for (uint32_t i = 0; i < n; i++) b.grow(boxes[i].lo, boxes[i].hi);
         setChildBox(out.nodes[0], 0, b);
@@ -226,58 +222,90 @@ void buildBvh2(const BuildBox* boxes, uint32_t n, uint32_t maxLeaf, BuiltBvh& ou
         return;
     }
     const BuildCtx ctx{boxes, cent.data(), out.order.data(), maxLeaf, kMaxSahDepth};
-    // ---- top of the tree, breadth first, until every open range is small enough to be one task -------------------------
-    constexpr uint32_t kParallelMin = 1u << 16;            // below this many items the whole build is one task
-    const uint32_t taskSize = std::max<uint32_t>(4096, n / 128);
-    std::vector<Range> open{{0, n, 0, 0}}, tasks;
-    if (n < kParallelMin) { tasks = open; open.clear(); }
-    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-    std::vector<uint32_t> scratch;
-    while (!open.empty()) {
-        std::vector<Range> next;
-        for (const Range& r : open) {
-            out.depth = std::max(out.depth, r.depth + 1);
-            std::vector<Range> kids;
-            splitRange(ctx, r, out.nodes, kids, hw, &scratch);
-            for (const Range& k : kids) (k.count <= taskSize ? tasks : next).push_back(k);
-        }
-        open.swap(next);
-    }
-    std::sort(tasks.begin(), tasks.end(), [](const Range& a, const Range& b) { return a.first < b.first; });
-    // ---- subtrees: one task each, local node arrays (local node 0 stands for the task's root in the main array) ------------
-    struct Sub { std::vector<BvhNode2> nodes; uint32_t depth = 0; };
-    std::vector<Sub> subs(tasks.size());
-    auto runTask = [&](size_t t) {
-        Sub& sub = subs[t];
-        sub.nodes.push_back(out.nodes[(size_t)tasks[t].node]);
-        std::vector<Range> work{{tasks[t].first, tasks[t].count, 0, tasks[t].depth}};
-        while (!work.empty()) {
-            const Range r = work.back(); work.pop_back();
-            sub.depth = std::max(sub.depth, r.depth + 1);
-            splitRange(ctx, r, sub.nodes, work);
+    std::vector<BvhNode2> nodes((size_t)n, blank);       // every inner node has >= 2 items below it: fewer than n nodes
+    std::atomic<uint32_t> nextNode{1};
+    std::atomic<uint32_t> maxDepth{1};
+    // wires the two halves of a split range into nodes[r.node]; inner children get a fresh node and are handed to `emit`
+    auto wire = [&](const Range& r, const Split& sp, auto&& emit) {
+        const uint32_t cnt[2] = {sp.mid, r.count - sp.mid}, fst[2] = {r.first, r.first + sp.mid};
+        for (int s = 0; s < 2; s++) {
+            setChildBox(nodes[(size_t)r.node], s, sp.box[s]);
+            if (cnt[s] <= maxLeaf) { nodes[(size_t)r.node].c[s] = (int32_t)fst[s]; nodes[(size_t)r.node].c[2 + s] = (int32_t)cnt[s]; }
+            else {
+                const int32_t idx = (int32_t)nextNode.fetch_add(1);
+                nodes[(size_t)r.node].c[s] = idx; nodes[(size_t)r.node].c[2 + s] = 0;
+                emit(Range{fst[s], cnt[s], idx, r.depth + 1});
+            }
         }
     };
-    const unsigned nThreads = (unsigned)std::min<size_t>(hw, tasks.size());
-    if (nThreads <= 1) for (size_t t = 0; t < tasks.size(); t++) runTask(t);
+    auto noteDepth = [&](uint32_t d) { uint32_t cur = maxDepth.load(std::memory_order_relaxed); while (d > cur && !maxDepth.compare_exchange_weak(cur, d)) {} };
+
+    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    constexpr uint32_t kBigRange = 1u << 18;             // ranges at least this big: passes over the items run on all threads
+    constexpr uint32_t kShare = 1u << 13;                // children at least this big go to the shared queue
+    std::vector<Range> queue;
+    {   // ---- top of the tree on the calling thread -------------------------------------------------------------------------------
+        std::vector<Range> big{{0, n, 0, 0}};
+        std::vector<uint32_t> scratch;
+        while (!big.empty()) {
+            const Range r = big.back(); big.pop_back();
+            noteDepth(r.depth + 1);
+            const Split sp = splitRange(ctx, r, hw, &scratch);
+            wire(r, sp, [&](const Range& k) { (hw > 1 && k.count >= kBigRange ? big : queue).push_back(k); });
+        }
+    }
+    // ---- everything below: a shared queue of ranges -----------------------------------------------------------------------------
+    std::mutex mtx;
+    std::atomic<int> busy{0};
+    auto worker = [&] {
+        std::vector<Range> local;
+        uint32_t deepest = 1;
+        for (;;) {
+            Range r;
+            {
+                std::lock_guard<std::mutex> g(mtx);
+                if (queue.empty()) { if (busy.load() == 0) break; else { } }
+                if (!queue.empty()) { r = queue.back(); queue.pop_back(); busy.fetch_add(1); local.push_back(r); }
+            }
+            if (local.empty()) { std::this_thread::yield(); continue; }
+            while (!local.empty()) {
+                const Range cur = local.back(); local.pop_back();
+                deepest = std::max(deepest, cur.depth + 1);
+                const Split sp = splitRange(ctx, cur);
+                wire(cur, sp, [&](const Range& k) {
+                    if (hw > 1 && k.count >= kShare) { std::lock_guard<std::mutex> g(mtx); queue.push_back(k); }
+                    else local.push_back(k);
+                });
+            }
+            busy.fetch_sub(1);
+        }
+        noteDepth(deepest);
+    };
+    if (hw <= 1 || n < (1u << 15)) worker();
     else {
-        std::atomic<size_t> nextTask{0};
         std::vector<std::thread> pool;
-        for (unsigned w = 0; w < nThreads; w++)
-            pool.emplace_back([&] { for (;;) { const size_t t = nextTask.fetch_add(1); if (t >= tasks.size()) break; runTask(t); } });
+        for (unsigned w = 1; w < hw; w++) pool.emplace_back(worker);
+        worker();
         for (auto& th : pool) th.join();
     }
-    // ---- stitch: local node k >= 1 of task t becomes main node base_t + k - 1 -------------------------------------------------
-    for (size_t t = 0; t < tasks.size(); t++) {
-        const Sub& sub = subs[t];
-        const int32_t base = (int32_t)out.nodes.size();
-        auto remap = [&](BvhNode2 nd) {
-            for (int s = 0; s < 2; s++) if (nd.c[2 + s] == 0 && nd.c[s] >= 1) nd.c[s] = base + nd.c[s] - 1;
-            return nd;
-        };
-        out.nodes[(size_t)tasks[t].node] = remap(sub.nodes[0]);
-        for (size_t k = 1; k < sub.nodes.size(); k++) out.nodes.push_back(remap(sub.nodes[k]));
-        out.depth = std::max(out.depth, sub.depth);
+    // ---- depth-first renumbering (deterministic layout; a node's first child follows it) --------------------------------------------
+    const uint32_t used = nextNode.load();
+    out.nodes.resize(used);
+    std::vector<uint32_t> newOf(used, 0), stack{0};
+    uint32_t counter = 0;
+    std::vector<uint32_t> orderDfs; orderDfs.reserve(used);
+    while (!stack.empty()) {
+        const uint32_t k = stack.back(); stack.pop_back();
+        newOf[k] = counter++; orderDfs.push_back(k);
+        const BvhNode2& nd = nodes[k];
+        for (int s = 1; s >= 0; s--) if (nd.c[2 + s] == 0 && nd.c[s] >= 0) stack.push_back((uint32_t)nd.c[s]);
     }
+    for (uint32_t i = 0; i < used; i++) {
+        BvhNode2 nd = nodes[orderDfs[i]];
+        for (int s = 0; s < 2; s++) if (nd.c[2 + s] == 0 && nd.c[s] >= 0) nd.c[s] = (int32_t)newOf[(uint32_t)nd.c[s]];
+        out.nodes[i] = nd;
+    }
+    out.depth = maxDepth.load();
 }
 
 void reorderTopBfs(BuiltBvh& bvh, uint32_t k) {
