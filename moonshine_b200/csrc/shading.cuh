@@ -220,7 +220,31 @@ DI float microfacetPdf(const MaterialParams& m, float3 w_i, float3 w_o) {       
 DI float pbrPdf(const MaterialParams& m, float3 w_i, float3 w_o) {                        // :240-249
     return lerp1(lambertPdf(w_i, w_o), microfacetPdf(m, w_i, w_o), m.pSpec);
 }
+#ifndef MSNE_PBR_EVAL_NOINLINE
+#define MSNE_PBR_EVAL_NOINLINE 0   // measurement variant: StandardPBR::eval (three call sites per hit) out of line
+#endif
+// scalar arguments / return in registers (no struct through local memory)
+#if MSNE_PBR_EVAL_NOINLINE
+__device__ __noinline__
+#else
+DI
+#endif
+float3 pbrEvalImpl(float cr, float cg, float cb, float metalness, float alpha, float ior, float dr, float dg, float db, float lambdaO,
+                   float wix, float wiy, float wiz, float wox, float woy, float woz);
 DI float3 pbrEval(const MaterialParams& m, float3 w_i, float3 w_o) {                      // :251-266
+    return pbrEvalImpl(m.color.x, m.color.y, m.color.z, m.metalness, m.alpha, m.ior, m.diffuse.x, m.diffuse.y, m.diffuse.z, m.lambdaO,
+                       w_i.x, w_i.y, w_i.z, w_o.x, w_o.y, w_o.z);
+}
+#if MSNE_PBR_EVAL_NOINLINE
+__device__ __noinline__
+#else
+DI
+#endif
+float3 pbrEvalImpl(float cr, float cg, float cb, float metalness, float alpha, float ior, float dr, float dg, float db, float lambdaO,
+                   float wix, float wiy, float wiz, float wox, float woy, float woz) {
+    MaterialParams m;
+    m.color = mk3(cr, cg, cb); m.metalness = metalness; m.alpha = alpha; m.ior = ior; m.diffuse = mk3(dr, dg, db); m.lambdaO = lambdaO;
+    const float3 w_i = mk3(wix, wiy, wiz), w_o = mk3(wox, woy, woz);
     const float3 h = normalize(w_i + w_o);
     const float fD = fresnelDielectric(dot(w_i, h), MS_AIR_IOR, m.ior);
     const float3 fMetallic = schlick3(dot(w_i, h), m.color);

@@ -33,13 +33,18 @@ struct HitRec { uint32_t inst, tri; float u, v; };
 #ifndef MSNE_SLAB_EPS
 #define MSNE_SLAB_EPS 4e-7f   // measurement variants only; 0 makes the slab test unsafe for far / axis-parallel rays
 #endif
+#ifndef MSNE_SLAB_SUB
+#define MSNE_SLAB_SUB 0   // 1: slab distances as (plane - o) * idir (two instructions per plane, relative error only, no margin constants)
+#endif
 #ifndef MSNE_TRI_FALLBACK_INLINE
 #define MSNE_TRI_FALLBACK_INLINE 0
 #endif
 
 struct SpaceRay {
     float3 o, idir;
+#if !MSNE_SLAB_SUB
     float3 oodLo, oodHi;   // o * idir, pushed outwards per axis: subtracted from lo * idir / hi * idir respectively (slab)
+#endif
     float Sx, Sy, Sz;      // shear of the ray onto its dominant axis (triTest)
     uint32_t k;            // kx | ky << 2 | kz << 4: the axis permutation of that shear
     DI void set(float3 o_, float3 d) {
@@ -52,11 +57,13 @@ struct SpaceRay {
         // the box. Each axis therefore carries its own margin (MSNE_SLAB_EPS ~ 7 ulp of |o * idir|), applied outwards: the plane the
         // ray enters through moves towards the ray, the one it leaves through away from it. No box is skipped that holds a triangle
         // the ray passes through - traversal finds what testing every triangle would find - and the margin costs no instruction.
+#if !MSNE_SLAB_SUB
         const float3 ood = mk3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
         const float3 e = mk3(MSNE_SLAB_EPS * fabsf(ood.x), MSNE_SLAB_EPS * fabsf(ood.y), MSNE_SLAB_EPS * fabsf(ood.z));
         // idir > 0: lo is the entry plane (distance must not come out too late: subtract MORE), hi the exit plane (subtract LESS)
         oodLo = mk3(idir.x > 0.0f ? ood.x + e.x : ood.x - e.x, idir.y > 0.0f ? ood.y + e.y : ood.y - e.y, idir.z > 0.0f ? ood.z + e.z : ood.z - e.z);
         oodHi = mk3(idir.x > 0.0f ? ood.x - e.x : ood.x + e.x, idir.y > 0.0f ? ood.y - e.y : ood.y + e.y, idir.z > 0.0f ? ood.z - e.z : ood.z + e.z);
+#endif
         // dominant axis kz, the other two in cyclic order, swapped when d[kz] < 0 so that the winding is preserved
         const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
         const uint32_t kz = ax > ay ? (ax > az ? 0u : 2u) : (ay > az ? 1u : 2u);
@@ -71,9 +78,15 @@ struct SpaceRay {
 
 // returns true when the child's box overlaps [tmin, tmax] along the ray (conservative)
 DI bool slab(const SpaceRay& r, float lox, float hix, float loy, float hiy, float loz, float hiz, float tmin, float tmax, float& tnear) {
+#if MSNE_SLAB_SUB
+    const float tx0 = (lox - r.o.x) * r.idir.x, tx1 = (hix - r.o.x) * r.idir.x;
+    const float ty0 = (loy - r.o.y) * r.idir.y, ty1 = (hiy - r.o.y) * r.idir.y;
+    const float tz0 = (loz - r.o.z) * r.idir.z, tz1 = (hiz - r.o.z) * r.idir.z;
+#else
     const float tx0 = fmaf(lox, r.idir.x, -r.oodLo.x), tx1 = fmaf(hix, r.idir.x, -r.oodHi.x);
     const float ty0 = fmaf(loy, r.idir.y, -r.oodLo.y), ty1 = fmaf(hiy, r.idir.y, -r.oodHi.y);
     const float tz0 = fmaf(loz, r.idir.z, -r.oodLo.z), tz1 = fmaf(hiz, r.idir.z, -r.oodHi.z);
+#endif
     tnear = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), tmin));
     const float tfar = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), tmax));
     return tnear <= tfar * 1.0000004f;

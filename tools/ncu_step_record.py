@@ -6,7 +6,7 @@ launch population):
     MSNE_WAVE_CONTEXTS=1 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_bytes.sum,\\
 smsp__thread_inst_executed_per_inst_executed.ratio,smsp__issue_active.avg.pct_of_peak_sustained_active,smsp__inst_executed.sum \\
         --clock-control none --csv --log-file gpurun_out/step_metrics.csv python tools/profile_step.py step 2
-    python tools/ncu_step_record.py gpurun_out/step_metrics.csv profiles/trace_kernel_traffic.json profiles/r02_step_kernels.txt
+    python tools/ncu_step_record.py gpurun_out/step_metrics.csv profiles/trace_kernel_traffic.json profiles/r02_step_kernels.txt profiles/r02_step_launches.csv
 
 The first step in the list is the warm-up (it learns the survival profile); the record is taken from the LAST k_generate onwards."""
 import collections
@@ -26,12 +26,19 @@ def load(path):
     return list(per.values())
 
 
-def main(path, out_json, out_txt=None):
+def main(path, out_json, out_txt=None, out_csv=None):
     launches = load(path)
     # one step = from the generate of its first wave; the step of interest is the last complete one: find the k_generate launches and
     # keep everything from the (n_waves_per_step)-th last onwards - with one context a 64-spp step is a single wave
     gens = [i for i, d in enumerate(launches) if d["kernel"].startswith("k_generate")]
     step = launches[gens[-1]:]
+    if out_csv:   # compact per-launch list of the step (the raw ncu csv is ~1 MB): what every figure below is computed from
+        with open(out_csv, "w") as f:
+            f.write("launch,kernel,time_ns,dram_read_bytes,dram_write_bytes,l2_bytes,warp_inst,lanes_per_inst,issue_active_pct\n")
+            for i, d in enumerate(step):
+                f.write(f"{i},{d['kernel'].replace(',', ';')},{d.get('gpu__time_duration.sum', 0):.0f},{d.get('dram__bytes_read.sum', 0):.0f},"
+                        f"{d.get('dram__bytes_write.sum', 0):.0f},{d.get('lts__t_bytes.sum', 0):.0f},{d.get('smsp__inst_executed.sum', 0):.0f},"
+                        f"{d.get('smsp__thread_inst_executed_per_inst_executed.ratio', 0):.3f},{d.get('smsp__issue_active.avg.pct_of_peak_sustained_active', 0):.2f}\n")
     agg = collections.OrderedDict()
     for d in step:
         a = agg.setdefault(d["kernel"], collections.Counter())
@@ -65,11 +72,11 @@ def main(path, out_json, out_txt=None):
                "l2": {"bytes_per_launch": tr["l2"] / tr["launches"], "gb_per_s_under_ncu": tr["l2"] / 1e9 / (tr["ms"] / 1e3)},
                "simt": {"lanes_per_inst": tr["lane_inst"] / max(tr["inst"], 1), "issue_active_pct": tr["issue_w"] / max(tr["ns"], 1)},
                "step_dram_bytes": sum(a["dram"] for a in agg.values()),
-               "source": path, "regenerate": "tools/ncu_step_record.py (see its docstring for the ncu command)",
+               "source": out_csv or path, "regenerate": "tools/ncu_step_record.py (see its docstring for the ncu command)",
                "note": "every k_trace launch of one 64-spp step (one 128 Mi-path wave, one wave in flight): the same launch population bench.py averages `achieved` over"}
         json.dump(rec, open(out_json, "w"), indent=1)
         print("wrote", out_json)
 
 
 if __name__ == "__main__":
-    main(*sys.argv[1:4])
+    main(*sys.argv[1:5])
