@@ -221,7 +221,11 @@ def main():
         # the product's own multi-GPU path: the library holds the NCCL communicator (HdMoonshineExtCommInit shards the pixel tiles by
         # rank; HdMoonshineRender / CommReduceSensor end with one ncclReduce of the frame to rank 0). torch.distributed is only the
         # harness plumbing here (barrier, max/sum of the timings).
-        m.CommInit(hydra.exchange_unique_id(rank, world, "bench_" + os.environ.get("MASTER_PORT", "0")), rank, world)
+        uid = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local_rank}")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(hydra.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, src=0)   # the 128-byte NCCL id reaches the other ranks over the harness's own process group
+        m.CommInit(bytes(uid.cpu().numpy().tobytes()), rank, world)
     sensor, lens = m.CreateSensor(W, H), m.CreateLens(scene.lens)
     batch = args.batch_spp * world
 

@@ -446,10 +446,12 @@ def comm_unique_id() -> bytes:
 
 def exchange_unique_id(rank: int, world: int, tag: str, timeout_s: float = 120.0) -> bytes:
     """File rendezvous for the NCCL id between the ranks of ONE node (no torch, no MPI): rank 0 writes, the others poll.
-    `tag` must be the same on every rank and unique per job (e.g. MASTER_PORT)."""
+    `tag` must be the same on every rank and unique per job; the parent process id is appended (the ranks of one launcher -
+    torchrun or `offline --gpus N` - share it), so a file left behind by an earlier job on the same port is never picked up.
+    Rank 0 should call `retire_unique_id` once every rank has joined (CommInit is collective)."""
     import tempfile
     import time
-    path = os.path.join(tempfile.gettempdir(), f"msne_nccl_id_{tag}")
+    path = os.path.join(tempfile.gettempdir(), f"msne_nccl_id_{tag}_{os.getppid()}")
     if rank == 0:
         uid = comm_unique_id()
         with open(path + ".tmp", "wb") as f:
@@ -462,6 +464,14 @@ def exchange_unique_id(rank: int, world: int, tag: str, timeout_s: float = 120.0
             return open(path, "rb").read()
         time.sleep(0.02)
     raise RuntimeError(f"rank {rank}: no NCCL id from rank 0 at {path}")
+
+
+def retire_unique_id(tag: str) -> None:
+    import tempfile
+    try:
+        os.remove(os.path.join(tempfile.gettempdir(), f"msne_nccl_id_{tag}_{os.getppid()}"))
+    except OSError:
+        pass
 
 
 def render_scene(scene, n_launches: int = 1, device: int = 0, paths_in_flight: Optional[int] = None, shard=None, ray_sorting: Optional[int] = None,

@@ -462,7 +462,10 @@ def main(argv: Optional[List[str]] = None) -> int:
     m = hydra.HdMoonshine(device)
     S.load_scene(m, scene)
     if world > 1:
-        m.CommInit(hydra.exchange_unique_id(rank, world, os.environ.get("MSNE_JOB_TAG", os.environ.get("MASTER_PORT", "0"))), rank, world)
+        tag = os.environ.get("MSNE_JOB_TAG", os.environ.get("MASTER_PORT", "0"))
+        m.CommInit(hydra.exchange_unique_id(rank, world, tag), rank, world)
+        if rank == 0:
+            hydra.retire_unique_id(tag)      # CommInit is collective: every rank has read the id by now
     sensor, lens = m.CreateSensor(*extent), m.CreateLens(scene.lens)
     if rank == 0:
         print(f"{time.perf_counter() - t0:.3f} seconds to load world")

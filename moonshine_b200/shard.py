@@ -54,6 +54,8 @@ def init_comm(m, rank: int = None, world: int = None, tag: str = None):
     if world > 1:
         tag = tag or os.environ.get("MSNE_JOB_TAG", os.environ.get("MASTER_PORT", "0"))
         m.CommInit(hydra.exchange_unique_id(rank, world, tag), rank, world)
+        if rank == 0:
+            hydra.retire_unique_id(tag)
     return rank, world
 
 
