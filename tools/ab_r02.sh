@@ -19,6 +19,7 @@ for v in "$@"; do
     cfg5) python bench.py --workload cfg5 --steps 3 --warmup 3 --batch-spp 8 --no-cpu-baseline 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
     cfg5_*) MSNE_LIB=$PWD/moonshine_b200/libmoonshine_${v#cfg5_}.so python bench.py --workload cfg5 --steps 3 --warmup 3 --batch-spp 8 --no-cpu-baseline 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
     cfg2) python bench.py --workload cfg2 --steps 6 --warmup 3 --no-cpu-baseline 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
+    leaf*) MSNE_MAX_LEAF=${v#leaf} $B 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
     nosort) MSNE_SORT_THRESHOLD=0 $B 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
     tail8k) MSNE_TAIL_THRESHOLD=8192 $B 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
     tail128k) MSNE_TAIL_THRESHOLD=131072 $B 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
