@@ -100,23 +100,27 @@ struct Bvh {
     }
 };
 
-// Conservative slab test evaluated in double precision. The boxes bound the triangles geometrically, but the FP32 triangle test
-// (tri_test, the definition of a hit) accepts rays within a few ulp of |o| of an edge and reports t with a few ulp of error, so
-// the comparison is widened relatively (1e-6) and absolutely (1e-6 of the largest |o / d|, the scale of those errors in t):
-// the walk then returns exactly what testing every triangle returns (`brute`), which is what "closest hit" means here.
-inline bool ray_box(const AABB& b, const double o[3], const double inv[3], double tmax) {
+// Conservative slab test evaluated in double precision. The boxes bound the triangles geometrically, but the triangle test
+// (tri_test, the definition of a hit) works on vertices translated by o in binary32, i.e. on geometry moved by up to an ulp of
+// |v - o|, and reports t with a few ulp of error: every axis' interval is widened by 1e-6 of |o / d| on that axis (the scale of
+// those errors in t) and the comparison relatively by 1e-6. The walk then returns exactly what testing every triangle returns
+// (`brute`, cross-check mode), which is what "closest hit" means here.
+struct RayBoxEps { double e[3]; };
+inline RayBoxEps ray_box_eps(const double o[3], const double inv[3]) {
+    RayBoxEps r;
+    for (int a = 0; a < 3; a++) { const double m = std::fabs(o[a] * inv[a]); r.e[a] = (m == m && m < 1e300) ? m * 1e-6 : 0.0; }
+    return r;
+}
+inline bool ray_box(const AABB& b, const double o[3], const double inv[3], double tmax, const RayBoxEps& eps) {
     double t0 = 0.0, t1 = tmax;
-    double eps = 0.0;
-    for (int a = 0; a < 3; a++) { const double m = std::fabs(o[a] * inv[a]); if (m == m && m < 1e300 && m > eps) eps = m; }
-    eps *= 1e-6;
     const float lo[3] = {b.lo.x, b.lo.y, b.lo.z}, hi[3] = {b.hi.x, b.hi.y, b.hi.z};
     for (int a = 0; a < 3; a++) {
         double ta = (lo[a] - o[a]) * inv[a], tb = (hi[a] - o[a]) * inv[a];
         if (ta != ta || tb != tb) continue;  // 0*inf: origin on the slab plane, direction parallel -> no constraint
         if (ta > tb) std::swap(ta, tb);
-        t0 = std::max(t0, ta); t1 = std::min(t1, tb);
+        t0 = std::max(t0, ta - eps.e[a]); t1 = std::min(t1, tb + eps.e[a]);
     }
-    return t0 <= t1 * 1.000001 + eps + 1e-30;
+    return t0 <= t1 * 1.000001 + 1e-30;
 }
 
 struct Blas {
@@ -141,8 +145,7 @@ inline RayShear ray_shear(float3 d) {
     r.Sx = dv[r.kx] / dv[r.kz]; r.Sy = dv[r.ky] / dv[r.kz]; r.Sz = 1.0f / dv[r.kz];
     return r;
 }
-inline bool tri_test(const Tri& tr, float3 o, float3 d, float tmin, float tmax, float& t, float& u, float& v) {
-    const RayShear r = ray_shear(d);
+inline bool tri_test(const Tri& tr, float3 o, const RayShear& r, float tmin, float tmax, float& t, float& u, float& v) {
     const float3 A3 = tr.v0 - o, B3 = tr.v1 - o, C3 = tr.v2 - o;
     const float A[3] = {A3.x, A3.y, A3.z}, B[3] = {B3.x, B3.y, B3.z}, C[3] = {C3.x, C3.y, C3.z};
     const float Ax = A[r.kx] - r.Sx * A[r.kz], Ay = A[r.ky] - r.Sy * A[r.kz];
@@ -226,10 +229,10 @@ struct Accel {
     Intersection traceImpl(float3 o, float3 d, float tmin, float tmax, bool anyHit, bool brute) const {
         Intersection best; best.instanceIndex = MAX_UINT; best.geometryIndex = best.primitiveIndex = 0; best.barycentrics = {0, 0};
         float bestT = tmax;
-        auto consider = [&](uint32_t inst, const Tri& tr, float3 oo, float3 od) -> bool {
+        auto consider = [&](uint32_t inst, const Tri& tr, float3 oo, const RayShear& shear) -> bool {
             float t, u, v;
             // closest: accept t <= bestT so ties can be resolved by id; any: plain interval test
-            if (!tri_test(tr, oo, od, tmin, tmax, t, u, v)) return false;
+            if (!tri_test(tr, oo, shear, tmin, tmax, t, u, v)) return false;
             if (anyHit) { best.instanceIndex = inst; return true; }
             bool better = t < bestT;
             if (!better && t == bestT && best.instanceIndex != MAX_UINT) {
@@ -244,19 +247,21 @@ struct Accel {
             const InstanceRec& in = (*instances)[inst];
             const Blas& b = blases[instanceBlas[inst]];
             float3 oo = mul_point(in.worldToInstance, o), od = mul_vec(in.worldToInstance, d);
+            const RayShear shear = ray_shear(od);      // once per object-space ray
             if (brute) {
-                for (const Tri& tr : b.tris) if (consider(inst, tr, oo, od)) return true;
+                for (const Tri& tr : b.tris) if (consider(inst, tr, oo, shear)) return true;
                 return false;
             }
             const double O[3] = {oo.x, oo.y, oo.z};
             const double I[3] = {1.0 / (double)od.x, 1.0 / (double)od.y, 1.0 / (double)od.z};
+            const RayBoxEps eps = ray_box_eps(O, I);
             int stack[128]; int sp = 0; stack[sp++] = 0;
             while (sp) {
                 const BvhNode& n = b.bvh.nodes[stack[--sp]];
-                if (!ray_box(n.box, O, I, (double)bestT)) continue;
+                if (!ray_box(n.box, O, I, (double)bestT, eps)) continue;
                 if (n.count) {
                     for (uint32_t i = n.first; i < n.first + n.count; i++)
-                        if (consider(inst, b.tris[b.bvh.order[i]], oo, od)) return true;
+                        if (consider(inst, b.tris[b.bvh.order[i]], oo, shear)) return true;
                 } else { stack[sp++] = n.left; stack[sp++] = n.right; }
             }
             return false;
@@ -269,10 +274,11 @@ struct Accel {
         if (tlas.nodes.empty()) return best;
         const double O[3] = {o.x, o.y, o.z};
         const double I[3] = {1.0 / (double)d.x, 1.0 / (double)d.y, 1.0 / (double)d.z};
+        const RayBoxEps eps = ray_box_eps(O, I);
         int stack[128]; int sp = 0; stack[sp++] = 0;
         while (sp) {
             const BvhNode& n = tlas.nodes[stack[--sp]];
-            if (!ray_box(n.box, O, I, (double)bestT)) continue;
+            if (!ray_box(n.box, O, I, (double)bestT, eps)) continue;
             if (n.count) {
                 for (uint32_t i = n.first; i < n.first + n.count; i++)
                     if (traceInstance(tlasItems[tlas.order[i]])) return best;
