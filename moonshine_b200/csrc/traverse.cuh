@@ -5,7 +5,7 @@
 // reference behaviour and is stated in DESIGN.md §"Intersection"; the CPU oracle implements the same
 // definition independently (oracle/bvh.h):
 //   object-space ray   o' = mulPoint(w2o, o), d' = mulVec(w2o, d)   (t shared between spaces)
-//   kz = dominant axis of d, (kx, ky) the other two in cyclic order (swapped if d[kz] < 0); Sx=d[kx]/d[kz], Sy=d[ky]/d[kz], Sz=1/d[kz]
+//   kz = dominant axis of d, (kx, ky) the other two in cyclic order (swapped if d[kz] < 0); Sz=1/d[kz], Sx=d[kx]*Sz, Sy=d[ky]*Sz
 //   A=v0-o, B=v1-o, C=v2-o;  Ax=A[kx]-Sx*A[kz], Ay=A[ky]-Sy*A[kz] (same for B, C);  Az=Sz*A[kz] ...
 //   U=Cx*By-Cy*Bx, V=Ax*Cy-Ay*Cx, W=Bx*Ay-By*Ax; any |value| <= 2^-22 (|p|+|q|) of its two products -> U, V, W, u, v, t are
 //   recomputed in binary64 (exact products, exact sign of the difference): signs are the EXACT signs of the 2-D edge functions
@@ -35,6 +35,9 @@ struct HitRec { uint32_t inst, tri; float u, v; };
 #endif
 #ifndef MSNE_SLAB_SUB
 #define MSNE_SLAB_SUB 0   // 1: slab distances as (plane - o) * idir (two instructions per plane, relative error only, no margin constants)
+#endif
+#ifndef MSNE_STASH_WORLD_RAY
+#define MSNE_STASH_WORLD_RAY 0   // measurement variant: keep the world-space ray constants instead of recomputing them on leaving an instance
 #endif
 #ifndef MSNE_TRI_FALLBACK_INLINE
 #define MSNE_TRI_FALLBACK_INLINE 0
@@ -71,7 +74,7 @@ struct SpaceRay {
         const float dz = kz == 0u ? d.x : (kz == 1u ? d.y : d.z);
         if (dz < 0.0f) { const uint32_t tmp = kx; kx = ky; ky = tmp; }
         const float dx = kx == 0u ? d.x : (kx == 1u ? d.y : d.z), dy = ky == 0u ? d.x : (ky == 1u ? d.y : d.z);
-        Sx = dx / dz; Sy = dy / dz; Sz = 1.0f / dz;
+        Sz = 1.0f / dz; Sx = dx * Sz; Sy = dy * Sz;   // one division: set() runs at every instance entry and exit of the two-level walk
         k = kx | (ky << 2) | (kz << 4);
     }
 };
@@ -153,6 +156,9 @@ DI bool traceRay(const DeviceScene& sc, const float3 o, const float3 d, const fl
     int sp = 0;
     stack[sp++] = REF_END;
     SpaceRay ray; ray.set(o, d);
+#if MSNE_STASH_WORLD_RAY
+    const SpaceRay worldRay = ray;   // two-level: restored when the walk leaves an instance (the compiler keeps it in local memory)
+#endif
     const BvhNode2* nodes = TWO_LEVEL ? sc.tlasNodes : sc.blasNodes;
     uint32_t curInst = TWO_LEVEL ? MISS_ID : STATIC_INST;
     int node = TWO_LEVEL ? 0 : (int)sc.staticRoot;   // current reference (dtypes.h): inner node, leaf (<0), TLAS item, or sentinel
@@ -206,7 +212,12 @@ DI bool traceRay(const DeviceScene& sc, const float3 o, const float3 d, const fl
         // ---- level changes (rare relative to node steps) -----------------------------------------------------------
         if (TWO_LEVEL && (uint32_t)node >= (uint32_t)REF_ITEM && node != REF_END) {
             if (node == REF_LEAVE) {
-                ray.set(o, d); nodes = sc.tlasNodes; curInst = MISS_ID;
+#if MSNE_STASH_WORLD_RAY
+                ray = worldRay;
+#else
+                ray.set(o, d);
+#endif
+                nodes = sc.tlasNodes; curInst = MISS_ID;
                 node = stack[--sp];
             } else if (node == REF_EMPTY) {
                 // only reachable from the probes (caller-supplied tmax / direction scale can make the slab test accept the

@@ -142,7 +142,7 @@ inline RayShear ray_shear(float3 d) {
     r.kx = r.kz == 2u ? 0u : r.kz + 1u; r.ky = r.kx == 2u ? 0u : r.kx + 1u;
     const float dv[3] = {d.x, d.y, d.z};
     if (dv[r.kz] < 0.0f) std::swap(r.kx, r.ky);
-    r.Sx = dv[r.kx] / dv[r.kz]; r.Sy = dv[r.ky] / dv[r.kz]; r.Sz = 1.0f / dv[r.kz];
+    r.Sz = 1.0f / dv[r.kz]; r.Sx = dv[r.kx] * r.Sz; r.Sy = dv[r.ky] * r.Sz;
     return r;
 }
 inline bool tri_test(const Tri& tr, float3 o, const RayShear& r, float tmin, float tmax, float& t, float& u, float& v) {
