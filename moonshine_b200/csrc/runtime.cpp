@@ -317,6 +317,13 @@ struct HdMoonshine {
     bool sortActive = false;         // decided per render (renderLaunches)
     SortFrame sortFrame{};           // scene bounds for the origin cells (buildTlas)
     cudaEvent_t evStart = nullptr, evStop = nullptr, evAccum[kWaveContexts]{};
+    // Waves may still be in flight when HdMoonshineExtRenderLaunches returns (the offline loop records all its launches and waits
+    // once, offline/main.zig:131-194): `timelineOpen` from the first enqueue until finishWaves(), which every other entry point
+    // calls first. Consecutive calls keep alternating the contexts and chaining the accumulates, so the last wave of one call
+    // overlaps the first of the next.
+    bool timelineOpen = false;
+    uint64_t waveSerial = 0;
+    cudaEvent_t lastAccumEvent = nullptr;
     int traceBlocks = 0, shadeBlocks = 0, shadeInlineBlocks = 0;
     uint32_t maxLeaf = 3;   // triangles per BVH leaf (<= 8: 3-bit count in the leaf reference); 2-3 measured best
     uint64_t tailThreshold = 32768;   // once fewer paths than this are expected to survive, k_tail finishes the wave
@@ -728,6 +735,10 @@ struct HdMoonshine {
         }
     }
 
+    bool sceneDirty() const {
+        return tablesDirty || geomDirty || tlasDirty || aliasDirty || !dirtyInstances.empty() || (emitterFollowsEdits && emitterStale) ||
+               emitterRecIndexed != (consts.indexed_attributes != 0);
+    }
     void syncScene() {
         if (tablesDirty) {
             std::vector<DMesh> dm(meshes.size());
@@ -914,6 +925,7 @@ struct HdMoonshine {
     void ensurePool(WaveCtx& c, uint64_t wanted) {
         const uint32_t P = (uint32_t)std::min<uint64_t>(wanted, 0x7FFFFFFFull / 4);
         if (c.pb.capacity >= P && c.pb.capacity != 0) return;
+        finishWaves();
         // poolBufs: [0],[1] interleaved ray lanes R0/R1 of the two ping-pong buffers (dtypes.h RAY_STRIDE), [2..9] S0,S1,N0,N1 x 2,
         // [10] interleaved shadow-ray lanes Q0/Q1 (2 P rays), [11] result
         CK(cudaStreamSynchronize(c.stream));
@@ -936,6 +948,7 @@ struct HdMoonshine {
     void ensureSortBuffers(WaveCtx& c) {
         const size_t P = c.pb.capacity;
         if (c.sortKeysExt.n >= P) return;
+        finishWaves();
         c.sortKeysExt.alloc(P); c.sortKeysShadow.alloc(2 * P);
         c.sortPermExt.alloc(P); c.sortPermShadow.alloc(2 * P);
         c.sortBlockHist.ensure((size_t)2 * smCount * 32768);
@@ -1047,15 +1060,16 @@ struct HdMoonshine {
     }
 
     // offline/main.zig:131-165: n launches of samples_per_run samples each; sensor.sample_count advances
-    void renderLaunches(Sensor& s, const Lens& lens, uint32_t nLaunches) {
+    void renderLaunches(Sensor& s, const Lens& lens, uint32_t nLaunches, bool wait) {
         use();
+        if (sceneDirty() || s.shardRank != shardRank || s.shardWorld != shardWorld || s.pixIds.p == nullptr) finishWaves();   // uploads must not race the waves
         if (s.shardRank != shardRank || s.shardWorld != shardWorld || s.pixIds.p == nullptr) { buildPixIds(s); clearSensor(s); }
         syncScene();
         const DeviceScene sc = deviceScene();
         const DConstants k = deviceConstants();
         const DCamera cam = makeCamera(lens, s.extent.width, s.extent.height);
         const uint64_t totalSamples = (uint64_t)nLaunches * k.samples_per_run;
-        if (s.nPix == 0 || totalSamples == 0) { s.sample_count += (uint32_t)totalSamples; return; }
+        if (s.nPix == 0 || totalSamples == 0) { s.sample_count += (uint32_t)totalSamples; if (wait) finishWaves(); return; }
         const uint64_t totalPaths = (uint64_t)s.nPix * totalSamples;
         // pool per context: half of the paths in flight; a render that fits one context uses only that one
         const int nCtx = waveContextsInUse;
@@ -1076,33 +1090,47 @@ struct HdMoonshine {
         sortActive = sortThreshold != 0 && P >= sortThreshold && (sortAnyScene || bvhNodes >= kSortMinNodes);
         if (sortActive) for (int i = 0; i < used; i++) ensureSortBuffers(ctx[i]);
         // everything queued on the main stream so far (uploads, sensor clears) precedes the waves; the waves' streams start at evStart
-        CK(cudaEventRecord(evStart, stream));
-        for (int i = 0; i < used; i++) CK(cudaStreamWaitEvent(ctx[i].stream, evStart, 0));
-        uint64_t wave = 0;
-        cudaEvent_t lastAccum = nullptr;
+        if (!timelineOpen) {
+            CK(cudaEventRecord(evStart, stream));
+            for (WaveCtx& c : ctx) CK(cudaStreamWaitEvent(c.stream, evStart, 0));
+            timelineOpen = true;
+            lastAccumEvent = nullptr;
+        }
         for (uint32_t p0 = 0; p0 < s.nPix; p0 += pixChunk) {
             const uint32_t np = std::min(pixChunk, s.nPix - p0);
             for (uint64_t s0 = 0; s0 < totalSamples; s0 += samplesPerWave) {
                 const uint32_t ns = (uint32_t)std::min<uint64_t>(samplesPerWave, totalSamples - s0);
-                WaveCtx& c = ctx[wave % (uint64_t)used];
+                WaveCtx& c = ctx[waveSerial % (uint64_t)used];
                 harvest(c);   // the wave before last: its log feeds this wave's schedule while the last one keeps the GPU busy
-                enqueueWave(c, s, cam, sc, k, p0, np, s.sample_count + (uint32_t)s0, ns, lastAccum);
-                cudaEvent_t ev = evAccum[wave % (uint64_t)kWaveContexts];
+                enqueueWave(c, s, cam, sc, k, p0, np, s.sample_count + (uint32_t)s0, ns, lastAccumEvent);
+                cudaEvent_t ev = evAccum[waveSerial % (uint64_t)kWaveContexts];
                 CK(cudaEventRecord(ev, c.stream));
-                lastAccum = ev;
-                wave++;
+                lastAccumEvent = ev;
+                waveSerial++;
             }
         }
-        for (int i = 0; i < used; i++) CK(cudaStreamWaitEvent(stream, ctx[i].evDone, 0));
+        stats.samples += totalPaths;
+        s.sample_count += (uint32_t)totalSamples;
+        if (wait) finishWaves();
+    }
+
+    // waits for every wave in flight, reads their logs, closes the device-time interval opened by the first enqueue
+    void finishWaves() {
+        if (!timelineOpen) return;
+        use();
+        for (WaveCtx& c : ctx) if (c.pending) CK(cudaStreamWaitEvent(stream, c.evDone, 0));
         CK(cudaEventRecord(evStop, stream));
         CK(cudaStreamSynchronize(stream));
         stats.host_syncs++;
-        for (int i = 0; i < used; i++) harvest(ctx[i]);
+        for (WaveCtx& c : ctx) harvest(c);
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, evStart, evStop));
         stats.device_ms += ms;
-        stats.samples += totalPaths;
-        s.sample_count += (uint32_t)totalSamples;
+        timelineOpen = false;
+        lastAccumEvent = nullptr;
+    }
+    void finishWavesOrDie() noexcept {
+        try { finishWaves(); } catch (const std::exception& e) { fatal(e.what()); }
     }
 
     void readSensor(Sensor& s) {
@@ -1145,7 +1173,10 @@ struct HdMoonshine {
 // ================================================================================================
 // C ABI
 // ================================================================================================
-#define LOCK(h) std::lock_guard<std::mutex> lock_((h)->mutex)
+// every entry point serialises on the object's mutex (hydra.zig:78) and, except the two that enqueue waves, first waits for the
+// waves an earlier HdMoonshineExtRenderLaunches left in flight
+#define LOCK_ASYNC(h) std::lock_guard<std::mutex> lock_((h)->mutex)
+#define LOCK(h) std::lock_guard<std::mutex> lock_((h)->mutex); (h)->finishWavesOrDie()
 #define ABORT_ON_THROW(...)                          \
     try { __VA_ARGS__ } catch (const std::exception& e) { fatal(e.what()); }
 
@@ -1207,15 +1238,15 @@ HdMoonshine* HdMoonshineCreate(void) {
 
 void HdMoonshineDestroy(HdMoonshine* h) {
     if (!h) return;
-    { LOCK(h); }   // hydra.zig:542-558 takes no lock; here an entry point still running on another thread finishes first
+    { LOCK(h); }   // also waits for waves in flight   // hydra.zig:542-558 takes no lock; here an entry point still running on another thread finishes first
     delete h;
 }
 
 bool HdMoonshineRender(HdMoonshine* h, SensorHandle sensor, LensHandle lens) {
-    LOCK(h);
+    LOCK_ASYNC(h);
     try {
         Sensor& s = *h->sensors.at(sensor);
-        h->renderLaunches(s, h->lenses.at(lens), 1);   // hydra.zig:316-329: one traceRays per call
+        h->renderLaunches(s, h->lenses.at(lens), 1, true);   // hydra.zig:316-329: one traceRays per call, then wait idle (:358)
         if (h->comm) h->reduceSensor(s, 0);            // one rank per GPU: assemble the tiles on rank 0, whose host buffer gets the frame
         else h->readSensor(s);                         // hydra.zig:332-358: copy to the persistent host buffer, wait idle
         return true;
@@ -1426,8 +1457,10 @@ bool HdMoonshineExtBuildEmitterTable(HdMoonshine* h) {
     try { h->use(); h->buildEmitterTable(); h->clearAllSensors(); return true; } catch (const std::exception& e) { g_lastError = e.what(); return false; }
 }
 bool HdMoonshineExtRenderLaunches(HdMoonshine* h, SensorHandle s, LensHandle l, uint32_t n) {
-    LOCK(h);
-    try { h->renderLaunches(*h->sensors.at(s), h->lenses.at(l), n); return true; } catch (const std::exception& e) { g_lastError = e.what(); return false; }
+    LOCK_ASYNC(h);
+    // returns once the launches are ENQUEUED; the next entry point that needs their result (ReadSensor, Render, GetStats, any edit)
+    // waits for them. Consecutive calls therefore overlap: the tail of one call's last wave runs under the next call's first.
+    try { h->renderLaunches(*h->sensors.at(s), h->lenses.at(l), n, false); return true; } catch (const std::exception& e) { g_lastError = e.what(); return false; }
 }
 bool HdMoonshineExtReadSensor(HdMoonshine* h, SensorHandle s) {
     LOCK(h);
@@ -1446,6 +1479,7 @@ uint32_t HdMoonshineExtGetSensorSampleCount(const HdMoonshine* h, SensorHandle s
 void* HdMoonshineExtGetSensorDevicePtr(const HdMoonshine* h, SensorHandle s) {
     HdMoonshine* m = const_cast<HdMoonshine*>(h);
     std::lock_guard<std::mutex> lock_(m->mutex);
+    m->finishWavesOrDie();
     if (s >= m->sensors.size()) fatal("HdMoonshineExtGetSensorDevicePtr: no such sensor");
     return m->sensors[s]->image.p;
 }
@@ -1538,6 +1572,7 @@ void HdMoonshineExtSetSchedule(HdMoonshine* h, uint64_t tailPaths, uint64_t binn
 void HdMoonshineExtGetStats(const HdMoonshine* h, MsneStats* out) {
     HdMoonshine* m = const_cast<HdMoonshine*>(h);
     std::lock_guard<std::mutex> lock_(m->mutex);
+    m->finishWavesOrDie();
     ABORT_ON_THROW(m->fetchStats(*out);)
 }
 void HdMoonshineExtResetStats(HdMoonshine* h) {

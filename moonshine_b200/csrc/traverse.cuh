@@ -37,7 +37,7 @@ struct HitRec { uint32_t inst, tri; float u, v; };
 #define MSNE_SLAB_SUB 0   // 1: slab distances as (plane - o) * idir (two instructions per plane, relative error only, no margin constants)
 #endif
 #ifndef MSNE_STASH_WORLD_RAY
-#define MSNE_STASH_WORLD_RAY 0   // measurement variant: keep the world-space ray constants instead of recomputing them on leaving an instance
+#define MSNE_STASH_WORLD_RAY 1   // keep the world-space ray constants (local memory) instead of recomputing them on leaving an instance: +1.4 % on cfg5
 #endif
 #ifndef MSNE_TRI_FALLBACK_INLINE
 #define MSNE_TRI_FALLBACK_INLINE 0
