@@ -9,9 +9,8 @@ GPUs the image is sharded into 32x32 tiles round-robin over ranks and each step 
 of the rank's tiles (weak scaling: per-GPU work fixed), followed by ONE NCCL reduce of the RGBA32F radiance
 buffer to rank 0 inside the timed region - issued by the library itself (HdMoonshineExtCommInit / CommReduceSensor).
 
-  value    Mrays/s = (closest-hit + shadow rays traced by all ranks) / max-over-ranks device time (CUDA events on the
-           library's stream: first k_generate of the first step .. last k_accumulate of the last; steps are enqueued
-           back to back and waited for once, at the closing barrier + synchronize).
+  value    Mrays/s = (closest-hit + shadow rays traced by all ranks) / max-over-ranks device time (CUDA events
+           on the library's stream around each step, first k_generate .. last k_accumulate).
   e2e      same metric through the reference-facing call HdMoonshineRender (hydra/moonshine.h:74): per step
            one launch of samples_per_run = batch_spp samples + the D2H copy of the sensor into the host buffer,
            wall-clock, host<->device copies inside the timed region.
@@ -240,7 +239,7 @@ def main():
 
     t_first = time.perf_counter()
     m.RenderLaunches(sensor, lens, batch)          # first render: builds the acceleration structure (host, all cores) and uploads it
-    accel_ms = m.GetStats().accel_sync_ms          # (GetStats waits for the launches RenderLaunches only enqueued)
+    accel_ms = m.GetStats().accel_sync_ms
     first_render_s = time.perf_counter() - t_first
     setup = {"generate_scene_s": t_generated - t_scene, "load_through_abi_s": t_loaded - t_generated,
              "accel_build_ms": accel_ms, "first_render_s": first_render_s,
@@ -258,7 +257,7 @@ def main():
     clocks.start()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        m.RenderLaunches(sensor, lens, batch)   # enqueues the step's waves; consecutive steps overlap tail-to-head, the bracket below waits
+        m.RenderLaunches(sensor, lens, batch)
     reduce_ms = 0.0
     if world > 1:
         tr = time.perf_counter()

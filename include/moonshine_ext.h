@@ -79,9 +79,7 @@ MSNE_API MeshHandle HdMoonshineExtCreateMeshIndexed(HdMoonshine*, const F32x3* p
 /* Accel.create semantics: rebuild the emitter alias table over every `sampled` geometry of every instance */
 MSNE_API bool HdMoonshineExtBuildEmitterTable(HdMoonshine*);
 
-/* offline loop (offline/main.zig:131-165 records its launches and waits once): n_launches x (push constants, trace rays) are ENQUEUED,
- * sensor.sample_count advances; the call does not wait for the device and does no read-back. Whatever needs the result waits first:
- * ReadSensor, Render, GetStats, CommReduceSensor, GetSensorDevicePtr and every entry point that edits the scene. */
+/* offline loop: n_launches x (push constants, trace rays), sensor.sample_count advances; no read-back */
 MSNE_API bool HdMoonshineExtRenderLaunches(HdMoonshine*, SensorHandle, LensHandle, uint32_t n_launches);
 MSNE_API bool HdMoonshineExtReadSensor(HdMoonshine*, SensorHandle);      /* device image -> host buffer of GetSensorData */
 MSNE_API void HdMoonshineExtClearSensor(HdMoonshine*, SensorHandle);     /* Sensor.clear (core/Sensor.zig:81-83) */

@@ -317,10 +317,9 @@ struct HdMoonshine {
     bool sortActive = false;         // decided per render (renderLaunches)
     SortFrame sortFrame{};           // scene bounds for the origin cells (buildTlas)
     cudaEvent_t evStart = nullptr, evStop = nullptr, evAccum[kWaveContexts]{};
-    // Waves may still be in flight when HdMoonshineExtRenderLaunches returns (the offline loop records all its launches and waits
-    // once, offline/main.zig:131-194): `timelineOpen` from the first enqueue until finishWaves(), which every other entry point
-    // calls first. Consecutive calls keep alternating the contexts and chaining the accumulates, so the last wave of one call
-    // overlaps the first of the next.
+    // `timelineOpen` from the first enqueue of a render call until finishWaves(). The machinery allows a render call to return with
+    // its waves still in flight (renderLaunches(wait = false); every other entry point calls finishWaves() first, consecutive calls
+    // keep alternating the contexts and chaining the accumulates); both public render entry points wait, see HdMoonshineExtRenderLaunches.
     bool timelineOpen = false;
     uint64_t waveSerial = 0;
     cudaEvent_t lastAccumEvent = nullptr;
@@ -1458,9 +1457,10 @@ bool HdMoonshineExtBuildEmitterTable(HdMoonshine* h) {
 }
 bool HdMoonshineExtRenderLaunches(HdMoonshine* h, SensorHandle s, LensHandle l, uint32_t n) {
     LOCK_ASYNC(h);
-    // returns once the launches are ENQUEUED; the next entry point that needs their result (ReadSensor, Render, GetStats, any edit)
-    // waits for them. Consecutive calls therefore overlap: the tail of one call's last wave runs under the next call's first.
-    try { h->renderLaunches(*h->sensors.at(s), h->lenses.at(l), n, false); return true; } catch (const std::exception& e) { g_lastError = e.what(); return false; }
+    // Waits for its waves like HdMoonshineRender does. Returning right after the enqueue (wait = false: consecutive calls then overlap
+    // tail to head, every other entry point waits through finishWaves) was measured: 2509 vs 2527 Mrays/s on the metric config -
+    // two waves that are BOTH in their throughput-bound phase only take SMs and cache from each other (profiles/r02_sweeps.md).
+    try { h->renderLaunches(*h->sensors.at(s), h->lenses.at(l), n, true); return true; } catch (const std::exception& e) { g_lastError = e.what(); return false; }
 }
 bool HdMoonshineExtReadSensor(HdMoonshine* h, SensorHandle s) {
     LOCK(h);
