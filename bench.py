@@ -196,6 +196,7 @@ def main():
     ap.add_argument("--paths-in-flight", type=int, default=0, help="wavefront pool size in paths (0 = library default, 128 Mi)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps (capped at 32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--render-ahead", type=int, default=2, help="waves kept in flight beyond the one a call waits for, in the e2e_interactive.render_ahead leg (1..3)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -365,6 +366,27 @@ def main():
     e2e_interactive = {"value": int_rays / int_wall / 1e6, "unit": UNIT, "calls": n_int, "ms_per_call": int_wall / n_int * 1e3,
                        "device_ms_per_call": st3.device_ms / n_int, "launches_per_call": st3.kernel_launches / n_int,
                        "call": "HdMoonshineRender(sensor, lens), samples_per_run = 1 per GPU-frame, sensor read back every call"}
+
+    # the same call pattern with render-ahead on (HdMoonshineExtSetRenderAhead): every call also starts the next sample's wave, whose
+    # bandwidth-bound head then runs under the latency-bound tail of the wave being waited for; frames are the same bits
+    m.SetRenderAhead(args.render_ahead)
+    m.Render(sensor, lens)
+    m.Render(sensor, lens)
+    barrier()
+    m.ResetStats()
+    t0 = time.perf_counter()
+    for _ in range(n_int):
+        if not m.Render(sensor, lens):
+            raise SystemExit("HdMoonshineRender failed: " + m.last_error())
+    barrier()
+    ahead_wall = time.perf_counter() - t0
+    st4 = m.GetStats()
+    m.SetRenderAhead(0)
+    ahead_rays = allreduce(float(st4.rays_closest + st4.rays_shadow), dist.ReduceOp.SUM if world > 1 else None)
+    ahead_wall = allreduce(ahead_wall, dist.ReduceOp.MAX if world > 1 else None)
+    e2e_interactive["render_ahead"] = {"value": ahead_rays / ahead_wall / 1e6, "unit": UNIT, "calls": n_int, "ms_per_call": ahead_wall / n_int * 1e3,
+                                       "launches_per_call": st4.kernel_launches / n_int, "waves_ahead": args.render_ahead, "waves_dropped": int(st4.ahead_discarded),
+                                       "call": "the same calls after HdMoonshineExtSetRenderAhead(waves_ahead); rays of claimed waves only"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -62,6 +62,7 @@ typedef struct MsneStats {
     uint64_t host_syncs;                /* host<->device synchronisations inside render loops (one per render call, none per bounce) */
     uint64_t tail_paths;                /* paths left to k_tail after the wavefront bounces, summed over waves */
     double   accel_sync_ms;             /* host wall time spent bringing the acceleration structure up to date after edits (builds, refits, record uploads) */
+    uint64_t ahead_discarded;           /* render-ahead: speculative waves dropped unseen because the next call did not ask for that sample */
 } MsneStats;
 
 /* must be called before HdMoonshineCreate; selects the CUDA device of objects created afterwards */
@@ -113,6 +114,13 @@ MSNE_API void HdMoonshineExtSetProfiling(HdMoonshine*, bool per_kernel_events);
  * (32768, 262144, 2). Also forgets the survival profile learnt from earlier waves. */
 MSNE_API void HdMoonshineExtSetSchedule(HdMoonshine*, uint64_t tail_paths, uint64_t binned_paths, uint32_t wave_contexts);
 
+/* Render-ahead for one-sample-per-call rendering (the Hydra delegate's pattern, hydra/hydra.zig:316-358). waves_ahead > 0:
+ * HdMoonshineRender keeps that many FURTHER samples' waves (same sensor, lens, scene; at most 3) in flight when it waits for its own,
+ * holds their samples back from the sensor, and the following HdMoonshineRender calls claim them one by one if they ask for exactly
+ * those samples - otherwise (any other entry point in between, another sensor / lens, an edited scene) the waves are dropped unseen.
+ * Frames and sample counts are bit for bit those of render-ahead off; ray counters cover claimed waves only
+ * (MsneStats.ahead_discarded counts the dropped ones). 0 = off (default); MSNE_RENDER_AHEAD=<n> sets it at creation. */
+MSNE_API void HdMoonshineExtSetRenderAhead(HdMoonshine*, uint32_t waves_ahead);
 MSNE_API void HdMoonshineExtGetStats(const HdMoonshine*, MsneStats*);
 MSNE_API void HdMoonshineExtResetStats(HdMoonshine*);
 

@@ -89,6 +89,7 @@ struct DeviceScene {
     const BvhNode2* blasNodes;     // pooled BLAS nodes
     const BvhNode4* static4;       // 4-wide collapse of the merged static BLAS (root = node 0), or null (MSNE_TRACE4 experiment)
     const TriRec* tris;            // pooled triangles (leaf order)
+    const float4* triFrames;       // per pooled triangle 64 B: its tangent frame, evaluated once per build (shading.cuh MSNE_TRI_FRAMES, kernels.cu k_tri_frames)
     const DInstance* instances;
     const DGeometry* geometries;
     const DMesh* meshes;

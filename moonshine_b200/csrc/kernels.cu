@@ -869,7 +869,7 @@ DI void shadeOne(const DeviceScene& sc, const DConstants& k, const PathBuffers& 
     const uint32_t instanceID = __ldg(&sc.instances[instanceIndex].customIndex);
     const DGeometry geometry = sc.geometries[instanceID + geometryIndex];
     const bool geomSampled = (geometry.sampled & 0xFFu) != 0;   // only the low byte is defined (Accel.zig:40-44)
-    const MeshAttributes attrs = lookupAttributes(sc, k, instanceIndex, geometry.mesh, primitiveIndex, bary, tr);
+    MeshAttributes attrs = lookupAttributes<true>(sc, k, instanceIndex, geometry.mesh, primitiveIndex, bary, tr, H.y & H_TRI_MASK);
     const DMaterial& dm = sc.materials[geometry.material];   // read in place (112 B: header + resolved constants), field by field
     const Frame textureFrame = getTextureFrame(sc, k, dm, attrs.texcoord, attrs.frame);
     const float3 emissiveLight = xyz(sampleMaterialSlot(sc, dm, MAT_SLOT_EMISSIVE, dm.emissive, attrs.texcoord));
@@ -883,7 +883,7 @@ DI void shadeOne(const DeviceScene& sc, const DConstants& k, const PathBuffers& 
     Frame shadingFrame;
     if ((frontfacing && dot(outgoingDirWs, textureFrame.n) > 0) || (!frontfacing && -dot(outgoingDirWs, textureFrame.n) > 0)) shadingFrame = textureFrame;
     else if ((frontfacing && dot(outgoingDirWs, attrs.frame.n) > 0) || (!frontfacing && -dot(outgoingDirWs, attrs.frame.n) > 0)) shadingFrame = attrs.frame;
-    else shadingFrame = attrs.triangleFrame;
+    else { completeTriangleFrame(sc, attrs, instanceIndex, H.y & H_TRI_MASK); shadingFrame = attrs.triangleFrame; }
     const float3 outgoingDirSs = shadingFrame.worldToFrame(outgoingDirWs);
 
     // emission (integrator.hlsl:109-124)
@@ -1207,6 +1207,40 @@ DI void writeChildBox(BvhNode2* nodes, uint32_t packed, const float lo[3], const
     xy[0] = lo[0]; xy[1] = hi[0]; xy[2] = lo[1]; xy[3] = hi[1];
     n->n2[2 * s] = lo[2]; n->n2[2 * s + 1] = hi[2];
 }
+// ------------------------------------------------------------------------------------------------
+// frame records: the triangle-only part of MeshAttributes::lookupAndInterpolate(...).inWorld(...) (world.hlsl:137-147, :160-176),
+// evaluated once per pooled triangle with the functions the hit path would call (shading.cuh lookupAttributes) - same operands,
+// same IEEE operations, so a hit that reads the record sees the bits it would have computed.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_tri_frames(DeviceScene sc, DConstants k, const uint32_t* __restrict__ triMesh, uint32_t n, float4* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t tm = triMesh[i];
+    const DMesh mesh = sc.meshes[tm & 0x7FFFFFFFu];
+    const bool inWorld = (tm >> 31) != 0;
+    const float4* tp = reinterpret_cast<const float4*>(sc.tris + i);
+    const float4 r0 = __ldg(tp), r1 = __ldg(tp + 1), r2 = __ldg(tp + 2);
+    const float3 p0 = mk3(r0.x, r0.y, r0.z), p1 = mk3(r1.x, r1.y, r1.z), p2 = mk3(r2.x, r2.y, r2.z);
+    const uint32_t primitiveIndex = __float_as_uint(r1.w);
+    const uint32_t ix = __ldg(mesh.idx + 3 * (size_t)primitiveIndex), iy = __ldg(mesh.idx + 3 * (size_t)primitiveIndex + 1), iz = __ldg(mesh.idx + 3 * (size_t)primitiveIndex + 2);
+    uint32_t ax, ay, az;
+    attributeIndices(k, primitiveIndex, ix, iy, iz, ax, ay, az);
+    float2 t0, t1, t2;
+    cornerTexcoords(mesh, ax, ay, az, t0, t1, t2);
+    const Frame obj = objectTriangleFrame(p0, p1, p2, t0, t1, t2);
+    Frame rec = obj;
+    if (inWorld) {
+        float m[12];
+        loadRows(sc.instances[__float_as_uint(r2.w)].w2o, m);
+        rec = obj.inSpaceTranspose(m);
+    }
+    float4* o = out + 4 * (size_t)i;
+    o[0] = make_float4(obj.s.x, obj.s.y, obj.s.z, inWorld ? 1.0f : 0.0f);
+    o[1] = make_float4(rec.n.x, rec.n.y, rec.n.z, 0.0f);
+    o[2] = make_float4(rec.s.x, rec.s.y, rec.s.z, 0.0f);
+    o[3] = make_float4(rec.t.x, rec.t.y, rec.t.z, 0.0f);
+}
+
 __global__ void k_tlas_boxes(TlasRefit r, const uint32_t* __restrict__ dirty, uint32_t nDirty) {
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= nDirty) return;
@@ -1344,6 +1378,12 @@ void launchMathProbe(cudaStream_t st, int fn, const float* a, const float* b, ui
 void launchBsdfProbe(cudaStream_t st, const float* q14, uint32_t n, float* out4) { k_bsdf_probe<<<grid1(n, 128), 128, 0, st>>>(q14, n, out4); }
 void launchEnvProbe(cudaStream_t st, const DeviceScene& sc, int op, const float* in3, uint32_t n, float* out7) {
     k_env_probe<<<grid1(n, 128), 128, 0, st>>>(sc, op, in3, n, out7);
+}
+__global__ void k_commit_counts(unsigned long long* c) { c[0] += c[2]; c[1] += c[3]; c[2] = 0; c[3] = 0; }
+void launchCommitCounts(cudaStream_t st, unsigned long long* counts) { k_commit_counts<<<1, 1, 0, st>>>(counts); }
+void launchTriFrames(cudaStream_t st, const DeviceScene& sc, const DConstants& k, const uint32_t* triMesh, uint32_t n, float4* out) {
+    if (n == 0) return;
+    k_tri_frames<<<grid1(n, 128), 128, 0, st>>>(sc, k, triMesh, n, out);
 }
 void launchTlasRefit(cudaStream_t st, const TlasRefit& r, const uint32_t* dirty, uint32_t nDirty, uint32_t nSlots) {
     if (nDirty) k_tlas_boxes<<<grid1(nDirty, 128), 128, 0, st>>>(r, dirty, nDirty);

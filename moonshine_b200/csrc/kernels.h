@@ -47,6 +47,8 @@ void launchShade(cudaStream_t st, int blocks, const DeviceScene& sc, const DCons
 void launchShadeBinned(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf, int32_t slot, const SortKeys& keys);
 void launchShadeInlineNee(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf, int32_t slot, const SortKeys& keys);
 void launchTail(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf, bool inlineNee);
+// counts[0..1] += counts[2..3]; counts[2..3] = 0 (ray counters of a wave that was rendered ahead and is now claimed)
+void launchCommitCounts(cudaStream_t st, unsigned long long* counts);
 void launchAccumulate(cudaStream_t st, const float4* result, float4* image, float4* runState, const uint32_t* pixIds, uint32_t nPix, uint32_t nSamples,
                       uint32_t firstSample, uint32_t spr);
 void launchEnvResample(cudaStream_t st, const float4* src, uint32_t W, uint32_t H, float4* dstRgb, float* dstLum, uint32_t S);
@@ -66,6 +68,9 @@ struct TlasRefit {
     uint32_t* arrived;            // per node, zero between refits
 };
 void launchTlasRefit(cudaStream_t st, const TlasRefit& r, const uint32_t* dirty, uint32_t nDirty, uint32_t nSlots);
+// per-pooled-triangle frame records (shading.cuh MSNE_TRI_FRAMES): triMesh[i] = mesh index of pooled triangle i, bit 31 set for members of
+// the merged static BLAS (their instance - TriRec.inst - is known, so the record holds the world-space frame)
+void launchTriFrames(cudaStream_t st, const DeviceScene& sc, const DConstants& k, const uint32_t* triMesh, uint32_t n, float4* out);
 void launchPick(cudaStream_t st, const DeviceScene& sc, const DCamera& cam, float x, float y, MsneClick* out);
 void launchPrimaryProbe(cudaStream_t st, const DCamera& cam, const DConstants& k, uint32_t sample, float* rays6, uint32_t* rngState);
 int traceOccupancyBlocksPerSm();

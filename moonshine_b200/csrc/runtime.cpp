@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -227,6 +228,9 @@ struct HdMoonshine {
     std::vector<Blas> blases;
     std::vector<BvhNode2> blasNodePool;
     std::vector<TriRec> triPool;
+    std::vector<uint32_t> triMeshPool;   // per pooled triangle: mesh index, bit 31 = member of the merged static BLAS (frame records, kernels.cu k_tri_frames)
+    DevBuf<float4> dTriFrames;
+    bool triFramesDirty = true, triFramesIndexed = false;
 
     // geomDirty: the set of flattened (identity-transform, visible) instances or the BLAS pool changed -> rebuild BLASes + TLAS.
     // tlasDirty: only transforms / visibility of transformed instances changed -> rebuild the TLAS and instance records.
@@ -354,11 +358,11 @@ struct HdMoonshine {
             CK(cudaEventCreateWithFlags(&c.evDone, cudaEventDisableTiming));
             for (auto& p : c.profEv) for (auto& e : p) CK(cudaEventCreate(&e));
             CK(cudaMallocHost((void**)&c.hostHistory, kMaxHistory * sizeof(Counters)));
-            c.dCounters.alloc(2); c.dScalars.alloc(16); c.dRayCounts.alloc(2); c.dHistory.alloc(kMaxHistory);
+            c.dCounters.alloc(2); c.dScalars.alloc(16); c.dRayCounts.alloc(4); c.dHistory.alloc(kMaxHistory);
             c.sortHist.alloc(2 * 32768); c.sortCursor.alloc(2 * 32768);
             CK(cudaMemsetAsync(c.dCounters.p, 0, 2 * sizeof(Counters), stream));
             CK(cudaMemsetAsync(c.dScalars.p, 0, 16 * sizeof(uint32_t), stream));
-            CK(cudaMemsetAsync(c.dRayCounts.p, 0, 2 * sizeof(unsigned long long), stream));
+            CK(cudaMemsetAsync(c.dRayCounts.p, 0, 4 * sizeof(unsigned long long), stream));
             CK(cudaMemsetAsync(c.dHistory.p, 0, kMaxHistory * sizeof(Counters), stream));
             CK(cudaMemsetAsync(c.sortHist.p, 0, 2 * 32768 * sizeof(uint32_t), stream));
         }
@@ -380,8 +384,12 @@ struct HdMoonshine {
         if (const char* e = getenv("MSNE_TILE_EDGE")) tileEdge = (uint32_t)std::min(256, std::max(8, atoi(e) / 8 * 8));
         if (const char* e = getenv("MSNE_WAVE_CONTEXTS")) waveContextsInUse = std::min(kWaveContexts, std::max(1, atoi(e)));
         if (const char* e = getenv("MSNE_BINNED_THRESHOLD")) binnedThreshold = strtoull(e, nullptr, 10);
+        if (const char* e = getenv("MSNE_RENDER_AHEAD")) { renderAhead = atoi(e) != 0; if (atoi(e) > 0) aheadDepth = (uint32_t)atoi(e); }
         traceBlocks = smCount * std::max(1, traceOccupancyBlocksPerSm());
         shadeBlocks = smCount * std::max(1, shadeOccupancyBlocksPerSm());
+        // measurement knobs: launch fewer blocks per SM than fit, so that kernels of the OTHER wave context can share the SMs
+        if (const char* e = getenv("MSNE_TRACE_GRID_PER_SM")) traceBlocks = smCount * std::max(1, atoi(e));
+        if (const char* e = getenv("MSNE_SHADE_GRID_PER_SM")) shadeBlocks = smCount * std::max(1, atoi(e));
         shadeInlineBlocks = smCount * std::max(1, shadeInlineOccupancyBlocksPerSm());
         CK(cudaStreamSynchronize(stream));
     }
@@ -432,7 +440,7 @@ struct HdMoonshine {
 
     // ---- acceleration structure (replaces Accel.zig:94-184 makeBlases and :440-489 TLAS build) ------
     // pools a host BVH: children become the pre-encoded traversal references of dtypes.h
-    uint32_t appendBlas(const BuiltBvh& bvh, const std::vector<TriRec>& tris) {
+    uint32_t appendBlas(const BuiltBvh& bvh, const std::vector<TriRec>& tris, const std::vector<uint32_t>& triMesh) {
         // leaf references hold the pooled triangle index in 28 bits (dtypes.h), hit records in 29 (H_TRI_MASK); inner references must
         // stay below REF_ITEM. The merged static BLAS duplicates triangles per identity instance, so the pools can grow quickly.
         if (triPool.size() + tris.size() >= (1ull << 28)) throw std::runtime_error("acceleration structure: more than 2^28 pooled triangles");
@@ -448,7 +456,7 @@ struct HdMoonshine {
             n.c[2] = n.c[3] = 0;
             blasNodePool.push_back(n);
         }
-        for (uint32_t i = 0; i < bvh.order.size(); i++) triPool.push_back(tris[bvh.order[i]]);
+        for (uint32_t i = 0; i < bvh.order.size(); i++) { triPool.push_back(tris[bvh.order[i]]); triMeshPool.push_back(triMesh[bvh.order[i]]); }
         return nodeBase;
     }
     static void meshTriangles(const HostMesh& m, uint32_t geom, uint32_t inst, std::vector<TriRec>& tris, std::vector<BuildBox>& boxes) {
@@ -536,11 +544,12 @@ struct HdMoonshine {
         if (it != blasByKey.end()) return it->second;
         std::vector<BuildBox> boxes;
         std::vector<TriRec> tris;
-        for (uint32_t g = 0; g < key.size(); g++) meshTriangles(*meshes[key[g]], g, 0, tris, boxes);
+        std::vector<uint32_t> triMesh;
+        for (uint32_t g = 0; g < key.size(); g++) { meshTriangles(*meshes[key[g]], g, 0, tris, boxes); triMesh.resize(tris.size(), key[g]); }
         BuiltBvh bvh;
         buildDepthLimited(boxes, maxLeaf, kMaxBlasDepth, bvh);
         maxBlasDepth = std::max(maxBlasDepth, bvh.depth);
-        Blas b; b.rootNode = appendBlas(bvh, tris); b.bounds = bvh.bounds; b.depth = bvh.depth;
+        Blas b; b.rootNode = appendBlas(bvh, tris, triMesh); b.bounds = bvh.bounds; b.depth = bvh.depth;
         blases.push_back(b);
         const uint32_t id = (uint32_t)blases.size() - 1;
         blasByKey[key] = id;
@@ -559,16 +568,17 @@ struct HdMoonshine {
     uint64_t stats_static_builds = 0, stats_tlas_builds = 0, stats_tlas_refits = 0;
     uint32_t tlasDepth = 0;
     void buildGeometry() {
-        blasNodePool.clear(); triPool.clear(); blasByKey.clear(); blases.clear();
+        blasNodePool.clear(); triPool.clear(); triMeshPool.clear(); blasByKey.clear(); blases.clear();
         maxBlasDepth = 1;
         const uint32_t nInst = (uint32_t)instances.size();
         std::vector<TriRec> stTris;
         std::vector<BuildBox> stBoxes;
+        std::vector<uint32_t> stMesh;
         for (uint32_t i = 0; i < nInst; i++) {
             HostInstance& in = instances[i];
             in.inStatic = in.visible && isIdentity(in.transform);
             if (!in.inStatic) continue;
-            for (uint32_t g = 0; g < in.meshKey.size(); g++) meshTriangles(*meshes[in.meshKey[g]], g, i, stTris, stBoxes);
+            for (uint32_t g = 0; g < in.meshKey.size(); g++) { meshTriangles(*meshes[in.meshKey[g]], g, i, stTris, stBoxes); stMesh.resize(stTris.size(), in.meshKey[g] | 0x80000000u); }
         }
         staticTris = stTris.size(); hiddenStaticTris = 0;
         staticRec = DInstance{};
@@ -580,7 +590,7 @@ struct HdMoonshine {
             BuiltBvh bvh;
             buildDepthLimited(stBoxes, maxLeaf, kMaxBlasDepth, bvh);
             maxBlasDepth = std::max(maxBlasDepth, bvh.depth);
-            staticRec.blasRoot = appendBlas(bvh, stTris);
+            staticRec.blasRoot = appendBlas(bvh, stTris, stMesh);
             staticBounds = bvh.bounds;
             if (trace4) collapseStatic4(staticRec.blasRoot);
         }
@@ -591,6 +601,7 @@ struct HdMoonshine {
         dBlasNodes.upload(blasNodePool.data(), blasNodePool.size(), stream);
         dTris.upload(triPool.data(), triPool.size(), stream);
         CK(cudaStreamSynchronize(stream));
+        triFramesDirty = true;
         stats_static_builds++;
     }
 
@@ -815,6 +826,7 @@ struct HdMoonshine {
         } else if (!dirtyInstances.empty()) uploadDirtyRecords();   // visibility toggles: records only
         dirtyInstances.clear();
         if (accelWork) stats.accel_sync_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (triFramesDirty || triFramesIndexed != (consts.indexed_attributes != 0)) buildTriFrames();
         if (emitterFollowsEdits && emitterStale) { buildEmitterTable(); emitterStale = false; }
         if (aliasDirty || emitterRecIndexed != (consts.indexed_attributes != 0)) {
             dAlias.upload(alias.data(), alias.size(), stream);
@@ -824,11 +836,25 @@ struct HdMoonshine {
         }
     }
 
+    // frame records of the pooled triangles (shading.cuh MSNE_TRI_FRAMES): needs the mesh table, the pooled triangles and the instance
+    // records on the device; depends on indexed_attributes (which texcoords a corner reads)
+    void buildTriFrames() {
+        triFramesIndexed = consts.indexed_attributes != 0;
+        triFramesDirty = false;
+        if (triPool.empty()) return;
+        DevBuf<uint32_t> dTriMesh;
+        dTriMesh.upload(triMeshPool.data(), triMeshPool.size(), stream);
+        dTriFrames.ensure(4 * triPool.size());
+        launchTriFrames(stream, deviceScene(), deviceConstants(), dTriMesh.p, (uint32_t)triPool.size(), dTriFrames.p);
+        stats.kernel_launches += 1;
+        CK(cudaStreamSynchronize(stream));   // dTriMesh dies here
+    }
+
     DeviceScene deviceScene() const {
         DeviceScene sc{};
         sc.tlasNodes = hasTlas ? dTlasNodes.p : nullptr;
         sc.tlasItems = dTlasItems.p;
-        sc.blasNodes = dBlasNodes.p; sc.tris = dTris.p; sc.instances = dInstances.p; sc.geometries = dGeometries.p;
+        sc.blasNodes = dBlasNodes.p; sc.tris = dTris.p; sc.triFrames = dTriFrames.p; sc.instances = dInstances.p; sc.geometries = dGeometries.p;
         sc.meshes = dMeshes.p; sc.materials = dMaterials.p; sc.textures = dTextures.p;
         sc.alias = dAlias.p; sc.aliasEntries = (uint32_t)alias.size(); sc.emitterTris = dEmitterTris.p;
         sc.envRgb = reinterpret_cast<const float*>(dEnvRgb.p); sc.envLum = dEnvLum.p; sc.envSize = envSize; sc.envLevels = envLevels;
@@ -1056,9 +1082,11 @@ struct HdMoonshine {
 
     // one wave: `nSamples` consecutive samples of `nPix` owned pixels starting at pixIds + pixOffset, enqueued on c.stream without
     // any host synchronisation; `afterAccum` (may be null): the previous wave's accumulate, which this wave's must follow
+    // `withAccumulate` = false: the wave stops short of adding its samples to the sensor (render-ahead: enqueueAccumulate commits it later)
     void enqueueWave(WaveCtx& c, Sensor& s, const DCamera& cam, const DeviceScene& sc, const DConstants& k, uint32_t pixOffset, uint32_t nPix,
-                     uint32_t firstSample, uint32_t nSamples, cudaEvent_t afterAccum) {
-        const WaveState ws = waveState(c);
+                     uint32_t firstSample, uint32_t nSamples, cudaEvent_t afterAccum, bool withAccumulate = true) {
+        WaveState ws = waveState(c);
+        if (!withAccumulate) ws.rayCounts = c.dRayCounts.p + 2;   // a wave that may be dropped counts its rays aside until it is claimed
         const PathBuffers& pb = c.pb;
         cudaStream_t st = c.stream;
         const uint64_t nPaths = (uint64_t)nPix * nSamples;
@@ -1107,16 +1135,111 @@ struct HdMoonshine {
         launchTail(st, smCount * 4, sc, k, pb, ws, K & 1u, inlineNee);
         stats.kernel_launches += 2;
         CK(cudaMemcpyAsync(c.hostHistory, c.dHistory.p, K * sizeof(Counters), cudaMemcpyDeviceToHost, st));
-        if (afterAccum) CK(cudaStreamWaitEvent(st, afterAccum, 0));
-        launchAccumulate(st, pb.result, s.image.p, s.runState.p + pixOffset, s.pixIds.p + pixOffset, nPix, nSamples, firstSample, k.samples_per_run);
+        c.bounces = K; c.paths = nPaths;
+        if (withAccumulate) enqueueAccumulate(c, s, k, pixOffset, nPix, firstSample, nSamples, afterAccum);
+    }
+    // the last launch of a wave: its samples join the sensor's running mean (main.hlsl:43-51), in sample order
+    void enqueueAccumulate(WaveCtx& c, Sensor& s, const DConstants& k, uint32_t pixOffset, uint32_t nPix, uint32_t firstSample, uint32_t nSamples, cudaEvent_t afterAccum, bool deferred = false) {
+        if (afterAccum) CK(cudaStreamWaitEvent(c.stream, afterAccum, 0));
+        if (deferred) { launchCommitCounts(c.stream, c.dRayCounts.p); stats.kernel_launches++; }   // the rays the wave counted aside
+        launchAccumulate(c.stream, c.pb.result, s.image.p, s.runState.p + pixOffset, s.pixIds.p + pixOffset, nPix, nSamples, firstSample, k.samples_per_run);
         stats.kernel_launches++;
-        CK(cudaEventRecord(c.evDone, st));
-        c.pending = true; c.bounces = K; c.paths = nPaths;
+        CK(cudaEventRecord(c.evDone, c.stream));
+        c.pending = true;
+    }
+
+    // ---- render-ahead (HdMoonshineExtSetRenderAhead) ------------------------------------------------------------------------------
+    // The Hydra delegate renders ONE sample per HdMoonshineRender call and reads the sensor back after each (hydra.zig:316-358). A wave
+    // of one sample ends in a latency-bound tail - a few thousand long paths, ~150 bounces deep - that leaves most of the GPU idle
+    // for a third of the call. With render-ahead on, a call also enqueues the NEXT sample's wave (same sensor, lens and scene) on the
+    // other wave context before it waits for its own, so that wave's bandwidth-bound head runs under this wave's tail; its samples
+    // stay in the context's pool (no accumulate) until the next call claims them. A sample is a pure function of (scene, lens, sample
+    // index), so the claimed wave is bit for bit what the call would have rendered itself; any other entry point, another sensor or
+    // lens, or an edited scene drops the speculative wave unseen (one wave of GPU time lost).
+    bool renderAhead = false;
+    uint32_t aheadDepth = 2;   // waves kept in flight beyond the one a call waits for (1..kWaveContexts-1); MSNE_RENDER_AHEAD=<depth>
+    struct AheadWave { int ctx; uint32_t firstSample; };
+    std::deque<AheadWave> aheadQ;   // speculative waves, oldest first: rendered, not accumulated
+    const Sensor* aheadSensor = nullptr;
+    Lens aheadLens{};
+    uint32_t aheadSpr = 0;
+    void discardAhead() {
+        if (aheadQ.empty()) return;
+        use();
+        for (const AheadWave& w : aheadQ) {
+            WaveCtx& c = ctx[w.ctx];
+            CK(cudaMemsetAsync(c.dRayCounts.p + 2, 0, 2 * sizeof(unsigned long long), c.stream));
+            CK(cudaStreamSynchronize(c.stream));   // never accumulated: nothing to undo, the pool is simply reused
+            stats.ahead_discarded++;
+        }
+        aheadQ.clear();
+    }
+    // true when this call pattern can be served by renderAheadCall: one wave of samples_per_run samples over the sensor's pixels
+    bool aheadEligible(const Sensor& s) const {
+        if (!renderAhead) return false;
+        const uint64_t paths = (uint64_t)s.extent.width * s.extent.height * consts.samples_per_run;
+        return paths > 0 && paths <= std::max<uint64_t>(1, pathsInFlight / 2) && paths <= 0x7FFFFFFFull / 4;
+    }
+    void renderAheadCall(Sensor& s, const Lens& lens) {
+        use();
+        const bool reshard = s.shardRank != shardRank || s.shardWorld != shardWorld || s.pixIds.p == nullptr;
+        if (!aheadQ.empty() && (aheadSensor != &s || memcmp(&aheadLens, &lens, sizeof(Lens)) != 0 || aheadQ.front().firstSample != s.sample_count ||
+                                aheadSpr != consts.samples_per_run || sceneDirty() || reshard))
+            discardAhead();
+        if (sceneDirty() || reshard) finishWaves();   // uploads must not race waves in flight
+        if (reshard) { buildPixIds(s); clearSensor(s); }
+        syncScene();
+        const DeviceScene sc = deviceScene();
+        const DConstants k = deviceConstants();
+        const DCamera cam = makeCamera(lens, s.extent.width, s.extent.height);
+        const uint32_t spr = k.samples_per_run;
+        if (s.nPix == 0) { discardAhead(); s.sample_count += spr; return; }
+        const uint64_t paths = (uint64_t)s.nPix * spr;
+        const uint64_t wantP = (paths + 31) & ~31ull;
+        const int depth = (int)std::min<uint32_t>(std::max<uint32_t>(aheadDepth, 1), kWaveContexts - 1), nCtx = depth + 1;
+        for (int i = 0; i < nCtx; i++) if (ctx[i].pb.capacity < wantP) ensurePool(ctx[i], wantP);   // reallocation waits for (and drops) everything in flight
+        size_t bvhNodes = blasNodePool.size() + tlasHostNodes.size();
+        sortActive = sortThreshold != 0 && wantP >= sortThreshold && (sortAnyScene || bvhNodes >= kSortMinNodes);
+        if (sortActive) for (int i = 0; i < nCtx; i++) ensureSortBuffers(ctx[i]);
+        CK(cudaEventRecord(evStart, stream));
+        for (int i = 0; i < nCtx; i++) CK(cudaStreamWaitEvent(ctx[i].stream, evStart, 0));   // uploads / clears queued on the main stream come first
+        aheadSensor = &s; aheadLens = lens; aheadSpr = spr;
+        auto launchNext = [&](uint32_t first, int busy) {   // sample `first` on a context that holds no unclaimed wave
+            int c = -1;
+            for (int i = 0; i < nCtx && c < 0; i++) {
+                bool used = i == busy;
+                for (const AheadWave& w : aheadQ) used = used || w.ctx == i;
+                if (!used) c = i;
+            }
+            if (c < 0) throw std::runtime_error("render-ahead: no free wave context");
+            harvest(ctx[c]);
+            enqueueWave(ctx[c], s, cam, sc, k, 0, s.nPix, first, spr, nullptr, false);
+            aheadQ.push_back(AheadWave{c, first});
+        };
+        if (aheadQ.empty()) launchNext(s.sample_count, -1);   // nothing rendered ahead: this call's own sample
+        const AheadWave cur = aheadQ.front();
+        aheadQ.pop_front();
+        // keep `depth` samples in flight beyond this one before waiting: their bandwidth-bound heads run under this wave's tail
+        uint32_t nextFirst = (aheadQ.empty() ? cur.firstSample : aheadQ.back().firstSample) + spr;
+        while ((int)aheadQ.size() < depth) { launchNext(nextFirst, cur.ctx); nextFirst += spr; }
+        // claim the current wave: its rays and samples count from here on
+        enqueueAccumulate(ctx[cur.ctx], s, k, 0, s.nPix, s.sample_count, spr, nullptr, true);
+        stats.samples += paths;
+        s.sample_count += spr;
+        CK(cudaStreamWaitEvent(stream, ctx[cur.ctx].evDone, 0));
+        CK(cudaEventRecord(evStop, stream));
+        CK(cudaStreamSynchronize(stream));
+        stats.host_syncs++;
+        harvest(ctx[cur.ctx]);
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, evStart, evStop));
+        stats.device_ms += ms;
     }
 
     // offline/main.zig:131-165: n launches of samples_per_run samples each; sensor.sample_count advances
     void renderLaunches(Sensor& s, const Lens& lens, uint32_t nLaunches, bool wait) {
         use();
+        discardAhead();   // this path reuses the wave contexts from the start
         if (sceneDirty() || s.shardRank != shardRank || s.shardWorld != shardWorld || s.pixIds.p == nullptr) finishWaves();   // uploads must not race the waves
         if (s.shardRank != shardRank || s.shardWorld != shardWorld || s.pixIds.p == nullptr) { buildPixIds(s); clearSensor(s); }
         syncScene();
@@ -1171,6 +1294,7 @@ struct HdMoonshine {
 
     // waits for every wave in flight, reads their logs, closes the device-time interval opened by the first enqueue
     void finishWaves() {
+        discardAhead();
         if (!timelineOpen) return;
         use();
         for (WaveCtx& c : ctx) if (c.pending) CK(cudaStreamWaitEvent(stream, c.evDone, 0));
@@ -1301,7 +1425,8 @@ bool HdMoonshineRender(HdMoonshine* h, SensorHandle sensor, LensHandle lens) {
     LOCK_ASYNC(h);
     try {
         Sensor& s = *h->sensors.at(sensor);
-        h->renderLaunches(s, h->lenses.at(lens), 1, true);   // hydra.zig:316-329: one traceRays per call, then wait idle (:358)
+        if (h->aheadEligible(s)) h->renderAheadCall(s, h->lenses.at(lens));   // same sample, plus the next one started early
+        else h->renderLaunches(s, h->lenses.at(lens), 1, true);   // hydra.zig:316-329: one traceRays per call, then wait idle (:358)
         if (h->comm) h->reduceSensor(s, 0);            // one rank per GPU: assemble the tiles on rank 0, whose host buffer gets the frame
         else h->readSensor(s);                         // hydra.zig:332-358: copy to the persistent host buffer, wait idle
         return true;
@@ -1625,6 +1750,11 @@ void HdMoonshineExtSetSchedule(HdMoonshine* h, uint64_t tailPaths, uint64_t binn
     h->waveContextsInUse = waveContexts == 0 ? HdMoonshine::kDefaultWaveContexts : (int)std::min<uint32_t>(waveContexts, HdMoonshine::kWaveContexts);
     h->survivalIn.clear();
 }
+void HdMoonshineExtSetRenderAhead(HdMoonshine* h, uint32_t wavesAhead) {
+    LOCK(h);
+    h->renderAhead = wavesAhead != 0;
+    if (wavesAhead) h->aheadDepth = std::min<uint32_t>(wavesAhead, HdMoonshine::kWaveContexts - 1);
+}
 void HdMoonshineExtGetStats(const HdMoonshine* h, MsneStats* out) {
     HdMoonshine* m = const_cast<HdMoonshine*>(h);
     std::lock_guard<std::mutex> lock_(m->mutex);
@@ -1637,7 +1767,7 @@ void HdMoonshineExtResetStats(HdMoonshine* h) {
         h->use();
         h->stats = MsneStats{};
         for (HdMoonshine::WaveCtx& c : h->ctx) {
-            CK(cudaMemsetAsync(c.dRayCounts.p, 0, 2 * sizeof(unsigned long long), c.stream));
+            CK(cudaMemsetAsync(c.dRayCounts.p, 0, 4 * sizeof(unsigned long long), c.stream));
             CK(cudaMemsetAsync(c.dScalars.p + 3, 0, sizeof(uint32_t), c.stream));
             CK(cudaStreamSynchronize(c.stream));
         }

@@ -353,7 +353,6 @@ DI Frame getTextureFrame(const DeviceScene& sc, const DConstants& k, const DMate
 }
 
 // ---- world.hlsl:86-176 -----------------------------------------------------------------------------
-struct MeshAttributes { float3 position; float2 texcoord; Frame triangleFrame, frame; };
 
 DI float3 ld3(const float* p, uint32_t i) { return mk3(__ldg(p + 3 * (size_t)i), __ldg(p + 3 * (size_t)i + 1), __ldg(p + 3 * (size_t)i + 2)); }
 DI float2 ld2(const float* p, uint32_t i) { return mk2(__ldg(p + 2 * (size_t)i), __ldg(p + 2 * (size_t)i + 1)); }
@@ -372,18 +371,73 @@ DI void getTangentBitangent(float3 p0, float3 p1, float3 p2, float2 t0, float2 t
     }
 }
 
+// Object-space triangle frame (world.hlsl:137-147): tangent / bitangent from the texcoords, geometric normal, reorthogonalised.
+DI Frame objectTriangleFrame(float3 p0, float3 p1, float3 p2, float2 t0, float2 t1, float2 t2) {
+    Frame f;
+    getTangentBitangent(p0, p1, p2, t0, t1, t2, f.s, f.t);
+    f.n = normalize(cross(p0 - p2, p1 - p2));
+    f.reorthogonalize();
+    return f;
+}
+// attribute indices of a triangle's corners (world.hlsl:130): `cond ? uint3 : float3` promotes both arms to float3 before
+// converting back to uint3
+DI void attributeIndices(const DConstants& k, uint32_t primitiveIndex, uint32_t ix, uint32_t iy, uint32_t iz, uint32_t& ax, uint32_t& ay, uint32_t& az) {
+    if (k.indexed_attributes) { ax = (uint32_t)(float)ix; ay = (uint32_t)(float)iy; az = (uint32_t)(float)iz; }
+    else { ax = (uint32_t)(float)(primitiveIndex * 3 + 0); ay = (uint32_t)(float)(primitiveIndex * 3 + 1); az = (uint32_t)(float)(primitiveIndex * 3 + 2); }
+}
+DI void cornerTexcoords(const DMesh& mesh, uint32_t ax, uint32_t ay, uint32_t az, float2& t0, float2& t1, float2& t2) {
+    if (mesh.uv != nullptr) { t0 = ld2(mesh.uv, ax); t1 = ld2(mesh.uv, ay); t2 = ld2(mesh.uv, az); }
+    else { t0 = mk2(0, 0); t1 = mk2(1, 0); t2 = mk2(1, 1); }
+}
+DI void loadRows(const float* rows, float m[12]) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) { const float4 r = __ldg(reinterpret_cast<const float4*>(rows) + i); m[4 * i] = r.x; m[4 * i + 1] = r.y; m[4 * i + 2] = r.z; m[4 * i + 3] = r.w; }
+}
+
+// Per-pooled-triangle frame records (MSNE_TRI_FRAMES, kernels.cu k_tri_frames; 64 B each, DeviceScene::triFrames): everything of
+// lookupAndInterpolate(...).inWorld(...) that depends on the TRIANGLE and not on the hit point - the tangent frame from positions and
+// texcoords, its reorthogonalisation, and (for members of the merged static BLAS, whose instance is known) its transform to world
+// space - is evaluated once per scene build by the very same device functions, so a hit reads the bits it would have computed:
+//   f[0] = (object-space s, w = 1 if f[1..3] are in world space, else 0)   f[1] = n   f[2] = s   f[3] = t
+// f[1..3]: world space for static members, object space for triangles of shared BLASes (their instance is only known at the hit).
+// A hit on a mesh with normals needs f[0], f[1] (one 32-byte sector); s and t of the triangle frame are only read by meshes
+// without normals and by the last fallback of the shading-frame selection (integrator.hlsl:93-104).
+#ifndef MSNE_TRI_FRAMES
+#define MSNE_TRI_FRAMES 1
+#endif
+struct MeshAttributes {
+    float3 position; float2 texcoord; Frame triangleFrame, frame;
+    bool triangleFrameComplete;   // false: triangleFrame.s / .t are still in the frame record (completeTriangleFrame)
+};
+
+// triangleFrame.s / .t of a hit whose lookup left them in the frame record
+DI void completeTriangleFrame(const DeviceScene& sc, MeshAttributes& a, uint32_t instanceIndex, uint32_t triIndex) {
+    if (!MSNE_TRI_FRAMES || a.triangleFrameComplete) return;
+    const float4* fr = sc.triFrames + 4 * (size_t)triIndex;
+    const float4 f0 = __ldg(fr), f2 = __ldg(fr + 2), f3 = __ldg(fr + 3);
+    a.triangleFrame.s = mk3(f2.x, f2.y, f2.z); a.triangleFrame.t = mk3(f3.x, f3.y, f3.z);
+    if (f0.w == 0.0f) {
+        float m[12];
+        loadRows(sc.instances[instanceIndex].w2o, m);
+        a.triangleFrame.s = normalize(mulTranspose3(m, a.triangleFrame.s));   // Frame::inSpaceTranspose, component by component
+        a.triangleFrame.t = normalize(mulTranspose3(m, a.triangleFrame.t));
+    }
+    a.triangleFrameComplete = true;
+}
+
 // MeshAttributes::lookupAndInterpolate(...).inWorld(...)  (world.hlsl:114-176)
-// `tri`: the pooled triangle record of a traced hit (nullptr for light samples). Its vertices are the mesh's object-space
-// positions copied verbatim (runtime.cpp meshTriangles), so the hit path takes them from the 48-byte record the trace
+// HIT: `tri` is the pooled triangle record of a traced hit, `triIndex` its index (light samples: HIT = false). Its vertices are the mesh's
+// object-space positions copied verbatim (runtime.cpp meshTriangles), so the hit path takes them from the 48-byte record the trace
 // kernel just touched instead of chasing index -> position (same bits, one dependent hop and nine scalar loads less).
+template <bool HIT = false>
 DI MeshAttributes lookupAttributes(const DeviceScene& sc, const DConstants& k, uint32_t instanceIndex, uint32_t meshIdx, uint32_t primitiveIndex, float2 attribs,
-                                   const TriRec* tri = nullptr) {
+                                   const TriRec* tri = nullptr, uint32_t triIndex = 0) {
     const DMesh mesh = sc.meshes[meshIdx];
     const float3 bary = mk3(1.0f - attribs.x - attribs.y, attribs.x, attribs.y);
     MeshAttributes a;
     const uint32_t ix = __ldg(mesh.idx + 3 * (size_t)primitiveIndex), iy = __ldg(mesh.idx + 3 * (size_t)primitiveIndex + 1), iz = __ldg(mesh.idx + 3 * (size_t)primitiveIndex + 2);
     float3 p0, p1, p2;
-    if (MSNE_POS_FROM_TRIREC && tri != nullptr) {
+    if (MSNE_POS_FROM_TRIREC && HIT) {
         const float4* tp = reinterpret_cast<const float4*>(tri);
         const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
         p0 = mk3(t0.x, t0.y, t0.z); p1 = mk3(t1.x, t1.y, t1.z); p2 = mk3(t2.x, t2.y, t2.z);
@@ -391,17 +445,37 @@ DI MeshAttributes lookupAttributes(const DeviceScene& sc, const DConstants& k, u
         p0 = ld3(mesh.pos, ix); p1 = ld3(mesh.pos, iy); p2 = ld3(mesh.pos, iz);
     }
     a.position = interp3(bary, p0, p1, p2);
-    // :130 — `cond ? uint3 : float3` promotes both arms to float3 before converting back to uint3
     uint32_t ax, ay, az;
-    if (k.indexed_attributes) { ax = (uint32_t)(float)ix; ay = (uint32_t)(float)iy; az = (uint32_t)(float)iz; }
-    else { ax = (uint32_t)(float)(primitiveIndex * 3 + 0); ay = (uint32_t)(float)(primitiveIndex * 3 + 1); az = (uint32_t)(float)(primitiveIndex * 3 + 2); }
+    attributeIndices(k, primitiveIndex, ix, iy, iz, ax, ay, az);
     float2 t0, t1, t2;
-    if (mesh.uv != nullptr) { t0 = ld2(mesh.uv, ax); t1 = ld2(mesh.uv, ay); t2 = ld2(mesh.uv, az); }
-    else { t0 = mk2(0, 0); t1 = mk2(1, 0); t2 = mk2(1, 1); }
+    cornerTexcoords(mesh, ax, ay, az, t0, t1, t2);
     a.texcoord = interp2(bary, t0, t1, t2);
-    getTangentBitangent(p0, p1, p2, t0, t1, t2, a.triangleFrame.s, a.triangleFrame.t);
-    a.triangleFrame.n = normalize(cross(p0 - p2, p1 - p2));
-    a.triangleFrame.reorthogonalize();
+    const DInstance* in = sc.instances + instanceIndex;
+    float m[12];
+    loadRows(in->o2w, m);
+    a.position = mulPoint(m, a.position);
+    loadRows(in->w2o, m);
+    if (MSNE_TRI_FRAMES && HIT) {
+        const float4* fr = sc.triFrames + 4 * (size_t)triIndex;
+        const float4 f0 = __ldg(fr), f1 = __ldg(fr + 1);
+        const bool inWorld = f0.w != 0.0f;
+        const float3 recN = mk3(f1.x, f1.y, f1.z);
+        a.triangleFrame.n = inWorld ? recN : normalize(mulTranspose3(m, recN));
+        a.triangleFrameComplete = false;
+        if (mesh.nrm != nullptr) {
+            const float3 n0 = ld3(mesh.nrm, ax), n1 = ld3(mesh.nrm, ay), n2 = ld3(mesh.nrm, az);
+            a.frame.s = mk3(f0.x, f0.y, f0.z);   // object-space s of the triangle frame; t is rebuilt by reorthogonalize()
+            a.frame.t = mk3(0.0f);
+            a.frame.n = normalize(interp3(bary, n0, n1, n2));
+            a.frame.reorthogonalize();
+            a.frame = a.frame.inSpaceTranspose(m);
+        } else {
+            completeTriangleFrame(sc, a, instanceIndex, triIndex);
+            a.frame = a.triangleFrame;            // the same three vectors through the same transform
+        }
+        return a;
+    }
+    a.triangleFrame = objectTriangleFrame(p0, p1, p2, t0, t1, t2);
     a.frame = a.triangleFrame;
     if (mesh.nrm != nullptr) {
         const float3 n0 = ld3(mesh.nrm, ax), n1 = ld3(mesh.nrm, ay), n2 = ld3(mesh.nrm, az);
@@ -409,15 +483,9 @@ DI MeshAttributes lookupAttributes(const DeviceScene& sc, const DConstants& k, u
         a.frame.reorthogonalize();
     }
     // inWorld
-    const DInstance* in = sc.instances + instanceIndex;
-    float m[12];
-#pragma unroll
-    for (int i = 0; i < 3; i++) { const float4 r = __ldg(reinterpret_cast<const float4*>(in->o2w) + i); m[4 * i] = r.x; m[4 * i + 1] = r.y; m[4 * i + 2] = r.z; m[4 * i + 3] = r.w; }
-    a.position = mulPoint(m, a.position);
-#pragma unroll
-    for (int i = 0; i < 3; i++) { const float4 r = __ldg(reinterpret_cast<const float4*>(in->w2o) + i); m[4 * i] = r.x; m[4 * i + 1] = r.y; m[4 * i + 2] = r.z; m[4 * i + 3] = r.w; }
     a.triangleFrame = a.triangleFrame.inSpaceTranspose(m);
     a.frame = a.frame.inSpaceTranspose(m);
+    a.triangleFrameComplete = true;
     return a;
 }
 

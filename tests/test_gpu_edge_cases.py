@@ -289,3 +289,48 @@ def test_set_geometry_material_equals_building_with_that_material():
     img_b, _, _ = gpu_render(sc, 1)
     assert not np.array_equal(img_a, a.GetSensorData(sensor) * 0)
     np.testing.assert_array_equal(img_a.view(np.uint32), img_b.view(np.uint32))
+
+
+def _one_sample_calls(m, sensor, lens, n):
+    """n HdMoonshineRender calls (one sample each, sensor read back every call) -> the n frames"""
+    frames = []
+    for _ in range(n):
+        assert m.Render(sensor, lens), m.last_error()
+        frames.append(m.GetSensorData(sensor).copy())
+    return frames
+
+
+@pytest.mark.parametrize("waves_ahead", [1, 3])
+def test_render_ahead_frames_are_the_bits_of_plain_rendering(waves_ahead):
+    """HdMoonshineExtSetRenderAhead: every call's frame and sample count are those of render-ahead off (the speculative wave is the
+    sample the next call would have rendered itself); edits, another lens and sensor clears in between drop it unseen."""
+    sc = scenes.material_zoo((96, 64))
+    sc.constants = scenes.Constants(samples_per_run=1, max_bounces=8, env_samples_per_bounce=1, mesh_samples_per_bounce=1)
+    other_lens = scenes.Lens((0.2, -3.0, 1.2), (0, 1, -0.2), (0, 0, 1), math.radians(50))
+
+    def session(ahead):
+        m = hydra.HdMoonshine()
+        _, _, _, insts = scenes.load_scene(m, sc)
+        m.SetRenderAhead(ahead)
+        sensor, lens = m.CreateSensor(*sc.extent), m.CreateLens(sc.lens)
+        lens2 = m.CreateLens(other_lens)
+        out = _one_sample_calls(m, sensor, lens, 4)
+        m.SetInstanceTransform(insts[0], [[1, 0, 0, 0.25], [0, 1, 0, 0], [0, 0, 1, 0.1]])   # an edit between two calls
+        out += _one_sample_calls(m, sensor, lens, 2)
+        out += _one_sample_calls(m, sensor, lens2, 2)                                        # another lens
+        m.SetLens(lens, other_lens)                                                          # the same handle, new values
+        out += _one_sample_calls(m, sensor, lens, 2)
+        m.ClearSensor(sensor)
+        out += _one_sample_calls(m, sensor, lens, 3)
+        assert m.SensorSampleCount(sensor) == 3
+        st = m.GetStats()
+        m.Destroy()
+        return out, st
+
+    plain, st0 = session(0)
+    ahead, st1 = session(waves_ahead)
+    assert len(plain) == len(ahead) == 13
+    for i, (a, b) in enumerate(zip(plain, ahead)):
+        assert (a.view(np.uint32) == b.view(np.uint32)).all(), f"call {i}: render-ahead frame differs"
+    assert st0.ahead_discarded == 0 and st1.ahead_discarded >= 4   # the edit, the other lens, SetLens, the clear
+    assert st1.samples == st0.samples

@@ -271,7 +271,7 @@ int main(int argc, char** argv) {
     double totalCost = 0; uint64_t totalRays = 0;
     auto measure = [&](const char* name, const std::vector<Ray>& rays) {
         uint64_t nodes = 0, leaves = 0, tris = 0, warpNode = 0, warpTri = 0, warps = 0;
-        uint64_t laneHist[33] = {0};
+        uint64_t laneHist[33] = {0}; uint64_t idleDone = 0, idleWait = 0;
         std::vector<Lane> L(32);
         for (size_t base = 0; base < rays.size(); base += 32) {
             const size_t cnt = std::min<size_t>(32, rays.size() - base);
@@ -284,6 +284,9 @@ int main(int argc, char** argv) {
                 if (!any) break;
                 // active-lane histogram of the node steps of this phase: step k of the phase is executed by the lanes with steps > k
                 for (int k = 0; k < mN; k++) { int a = 0; for (size_t i = 0; i < cnt; i++) a += steps[i] > k; laneHist[a]++; }
+                // idle lane-steps of this phase, split by cause: the lane's ray is finished / the lane waits at a leaf for the longest walk
+                idleDone += (uint64_t)mN * (32 - nAct);
+                for (size_t i = 0; i < cnt; i++) if (steps[i] || L[i].node != END) idleWait += (uint64_t)(mN - steps[i]);
                 for (size_t i = 0; i < cnt; i++) if (L[i].node != END) mT = std::max(mT, leafPhase(L[i], sc));
                 warpNode += mN; warpTri += mT;
             }
@@ -293,7 +296,8 @@ int main(int argc, char** argv) {
             uint64_t tot = 0; for (int a = 0; a <= 32; a++) tot += laneHist[a];
             uint64_t acc = 0; printf("   node steps by active lanes (cumulative %%):");
             for (int a = 1; a <= 32; a++) { acc += laneHist[a]; if (a == 1 || a == 2 || a == 4 || a == 8 || a == 16 || a == 24 || a == 32) printf(" <=%d: %.0f", a, 100.0 * acc / tot); }
-            printf("\n");
+            printf("\n   lane-steps: useful %.0f %%, idle because the ray is finished %.0f %%, idle at a leaf waiting for the longest walk %.0f %%\n",
+                   100.0 * nodes / (32.0 * warpNode), 100.0 * idleDone / (32.0 * warpNode), 100.0 * idleWait / (32.0 * warpNode));
         }
         const double nr = (double)rays.size();
         const double cost = (warpNode * CN + warpTri * CT);
@@ -385,6 +389,49 @@ int main(int argc, char** argv) {
                 }
                 printf("vote b%d T=%2d: cost/ray %6.1f (+%.1f with the vote) node-its %.2f tri-its %.2f per ray\n", b, T, (nodeIt * CN + triIt * CT) / rays.size(),
                        its * CB / rays.size(), (double)nodeIt / rays.size(), (double)triIt / rays.size());
+            }
+        }
+    }
+    // MSNE_SIM_SUSPEND: model of suspend-and-regroup - when, after an outer iteration, at most T lanes of a warp are still walking
+    // (and the warp has run at least MIN node steps), those lanes write their traversal state to a continuation list and the warp
+    // takes its next ticket; the continuations are walked 32 at a time in a second pass (same rule), a third pass runs to the end.
+    if (getenv("MSNE_SIM_SUSPEND")) {
+        const double CS = 80, CR = 60;   // warp instructions of one suspend event (<= T lanes store state + stack) / one resumed warp (loads)
+        for (int b = 2; b <= 3; b++) {
+            for (int kind = 0; kind < 2; kind++) {
+                const std::vector<Ray>& rays = kind == 0 ? byBounce[b] : shadowBy[b];
+                for (int T : {0, 2, 4, 6, 8, 12, 16}) {
+                    uint64_t warpNode = 0, warpTri = 0, suspends = 0, resumedWarps = 0, suspendedRays = 0;
+                    std::vector<Lane> cur, next;
+                    cur.resize(rays.size());
+                    for (size_t i = 0; i < rays.size(); i++) start(cur[i], rays[i]);
+                    for (int pass = 0; pass < 3 && !cur.empty(); pass++) {
+                        next.clear();
+                        const int Tp = pass == 2 ? 0 : T;
+                        for (size_t base = 0; base < cur.size(); base += 32) {
+                            const size_t cnt = std::min<size_t>(32, cur.size() - base);
+                            Lane* L = &cur[base];
+                            if (pass) resumedWarps++;
+                            for (;;) {
+                                int mN = 0, mT = 0, act = 0;
+                                for (size_t i = 0; i < cnt; i++) if (L[i].node != END) mN = std::max(mN, innerPhase(L[i], sc));
+                                for (size_t i = 0; i < cnt; i++) if (L[i].node != END) mT = std::max(mT, leafPhase(L[i], sc));
+                                warpNode += mN; warpTri += mT;
+                                for (size_t i = 0; i < cnt; i++) act += L[i].node != END;
+                                if (act == 0) break;
+                                if (act <= Tp) {
+                                    for (size_t i = 0; i < cnt; i++) if (L[i].node != END) { next.push_back(L[i]); suspendedRays++; }
+                                    suspends++;
+                                    break;
+                                }
+                            }
+                        }
+                        cur.swap(next);
+                    }
+                    const double cost = warpNode * CN + warpTri * CT + suspends * CS + resumedWarps * CR;
+                    printf("suspend %s b%d T=%2d: cost/ray %6.1f (node-steps %.2f tri-steps %.2f per ray; %.1f %% of the rays suspended)\n", kind ? "shadow" : "ext   ", b, T,
+                           cost / rays.size(), (double)warpNode / rays.size(), (double)warpTri / rays.size(), 100.0 * suspendedRays / rays.size());
+                }
             }
         }
     }
