@@ -37,12 +37,6 @@ inline void setEmptyChild(BvhNode2& n, int s) {
     xy[0] = xy[1] = xy[2] = xy[3] = 3e38f; n.n2[2 * s] = n.n2[2 * s + 1] = 3e38f;
 }
 
-// BVH4 node for the quad-cooperative trace kernel (kernels.cu k_trace4; experiment, MSNE_TRACE4): four 32-byte child records, so
-// the four lanes that share a ray read one 128-byte line, 32 bytes each:
-//   child j: (lo.x, lo.y, lo.z, hi.x) (hi.y, hi.z, ref bits, -)     ref: >= 0 node index, < 0 leaf (same encoding as BvhNode2), REF_EMPTY
-struct BvhNode4 { float child[4][8]; };
-static_assert(sizeof(BvhNode4) == 128, "BvhNode4 must be 128 B");
-
 static const int32_t REF_ITEM = 0x40000000, REF_EMPTY = 0x7FFFFFFD, REF_LEAVE = 0x7FFFFFFE, REF_END = 0x7FFFFFFF;
 
 // Triangle record, 48 B: three vertices in object space + ids (watertight edge test needs all three)
@@ -87,7 +81,6 @@ struct DeviceScene {
     const BvhNode2* tlasNodes;     // may be null when there are no visible instances
     const uint32_t* tlasItems;     // TLAS leaf slot -> instance index
     const BvhNode2* blasNodes;     // pooled BLAS nodes
-    const BvhNode4* static4;       // 4-wide collapse of the merged static BLAS (root = node 0), or null (MSNE_TRACE4 experiment)
     const TriRec* tris;            // pooled triangles (leaf order)
     const float4* triFrames;       // per pooled triangle 64 B: its tangent frame, evaluated once per build (shading.cuh MSNE_TRI_FRAMES, kernels.cu k_tri_frames)
     const DInstance* instances;

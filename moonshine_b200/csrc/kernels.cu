@@ -308,173 +308,6 @@ __global__ void __launch_bounds__(TRACE_THREADS, TWO_LEVEL ? TRACE_BLOCKS_PER_SM
 }
 
 // ------------------------------------------------------------------------------------------------
-// k_trace4 (experiment, MSNE_TRACE4=1; single-level scenes only): FOUR lanes share one ray. The quad reads one 128-byte BVH4 node
-// per step - each lane tests one child box - orders the children it hits with three shuffles and keeps the rest on a shared-memory
-// stack; at a leaf each lane tests one triangle. A quad that finishes its ray takes the next one of the warp's ticket straight
-// away, so the eight quads of a warp never wait for the longest ray of a ticket (what keeps k_trace at 13 of 32 lanes). The
-// exact triangle test and the id tie-break make the results independent of the tree, so this kernel and k_trace agree bit for bit.
-// ------------------------------------------------------------------------------------------------
-#define TRACE4_STACK 64
-template <bool SORTED>
-__global__ void __launch_bounds__(TRACE_THREADS, 6) k_trace4(DeviceScene sc, PathBuffers pb, WaveState ws, uint32_t buf,
-                                                              const uint32_t* __restrict__ permExt, const uint32_t* __restrict__ permShadow) {
-    __shared__ int stack[TRACE_THREADS / 4][TRACE4_STACK];
-    const Counters cin = ws.counters[buf];
-    const uint32_t nLive = cin.nLive, nShadow = cin.nShadow;
-    const uint32_t live32 = (nLive + 31u) & ~31u;
-    const uint32_t total = live32 + nShadow;
-    const uint32_t lane = threadIdx.x & 31u, sub = lane & 3u, quadBase = lane & ~3u;
-    int* myStack = stack[threadIdx.x >> 2];
-    const float4* __restrict__ extRays = pb.R0[buf];
-    const float4* __restrict__ shadowRays = pb.Q0;
-    constexpr uint32_t NONE = 0xFFFFFFFFu, DONE = 0xFFFFFFFEu;
-    constexpr int END = REF_END;
-    // per-quad state (the same values in its four lanes)
-    uint32_t slot = NONE;        // queue slot of the ray in flight
-    bool isExt = false;
-    SpaceRay ray;
-    float bestT = 0.0f, hu = 0.0f, hv = 0.0f;
-    uint32_t hitInst = MISS_ID, hitTri = 0;
-    int node = END, sp = 0;
-    uint32_t shadowTarget = 0;
-    uint32_t tBase = 0, tPos = 32u;   // the warp's ticket: next unassigned position (warp-uniform)
-    bool drained = false;             // the ticket counter ran past the queue (warp-uniform)
-    for (;;) {
-        // ---- hand rays to idle quads ------------------------------------------------------------------------------------------
-        const uint32_t needMask = __ballot_sync(0xFFFFFFFFu, slot == NONE && sub == 0u);
-        if (needMask && !drained) {
-            if (tPos >= 32u) {
-                uint32_t b = 0;
-                if (lane == 0) b = atomicAdd(ws.traceTicket, 32u);
-                tBase = __shfl_sync(0xFFFFFFFFu, b, 0);
-                tPos = 0;
-                if (tBase >= total) drained = true;
-            }
-            if (!drained) {
-                const uint32_t rank = (uint32_t)__popc(needMask & ((1u << quadBase) - 1u));
-                const uint32_t want = (uint32_t)__popc(needMask), give = want < 32u - tPos ? want : 32u - tPos;
-                if (slot == NONE && rank < give) {
-                    const uint32_t i = tBase + tPos + rank;
-                    uint32_t q = NONE;
-                    if (i < live32) { if (i < nLive) q = SORTED ? __ldg(permExt + i) : i; }
-                    else if (i < total) q = SORTED ? __ldg(permShadow + (i - live32)) : i - live32;
-                    if (q != NONE) {
-                        isExt = i < live32;
-                        const float4* src = (isExt ? extRays : shadowRays) + RAY_STRIDE * (size_t)q;
-                        const float4 r0 = qld(src), r1 = qld(src + 1);
-                        ray.set(mk3(r0.x, r0.y, r0.z), mk3(r1.x, r1.y, r1.z));
-                        bestT = isExt ? MS_INFINITY : r0.w;
-                        shadowTarget = __float_as_uint(r1.w);
-                        hitInst = MISS_ID; hitTri = 0; hu = 0.0f; hv = 0.0f;
-                        node = 0; sp = 0; slot = q;
-                    }
-                }
-                tPos += give;
-            }
-        }
-        if (drained && slot == NONE) slot = DONE;
-        if (__ballot_sync(0xFFFFFFFFu, slot < DONE) == 0u) break;
-        const bool active = slot < DONE;
-        // ---- inner node: one child box per lane ---------------------------------------------------------------------------
-        const uint32_t innerMask = __ballot_sync(0xFFFFFFFFu, active && node >= 0 && node != END);
-        if (active && node >= 0 && node != END) {
-            const float4* cp = reinterpret_cast<const float4*>(sc.static4 + node) + sub * 2u;
-            const float4 a = __ldg(cp), b = __ldg(cp + 1);
-            const int ref = __float_as_int(b.z);
-            float tn;
-            const bool h = slab(ray, a.x, a.w, a.y, b.x, a.z, b.y, 0.0f, bestT, tn);   // an empty child's box is unreachable
-            const uint32_t m = (__ballot_sync(innerMask, h) >> quadBase) & 0xFu;
-            // rank among the hit children by entry distance (ties by child index)
-            uint32_t rank = 0;
-#pragma unroll
-            for (uint32_t j = 0; j < 4u; j++) {
-                const float tj = __shfl_sync(innerMask, tn, (int)(quadBase + j));
-                if (((m >> j) & 1u) && (tj < tn || (tj == tn && j < sub))) rank++;
-            }
-            const uint32_t cnt = (uint32_t)__popc(m);
-            const uint32_t firstBits = (__ballot_sync(innerMask, h && rank == 0u) >> quadBase) & 0xFu;
-            const int next = __shfl_sync(innerMask, ref, (int)(quadBase + (firstBits ? (uint32_t)__ffs((int)firstBits) - 1u : 0u)));
-            if (cnt == 0u) node = sp ? myStack[--sp] : END;
-            else {
-                if (h && rank > 0u && sp + (int)(cnt - 1u - rank) < TRACE4_STACK) myStack[sp + (int)(cnt - 1u - rank)] = ref;   // nearest of the rest on top
-                sp += (int)cnt - 1;
-                node = next;
-            }
-            __syncwarp(innerMask);   // the quad's stack writes are visible to its four lanes before anybody pops
-        }
-        // ---- leaf: one triangle per lane ----------------------------------------------------------------------------------
-        const uint32_t leafMask = __ballot_sync(0xFFFFFFFFu, active && node < 0);
-        if (active && node < 0) {
-            const uint32_t x = ~(uint32_t)node, first = x >> 3, count = (x & 7u) + 1u;
-            float t = MS_INFINITY, u = 0.0f, v = 0.0f;
-            uint32_t inst = MISS_ID, geom = 0, prim = 0, tri = first + sub;
-            bool hit = false;
-            if (sub < count) {
-                const float4* tp = reinterpret_cast<const float4*>(sc.tris + tri);
-                const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
-                hit = triTest(t0, t1, t2, ray, 0.0f, isExt ? MS_INFINITY : bestT, t, u, v);
-                inst = __float_as_uint(t2.w); geom = __float_as_uint(t0.w); prim = __float_as_uint(t1.w);
-                if (hit && sc.staticHidden && !__ldg(&sc.instances[inst].visible)) hit = false;
-                if (!hit) { t = MS_INFINITY; inst = MISS_ID; }
-            }
-            // a warp holds extension and shadow quads at once: each kind synchronises over its own lanes only
-            const uint32_t shadowLeaf = __ballot_sync(leafMask, !isExt), extLeaf = leafMask & ~shadowLeaf;
-            if (!isExt) {
-                // any hit ends a shadow ray
-                if ((__ballot_sync(shadowLeaf, hit) >> quadBase) & 0xFu) { hitInst = 0; node = END; }
-                else node = sp ? myStack[--sp] : END;
-            } else {
-                // the quad's best candidate: min t, ties -> smallest (instance, geometry, primitive)
-#pragma unroll
-                for (int o = 1; o <= 2; o <<= 1) {
-                    const float t_ = __shfl_xor_sync(extLeaf, t, o), u_ = __shfl_xor_sync(extLeaf, u, o), v_ = __shfl_xor_sync(extLeaf, v, o);
-                    const uint32_t i_ = __shfl_xor_sync(extLeaf, inst, o), g_ = __shfl_xor_sync(extLeaf, geom, o), p_ = __shfl_xor_sync(extLeaf, prim, o);
-                    const uint32_t r_ = __shfl_xor_sync(extLeaf, tri, o);
-                    const bool other = t_ < t || (t_ == t && i_ != MISS_ID && (i_ != inst ? i_ < inst : (g_ != geom ? g_ < geom : p_ < prim)));
-                    if (other) { t = t_; u = u_; v = v_; inst = i_; geom = g_; prim = p_; tri = r_; }
-                }
-                if (inst != MISS_ID) {
-                    bool better = t < bestT;
-                    if (!better && t == bestT && hitInst != MISS_ID) {
-                        if (inst != hitInst) better = inst < hitInst;
-                        else {
-                            const uint32_t bg = sc.tris[hitTri].geom, bp = sc.tris[hitTri].prim;
-                            better = geom != bg ? geom < bg : prim < bp;
-                        }
-                    }
-                    if (better) { bestT = t; hitInst = inst; hitTri = tri; hu = u; hv = v; }
-                }
-                node = sp ? myStack[--sp] : END;
-            }
-        }
-        // ---- a finished ray: publish, free the quad ----------------------------------------------------------------------------
-        if (active && node == END) {
-            if (sub == 0u) {
-                if (isExt) {
-                    HitRec hr; hr.inst = hitInst; hr.tri = hitTri; hr.u = hu; hr.v = hv;
-                    const uint32_t bin = hitBin(sc, hr);
-                    qst(pb.H + slot, make_uint4(hitInst, hitTri | (bin << H_BIN_SHIFT), __float_as_uint(hu), __float_as_uint(hv)));
-                } else if (hitInst != MISS_ID) {
-                    float4* n = (shadowTarget & 1u) ? pb.N1[buf] : pb.N0[buf];
-                    n[shadowTarget >> 1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            }
-            slot = NONE;
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        const uint32_t done = atomicAdd(ws.traceDone, 1u);
-        if (done == gridDim.x - 1) {
-            *ws.traceTicket = 0; *ws.traceDone = 0;
-            ws.rayCounts[0] += nLive; ws.rayCounts[1] += nShadow;
-            __threadfence();
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
 // ray reordering for incoherent bounces (runtime.cpp: only queues above the sort threshold)
 // ------------------------------------------------------------------------------------------------
 // 16-bit key of a queued ray: [14:12] direction octant, [11:0] origin cell (z, y, x cell coordinates concatenated; thousands of
@@ -1300,17 +1133,7 @@ void launchGenerate(cudaStream_t st, const DCamera& cam, const DConstants& k, co
                     uint32_t nPix, uint32_t nSamples, uint32_t firstSample) {
     k_generate<<<grid1((uint64_t)nPix * nSamples, 256), 256, 0, st>>>(cam, k, pb, counters, pixIds, nPix, nSamples, firstSample);
 }
-static int trace4Blocks() {
-    static int n = [] {
-        int dev = 0, sms = 148, per = 0;
-        cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, k_trace4<true>, TRACE_THREADS, 0);
-        return sms * (per > 0 ? per : 1);
-    }();
-    return n;
-}
 void launchTrace(cudaStream_t st, int blocks, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf) {
-    if (sc.static4) { k_trace4<false><<<trace4Blocks(), TRACE_THREADS, 0, st>>>(sc, pb, ws, buf, nullptr, nullptr); return; }
     if (sc.staticOnly) k_trace<false, false><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf, nullptr, nullptr);
     else k_trace<true, false><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf, nullptr, nullptr);
 }
@@ -1329,7 +1152,6 @@ void launchSortRays(cudaStream_t st, int smCount, const SortBuffers& sb, const C
     k_sort_scatter<<<dim3(smCount, 2), SORT_THREADS, smemBytes, st>>>(j);
 }
 void launchTraceSorted(cudaStream_t st, int blocks, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const uint32_t* permExt, const uint32_t* permShadow) {
-    if (sc.static4) { k_trace4<true><<<trace4Blocks(), TRACE_THREADS, 0, st>>>(sc, pb, ws, buf, permExt, permShadow); return; }
     if (sc.staticOnly) k_trace<false, true><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf, permExt, permShadow);
     else k_trace<true, true><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf, permExt, permShadow);
 }
@@ -1355,9 +1177,9 @@ void launchShadeBinned(cudaStream_t st, int blocks, const DeviceScene& sc, const
     k_shade<2, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, -1, keys);   // PerfectMirror
     k_shade<4, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, slot, keys);   // miss + dead
 }
-void launchTail(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf, bool inlineNee) {
-    if (inlineNee) k_tail<true><<<blocks, 128, 0, st>>>(sc, k, pb, ws, buf);
-    else k_tail<false><<<blocks, 128, 0, st>>>(sc, k, pb, ws, buf);
+void launchTail(cudaStream_t st, int blocks, int threads, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf, bool inlineNee) {
+    if (inlineNee) k_tail<true><<<blocks, threads, 0, st>>>(sc, k, pb, ws, buf);
+    else k_tail<false><<<blocks, threads, 0, st>>>(sc, k, pb, ws, buf);
 }
 void launchAccumulate(cudaStream_t st, const float4* result, float4* image, float4* runState, const uint32_t* pixIds, uint32_t nPix, uint32_t nSamples,
                       uint32_t firstSample, uint32_t spr) {

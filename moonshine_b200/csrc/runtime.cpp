@@ -254,8 +254,6 @@ struct HdMoonshine {
     bool emitterFollowsEdits = false, emitterStale = false;
 
     DevBuf<BvhNode2> dTlasNodes, dBlasNodes;
-    DevBuf<BvhNode4> dStatic4;       // MSNE_TRACE4=1: 4-wide collapse of the merged static BLAS for the quad-cooperative trace kernel
-    bool trace4 = false;
     DevBuf<uint32_t> dTlasItems;
     DevBuf<TriRec> dTris;
     DevBuf<DInstance> dInstances;
@@ -331,6 +329,7 @@ struct HdMoonshine {
     cudaEvent_t lastAccumEvent = nullptr;
     int traceBlocks = 0, shadeBlocks = 0, shadeInlineBlocks = 0;
     uint32_t maxLeaf = 3;   // triangles per BVH leaf (<= 8: 3-bit count in the leaf reference); 2-3 measured best
+    int tailBlockThreads = 128;       // k_tail block size (32, 64 or 128; MSNE_TAIL_BLOCK): a block holds its registers until its longest path ends
     uint64_t tailThreshold = 32768;   // once fewer paths than this are expected to survive, k_tail finishes the wave
     bool forceTwoLevel = false;       // MSNE_TWO_LEVEL=1: never use the single-level trace kernel (A/B measurements)
     bool logBounces = false;          // MSNE_LOG_BOUNCES=1: queue sizes after every bounce on stderr (printed when the wave's log is read)
@@ -378,9 +377,9 @@ struct HdMoonshine {
         if (const char* e = getenv("MSNE_TLAS_MAX_REFITS")) maxRefits = (uint32_t)std::max(0, atoi(e));
         if (const char* e = getenv("MSNE_TWO_LEVEL")) forceTwoLevel = atoi(e) != 0;
         if (const char* e = getenv("MSNE_LOG_BOUNCES")) logBounces = atoi(e) != 0;
+        if (const char* e = getenv("MSNE_TAIL_BLOCK")) { const int t = atoi(e); if (t == 32 || t == 64 || t == 128) tailBlockThreads = t; }
         if (const char* e = getenv("MSNE_TAIL_THRESHOLD")) tailThreshold = strtoull(e, nullptr, 10);
         if (const char* e = getenv("MSNE_SORT_THRESHOLD")) { sortThreshold = strtoull(e, nullptr, 10); sortAnyScene = true; }
-        if (const char* e = getenv("MSNE_TRACE4")) trace4 = atoi(e) != 0;
         if (const char* e = getenv("MSNE_TILE_EDGE")) tileEdge = (uint32_t)std::min(256, std::max(8, atoi(e) / 8 * 8));
         if (const char* e = getenv("MSNE_WAVE_CONTEXTS")) waveContextsInUse = std::min(kWaveContexts, std::max(1, atoi(e)));
         if (const char* e = getenv("MSNE_BINNED_THRESHOLD")) binnedThreshold = strtoull(e, nullptr, 10);
@@ -489,56 +488,6 @@ struct HdMoonshine {
         buildBvh2(boxes.data(), (uint32_t)boxes.size(), maxLeaf, out, depthLimit - lg - 1);
         if (out.depth > depthLimit) throw std::runtime_error("acceleration structure: depth limit not met");
     }
-    // 4-wide collapse of the pooled BVH2 rooted at `root` (references already in their device encoding): a node's children are
-    // its BVH2 children with the largest inner ones replaced by THEIR children until there are four.
-    void collapseStatic4(uint32_t root) {
-        struct Cand { float lo[3], hi[3]; int32_t ref; };
-        auto childOf = [&](const BvhNode2& n, int s) {
-            Cand c;
-            const float* xy = s == 0 ? n.n0 : n.n1;
-            c.lo[0] = xy[0]; c.hi[0] = xy[1]; c.lo[1] = xy[2]; c.hi[1] = xy[3]; c.lo[2] = n.n2[2 * s]; c.hi[2] = n.n2[2 * s + 1];
-            c.ref = n.c[s];
-            return c;
-        };
-        auto area = [](const Cand& c) { const float dx = c.hi[0] - c.lo[0], dy = c.hi[1] - c.lo[1], dz = c.hi[2] - c.lo[2]; return dx * dy + dy * dz + dz * dx; };
-        std::vector<BvhNode4> out;
-        std::vector<std::pair<uint32_t, uint32_t>> work;   // (BVH2 node, BVH4 slot)
-        out.emplace_back(); work.push_back({root, 0});
-        while (!work.empty()) {
-            const auto [n2, n4] = work.back(); work.pop_back();
-            std::vector<Cand> cand;
-            for (int s = 0; s < 2; s++) if (blasNodePool[n2].c[s] != REF_EMPTY) cand.push_back(childOf(blasNodePool[n2], s));
-            while (cand.size() < 4) {
-                int best = -1;
-                for (size_t i = 0; i < cand.size(); i++)
-                    if (cand[i].ref >= 0 && cand[i].ref < REF_ITEM && (best < 0 || area(cand[i]) > area(cand[(size_t)best]))) best = (int)i;
-                if (best < 0) break;
-                const BvhNode2& inner = blasNodePool[(size_t)cand[(size_t)best].ref];
-                int nonEmpty = 0;
-                for (int s = 0; s < 2; s++) if (inner.c[s] != REF_EMPTY) nonEmpty++;
-                if (cand.size() - 1 + (size_t)nonEmpty > 4) break;
-                cand.erase(cand.begin() + best);
-                for (int s = 0; s < 2; s++) if (inner.c[s] != REF_EMPTY) cand.push_back(childOf(inner, s));
-            }
-            BvhNode4 node;
-            for (int j = 0; j < 4; j++) {
-                float* r = node.child[j];
-                if (j < (int)cand.size()) {
-                    const Cand& c = cand[(size_t)j];
-                    r[0] = c.lo[0]; r[1] = c.lo[1]; r[2] = c.lo[2]; r[3] = c.hi[0]; r[4] = c.hi[1]; r[5] = c.hi[2];
-                    int32_t ref = c.ref;
-                    if (ref >= 0 && ref < REF_ITEM) { out.emplace_back(); ref = (int32_t)out.size() - 1; work.push_back({(uint32_t)c.ref, (uint32_t)ref}); }
-                    memcpy(&r[6], &ref, 4); r[7] = 0.0f;
-                } else {
-                    for (int q = 0; q < 6; q++) r[q] = 3e38f;
-                    const int32_t ref = REF_EMPTY; memcpy(&r[6], &ref, 4); r[7] = 0.0f;
-                }
-            }
-            out[n4] = node;
-        }
-        dStatic4.upload(out.data(), out.size(), stream);
-        CK(cudaStreamSynchronize(stream));
-    }
     uint32_t getBlas(const std::vector<uint32_t>& key) {
         auto it = blasByKey.find(key);
         if (it != blasByKey.end()) return it->second;
@@ -592,7 +541,6 @@ struct HdMoonshine {
             maxBlasDepth = std::max(maxBlasDepth, bvh.depth);
             staticRec.blasRoot = appendBlas(bvh, stTris, stMesh);
             staticBounds = bvh.bounds;
-            if (trace4) collapseStatic4(staticRec.blasRoot);
         }
         for (uint32_t i = 0; i < nInst; i++) {
             HostInstance& in = instances[i];
@@ -863,7 +811,6 @@ struct HdMoonshine {
         sc.texLuts = dSrgbLut.p;
         sc.staticOnly = (tlasStaticOnly && !forceTwoLevel) ? 1u : 0u; sc.staticRoot = staticRec.blasRoot;
         sc.staticHidden = hiddenStaticTris ? 1u : 0u;
-        sc.static4 = (trace4 && haveStatic && sc.staticOnly) ? dStatic4.p : nullptr;
         return sc;
     }
     DConstants deviceConstants() const {
@@ -1119,7 +1066,6 @@ struct HdMoonshine {
                 launchTrace(st, traceBlocks, sc, pb, ws, buf);
                 if (prof) { CK(cudaEventRecord(c.profEv[c.profUsed][1], st)); c.profUsed++; }
                 stats.kernel_launches += 1;
-                if (sc.static4 && !inlineNee && expectedIn(b, nPaths) >= (double)binnedThreshold) { launchBin(st, smCount, pb, ws, buf); stats.kernel_launches += 1; }   // k_trace4 leaves the binning to k_bin
             }
             // the rays this pass queues get their sort keys from it when the next bounce is going to be traced in sorted order
             SortKeys keys{};
@@ -1132,7 +1078,7 @@ struct HdMoonshine {
         // whatever is still alive (normally < tailThreshold paths; more only when the profile was off): trace once more and let
         // k_tail finish every remaining path in a single launch instead of ~130 launch pairs at the latency floor
         launchTrace(st, traceBlocks, sc, pb, ws, K & 1u);
-        launchTail(st, smCount * 4, sc, k, pb, ws, K & 1u, inlineNee);
+        launchTail(st, smCount * 4 * (128 / tailBlockThreads), tailBlockThreads, sc, k, pb, ws, K & 1u, inlineNee);
         stats.kernel_launches += 2;
         CK(cudaMemcpyAsync(c.hostHistory, c.dHistory.p, K * sizeof(Counters), cudaMemcpyDeviceToHost, st));
         c.bounces = K; c.paths = nPaths;
