@@ -114,6 +114,10 @@ MSNE_API void HdMoonshineExtSetProfiling(HdMoonshine*, bool per_kernel_events);
  * (32768, 262144, 2). Also forgets the survival profile learnt from earlier waves. */
 MSNE_API void HdMoonshineExtSetSchedule(HdMoonshine*, uint64_t tail_paths, uint64_t binned_paths, uint32_t wave_contexts);
 
+/* Suspend-and-regroup tracing (performance hint, same bits): in sorted bounces of scenes without transformed instances a warp of the
+ * trace kernel hands its last `lanes` walking rays (0 = off, at most 16) to a later pass that walks such long rays together, instead
+ * of idling its other lanes until they end. MSNE_TRACE_SUSPEND=<lanes> sets it at creation. */
+MSNE_API void HdMoonshineExtSetTraceSuspend(HdMoonshine*, uint32_t lanes);
 /* Render-ahead for one-sample-per-call rendering (the Hydra delegate's pattern, hydra/hydra.zig:316-358). waves_ahead > 0:
  * HdMoonshineRender keeps that many FURTHER samples' waves (same sensor, lens, scene; at most 3) in flight when it waits for its own,
  * holds their samples back from the sensor, and the following HdMoonshineRender calls claim them one by one if they ask for exactly

@@ -308,6 +308,118 @@ __global__ void __launch_bounds__(TRACE_THREADS, TWO_LEVEL ? TRACE_BLOCKS_PER_SM
 }
 
 // ------------------------------------------------------------------------------------------------
+// k_trace_rs: sorted bounce of a static-only scene with suspend-and-regroup (kernels.h ContBuffers, traverse.cuh walkResumable).
+// A while-while warp is kept until its longest ray ends; in a sorted bounce 26 % of a warp's lane-steps are lanes whose ray is
+// finished (tools/bvh_sim.cpp). Here the last few walking lanes of a warp write their traversal state to a continuation record
+// and the warp takes its next ticket; the records - the long rays of the bounce - are walked together, 32 per warp, by the next
+// pass. Results are those of k_trace bit for bit (same walk, same tie-break; hit records land in the same slots).
+// PASS 0: tickets over the sorted queues (as k_trace<false, true>), PASS 1 / 2: tickets over the records of recA / recB.
+// ------------------------------------------------------------------------------------------------
+#define RS_REC_U4 8   // uint4 per record: 2 header + 6 x 4 stack entries
+template <int PASS>
+__global__ void __launch_bounds__(TRACE_THREADS, TRACE1_BLOCKS_PER_SM) k_trace_rs(DeviceScene sc, PathBuffers pb, WaveState ws, uint32_t buf, const uint32_t* __restrict__ permExt,
+                                                                                  const uint32_t* __restrict__ permShadow, ContBuffers cb, uint32_t threshold) {
+    __shared__ uint32_t liveCount[TRACE_THREADS / 32];
+    const Counters cin = ws.counters[buf];
+    const uint32_t nLive = cin.nLive, nShadow = cin.nShadow;
+    const uint32_t live32 = (nLive + 31u) & ~31u;
+    const uint32_t total = PASS == 0 ? live32 + nShadow : cb.counts[PASS - 1];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t ltMask = (1u << lane) - 1u;
+    const float4* __restrict__ extRays = pb.R0[buf];
+    const float4* __restrict__ shadowRays = pb.Q0;
+    const uint4* __restrict__ inRec = PASS == 1 ? cb.recA : cb.recB;
+    uint4* outRec = PASS == 0 ? cb.recA : cb.recB;
+    uint32_t* outCount = cb.counts + (PASS == 0 ? 0 : 1);
+    const uint32_t thr = PASS == 2 ? 0u : threshold;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(ws.traceTicket, 32u);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (base >= total) break;
+        const uint32_t i = base + lane;
+        uint32_t idx = 0xFFFFFFFFu;
+        bool ext = false;
+        WalkState w;
+        w.node = (int)sc.staticRoot; w.sp = 1; w.bestT = 0.0f; w.inst = MISS_ID; w.tri = 0; w.u = 0.0f; w.v = 0.0f;
+        int stack[MSNE_STACK];
+        stack[0] = REF_FINISH;
+        if (PASS == 0) {
+            ext = base < live32;
+            if (ext) { if (i < nLive) idx = __ldg(permExt + i); }
+            else if (i < total) idx = __ldg(permShadow + (i - live32));
+        } else if (i < total) {
+            const uint4* rec = inRec + (size_t)i * RS_REC_U4;
+            const uint4 h0 = rec[0], h1 = rec[1];
+            idx = h0.x & 0x7FFFFFFFu; ext = (h0.x >> 31) != 0u;
+            w.bestT = __uint_as_float(h0.y); w.inst = h0.z; w.tri = h0.w;
+            w.u = __uint_as_float(h1.x); w.v = __uint_as_float(h1.y); w.node = (int)h1.z; w.sp = (int)h1.w;
+            for (int j = 0; j < w.sp; j += 4) {
+                const uint4 e = rec[2 + (j >> 2)];
+                stack[j] = (int)e.x; stack[j + 1] = (int)e.y; stack[j + 2] = (int)e.z; stack[j + 3] = (int)e.w;
+            }
+        }
+        const bool valid = idx != 0xFFFFFFFFu;
+        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+        if (valid) {
+            const float4* src = (ext ? extRays : shadowRays) + RAY_STRIDE * (size_t)idx;
+            r0 = qld(src); r1 = qld(src + 1);
+        }
+        const uint32_t validMask = __ballot_sync(0xFFFFFFFFu, valid);
+        if (lane == 0) liveCount[warp] = (uint32_t)__popc(validMask);
+        __syncwarp();
+        bool suspended = false;
+        if (valid) {
+            SpaceRay ray; ray.set(mk3(r0.x, r0.y, r0.z), mk3(r1.x, r1.y, r1.z));
+            if (ext) {
+                if (PASS == 0) w.bestT = MS_INFINITY;
+                suspended = walkResumable<false>(sc, ray, 0.0f, MS_INFINITY, w, stack, &liveCount[warp], thr);
+            } else {
+                if (PASS == 0) w.bestT = r0.w;
+                suspended = walkResumable<true>(sc, ray, 0.0f, r0.w, w, stack, &liveCount[warp], thr);
+            }
+        }
+        __syncwarp();
+        if (valid && !suspended) {
+            if (ext) {
+                HitRec h; h.inst = w.inst; h.tri = w.tri; h.u = w.u; h.v = w.v;
+                const uint32_t bin = hitBin(sc, h);
+                qst(pb.H + idx, make_uint4(h.inst, h.tri | (bin << H_BIN_SHIFT), __float_as_uint(h.u), __float_as_uint(h.v)));
+            } else if (w.inst != MISS_ID) {
+                const uint32_t target = __float_as_uint(r1.w);
+                float4* n = (target & 1u) ? pb.N1[buf] : pb.N0[buf];
+                n[target >> 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        // ---- the lanes that stopped: one reservation per warp, one record per lane
+        const uint32_t susMask = __ballot_sync(0xFFFFFFFFu, suspended);
+        if (susMask) {
+            uint32_t rb = 0;
+            if (lane == 0) rb = atomicAdd(outCount, (uint32_t)__popc(susMask));
+            rb = __shfl_sync(0xFFFFFFFFu, rb, 0);
+            if (suspended) {
+                uint4* rec = outRec + (size_t)(rb + __popc(susMask & ltMask)) * RS_REC_U4;
+                rec[0] = make_uint4(idx | (ext ? 0x80000000u : 0u), __float_as_uint(w.bestT), w.inst, w.tri);
+                rec[1] = make_uint4(__float_as_uint(w.u), __float_as_uint(w.v), (uint32_t)w.node, (uint32_t)w.sp);
+                for (int j = 0; j < w.sp; j += 4) rec[2 + (j >> 2)] = make_uint4((uint32_t)stack[j], (uint32_t)stack[j + 1], (uint32_t)stack[j + 2], (uint32_t)stack[j + 3]);
+            }
+        }
+    }
+    // last block out: re-arm the ticket; pass 0 publishes the ray counts, passes 1 and 2 clear the record count they consumed
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const uint32_t done = atomicAdd(ws.traceDone, 1u);
+        if (done == gridDim.x - 1) {
+            *ws.traceTicket = 0; *ws.traceDone = 0;
+            if (PASS == 0) { ws.rayCounts[0] += nLive; ws.rayCounts[1] += nShadow; }
+            else cb.counts[PASS - 1] = 0;
+            __threadfence();
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // ray reordering for incoherent bounces (runtime.cpp: only queues above the sort threshold)
 // ------------------------------------------------------------------------------------------------
 // 16-bit key of a queued ray: [14:12] direction octant, [11:0] origin cell (z, y, x cell coordinates concatenated; thousands of
@@ -1154,6 +1266,13 @@ void launchSortRays(cudaStream_t st, int smCount, const SortBuffers& sb, const C
 void launchTraceSorted(cudaStream_t st, int blocks, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const uint32_t* permExt, const uint32_t* permShadow) {
     if (sc.staticOnly) k_trace<false, true><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf, permExt, permShadow);
     else k_trace<true, true><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf, permExt, permShadow);
+}
+void launchTraceSuspend(cudaStream_t st, int blocks, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const uint32_t* permExt,
+                        const uint32_t* permShadow, const ContBuffers& cb, uint32_t threshold, int passes) {
+    // passes: 3 = suspend twice (records A, then B), 2 = suspend once (pass 1 walks the records to the end), 1 = never (measurement: the kernel alone)
+    k_trace_rs<0><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf, permExt, permShadow, cb, passes >= 2 ? threshold : 0u);
+    if (passes >= 2) k_trace_rs<1><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf, permExt, permShadow, cb, passes >= 3 ? threshold : 0u);
+    if (passes >= 3) k_trace_rs<2><<<blocks, TRACE_THREADS, 0, st>>>(sc, pb, ws, buf, permExt, permShadow, cb, 0u);
 }
 void launchBin(cudaStream_t st, int smCount, const PathBuffers& pb, const WaveState& ws, uint32_t buf) { k_bin<<<smCount * 8, 256, 0, st>>>(pb, ws, buf); }
 // Register caps (measured, profiles/r01_sweeps.md): the all-material kernel runs best at 80 registers

@@ -41,6 +41,13 @@ struct SortBuffers {          // sized for P extension + 2 P shadow rays (runtim
 // three launches (count, scan, scatter); the item counts are read from `counters` (device memory) when the kernels run
 void launchSortRays(cudaStream_t st, int smCount, const SortBuffers& sb, const Counters* counters);
 void launchTraceSorted(cudaStream_t st, int blocks, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const uint32_t* permExt, const uint32_t* permShadow);
+// Suspend-and-regroup tracing of a sorted bounce (static-only scenes; kernels.cu k_trace_rs, traverse.cuh walkResumable): pass 0 walks
+// the sorted tickets and files the last `threshold` walking lanes of every warp as 128-byte continuation records in recA, pass 1
+// walks recA 32 records per warp (same rule, into recB), pass 2 walks recB to the end. capA >= ceil(rays / 32) * threshold,
+// capB >= ceil(capA / 32) * threshold (a ticket never files more than `threshold` records); counts are zero between bounces.
+struct ContBuffers { uint4* recA; uint4* recB; uint32_t* counts; };   // counts[0] = records in recA, counts[1] = in recB
+void launchTraceSuspend(cudaStream_t st, int blocks, const DeviceScene& sc, const PathBuffers& pb, const WaveState& ws, uint32_t buf, const uint32_t* permExt,
+                        const uint32_t* permShadow, const ContBuffers& cb, uint32_t threshold, int passes);
 void launchBin(cudaStream_t st, int smCount, const PathBuffers& pb, const WaveState& ws, uint32_t buf);
 // `slot` >= 0 on the launch that ends a bounce: the bounce's output counts are logged in ws.history[slot]
 void launchShade(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf, int32_t slot, const SortKeys& keys);

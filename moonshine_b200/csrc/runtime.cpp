@@ -305,6 +305,8 @@ struct HdMoonshine {
         // global histogram + bin cursors of the counting sort
         DevBuf<uint16_t> sortKeysExt, sortKeysShadow;
         DevBuf<uint32_t> sortPermExt, sortPermShadow, sortHist, sortCursor, sortBlockHist;
+        DevBuf<uint4> contA, contB;        // suspend-and-regroup tracing: continuation records (128 B each)
+        DevBuf<uint32_t> contCounts;
         cudaEvent_t evDone = nullptr;      // recorded after the wave's k_accumulate
         bool pending = false;              // a wave was enqueued and its log not read yet
         uint32_t bounces = 0;              // wavefront bounces that wave scheduled
@@ -315,6 +317,8 @@ struct HdMoonshine {
     };
     WaveCtx ctx[kWaveContexts];
     uint64_t pathsInFlight = 1ull << 27;   // over both contexts: 2 x 64 Mi paths x (308 + 18) B = 41 GiB of the 180 GB HBM
+    uint32_t suspendThreshold = 0;   // > 0: sorted bounces of static-only scenes are traced by k_trace_rs, whose warps hand their last N walking lanes to a later pass (MSNE_TRACE_SUSPEND)
+    int suspendPasses = 3;           // MSNE_TRACE_SUSPEND_PASSES: 3 = suspend twice, 2 = once, 1 = never (the kernel alone; measurements)
     uint64_t sortThreshold = 262144; // extension-ray queues at least this long are traced in sorted order (0 = never)
     bool sortAnyScene = false;       // false: only scenes with >= kSortMinNodes BVH nodes (a 36-triangle Cornell box loses 4 % to the sort)
     static constexpr size_t kSortMinNodes = 2048;
@@ -377,6 +381,8 @@ struct HdMoonshine {
         if (const char* e = getenv("MSNE_TLAS_MAX_REFITS")) maxRefits = (uint32_t)std::max(0, atoi(e));
         if (const char* e = getenv("MSNE_TWO_LEVEL")) forceTwoLevel = atoi(e) != 0;
         if (const char* e = getenv("MSNE_LOG_BOUNCES")) logBounces = atoi(e) != 0;
+        if (const char* e = getenv("MSNE_TRACE_SUSPEND")) suspendThreshold = (uint32_t)std::min(16, std::max(0, atoi(e)));
+        if (const char* e = getenv("MSNE_TRACE_SUSPEND_PASSES")) suspendPasses = std::min(3, std::max(1, atoi(e)));
         if (const char* e = getenv("MSNE_TAIL_BLOCK")) { const int t = atoi(e); if (t == 32 || t == 64 || t == 128) tailBlockThreads = t; }
         if (const char* e = getenv("MSNE_TAIL_THRESHOLD")) tailThreshold = strtoull(e, nullptr, 10);
         if (const char* e = getenv("MSNE_SORT_THRESHOLD")) { sortThreshold = strtoull(e, nullptr, 10); sortAnyScene = true; }
@@ -980,6 +986,15 @@ struct HdMoonshine {
         c.sortPermExt.alloc(P); c.sortPermShadow.alloc(2 * P);
         c.sortBlockHist.ensure((size_t)2 * smCount * 32768);
     }
+    // continuation records of suspend-and-regroup tracing (kernels.h ContBuffers): a ticket files at most `suspendThreshold` records
+    void ensureContBuffers(WaveCtx& c) {
+        const size_t P = c.pb.capacity, T = suspendThreshold;
+        const size_t capA = ((3 * P + 31) / 32 + 1) * T + 32, capB = ((capA + 31) / 32 + 1) * T + 32;
+        if (c.contA.n >= capA * 8 && c.contB.n >= capB * 8 && c.contCounts.n) return;
+        finishWaves();
+        c.contA.alloc(capA * 8); c.contB.alloc(capB * 8);
+        if (!c.contCounts.n) { c.contCounts.alloc(2); CK(cudaMemsetAsync(c.contCounts.p, 0, 2 * sizeof(uint32_t), stream)); CK(cudaStreamSynchronize(stream)); }
+    }
     static SortBuffers sortBuffers(const WaveCtx& c) {
         return SortBuffers{c.sortKeysExt.p, c.sortKeysShadow.p, c.sortPermExt.p, c.sortPermShadow.p, c.sortHist.p, c.sortCursor.p, c.sortBlockHist.p};
     }
@@ -1056,7 +1071,10 @@ struct HdMoonshine {
                 if (prof) CK(cudaEventRecord(c.profEv[c.profUsed][2], st));
                 launchSortRays(st, smCount, sortBuffers(c), c.dCounters.p + buf);
                 if (prof) CK(cudaEventRecord(c.profEv[c.profUsed][0], st));
-                launchTraceSorted(st, traceBlocks, sc, pb, ws, buf, c.sortPermExt.p, c.sortPermShadow.p);
+                if (suspendThreshold && sc.staticOnly && c.contCounts.n) {
+                    launchTraceSuspend(st, traceBlocks, sc, pb, ws, buf, c.sortPermExt.p, c.sortPermShadow.p, ContBuffers{c.contA.p, c.contB.p, c.contCounts.p}, suspendThreshold, suspendPasses);
+                    stats.kernel_launches += (uint64_t)suspendPasses - 1;
+                } else launchTraceSorted(st, traceBlocks, sc, pb, ws, buf, c.sortPermExt.p, c.sortPermShadow.p);
                 if (prof) CK(cudaEventRecord(c.profEv[c.profUsed][1], st));
                 launchBin(st, smCount, pb, ws, buf);
                 if (prof) { CK(cudaEventRecord(c.profEv[c.profUsed][3], st)); c.profUsed++; }
@@ -1146,7 +1164,7 @@ struct HdMoonshine {
         for (int i = 0; i < nCtx; i++) if (ctx[i].pb.capacity < wantP) ensurePool(ctx[i], wantP);   // reallocation waits for (and drops) everything in flight
         size_t bvhNodes = blasNodePool.size() + tlasHostNodes.size();
         sortActive = sortThreshold != 0 && wantP >= sortThreshold && (sortAnyScene || bvhNodes >= kSortMinNodes);
-        if (sortActive) for (int i = 0; i < nCtx; i++) ensureSortBuffers(ctx[i]);
+        if (sortActive) for (int i = 0; i < nCtx; i++) { ensureSortBuffers(ctx[i]); if (suspendThreshold) ensureContBuffers(ctx[i]); }
         CK(cudaEventRecord(evStart, stream));
         for (int i = 0; i < nCtx; i++) CK(cudaStreamWaitEvent(ctx[i].stream, evStart, 0));   // uploads / clears queued on the main stream come first
         aheadSensor = &s; aheadLens = lens; aheadSpr = spr;
@@ -1212,7 +1230,7 @@ struct HdMoonshine {
         for (int i = 1; i < used; i++) ensurePool(ctx[i], P);
         size_t bvhNodes = blasNodePool.size() + tlasHostNodes.size();
         sortActive = sortThreshold != 0 && P >= sortThreshold && (sortAnyScene || bvhNodes >= kSortMinNodes);
-        if (sortActive) for (int i = 0; i < used; i++) ensureSortBuffers(ctx[i]);
+        if (sortActive) for (int i = 0; i < used; i++) { ensureSortBuffers(ctx[i]); if (suspendThreshold) ensureContBuffers(ctx[i]); }
         // everything queued on the main stream so far (uploads, sensor clears) precedes the waves; the waves' streams start at evStart
         if (!timelineOpen) {
             CK(cudaEventRecord(evStart, stream));
@@ -1695,6 +1713,10 @@ void HdMoonshineExtSetSchedule(HdMoonshine* h, uint64_t tailPaths, uint64_t binn
     h->binnedThreshold = binnedPaths == UINT64_MAX ? 262144 : binnedPaths;
     h->waveContextsInUse = waveContexts == 0 ? HdMoonshine::kDefaultWaveContexts : (int)std::min<uint32_t>(waveContexts, HdMoonshine::kWaveContexts);
     h->survivalIn.clear();
+}
+void HdMoonshineExtSetTraceSuspend(HdMoonshine* h, uint32_t lanes) {
+    LOCK(h);
+    h->suspendThreshold = std::min<uint32_t>(lanes, 16);
 }
 void HdMoonshineExtSetRenderAhead(HdMoonshine* h, uint32_t wavesAhead) {
     LOCK(h);

@@ -250,4 +250,83 @@ DI bool traceRay(const DeviceScene& sc, const float3 o, const float3 d, const fl
     return hit.inst != MISS_ID;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Resumable single-level walk (kernels.cu k_trace_rs: suspend-and-regroup for sorted bounces of static-only scenes).
+// The node step, the leaf test and the tie-break are those of traceRay<ANY_HIT, false>, statement for statement, so a ray that is
+// walked in one go, or suspended and resumed any number of times, visits the same nodes in the same order and returns the same
+// bits. What is added:
+//  * the bottom of the stack is REF_FINISH, a leaf-coded reference no BLAS holds: a lane whose walk runs out pops it, lands in the
+//    leaf section (not in the hot node loop) and signs off from its warp's count of walking lanes in shared memory;
+//  * after every leaf visit a lane looks at that count: once at most `threshold` lanes of the warp are still walking - the others
+//    only wait for them (while-while traversal keeps a warp until its longest ray ends: profiles/r02_sweeps.md section 8) - it
+//    stops with its state (next reference, stack, closest hit so far) intact; the kernel files those lanes as continuation
+//    records and a later pass walks 32 of them per warp. threshold = 0: never.
+// ------------------------------------------------------------------------------------------------
+static const int32_t REF_FINISH = (int32_t)0x80000000;
+#ifndef MSNE_RS_MAX_SAVE
+#define MSNE_RS_MAX_SAVE 24   // stack entries a continuation record holds (deeper walks are not suspended)
+#endif
+struct WalkState { int node, sp; float bestT; uint32_t inst, tri; float u, v; };
+
+template <bool ANY_HIT>
+DI bool walkResumable(const DeviceScene& sc, const SpaceRay& ray, const float tmin, const float tmax, WalkState& w, int* stack, uint32_t* live, const uint32_t threshold) {
+    const BvhNode2* nodes = sc.blasNodes;
+    int node = w.node, sp = w.sp;
+    float bestT = w.bestT;
+    bool suspended = false;
+    while (node != REF_END) {
+        while ((uint32_t)node < (uint32_t)REF_ITEM) {
+            const float4* np = reinterpret_cast<const float4*>(nodes + node);
+            const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2);
+            const int2 c = __ldg(reinterpret_cast<const int2*>(np + 3));
+            float tn0, tn1;
+            const bool h0 = slab(ray, n0.x, n0.y, n0.z, n0.w, n2.x, n2.y, tmin, bestT, tn0);
+            const bool h1 = slab(ray, n1.x, n1.y, n1.z, n1.w, n2.z, n2.w, tmin, bestT, tn1);
+            if (h0 && h1) {
+                const bool swap = tn1 < tn0;
+                node = swap ? c.y : c.x;
+                stack[sp++] = swap ? c.x : c.y;
+            } else if (h0) node = c.x;
+            else if (h1) node = c.y;
+            else node = stack[--sp];
+        }
+        while (node < 0) {
+            if (node == REF_FINISH) { atomicSub(live, 1u); node = REF_END; break; }
+            const uint32_t x = ~(uint32_t)node;
+            const uint32_t first = x >> 3, count = (x & 7u) + 1u;
+            for (uint32_t i = 0; i < count; i++) {
+                const float4* tp = reinterpret_cast<const float4*>(sc.tris + (first + i));
+                const float4 t0 = __ldg(tp), t1 = __ldg(tp + 1), t2 = __ldg(tp + 2);
+                float t, u, v;
+                if (!triTest(t0, t1, t2, ray, tmin, tmax, t, u, v)) continue;
+                const uint32_t inst = __float_as_uint(t2.w);
+                if (sc.staticHidden && !__ldg(&sc.instances[inst].visible)) continue;
+                if (ANY_HIT) { w.inst = inst; node = REF_END; break; }
+                bool better = t < bestT;
+                if (!better && t == bestT && w.inst != MISS_ID) {
+                    if (inst != w.inst) better = inst < w.inst;
+                    else {
+                        const uint32_t g = __float_as_uint(t0.w), p = __float_as_uint(t1.w);
+                        const uint32_t bg = sc.tris[w.tri].geom, bp = sc.tris[w.tri].prim;
+                        better = g != bg ? g < bg : p < bp;
+                    }
+                }
+                if (better) { bestT = t; w.inst = inst; w.tri = first + i; w.u = u; w.v = v; }
+            }
+            if (ANY_HIT && node == REF_END) atomicSub(live, 1u);
+            else {
+                node = stack[--sp];
+                if (threshold != 0u && node != REF_FINISH && sp <= MSNE_RS_MAX_SAVE && *reinterpret_cast<volatile uint32_t*>(live) <= threshold) {
+                    w.node = node; w.sp = sp;
+                    atomicSub(live, 1u);
+                    suspended = true;
+                    node = REF_END;
+                }
+            }
+        }
+    }
+    w.bestT = bestT;
+    return suspended;
+}
+
 }  // namespace msne

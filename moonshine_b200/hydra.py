@@ -125,6 +125,7 @@ SIGNATURES = {
     "HdMoonshineExtSetRaySorting": (None, [_VP, C.c_uint64]),
     "HdMoonshineExtSetProfiling": (None, [_VP, C.c_bool]),
     "HdMoonshineExtSetSchedule": (None, [_VP, C.c_uint64, C.c_uint64, _U32]),
+    "HdMoonshineExtSetTraceSuspend": (None, [_VP, _U32]),
     "HdMoonshineExtSetRenderAhead": (None, [_VP, _U32]),
     "HdMoonshineExtGetStats": (None, [_VP, C.POINTER(MsneStats)]),
     "HdMoonshineExtResetStats": (None, [_VP]),
@@ -326,6 +327,7 @@ class HdMoonshine:
         big = 0xFFFFFFFFFFFFFFFF
         self.L.HdMoonshineExtSetSchedule(self.h, big if tail_paths is None else tail_paths, big if binned_paths is None else binned_paths, wave_contexts)
 
+    def SetTraceSuspend(self, lanes: int): self.L.HdMoonshineExtSetTraceSuspend(self.h, int(lanes))
     def SetRenderAhead(self, waves_ahead: int): self.L.HdMoonshineExtSetRenderAhead(self.h, int(waves_ahead))
 
     def GetStats(self) -> MsneStats:
@@ -479,7 +481,7 @@ def retire_unique_id(tag: str) -> None:
 
 
 def render_scene(scene, n_launches: int = 1, device: int = 0, paths_in_flight: Optional[int] = None, shard=None, ray_sorting: Optional[int] = None,
-                 tail_paths: Optional[int] = None, binned_paths: Optional[int] = None, wave_contexts: int = 0):
+                 tail_paths: Optional[int] = None, binned_paths: Optional[int] = None, wave_contexts: int = 0, trace_suspend: Optional[int] = None):
     """Load a scenes.Scene into a fresh HdMoonshine, render `n_launches` launches, return (image HxWx4, stats, obj)."""
     from . import scenes as _sc
     m = HdMoonshine(device)
@@ -489,6 +491,8 @@ def render_scene(scene, n_launches: int = 1, device: int = 0, paths_in_flight: O
         m.SetRaySorting(ray_sorting)
     if tail_paths is not None or binned_paths is not None or wave_contexts:
         m.SetSchedule(tail_paths, binned_paths, wave_contexts)
+    if trace_suspend is not None:
+        m.SetTraceSuspend(trace_suspend)
     _sc.load_scene(m, scene)
     if shard:
         m.SetTileShard(*shard)

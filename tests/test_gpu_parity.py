@@ -160,6 +160,18 @@ def test_ray_sorting_is_bitwise_invariant():
         assert sb.kernel_launches > sa.kernel_launches + 8   # the sort really ran, on several bounces
 
 
+def test_suspend_and_regroup_tracing_is_bitwise_invariant():
+    """k_trace_rs (sorted bounces of static-only scenes): warps hand their last N walking lanes to a later pass as continuation
+    records (traversal stack + closest hit so far); a ray walked in one go or in up to three pieces returns the same bits."""
+    for sc in (scenes.cornell_box((48, 48)), scenes.bathroom((96, 54), detail=0.05)):
+        a, sa, _ = gpu_render(sc, 4, ray_sorting=1, tail_paths=16)
+        for lanes in (2, 8, 16):
+            b, sb, _ = gpu_render(sc, 4, ray_sorting=1, tail_paths=16, trace_suspend=lanes)
+            np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32), err_msg=f"{lanes} lanes")
+            assert (sa.rays_closest, sa.rays_shadow) == (sb.rays_closest, sb.rays_shadow)
+            assert sb.kernel_launches > sa.kernel_launches + 8   # the two extra passes really ran, on several bounces
+
+
 def test_schedule_hints_never_change_the_image():
     """Which launches a bounce gets (binned or generic shading, how early k_tail takes over, one or two waves in flight) is a
     hint taken from the previous wave's survival profile; the image must be the same bits whatever the hints are."""

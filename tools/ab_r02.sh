@@ -23,6 +23,8 @@ for v in "$@"; do
     tg*) MSNE_TRACE_GRID_PER_SM=${v#tg} $B 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
     sg*) MSNE_SHADE_GRID_PER_SM=${v#sg} $B 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
     ahead*) $B --render-ahead ${v#ahead} 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
+    rsp*) MSNE_TRACE_SUSPEND=8 MSNE_TRACE_SUSPEND_PASSES=${v#rsp} $B 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
+    rs*) MSNE_TRACE_SUSPEND=${v#rs} $B 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
     tb*) MSNE_TAIL_BLOCK=${v#tb} $B 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
     nosort) MSNE_SORT_THRESHOLD=0 $B 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
     tail8k) MSNE_TAIL_THRESHOLD=8192 $B 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
