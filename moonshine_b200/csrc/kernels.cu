@@ -1278,7 +1278,7 @@ void launchBin(cudaStream_t st, int smCount, const PathBuffers& pb, const WaveSt
 // Register caps (measured, profiles/r01_sweeps.md): the all-material kernel runs best at 80 registers
 // (6 blocks/SM); the specialised kernels are smaller and take the same cap.
 #ifndef SHADE_MINB
-#define SHADE_MINB 6
+#define SHADE_MINB 4   // 128 registers, 16 warps per SM, next to no spill: 2575 vs 2543 (6: 80 registers, 460 B of spill stores) vs 2389 (3) Mrays/s on cfg3 (profiles/r02_sweeps.md section 7)
 #endif
 void launchShade(cudaStream_t st, int blocks, const DeviceScene& sc, const DConstants& k, const PathBuffers& pb, const WaveState& ws, uint32_t buf, int32_t slot, const SortKeys& keys) {
     k_shade<-1, SHADE_MINB><<<blocks, SHADE_THREADS, 0, st>>>(sc, k, pb, ws, buf, slot, keys);
