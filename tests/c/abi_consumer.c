@@ -4,7 +4,7 @@
  *
  *   abi_consumer render <out.f32>   cfg1 (BASELINE.json configs[0]: one Lambert triangle, 1x1 white env, 64x64, 1 spp, offline
  *                                   constants) through HdMoonshineRender; writes the 64*64*4 float sensor buffer
- *   abi_consumer stress             8 threads create textures / materials / meshes / instances and edit them while the main
+ *   abi_consumer stress [n]         (n: render-ahead depth, default off) 8 threads create textures / materials / meshes / instances and edit them while the main
  *                                   thread renders: the per-object mutex (hydra.zig:78) must serialise everything
  * Test infrastructure (tests/test_c_consumer.py builds and runs it); not part of the product.
  */
@@ -91,9 +91,10 @@ static void* worker(void* arg) {
     return NULL;
 }
 
-static int stress(void) {
+static int stress(int render_ahead) {
     HdMoonshine* m = HdMoonshineCreate();
     CHECK(m != NULL);
+    if (render_ahead) HdMoonshineExtSetRenderAhead(m, (uint32_t)render_ahead);   /* edits from the workers keep dropping the waves rendered ahead */
     const Extent2D extent = {96, 64};
     const SensorHandle sensor = HdMoonshineCreateSensor(m, extent);
     const Lens lens = {{0, -6, 3}, {0, 0.8944272f, -0.4472136f}, {0, 0, 1}, 0.9f, 0.0f, 1.0f};
@@ -119,15 +120,15 @@ static int stress(void) {
     for (int i = 0; i < 96 * 64; i++) { CHECK(px[4 * i] == px[4 * i]); sum += px[4 * i]; }   /* no NaN */
     MsneStats st;
     HdMoonshineExtGetStats(m, &st);
-    printf("stress ok: %d renders during edits, %d instances, mean red %.6f, rays %llu\n", renders, kThreads * kPerThread, sum / (96 * 64),
-           (unsigned long long)(st.rays_closest + st.rays_shadow));
+    printf("stress ok: %d renders during edits, %d instances, mean red %.6f, rays %llu, waves dropped %llu\n", renders, kThreads * kPerThread, sum / (96 * 64),
+           (unsigned long long)(st.rays_closest + st.rays_shadow), (unsigned long long)st.ahead_discarded);
     HdMoonshineDestroy(m);
     return 0;
 }
 
 int main(int argc, char** argv) {
     if (argc >= 3 && strcmp(argv[1], "render") == 0) return render_cfg1(argv[2]);
-    if (argc >= 2 && strcmp(argv[1], "stress") == 0) return stress();
-    fprintf(stderr, "usage: abi_consumer render <out.f32> | stress\n");
+    if (argc >= 2 && strcmp(argv[1], "stress") == 0) return stress(argc >= 3 ? atoi(argv[2]) : 0);
+    fprintf(stderr, "usage: abi_consumer render <out.f32> | stress [render_ahead_waves]\n");
     return 64;
 }

@@ -53,3 +53,12 @@ def test_c_program_multithreaded_stress(tmp_path):
     r = subprocess.run([exe, "stress"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "stress ok" in r.stdout
+
+
+@pytest.mark.gpu
+def test_c_program_multithreaded_stress_with_render_ahead(tmp_path):
+    """The same with HdMoonshineExtSetRenderAhead(2): the workers' edits keep dropping the waves the render thread started early."""
+    exe = _build(tmp_path)
+    r = subprocess.run([exe, "stress", "2"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "stress ok" in r.stdout
