@@ -1,0 +1,158 @@
+"""Physics-level checks of the oracle's BSDFs and environment sampling (CPU only). The GPU kernels are compared with the oracle bit
+for bit (tests/test_gpu_probes.py), and both restate the same HLSL - so a shared misreading of material.hlsl / light.hlsl would pass
+every GPU-vs-oracle test. These tests hold the oracle to what any correct implementation of those models must satisfy, whatever the
+source text says: Helmholtz reciprocity, energy conservation, pdf normalisation, agreement between sample() and pdf(), Snell's law
+and the Fresnel split of glass, and env-map sampling proportional to luminance."""
+import math
+
+import numpy as np
+
+from moonshine_b200 import scenes
+from oracle import binding
+from oracle.binding import Oracle
+
+PBR, GLASS, LAMBERT = scenes.MAT_STANDARD_PBR, scenes.MAT_GLASS, scenes.MAT_LAMBERT
+
+
+def _bsdf(type_, color, metal, rough, ior, op, a, wo):
+    a = np.atleast_2d(np.asarray(a, np.float32))
+    q = np.zeros((len(a), 14), np.float32)
+    q[:, 0], q[:, 1:4], q[:, 4], q[:, 5], q[:, 6], q[:, 7], q[:, 8:11] = type_, color, metal, rough, ior, op, a
+    q[:, 11:14] = wo
+    return binding.bsdf_batch(q).astype(np.float64)
+
+
+def _upper_hemisphere(nz=256, nphi=512):
+    """midpoint grid, equal solid angle per cell: directions (n, 3), cell solid angle"""
+    z = (np.arange(nz) + 0.5) / nz
+    phi = (np.arange(nphi) + 0.5) / nphi * 2 * np.pi
+    zz, pp = np.meshgrid(z, phi, indexing="ij")
+    r = np.sqrt(1 - zz * zz)
+    d = np.stack([r * np.cos(pp), r * np.sin(pp), zz], -1).reshape(-1, 3).astype(np.float32)
+    return d, 2 * np.pi / len(d)
+
+
+def _unit(v):
+    v = np.asarray(v, np.float64)
+    return (v / np.linalg.norm(v)).astype(np.float32)
+
+
+CONFIGS = [(0.5, 0.0), (0.5, 1.0), (0.2, 1.0), (0.25, 0.3), (0.9, 0.5)]   # (roughness, metalness)
+VIEWS = [(0, 0, 1), (0.6, 0, 0.8), (0.95, 0.0, 0.31225)]
+
+
+def test_standard_pbr_is_reciprocal():
+    """f(w_i, w_o) = f(w_o, w_i): GGX with Smith G and Schlick F plus a Lambert lobe is symmetric in its two directions."""
+    rs = np.random.RandomState(1)
+
+    def hemi(n):
+        v = rs.randn(n, 3)
+        v[:, 2] = np.abs(v[:, 2]) + 0.05
+        return (v / np.linalg.norm(v, axis=1, keepdims=True)).astype(np.float32)
+
+    for rough, metal in CONFIGS:
+        wi, wo = hemi(1500), hemi(1500)
+        a = _bsdf(PBR, (0.9, 0.5, 0.3), metal, rough, 1.5, 0, wi, wo)[:, :3]
+        b = _bsdf(PBR, (0.9, 0.5, 0.3), metal, rough, 1.5, 0, wo, wi)[:, :3]
+        np.testing.assert_allclose(a, b, rtol=2e-5, atol=1e-7)
+
+
+def test_standard_pbr_pdf_is_a_sub_normalised_density_and_white_metal_never_gains_energy():
+    d, dw = _upper_hemisphere()
+    for rough, metal in CONFIGS:
+        for view in VIEWS:
+            wo = _unit(view)
+            pdf = _bsdf(PBR, (1, 1, 1), metal, rough, 1.5, 1, d, wo)[:, 0]
+            assert (pdf >= 0).all()
+            total = pdf.sum() * dw
+            # half-vector sampling reflects some directions below the horizon, where the pdf is 0: the integral is at most 1
+            assert 0.6 < total < 1.002, (rough, metal, view, total)
+            if metal == 1.0:
+                f = _bsdf(PBR, (1, 1, 1), metal, rough, 1.5, 0, d, wo)[:, 0]
+                albedo = (f * d[:, 2]).sum() * dw
+                assert 0.5 < albedo < 1.002, (rough, view, albedo)   # single-scattering microfacets lose energy, never gain
+
+
+def test_standard_pbr_samples_are_distributed_as_its_pdf():
+    """Histogram of sample() over a coarse grid of the hemisphere == integral of pdf() over each cell (and the pdf sample() reports
+    is pdf() of the direction - tests/test_oracle_kat.py). Directions sampled below the horizon carry pdf 0 and are dropped."""
+    n_side = 700
+    u = (np.stack(np.meshgrid(np.arange(n_side), np.arange(n_side), indexing="ij"), -1).reshape(-1, 2) + 0.5) / n_side   # stratified
+    sq = np.concatenate([u, np.zeros((len(u), 1))], 1).astype(np.float32)
+    d, dw = _upper_hemisphere(256, 512)
+    cz, cphi = 4, 8   # coarse cells: 4 bands of cos(theta) x 8 sectors of phi
+    cell_of = lambda v: np.minimum((v[:, 2] * cz).astype(int), cz - 1) * cphi + ((np.arctan2(v[:, 1], v[:, 0]) % (2 * np.pi)) / (2 * np.pi) * cphi).astype(int) % cphi
+    grid_cells = cell_of(d.astype(np.float64))
+    for rough, metal in [(0.5, 0.0), (0.3, 1.0), (0.8, 0.5)]:
+        wo = _unit((0.5, 0.2, 0.84))
+        s = _bsdf(PBR, (0.8, 0.8, 0.8), metal, rough, 1.5, 2, sq, wo)
+        ok = s[:, 3] > 0
+        assert ok.mean() > 0.6
+        hist = np.bincount(cell_of(s[ok, :3]), minlength=cz * cphi) / len(sq)
+        pdf = _bsdf(PBR, (0.8, 0.8, 0.8), metal, rough, 1.5, 1, d, wo)[:, 0]
+        expect = np.bincount(grid_cells, weights=pdf * dw, minlength=cz * cphi)
+        assert abs(hist.sum() - expect.sum()) < 0.002
+        np.testing.assert_allclose(hist, expect, atol=0.002, err_msg=str((rough, metal)))   # 32 cells holding up to 0.64 of the mass
+
+
+def test_glass_obeys_snell_and_splits_energy_by_fresnel():
+    ior, air = 1.5, 1.000277   # material.hlsl:348-351 (AIR_IOR)
+    rs = np.random.RandomState(3)
+    for cos_o in (1.0, 0.8, 0.5, 0.2):
+        sin_o = math.sqrt(1 - cos_o * cos_o)
+        wo = np.array([sin_o, 0, cos_o], np.float32)
+        sq = np.concatenate([rs.rand(20000, 2), np.zeros((20000, 1))], 1).astype(np.float32)
+        s = _bsdf(GLASS, (1, 1, 1), 0, 0, ior, 2, sq, wo)
+        refl = s[:, 2] > 0
+        # reflected: mirror direction; transmitted: Snell, in the plane of incidence, on the other side
+        np.testing.assert_allclose(s[refl, :3], np.broadcast_to([-sin_o, 0, cos_o], (refl.sum(), 3)), atol=2e-6)
+        sin_t = sin_o * air / ior
+        np.testing.assert_allclose(s[~refl, :3], np.broadcast_to([-sin_t, 0, -math.sqrt(1 - sin_t * sin_t)], ((~refl).sum(), 3)), atol=2e-6)
+        # unpolarised Fresnel reflectance of a dielectric interface
+        cos_t = math.sqrt(1 - sin_t * sin_t)
+        rp = (ior * cos_o - air * cos_t) / (ior * cos_o + air * cos_t)
+        rs_ = (air * cos_o - ior * cos_t) / (air * cos_o + ior * cos_t)
+        fresnel = 0.5 * (rp * rp + rs_ * rs_)
+        assert abs(refl.mean() - fresnel) < 4 * math.sqrt(fresnel * (1 - fresnel) / 20000) + 1e-3, (cos_o, refl.mean(), fresnel)
+        # each branch's pdf is its selection probability; eval * |cos| / pdf = 1 (no energy lost or gained at the interface)
+        e = _bsdf(GLASS, (1, 1, 1), 0, 0, ior, 0, s[:, :3].astype(np.float32), wo)[:, 0]
+        np.testing.assert_allclose(e * np.abs(s[:, 2]) / s[:, 3], 1.0, rtol=1e-5)
+
+
+def test_lambert_is_a_normalised_cosine_lobe():
+    d, dw = _upper_hemisphere()
+    wo = _unit((0.3, -0.4, 0.866))
+    pdf = _bsdf(LAMBERT, (0.7, 0.7, 0.7), 0, 0, 1.5, 1, d, wo)[:, 0]
+    assert abs(pdf.sum() * dw - 1.0) < 1e-3
+    f = _bsdf(LAMBERT, (0.7, 0.7, 0.7), 0, 0, 1.5, 0, d, wo)[:, 0]
+    assert abs((f * d[:, 2]).sum() * dw - 0.7) < 1e-3   # albedo = colour
+
+
+def test_env_map_is_sampled_in_proportion_to_luminance():
+    """EnvMap::sample picks texel (x, y) with probability lum / sum and reports pdf = that probability * texels / 4 pi
+    (equal-area mapping: every texel subtends the same solid angle); eval() of the sampled direction agrees."""
+    rs = np.random.RandomState(5)
+    n = 8
+    rgba = np.ones((n, n, 4), np.float32)
+    rgba[..., :3] = rs.rand(n, n, 3).astype(np.float32) ** 3 * 4 + 0.01   # uneven, strictly positive
+    o = Oracle()
+    o.set_background(rgba)
+    rgb_dev, lum_levels = o.env_data()
+    size = rgb_dev.shape[0]
+    assert size == n
+    lum = lum_levels[: n * n].reshape(n, n).astype(np.float64)
+    m = 400
+    u = (np.stack(np.meshgrid(np.arange(m), np.arange(m), indexing="ij"), -1).reshape(-1, 2) + 0.5) / m
+    out = o.env_probe(0, np.concatenate([u, np.zeros((len(u), 1))], 1).astype(np.float32)).astype(np.float64)
+    dirs, radiance, pdf = out[:, :3], out[:, 3:6], out[:, 6]
+    np.testing.assert_allclose(np.linalg.norm(dirs, axis=1), 1.0, atol=1e-5)
+    # which texel a sample landed in: its radiance is that texel's colour (colours are distinct)
+    flat = rgb_dev.reshape(-1, 4)[:, :3].astype(np.float64)
+    tex = np.argmin(((radiance[:, None, :] - flat[None, :, :]) ** 2).sum(-1), axis=1)
+    freq = np.bincount(tex, minlength=n * n) / len(u)
+    prob = (lum / lum.sum()).reshape(-1)
+    np.testing.assert_allclose(freq, prob, atol=2e-3)
+    np.testing.assert_allclose(pdf, prob[tex] * n * n / (4 * math.pi), rtol=1e-4)
+    ev = o.env_probe(1, dirs.astype(np.float32)).astype(np.float64)
+    np.testing.assert_allclose(ev[:, 3], pdf, rtol=1e-4)
+    np.testing.assert_allclose(ev[:, :3], radiance, rtol=1e-6)
