@@ -156,3 +156,70 @@ def test_env_map_is_sampled_in_proportion_to_luminance():
     ev = o.env_probe(1, dirs.astype(np.float32)).astype(np.float64)
     np.testing.assert_allclose(ev[:, 3], pdf, rtol=1e-4)
     np.testing.assert_allclose(ev[:, :3], radiance, rtol=1e-6)
+
+
+# ---- integrator level: direct lighting against closed forms / plain quadrature -------------------------------------------------
+def _floor_scene(albedo, extent=(24, 24), spr=256):
+    s = scenes.Scene("floor", extent=extent, lens=scenes.Lens((3.0, 0.0, 1.5), (-3.0, 0.0, -1.5), (0, 0, 1), math.radians(1.0), 0.0, 1.0))
+    n, black, c = s.solid2(0.5, 0.5), s.solid3(0, 0, 0), s.solid3(albedo, albedo, albedo)
+    floor_mat = s.add_material(type=LAMBERT, normal=n, emissive=black, color=c)
+    quad = np.array([[-10, -10, 0], [10, -10, 0], [10, 10, 0], [-10, 10, 0]], np.float32)
+    floor = s.add_mesh(quad, np.array([[0, 1, 2], [0, 2, 3]], np.uint32))
+    s.add_instance([(floor, floor_mat, False)])
+    return s, n, black
+
+
+def _mean_rgb(sc):
+    o = Oracle()
+    scenes.load_scene(o, sc)
+    img, counts = o.render(sc.lens, *sc.extent)
+    assert np.isfinite(img).all()
+    return img[..., :3].reshape(-1, 3).mean(0).astype(np.float64), counts
+
+
+def test_square_light_over_a_lambert_floor_matches_the_form_factor():
+    """Radiance leaving a Lambert floor under a one-sided square emitter = albedo * L * F, F the closed-form configuration factor of a
+    differential element to a parallel rectangle. Holds MeshLights::sample, the area -> solid-angle measure, the emission test and the
+    power-heuristic weights (light.hlsl:105-158, integrator.hlsl:10-35, :109-124) to the radiometry they implement: BSDF sampling
+    alone, light sampling with MIS, and two light samples per bounce must all land on the same number."""
+    albedo, L, a, h = 0.6, 5.0, 1.0, 1.0
+    x = (a / 2) / h
+    corner = (x / math.sqrt(1 + x * x) * math.atan(x / math.sqrt(1 + x * x))) * 2 / (2 * math.pi)
+    expect = albedo * L * 4 * corner
+    assert abs(expect - 0.7183) < 1e-3
+    for mesh_samples in (0, 1, 2):
+        sc, n, black = _floor_scene(albedo)
+        light_mat = sc.add_material(type=LAMBERT, normal=n, emissive=sc.solid3(L, L, L), color=black)
+        q = a / 2
+        light = sc.add_mesh(np.array([[-q, -q, h], [-q, q, h], [q, q, h], [q, -q, h]], np.float32), np.array([[0, 1, 2], [0, 2, 3]], np.uint32))   # faces -z
+        sc.add_instance([(light, light_mat, mesh_samples > 0)])
+        sc.background = np.array([[[0, 0, 0, 1]]], np.float32)
+        sc.constants = scenes.Constants(samples_per_run=256, max_bounces=1, env_samples_per_bounce=0, mesh_samples_per_bounce=mesh_samples)
+        sc.build_emitter_table = mesh_samples > 0
+        rgb, counts = _mean_rgb(sc)
+        assert (counts[1] > 0) == (mesh_samples > 0)
+        np.testing.assert_allclose(rgb, expect, rtol=0.006, err_msg=f"mesh_samples={mesh_samples}")
+
+
+def test_uneven_sky_over_a_lambert_floor_matches_quadrature_of_the_same_sky():
+    """Radiance leaving a Lambert floor under an environment map = albedo / pi * integral of L cos over the hemisphere. The integral is
+    taken by plain quadrature through EnvMap::incomingRadiance (the lookup the integrator itself uses for escaping rays); BSDF sampling
+    alone, env importance sampling with MIS and three env samples per bounce must agree with it."""
+    rs = np.random.RandomState(11)
+    sky = np.ones((16, 16, 4), np.float32)
+    sky[..., :3] = (rs.rand(16, 16, 1) ** 4 * 6 + 0.05).astype(np.float32) * np.array([1.0, 0.8, 0.6], np.float32)
+    albedo = 0.7
+    d, dw = _upper_hemisphere(384, 768)
+    o = Oracle()
+    o.set_background(sky)
+    # escaping rays read the sky bilinearly when there is no env sampling (EnvMap::incomingRadiance, op 2) and by nearest texel when
+    # there is (EnvMap::eval, op 1, light.hlsl:83-102): each estimator is held to the quadrature of the sky it integrates
+    expect_by_lookup = {op: albedo / math.pi * (o.env_probe(op, d)[:, :3].astype(np.float64) * d[:, 2:3]).sum(0) * dw for op in (1, 2)}
+    for env_samples in (0, 1, 3):
+        expect = expect_by_lookup[2 if env_samples == 0 else 1]
+        sc, _, _ = _floor_scene(albedo, spr=512)
+        sc.background = sky
+        sc.constants = scenes.Constants(samples_per_run=512, max_bounces=1, env_samples_per_bounce=env_samples, mesh_samples_per_bounce=0)
+        sc.build_emitter_table = False
+        rgb, _ = _mean_rgb(sc)
+        np.testing.assert_allclose(rgb, expect, rtol=0.006, err_msg=f"env_samples={env_samples}")
