@@ -54,6 +54,7 @@ def lib():
         L.OracleRenderPixels.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.OracleDebugPath.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]
         L.OracleEnvProbe.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.OracleTextureProbe.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p]
         L.OracleBsdfBatch.argtypes = [C.c_size_t, C.c_void_p, C.c_void_p]
         L.OracleMathProbe.argtypes = [C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
         L.OracleHashPcg.restype = C.c_uint32
@@ -198,6 +199,13 @@ class Oracle:
         a = np.ascontiguousarray(inputs3, np.float32).reshape(-1, 3)
         out = np.zeros((len(a), 7), np.float32)
         self.L.OracleEnvProbe(self.h, op, len(a), _p(a), _p(out))
+        return out
+
+    def texture_probe(self, tex, uv, mirror=False):
+        """SampleLevel(texture `tex`, uv, 0) at n coordinates -> (n, 4)."""
+        a = np.ascontiguousarray(uv, np.float32).reshape(-1, 2)
+        out = np.zeros((len(a), 4), np.float32)
+        self.L.OracleTextureProbe(self.h, tex, int(mirror), len(a), _p(a), _p(out))
         return out
 
     def primary_rays(self, lens, width, height, sample):

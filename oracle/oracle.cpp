@@ -296,6 +296,15 @@ void OracleEnvProbe(Oracle* o, int op, size_t n, const float* in3, float* out7) 
         }
     }
 }
+// SampleLevel(texture, uv, 0) of texture `tex` at n coordinates (material sampler: linear, REPEAT; mirror != 0: the background's
+// MIRRORED_REPEAT sampler) -> n x rgba. For tests that hold the sampler to the Vulkan filtering rules (tests/test_oracle_physics.py).
+void OracleTextureProbe(Oracle* o, uint32_t tex, int mirror, size_t n, const float* uv2, float* out4) {
+    const Texture& t = o->sc.textures.at(tex);
+    for (size_t i = 0; i < n; i++) {
+        const float4 c = sample_bilinear(t, {uv2[2 * i], uv2[2 * i + 1]}, mirror != 0);
+        out4[4 * i] = c.x; out4[4 * i + 1] = c.y; out4[4 * i + 2] = c.z; out4[4 * i + 3] = c.w;
+    }
+}
 // batched OracleBsdf: queries = n x {type, color rgb, metalness, roughness, ior, op, a.xyz, w_o.xyz} (14 floats; type/op as floats)
 void OracleBsdfBatch(size_t n, const float* q14, float* out4);
 void OracleMathProbe(int fn, size_t n, const float* a, const float* b, float* out);

@@ -223,3 +223,58 @@ def test_uneven_sky_over_a_lambert_floor_matches_quadrature_of_the_same_sky():
         sc.build_emitter_table = False
         rgb, _ = _mean_rgb(sc)
         np.testing.assert_allclose(rgb, expect, rtol=0.006, err_msg=f"env_samples={env_samples}")
+
+
+# ---- texturing: the software sampler against the Vulkan filtering rules, written independently in float64 -----------------------
+def _vulkan_linear(texels, uv, mirror):
+    """VK_FILTER_LINEAR at LOD 0 with REPEAT / MIRRORED_REPEAT addressing (Vulkan spec, 'Texel Filtering' and 'Wrapping Operation'):
+    unnormalised coordinate u = s * width - 0.5, i0 = floor(u), weight = frac(u), neighbours i0 and i0 + 1 wrapped per axis."""
+    h, w = texels.shape[:2]
+    u, v = uv[:, 0].astype(np.float64) * w - 0.5, uv[:, 1].astype(np.float64) * h - 0.5
+    i0, j0 = np.floor(u).astype(np.int64), np.floor(v).astype(np.int64)
+    a, b = (u - i0)[:, None], (v - j0)[:, None]
+
+    def wrap(i, n):
+        if not mirror:
+            return i % n
+        m = i % (2 * n)
+        return np.where(m < n, m, 2 * n - 1 - m)   # mirror(n - 1 - mirror((i mod 2n) - n)) of the spec, simplified
+
+    t = texels.astype(np.float64)
+    i1, j1 = wrap(i0 + 1, w), wrap(j0 + 1, h)
+    i0, j0 = wrap(i0, w), wrap(j0, h)
+    return (t[j0, i0] * (1 - a) + t[j0, i1] * a) * (1 - b) + (t[j1, i0] * (1 - a) + t[j1, i1] * a) * b
+
+
+def _srgb_eotf(c8):
+    s = c8.astype(np.float64) / 255.0
+    return np.where(s <= 0.04045, s / 12.92, ((s + 0.055) / 1.055) ** 2.4)
+
+
+def test_texture_sampler_follows_the_vulkan_filtering_rules_for_every_format():
+    rs = np.random.RandomState(9)
+    w, h = 13, 7   # not powers of two, not square
+    uv = np.concatenate([rs.rand(4000, 2) * 6 - 3,                                   # several wraps either side of [0, 1)
+                         (rs.randint(-3 * w, 3 * w, (500, 2)) + 0.5) / np.array([w, h]),   # texel centres: no blending
+                         rs.randint(-2, 3, (100, 2)).astype(np.float64)]).astype(np.float32)   # texture corners
+    o = Oracle()
+    cases = []
+    f32 = rs.randn(h, w, 4).astype(np.float32)
+    cases.append((scenes.TEX_R32F, f32[..., 0].copy(), np.concatenate([f32[..., :1], np.zeros((h, w, 2)), np.ones((h, w, 1))], -1)))
+    cases.append((scenes.TEX_RG32F, f32[..., :2].copy(), np.concatenate([f32[..., :2], np.zeros((h, w, 1)), np.ones((h, w, 1))], -1)))
+    cases.append((scenes.TEX_RGBA32F, f32.copy(), f32))
+    u8 = rs.randint(0, 256, (h, w, 4)).astype(np.uint8)
+    cases.append((scenes.TEX_R8_UNORM, u8[..., 0].copy(), np.concatenate([u8[..., :1] / 255.0, np.zeros((h, w, 2)), np.ones((h, w, 1))], -1)))
+    cases.append((scenes.TEX_RG8_UNORM, u8[..., :2].copy(), np.concatenate([u8[..., :2] / 255.0, np.zeros((h, w, 1)), np.ones((h, w, 1))], -1)))
+    cases.append((scenes.TEX_RGBA8_SRGB, u8.copy(), np.concatenate([_srgb_eotf(u8[..., :3]), u8[..., 3:] / 255.0], -1)))   # alpha stays linear
+    f16 = (rs.randn(h, w, 4) * 3).astype(np.float16)
+    cases.append((scenes.TEX_RGBA16F, f16.copy(), f16.astype(np.float64)))
+    for fmt, data, decoded in cases:
+        tex = o.create_texture(data, w, h, fmt)
+        for mirror in (False, True):
+            got = o.texture_probe(tex, uv, mirror).astype(np.float64)
+            want = _vulkan_linear(decoded, uv, mirror)
+            np.testing.assert_allclose(got, want, rtol=0, atol=2e-5 * max(1.0, np.abs(decoded).max()), err_msg=f"format {fmt} mirror {mirror}")
+    # a 1x1 image is its texel whatever the coordinate
+    one = o.create_texture(np.array([0.25, 0.5, 0.75, 1.0], np.float32), 1, 1, scenes.TEX_RGBA32F)
+    np.testing.assert_array_equal(o.texture_probe(one, uv[:50]), np.broadcast_to(np.array([0.25, 0.5, 0.75, 1.0], np.float32), (50, 4)))
