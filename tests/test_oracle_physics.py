@@ -278,3 +278,53 @@ def test_texture_sampler_follows_the_vulkan_filtering_rules_for_every_format():
     # a 1x1 image is its texel whatever the coordinate
     one = o.create_texture(np.array([0.25, 0.5, 0.75, 1.0], np.float32), 1, 1, scenes.TEX_RGBA32F)
     np.testing.assert_array_equal(o.texture_probe(one, uv[:50]), np.broadcast_to(np.array([0.25, 0.5, 0.75, 1.0], np.float32), (50, 4)))
+
+
+# ---- camera: the thin lens against geometric optics ---------------------------------------------------------------------------
+def test_thin_lens_rays_focus_on_the_focal_plane_and_cover_the_field_of_view():
+    """camera.hlsl:14-43 + the pixel filter of main.hlsl:85-88, held to optics: (a) with a pinhole the mean direction of a pixel's
+    samples is the ray through that pixel's centre of a vfov / aspect frustum (top row at +vfov/2: image y runs downwards);
+    (b) with an aperture, origins fill a disc of diameter `aperture` around the lens centre, perpendicular to the view direction, and
+    every ray of a sample passes through the point of the focal plane its pinhole twin passes through."""
+    w, h, vfov, focus = 48, 24, math.radians(50.0), 2.5
+    origin, forward, up = np.array([0.3, -1.0, 0.7]), _unit((1.0, 0.4, -0.2)).astype(np.float64), np.array([0.0, 0.0, 1.0])
+    right = np.cross(forward, up); right /= np.linalg.norm(right)
+    true_up = np.cross(right, forward)
+    o = Oracle()
+    pin = scenes.Lens(tuple(origin), tuple(forward), tuple(up), vfov, 0.0, focus)
+    acc = np.zeros((h, w, 3))
+    n_samples = 48
+    for s in range(n_samples):
+        rays, _ = o.primary_rays(pin, w, h, s)
+        np.testing.assert_allclose(rays[..., :3], np.broadcast_to(origin.astype(np.float32), (h, w, 3)), atol=1e-6)
+        d = rays[..., 3:6].astype(np.float64)
+        np.testing.assert_allclose(np.linalg.norm(d, axis=-1), 1.0, atol=1e-5)
+        # where the ray meets the plane one unit in front of the eye, in (right, up) coordinates
+        t = 1.0 / (d @ forward)
+        acc += np.stack([(d @ right) * t, (d @ true_up) * t, t], -1)
+    mean = acc / n_samples
+    th = math.tan(vfov / 2)
+    px = ((np.arange(w) + 0.5) / w * 2 - 1) * th * (w / h)
+    py = (1 - (np.arange(h) + 0.5) / h * 2) * th
+    pixel = 2 * th / h   # one pixel on that plane
+    assert np.abs(mean[..., 0] - px[None, :]).max() < 0.35 * pixel   # mean of 48 filter offsets (sigma ~ half a pixel)
+    assert np.abs(mean[..., 1] - py[:, None]).max() < 0.35 * pixel
+    # (b)
+    aperture = 0.2
+    lens = scenes.Lens(tuple(origin), tuple(forward), tuple(up), vfov, aperture, focus)
+    radii = []
+    for s in range(8):
+        rp, _ = o.primary_rays(pin, w, h, s)
+        ra, _ = o.primary_rays(lens, w, h, s)
+        off = ra[..., :3].astype(np.float64) - origin
+        assert np.abs(off @ forward).max() < 1e-6                     # the lens disc is perpendicular to the view direction
+        radii.append(np.linalg.norm(off, axis=-1).ravel())
+        # both rays of a sample meet on the focal plane (the plane `focus` in front of the eye)
+        def on_focal_plane(r):
+            oo, dd = r[..., :3].astype(np.float64), r[..., 3:6].astype(np.float64)
+            t = (focus - (oo - origin) @ forward) / (dd @ forward)
+            return oo + dd * t[..., None]
+        np.testing.assert_allclose(on_focal_plane(ra), on_focal_plane(rp), atol=5e-5)
+    radii = np.concatenate(radii)
+    assert radii.max() <= aperture / 2 + 1e-6 and radii.max() > 0.49 * aperture
+    assert abs((radii ** 2).mean() / (aperture / 2) ** 2 - 0.5) < 0.02   # uniform over the disc: E[r^2] = R^2 / 2
