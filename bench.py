@@ -196,7 +196,8 @@ def main():
     ap.add_argument("--paths-in-flight", type=int, default=0, help="wavefront pool size in paths (0 = library default, 128 Mi)")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = same as --steps (capped at 32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--render-ahead", type=int, default=2, help="waves kept in flight beyond the one a call waits for, in the e2e_interactive.render_ahead leg (1..3)")
+    ap.add_argument("--ahead-tail-paths", type=int, default=0, help="measurement: k_tail threshold for the two e2e_interactive legs (0 = library default)")
+    ap.add_argument("--render-ahead", type=int, default=3, help="waves kept in flight beyond the one a call waits for, in the e2e_interactive.render_ahead leg (1..3)")
     args = ap.parse_args()
 
     if args.impl == "reference":
@@ -348,6 +349,8 @@ def main():
 
     # ---- e2e_interactive: the call pattern of the Hydra delegate (hydra/hydra.zig:316-329: ONE sample per HdMoonshineRender,
     # sensor copied to the host after every call), same scene and constants as above -------------------------------------------
+    if args.ahead_tail_paths:
+        m.SetSchedule(tail_paths=args.ahead_tail_paths)
     m.SetSpecConstants(scenes.Constants(samples_per_run=world))   # weak scaling: every rank still renders 1 spp of the full frame's worth of paths
     m.Render(sensor, lens)
     m.Render(sensor, lens)
@@ -382,6 +385,8 @@ def main():
     ahead_wall = time.perf_counter() - t0
     st4 = m.GetStats()
     m.SetRenderAhead(0)
+    if args.ahead_tail_paths:
+        m.SetSchedule()
     ahead_rays = allreduce(float(st4.rays_closest + st4.rays_shadow), dist.ReduceOp.SUM if world > 1 else None)
     ahead_wall = allreduce(ahead_wall, dist.ReduceOp.MAX if world > 1 else None)
     e2e_interactive["render_ahead"] = {"value": ahead_rays / ahead_wall / 1e6, "unit": UNIT, "calls": n_int, "ms_per_call": ahead_wall / n_int * 1e3,

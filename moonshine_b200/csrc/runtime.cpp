@@ -335,6 +335,11 @@ struct HdMoonshine {
     uint32_t maxLeaf = 3;   // triangles per BVH leaf (<= 8: 3-bit count in the leaf reference); 2-3 measured best
     int tailBlockThreads = 128;       // k_tail block size (32, 64 or 128; MSNE_TAIL_BLOCK): a block holds its registers until its longest path ends
     uint64_t tailThreshold = 32768;   // once fewer paths than this are expected to survive, k_tail finishes the wave
+    bool tailExplicit = false;        // the caller chose tailThreshold (HdMoonshineExtSetSchedule / MSNE_TAIL_THRESHOLD)
+    // render-ahead keeps the wavefront going four times longer: k_tail holds a quarter of an SM's registers per block until its longest
+    // path ends, which is what the younger waves' kernels wait for (8 Ki: 9.5 ms per call on cfg3, 32 Ki: 9.9, 128 Ki: 11.6; plain calls
+    // want 16-32 Ki: profiles/r02_sweeps.md section 9)
+    static constexpr uint64_t kAheadTailThreshold = 8192;
     bool forceTwoLevel = false;       // MSNE_TWO_LEVEL=1: never use the single-level trace kernel (A/B measurements)
     bool logBounces = false;          // MSNE_LOG_BOUNCES=1: queue sizes after every bounce on stderr (printed when the wave's log is read)
     uint64_t binnedThreshold = 262144;   // bounces expected to shade fewer paths than this use the single generic shade launch
@@ -384,7 +389,7 @@ struct HdMoonshine {
         if (const char* e = getenv("MSNE_TRACE_SUSPEND")) suspendThreshold = (uint32_t)std::min(16, std::max(0, atoi(e)));
         if (const char* e = getenv("MSNE_TRACE_SUSPEND_PASSES")) suspendPasses = std::min(3, std::max(1, atoi(e)));
         if (const char* e = getenv("MSNE_TAIL_BLOCK")) { const int t = atoi(e); if (t == 32 || t == 64 || t == 128) tailBlockThreads = t; }
-        if (const char* e = getenv("MSNE_TAIL_THRESHOLD")) tailThreshold = strtoull(e, nullptr, 10);
+        if (const char* e = getenv("MSNE_TAIL_THRESHOLD")) { tailThreshold = strtoull(e, nullptr, 10); tailExplicit = true; }
         if (const char* e = getenv("MSNE_SORT_THRESHOLD")) { sortThreshold = strtoull(e, nullptr, 10); sortAnyScene = true; }
         if (const char* e = getenv("MSNE_TILE_EDGE")) tileEdge = (uint32_t)std::min(256, std::max(8, atoi(e) / 8 * 8));
         if (const char* e = getenv("MSNE_WAVE_CONTEXTS")) waveContextsInUse = std::min(kWaveContexts, std::max(1, atoi(e)));
@@ -1168,6 +1173,8 @@ struct HdMoonshine {
         CK(cudaEventRecord(evStart, stream));
         for (int i = 0; i < nCtx; i++) CK(cudaStreamWaitEvent(ctx[i].stream, evStart, 0));   // uploads / clears queued on the main stream come first
         aheadSensor = &s; aheadLens = lens; aheadSpr = spr;
+        struct TailGuard { uint64_t& ref; uint64_t saved; ~TailGuard() { ref = saved; } } tailGuard{tailThreshold, tailThreshold};
+        if (!tailExplicit) tailThreshold = kAheadTailThreshold;
         auto launchNext = [&](uint32_t first, int busy) {   // sample `first` on a context that holds no unclaimed wave
             int c = -1;
             for (int i = 0; i < nCtx && c < 0; i++) {
@@ -1710,6 +1717,7 @@ void HdMoonshineExtSetProfiling(HdMoonshine* h, bool on) { LOCK(h); h->profiling
 void HdMoonshineExtSetSchedule(HdMoonshine* h, uint64_t tailPaths, uint64_t binnedPaths, uint32_t waveContexts) {
     LOCK(h);
     h->tailThreshold = tailPaths == UINT64_MAX ? 32768 : tailPaths;
+    h->tailExplicit = tailPaths != UINT64_MAX;
     h->binnedThreshold = binnedPaths == UINT64_MAX ? 262144 : binnedPaths;
     h->waveContextsInUse = waveContexts == 0 ? HdMoonshine::kDefaultWaveContexts : (int)std::min<uint32_t>(waveContexts, HdMoonshine::kWaveContexts);
     h->survivalIn.clear();

@@ -25,6 +25,8 @@ for v in "$@"; do
     ahead*) $B --render-ahead ${v#ahead} 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
     rsp*) MSNE_TRACE_SUSPEND=8 MSNE_TRACE_SUSPEND_PASSES=${v#rsp} $B 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
     rs*) MSNE_TRACE_SUSPEND=${v#rs} $B 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
+    ttb*) MSNE_TAIL_BLOCK=32 $B --steps 3 --ahead-tail-paths ${v#ttb} 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
+    tt*) $B --steps 3 --ahead-tail-paths ${v#tt} 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
     tb*) MSNE_TAIL_BLOCK=${v#tb} $B 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
     nosort) MSNE_SORT_THRESHOLD=0 $B 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
     tail8k) MSNE_TAIL_THRESHOLD=8192 $B 2>gpurun_out/ab_$v.err | python -c "$pick" $v ;;
