@@ -328,3 +328,46 @@ def test_thin_lens_rays_focus_on_the_focal_plane_and_cover_the_field_of_view():
     radii = np.concatenate(radii)
     assert radii.max() <= aperture / 2 + 1e-6 and radii.max() > 0.49 * aperture
     assert abs((radii ** 2).mean() / (aperture / 2) ** 2 - 0.5) < 0.02   # uniform over the disc: E[r^2] = R^2 / 2
+
+
+# ---- normal mapping: tangent-space convention ------------------------------------------------------------------------------------
+def test_normal_map_tilts_the_shading_normal_along_increasing_u():
+    """A tangent-space normal (x, y, z) means x along dP/du, y along dP/dv, z along the surface normal (world.hlsl:86-100 builds the
+    frame from the texcoord derivatives, material.hlsl:489-517 decodes and applies the map). A floor whose u runs along world +x, lit
+    by a small far emitter 45 degrees towards +x: tilting the map's normal 30 degrees towards +x must brighten the Lambert response
+    by cos 15 / cos 45, tilting it towards -x must darken it by cos 75 / cos 45 - the geometry term does not move."""
+    rho, L = 0.8, 4000.0
+    ldir = np.array([math.sin(math.radians(45)), 0.0, math.cos(math.radians(45))])
+
+    def render(nx):
+        s = scenes.Scene("normal-map", extent=(16, 16), lens=scenes.Lens((0.0, -3.0, 3.0), (0.0, 3.0, -3.0), (0, 0, 1), math.radians(1.0), 0.0, 1.0))
+        black, white = s.solid3(0, 0, 0), s.solid3(rho, rho, rho)
+        floor_mat = s.add_material(type=LAMBERT, normal=s.solid2(0.5 + 0.5 * nx, 0.5), emissive=black, color=white)   # rg = n.xy * 0.5 + 0.5
+        quad = np.array([[-4, -4, 0], [4, -4, 0], [4, 4, 0], [-4, 4, 0]], np.float32)
+        uv = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], np.float32)                                                    # u along +x, v along +y
+        nrm = np.array([[0, 0, 1]] * 4, np.float32)
+        floor = s.add_mesh(quad, np.array([[0, 1, 2], [0, 2, 3]], np.uint32), normals=nrm, texcoords=uv)
+        s.add_instance([(floor, floor_mat, False)])
+        # emitter: a 0.2 x 0.2 square 10 units away along ldir, facing the origin
+        c = ldir * 10.0
+        e1 = np.array([0.0, 1.0, 0.0])
+        e2 = np.cross(ldir, e1)
+        corners = np.array([c + 0.1 * (-e1 - e2), c + 0.1 * (e1 - e2), c + 0.1 * (e1 + e2), c + 0.1 * (-e1 + e2)], np.float32)
+        light_mat = s.add_material(type=LAMBERT, normal=s.solid2(0.5, 0.5), emissive=s.solid3(L, L, L), color=black)
+        tri = np.array([[0, 1, 2], [0, 2, 3]], np.uint32)
+        n_geo = np.cross(corners[0] - corners[2], corners[1] - corners[2])
+        if np.dot(n_geo, -ldir) < 0:          # emission leaves the side the geometric normal points to: towards the origin
+            tri = tri[:, ::-1].copy()
+        light = s.add_mesh(corners, tri)
+        s.add_instance([(light, light_mat, True)])
+        s.background = np.array([[[0, 0, 0, 1]]], np.float32)
+        s.constants = scenes.Constants(samples_per_run=512, max_bounces=1, env_samples_per_bounce=0, mesh_samples_per_bounce=1)
+        rgb, counts = _mean_rgb(s)
+        assert counts[1] > 0
+        return rgb[0]
+
+    flat, plus, minus = render(0.0), render(0.5), render(-0.5)
+    irradiance = L * 0.04 / 100.0 * math.cos(math.radians(45))          # L * A / r^2 * cos at the floor (the emitter faces the floor point)
+    assert abs(flat / (rho / math.pi * irradiance) - 1) < 0.005
+    assert abs(plus / flat - math.cos(math.radians(15)) / math.cos(math.radians(45))) < 0.005
+    assert abs(minus / flat - math.cos(math.radians(75)) / math.cos(math.radians(45))) < 0.005
