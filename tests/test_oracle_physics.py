@@ -371,3 +371,55 @@ def test_normal_map_tilts_the_shading_normal_along_increasing_u():
     assert abs(flat / (rho / math.pi * irradiance) - 1) < 0.005
     assert abs(plus / flat - math.cos(math.radians(15)) / math.cos(math.radians(45))) < 0.005
     assert abs(minus / flat - math.cos(math.radians(75)) / math.cos(math.radians(45))) < 0.005
+
+
+# ---- instancing: a transformed instance is the transformed mesh -------------------------------------------------------------------
+def test_an_instance_transform_renders_the_transformed_mesh():
+    """Rays enter an instance through worldToInstance, hit attributes leave it through inWorld: positions by the instance matrix,
+    frames by the inverse transpose (world.hlsl:160-176, reflection_frame.hlsl:23-29). (a) Rotation, uniform scale and translation:
+    the instanced unit sphere is, pixel for pixel, the sphere baked into world-space vertices (same random streams, same frames up
+    to rounding). (b) Non-uniform scale: tangents carried by the inverse transpose differ from tangents of the baked mesh, so samples
+    are rotated about the normal - the images agree in expectation only - but the NORMAL must be the inverse-transpose one: baking
+    normals like directions shades the ellipsoid visibly differently."""
+    pos, idx = scenes.icosphere(3)
+    pos = np.asarray(pos, np.float64)
+    nrm = pos / np.linalg.norm(pos, axis=1, keepdims=True)
+    a = math.radians(35.0)
+    rot = np.array([[math.cos(a), -math.sin(a), 0], [math.sin(a), math.cos(a), 0], [0, 0, 1]])
+    t = np.array([0.2, -0.1, 0.15])
+    rs = np.random.RandomState(4)
+    sky = np.ones((8, 8, 4), np.float32)
+    sky[..., :3] = (rs.rand(8, 8, 1) ** 2 * 3 + 0.1).astype(np.float32)   # uneven light: shading depends on the normal
+
+    def render(p, n, xf, spr):
+        s = scenes.Scene("instancing", extent=(48, 48))
+        mat = s.add_material(type=LAMBERT, normal=s.solid2(0.5, 0.5), emissive=s.solid3(0, 0, 0), color=s.solid3(0.7, 0.7, 0.7))
+        mesh = s.add_mesh(p.astype(np.float32), idx, normals=n.astype(np.float32))
+        s.add_instance([(mesh, mat, False)], transform=xf)
+        s.background = sky
+        s.constants = scenes.Constants(samples_per_run=spr, max_bounces=4, env_samples_per_bounce=1, mesh_samples_per_bounce=0)
+        s.build_emitter_table = False
+        o = Oracle()
+        scenes.load_scene(o, s)
+        img, _ = o.render(s.lens, *s.extent)
+        return img[..., :3].astype(np.float64)
+
+    def baked(m, normals_by):
+        n = nrm @ normals_by
+        return pos @ m.T + t, n / np.linalg.norm(n, axis=1, keepdims=True)
+
+    # (a) similarity transform
+    m = rot * 0.9
+    instanced = render(pos, nrm, np.concatenate([m, t[:, None]], 1), 8)
+    ref = render(*baked(m, np.linalg.inv(m)), None, 8)
+    close = np.abs(instanced - ref).max(-1) <= 2e-3 * np.maximum(1.0, ref.max(-1))
+    assert close.mean() > 0.99, close.mean()          # only silhouette / grazing pixels may take other paths
+    # (b) non-uniform scale, compared over 6 x 6 pixel blocks at 64 spp
+    m = rot @ np.diag([1.6, 0.8, 0.5])
+    blocks = lambda img: img.reshape(8, 6, 8, 6, 3).mean((1, 3))
+    instanced = blocks(render(pos, nrm, np.concatenate([m, t[:, None]], 1), 64))
+    right = blocks(render(*baked(m, np.linalg.inv(m)), None, 64))       # rows: (M^-T n)^T
+    wrong = blocks(render(*baked(m, m.T), None, 64))                    # normals carried like directions
+    err_right, err_wrong = np.abs(instanced - right).mean(), np.abs(instanced - wrong).mean()
+    assert err_right < 0.005 * right.mean(), (err_right, right.mean())
+    assert err_wrong > 8 * err_right, (err_wrong, err_right)
