@@ -423,3 +423,36 @@ def test_an_instance_transform_renders_the_transformed_mesh():
     err_right, err_wrong = np.abs(instanced - right).mean(), np.abs(instanced - wrong).mean()
     assert err_right < 0.005 * right.mean(), (err_right, right.mean())
     assert err_wrong > 8 * err_right, (err_wrong, err_right)
+
+
+def test_unevenly_tessellated_one_sided_emitter():
+    """The same square light cut into four triangles of very different areas (a fan around an off-centre point) must light the floor
+    exactly as before: MeshLights::sample has to pick triangles with the probability its pdf assumes (area / total area, alias table
+    of Accel.zig:491-538). Seen from behind, the emitter is black: emission leaves the side of the geometric normal only."""
+    albedo, L, a, h = 0.6, 5.0, 1.0, 1.0
+    x = (a / 2) / h
+    expect = albedo * L * 4 * (x / math.sqrt(1 + x * x) * math.atan(x / math.sqrt(1 + x * x))) * 2 / (2 * math.pi)
+    q = a / 2
+    verts = np.array([[-q, -q, h], [-q, q, h], [q, q, h], [q, -q, h], [0.35, -0.4, h]], np.float32)   # 4 = fan centre, near one corner
+    fan = np.array([[0, 1, 4], [1, 2, 4], [2, 3, 4], [3, 0, 4]], np.uint32)                               # faces -z like the two-triangle quad
+    areas = [0.5 * np.linalg.norm(np.cross(verts[t[1]] - verts[t[0]], verts[t[2]] - verts[t[0]])) for t in fan]
+    assert max(areas) / min(areas) > 8 and abs(sum(areas) - a * a) < 1e-6
+    sc, n, black = _floor_scene(albedo)
+    light_mat = sc.add_material(type=LAMBERT, normal=n, emissive=sc.solid3(L, L, L), color=black)
+    sc.add_instance([(sc.add_mesh(verts, fan), light_mat, True)])
+    sc.background = np.array([[[0, 0, 0, 1]]], np.float32)
+    sc.constants = scenes.Constants(samples_per_run=256, max_bounces=1, env_samples_per_bounce=0, mesh_samples_per_bounce=1)
+    rgb, counts = _mean_rgb(sc)
+    assert counts[1] > 0
+    np.testing.assert_allclose(rgb, expect, rtol=0.006)
+    # the back of the emitter, looked at from above
+    sc.lens = scenes.Lens((0.0, 0.0, 4.0), (0.0, 0.0, -1.0), (0, 1, 0), math.radians(2.0), 0.0, 1.0)
+    o = Oracle()
+    scenes.load_scene(o, sc)
+    img, _ = o.render(sc.lens, *sc.extent)
+    assert np.abs(img[..., :3]).max() == 0.0     # back face: no emission; it is black (albedo 0) and hides the lit floor below it
+    sc.lens = scenes.Lens((0.0, 0.0, 0.2), (0.0, 0.0, 1.0), (0, 1, 0), math.radians(2.0), 0.0, 1.0)
+    o = Oracle()
+    scenes.load_scene(o, sc)
+    img, _ = o.render(sc.lens, *sc.extent)
+    np.testing.assert_allclose(img[..., :3], L, rtol=1e-6)   # front face, looked at from the floor: its radiance
