@@ -12,7 +12,11 @@
 // values derived from shaders/utils/random.hlsl:8-45 and (b) the reference's own
 // furnace tests engine/tests.zig:257-364,366-455 (tests/test_oracle_furnace.py). Ray/triangle
 // arithmetic and texture filtering (driver/hardware in the reference) are "parity unpinned" and
-// are defined in bvh.h / scene.h.
+// are defined in bvh.h / scene.h. Beyond the reference's own material, tests/test_oracle_physics.py
+// holds the restatement to what any correct implementation of these models satisfies (reciprocity,
+// energy, pdf vs sample distribution, Snell / Fresnel, configuration factors, sky quadrature,
+// Vulkan filtering rules, thin-lens optics, tangent-space and instancing conventions) - that
+// narrows what a misreading of the HLSL could be, it does not replace vectors from the reference.
 #include <atomic>
 #include <thread>
 #include "host.h"
