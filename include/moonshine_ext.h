@@ -63,6 +63,7 @@ typedef struct MsneStats {
     uint64_t tail_paths;                /* paths left to k_tail after the wavefront bounces, summed over waves */
     double   accel_sync_ms;             /* host wall time spent bringing the acceleration structure up to date after edits (builds, refits, record uploads) */
     uint64_t ahead_discarded;           /* render-ahead: speculative waves dropped unseen because the next call did not ask for that sample */
+    uint64_t pool_bytes;                /* device memory held by the wavefront pools right now (path state, queues, sort buffers); see HdMoonshineExtReleasePools */
 } MsneStats;
 
 /* must be called before HdMoonshineCreate; selects the CUDA device of objects created afterwards */
@@ -103,6 +104,10 @@ MSNE_API bool HdMoonshineExtCommReduceSensor(HdMoonshine*, SensorHandle, uint32_
 MSNE_API bool HdMoonshineExtCommAllReduceU64(HdMoonshine*, uint64_t* values, size_t n);   /* sum over ranks, in place (ray counters) */
 MSNE_API void HdMoonshineExtCommDestroy(HdMoonshine*);
 MSNE_API void HdMoonshineExtSetPathsInFlight(HdMoonshine*, uint64_t max_paths);   /* wavefront pool size (0 = default) */
+/* The pools grow to what the largest render so far needed (326 B per path in flight: 0.7 GB for a one-sample 1080p call, 41 GiB for
+ * the default 2 x 64 Mi paths of a long offline render) and stay allocated between renders. This returns them to the driver; the
+ * next render allocates what it needs again. MsneStats.pool_bytes reports the current holding. */
+MSNE_API bool HdMoonshineExtReleasePools(HdMoonshine*);
 /* extension-ray queues of at least `min_rays` are traced in sorted order (direction octant + origin cell); 0 = never,
  * UINT64_MAX = library default (262144, and only for scenes whose BVHs hold >= 2048 nodes). Ordering only: images are
  * bitwise identical either way. */

@@ -983,6 +983,28 @@ struct HdMoonshine {
         }
         pb.Q0 = c.poolBufs[10].p; pb.Q1 = c.poolBufs[10].p + 1; pb.result = c.poolBufs[11].p; pb.H = c.poolH.p; pb.typeList = c.poolTypeList.p; pb.capacity = P;
     }
+    // bytes of device memory held by the wave pools (path state, queues, sort and continuation buffers) of all contexts
+    uint64_t poolBytes() const {
+        uint64_t b = 0;
+        for (const WaveCtx& c : ctx) {
+            for (const auto& buf : c.poolBufs) b += buf.n * sizeof(float4);
+            b += c.poolH.n * sizeof(uint4) + c.poolTypeList.n * 4 + c.sortKeysExt.n * 2 + c.sortKeysShadow.n * 2 + c.sortPermExt.n * 4 + c.sortPermShadow.n * 4 +
+                 c.sortBlockHist.n * 4 + c.contA.n * sizeof(uint4) + c.contB.n * sizeof(uint4);
+        }
+        return b;
+    }
+    // gives the wave pools back to the driver (they are sized by the largest render so far and never shrink on their own); the next
+    // render allocates what it needs
+    void releasePools() {
+        finishWaves();
+        for (WaveCtx& c : ctx) {
+            if (c.stream) CK(cudaStreamSynchronize(c.stream));
+            c.poolBufs.clear(); c.poolH.release(); c.poolTypeList.release();
+            c.sortKeysExt.release(); c.sortKeysShadow.release(); c.sortPermExt.release(); c.sortPermShadow.release(); c.sortBlockHist.release();
+            c.contA.release(); c.contB.release();
+            c.pb = PathBuffers{};
+        }
+    }
     void ensureSortBuffers(WaveCtx& c) {
         const size_t P = c.pb.capacity;
         if (c.sortKeysExt.n >= P) return;
@@ -1306,6 +1328,7 @@ struct HdMoonshine {
     void fetchStats(MsneStats& out) {
         use();
         out = stats;
+        out.pool_bytes = poolBytes();
         out.rays_closest = 0; out.rays_shadow = 0; out.max_bounce_reached = 0;
         for (WaveCtx& c : ctx) {
             unsigned long long rc[2] = {0, 0};
@@ -1721,6 +1744,10 @@ void HdMoonshineExtSetSchedule(HdMoonshine* h, uint64_t tailPaths, uint64_t binn
     h->binnedThreshold = binnedPaths == UINT64_MAX ? 262144 : binnedPaths;
     h->waveContextsInUse = waveContexts == 0 ? HdMoonshine::kDefaultWaveContexts : (int)std::min<uint32_t>(waveContexts, HdMoonshine::kWaveContexts);
     h->survivalIn.clear();
+}
+bool HdMoonshineExtReleasePools(HdMoonshine* h) {
+    LOCK(h);
+    try { h->use(); h->releasePools(); return true; } catch (const std::exception& e) { g_lastError = e.what(); return false; }
 }
 void HdMoonshineExtSetTraceSuspend(HdMoonshine* h, uint32_t lanes) {
     LOCK(h);

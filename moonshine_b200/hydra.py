@@ -66,7 +66,7 @@ class MsneStats(C.Structure):
                 ("device_ms", C.c_double), ("trace_ms", C.c_double), ("trace_launches", C.c_uint64), ("max_bounce_reached", C.c_uint64),
                 ("static_blas_builds", C.c_uint64), ("tlas_builds", C.c_uint64), ("tlas_refits", C.c_uint64), ("sort_ms", C.c_double),
                 ("waves", C.c_uint64), ("host_syncs", C.c_uint64), ("tail_paths", C.c_uint64), ("accel_sync_ms", C.c_double),
-                ("ahead_discarded", C.c_uint64)]
+                ("ahead_discarded", C.c_uint64), ("pool_bytes", C.c_uint64)]
 
 
 class MsneClickData(C.Structure):   # input.hlsl:1-6
@@ -125,6 +125,7 @@ SIGNATURES = {
     "HdMoonshineExtSetRaySorting": (None, [_VP, C.c_uint64]),
     "HdMoonshineExtSetProfiling": (None, [_VP, C.c_bool]),
     "HdMoonshineExtSetSchedule": (None, [_VP, C.c_uint64, C.c_uint64, _U32]),
+    "HdMoonshineExtReleasePools": (C.c_bool, [_VP]),
     "HdMoonshineExtSetTraceSuspend": (None, [_VP, _U32]),
     "HdMoonshineExtSetRenderAhead": (None, [_VP, _U32]),
     "HdMoonshineExtGetStats": (None, [_VP, C.POINTER(MsneStats)]),
@@ -327,6 +328,7 @@ class HdMoonshine:
         big = 0xFFFFFFFFFFFFFFFF
         self.L.HdMoonshineExtSetSchedule(self.h, big if tail_paths is None else tail_paths, big if binned_paths is None else binned_paths, wave_contexts)
 
+    def ReleasePools(self) -> bool: return bool(self.L.HdMoonshineExtReleasePools(self.h))
     def SetTraceSuspend(self, lanes: int): self.L.HdMoonshineExtSetTraceSuspend(self.h, int(lanes))
     def SetRenderAhead(self, waves_ahead: int): self.L.HdMoonshineExtSetRenderAhead(self.h, int(waves_ahead))
 

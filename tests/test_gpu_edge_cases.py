@@ -334,3 +334,29 @@ def test_render_ahead_frames_are_the_bits_of_plain_rendering(waves_ahead):
         assert (a.view(np.uint32) == b.view(np.uint32)).all(), f"call {i}: render-ahead frame differs"
     assert st0.ahead_discarded == 0 and st1.ahead_discarded >= 4   # the edit, the other lens, SetLens, the clear
     assert st1.samples == st0.samples
+
+
+def test_released_pools_are_rebuilt_on_demand_with_the_same_bits():
+    """HdMoonshineExtReleasePools: the wavefront pools (sized by the largest render so far) go back to the driver; the next render
+    allocates what it needs and continues the accumulation bit for bit."""
+    sc = scenes.material_zoo((96, 64))
+
+    def session(release):
+        m = hydra.HdMoonshine()
+        scenes.load_scene(m, sc)
+        m.SetRaySorting(1)
+        sensor, lens = m.CreateSensor(*sc.extent), m.CreateLens(sc.lens)
+        m.RenderLaunches(sensor, lens, 3)
+        held = m.GetStats().pool_bytes
+        assert held > 96 * 64 * 300
+        if release:
+            assert m.ReleasePools()
+            assert m.GetStats().pool_bytes == 0
+        m.RenderLaunches(sensor, lens, 2)
+        assert m.GetStats().pool_bytes > 0
+        img = m.ReadSensor(sensor).copy()
+        m.Destroy()
+        return img
+
+    a, b = session(False), session(True)
+    np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))
