@@ -9,7 +9,7 @@ import pytest
 
 from moonshine_b200 import hydra, scenes
 from oracle.binding import Oracle
-from gpu_common import gpu_render, oracle_render, random_rays, within_tol_fraction
+from gpu_common import gpu_render, identical_fraction, oracle_render, random_rays, within_tol_fraction
 
 pytestmark = pytest.mark.gpu
 
@@ -170,6 +170,18 @@ def test_suspend_and_regroup_tracing_is_bitwise_invariant():
             np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32), err_msg=f"{lanes} lanes")
             assert (sa.rays_closest, sa.rays_shadow) == (sb.rays_closest, sb.rays_shadow)
             assert sb.kernel_launches > sa.kernel_launches + 8   # the two extra passes really ran, on several bounces
+
+
+def test_physics_scenes_are_bit_identical_on_the_gpu():
+    """The scenes of tests/test_oracle_physics.py (explicit texcoords + normals + a tilted normal map, an unevenly tessellated
+    emitter with two light samples per bounce, an uneven sky with three env samples per bounce, non-uniformly scaled instances):
+    what those tests establish for the oracle holds for the CUDA path because its images are the oracle's, bit for bit."""
+    from test_oracle_physics import physics_scenes
+    for sc in physics_scenes():
+        g, sg, _ = gpu_render(sc, 1)
+        r, counts, _ = oracle_render(sc, 1)
+        assert identical_fraction(g, r) == 1.0, sc.name
+        assert int(sg.rays_closest) == int(counts[0]), sc.name
 
 
 def test_schedule_hints_never_change_the_image():

@@ -456,3 +456,50 @@ def test_unevenly_tessellated_one_sided_emitter():
     scenes.load_scene(o, sc)
     img, _ = o.render(sc.lens, *sc.extent)
     np.testing.assert_allclose(img[..., :3], L, rtol=1e-6)   # front face, looked at from the floor: its radiance
+
+
+# ---- the scenes above, for the GPU twin (tests/test_gpu_parity.py::test_physics_scenes_are_bit_identical_on_the_gpu) ----------------
+def physics_scenes():
+    """Small scenes in the style of the checks above that lean on code paths the procedural BASELINE scenes use lightly: explicit
+    texcoords + vertex normals + a tilted constant normal map, an unevenly tessellated one-sided emitter with two light samples per
+    bounce, an uneven sky with three env samples per bounce, a non-uniformly scaled instance."""
+    out = []
+    # normal-mapped floor under a far emitter
+    s = scenes.Scene("phys-normal-map", extent=(16, 16), lens=scenes.Lens((0.0, -3.0, 3.0), (0.0, 3.0, -3.0), (0, 0, 1), math.radians(4.0), 0.0, 1.0))
+    black, white = s.solid3(0, 0, 0), s.solid3(0.8, 0.8, 0.8)
+    floor_mat = s.add_material(type=LAMBERT, normal=s.solid2(0.75, 0.4), emissive=black, color=white)
+    quad = np.array([[-4, -4, 0], [4, -4, 0], [4, 4, 0], [-4, 4, 0]], np.float32)
+    floor = s.add_mesh(quad, np.array([[0, 1, 2], [0, 2, 3]], np.uint32), normals=np.array([[0, 0, 1]] * 4, np.float32),
+                       texcoords=np.array([[0, 0], [1, 0], [1, 1], [0, 1]], np.float32))
+    s.add_instance([(floor, floor_mat, False)])
+    light_mat = s.add_material(type=LAMBERT, normal=s.solid2(0.5, 0.5), emissive=s.solid3(400, 300, 200), color=black)
+    verts = np.array([[-0.5, -0.5, 2], [-0.5, 0.5, 2], [0.5, 0.5, 2], [0.5, -0.5, 2], [0.35, -0.4, 2]], np.float32)
+    fan = np.array([[0, 1, 4], [1, 2, 4], [2, 3, 4], [3, 0, 4]], np.uint32)
+    s.add_instance([(s.add_mesh(verts, fan), light_mat, True)])
+    s.background = np.array([[[0, 0, 0, 1]]], np.float32)
+    s.constants = scenes.Constants(samples_per_run=64, max_bounces=3, env_samples_per_bounce=0, mesh_samples_per_bounce=2)
+    out.append(s)
+    # uneven sky, three env samples per bounce, a non-uniformly scaled and rotated instance with vertex normals
+    rs = np.random.RandomState(11)
+    sky = np.ones((16, 16, 4), np.float32)
+    sky[..., :3] = (rs.rand(16, 16, 1) ** 4 * 6 + 0.05).astype(np.float32) * np.array([1.0, 0.8, 0.6], np.float32)
+    s = scenes.Scene("phys-sky-instance", extent=(40, 40))
+    mat = s.add_material(type=LAMBERT, normal=s.solid2(0.5, 0.5), emissive=s.solid3(0, 0, 0), color=s.solid3(0.7, 0.7, 0.7))
+    pos, idx = scenes.icosphere(3)
+    pos = np.asarray(pos, np.float32)
+    mesh = s.add_mesh(pos, idx, normals=pos / np.linalg.norm(pos, axis=1, keepdims=True))
+    a = math.radians(35.0)
+    m = np.array([[math.cos(a), -math.sin(a), 0], [math.sin(a), math.cos(a), 0], [0, 0, 1]]) @ np.diag([1.6, 0.8, 0.5])
+    s.add_instance([(mesh, mat, False)], transform=np.concatenate([m, [[0.2], [-0.1], [0.15]]], 1))
+    s.add_instance([(mesh, mat, False)], transform=np.array([[0.4, 0, 0, -0.2], [0, 0.4, 0, 0.9], [0, 0, 0.4, 0.6]], np.float32))
+    s.background = sky
+    s.constants = scenes.Constants(samples_per_run=16, max_bounces=6, env_samples_per_bounce=3, mesh_samples_per_bounce=0)
+    s.build_emitter_table = False
+    out.append(s)
+    return out
+
+
+def test_physics_scenes_render_on_the_oracle():
+    for sc in physics_scenes():
+        rgb, counts = _mean_rgb(sc)
+        assert (rgb > 0).all() and counts[0] > 0 and counts[1] > 0
