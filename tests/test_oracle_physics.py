@@ -503,3 +503,87 @@ def test_physics_scenes_render_on_the_oracle():
     for sc in physics_scenes():
         rgb, counts = _mean_rgb(sc)
         assert (rgb > 0).all() and counts[0] > 0 and counts[1] > 0
+
+
+def test_mirror_floor_shows_the_sky_in_the_reflected_direction():
+    """One sample per pixel on a perfect-mirror floor: the pixel must hold the sky's radiance in the direction of its own primary ray
+    reflected about the floor normal (d.x, d.y, -d.z) - law of reflection, unit throughput (eval * |cos| / pdf of material.hlsl:313-330),
+    and the pixel <-> primary-ray correspondence of raygen (main.hlsl:54-95), all at once and per pixel."""
+    rs = np.random.RandomState(21)
+    sky = np.ones((32, 32, 4), np.float32)
+    sky[..., :3] = (rs.rand(32, 32, 3) ** 2 * 3 + 0.05).astype(np.float32)
+    s = scenes.Scene("mirror-floor", extent=(40, 24), lens=scenes.Lens((0.0, -2.0, 2.0), (0.0, 1.0, -1.0), (0, 0, 1), math.radians(40.0), 0.0, 1.0))
+    mat = s.add_material(type=scenes.MAT_PERFECT_MIRROR, normal=s.solid2(0.5, 0.5), emissive=s.solid3(0, 0, 0))
+    quad = np.array([[-50, -50, 0], [50, -50, 0], [50, 50, 0], [-50, 50, 0]], np.float32)
+    s.add_instance([(s.add_mesh(quad, np.array([[0, 1, 2], [0, 2, 3]], np.uint32)), mat, False)])
+    s.background = sky
+    s.constants = scenes.Constants(samples_per_run=1, max_bounces=8, env_samples_per_bounce=1, mesh_samples_per_bounce=0)
+    s.build_emitter_table = False
+    o = Oracle()
+    scenes.load_scene(o, s)
+    img, counts = o.render(s.lens, *s.extent)
+    rays, _ = o.primary_rays(s.lens, *s.extent, 0)
+    d = rays[..., 3:6].reshape(-1, 3).copy()
+    assert (d[:, 2] < 0).all()                       # every primary ray goes down to the floor
+    d[:, 2] = -d[:, 2]
+    expect = o.env_probe(2, d)[:, :3].reshape(img.shape[0], img.shape[1], 3)
+    np.testing.assert_allclose(img[..., :3], expect, rtol=2e-5, atol=1e-6)
+    assert counts[0] == 2 * img.shape[0] * img.shape[1] and counts[1] == 0   # primary + reflected ray per pixel, no shadow rays on a delta surface
+
+
+def test_glass_slab_transmits_undeviated_and_reflects_like_a_stack_of_two_interfaces():
+    """A plane-parallel glass slab under a sky, one sample per pixel: whatever sequence of refractions and internal reflections a path
+    takes, it leaves either upwards in the mirrored direction or downwards in its ORIGINAL direction (Snell at the way in undone at the
+    way out) with unit throughput; and the share of paths that come back up is the incoherent two-interface reflectance 2R / (1 + R),
+    R the Fresnel reflectance of one interface at that angle."""
+    rs = np.random.RandomState(22)
+    sky = np.ones((32, 32, 4), np.float32)
+    sky[..., :3] = (rs.rand(32, 32, 3) ** 2 * 3 + 0.05).astype(np.float32)
+    ior, air, incidence = 1.5, 1.000277, math.radians(55.0)
+    fwd = (0.0, math.sin(incidence), -math.cos(incidence))
+    s = scenes.Scene("glass-slab", extent=(96, 96), lens=scenes.Lens((0.0, -3 * math.sin(incidence), 3 * math.cos(incidence)), fwd, (0, 0, 1), math.radians(1.0), 0.0, 1.0))
+    mat = s.add_material(type=GLASS, normal=s.solid2(0.5, 0.5), emissive=s.solid3(0, 0, 0), ior=ior)
+    e = 200.0
+    top = np.array([[-e, -e, 0], [e, -e, 0], [e, e, 0], [-e, e, 0]], np.float32)
+    bottom = top[::-1].copy() - np.array([0, 0, 0.5], np.float32)          # faces -z
+    tri = np.array([[0, 1, 2], [0, 2, 3]], np.uint32)
+    s.add_instance([(s.add_mesh(top, tri), mat, False), (s.add_mesh(bottom, tri), mat, False)])
+    s.background = sky
+    s.constants = scenes.Constants(samples_per_run=1, max_bounces=64, env_samples_per_bounce=1, mesh_samples_per_bounce=0)
+    s.build_emitter_table = False
+    o = Oracle()
+    scenes.load_scene(o, s)
+    img, counts = o.render(s.lens, *s.extent)
+    rays, _ = o.primary_rays(s.lens, *s.extent, 0)
+    d = rays[..., 3:6].reshape(-1, 3)
+    through = o.env_probe(2, d)[:, :3]
+    mirrored = o.env_probe(2, d * np.array([1, 1, -1], np.float32))[:, :3]
+    got = img[..., :3].reshape(-1, 3).astype(np.float64)
+
+    def weight_if_match(target):
+        """got = w * target with one w for the three channels and w = 0.95^-k, k = 0, 1, 2 ...: unit throughput, times one division by
+        the survival probability for every Russian-roulette test passed after the third bounce (integrator.hlsl:128-135) -> w, else nan"""
+        ratio = got / target
+        same = np.abs(ratio - ratio[:, :1]).max(1) < 3e-4
+        k = np.log(np.maximum(ratio[:, 0], 1e-30)) / -math.log(0.95)
+        ok = same & (np.abs(k - np.round(k)) < 2e-2) & (k > -0.5)
+        return np.where(ok, ratio[:, 0], np.nan)
+
+    w_through, w_mirrored = weight_if_match(through.astype(np.float64)), weight_if_match(mirrored.astype(np.float64))
+    killed = (got == 0).all(1)                          # ended by Russian roulette inside the slab
+    is_through, is_mirrored = ~np.isnan(w_through), ~np.isnan(w_mirrored)
+    assert (is_through | is_mirrored | killed).all()    # nothing else comes out of a slab
+    assert not (is_through & is_mirrored).any()
+    assert killed.mean() < 0.002 and (np.nan_to_num(w_through) + np.nan_to_num(w_mirrored) > 1.01).mean() < 0.002   # roulette only touches paths of 4+ bounces
+    cos_i = math.cos(incidence)
+    sin_t = math.sin(incidence) * air / ior
+    cos_t = math.sqrt(1 - sin_t * sin_t)
+    rp = (ior * cos_i - air * cos_t) / (ior * cos_i + air * cos_t)
+    rs_ = (air * cos_i - ior * cos_t) / (air * cos_i + ior * cos_t)
+    r1 = 0.5 * (rp * rp + rs_ * rs_)
+    expect = 2 * r1 / (1 + r1)
+    n = len(got)
+    reflected, transmitted = np.nansum(w_mirrored) / n, np.nansum(w_through) / n      # unbiased estimates of the two energy shares
+    assert abs(reflected - expect) < 4 * math.sqrt(expect * (1 - expect) / n) + 2e-3, (reflected, expect)
+    assert abs(reflected + transmitted - 1.0) < 2e-3                                   # energy is conserved
+    assert counts[1] == 0
