@@ -316,6 +316,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, TWO_LEVEL ? TRACE_BLOCKS_PER_SM
 // PASS 0: tickets over the sorted queues (as k_trace<false, true>), PASS 1 / 2: tickets over the records of recA / recB.
 // ------------------------------------------------------------------------------------------------
 #define RS_REC_U4 8   // uint4 per record: 2 header + 6 x 4 stack entries
+static_assert(2 + (MSNE_RS_MAX_SAVE + 3) / 4 <= RS_REC_U4, "a continuation record must hold every stack entry a suspended walk may save");
+static_assert(MSNE_RS_MAX_SAVE + 4 <= MSNE_STACK, "restoring a record writes whole uint4 groups into the traversal stack");
 template <int PASS>
 __global__ void __launch_bounds__(TRACE_THREADS, TRACE1_BLOCKS_PER_SM) k_trace_rs(DeviceScene sc, PathBuffers pb, WaveState ws, uint32_t buf, const uint32_t* __restrict__ permExt,
                                                                                   const uint32_t* __restrict__ permShadow, ContBuffers cb, uint32_t threshold) {
