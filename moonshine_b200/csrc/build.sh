@@ -10,3 +10,8 @@ $NVCC -gencode arch=compute_100a,code=sm_100a -std=c++17 -O3 -lineinfo -fmad=fal
       -Xcompiler -fPIC,-ffp-contract=off,-fno-fast-math,-Wall,-Wno-unused-function \
       -shared kernels.cu runtime.cpp bvh_build.cpp -ldl -o $OUT "$@"
 echo "built $(realpath $OUT)"
+# the native `offline` front end (offline/main.zig:27-203 over the C ABI): only next to the default library
+if [ "$OUT" = "../libmoonshine.so" ] && [ $# -eq 0 ]; then
+  ${CXX:-g++} -std=c++17 -O2 -Wall -Wextra -ffp-contract=off offline_main.cpp -o ../offline -L.. -lmoonshine -lz -Wl,-rpath,'$ORIGIN'
+  echo "built $(realpath ../offline)"
+fi

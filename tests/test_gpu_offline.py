@@ -37,3 +37,25 @@ def test_offline_cli_argument_errors(tmp_path):
         offline.main(["scene.gltf", "sky.exr", "out.exr"])
     with pytest.raises(SystemExit, match="OnlySupportsExrOutput"):
         offline.main(["scene.glb", "sky.exr", "out.png"])
+
+
+def test_native_offline_executable_writes_the_same_exr(tmp_path):
+    """moonshine_b200/offline (csrc/offline_main.cpp: offline/main.zig:27-203 as a native program over the C ABI, own GLB / PNG / EXR
+    code): the file it writes is, byte for byte, the file the Python front end writes for the same arguments."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "moonshine_b200", "offline")
+    if not os.path.exists(exe):
+        subprocess.check_call(["bash", os.path.join(root, "moonshine_b200", "csrc", "build.sh")])
+    src = scenes.material_zoo((80, 56))
+    src.materials[1].color = src.solid3(0.7, 0.6, 0.2)
+    src.textures[src.materials[0].metalness] = scenes.Texture(((np.indices((32, 32)).sum(0) % 2) * 255).astype(np.uint8), 32, 32, scenes.TEX_R8_UNORM)
+    glb, sky, out_py, out_native = (str(tmp_path / n) for n in ("in.glb", "sky.exr", "py.exr", "native.exr"))
+    offline.write_glb(src, glb)
+    offline.write_exr(sky, src.background)
+    assert offline.main([glb, sky, out_py, "3", "--extent", "80x56"]) == 0
+    r = subprocess.run([exe, glb, sky, out_native, "3", "--extent", "80x56"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "seconds to render" in r.stdout
+    assert open(out_native, "rb").read() == open(out_py, "rb").read()
